@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- the coverage hot path on synthetic reads of BASELINE.json's shapes.
+
+  python bench.py --gpus N --steps K --warmup W            (one rank per GPU under torchrun for N>1)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+A "step" = one pass of the hot path over one batch: mapped reads (SoA) -> per-base depth of every
+contig -> per-contig statistics (the work of reference metacov/pileup.py:9-26 driven by the loop at
+metacov/cli.py:85-95).  Workload at N=1: config C2 of BASELINE.json (10 M x 150 bp reads over 1 000
+contigs of 50 kb); for N>1 every rank gets its own C2-sized contig range (weak scaling, no
+data-path collective, one NCCL all-gather of the 64-byte per-contig statistics records).
+
+Prints ONE JSON line (rank 0).  `value` is timed with the SoA already resident in HBM; `e2e` is the
+same metric through the public API with HOST buffers (H2D + D2H inside the timed region).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "aligned bases/sec -> per-base coverage + per-contig stats"
+UNIT = "aligned_bases/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons sampled during the timed region (NVML)."""
+
+    def __init__(self, index, period=0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def make_workload(name, scale, n_ranks):
+    """Global workload = n_ranks copies of the named shape, split into contiguous contig ranges."""
+    from metacov_b200 import synth
+    w = synth.WORKLOADS[name](scale * n_ranks)
+    return w
+
+
+def cpu_port_time(batch, lengths, regions, threads, reps=2):
+    """The C restatement (oracle/coverage.c), contig-parallel: depth + per-contig statistics."""
+    from oracle import cport
+    tid, st, en = regions
+    best = None
+    aligned = 0
+    for _ in range(reps + 1):
+        t0 = time.perf_counter()
+        d, off, info = cport.depth(batch, lengths, mode="par", threads=threads)
+        cport.region_stats(d, off, lengths, tid, st, en, threads=threads)
+        dt = time.perf_counter() - t0
+        aligned = info["aligned_bases"]
+        best = dt if best is None else min(best, dt)
+    return aligned, best
+
+
+def python_port_rate(batch, lengths, max_contigs=1):
+    """The reference's own structure: one Python object per pileup column and numpy/sorted()
+    reductions per region (metacov/pileup.py:13-26), over the restated htslib engine.  Tiny sample."""
+    from oracle import bamio, classic as oc
+    from oracle.pysam_boundary import FakeAlignmentFile
+    sel = np.asarray(batch.tid) < max_contigs
+    n = int(sel.sum())
+    r = bamio.BamRecords()
+    o = np.asarray(batch.cig_off).astype(np.int64)
+    r.tid, r.pos = np.asarray(batch.tid)[:n], np.asarray(batch.pos)[:n]
+    r.flag, r.mapq = np.asarray(batch.flag)[:n], np.asarray(batch.mapq)[:n]
+    r.cig_off, r.cig = o[:n + 1], np.asarray(batch.cig)[:o[n]]
+    r.names, r.seqs = [""] * n, [None] * n
+    r.reflen = bamio.cigar_reflen(r.cig_off, r.cig)
+    names = tuple("c%d" % c for c in range(max_contigs))
+    bam = FakeAlignmentFile(bamio.BamHeader("", names, tuple(int(x) for x in lengths[:max_contigs])), r)
+    t0 = time.perf_counter()
+    total = 0
+    for c in range(max_contigs):
+        total += oc.classic(bam, names[c], 0, int(lengths[c]))["sum"]
+    return total / (time.perf_counter() - t0), n
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path on the host cores (the reference itself
+    needs pysam/htslib, absent from this image, so this is the C port of oracle/, kind 'port')."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from metacov_b200 import synth
+    w = make_workload(args.workload, args.scale, 1)
+    cores = os.cpu_count() or 1
+    batch, _ = synth.generate_host(w)
+    tid = np.arange(w.n_contigs, dtype=np.int32)
+    regions = (tid, np.zeros_like(tid), w.contig_len)
+    from oracle import cport
+    cport.build()
+    times = []
+    aligned = 0
+    for k in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        d, off, info = cport.depth(batch, w.contig_len, mode="par", threads=cores)
+        cport.region_stats(d, off, w.contig_len, *regions, threads=cores)
+        dt = time.perf_counter() - t0
+        aligned = info["aligned_bases"]
+        if k >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = aligned / (ms / 1e3)
+    py_rate, py_n = python_port_rate(batch, w.contig_len, 1)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": "%s: %s" % (args.workload, w.describe()), "scale": args.scale},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "full %s workload per step (C port oracle/coverage.c, contig-parallel pthreads)" % args.workload,
+                         "python_port_value": py_rate,
+                         "python_port_sample": "first contig (%d reads) through the reference-structured Python loop, 1 core" % py_n},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def batch_bytes(b):
+    tot = 0
+    for a in b:
+        tot += a.numel() * a.element_size() if hasattr(a, "numel") else a.nbytes
+    return int(tot)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from metacov_b200 import CoverageEngine, ReadBatch, sharding, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- workload: contiguous contig range of this rank --------------------------------------
+    w = make_workload(args.workload, args.scale, world)
+    rpc = np.diff(w.read_start)
+    bounds = sharding.partition_contigs(w.contig_len, rpc, world)
+    c0, c1 = int(bounds[rank]), int(bounds[rank + 1])
+    r0, r1 = sharding.shard_read_range(w.read_start, bounds, rank)
+    lengths = w.contig_len[c0:c1]
+    dbatch, _ = synth.generate_device(w, local, i0=r0, n=r1 - r0, tid_base=c0)
+    n_reads = r1 - r0
+    g = c1 - c0
+    reg_tid = np.arange(g, dtype=np.int32)
+    reg_start = np.zeros(g, dtype=np.int32)
+    reg_end = lengths.astype(np.int32)
+    owner = sharding.assign_regions(np.arange(w.n_contigs), bounds)
+
+    stream = torch.cuda.current_stream().cuda_stream
+    eng = CoverageEngine(lengths, device=local, stream=stream)
+
+    def step(batch):
+        eng.depth_sorted(batch)
+        st = eng.region_stats(reg_tid, reg_start, reg_end)
+        if world > 1:
+            st = sharding.gather_region_stats(st, owner, rank, world, device=dev)
+        return st
+
+    for _ in range(max(args.warmup, 3)):
+        stats = step(dbatch)
+    info = eng.pass_info()
+    aligned_local = info["aligned_bases"]
+    aligned_t = torch.tensor([aligned_local], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(aligned_t)
+    aligned_total = int(aligned_t.item())
+
+    # ---- timed region: device-resident inputs ---------------------------------------------------
+    sampler = ClockSampler(local)
+    eng.profile(True)
+    l0 = eng.launch_count()
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step(dbatch)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    t_t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_t, op=dist.ReduceOp.MAX)
+    ms_step = float(t_t.item()) / args.steps
+    launches = eng.launch_count() - l0
+    kt = eng.profile_read()
+    eng.profile(False)
+
+    # ---- e2e: host (pinned) SoA through the public API, H2D + D2H inside --------------------------
+    e2e = None
+    hbatch = None
+    if not args.no_e2e:
+        hbatch = ReadBatch(*[t.cpu().pin_memory() for t in dbatch])
+        for _ in range(2):
+            eng.compute_depth(hbatch)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            eng.compute_depth(hbatch)
+            st = eng.region_stats(reg_tid, reg_start, reg_end)
+            if world > 1:
+                st = sharding.gather_region_stats(st, owner, rank, world, device=dev)
+        barrier()
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        d_t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(d_t, op=dist.ReduceOp.MAX)
+        e2e = {"value": aligned_total / float(d_t.item()), "unit": UNIT,
+               "h2d_bytes_per_step": batch_bytes(hbatch) + g * 16, "d2h_bytes_per_step": g * 64 + 64,
+               "ms_per_step": 1e3 * float(d_t.item())}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (CUDA events around every launch, timed region) ------------
+    peak, peak_src = peaks()
+    flag = dbatch.flag.to(torch.int32) & 0xFFFF
+    passing = ((flag & 0x704) == 0) & ~(((flag & 1) != 0) & ((flag & 2) == 0)) & ((flag & 4) == 0)
+    ncig = (dbatch.cig_off[1:].to(torch.int64) & 0xFFFFFFFF) - (dbatch.cig_off[:-1].to(torch.int64) & 0xFFFFFFFF)
+    cig_pass = int((ncig * passing).sum().item())
+    n_pass = int(passing.sum().item())
+    slots = eng.n_slots
+    L_regions = int(lengths.astype(np.int64).sum())
+    alg_bytes = {
+        "k_fused_prep": 15 * n_reads + 4 * cig_pass + 8 * n_reads,
+        "k_fused_tile": 8 * n_reads + 4 * slots,
+        "k_region_stats": 4 * L_regions + 64 * g,
+        "k_expand": 15 * n_reads + 4 * cig_pass + 8 * n_pass,
+        "k_scan_inplace": 8 * slots,
+        "memset_depth": 4 * slots,
+    }
+    kernels = {}
+    for name, (n_l, tot) in kt.items():
+        per = tot / max(n_l, 1)
+        ent = {"launches": int(n_l), "ms_per_launch": per, "share_of_step": tot / args.steps / ms_step}
+        if name in alg_bytes and per > 0:
+            ent["algorithmic_bytes"] = alg_bytes[name]
+            ent["gbs"] = alg_bytes[name] / per / 1e6
+            ent["frac"] = ent["gbs"] / peak
+        kernels[name] = ent
+    dom = max((k for k in kernels if "gbs" in kernels[k]), key=lambda k: kernels[k]["ms_per_launch"] * kernels[k]["launches"])
+    roof = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
+            "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes"], "kernels": kernels}
+    whole_bytes = alg_bytes["k_fused_prep"] + alg_bytes["k_fused_tile"] + alg_bytes["k_region_stats"]
+    roof["whole_step"] = {"algorithmic_bytes": whole_bytes, "gbs": whole_bytes / ms_step / 1e6,
+                          "frac": whole_bytes / ms_step / 1e6 / peak}
+
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only) --------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        from oracle import cport
+        cport.build()
+        if hbatch is None:
+            hbatch = ReadBatch(*[t.cpu() for t in dbatch])
+        nb = ReadBatch(*[t.numpy().view({"torch.int16": np.uint16, "torch.int32": np.int32, "torch.uint8": np.uint8}[str(t.dtype)])
+                         for t in hbatch])
+        nb = ReadBatch(nb.tid, nb.pos, nb.flag, nb.mapq, nb.cig_off.view(np.uint32), nb.cig.view(np.uint32))
+        cores = os.cpu_count() or 1
+        al, dt = cpu_port_time(nb, lengths, (reg_tid, reg_start, reg_end), cores)
+        al1, dt1 = cpu_port_time(nb, lengths, (reg_tid, reg_start, reg_end), 1, reps=0)
+        py_rate, py_n = python_port_rate(nb, lengths, 1)
+        cpu = {"value": al / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "full %s shard (%d reads) per step, C port oracle/coverage.c contig-parallel, best of 3" % (args.workload, n_reads),
+               "one_core_value": al1 / dt1,
+               "python_port_value": py_rate,
+               "python_port_sample": "first contig (%d reads), reference-structured Python loop (one object per column), 1 core" % py_n}
+
+    line = {
+        "metric": METRIC, "value": aligned_total / (ms_step / 1e3), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": "%s x%d ranks: %s" % (args.workload, world, w.describe()), "scale": args.scale,
+                   "per_gpu": {"reads": n_reads, "contigs": g, "slots": int(slots)},
+                   "regions": "one whole-contig region per contig (reference util.py:64-69)",
+                   "l2": "inputs+depth (%d MB per GPU) exceed the 126 MB L2; no explicit flush" %
+                         ((batch_bytes(dbatch) + 4 * slots) // 2 ** 20),
+                   "parallelism": "contig-range shards, 1 all-gather of 64 B/region" if world > 1 else "single GPU"},
+        "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "aligned_bases_per_step": aligned_total,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the named workload per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

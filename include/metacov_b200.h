@@ -1,0 +1,241 @@
+/* metacov_b200.h -- C-ABI of the B200-native coverage hot path.
+ *
+ * Drop-in boundary for the coverage path of epruesse/metacov.  The reference
+ * has no FFI of its own for this path: its boundary is the Python surface
+ * (metacov/pileup.py:9 `classic`, metacov/scan.pyx:623 `scan_reads`) on top of
+ * the pysam object protocol (`AlignmentFile.pileup` pileup.py:13, `.fetch`
+ * pileup.py:90, raw `bam1_t` fields scan.pyx:243-294).  Every entry point below
+ * names the reference interface it replaces.  Plain C: pointers and sizes only.
+ *
+ * Conventions
+ *   - every function returns MCOV_OK (0) or a negative mcov_status; nothing
+ *     throws across the ABI; `mcov_last_error(ctx)` has the message.
+ *   - one context per GPU; a context is NOT thread-safe.
+ *   - work is enqueued on the context's CUDA stream; calls that hand results
+ *     to host memory synchronise that stream before returning.
+ *   - the caller owns every array it passes; host arrays passed to
+ *     `mcov_push_reads` may be reused as soon as the call returns.
+ *   - there is no CPU fallback: without a CUDA device `mcov_create` fails.
+ */
+#ifndef METACOV_B200_H
+#define METACOV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCOV_ABI_VERSION 1
+
+typedef enum mcov_status {
+  MCOV_OK = 0,
+  MCOV_ERR_ARG = -1,      /* bad argument (null pointer, negative size, bad tid ...) */
+  MCOV_ERR_STATE = -2,    /* call out of order (e.g. push after finalize)            */
+  MCOV_ERR_CUDA = -3,     /* CUDA runtime error, text in mcov_last_error             */
+  MCOV_ERR_NOMEM = -4,
+  MCOV_ERR_IO = -5,       /* BAM/BGZF/BAI decode error                               */
+  MCOV_ERR_RANGE = -6,    /* value outside what the kernels represent exactly        */
+  MCOV_ERR_UNSORTED = -7  /* sorted-only entry point fed unsorted reads              */
+} mcov_status;
+
+typedef enum mcov_mem_kind {
+  MCOV_MEM_HOST = 0,      /* pageable or pinned host memory  */
+  MCOV_MEM_DEVICE = 1     /* device memory on the ctx's GPU  */
+} mcov_mem_kind;
+
+typedef struct mcov_ctx mcov_ctx;
+
+/* The implicit arguments of `bam.pileup(ref, start, end)` (reference
+ * metacov/pileup.py:13 calls it with pysam's defaults) made explicit.
+ * Defaults = pysam stepper "samtools": see SURVEY.md Appendix A-1/A-2. */
+typedef struct mcov_filter {
+  uint16_t flag_filter;    /* drop if (flag & flag_filter)            default 0x704 */
+  uint16_t flag_require;   /* if !=0 drop unless (flag & flag_require) default 0    */
+  uint8_t  min_mapq;       /* drop if mapq < min_mapq                 default 0     */
+  uint8_t  ignore_orphans; /* drop paired && !proper_pair             default 1     */
+  uint8_t  reserved[2];
+  int32_t  max_depth;      /* htslib maxcnt; <=0 disables the cap     default 8000  */
+} mcov_filter;
+
+/* Exact integer statistics of one region [start,end) of one contig; the host
+ * finishes `classic`'s seven outputs (reference metacov/pileup.py:18-26) from
+ * these without touching the depth again.  64 bytes. */
+typedef struct mcov_region_stats {
+  int64_t  sum;        /* sum of depth                       -> 'sum', 'avg'           */
+  uint64_t sumsq;      /* sum of depth^2                     -> 'std'                  */
+  int64_t  iq_sum;     /* sum of sorted depth[n/4 : n-n/4)   -> 'q23'                  */
+  int64_t  n_ge1;      /* positions with depth >= 1          (breadth; additive)       */
+  int64_t  n_geN;      /* positions with depth >= breadth_n  (breadth; additive)       */
+  int32_t  min;        /*                                    -> 'min'                  */
+  int32_t  max;        /*                                    -> 'max'                  */
+  int32_t  med_lo;     /* sorted depth[(n-1)/2]              -> 'med' = (lo+hi)/2      */
+  int32_t  med_hi;     /* sorted depth[n/2]                                            */
+  int32_t  reserved;
+  int32_t  flags;      /* bit0: order statistics valid; bit1: depth overflowed the
+                          histogram range and the radix path was used                 */
+} mcov_region_stats;
+
+/* ---- context ------------------------------------------------------------ */
+
+/* device: CUDA ordinal.  stream: a cudaStream_t (e.g. torch's current stream
+ * handle) or NULL for a stream owned by the context. */
+int  mcov_create(mcov_ctx** out, int device, void* stream);
+void mcov_destroy(mcov_ctx* ctx);
+const char* mcov_last_error(const mcov_ctx* ctx);
+int  mcov_abi_version(void);
+
+/* Replaces `AlignmentFile.references/.lengths` as the shape of the depth
+ * store (reference metacov/util.py:64-69 iterates them; pileup.py:10-11
+ * allocates one float64 vector per region -- here ONE int32 array holds every
+ * contig: contig c owns len[c]+1 slots starting at a 16-byte aligned offset). */
+int  mcov_set_contigs(mcov_ctx* ctx, int32_t n_contigs, const int32_t* len);
+int64_t mcov_n_slots(const mcov_ctx* ctx);
+/* slot offset of contig `tid` inside the depth array */
+int64_t mcov_contig_offset(const mcov_ctx* ctx, int32_t tid);
+
+/* Optional: caller-owned device buffer (e.g. a torch.int32 tensor) of at
+ * least mcov_n_slots() elements to hold the depth. */
+int  mcov_bind_depth(mcov_ctx* ctx, int32_t* dev, int64_t n_slots);
+
+int  mcov_set_filter(mcov_ctx* ctx, const mcov_filter* f);
+void mcov_default_filter(mcov_filter* f);
+
+/* Start a new pass: clears the difference array and all counters. */
+int  mcov_begin(mcov_ctx* ctx);
+
+/* Replaces the per-record work of htslib's pileup engine behind
+ * `bam.pileup()` (reference metacov/pileup.py:13): filter each record, reduce
+ * its CIGAR to a reference length, and add +1 @ pos / -1 @ pos+reflen to the
+ * difference array.  SoA layout = the `bam1_t.core` fields the reference reads
+ * at scan.pyx:243-294.  cig_off has n+1 entries (offsets into cig); cig holds
+ * BAM-encoded ops (len<<4 | op).  Any order of reads is accepted. */
+int  mcov_push_reads(mcov_ctx* ctx, int64_t n,
+                     const int32_t* tid, const int32_t* pos,
+                     const uint16_t* flag, const uint8_t* mapq,
+                     const uint32_t* cig_off, const uint32_t* cig,
+                     int mem_kind);
+
+/* Prefix-scan the difference array into per-base depth.  Afterwards
+ * depth(tid, p) = value of `column.n` at that position (pileup.py:16). */
+int  mcov_finalize(mcov_ctx* ctx);
+
+/* One-call variant for coordinate-sorted input: expansion, scan and depth
+ * materialisation fused in one pass over the slot space (no separate clear,
+ * no atomics to L2).  Returns MCOV_ERR_UNSORTED if the reads are not sorted
+ * by (tid,pos); the caller then uses begin/push/finalize. */
+int  mcov_depth_sorted(mcov_ctx* ctx, int64_t n,
+                       const int32_t* tid, const int32_t* pos,
+                       const uint16_t* flag, const uint8_t* mapq,
+                       const uint32_t* cig_off, const uint32_t* cig,
+                       int mem_kind);
+
+/* Replaces the seven reductions of `classic` (reference
+ * metacov/pileup.py:18-26) for g regions at once (the loop at cli.py:85-95).
+ * tid/start/end are host arrays; 0 <= start <= end <= len[tid].
+ * breadth_n: threshold of n_geN.  host_out: g structs.  Synchronises. */
+int  mcov_region_stats_run(mcov_ctx* ctx, int64_t g,
+                           const int32_t* tid, const int32_t* start, const int32_t* end,
+                           int32_t breadth_n, mcov_region_stats* host_out);
+
+/* Fixed-window mean depth (additive feature named by north_star; no
+ * reference counterpart): for every contig, ceil(len/window) float64 means,
+ * concatenated in tid order into host_out (n_out = total windows). */
+int  mcov_window_means(mcov_ctx* ctx, int32_t window, double* host_out, int64_t n_out);
+
+/* Replaces reading `column.n` back one column at a time (pileup.py:13-16). */
+int  mcov_copy_depth(mcov_ctx* ctx, int32_t tid, int32_t start, int32_t end, int32_t* host_out);
+/* Device pointer to the depth array (valid after finalize / depth_sorted). */
+int32_t* mcov_depth_ptr(mcov_ctx* ctx);
+
+/* Counters of the last pass. */
+typedef struct mcov_pass_info {
+  int64_t n_reads;        /* records pushed                                   */
+  int64_t n_pass;         /* records that passed the filter with reflen > 0   */
+  int64_t aligned_bases;  /* sum of reflen over passing reads (unclipped)     */
+  int32_t max_depth_seen; /* max depth over all contigs                       */
+  int32_t cap_metric;     /* max_p depth[p-1]+starts[p] (fused path) or an
+                             upper bound of it (push path)                    */
+  int32_t sorted;         /* 1 if the input was coordinate-sorted             */
+  int32_t reserved;
+} mcov_pass_info;
+int  mcov_pass_info_get(mcov_ctx* ctx, mcov_pass_info* out);
+
+/* ---- launch accounting and per-kernel timing (bench / profiling support) -- */
+
+typedef struct mcov_kernel_time {
+  char    name[32];
+  int64_t launches;
+  double  total_ms;   /* CUDA-event time summed over the launches, on the ctx's stream */
+} mcov_kernel_time;
+
+/* kernels (and clears) enqueued by this context since it was created */
+int64_t mcov_launch_count(const mcov_ctx* ctx);
+/* on=1: bracket every kernel launch with CUDA events and reset the totals; on=0: stop. */
+int  mcov_profile_enable(mcov_ctx* ctx, int on);
+/* Synchronises; fills up to cap entries; returns the number written (>=0) or an error. */
+int  mcov_profile_read(mcov_ctx* ctx, mcov_kernel_time* out, int cap);
+
+/* ---- read-statistics scan (metacov scan) --------------------------------- */
+
+/* Replaces `ByFlag.process_read` + `IsizeHist.process_read` over every record
+ * (reference metacov/scan.pyx:406-420, 590-610; getter semantics
+ * scan.pyx:267-271: isize counts only if PROPER_PAIR, else bin 0).
+ * group_flags: the user-ordered flag masks of ByFlag (MSB first, scan.pyx:
+ * 414-418); n_groups_out = 2^n_group_flags.  hist_out: host u32
+ * [2^n_group_flags][n_bins]; |isize| >= n_bins is reported through
+ * *max_isize_out so the caller can retry with a larger table.
+ * group_counts_out: host u64[2^n_group_flags] reads per group. */
+int  mcov_isize_hist(mcov_ctx* ctx, int64_t n,
+                     const uint16_t* flag, const int32_t* isize, int mem_kind,
+                     int32_t n_group_flags, const uint16_t* group_flags,
+                     int32_t n_bins, uint32_t* hist_out,
+                     uint64_t* group_counts_out, int32_t* max_isize_out);
+
+/* ---- host BAM decoding (replaces pysam.AlignmentFile, cli.py:56, 211) ---- */
+
+typedef struct mcov_bam mcov_bam;
+
+int  mcov_bam_open(mcov_bam** out, const char* path, char* err, int errlen);
+void mcov_bam_close(mcov_bam* b);
+int32_t mcov_bam_n_ref(const mcov_bam* b);
+const char* mcov_bam_ref_name(const mcov_bam* b, int32_t tid);
+int32_t mcov_bam_ref_len(const mcov_bam* b, int32_t tid);
+const char* mcov_bam_header_text(const mcov_bam* b);
+/* BAI metadata pseudo-bin sums (pysam `.mapped` / `.unmapped`, cli.py:73-75);
+ * returns MCOV_ERR_IO if there is no index next to the BAM. */
+int  mcov_bam_index_stats(const mcov_bam* b, int64_t* mapped, int64_t* unmapped);
+/* Decode the whole file (every record, like IteratorRowAll scan.pyx:204) into
+ * SoA arrays owned by the handle; pointers stay valid until close. */
+int  mcov_bam_load(mcov_bam* b, int n_threads);
+int64_t mcov_bam_n_records(const mcov_bam* b);
+int64_t mcov_bam_n_cigar(const mcov_bam* b);
+const int32_t*  mcov_bam_tid(const mcov_bam* b);
+const int32_t*  mcov_bam_pos(const mcov_bam* b);
+const uint16_t* mcov_bam_flag(const mcov_bam* b);
+const uint8_t*  mcov_bam_mapq(const mcov_bam* b);
+const int32_t*  mcov_bam_lseq(const mcov_bam* b);
+const int32_t*  mcov_bam_isize(const mcov_bam* b);
+const uint32_t* mcov_bam_cig_off(const mcov_bam* b);
+const uint32_t* mcov_bam_cig(const mcov_bam* b);
+
+/* ---- synthetic workloads (bench / test support; include/mcov_synth.h) ---- */
+
+struct mcov_synth_params;
+/* n_cigar of reads [i0, i0+n) -> out[n] (host or device memory per mem_kind;
+ * device work is enqueued on `stream`, a cudaStream_t or NULL). */
+int  mcov_synth_gen_ncigar(const struct mcov_synth_params* P, int64_t i0, int64_t n,
+                       uint32_t* out, int mem_kind, void* stream);
+/* Fill the SoA of reads [i0, i0+n).  read_start[n_contigs+1] / contig_len are
+ * GLOBAL tables in the same memory kind as the outputs; tid_out = contig -
+ * tid_base.  cig_off[n+1] are offsets into cig.  reflen_out may be NULL. */
+int  mcov_synth_gen_reads(const struct mcov_synth_params* P, int64_t i0, int64_t n,
+                     const int64_t* read_start, const int32_t* contig_len, int32_t n_contigs,
+                     int32_t tid_base, const uint32_t* cig_off,
+                     int32_t* tid, int32_t* pos, uint16_t* flag, uint8_t* mapq, int32_t* isize,
+                     uint32_t* cig, int64_t* reflen_out, int mem_kind, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* METACOV_B200_H */

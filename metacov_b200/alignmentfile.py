@@ -1,0 +1,181 @@
+"""``AlignmentFile``: the subset of the pysam object protocol the coverage path
+consumes, backed by the native BGZF/BAM/BAI reader (csrc/bamio.cpp) and the
+CUDA depth engine.
+
+Protocol provided (reference call sites): constructor from a path
+(metacov/cli.py:56, 211); context manager (cli.py:258); ``references`` /
+``lengths`` (util.py:67-68, cli.py:80); ``mapped`` / ``unmapped``
+(cli.py:73-75, 214-216); ``pileup(ref, start, end)`` yielding objects with
+``.pos`` / ``.n`` (pileup.py:13-16).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import McovError, lib
+from .engine import CoverageEngine, ReadBatch
+
+
+def _view(ptr, n, dtype):
+    if n == 0 or not ptr:
+        return np.zeros(0, dtype=dtype)
+    buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=n)
+
+
+class PileupColumn:
+    """Stand-in for pysam.PileupColumn (only ``pos`` and ``n`` are read by the
+    reference, pileup.py:14-16)."""
+    __slots__ = ("reference_id", "pos", "n")
+
+    def __init__(self, tid, pos, n):
+        self.reference_id = tid
+        self.pos = pos
+        self.n = n
+
+    reference_pos = property(lambda self: self.pos)
+    nsegments = property(lambda self: self.n)
+
+
+class AlignmentFile:
+    def __init__(self, filename, mode="rb", device=0, **kw):
+        if "w" in mode:
+            raise ValueError("metacov_b200.AlignmentFile is read-only")
+        self.filename = filename
+        self._h = C.c_void_p()
+        err = C.create_string_buffer(256)
+        rc = lib.mcov_bam_open(C.byref(self._h), str(filename).encode(), err, len(err))
+        if rc != 0:
+            self._h = None
+            # pysam raises OSError/ValueError for unreadable files
+            raise OSError("%s: %s" % (filename, err.value.decode()))
+        n = lib.mcov_bam_n_ref(self._h)
+        self.references = tuple(lib.mcov_bam_ref_name(self._h, i).decode() for i in range(n))
+        self.lengths = tuple(lib.mcov_bam_ref_len(self._h, i) for i in range(n))
+        self.nreferences = n
+        self.text = lib.mcov_bam_header_text(self._h).decode()
+        self._tid = {name: i for i, name in enumerate(self.references)}
+        self._device = device
+        self._soa = None
+        self._engine = None
+        self._filter_kw = None
+        self._index_stats = None
+
+    # -- lifetime ---------------------------------------------------------
+    def close(self):
+        if getattr(self, "_engine", None) is not None:
+            self._engine.close()
+            self._engine = None
+        if getattr(self, "_h", None):
+            lib.mcov_bam_close(self._h)
+            self._h = None
+        self._soa = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+        return False
+
+    # -- header / index ---------------------------------------------------
+    def get_tid(self, reference):
+        return self._tid.get(reference, -1)
+
+    def get_reference_name(self, tid):
+        return self.references[tid]
+
+    def _idx(self):
+        if self._index_stats is None:
+            m, u = C.c_int64(0), C.c_int64(0)
+            rc = lib.mcov_bam_index_stats(self._h, C.byref(m), C.byref(u))
+            if rc != 0:
+                raise ValueError("mapping information not recorded in index or index not available")
+            self._index_stats = (m.value, u.value)
+        return self._index_stats
+
+    @property
+    def mapped(self):
+        return self._idx()[0]
+
+    @property
+    def unmapped(self):
+        return self._idx()[1]
+
+    def has_index(self):
+        try:
+            self._idx()
+            return True
+        except ValueError:
+            return False
+
+    # -- records ----------------------------------------------------------
+    def soa(self):
+        """Every record of the file as SoA numpy views (file order; the arrays
+        the reference reads field by field at scan.pyx:243-294)."""
+        if self._soa is None:
+            rc = lib.mcov_bam_load(self._h, 0)
+            if rc != 0:
+                raise McovError(rc, "BAM record decode failed")
+            n = lib.mcov_bam_n_records(self._h)
+            nc = lib.mcov_bam_n_cigar(self._h)
+            self._soa = dict(
+                tid=_view(lib.mcov_bam_tid(self._h), n, np.int32),
+                pos=_view(lib.mcov_bam_pos(self._h), n, np.int32),
+                flag=_view(lib.mcov_bam_flag(self._h), n, np.uint16),
+                mapq=_view(lib.mcov_bam_mapq(self._h), n, np.uint8),
+                l_seq=_view(lib.mcov_bam_lseq(self._h), n, np.int32),
+                isize=_view(lib.mcov_bam_isize(self._h), n, np.int32),
+                cig_off=_view(lib.mcov_bam_cig_off(self._h), n + 1, np.uint32),
+                cig=_view(lib.mcov_bam_cig(self._h), nc, np.uint32),
+            )
+        return self._soa
+
+    def __len__(self):
+        return len(self.soa()["tid"])
+
+    # -- coverage ---------------------------------------------------------
+    def set_pileup_filter(self, **kw):
+        """Override pysam's implicit pileup arguments (flag_filter, flag_require,
+        min_mapq, ignore_orphans, max_depth); invalidates the cached depth."""
+        self._filter_kw = kw
+        if self._engine is not None:
+            self._engine.close()
+            self._engine = None
+
+    def coverage_engine(self):
+        """The per-base depth of the whole file, computed once on the GPU."""
+        if self._engine is None:
+            s = self.soa()
+            eng = CoverageEngine(self.lengths, device=self._device, filt=self._filter_kw)
+            eng.compute_depth(ReadBatch(s["tid"], s["pos"], s["flag"], s["mapq"], s["cig_off"], s["cig"]))
+            info = eng.pass_info()
+            md = eng.filter.max_depth
+            if md > 0 and info["cap_metric"] > md:
+                eng.close()
+                from .pileup import DepthCapError
+                raise DepthCapError(
+                    "depth[p-1]+starts[p] reaches %d > max_depth=%d: htslib's pileup would drop reads here "
+                    "(order-dependent cap); raise max_depth via set_pileup_filter(max_depth=...)"
+                    % (info["cap_metric"], md))
+            self._engine = eng
+        return self._engine
+
+    def pileup(self, contig=None, start=None, stop=None, **kw):
+        """Columns with n > 0 inside [start, stop) (pysam also emits columns
+        outside the region when truncate=False; the reference discards them,
+        pileup.py:14-15)."""
+        tid = self._tid[contig]
+        start = 0 if start is None else max(int(start), 0)
+        stop = self.lengths[tid] if stop is None else min(int(stop), self.lengths[tid])
+        d = self.coverage_engine().copy_depth(tid, start, stop) if stop > start else np.zeros(0, np.int32)
+        for off in np.nonzero(d)[0]:
+            yield PileupColumn(tid, start + int(off), int(d[off]))
+
+    def count_coverage_depth(self, contig, start=None, stop=None):
+        """Per-base depth as an int32 array (additive helper)."""
+        tid = self._tid[contig]
+        return self.coverage_engine().copy_depth(tid, 0 if start is None else start, stop)

@@ -1,0 +1,276 @@
+// bamio.cpp -- host BGZF / BAM / BAI decoder feeding the SoA packer.
+//
+// Replaces the pysam/htslib objects the reference opens at metacov/cli.py:56
+// and :211 (`pysam.AlignmentFile`) and iterates at metacov/scan.pyx:204, 216
+// (`IteratorRowAll` over raw `bam1_t`), reading exactly the fields the
+// reference's getters read (scan.pyx:243-294: flag, pos, tid, l_qseq, isize)
+// plus mapq and the CIGAR for the coverage kernels.  Formats: SAM spec v1
+// section 4.1 (BGZF), 4.2 (BAM), 5.2 (BAI).  BGZF blocks are independent
+// deflate streams, so they are inflated in parallel by a few host threads.
+#include <zlib.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "metacov_b200.h"
+
+struct mcov_bam {
+  std::string path;
+  std::string text;
+  std::vector<std::string> ref_name;
+  std::vector<int32_t> ref_len;
+  std::vector<uint8_t> raw;          // compressed file
+  std::vector<uint8_t> data;         // inflated stream
+  size_t rec_begin = 0;              // offset of the first alignment record in `data`
+  bool loaded = false;
+  std::vector<int32_t> tid, pos, lseq, isize;
+  std::vector<uint16_t> flag;
+  std::vector<uint8_t> mapq;
+  std::vector<uint32_t> cig_off, cig;
+};
+
+namespace {
+
+struct Block { size_t coff, clen, uoff, ulen; uint32_t crc; };
+
+int set_err(char* err, int errlen, const char* msg) {
+  if (err && errlen > 0) std::snprintf(err, (size_t)errlen, "%s", msg);
+  return MCOV_ERR_IO;
+}
+
+inline uint16_t rd16(const uint8_t* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+inline uint32_t rd32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+inline uint64_t rd64(const uint8_t* p) { return (uint64_t)rd32(p) | ((uint64_t)rd32(p + 4) << 32); }
+
+bool index_blocks(const std::vector<uint8_t>& raw, std::vector<Block>& blocks, size_t& total) {
+  size_t off = 0, uoff = 0;
+  const size_t n = raw.size();
+  while (off < n) {
+    if (off + 18 > n) return false;
+    const uint8_t* h = raw.data() + off;
+    if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return false;
+    uint16_t xlen = rd16(h + 10);
+    if (off + 12 + xlen > n) return false;
+    int bsize = -1;
+    size_t p = off + 12, xend = off + 12 + xlen;
+    while (p + 4 <= xend) {
+      uint16_t slen = rd16(raw.data() + p + 2);
+      if (raw[p] == 'B' && raw[p + 1] == 'C' && slen == 2 && p + 6 <= xend) bsize = rd16(raw.data() + p + 4);
+      p += 4 + slen;
+    }
+    if (bsize < 0) return false;
+    size_t bend = off + (size_t)bsize + 1;
+    if (bend > n || (size_t)bsize + 1 < (size_t)(12 + xlen + 8)) return false;
+    Block b;
+    b.coff = off + 12 + xlen;
+    b.clen = bend - 8 - b.coff;
+    b.crc = rd32(raw.data() + bend - 8);
+    b.ulen = rd32(raw.data() + bend - 4);
+    b.uoff = uoff;
+    uoff += b.ulen;
+    blocks.push_back(b);
+    off = bend;
+  }
+  total = uoff;
+  return true;
+}
+
+bool inflate_block(const uint8_t* src, size_t clen, uint8_t* dst, size_t ulen, uint32_t crc) {
+  if (ulen == 0) return true;
+  z_stream zs;
+  std::memset(&zs, 0, sizeof(zs));
+  if (inflateInit2(&zs, -15) != Z_OK) return false;
+  zs.next_in = const_cast<Bytef*>(src);
+  zs.avail_in = (uInt)clen;
+  zs.next_out = dst;
+  zs.avail_out = (uInt)ulen;
+  int rc = inflate(&zs, Z_FINISH);
+  bool ok = (rc == Z_STREAM_END) && zs.total_out == ulen;
+  inflateEnd(&zs);
+  if (ok) ok = ((uint32_t)crc32(crc32(0L, Z_NULL, 0), dst, (uInt)ulen) == crc);
+  return ok;
+}
+
+bool inflate_all(mcov_bam* b, int n_threads) {
+  std::vector<Block> blocks;
+  size_t total = 0;
+  if (!index_blocks(b->raw, blocks, total)) return false;
+  b->data.resize(total);
+  if (n_threads < 1) n_threads = 1;
+  n_threads = (int)std::min<size_t>((size_t)n_threads, std::max<size_t>(blocks.size(), 1));
+  std::atomic<size_t> next(0);
+  std::atomic<bool> good(true);
+  auto work = [&]() {
+    for (;;) {
+      size_t k = next.fetch_add(1);
+      if (k >= blocks.size() || !good.load()) break;
+      const Block& bl = blocks[k];
+      if (!inflate_block(b->raw.data() + bl.coff, bl.clen, b->data.data() + bl.uoff, bl.ulen, bl.crc)) good.store(false);
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < n_threads; ++t) th.emplace_back(work);
+  work();
+  for (auto& t : th) t.join();
+  return good.load();
+}
+
+// parse the BAM header out of the inflated stream; returns false if malformed
+bool parse_header(mcov_bam* b) {
+  const std::vector<uint8_t>& d = b->data;
+  if (d.size() < 12 || std::memcmp(d.data(), "BAM\1", 4) != 0) return false;
+  uint32_t l_text = rd32(d.data() + 4);
+  size_t p = 8;
+  if (p + l_text + 4 > d.size()) return false;
+  b->text.assign(reinterpret_cast<const char*>(d.data() + p), strnlen(reinterpret_cast<const char*>(d.data() + p), l_text));
+  p += l_text;
+  uint32_t n_ref = rd32(d.data() + p);
+  p += 4;
+  b->ref_name.clear();
+  b->ref_len.clear();
+  for (uint32_t i = 0; i < n_ref; ++i) {
+    if (p + 4 > d.size()) return false;
+    uint32_t l_name = rd32(d.data() + p);
+    if (l_name == 0 || p + 4 + l_name + 4 > d.size()) return false;
+    b->ref_name.emplace_back(reinterpret_cast<const char*>(d.data() + p + 4), l_name - 1);
+    b->ref_len.push_back((int32_t)rd32(d.data() + p + 4 + l_name));
+    p += 8 + l_name;
+  }
+  b->rec_begin = p;
+  return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mcov_bam_open(mcov_bam** out, const char* path, char* err, int errlen) {
+  if (!out || !path) return set_err(err, errlen, "mcov_bam_open: null argument");
+  *out = nullptr;
+  FILE* fh = std::fopen(path, "rb");
+  if (!fh) return set_err(err, errlen, "mcov_bam_open: cannot open file");
+  mcov_bam* b = new mcov_bam();
+  b->path = path;
+  std::fseek(fh, 0, SEEK_END);
+  long sz = std::ftell(fh);
+  std::fseek(fh, 0, SEEK_SET);
+  b->raw.resize(sz > 0 ? (size_t)sz : 0);
+  size_t got = b->raw.empty() ? 0 : std::fread(b->raw.data(), 1, b->raw.size(), fh);
+  std::fclose(fh);
+  if (got != b->raw.size()) { delete b; return set_err(err, errlen, "mcov_bam_open: short read"); }
+  unsigned hw = std::thread::hardware_concurrency();
+  if (!inflate_all(b, hw ? (int)hw : 4)) { delete b; return set_err(err, errlen, "mcov_bam_open: not a valid BGZF file"); }
+  if (!parse_header(b)) { delete b; return set_err(err, errlen, "mcov_bam_open: not a valid BAM file"); }
+  std::vector<uint8_t>().swap(b->raw);
+  *out = b;
+  return MCOV_OK;
+}
+
+void mcov_bam_close(mcov_bam* b) { delete b; }
+
+int32_t mcov_bam_n_ref(const mcov_bam* b) { return b ? (int32_t)b->ref_name.size() : 0; }
+const char* mcov_bam_ref_name(const mcov_bam* b, int32_t tid) {
+  return (b && tid >= 0 && (size_t)tid < b->ref_name.size()) ? b->ref_name[tid].c_str() : nullptr;
+}
+int32_t mcov_bam_ref_len(const mcov_bam* b, int32_t tid) {
+  return (b && tid >= 0 && (size_t)tid < b->ref_len.size()) ? b->ref_len[tid] : -1;
+}
+const char* mcov_bam_header_text(const mcov_bam* b) { return b ? b->text.c_str() : nullptr; }
+
+int mcov_bam_index_stats(const mcov_bam* b, int64_t* mapped, int64_t* unmapped) {
+  if (!b || !mapped || !unmapped) return MCOV_ERR_ARG;
+  std::string cand[2] = {b->path + ".bai", b->path};
+  if (cand[1].size() > 4 && cand[1].compare(cand[1].size() - 4, 4, ".bam") == 0) cand[1].replace(cand[1].size() - 4, 4, ".bai");
+  FILE* fh = nullptr;
+  for (auto& c : cand) { fh = std::fopen(c.c_str(), "rb"); if (fh) break; }
+  if (!fh) return MCOV_ERR_IO;
+  std::vector<uint8_t> d;
+  uint8_t buf[65536];
+  size_t k;
+  while ((k = std::fread(buf, 1, sizeof(buf), fh)) > 0) d.insert(d.end(), buf, buf + k);
+  std::fclose(fh);
+  if (d.size() < 8 || std::memcmp(d.data(), "BAI\1", 4) != 0) return MCOV_ERR_IO;
+  uint32_t n_ref = rd32(d.data() + 4);
+  size_t p = 8;
+  uint64_t m = 0, u = 0;
+  for (uint32_t r = 0; r < n_ref; ++r) {
+    if (p + 4 > d.size()) return MCOV_ERR_IO;
+    uint32_t n_bin = rd32(d.data() + p);
+    p += 4;
+    for (uint32_t k2 = 0; k2 < n_bin; ++k2) {
+      if (p + 8 > d.size()) return MCOV_ERR_IO;
+      uint32_t bin = rd32(d.data() + p), n_chunk = rd32(d.data() + p + 4);
+      p += 8;
+      if (p + 16ull * n_chunk > d.size()) return MCOV_ERR_IO;
+      if (bin == 37450 && n_chunk == 2) { m += rd64(d.data() + p + 16); u += rd64(d.data() + p + 24); }
+      p += 16ull * n_chunk;
+    }
+    if (p + 4 > d.size()) return MCOV_ERR_IO;
+    uint32_t n_intv = rd32(d.data() + p);
+    p += 4 + 8ull * n_intv;
+  }
+  if (p + 8 <= d.size()) u += rd64(d.data() + p);     // n_no_coor
+  *mapped = (int64_t)m;
+  *unmapped = (int64_t)u;
+  return MCOV_OK;
+}
+
+int mcov_bam_load(mcov_bam* b, int /*n_threads*/) {
+  if (!b) return MCOV_ERR_ARG;
+  if (b->loaded) return MCOV_OK;
+  const uint8_t* d = b->data.data();
+  const size_t n = b->data.size();
+  // pass 1: count records and ops
+  size_t p = b->rec_begin, n_rec = 0, n_cig = 0;
+  while (p + 4 <= n) {
+    uint32_t bs = rd32(d + p);
+    if (bs < 32 || p + 4 + bs > n) return MCOV_ERR_IO;
+    n_cig += rd16(d + p + 4 + 12);
+    ++n_rec;
+    p += 4 + bs;
+  }
+  if (p != n) return MCOV_ERR_IO;
+  if (n_cig > 0xFFFFFFFFull) return MCOV_ERR_RANGE;
+  b->tid.resize(n_rec); b->pos.resize(n_rec); b->lseq.resize(n_rec); b->isize.resize(n_rec);
+  b->flag.resize(n_rec); b->mapq.resize(n_rec); b->cig_off.resize(n_rec + 1); b->cig.resize(n_cig);
+  p = b->rec_begin;
+  size_t co = 0;
+  for (size_t i = 0; i < n_rec; ++i) {
+    uint32_t bs = rd32(d + p);
+    const uint8_t* r = d + p + 4;
+    b->tid[i] = (int32_t)rd32(r);
+    b->pos[i] = (int32_t)rd32(r + 4);
+    uint8_t l_read_name = r[8];
+    b->mapq[i] = r[9];
+    uint16_t n_op = rd16(r + 12);
+    b->flag[i] = rd16(r + 14);
+    b->lseq[i] = (int32_t)rd32(r + 16);
+    b->isize[i] = (int32_t)rd32(r + 28);
+    if (32u + l_read_name + 4u * n_op > bs) return MCOV_ERR_IO;
+    b->cig_off[i] = (uint32_t)co;
+    std::memcpy(b->cig.data() + co, r + 32 + l_read_name, 4u * n_op);
+    co += n_op;
+    p += 4 + bs;
+  }
+  b->cig_off[n_rec] = (uint32_t)co;
+  std::vector<uint8_t>().swap(b->data);   // the SoA arrays are all that is kept
+  b->loaded = true;
+  return MCOV_OK;
+}
+
+int64_t mcov_bam_n_records(const mcov_bam* b) { return (b && b->loaded) ? (int64_t)b->tid.size() : -1; }
+int64_t mcov_bam_n_cigar(const mcov_bam* b) { return (b && b->loaded) ? (int64_t)b->cig.size() : -1; }
+const int32_t* mcov_bam_tid(const mcov_bam* b) { return (b && b->loaded) ? b->tid.data() : nullptr; }
+const int32_t* mcov_bam_pos(const mcov_bam* b) { return (b && b->loaded) ? b->pos.data() : nullptr; }
+const uint16_t* mcov_bam_flag(const mcov_bam* b) { return (b && b->loaded) ? b->flag.data() : nullptr; }
+const uint8_t* mcov_bam_mapq(const mcov_bam* b) { return (b && b->loaded) ? b->mapq.data() : nullptr; }
+const int32_t* mcov_bam_lseq(const mcov_bam* b) { return (b && b->loaded) ? b->lseq.data() : nullptr; }
+const int32_t* mcov_bam_isize(const mcov_bam* b) { return (b && b->loaded) ? b->isize.data() : nullptr; }
+const uint32_t* mcov_bam_cig_off(const mcov_bam* b) { return (b && b->loaded) ? b->cig_off.data() : nullptr; }
+const uint32_t* mcov_bam_cig(const mcov_bam* b) { return (b && b->loaded) ? b->cig.data() : nullptr; }
+
+}  // extern "C"

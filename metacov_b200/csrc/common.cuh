@@ -1,0 +1,125 @@
+// common.cuh -- shared device helpers and POD types for the coverage kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "metacov_b200.h"
+
+namespace mcov {
+
+constexpr int kNumSMsB200 = 148;
+
+// BAM CIGAR ops that consume reference: M(0) D(2) N(3) =(7) X(8)
+// (htslib bam_cigar_type bit 1).
+constexpr uint32_t kRefConsumeMask = 0x18Du;
+
+__host__ __device__ __forceinline__ uint32_t cigar_ref_len(uint32_t op) {
+  return ((kRefConsumeMask >> (op & 15u)) & 1u) ? (op >> 4) : 0u;
+}
+
+// Counters of one pass, device resident (mirrored to mcov_pass_info).
+struct PassCounters {
+  unsigned long long n_reads;
+  unsigned long long n_pass;
+  unsigned long long aligned_bases;
+  int max_depth_seen;
+  int cap_metric;
+  int unsorted;          // set to 1 if any adjacent pair of reads is out of (tid,pos) order
+  unsigned int ticket;   // dynamic tile id for the scan kernel
+  unsigned int ticket2;  // dynamic tile id for the fused tile kernel
+  unsigned int max_span; // max clipped span of a near read (fused path)
+  unsigned int n_far;    // reads whose span exceeds the near window (fused path)
+  unsigned int pad;
+};
+
+// pysam __advance_samtools predicate + bam_plp_push's own UNMAP drop
+// (SURVEY.md Appendix A-2).
+__device__ __forceinline__ bool read_passes(uint32_t flag, uint32_t mapq, const mcov_filter& f) {
+  if (flag & f.flag_filter) return false;
+  if (f.flag_require && !(flag & f.flag_require)) return false;
+  if (mapq < f.min_mapq) return false;
+  if (f.ignore_orphans && (flag & 0x1u) && !(flag & 0x2u)) return false;
+  if (flag & 0x4u) return false;
+  return true;
+}
+
+__device__ __forceinline__ int4 ld_stream_int4(const int4* p) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint4 ld_stream_uint4(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream_int4(int4* p, const int4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_max(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ int warp_min(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Reference length of one read whose ops are cig[b0, b1), computed by a whole
+// warp with 128-bit loads where alignment allows (long-read path, config C5:
+// thousands of ops per read, the CIGAR stream is the dominant HBM traffic).
+__device__ __forceinline__ unsigned long long warp_cigar_reflen(const uint32_t* __restrict__ cig,
+                                                                uint32_t b0, uint32_t b1, int lane,
+                                                                bool base_aligned16) {
+  unsigned long long acc = 0;
+  uint32_t k = b0;
+  if (base_aligned16) {
+    uint32_t a0 = (b0 + 3u) & ~3u;           // first 16-byte aligned op index
+    if (a0 > b1) a0 = b1;
+    // head (< 4 ops)
+    if (b0 + (uint32_t)lane < a0) acc += cigar_ref_len(__ldg(cig + b0 + lane));
+    uint32_t nvec = (b1 - a0) >> 2;
+    const uint4* v = reinterpret_cast<const uint4*>(cig + a0);
+    uint32_t j = lane;
+    // 4 independent 512-byte warp loads in flight
+    for (; j + 96u < nvec; j += 128u) {
+      uint4 q0 = ld_stream_uint4(v + j), q1 = ld_stream_uint4(v + j + 32u);
+      uint4 q2 = ld_stream_uint4(v + j + 64u), q3 = ld_stream_uint4(v + j + 96u);
+      acc += cigar_ref_len(q0.x) + cigar_ref_len(q0.y) + cigar_ref_len(q0.z) + cigar_ref_len(q0.w);
+      acc += cigar_ref_len(q1.x) + cigar_ref_len(q1.y) + cigar_ref_len(q1.z) + cigar_ref_len(q1.w);
+      acc += cigar_ref_len(q2.x) + cigar_ref_len(q2.y) + cigar_ref_len(q2.z) + cigar_ref_len(q2.w);
+      acc += cigar_ref_len(q3.x) + cigar_ref_len(q3.y) + cigar_ref_len(q3.z) + cigar_ref_len(q3.w);
+    }
+    for (; j < nvec; j += 32u) {
+      uint4 q = ld_stream_uint4(v + j);
+      acc += cigar_ref_len(q.x) + cigar_ref_len(q.y) + cigar_ref_len(q.z) + cigar_ref_len(q.w);
+    }
+    k = a0 + (nvec << 2);                     // tail (< 4 ops)
+    if (k + (uint32_t)lane < b1) acc += cigar_ref_len(__ldg(cig + k + lane));
+  } else {
+    for (uint32_t i = k + lane; i < b1; i += 32u) acc += cigar_ref_len(__ldg(cig + i));
+  }
+  return warp_sum(acc);
+}
+
+}  // namespace mcov

@@ -1,0 +1,131 @@
+// ctx.cuh -- the context behind the C-ABI (device buffers, streams, state).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "common.cuh"
+
+namespace mcov {
+
+// grow-only device / pinned buffers
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+enum PassState { kIdle = 0, kAccumulating = 1, kDepthReady = 2 };
+
+// kernel ids for the optional per-kernel CUDA-event timing (mcov_profile_*)
+enum KernelId {
+  kKExpand = 0, kKScan, kKFusedPrep, kKTileFirst, kKScanCounts, kKFarScatter, kKFusedTile,
+  kKInitStats, kKRegionStats, kKWindowSums, kKIsizeHist, kKGroupCount, kKSortedStats, kKClear, kKernelCount
+};
+
+struct ProfRec { int id; cudaEvent_t a, b; };
+
+struct ReadStage {            // one staging set for host-resident batches
+  DevBuf tid, pos, flag, mapq, cig_off, cig;
+  cudaEvent_t consumed = nullptr;   // recorded after the kernel that read this set
+  bool in_flight = false;
+};
+
+}  // namespace mcov
+
+struct mcov_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copied = nullptr;
+  std::string err;
+
+  int32_t n_contigs = 0;
+  std::vector<int32_t> len;
+  std::vector<int64_t> off;
+  int64_t n_slots = 0;        // padded to a multiple of 4
+  mcov::DevBuf d_len, d_off;
+
+  int32_t* depth = nullptr;   // difference array, then depth
+  mcov::DevBuf depth_own;
+  bool depth_bound = false;
+
+  mcov_filter filt;
+  int state = mcov::kIdle;
+
+  mcov::DevBuf d_pc;          // PassCounters
+  mcov::DevBuf d_status;      // scan tile status words
+  mcov::ReadStage stage[2];
+  int stage_next = 0;
+  int64_t n_reads_pushed = 0;
+
+  // fused (sorted) path scratch
+  mcov::DevBuf d_end_slot, d_start_slot, d_far_list, d_tile_cnt, d_tile_off, d_far_sorted;
+
+  // stats scratch
+  mcov::DevBuf d_tasks, d_rlen, d_rchunks, d_rhist, d_pool, d_done, d_out, d_win_slot, d_win_n, d_win_out;
+  mcov::PinBuf h_pin;
+
+  // launch accounting + optional per-kernel event timing
+  int64_t n_launches = 0;
+  bool profiling = false;
+  std::vector<mcov::ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
+  double prof_ms[mcov::kKernelCount] = {0};
+  int64_t prof_n[mcov::kKernelCount] = {0};
+
+  cudaEvent_t ev_get() {
+    if (!ev_pool.empty()) { cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
+  void prof_begin(int id) {
+    ++n_launches;
+    if (!profiling) return;
+    mcov::ProfRec r; r.id = id; r.a = ev_get(); r.b = ev_get();
+    cudaEventRecord(r.a, stream);
+    prof.push_back(r);
+  }
+  void prof_end() {
+    if (!profiling || prof.empty()) return;
+    cudaEventRecord(prof.back().b, stream);
+  }
+  // fold finished records into the per-kernel totals (stream must be synchronised)
+  void prof_collect() {
+    for (auto& r : prof) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { prof_ms[r.id] += ms; prof_n[r.id] += 1; }
+      ev_pool.push_back(r.a); ev_pool.push_back(r.b);
+    }
+    prof.clear();
+  }
+};
+
+// wrap one kernel launch (or memset) for accounting / timing
+#define MCOV_LAUNCH(ctx, id, ...) do { (ctx)->prof_begin(id); __VA_ARGS__; (ctx)->prof_end(); } while (0)

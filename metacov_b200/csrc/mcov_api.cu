@@ -1,0 +1,592 @@
+// mcov_api.cu -- C-ABI entry points of the coverage hot path (include/metacov_b200.h).
+//
+// No CPU fallback lives here: every compute entry point launches CUDA kernels
+// and fails with MCOV_ERR_CUDA when there is no device.
+#include <algorithm>
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "ctx.cuh"
+#include "k_expand.cuh"
+#include "k_fused.cuh"
+#include "k_hist.cuh"
+#include "k_scan.cuh"
+#include "k_stats.cuh"
+
+using namespace mcov;
+
+int mcov_order_stats_by_sort(mcov_ctx* ctx, const int32_t* d_region, int64_t n, int64_t pad,
+                             mcov_region_stats* d_stat, mcov::DevBuf& keys_out, mcov::DevBuf& temp);
+
+namespace {
+
+int fail(mcov_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
+  if (c) {
+    c->err = what;
+    if (e != cudaSuccess) { c->err += ": "; c->err += cudaGetErrorString(e); }
+  }
+  return code;
+}
+
+#define CU(call)                                                        \
+  do {                                                                  \
+    cudaError_t e__ = (call);                                           \
+    if (e__ != cudaSuccess) return fail(ctx, MCOV_ERR_CUDA, #call, e__); \
+  } while (0)
+
+int grid_for(int64_t n, int threads, int per_sm) {
+  int64_t want = (n + threads - 1) / threads;
+  int64_t cap = (int64_t)kNumSMsB200 * per_sm;
+  if (want < 1) want = 1;
+  return (int)std::min<int64_t>(want, cap);
+}
+
+PassCounters* pc_of(mcov_ctx* ctx) { return ctx->d_pc.as<PassCounters>(); }
+
+int ensure_depth(mcov_ctx* ctx) {
+  if (ctx->n_contigs <= 0) return fail(ctx, MCOV_ERR_STATE, "mcov_set_contigs has not been called");
+  if (!ctx->depth_bound) {
+    CU(ctx->depth_own.ensure((size_t)ctx->n_slots * sizeof(int32_t)));
+    ctx->depth = ctx->depth_own.as<int32_t>();
+  }
+  CU(ctx->d_pc.ensure(sizeof(PassCounters)));
+  return MCOV_OK;
+}
+
+// Stage host SoA into device memory on the copy stream (double-buffered), or
+// pass device pointers through.  On return `a` holds device pointers and the
+// compute stream has been made to wait for the copies.
+int stage_reads(mcov_ctx* ctx, int64_t n, const int32_t* tid, const int32_t* pos, const uint16_t* flag,
+                const uint8_t* mapq, const uint32_t* cig_off, const uint32_t* cig, int mem_kind,
+                ExpandArgs& a, ReadStage** used) {
+  *used = nullptr;
+  a.n = n;
+  if (mem_kind == MCOV_MEM_DEVICE) {
+    a.tid = tid; a.pos = pos; a.flag = flag; a.mapq = mapq; a.cig_off = cig_off; a.cig = cig;
+  } else if (mem_kind == MCOV_MEM_HOST) {
+    ReadStage& s = ctx->stage[ctx->stage_next];
+    ctx->stage_next ^= 1;
+    if (s.in_flight) { CU(cudaEventSynchronize(s.consumed)); s.in_flight = false; }
+    uint32_t n_cig = cig_off[n];
+    CU(s.tid.ensure(n * 4)); CU(s.pos.ensure(n * 4)); CU(s.flag.ensure(n * 2)); CU(s.mapq.ensure(n));
+    CU(s.cig_off.ensure((n + 1) * 4)); CU(s.cig.ensure((size_t)n_cig * 4 + 16));
+    cudaStream_t cs = ctx->copy_stream;
+    CU(cudaMemcpyAsync(s.tid.p, tid, n * 4, cudaMemcpyHostToDevice, cs));
+    CU(cudaMemcpyAsync(s.pos.p, pos, n * 4, cudaMemcpyHostToDevice, cs));
+    CU(cudaMemcpyAsync(s.flag.p, flag, n * 2, cudaMemcpyHostToDevice, cs));
+    CU(cudaMemcpyAsync(s.mapq.p, mapq, n, cudaMemcpyHostToDevice, cs));
+    CU(cudaMemcpyAsync(s.cig_off.p, cig_off, (n + 1) * 4, cudaMemcpyHostToDevice, cs));
+    if (n_cig) CU(cudaMemcpyAsync(s.cig.p, cig, (size_t)n_cig * 4, cudaMemcpyHostToDevice, cs));
+    CU(cudaEventRecord(ctx->copied, cs));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->copied, 0));
+    a.tid = s.tid.as<int32_t>(); a.pos = s.pos.as<int32_t>(); a.flag = s.flag.as<uint16_t>();
+    a.mapq = s.mapq.as<uint8_t>(); a.cig_off = s.cig_off.as<uint32_t>(); a.cig = s.cig.as<uint32_t>();
+    *used = &s;
+  } else {
+    return fail(ctx, MCOV_ERR_ARG, "mem_kind must be MCOV_MEM_HOST or MCOV_MEM_DEVICE");
+  }
+  a.contig_off = ctx->d_off.as<int64_t>();
+  a.contig_len = ctx->d_len.as<int32_t>();
+  a.n_contigs = ctx->n_contigs;
+  a.filt = ctx->filt;
+  a.delta = ctx->depth;
+  a.pc = pc_of(ctx);
+  a.cig_aligned16 = ((reinterpret_cast<uintptr_t>(a.cig) & 15u) == 0) ? 1 : 0;
+  return MCOV_OK;
+}
+
+int finish_stage(mcov_ctx* ctx, ReadStage* s) {
+  if (!s) return MCOV_OK;
+  CU(cudaEventRecord(s->consumed, ctx->stream));
+  s->in_flight = true;
+  // the caller may reuse its host arrays once the copies are done
+  CU(cudaEventSynchronize(ctx->copied));
+  return MCOV_OK;
+}
+
+// Fused depth path for coordinate-sorted reads (k_fused.cuh).  `a` holds device pointers.
+int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a) {
+  const int64_t n = a.n;
+  const int64_t n_tiles = (ctx->n_slots + kTile - 1) / kTile;
+  const int64_t cnt_pad = (n_tiles + 3) & ~(int64_t)3;                 // scanned in place as int32
+  const int64_t cnt_tiles = (cnt_pad + kScanTile - 1) / kScanTile;
+  const uint32_t far_cap = (uint32_t)std::min<int64_t>(std::max<int64_t>(n, 1), kFarCapDefault);
+  // one zeroed scratch block: [tile_cnt | tile_cursor | status_main | status_cnt]
+  const size_t o_cnt = 0, o_cur = o_cnt + (size_t)cnt_pad * 4, o_stm = (o_cur + (size_t)n_tiles * 4 + 7) & ~(size_t)7,
+               o_stc = o_stm + (size_t)n_tiles * 8, z_bytes = o_stc + (size_t)cnt_tiles * 8;
+  CU(ctx->d_status.ensure(z_bytes));
+  CU(ctx->d_start_slot.ensure((size_t)std::max<int64_t>(n, 1) * sizeof(uint2)));     // rec
+  CU(ctx->d_tile_off.ensure((size_t)(n_tiles + 1) * 8));                              // tile_first
+  CU(ctx->d_far_list.ensure((size_t)far_cap * 8));
+  CU(ctx->d_far_sorted.ensure((size_t)far_cap * 4));
+  cudaStream_t s = ctx->stream;
+  char* z = ctx->d_status.as<char>();
+  CU(cudaMemsetAsync(z, 0, z_bytes, s));
+  FusedArgs f;
+  f.e = a;
+  f.rec = ctx->d_start_slot.as<uint2>();
+  f.n_slots = ctx->n_slots;
+  f.n_tiles = n_tiles;
+  f.far_end = ctx->d_far_list.as<int64_t>();
+  f.far_cap = far_cap;
+  f.tile_cnt = reinterpret_cast<uint32_t*>(z + o_cnt);
+  f.tile_cursor = reinterpret_cast<uint32_t*>(z + o_cur);
+  f.far_sorted = ctx->d_far_sorted.as<uint32_t>();
+  f.tile_first = ctx->d_tile_off.as<int64_t>();
+  f.status = reinterpret_cast<unsigned long long*>(z + o_stm);
+  f.depth = ctx->depth;
+  if (n > 0) {
+    MCOV_LAUNCH(ctx, kKFusedPrep, (k_fused_prep<<<grid_for(n, kExpandThreads, 8), kExpandThreads, 0, s>>>(f)));
+    CU(cudaGetLastError());
+  }
+  MCOV_LAUNCH(ctx, kKTileFirst, (k_tile_first<<<(unsigned)((n_tiles + 1 + 255) / 256), 256, 0, s>>>(f)));
+  CU(cudaGetLastError());
+  MCOV_LAUNCH(ctx, kKScanCounts, (k_scan_inplace<false><<<(unsigned)cnt_tiles, kScanThreads, 0, s>>>(
+      reinterpret_cast<int32_t*>(f.tile_cnt), cnt_pad, reinterpret_cast<unsigned long long*>(z + o_stc), pc_of(ctx))));
+  CU(cudaGetLastError());
+  MCOV_LAUNCH(ctx, kKFarScatter, (k_far_scatter<<<kNumSMsB200 * 2, 256, 0, s>>>(f)));
+  CU(cudaGetLastError());
+  MCOV_LAUNCH(ctx, kKFusedTile, (k_fused_tile<<<(unsigned)n_tiles, kFusedThreads, 0, s>>>(f)));
+  CU(cudaGetLastError());
+  return MCOV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mcov_abi_version(void) { return MCOV_ABI_VERSION; }
+
+void mcov_default_filter(mcov_filter* f) {
+  if (!f) return;
+  std::memset(f, 0, sizeof(*f));
+  f->flag_filter = 0x704;   // UNMAP | SECONDARY | QCFAIL | DUP (pysam pileup default)
+  f->flag_require = 0;
+  f->min_mapq = 0;
+  f->ignore_orphans = 1;
+  f->max_depth = 8000;
+}
+
+int mcov_create(mcov_ctx** out, int device, void* stream) {
+  if (!out) return MCOV_ERR_ARG;
+  *out = nullptr;
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev <= 0 || device < 0 || device >= n_dev) return MCOV_ERR_CUDA;
+  mcov_ctx* ctx = new (std::nothrow) mcov_ctx();
+  if (!ctx) return MCOV_ERR_NOMEM;
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return MCOV_ERR_CUDA; }
+  if (stream) { ctx->stream = reinterpret_cast<cudaStream_t>(stream); ctx->own_stream = false; }
+  else {
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MCOV_ERR_CUDA; }
+    ctx->own_stream = true;
+  }
+  bool ok = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ctx->copied, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ctx->stage[0].consumed, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ctx->stage[1].consumed, cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) { mcov_destroy(ctx); return MCOV_ERR_CUDA; }
+  mcov_default_filter(&ctx->filt);
+  *out = ctx;
+  return MCOV_OK;
+}
+
+void mcov_destroy(mcov_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+  if (ctx->copied) cudaEventDestroy(ctx->copied);
+  for (auto& s : ctx->stage) {
+    if (s.consumed) cudaEventDestroy(s.consumed);
+    s.tid.release(); s.pos.release(); s.flag.release(); s.mapq.release(); s.cig_off.release(); s.cig.release();
+  }
+  DevBuf* bufs[] = {&ctx->d_len, &ctx->d_off, &ctx->depth_own, &ctx->d_pc, &ctx->d_status, &ctx->d_end_slot,
+                    &ctx->d_start_slot, &ctx->d_far_list, &ctx->d_tile_cnt, &ctx->d_tile_off, &ctx->d_far_sorted,
+                    &ctx->d_tasks, &ctx->d_rlen, &ctx->d_rchunks, &ctx->d_rhist, &ctx->d_pool, &ctx->d_done,
+                    &ctx->d_out, &ctx->d_win_slot, &ctx->d_win_n, &ctx->d_win_out};
+  for (DevBuf* b : bufs) b->release();
+  ctx->h_pin.release();
+  ctx->prof_collect();
+  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* mcov_last_error(const mcov_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int mcov_set_contigs(mcov_ctx* ctx, int32_t n_contigs, const int32_t* len) {
+  if (!ctx || n_contigs <= 0 || !len) return fail(ctx, MCOV_ERR_ARG, "mcov_set_contigs: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  ctx->len.assign(len, len + n_contigs);
+  ctx->off.resize((size_t)n_contigs + 1);
+  int64_t o = 0;
+  for (int32_t c = 0; c < n_contigs; ++c) {
+    if (len[c] < 0) return fail(ctx, MCOV_ERR_ARG, "mcov_set_contigs: negative contig length");
+    ctx->off[c] = o;
+    o += ((int64_t)len[c] + 1 + 3) & ~(int64_t)3;   // len+1 slots, next contig 16-byte aligned
+  }
+  ctx->off[n_contigs] = o;
+  ctx->n_slots = o;
+  ctx->n_contigs = n_contigs;
+  CU(ctx->d_len.ensure((size_t)n_contigs * 4));
+  CU(ctx->d_off.ensure(((size_t)n_contigs + 1) * 8));
+  CU(cudaMemcpyAsync(ctx->d_len.p, ctx->len.data(), (size_t)n_contigs * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_off.p, ctx->off.data(), ((size_t)n_contigs + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->state = kIdle;
+  ctx->depth_bound = false;
+  ctx->depth = nullptr;
+  return MCOV_OK;
+}
+
+int64_t mcov_n_slots(const mcov_ctx* ctx) { return ctx ? ctx->n_slots : 0; }
+
+int64_t mcov_contig_offset(const mcov_ctx* ctx, int32_t tid) {
+  if (!ctx || tid < 0 || tid >= ctx->n_contigs) return -1;
+  return ctx->off[tid];
+}
+
+int mcov_bind_depth(mcov_ctx* ctx, int32_t* dev, int64_t n_slots) {
+  if (!ctx) return MCOV_ERR_ARG;
+  if (!dev || n_slots < ctx->n_slots || (reinterpret_cast<uintptr_t>(dev) & 15u))
+    return fail(ctx, MCOV_ERR_ARG, "mcov_bind_depth: need a 16-byte aligned device buffer of >= mcov_n_slots() int32");
+  ctx->depth = dev;
+  ctx->depth_bound = true;
+  ctx->state = kIdle;
+  return MCOV_OK;
+}
+
+int mcov_set_filter(mcov_ctx* ctx, const mcov_filter* f) {
+  if (!ctx || !f) return fail(ctx, MCOV_ERR_ARG, "mcov_set_filter: null argument");
+  ctx->filt = *f;
+  return MCOV_OK;
+}
+
+int mcov_begin(mcov_ctx* ctx) {
+  if (!ctx) return MCOV_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  int rc = ensure_depth(ctx);
+  if (rc) return rc;
+  MCOV_LAUNCH(ctx, kKClear, CU(cudaMemsetAsync(ctx->depth, 0, (size_t)ctx->n_slots * 4, ctx->stream)));
+  CU(cudaMemsetAsync(ctx->d_pc.p, 0, sizeof(PassCounters), ctx->stream));
+  ctx->n_reads_pushed = 0;
+  ctx->state = kAccumulating;
+  return MCOV_OK;
+}
+
+int mcov_push_reads(mcov_ctx* ctx, int64_t n, const int32_t* tid, const int32_t* pos, const uint16_t* flag,
+                    const uint8_t* mapq, const uint32_t* cig_off, const uint32_t* cig, int mem_kind) {
+  if (!ctx) return MCOV_ERR_ARG;
+  if (ctx->state != kAccumulating) return fail(ctx, MCOV_ERR_STATE, "mcov_push_reads: call mcov_begin first");
+  if (n < 0) return fail(ctx, MCOV_ERR_ARG, "mcov_push_reads: n < 0");
+  if (n == 0) return MCOV_OK;
+  if (!tid || !pos || !flag || !mapq || !cig_off) return fail(ctx, MCOV_ERR_ARG, "mcov_push_reads: null array");
+  CU(cudaSetDevice(ctx->device));
+  ExpandArgs a;
+  ReadStage* st = nullptr;
+  int rc = stage_reads(ctx, n, tid, pos, flag, mapq, cig_off, cig, mem_kind, a, &st);
+  if (rc) return rc;
+  MCOV_LAUNCH(ctx, kKExpand, (k_expand<<<grid_for(n, kExpandThreads, 8), kExpandThreads, 0, ctx->stream>>>(a)));
+  CU(cudaGetLastError());
+  ctx->n_reads_pushed += n;
+  return finish_stage(ctx, st);
+}
+
+int mcov_finalize(mcov_ctx* ctx) {
+  if (!ctx) return MCOV_ERR_ARG;
+  if (ctx->state != kAccumulating) return fail(ctx, MCOV_ERR_STATE, "mcov_finalize: nothing accumulated");
+  CU(cudaSetDevice(ctx->device));
+  int64_t n_tiles = (ctx->n_slots + kScanTile - 1) / kScanTile;
+  CU(ctx->d_status.ensure((size_t)n_tiles * 8));
+  CU(cudaMemsetAsync(ctx->d_status.p, 0, (size_t)n_tiles * 8, ctx->stream));
+  CU(cudaMemsetAsync(&pc_of(ctx)->ticket, 0, sizeof(unsigned int), ctx->stream));
+  MCOV_LAUNCH(ctx, kKScan, (k_scan_inplace<true><<<(unsigned)n_tiles, kScanThreads, 0, ctx->stream>>>(
+      ctx->depth, ctx->n_slots, ctx->d_status.as<unsigned long long>(), pc_of(ctx))));
+  CU(cudaGetLastError());
+  ctx->state = kDepthReady;
+  return MCOV_OK;
+}
+
+int mcov_depth_sorted(mcov_ctx* ctx, int64_t n, const int32_t* tid, const int32_t* pos, const uint16_t* flag,
+                      const uint8_t* mapq, const uint32_t* cig_off, const uint32_t* cig, int mem_kind) {
+  if (!ctx) return MCOV_ERR_ARG;
+  if (n < 0) return fail(ctx, MCOV_ERR_ARG, "mcov_depth_sorted: n < 0");
+  if (n > 0 && (!tid || !pos || !flag || !mapq || !cig_off)) return fail(ctx, MCOV_ERR_ARG, "mcov_depth_sorted: null array");
+  CU(cudaSetDevice(ctx->device));
+  int rc = ensure_depth(ctx);
+  if (rc) return rc;
+  CU(cudaMemsetAsync(ctx->d_pc.p, 0, sizeof(PassCounters), ctx->stream));
+  ExpandArgs a;
+  ReadStage* st = nullptr;
+  if (n > 0) {
+    rc = stage_reads(ctx, n, tid, pos, flag, mapq, cig_off, cig, mem_kind, a, &st);
+    if (rc) return rc;
+  } else {
+    std::memset(&a, 0, sizeof(a));
+    a.pc = pc_of(ctx);
+  }
+  rc = fused_depth_sorted(ctx, a);
+  if (rc) return rc;
+  ctx->n_reads_pushed = n;
+  rc = finish_stage(ctx, st);
+  if (rc) return rc;
+  // sortedness is a property of the data: one small read-back decides
+  PassCounters h;
+  CU(cudaMemcpyAsync(&h, ctx->d_pc.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (h.unsorted) {
+    ctx->state = kIdle;
+    return fail(ctx, MCOV_ERR_UNSORTED, "mcov_depth_sorted: reads are not sorted by (tid,pos); use mcov_begin/push/finalize");
+  }
+  if ((int64_t)h.n_far > std::min<int64_t>(std::max<int64_t>(n, 1), kFarCapDefault)) {
+    ctx->state = kIdle;
+    return fail(ctx, MCOV_ERR_RANGE, "mcov_depth_sorted: too many long-span reads for the bucket list; use mcov_begin/push/finalize");
+  }
+  ctx->state = kDepthReady;
+  return MCOV_OK;
+}
+
+int mcov_pass_info_get(mcov_ctx* ctx, mcov_pass_info* out) {
+  if (!ctx || !out) return fail(ctx, MCOV_ERR_ARG, "mcov_pass_info_get: null argument");
+  if (ctx->state == kIdle) return fail(ctx, MCOV_ERR_STATE, "mcov_pass_info_get: no pass has run");
+  CU(cudaSetDevice(ctx->device));
+  PassCounters h;
+  CU(cudaMemcpyAsync(&h, ctx->d_pc.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  out->n_reads = ctx->n_reads_pushed;
+  out->n_pass = (int64_t)h.n_pass;
+  out->aligned_bases = (int64_t)h.aligned_bases;
+  out->max_depth_seen = h.max_depth_seen;
+  out->cap_metric = h.cap_metric;
+  out->sorted = h.unsorted ? 0 : 1;
+  out->reserved = 0;
+  return MCOV_OK;
+}
+
+static const char* kKernelNames[kKernelCount] = {
+    "k_expand", "k_scan_inplace", "k_fused_prep", "k_tile_first", "k_scan_counts", "k_far_scatter", "k_fused_tile",
+    "k_init_region_stats", "k_region_stats", "k_window_sums", "k_isize_hist", "k_group_count", "k_sorted_order_stats",
+    "memset_depth"};
+
+int64_t mcov_launch_count(const mcov_ctx* ctx) { return ctx ? ctx->n_launches : 0; }
+
+int mcov_profile_enable(mcov_ctx* ctx, int on) {
+  if (!ctx) return MCOV_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->prof_collect();
+  ctx->profiling = on != 0;
+  if (on) for (int k = 0; k < kKernelCount; ++k) { ctx->prof_ms[k] = 0; ctx->prof_n[k] = 0; }
+  return MCOV_OK;
+}
+
+int mcov_profile_read(mcov_ctx* ctx, mcov_kernel_time* out, int cap) {
+  if (!ctx || (cap > 0 && !out)) return MCOV_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->prof_collect();
+  int n = 0;
+  for (int k = 0; k < kKernelCount && n < cap; ++k) {
+    if (!ctx->prof_n[k]) continue;
+    std::snprintf(out[n].name, sizeof(out[n].name), "%s", kKernelNames[k]);
+    out[n].launches = ctx->prof_n[k];
+    out[n].total_ms = ctx->prof_ms[k];
+    ++n;
+  }
+  return n;
+}
+
+int32_t* mcov_depth_ptr(mcov_ctx* ctx) { return (ctx && ctx->state == kDepthReady) ? ctx->depth : nullptr; }
+
+int mcov_copy_depth(mcov_ctx* ctx, int32_t tid, int32_t start, int32_t end, int32_t* host_out) {
+  if (!ctx) return MCOV_ERR_ARG;
+  if (ctx->state != kDepthReady) return fail(ctx, MCOV_ERR_STATE, "mcov_copy_depth: depth not ready (finalize first)");
+  if (tid < 0 || tid >= ctx->n_contigs || start < 0 || end < start || end > ctx->len[tid] || (!host_out && end > start))
+    return fail(ctx, MCOV_ERR_ARG, "mcov_copy_depth: region out of range");
+  if (end == start) return MCOV_OK;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(host_out, ctx->depth + ctx->off[tid] + start, (size_t)(end - start) * 4, cudaMemcpyDeviceToHost,
+                     ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MCOV_OK;
+}
+
+int mcov_region_stats_run(mcov_ctx* ctx, int64_t g, const int32_t* tid, const int32_t* start, const int32_t* end,
+                          int32_t breadth_n, mcov_region_stats* host_out) {
+  if (!ctx) return MCOV_ERR_ARG;
+  if (ctx->state != kDepthReady) return fail(ctx, MCOV_ERR_STATE, "mcov_region_stats_run: depth not ready (finalize first)");
+  if (g < 0 || (g > 0 && (!tid || !start || !end || !host_out))) return fail(ctx, MCOV_ERR_ARG, "mcov_region_stats_run: bad arguments");
+  if (g == 0) return MCOV_OK;
+  if (g > INT32_MAX) return fail(ctx, MCOV_ERR_RANGE, "mcov_region_stats_run: more than 2^31-1 regions");
+  CU(cudaSetDevice(ctx->device));
+  // A region may reach past its contig: the reference's vector is end-start long whatever the
+  // contig length (pileup.py:10-11) and stays 0 there, so those positions count as depth 0.
+  int64_t total = 0;
+  for (int64_t i = 0; i < g; ++i) {
+    if (tid[i] < 0 || tid[i] >= ctx->n_contigs || start[i] < 0 || end[i] < start[i])
+      return fail(ctx, MCOV_ERR_ARG, "mcov_region_stats_run: need 0 <= start <= end and a valid tid");
+    int64_t len = ctx->len[tid[i]];
+    total += std::max<int64_t>(0, std::min<int64_t>(end[i], len) - std::min<int64_t>(start[i], len));
+  }
+  // chunk length: enough chunks to fill the machine several times over, few enough that
+  // most regions stay single-chunk
+  int64_t chunk = (total / ((int64_t)kNumSMsB200 * 16) + 4095) / 4096 * 4096;
+  chunk = std::max<int64_t>(8192, std::min<int64_t>(65536, chunk));
+  std::vector<StatTask> tasks;
+  tasks.reserve((size_t)(g + total / chunk + 1));
+  std::vector<int32_t> rlen((size_t)g), rpad((size_t)g), rchunks((size_t)g), rhist((size_t)g);
+  int32_t n_multi = 0;
+  for (int64_t i = 0; i < g; ++i) {
+    int64_t len = ctx->len[tid[i]];
+    int64_t cs = std::min<int64_t>(start[i], len), ce = std::min<int64_t>(end[i], len);
+    int32_t n = (int32_t)(ce - cs);
+    int32_t pad = (int32_t)((int64_t)end[i] - start[i] - n);
+    int32_t nch = (int32_t)((n + chunk - 1) / chunk);
+    if (nch == 0 && pad > 0) nch = 1;             // nothing but zeros: one empty chunk finishes it
+    rlen[i] = n; rpad[i] = pad; rchunks[i] = nch;
+    rhist[i] = nch > 1 ? n_multi++ : -1;
+    int64_t slot = ctx->off[tid[i]] + cs;
+    for (int32_t k = 0; k < nch; ++k) {
+      StatTask t;
+      t.slot = slot + (int64_t)k * chunk;
+      t.n = (int32_t)std::max<int64_t>(0, std::min<int64_t>(chunk, n - (int64_t)k * chunk));
+      t.region = (int32_t)i;
+      tasks.push_back(t);
+    }
+  }
+  cudaStream_t s = ctx->stream;
+  CU(ctx->d_out.ensure((size_t)g * sizeof(mcov_region_stats)));
+  MCOV_LAUNCH(ctx, kKInitStats, (k_init_region_stats<<<(unsigned)((g + 255) / 256), 256, 0, s>>>(ctx->d_out.as<mcov_region_stats>(), g)));
+  CU(cudaGetLastError());
+  if (!tasks.empty()) {
+    CU(ctx->d_tasks.ensure(tasks.size() * sizeof(StatTask)));
+    CU(ctx->d_rlen.ensure((size_t)g * 8)); CU(ctx->d_rchunks.ensure((size_t)g * 4)); CU(ctx->d_rhist.ensure((size_t)g * 4));
+    CU(ctx->d_done.ensure((size_t)g * 4));
+    CU(ctx->d_pool.ensure((size_t)std::max(n_multi, 1) * kHistBins * 4));
+    int32_t* d_rlen = ctx->d_rlen.as<int32_t>();
+    int32_t* d_rpad = d_rlen + g;
+    CU(cudaMemcpyAsync(ctx->d_tasks.p, tasks.data(), tasks.size() * sizeof(StatTask), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(d_rlen, rlen.data(), (size_t)g * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(d_rpad, rpad.data(), (size_t)g * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(ctx->d_rchunks.p, rchunks.data(), (size_t)g * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(ctx->d_rhist.p, rhist.data(), (size_t)g * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(ctx->d_done.p, 0, (size_t)g * 4, s));
+    if (n_multi) CU(cudaMemsetAsync(ctx->d_pool.p, 0, (size_t)n_multi * kHistBins * 4, s));
+    StatArgs a;
+    a.depth = ctx->depth; a.tasks = ctx->d_tasks.as<StatTask>(); a.region_len = d_rlen; a.region_pad = d_rpad;
+    a.region_chunks = ctx->d_rchunks.as<int32_t>(); a.region_hist = ctx->d_rhist.as<int32_t>();
+    a.hist_pool = ctx->d_pool.as<uint32_t>(); a.region_done = ctx->d_done.as<uint32_t>();
+    a.out = ctx->d_out.as<mcov_region_stats>(); a.breadth_n = breadth_n;
+    MCOV_LAUNCH(ctx, kKRegionStats, (k_region_stats<<<(unsigned)tasks.size(), kStatThreads, 0, s>>>(a)));
+    CU(cudaGetLastError());
+  }
+  CU(cudaMemcpyAsync(host_out, ctx->d_out.p, (size_t)g * sizeof(mcov_region_stats), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  // regions whose depth left the counting histogram's range: exact order statistics by a
+  // GPU radix sort of the region (rare: needs max_depth raised above 8191)
+  bool redo = false;
+  for (int64_t i = 0; i < g; ++i) {
+    if (end[i] == start[i]) { std::memset(&host_out[i], 0, sizeof(mcov_region_stats)); continue; }
+    if (host_out[i].flags & kStatOverflow) {
+      int rc = mcov_order_stats_by_sort(ctx, ctx->depth + ctx->off[tid[i]] + std::min<int64_t>(start[i], ctx->len[tid[i]]),
+                                        rlen[i], rpad[i], ctx->d_out.as<mcov_region_stats>() + i, ctx->d_win_slot,
+                                        ctx->d_win_out);
+      if (rc) return fail(ctx, rc, "mcov_region_stats_run: radix order statistics failed");
+      redo = true;
+    }
+  }
+  if (redo) {
+    std::vector<mcov_region_stats> again((size_t)g);
+    CU(cudaMemcpyAsync(again.data(), ctx->d_out.p, (size_t)g * sizeof(mcov_region_stats), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    for (int64_t i = 0; i < g; ++i)
+      if (end[i] != start[i] && (host_out[i].flags & kStatOverflow)) {
+        host_out[i].iq_sum = again[i].iq_sum; host_out[i].med_lo = again[i].med_lo; host_out[i].med_hi = again[i].med_hi;
+        host_out[i].flags = kStatValid | kStatOverflow;
+      }
+  }
+  return MCOV_OK;
+}
+
+int mcov_window_means(mcov_ctx* ctx, int32_t window, double* host_out, int64_t n_out) {
+  if (!ctx) return MCOV_ERR_ARG;
+  if (ctx->state != kDepthReady) return fail(ctx, MCOV_ERR_STATE, "mcov_window_means: depth not ready");
+  if (window <= 0 || !host_out) return fail(ctx, MCOV_ERR_ARG, "mcov_window_means: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  std::vector<int64_t> wslot;
+  std::vector<int32_t> wn;
+  for (int32_t c = 0; c < ctx->n_contigs; ++c)
+    for (int64_t p = 0; p < ctx->len[c]; p += window) {
+      wslot.push_back(ctx->off[c] + p);
+      wn.push_back((int32_t)std::min<int64_t>(window, ctx->len[c] - p));
+    }
+  int64_t nw = (int64_t)wslot.size();
+  if (nw != n_out) return fail(ctx, MCOV_ERR_ARG, "mcov_window_means: n_out != sum(ceil(len/window))");
+  if (nw == 0) return MCOV_OK;
+  cudaStream_t s = ctx->stream;
+  CU(ctx->d_win_slot.ensure((size_t)nw * 8)); CU(ctx->d_win_n.ensure((size_t)nw * 4)); CU(ctx->d_win_out.ensure((size_t)nw * 8));
+  CU(cudaMemcpyAsync(ctx->d_win_slot.p, wslot.data(), (size_t)nw * 8, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(ctx->d_win_n.p, wn.data(), (size_t)nw * 4, cudaMemcpyHostToDevice, s));
+  int64_t threads = nw * 32;
+  MCOV_LAUNCH(ctx, kKWindowSums, (k_window_sums<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(
+      ctx->depth, ctx->d_win_slot.as<int64_t>(), ctx->d_win_n.as<int32_t>(), nw, ctx->d_win_out.as<long long>())));
+  CU(cudaGetLastError());
+  std::vector<long long> sums((size_t)nw);
+  CU(cudaMemcpyAsync(sums.data(), ctx->d_win_out.p, (size_t)nw * 8, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  for (int64_t i = 0; i < nw; ++i) host_out[i] = (double)sums[i] / (double)wn[i];
+  return MCOV_OK;
+}
+
+int mcov_isize_hist(mcov_ctx* ctx, int64_t n, const uint16_t* flag, const int32_t* isize, int mem_kind,
+                    int32_t n_group_flags, const uint16_t* group_flags, int32_t n_bins, uint32_t* hist_out,
+                    uint64_t* group_counts_out, int32_t* max_isize_out) {
+  if (!ctx) return MCOV_ERR_ARG;
+  if (n < 0 || n_group_flags < 0 || n_group_flags > kMaxGroupFlags || n_bins <= 0 || !hist_out || !group_counts_out ||
+      !max_isize_out || (n_group_flags > 0 && !group_flags) || (n > 0 && (!flag || !isize)))
+    return fail(ctx, MCOV_ERR_ARG, "mcov_isize_hist: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  const int groups = 1 << n_group_flags;
+  const size_t hist_bytes = (size_t)groups * n_bins * 4;
+  cudaStream_t s = ctx->stream;
+  // scratch: [hist][group_cnt u64][max_isize int]
+  size_t off_cnt = (hist_bytes + 7) & ~(size_t)7, off_mx = off_cnt + (size_t)groups * 8;
+  CU(ctx->d_win_out.ensure(off_mx + 8));
+  char* base = ctx->d_win_out.as<char>();
+  CU(cudaMemsetAsync(base, 0, off_mx + 8, s));
+  IsizeArgs a;
+  a.n = n; a.n_group_flags = n_group_flags; a.n_bins = n_bins;
+  for (int k = 0; k < kMaxGroupFlags; ++k) a.group_flags[k] = k < n_group_flags ? group_flags[k] : 0;
+  a.hist = reinterpret_cast<uint32_t*>(base);
+  a.group_cnt = reinterpret_cast<unsigned long long*>(base + off_cnt);
+  a.max_isize = reinterpret_cast<int*>(base + off_mx);
+  if (n > 0) {
+    if (mem_kind == MCOV_MEM_HOST) {
+      ReadStage& st = ctx->stage[0];
+      if (st.in_flight) { CU(cudaEventSynchronize(st.consumed)); st.in_flight = false; }
+      CU(st.flag.ensure((size_t)n * 2)); CU(st.pos.ensure((size_t)n * 4));
+      CU(cudaMemcpyAsync(st.flag.p, flag, (size_t)n * 2, cudaMemcpyHostToDevice, s));
+      CU(cudaMemcpyAsync(st.pos.p, isize, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+      a.flag = st.flag.as<uint16_t>(); a.isize = st.pos.as<int32_t>();
+    } else if (mem_kind == MCOV_MEM_DEVICE) {
+      a.flag = flag; a.isize = isize;
+    } else return fail(ctx, MCOV_ERR_ARG, "mcov_isize_hist: bad mem_kind");
+    int use_smem = ((int64_t)groups * n_bins <= kIsizeSmemBins) ? 1 : 0;
+    int grid = grid_for(n, kHistThreads, 4);
+    MCOV_LAUNCH(ctx, kKIsizeHist, (k_isize_hist<<<grid, kHistThreads, 0, s>>>(a, use_smem)));
+    CU(cudaGetLastError());
+    MCOV_LAUNCH(ctx, kKGroupCount, (k_group_count<<<grid, kHistThreads, 0, s>>>(a)));
+    CU(cudaGetLastError());
+  }
+  CU(cudaMemcpyAsync(hist_out, a.hist, hist_bytes, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(group_counts_out, a.group_cnt, (size_t)groups * 8, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(max_isize_out, a.max_isize, 4, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return MCOV_OK;
+}
+
+}  // extern "C"

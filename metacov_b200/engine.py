@@ -1,0 +1,225 @@
+"""Host-side driver of the CUDA coverage path (thin layer over the C-ABI).
+
+One ``CoverageEngine`` = one ``mcov_ctx`` = one GPU.  It owns the per-base
+depth of every contig of one BAM (the quantity reference metacov/pileup.py:
+10-16 rebuilds per region) and answers region queries from it.
+"""
+import ctypes as C
+from collections import namedtuple
+
+import numpy as np
+
+from . import _capi
+from ._capi import McovError, lib
+
+ReadBatch = namedtuple("ReadBatch", "tid pos flag mapq cig_off cig")
+ReadBatch.__doc__ = """SoA of mapped reads: the bam1_t fields the coverage path needs.
+
+tid:int32[n] pos:int32[n] flag:uint16[n] mapq:uint8[n] cig_off:uint32[n+1]
+cig:uint32[cig_off[n]] (BAM encoding len<<4|op).  numpy arrays (host) or torch
+tensors (host or CUDA)."""
+
+_DT = dict(tid=np.int32, pos=np.int32, flag=np.uint16, mapq=np.uint8, cig_off=np.uint32, cig=np.uint32)
+
+
+def _is_torch(a):
+    return hasattr(a, "data_ptr") and hasattr(a, "is_cuda")
+
+
+def _mem_kind(batch):
+    kinds = set()
+    for name, a in zip(ReadBatch._fields, batch):
+        if _is_torch(a):
+            kinds.add(_capi.MEM_DEVICE if a.is_cuda else _capi.MEM_HOST)
+            if not a.is_contiguous():
+                raise ValueError("ReadBatch.%s must be contiguous" % name)
+        else:
+            kinds.add(_capi.MEM_HOST)
+    if len(kinds) != 1:
+        raise ValueError("ReadBatch mixes host and device arrays")
+    return kinds.pop()
+
+
+def _canon(batch):
+    """numpy members -> contiguous arrays of the ABI dtypes; torch members are
+    checked, not converted."""
+    out = []
+    for name, a in zip(ReadBatch._fields, batch):
+        if _is_torch(a):
+            import torch
+            want = {np.int32: torch.int32, np.uint16: (torch.uint16, torch.int16),
+                    np.uint8: torch.uint8, np.uint32: (torch.uint32, torch.int32)}[_DT[name]]
+            want = want if isinstance(want, tuple) else (want,)
+            if a.dtype not in want:
+                raise TypeError("ReadBatch.%s: dtype %s, expected %s" % (name, a.dtype, want[0]))
+            out.append(a)
+        else:
+            out.append(np.ascontiguousarray(a, dtype=_DT[name]))
+    return ReadBatch(*out)
+
+
+class CoverageEngine:
+    def __init__(self, lengths, device=0, stream=None, filt=None):
+        self._ctx = C.c_void_p()
+        rc = lib.mcov_create(C.byref(self._ctx), int(device), stream)
+        if rc != 0:
+            self._ctx = None
+            raise McovError(rc, "mcov_create failed: no usable CUDA device %d (there is no CPU fallback)" % device)
+        self.device = int(device)
+        self.lengths = np.ascontiguousarray(lengths, dtype=np.int32)
+        self._check(lib.mcov_set_contigs(self._ctx, len(self.lengths), _capi.ptr(self.lengths)))
+        self.n_slots = lib.mcov_n_slots(self._ctx)
+        self.filter = _capi.Filter()
+        lib.mcov_default_filter(C.byref(self.filter))
+        if filt is not None:
+            self.set_filter(**filt)
+        self._keep = None
+
+    # -- plumbing ---------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            raise McovError(rc, lib.mcov_last_error(self._ctx).decode())
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            lib.mcov_destroy(self._ctx)
+            self._ctx = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+        return False
+
+    def set_filter(self, flag_filter=None, flag_require=None, min_mapq=None, ignore_orphans=None, max_depth=None):
+        f = self.filter
+        if flag_filter is not None:
+            f.flag_filter = flag_filter
+        if flag_require is not None:
+            f.flag_require = flag_require
+        if min_mapq is not None:
+            f.min_mapq = min_mapq
+        if ignore_orphans is not None:
+            f.ignore_orphans = 1 if ignore_orphans else 0
+        if max_depth is not None:
+            f.max_depth = max_depth
+        self._check(lib.mcov_set_filter(self._ctx, C.byref(f)))
+
+    def contig_offset(self, tid):
+        return lib.mcov_contig_offset(self._ctx, int(tid))
+
+    def bind_depth(self, tensor):
+        """Use a caller-owned CUDA int32 tensor (>= n_slots elements) as the depth store."""
+        self._keep = tensor
+        self._check(lib.mcov_bind_depth(self._ctx, tensor.data_ptr(), tensor.numel()))
+
+    # -- depth ------------------------------------------------------------
+    def begin(self):
+        self._check(lib.mcov_begin(self._ctx))
+
+    def push(self, batch):
+        b = _canon(batch)
+        n = len(b.tid)
+        self._check(lib.mcov_push_reads(self._ctx, n, *[_capi.ptr(x) for x in b], _mem_kind(b)))
+
+    def finalize(self):
+        self._check(lib.mcov_finalize(self._ctx))
+
+    def depth_sorted(self, batch):
+        """Fused path; raises McovError(MCOV_ERR_UNSORTED) on unsorted input."""
+        b = _canon(batch)
+        n = len(b.tid)
+        self._check(lib.mcov_depth_sorted(self._ctx, n, *[_capi.ptr(x) for x in b], _mem_kind(b)))
+
+    def compute_depth(self, batch):
+        """Per-base depth of all contigs from one batch: the fused sorted path,
+        or clear + expand + scan when the reads are not coordinate-sorted (or
+        carry more long-span reads than the fused path buckets).  Both run on
+        the GPU."""
+        try:
+            self.depth_sorted(batch)
+            return "fused"
+        except McovError as e:
+            if e.code not in (_capi.MCOV_ERR_UNSORTED, _capi.MCOV_ERR_RANGE):
+                raise
+        self.begin()
+        self.push(batch)
+        self.finalize()
+        return "push"
+
+    def pass_info(self):
+        info = _capi.PassInfo()
+        self._check(lib.mcov_pass_info_get(self._ctx, C.byref(info)))
+        return {k: getattr(info, k) for k, _ in _capi.PassInfo._fields_ if k != "reserved"}
+
+    def copy_depth(self, tid, start=0, end=None):
+        end = int(self.lengths[tid]) if end is None else int(end)
+        out = np.empty(max(end - int(start), 0), dtype=np.int32)
+        self._check(lib.mcov_copy_depth(self._ctx, int(tid), int(start), end, _capi.ptr(out)))
+        return out
+
+    def depth_ptr(self):
+        return lib.mcov_depth_ptr(self._ctx)
+
+    # -- accounting ---------------------------------------------------------
+    def launch_count(self):
+        return lib.mcov_launch_count(self._ctx)
+
+    def profile(self, on=True):
+        self._check(lib.mcov_profile_enable(self._ctx, 1 if on else 0))
+
+    def profile_read(self):
+        """{kernel name: (launches, total_ms)} of the CUDA-event timing since profile(True)."""
+        arr = (_capi.KernelTime * 32)()
+        n = lib.mcov_profile_read(self._ctx, arr, 32)
+        if n < 0:
+            self._check(n)
+        return {arr[i].name.decode(): (arr[i].launches, arr[i].total_ms) for i in range(n)}
+
+    # -- statistics -------------------------------------------------------
+    def region_stats(self, tid, start, end, breadth_n=1):
+        """Exact integer statistics of g regions -> structured array
+        (``_capi.REGION_STATS_DTYPE``)."""
+        tid = np.ascontiguousarray(tid, dtype=np.int32)
+        start = np.ascontiguousarray(start, dtype=np.int32)
+        end = np.ascontiguousarray(end, dtype=np.int32)
+        g = len(tid)
+        if not (len(start) == len(end) == g):
+            raise ValueError("tid/start/end lengths differ")
+        out = np.zeros(g, dtype=_capi.REGION_STATS_DTYPE)
+        self._check(lib.mcov_region_stats_run(self._ctx, g, _capi.ptr(tid), _capi.ptr(start), _capi.ptr(end),
+                                              int(breadth_n), _capi.ptr(out)))
+        return out
+
+    def window_means(self, window):
+        n_out = int(sum((int(l) + window - 1) // window for l in self.lengths))
+        out = np.empty(n_out, dtype=np.float64)
+        self._check(lib.mcov_window_means(self._ctx, int(window), _capi.ptr(out), n_out))
+        return out
+
+    # -- read-statistics scan --------------------------------------------
+    def isize_hist(self, flag, isize, group_flags=(), n_bins=1024):
+        """ByFlag-grouped |isize| histogram.  Returns (hist[groups, bins], group_counts, max_isize);
+        the table is regrown until it covers max_isize (reference IsizeHist doubles its array,
+        scan.pyx:603-608)."""
+        gf = np.ascontiguousarray(group_flags, dtype=np.uint16)
+        groups = 1 << len(gf)
+        kind = _capi.MEM_DEVICE if (_is_torch(flag) and flag.is_cuda) else _capi.MEM_HOST
+        if not _is_torch(flag):
+            flag = np.ascontiguousarray(flag, dtype=np.uint16)
+            isize = np.ascontiguousarray(isize, dtype=np.int32)
+        n = len(flag)
+        while True:
+            hist = np.zeros((groups, n_bins), dtype=np.uint32)
+            cnt = np.zeros(groups, dtype=np.uint64)
+            mx = C.c_int32(0)
+            self._check(lib.mcov_isize_hist(self._ctx, n, _capi.ptr(flag), _capi.ptr(isize), kind, len(gf),
+                                            _capi.ptr(gf) if len(gf) else None, n_bins, _capi.ptr(hist),
+                                            _capi.ptr(cnt), C.addressof(mx)))
+            if mx.value < n_bins:
+                return hist, cnt, mx.value
+            while n_bins <= mx.value:
+                n_bins *= 2

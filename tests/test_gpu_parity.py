@@ -1,0 +1,267 @@
+"""Parity of the CUDA path (through the C-ABI) against the oracle and the committed golden
+vectors.  Integer results bit-exact; floats to the cent after the reference's round(.,2)
+(1e-6 relative before rounding is checked in test_host_logic)."""
+import numpy as np
+import pytest
+
+from helpers import assert_classic_equal, load_json, load_soa, regions_of
+from oracle import cport
+
+pytestmark = pytest.mark.gpu
+
+
+def engine_for(lengths, **filt):
+    from metacov_b200 import CoverageEngine
+    return CoverageEngine(lengths, filt=filt or None)
+
+
+def full_depth(eng):
+    return [eng.copy_depth(c) for c in range(len(eng.lengths))]
+
+
+def oracle_depth(batch, lengths, mode="diff", **filt):
+    d, off, info = cport.depth(batch, lengths, filt=cport.default_filter(**filt) if filt else None, mode=mode)
+    return [d[off[c]:off[c] + lengths[c]] for c in range(len(lengths))], d, off, info
+
+
+@pytest.mark.parametrize("soa,js", [("fixture_soa.npz", "fixture_classic.json"),
+                                    ("synth_small_soa.npz", "synth_small_classic.json")])
+@pytest.mark.parametrize("path", ["fused", "push"])
+def test_golden_depth_and_classic(soa, js, path):
+    from metacov_b200.pileup import finish_classic
+    z, b = load_soa(soa)
+    gold = load_json(js)
+    lengths = z["lengths"]
+    with engine_for(lengths) as eng:
+        if path == "fused":
+            eng.depth_sorted(b)
+        else:
+            eng.begin(); eng.push(b); eng.finalize()
+        want, _, _, info = oracle_depth(b, lengths)
+        for c, d in enumerate(full_depth(eng)):
+            assert np.array_equal(d, want[c]), (path, c)
+        pi = eng.pass_info()
+        assert pi["n_pass"] == info["n_pass"] and pi["aligned_bases"] == info["aligned_bases"]
+        assert pi["sorted"] == 1
+        tid, st, en = regions_of(gold, z["references"])
+        stats = eng.region_stats(tid, st, en)
+        for row, rec, a, e in zip(gold["classic"], stats, st, en):
+            assert rec["flags"] & 1
+            assert_classic_equal(finish_classic(rec, e - a), row["result"], (path, row))
+
+
+def test_fixture_depth_known_answers():
+    import hashlib
+    z, b = load_soa("fixture_soa.npz")
+    with engine_for(z["lengths"]) as eng:
+        assert eng.compute_depth(b) == "fused"
+        d = full_depth(eng)
+        assert hashlib.sha1(d[0].astype("<i4").tobytes()).hexdigest() == "11ed20e88c63aa6c8ee4c7a7b002e66f5b1b69aa"
+        assert hashlib.sha1(d[1].astype("<i4").tobytes()).hexdigest() == "d3075eb38351dde7ace91e8975de6333040f5373"
+        assert eng.pass_info()["n_pass"] == 3350
+
+
+@pytest.mark.parametrize("wl,scale", [("c2", 0.02), ("c3", 0.002), ("c5", 0.004)])
+@pytest.mark.parametrize("path", ["fused", "push"])
+def test_synthetic_configs_bit_exact(wl, scale, path):
+    """Scaled-down BASELINE configs: depth bit-exact against the C oracle, region stats equal."""
+    from metacov_b200 import synth
+    w = synth.WORKLOADS[wl](scale)
+    b, _ = synth.generate_host(w)
+    lengths = w.contig_len
+    with engine_for(lengths) as eng:
+        if path == "fused":
+            eng.depth_sorted(b)
+        else:
+            eng.begin()
+            # several pushes: batches split at arbitrary read boundaries
+            n = len(b.tid)
+            cuts = [0, n // 3, n // 3 + 1, n]
+            o = b.cig_off.astype(np.int64)
+            for lo, hi in zip(cuts[:-1], cuts[1:]):
+                from metacov_b200 import ReadBatch
+                eng.push(ReadBatch(b.tid[lo:hi], b.pos[lo:hi], b.flag[lo:hi], b.mapq[lo:hi],
+                                   (o[lo:hi + 1] - o[lo]).astype(np.uint32), b.cig[o[lo]:o[hi]]))
+            eng.finalize()
+        want, dflat, off, info = oracle_depth(b, lengths)
+        for c, d in enumerate(full_depth(eng)):
+            assert np.array_equal(d, want[c]), (wl, path, c)
+        pi = eng.pass_info()
+        assert pi["n_pass"] == info["n_pass"] and pi["aligned_bases"] == info["aligned_bases"]
+        assert pi["max_depth_seen"] == int(dflat.max())
+        # whole-contig regions plus random sub-ranges (overlapping)
+        rng = np.random.default_rng(3)
+        nc = len(lengths)
+        tid = np.r_[np.arange(nc), rng.integers(0, nc, 64)].astype(np.int32)
+        a = np.r_[np.zeros(nc, np.int64), [rng.integers(0, lengths[t]) for t in tid[nc:]]]
+        e = np.r_[lengths.astype(np.int64), [rng.integers(a[nc + k] + 1, lengths[t] + 1) for k, t in enumerate(tid[nc:])]]
+        got = eng.region_stats(tid, a, e, breadth_n=10)
+        ref = cport.region_stats(dflat, off, lengths, tid, a, e, breadth_n=10)
+        for k in ("sum", "sumsq", "iq_sum", "n_ge1", "n_geN", "min", "max", "med_lo", "med_hi"):
+            assert np.array_equal(got[k], ref[k]), (wl, path, k)
+
+
+def test_exact_cap_metric_fused():
+    """cap_metric of the fused path = max_p depth[p-1] + starts[p] (htslib no-op condition)."""
+    from metacov_b200 import synth
+    w = synth.c3(0.001)
+    b, _ = synth.generate_host(w)
+    with engine_for(w.contig_len) as eng:
+        eng.depth_sorted(b)
+        pi = eng.pass_info()
+        want, dflat, off, _ = oracle_depth(b, w.contig_len)
+        ok = cport.default_filter()
+        from oracle.pysam_boundary import PileupFilter
+        passing = PileupFilter().passes(b.flag, b.mapq)
+        from oracle import bamio
+        rl = bamio.cigar_reflen(b.cig_off, b.cig)
+        passing &= rl > 0
+        best = 0
+        for c in range(w.n_contigs):
+            sel = passing & (b.tid == c)
+            starts = np.bincount(b.pos[sel], minlength=w.contig_len[c] + 1)[:w.contig_len[c]]
+            prev = np.r_[0, want[c][:-1]]
+            best = max(best, int((prev + starts).max()))
+        assert pi["cap_metric"] == best
+        eng.begin(); eng.push(b); eng.finalize()
+        assert eng.pass_info()["cap_metric"] >= best      # push path: upper bound
+
+
+def test_unsorted_input_falls_to_push_path_on_gpu():
+    from metacov_b200 import McovError, ReadBatch, _capi
+    z, b = load_soa("synth_small_soa.npz")
+    perm = np.random.default_rng(5).permutation(len(b.tid))
+    o = b.cig_off.astype(np.int64)
+    ncig = np.diff(o)[perm]
+    cig = np.concatenate([b.cig[o[i]:o[i + 1]] for i in perm]) if len(b.cig) else b.cig
+    sb = ReadBatch(b.tid[perm], b.pos[perm], b.flag[perm], b.mapq[perm],
+                   np.r_[0, np.cumsum(ncig)].astype(np.uint32), cig.astype(np.uint32))
+    with engine_for(z["lengths"]) as eng:
+        with pytest.raises(McovError) as ei:
+            eng.depth_sorted(sb)
+        assert ei.value.code == _capi.MCOV_ERR_UNSORTED
+        assert eng.compute_depth(sb) == "push"
+        assert eng.pass_info()["sorted"] == 0
+        want, _, _, _ = oracle_depth(b, z["lengths"])
+        for c, d in enumerate(full_depth(eng)):
+            assert np.array_equal(d, want[c])
+
+
+def test_filters_and_edge_cases():
+    from metacov_b200 import McovError, ReadBatch
+    z, b = load_soa("synth_small_soa.npz")
+    lengths = z["lengths"]
+    for filt in (dict(ignore_orphans=0), dict(flag_filter=0x4), dict(min_mapq=30), dict(flag_require=0x10),
+                 dict(flag_filter=0, ignore_orphans=0)):
+        with engine_for(lengths, **filt) as eng:
+            eng.depth_sorted(b)
+            want, _, _, _ = oracle_depth(b, lengths, **filt)
+            for c, d in enumerate(full_depth(eng)):
+                assert np.array_equal(d, want[c]), filt
+    with engine_for(lengths) as eng:
+        # empty input: all-zero depth, stats of zeros
+        empty = ReadBatch(np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.uint16), np.zeros(0, np.uint8),
+                          np.zeros(1, np.uint32), np.zeros(0, np.uint32))
+        eng.depth_sorted(empty)
+        assert all(int(d.sum()) == 0 for d in full_depth(eng))
+        st = eng.region_stats([0, 2], [0, 10], [lengths[0], 11])
+        assert st["sum"].tolist() == [0, 0] and st["max"].tolist() == [0, 0] and (st["flags"] & 1).all()
+        # zero-length region -> zeros, no crash; bad regions -> MCOV_ERR_ARG
+        assert eng.region_stats([0], [5], [5])["flags"][0] == 0
+        with pytest.raises(McovError):
+            eng.region_stats([7], [0], [5])
+        with pytest.raises(McovError):
+            eng.region_stats([0], [9], [5])
+    # calls out of order
+    with engine_for(lengths) as eng:
+        with pytest.raises(McovError):
+            eng.finalize()
+        with pytest.raises(McovError):
+            eng.region_stats([0], [0], [5])
+        with pytest.raises(McovError):
+            eng.push(b)
+
+
+def test_region_beyond_contig_end_counts_zeros():
+    """pileup.py:10-11: the vector is end-start long whatever the contig length."""
+    z, b = load_soa("fixture_soa.npz")
+    with engine_for(z["lengths"]) as eng:
+        eng.depth_sorted(b)
+        _, dflat, off, _ = oracle_depth(b, z["lengths"])
+        tid, a, e = [0, 1, 1], [400, 0, 575], [500, 2000, 600]
+        got = eng.region_stats(tid, a, e)
+        ref = cport.region_stats(dflat, off, z["lengths"], tid, a, e)
+        for k in ("sum", "sumsq", "iq_sum", "n_ge1", "min", "max", "med_lo", "med_hi"):
+            assert np.array_equal(got[k], ref[k]), k
+
+
+def test_large_regions_multi_chunk_and_window_means():
+    """A region longer than one chunk merges partial histograms through the global pool."""
+    from metacov_b200 import synth
+    w = synth.Workload("big", [300_000, 70_000], [60_000, 9_000], seed=11)
+    b, _ = synth.generate_host(w)
+    with engine_for(w.contig_len) as eng:
+        eng.depth_sorted(b)
+        want, dflat, off, _ = oracle_depth(b, w.contig_len)
+        tid, a, e = [0, 0, 1, 0], [0, 5, 0, 100_000], [300_000, 299_999, 70_000, 100_001]
+        got = eng.region_stats(tid, a, e)
+        ref = cport.region_stats(dflat, off, w.contig_len, tid, a, e)
+        for k in ("sum", "sumsq", "iq_sum", "n_ge1", "min", "max", "med_lo", "med_hi"):
+            assert np.array_equal(got[k], ref[k]), k
+        wm = eng.window_means(1000)
+        exp = np.concatenate([[d[i:i + 1000].mean() for i in range(0, len(d), 1000)] for d in want])
+        assert np.allclose(wm, exp, rtol=0, atol=1e-12)
+
+
+def test_histogram_overflow_uses_gpu_radix_path():
+    """Depth beyond the counting histogram (needs max_depth raised): exact order statistics."""
+    from metacov_b200 import ReadBatch
+    n = 20000
+    rng = np.random.default_rng(2)
+    pos = np.sort(np.r_[np.full(12000, 100), rng.integers(0, 900, n - 12000)]).astype(np.int32)
+    b = ReadBatch(np.zeros(n, np.int32), pos, np.zeros(n, np.uint16), np.full(n, 30, np.uint8),
+                  np.arange(n + 1, dtype=np.uint32), np.full(n, 100 << 4, np.uint32))
+    with engine_for([1000], max_depth=0) as eng:
+        eng.depth_sorted(b)
+        pi = eng.pass_info()
+        assert pi["max_depth_seen"] > 8191 and pi["cap_metric"] > 8000
+        _, dflat, off, _ = oracle_depth(b, np.array([1000], np.int32))
+        tid, a, e = [0, 0, 0], [0, 90, 0], [1000, 250, 1500]
+        got = eng.region_stats(tid, a, e)
+        ref = cport.region_stats(dflat, off, np.array([1000], np.int32), tid, a, e)
+        assert (got["flags"] & 2).all()
+        for k in ("sum", "sumsq", "iq_sum", "min", "max", "med_lo", "med_hi"):
+            assert np.array_equal(got[k], ref[k]), k
+
+
+def test_isize_hist_byflag():
+    z, _ = load_soa("fixture_soa.npz")
+    with engine_for(z["lengths"]) as eng:
+        for gf in ((), (0x4, 0x40), (0x10, 0x1, 0x80)):
+            hist, cnt, mx = eng.isize_hist(z["flag"], z["isize"], gf, n_bins=64)   # forces a regrow
+            rh, rc, rmx = cport.isize_hist(z["flag"], z["isize"], gf, hist.shape[1])
+            assert mx == rmx == 248 and np.array_equal(hist, rh) and np.array_equal(cnt, rc)
+
+
+def test_device_resident_inputs_match_host_inputs():
+    import torch
+    from metacov_b200 import synth
+    w = synth.c2(0.01)
+    hb, hisz = synth.generate_host(w)
+    db, disz = synth.generate_device(w, 0)
+    for name, h, d in zip(hb._fields, hb, db):
+        hv = np.asarray(h)
+        dv = d.cpu().numpy().view(hv.dtype)
+        assert np.array_equal(hv, dv), name
+    with engine_for(w.contig_len) as eng:
+        eng.depth_sorted(db)
+        want, _, _, _ = oracle_depth(hb, w.contig_len)
+        for c, d in enumerate(full_depth(eng)):
+            assert np.array_equal(d, want[c])
+        # torch-owned depth buffer
+        buf = torch.zeros(eng.n_slots, dtype=torch.int32, device="cuda")
+        eng.bind_depth(buf)
+        eng.depth_sorted(db)
+        torch.cuda.synchronize()
+        o = eng.contig_offset(3)
+        assert np.array_equal(buf[o:o + int(w.contig_len[3])].cpu().numpy(), want[3])

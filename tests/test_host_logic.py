@@ -1,0 +1,102 @@
+"""Host-side logic of the product package, CPU only: float finishing of `classic`, the BAM
+reader, the synthetic generator, region parsing."""
+import io
+import os
+
+import numpy as np
+import pytest
+
+from helpers import REF_DATA, load_soa
+from oracle import bamio, classic as oc
+
+
+def int_stats(d):
+    """Exact integer statistics of a depth vector (what mcov_region_stats carries)."""
+    d = np.asarray(d, dtype=np.int64)
+    n = len(d)
+    s = np.sort(d)
+    q = n // 4
+    return {"sum": int(d.sum()), "sumsq": int((d * d).sum()), "iq_sum": int(s[q:n - q].sum()),
+            "min": int(d.min()), "max": int(d.max()), "med_lo": int(s[(n - 1) // 2]), "med_hi": int(s[n // 2])}
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_finish_classic_matches_numpy_reductions(seed):
+    """finish_classic (integer moments) vs the reference's numpy reductions (pileup.py:18-26):
+    ints identical, floats within 1e-6 relative before rounding, rounded values to the cent."""
+    from metacov_b200.pileup import finish_classic
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(1, 5000))
+    d = rng.integers(0, [3, 50, 600, 8000][seed % 4], n)
+    if seed % 3 == 0:
+        d = np.sort(d)
+    got = finish_classic(int_stats(d), n)
+    want = oc.stats_from_columns(d.astype(np.float64))
+    for k in ("min", "max", "med", "sum"):
+        assert got[k] == want[k] and isinstance(got[k], int)
+    for k in ("std", "avg", "q23"):
+        assert isinstance(got[k], np.floating)
+        assert abs(got[k] - want[k]) <= 0.01 + 1e-9
+    assert got["avg"] == want["avg"] and got["q23"] == want["q23"]
+    raw_std = np.std(d.astype(np.float64))
+    exact = np.sqrt((n * int((d.astype(object) ** 2).sum()) - int(d.sum()) ** 2) / (n * n))
+    assert abs(raw_std - exact) <= 1e-6 * max(raw_std, 1e-300)
+
+
+def test_native_bam_reader_roundtrip(tmp_path):
+    """csrc/bamio.cpp against the oracle's pure-Python reader on a BAM the oracle writer made."""
+    from metacov_b200 import AlignmentFile
+    z, b = load_soa("synth_small_soa.npz")
+    refs = [str(x) for x in z["references"]]
+    path = str(tmp_path / "t.bam")
+    isize = (np.arange(len(b.tid)) % 700 - 350).astype(np.int32)
+    bamio.write_bam(path, refs, z["lengths"].tolist(), b.tid, b.pos, b.flag, b.mapq, b.cig_off, b.cig, isize=isize)
+    hdr, recs = bamio.read_bam(path)
+    with AlignmentFile(path) as af:
+        assert af.references == tuple(refs) == hdr.references
+        assert af.lengths == tuple(z["lengths"].tolist())
+        s = af.soa()
+        for k, want in (("tid", b.tid), ("pos", b.pos), ("flag", b.flag), ("mapq", b.mapq), ("cig", b.cig),
+                        ("isize", isize), ("l_seq", recs.l_seq)):
+            assert np.array_equal(s[k], want), k
+        assert np.array_equal(s["cig_off"], b.cig_off)
+        un = (b.flag & 4) != 0
+        assert af.mapped == int(np.sum(~un & (b.tid >= 0))) and af.unmapped == int(np.sum(un))
+        assert af.get_tid("ctgC") == 2 and af.get_tid("nope") == -1
+    with pytest.raises(OSError):
+        AlignmentFile(str(tmp_path / "missing.bam"))
+    bad = tmp_path / "bad.bam"
+    bad.write_bytes(b"not a bam file at all, definitely")
+    with pytest.raises(OSError):
+        AlignmentFile(str(bad))
+
+
+@pytest.mark.skipif(not os.path.exists(REF_DATA), reason="reference fixtures not present on this box")
+def test_native_bam_reader_on_reference_fixture():
+    from metacov_b200 import AlignmentFile
+    z, b = load_soa("fixture_soa.npz")
+    with AlignmentFile(os.path.join(REF_DATA, "bbmap.sorted.bam")) as af:
+        assert af.references == ("ref1", "ref2") and af.lengths == (425, 575)
+        assert (af.mapped, af.unmapped) == (3979, 133)
+        s = af.soa()
+        assert len(af) == 4112
+        for k in ("tid", "pos", "flag", "mapq", "cig", "isize", "l_seq"):
+            assert np.array_equal(s[k], z[k]), k
+        assert np.array_equal(s["cig_off"], b.cig_off)
+
+
+def test_synth_generator_shapes_and_sortedness():
+    from metacov_b200 import synth
+    for w in (synth.c2(0.005), synth.c3(0.0005), synth.c5(0.001, span_min=2000, span_max=6000)):
+        b, isz, rl = synth.generate_host(w, want_reflen=True)
+        key = b.tid.astype(np.int64) * (1 << 32) + b.pos
+        assert np.all(np.diff(key) >= 0), w.name
+        assert np.array_equal(rl, bamio.cigar_reflen(b.cig_off, b.cig))
+        assert np.all(b.pos + rl <= w.contig_len[b.tid])
+        assert np.all(np.bincount(b.tid, minlength=w.n_contigs) == np.diff(w.read_start))
+        # any window of reads can be re-derived on its own (counter-based generator)
+        lo, n = w.n_reads // 3, min(1000, w.n_reads - w.n_reads // 3)
+        b2, isz2 = synth.generate_host(w, i0=lo, n=n)
+        assert np.array_equal(b2.pos, b.pos[lo:lo + n]) and np.array_equal(b2.flag, b.flag[lo:lo + n])
+        o = b.cig_off.astype(np.int64)
+        assert np.array_equal(b2.cig, b.cig[o[lo]:o[lo + n]])
