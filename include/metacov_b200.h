@@ -130,9 +130,19 @@ int  mcov_depth_sorted(mcov_ctx* ctx, int64_t n,
                        const uint32_t* cig_off, const uint32_t* cig,
                        int mem_kind);
 
+/* Same, but returns without waiting for the GPU: the sortedness verdict
+ * (MCOV_ERR_UNSORTED / MCOV_ERR_RANGE) is delivered by the next call that
+ * synchronises -- mcov_region_stats_run, mcov_copy_depth, mcov_pass_info_get. */
+int  mcov_depth_sorted_async(mcov_ctx* ctx, int64_t n,
+                             const int32_t* tid, const int32_t* pos,
+                             const uint16_t* flag, const uint8_t* mapq,
+                             const uint32_t* cig_off, const uint32_t* cig,
+                             int mem_kind);
+
 /* Replaces the seven reductions of `classic` (reference
  * metacov/pileup.py:18-26) for g regions at once (the loop at cli.py:85-95).
- * tid/start/end are host arrays; 0 <= start <= end <= len[tid].
+ * tid/start/end are host arrays; 0 <= start <= end.  Positions >= len[tid]
+ * count as depth 0 (the reference's vector is end-start long, pileup.py:10-11).
  * breadth_n: threshold of n_geN.  host_out: g structs.  Synchronises. */
 int  mcov_region_stats_run(mcov_ctx* ctx, int64_t g,
                            const int32_t* tid, const int32_t* start, const int32_t* end,

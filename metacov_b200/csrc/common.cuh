@@ -7,6 +7,8 @@
 namespace mcov {
 
 constexpr int kNumSMsB200 = 148;
+constexpr int kStatValidBit = 1;     // mcov_region_stats.flags bit0: record valid
+constexpr int kStatOverflowBit = 2;  // bit1: depth left the counting histogram, radix path used
 
 // BAM CIGAR ops that consume reference: M(0) D(2) N(3) =(7) X(8)
 // (htslib bam_cigar_type bit 1).
@@ -59,13 +61,16 @@ __device__ __forceinline__ void st_stream_int4(int4* p, const int4& v) {
                :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// Look-back status words carry state and value in ONE 64-bit word, so a relaxed (L1-bypassing)
+// load/store pair is enough: nothing else has to be ordered with it.  (acquire/release at gpu scope
+// would make ptxas emit CCTL.IVALL / MEMBAR around every poll.)
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
   unsigned long long v;
-  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
 
 template <typename T>

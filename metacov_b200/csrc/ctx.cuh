@@ -49,6 +49,15 @@ enum KernelId {
 
 struct ProfRec { int id; cudaEvent_t a, b; };
 
+// cached chunk table of the last region set (mcov_region_stats_run)
+struct RegionPlan {
+  bool valid = false;
+  int64_t g = 0, n_tasks = 0;
+  int32_t n_multi = 0;
+  int64_t n_contigs_epoch = -1;
+  std::vector<int32_t> tid, start, end, rlen, rpad;
+};
+
 struct ReadStage {            // one staging set for host-resident batches
   DevBuf tid, pos, flag, mapq, cig_off, cig;
   cudaEvent_t consumed = nullptr;   // recorded after the kernel that read this set
@@ -83,6 +92,9 @@ struct mcov_ctx {
   mcov::ReadStage stage[2];
   int stage_next = 0;
   int64_t n_reads_pushed = 0;
+  bool verdict_pending = false;   // an asynchronous fused pass has not been checked for sortedness yet
+  int64_t contig_epoch = 0;
+  mcov::RegionPlan plan;
 
   // fused (sorted) path scratch
   mcov::DevBuf d_end_slot, d_start_slot, d_far_list, d_tile_cnt, d_tile_off, d_far_sorted;

@@ -17,7 +17,7 @@
 
 using namespace mcov;
 
-int mcov_order_stats_by_sort(mcov_ctx* ctx, const int32_t* d_region, int64_t n, int64_t pad,
+int mcov_order_stats_by_sort(mcov_ctx* ctx, const int32_t* d_region, int64_t n, int64_t pad, int breadth_n,
                              mcov_region_stats* d_stat, mcov::DevBuf& keys_out, mcov::DevBuf& temp);
 
 namespace {
@@ -110,15 +110,16 @@ int finish_stage(mcov_ctx* ctx, ReadStage* s) {
 int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a) {
   const int64_t n = a.n;
   const int64_t n_tiles = (ctx->n_slots + kTile - 1) / kTile;
-  const int64_t cnt_pad = (n_tiles + 3) & ~(int64_t)3;                 // scanned in place as int32
-  const int64_t cnt_tiles = (cnt_pad + kScanTile - 1) / kScanTile;
+  const int64_t cnt_pad = (n_tiles + 1 + 3) & ~(int64_t)3;             // per-tile arrays, scanned in place as int32
+  const int64_t scan_len = 2 * cnt_pad;                                // [tile_agg | tile_cnt]
+  const int64_t scan_tiles = (scan_len + kScanTile - 1) / kScanTile;
   const uint32_t far_cap = (uint32_t)std::min<int64_t>(std::max<int64_t>(n, 1), kFarCapDefault);
-  // one zeroed scratch block: [tile_cnt | tile_cursor | status_main | status_cnt]
-  const size_t o_cnt = 0, o_cur = o_cnt + (size_t)cnt_pad * 4, o_stm = (o_cur + (size_t)n_tiles * 4 + 7) & ~(size_t)7,
-               o_stc = o_stm + (size_t)n_tiles * 8, z_bytes = o_stc + (size_t)cnt_tiles * 8;
+  // one zeroed scratch block: [tile_agg | tile_cnt | tile_cursor | scan status]
+  const size_t o_agg = 0, o_cnt = o_agg + (size_t)cnt_pad * 4, o_cur = o_cnt + (size_t)cnt_pad * 4,
+               o_st = (o_cur + (size_t)n_tiles * 4 + 7) & ~(size_t)7, z_bytes = o_st + (size_t)scan_tiles * 8;
   CU(ctx->d_status.ensure(z_bytes));
-  CU(ctx->d_start_slot.ensure((size_t)std::max<int64_t>(n, 1) * sizeof(uint2)));     // rec
-  CU(ctx->d_tile_off.ensure((size_t)(n_tiles + 1) * 8));                              // tile_first
+  CU(ctx->d_start_slot.ensure((size_t)(std::max<int64_t>(n, 1) + 4) * sizeof(uint2)));   // rec
+  CU(ctx->d_tile_off.ensure((size_t)(n_tiles + 1) * 8));                                 // tile_first
   CU(ctx->d_far_list.ensure((size_t)far_cap * 8));
   CU(ctx->d_far_sorted.ensure((size_t)far_cap * 4));
   cudaStream_t s = ctx->stream;
@@ -131,25 +132,44 @@ int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a) {
   f.n_tiles = n_tiles;
   f.far_end = ctx->d_far_list.as<int64_t>();
   f.far_cap = far_cap;
+  f.tile_agg = reinterpret_cast<int32_t*>(z + o_agg);
   f.tile_cnt = reinterpret_cast<uint32_t*>(z + o_cnt);
   f.tile_cursor = reinterpret_cast<uint32_t*>(z + o_cur);
   f.far_sorted = ctx->d_far_sorted.as<uint32_t>();
   f.tile_first = ctx->d_tile_off.as<int64_t>();
-  f.status = reinterpret_cast<unsigned long long*>(z + o_stm);
   f.depth = ctx->depth;
+  auto al = [](const void* p, uintptr_t m) { return (reinterpret_cast<uintptr_t>(p) & (m - 1)) == 0; };
+  f.vec_ok = (n > 0 && al(a.tid, 16) && al(a.pos, 16) && al(a.cig_off, 16) && al(a.flag, 8) && al(a.mapq, 4)) ? 1 : 0;
   if (n > 0) {
-    MCOV_LAUNCH(ctx, kKFusedPrep, (k_fused_prep<<<grid_for(n, kExpandThreads, 8), kExpandThreads, 0, s>>>(f)));
+    const int64_t groups = (n + kPrepPer - 1) / kPrepPer;
+    MCOV_LAUNCH(ctx, kKFusedPrep, (k_fused_prep<<<grid_for(groups, kPrepThreads, 8), kPrepThreads, 0, s>>>(f)));
     CU(cudaGetLastError());
+  } else {
+    CU(cudaMemsetAsync(f.tile_first, 0, (size_t)(n_tiles + 1) * 8, s));
   }
-  MCOV_LAUNCH(ctx, kKTileFirst, (k_tile_first<<<(unsigned)((n_tiles + 1 + 255) / 256), 256, 0, s>>>(f)));
-  CU(cudaGetLastError());
-  MCOV_LAUNCH(ctx, kKScanCounts, (k_scan_inplace<false><<<(unsigned)cnt_tiles, kScanThreads, 0, s>>>(
-      reinterpret_cast<int32_t*>(f.tile_cnt), cnt_pad, reinterpret_cast<unsigned long long*>(z + o_stc), pc_of(ctx))));
+  MCOV_LAUNCH(ctx, kKScanCounts, (k_scan_inplace<false><<<(unsigned)scan_tiles, kScanThreads, 0, s>>>(
+      f.tile_agg, scan_len, reinterpret_cast<unsigned long long*>(z + o_st), pc_of(ctx))));
   CU(cudaGetLastError());
   MCOV_LAUNCH(ctx, kKFarScatter, (k_far_scatter<<<kNumSMsB200 * 2, 256, 0, s>>>(f)));
   CU(cudaGetLastError());
   MCOV_LAUNCH(ctx, kKFusedTile, (k_fused_tile<<<(unsigned)n_tiles, kFusedThreads, 0, s>>>(f)));
   CU(cudaGetLastError());
+  return MCOV_OK;
+}
+
+// Deliver the deferred verdict of an asynchronous fused pass (stream already synchronised,
+// `h` = the pass counters just read back).
+int fused_verdict(mcov_ctx* ctx, const PassCounters& h) {
+  if (!ctx->verdict_pending) return MCOV_OK;
+  ctx->verdict_pending = false;
+  if (h.unsorted) {
+    ctx->state = kIdle;
+    return fail(ctx, MCOV_ERR_UNSORTED, "mcov_depth_sorted: reads are not sorted by (tid,pos); use mcov_begin/push/finalize");
+  }
+  if ((int64_t)h.n_far > std::min<int64_t>(std::max<int64_t>(ctx->n_reads_pushed, 1), kFarCapDefault)) {
+    ctx->state = kIdle;
+    return fail(ctx, MCOV_ERR_RANGE, "mcov_depth_sorted: too many long-span reads for the bucket list; use mcov_begin/push/finalize");
+  }
   return MCOV_OK;
 }
 
@@ -240,6 +260,8 @@ int mcov_set_contigs(mcov_ctx* ctx, int32_t n_contigs, const int32_t* len) {
   ctx->state = kIdle;
   ctx->depth_bound = false;
   ctx->depth = nullptr;
+  ctx->contig_epoch += 1;
+  ctx->plan.valid = false;
   return MCOV_OK;
 }
 
@@ -274,6 +296,7 @@ int mcov_begin(mcov_ctx* ctx) {
   MCOV_LAUNCH(ctx, kKClear, CU(cudaMemsetAsync(ctx->depth, 0, (size_t)ctx->n_slots * 4, ctx->stream)));
   CU(cudaMemsetAsync(ctx->d_pc.p, 0, sizeof(PassCounters), ctx->stream));
   ctx->n_reads_pushed = 0;
+  ctx->verdict_pending = false;
   ctx->state = kAccumulating;
   return MCOV_OK;
 }
@@ -311,8 +334,8 @@ int mcov_finalize(mcov_ctx* ctx) {
   return MCOV_OK;
 }
 
-int mcov_depth_sorted(mcov_ctx* ctx, int64_t n, const int32_t* tid, const int32_t* pos, const uint16_t* flag,
-                      const uint8_t* mapq, const uint32_t* cig_off, const uint32_t* cig, int mem_kind) {
+static int depth_sorted_impl(mcov_ctx* ctx, int64_t n, const int32_t* tid, const int32_t* pos, const uint16_t* flag,
+                             const uint8_t* mapq, const uint32_t* cig_off, const uint32_t* cig, int mem_kind, bool wait) {
   if (!ctx) return MCOV_ERR_ARG;
   if (n < 0) return fail(ctx, MCOV_ERR_ARG, "mcov_depth_sorted: n < 0");
   if (n > 0 && (!tid || !pos || !flag || !mapq || !cig_off)) return fail(ctx, MCOV_ERR_ARG, "mcov_depth_sorted: null array");
@@ -334,20 +357,24 @@ int mcov_depth_sorted(mcov_ctx* ctx, int64_t n, const int32_t* tid, const int32_
   ctx->n_reads_pushed = n;
   rc = finish_stage(ctx, st);
   if (rc) return rc;
+  ctx->state = kDepthReady;
+  ctx->verdict_pending = true;
+  if (!wait) return MCOV_OK;
   // sortedness is a property of the data: one small read-back decides
   PassCounters h;
   CU(cudaMemcpyAsync(&h, ctx->d_pc.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  if (h.unsorted) {
-    ctx->state = kIdle;
-    return fail(ctx, MCOV_ERR_UNSORTED, "mcov_depth_sorted: reads are not sorted by (tid,pos); use mcov_begin/push/finalize");
-  }
-  if ((int64_t)h.n_far > std::min<int64_t>(std::max<int64_t>(n, 1), kFarCapDefault)) {
-    ctx->state = kIdle;
-    return fail(ctx, MCOV_ERR_RANGE, "mcov_depth_sorted: too many long-span reads for the bucket list; use mcov_begin/push/finalize");
-  }
-  ctx->state = kDepthReady;
-  return MCOV_OK;
+  return fused_verdict(ctx, h);
+}
+
+int mcov_depth_sorted(mcov_ctx* ctx, int64_t n, const int32_t* tid, const int32_t* pos, const uint16_t* flag,
+                      const uint8_t* mapq, const uint32_t* cig_off, const uint32_t* cig, int mem_kind) {
+  return depth_sorted_impl(ctx, n, tid, pos, flag, mapq, cig_off, cig, mem_kind, true);
+}
+
+int mcov_depth_sorted_async(mcov_ctx* ctx, int64_t n, const int32_t* tid, const int32_t* pos, const uint16_t* flag,
+                            const uint8_t* mapq, const uint32_t* cig_off, const uint32_t* cig, int mem_kind) {
+  return depth_sorted_impl(ctx, n, tid, pos, flag, mapq, cig_off, cig, mem_kind, false);
 }
 
 int mcov_pass_info_get(mcov_ctx* ctx, mcov_pass_info* out) {
@@ -357,6 +384,7 @@ int mcov_pass_info_get(mcov_ctx* ctx, mcov_pass_info* out) {
   PassCounters h;
   CU(cudaMemcpyAsync(&h, ctx->d_pc.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  { int vr = fused_verdict(ctx, h); if (vr) return vr; }
   out->n_reads = ctx->n_reads_pushed;
   out->n_pass = (int64_t)h.n_pass;
   out->aligned_bases = (int64_t)h.aligned_bases;
@@ -369,7 +397,7 @@ int mcov_pass_info_get(mcov_ctx* ctx, mcov_pass_info* out) {
 
 static const char* kKernelNames[kKernelCount] = {
     "k_expand", "k_scan_inplace", "k_fused_prep", "k_tile_first", "k_scan_counts", "k_far_scatter", "k_fused_tile",
-    "k_init_region_stats", "k_region_stats", "k_window_sums", "k_isize_hist", "k_group_count", "k_sorted_order_stats",
+    "k_init_region_stats", "k_region_stats", "k_window_sums", "k_isize_hist", "k_group_count", "k_sorted_stats",
     "memset_depth"};
 
 int64_t mcov_launch_count(const mcov_ctx* ctx) { return ctx ? ctx->n_launches : 0; }
@@ -411,7 +439,10 @@ int mcov_copy_depth(mcov_ctx* ctx, int32_t tid, int32_t start, int32_t end, int3
   CU(cudaSetDevice(ctx->device));
   CU(cudaMemcpyAsync(host_out, ctx->depth + ctx->off[tid] + start, (size_t)(end - start) * 4, cudaMemcpyDeviceToHost,
                      ctx->stream));
+  PassCounters h;
+  if (ctx->verdict_pending) CU(cudaMemcpyAsync(&h, ctx->d_pc.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  if (ctx->verdict_pending) return fused_verdict(ctx, h);
   return MCOV_OK;
 }
 
@@ -420,82 +451,101 @@ int mcov_region_stats_run(mcov_ctx* ctx, int64_t g, const int32_t* tid, const in
   if (!ctx) return MCOV_ERR_ARG;
   if (ctx->state != kDepthReady) return fail(ctx, MCOV_ERR_STATE, "mcov_region_stats_run: depth not ready (finalize first)");
   if (g < 0 || (g > 0 && (!tid || !start || !end || !host_out))) return fail(ctx, MCOV_ERR_ARG, "mcov_region_stats_run: bad arguments");
-  if (g == 0) return MCOV_OK;
   if (g > INT32_MAX) return fail(ctx, MCOV_ERR_RANGE, "mcov_region_stats_run: more than 2^31-1 regions");
   CU(cudaSetDevice(ctx->device));
-  // A region may reach past its contig: the reference's vector is end-start long whatever the
-  // contig length (pileup.py:10-11) and stays 0 there, so those positions count as depth 0.
-  int64_t total = 0;
-  for (int64_t i = 0; i < g; ++i) {
-    if (tid[i] < 0 || tid[i] >= ctx->n_contigs || start[i] < 0 || end[i] < start[i])
-      return fail(ctx, MCOV_ERR_ARG, "mcov_region_stats_run: need 0 <= start <= end and a valid tid");
-    int64_t len = ctx->len[tid[i]];
-    total += std::max<int64_t>(0, std::min<int64_t>(end[i], len) - std::min<int64_t>(start[i], len));
-  }
-  // chunk length: enough chunks to fill the machine several times over, few enough that
-  // most regions stay single-chunk
-  int64_t chunk = (total / ((int64_t)kNumSMsB200 * 16) + 4095) / 4096 * 4096;
-  chunk = std::max<int64_t>(8192, std::min<int64_t>(65536, chunk));
-  std::vector<StatTask> tasks;
-  tasks.reserve((size_t)(g + total / chunk + 1));
-  std::vector<int32_t> rlen((size_t)g), rpad((size_t)g), rchunks((size_t)g), rhist((size_t)g);
-  int32_t n_multi = 0;
-  for (int64_t i = 0; i < g; ++i) {
-    int64_t len = ctx->len[tid[i]];
-    int64_t cs = std::min<int64_t>(start[i], len), ce = std::min<int64_t>(end[i], len);
-    int32_t n = (int32_t)(ce - cs);
-    int32_t pad = (int32_t)((int64_t)end[i] - start[i] - n);
-    int32_t nch = (int32_t)((n + chunk - 1) / chunk);
-    if (nch == 0 && pad > 0) nch = 1;             // nothing but zeros: one empty chunk finishes it
-    rlen[i] = n; rpad[i] = pad; rchunks[i] = nch;
-    rhist[i] = nch > 1 ? n_multi++ : -1;
-    int64_t slot = ctx->off[tid[i]] + cs;
-    for (int32_t k = 0; k < nch; ++k) {
-      StatTask t;
-      t.slot = slot + (int64_t)k * chunk;
-      t.n = (int32_t)std::max<int64_t>(0, std::min<int64_t>(chunk, n - (int64_t)k * chunk));
-      t.region = (int32_t)i;
-      tasks.push_back(t);
-    }
-  }
   cudaStream_t s = ctx->stream;
-  CU(ctx->d_out.ensure((size_t)g * sizeof(mcov_region_stats)));
-  MCOV_LAUNCH(ctx, kKInitStats, (k_init_region_stats<<<(unsigned)((g + 255) / 256), 256, 0, s>>>(ctx->d_out.as<mcov_region_stats>(), g)));
-  CU(cudaGetLastError());
-  if (!tasks.empty()) {
-    CU(ctx->d_tasks.ensure(tasks.size() * sizeof(StatTask)));
+  RegionPlan& rp = ctx->plan;
+  // The chunk table of a region set is cached on the device: a caller that asks for the same
+  // regions again (cli.py loops, benchmarks) pays for it once.
+  const bool same = rp.valid && rp.g == g && rp.n_contigs_epoch == ctx->contig_epoch && g > 0 &&
+                    std::memcmp(rp.tid.data(), tid, (size_t)g * 4) == 0 &&
+                    std::memcmp(rp.start.data(), start, (size_t)g * 4) == 0 &&
+                    std::memcmp(rp.end.data(), end, (size_t)g * 4) == 0;
+  if (!same && g > 0) {
+    rp.valid = false;
+    // A region may reach past its contig: the reference's vector is end-start long whatever the
+    // contig length (pileup.py:10-11) and stays 0 there, so those positions count as depth 0.
+    int64_t total = 0;
+    for (int64_t i = 0; i < g; ++i) {
+      if (tid[i] < 0 || tid[i] >= ctx->n_contigs || start[i] < 0 || end[i] < start[i])
+        return fail(ctx, MCOV_ERR_ARG, "mcov_region_stats_run: need 0 <= start <= end and a valid tid");
+      int64_t len = ctx->len[tid[i]];
+      total += std::max<int64_t>(0, std::min<int64_t>(end[i], len) - std::min<int64_t>(start[i], len));
+    }
+    // chunk length: enough chunks to fill the machine several times over; a region is split evenly
+    int64_t chunk_max = (total / ((int64_t)kNumSMsB200 * 24) + 4095) / 4096 * 4096;
+    chunk_max = std::max<int64_t>(8192, std::min<int64_t>(32768, chunk_max));
+    std::vector<StatTask> tasks;
+    tasks.reserve((size_t)(g + total / chunk_max + 1));
+    rp.rlen.assign((size_t)g, 0); rp.rpad.assign((size_t)g, 0);
+    std::vector<int32_t> rchunks((size_t)g), rhist((size_t)g);
+    int32_t n_multi = 0;
+    for (int64_t i = 0; i < g; ++i) {
+      int64_t len = ctx->len[tid[i]];
+      int64_t cs = std::min<int64_t>(start[i], len), ce = std::min<int64_t>(end[i], len);
+      int64_t n = ce - cs;
+      int32_t pad = (int32_t)((int64_t)end[i] - start[i] - n);
+      int32_t nch = (int32_t)((n + chunk_max - 1) / chunk_max);
+      if (nch == 0 && pad > 0) nch = 1;             // nothing but zeros: one empty chunk finishes it
+      int64_t per = nch > 0 ? (((n + nch - 1) / nch + 3) & ~(int64_t)3) : 0;     // even split, 16-byte multiple
+      rp.rlen[i] = (int32_t)n; rp.rpad[i] = pad; rchunks[i] = nch;
+      rhist[i] = nch > 1 ? n_multi++ : -1;
+      int64_t slot = ctx->off[tid[i]] + cs;
+      for (int32_t k = 0; k < nch; ++k) {
+        StatTask t;
+        t.slot = slot + (int64_t)k * per;
+        t.n = (int32_t)std::max<int64_t>(0, std::min<int64_t>(per, n - (int64_t)k * per));
+        t.region = (int32_t)i;
+        tasks.push_back(t);
+      }
+    }
+    rp.n_tasks = (int64_t)tasks.size();
+    rp.n_multi = n_multi;
+    CU(ctx->d_out.ensure((size_t)g * sizeof(mcov_region_stats)));
+    CU(ctx->d_tasks.ensure(std::max<size_t>(tasks.size(), 1) * sizeof(StatTask)));
     CU(ctx->d_rlen.ensure((size_t)g * 8)); CU(ctx->d_rchunks.ensure((size_t)g * 4)); CU(ctx->d_rhist.ensure((size_t)g * 4));
-    CU(ctx->d_done.ensure((size_t)g * 4));
-    CU(ctx->d_pool.ensure((size_t)std::max(n_multi, 1) * kHistBins * 4));
+    // [region_done | hist_pool] are cleared together before every run
+    CU(ctx->d_pool.ensure((size_t)g * 4 + (size_t)std::max(n_multi, 1) * kHistBins * 4 + 16));
     int32_t* d_rlen = ctx->d_rlen.as<int32_t>();
-    int32_t* d_rpad = d_rlen + g;
-    CU(cudaMemcpyAsync(ctx->d_tasks.p, tasks.data(), tasks.size() * sizeof(StatTask), cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(d_rlen, rlen.data(), (size_t)g * 4, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(d_rpad, rpad.data(), (size_t)g * 4, cudaMemcpyHostToDevice, s));
+    if (!tasks.empty()) CU(cudaMemcpyAsync(ctx->d_tasks.p, tasks.data(), tasks.size() * sizeof(StatTask), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(d_rlen, rp.rlen.data(), (size_t)g * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(d_rlen + g, rp.rpad.data(), (size_t)g * 4, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(ctx->d_rchunks.p, rchunks.data(), (size_t)g * 4, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(ctx->d_rhist.p, rhist.data(), (size_t)g * 4, cudaMemcpyHostToDevice, s));
-    CU(cudaMemsetAsync(ctx->d_done.p, 0, (size_t)g * 4, s));
-    if (n_multi) CU(cudaMemsetAsync(ctx->d_pool.p, 0, (size_t)n_multi * kHistBins * 4, s));
-    StatArgs a;
-    a.depth = ctx->depth; a.tasks = ctx->d_tasks.as<StatTask>(); a.region_len = d_rlen; a.region_pad = d_rpad;
-    a.region_chunks = ctx->d_rchunks.as<int32_t>(); a.region_hist = ctx->d_rhist.as<int32_t>();
-    a.hist_pool = ctx->d_pool.as<uint32_t>(); a.region_done = ctx->d_done.as<uint32_t>();
-    a.out = ctx->d_out.as<mcov_region_stats>(); a.breadth_n = breadth_n;
-    MCOV_LAUNCH(ctx, kKRegionStats, (k_region_stats<<<(unsigned)tasks.size(), kStatThreads, 0, s>>>(a)));
-    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s));                   // the host vectors above go out of scope
+    rp.tid.assign(tid, tid + g); rp.start.assign(start, start + g); rp.end.assign(end, end + g);
+    rp.g = g; rp.n_contigs_epoch = ctx->contig_epoch; rp.valid = true;
   }
-  CU(cudaMemcpyAsync(host_out, ctx->d_out.p, (size_t)g * sizeof(mcov_region_stats), cudaMemcpyDeviceToHost, s));
+  if (g > 0) {
+    const size_t done_bytes = ((size_t)g * 4 + 15) & ~(size_t)15;
+    if (rp.n_multi) CU(cudaMemsetAsync(ctx->d_pool.p, 0, done_bytes + (size_t)rp.n_multi * kHistBins * 4, s));
+    if (rp.n_tasks) {
+      StatArgs a;
+      int32_t* d_rlen = ctx->d_rlen.as<int32_t>();
+      a.depth = ctx->depth; a.tasks = ctx->d_tasks.as<StatTask>(); a.region_len = d_rlen; a.region_pad = d_rlen + g;
+      a.region_chunks = ctx->d_rchunks.as<int32_t>(); a.region_hist = ctx->d_rhist.as<int32_t>();
+      a.region_done = ctx->d_pool.as<uint32_t>();
+      a.hist_pool = reinterpret_cast<uint32_t*>(ctx->d_pool.as<char>() + done_bytes);
+      a.out = ctx->d_out.as<mcov_region_stats>(); a.breadth_n = breadth_n;
+      MCOV_LAUNCH(ctx, kKRegionStats, (k_region_stats<<<(unsigned)rp.n_tasks, kStatThreads, 0, s>>>(a)));
+      CU(cudaGetLastError());
+    }
+    CU(cudaMemcpyAsync(host_out, ctx->d_out.p, (size_t)g * sizeof(mcov_region_stats), cudaMemcpyDeviceToHost, s));
+  }
+  PassCounters h;
+  if (ctx->verdict_pending) CU(cudaMemcpyAsync(&h, ctx->d_pc.p, sizeof(h), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
-  // regions whose depth left the counting histogram's range: exact order statistics by a
-  // GPU radix sort of the region (rare: needs max_depth raised above 8191)
+  if (ctx->verdict_pending) { int vr = fused_verdict(ctx, h); if (vr) return vr; }
+  // regions whose depth left the counting histogram's range: exact statistics by a GPU radix sort
+  // of the region (rare: needs max_depth raised above 8190)
   bool redo = false;
   for (int64_t i = 0; i < g; ++i) {
     if (end[i] == start[i]) { std::memset(&host_out[i], 0, sizeof(mcov_region_stats)); continue; }
     if (host_out[i].flags & kStatOverflow) {
       int rc = mcov_order_stats_by_sort(ctx, ctx->depth + ctx->off[tid[i]] + std::min<int64_t>(start[i], ctx->len[tid[i]]),
-                                        rlen[i], rpad[i], ctx->d_out.as<mcov_region_stats>() + i, ctx->d_win_slot,
-                                        ctx->d_win_out);
-      if (rc) return fail(ctx, rc, "mcov_region_stats_run: radix order statistics failed");
+                                        rp.rlen[i], rp.rpad[i], breadth_n, ctx->d_out.as<mcov_region_stats>() + i,
+                                        ctx->d_win_slot, ctx->d_win_out);
+      if (rc) return fail(ctx, rc, "mcov_region_stats_run: radix statistics failed");
       redo = true;
     }
   }
@@ -504,10 +554,7 @@ int mcov_region_stats_run(mcov_ctx* ctx, int64_t g, const int32_t* tid, const in
     CU(cudaMemcpyAsync(again.data(), ctx->d_out.p, (size_t)g * sizeof(mcov_region_stats), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     for (int64_t i = 0; i < g; ++i)
-      if (end[i] != start[i] && (host_out[i].flags & kStatOverflow)) {
-        host_out[i].iq_sum = again[i].iq_sum; host_out[i].med_lo = again[i].med_lo; host_out[i].med_hi = again[i].med_hi;
-        host_out[i].flags = kStatValid | kStatOverflow;
-      }
+      if (end[i] != start[i] && (host_out[i].flags & kStatOverflow)) host_out[i] = again[i];
   }
   return MCOV_OK;
 }

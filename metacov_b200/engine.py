@@ -128,11 +128,14 @@ class CoverageEngine:
     def finalize(self):
         self._check(lib.mcov_finalize(self._ctx))
 
-    def depth_sorted(self, batch):
-        """Fused path; raises McovError(MCOV_ERR_UNSORTED) on unsorted input."""
+    def depth_sorted(self, batch, wait=True):
+        """Fused path; raises McovError(MCOV_ERR_UNSORTED) on unsorted input.  With
+        wait=False the call only enqueues the work and the verdict is raised by the next
+        synchronising call (region_stats / copy_depth / pass_info)."""
         b = _canon(batch)
         n = len(b.tid)
-        self._check(lib.mcov_depth_sorted(self._ctx, n, *[_capi.ptr(x) for x in b], _mem_kind(b)))
+        fn = lib.mcov_depth_sorted if wait else lib.mcov_depth_sorted_async
+        self._check(fn(self._ctx, n, *[_capi.ptr(x) for x in b], _mem_kind(b)))
 
     def compute_depth(self, batch):
         """Per-base depth of all contigs from one batch: the fused sorted path,
