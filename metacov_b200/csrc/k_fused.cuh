@@ -62,8 +62,6 @@ struct FusedArgs {
   int vec_ok;                 // SoA base pointers aligned for 128-bit loads
 };
 
-struct Key { int64_t key; int64_t len_off; };
-
 // slot key of a read: contig offset + clamped position; reads without a valid
 // contig sort after every slot
 __device__ __forceinline__ int64_t slot_key(const ExpandArgs& a, int32_t t, int32_t p, int64_t n_slots, int64_t& len,
@@ -75,18 +73,89 @@ __device__ __forceinline__ int64_t slot_key(const ExpandArgs& a, int32_t t, int3
   return base + q;
 }
 
-// fill tile_first[lo..hi] = v; long gaps are written by the whole warp
-__device__ __forceinline__ void fill_tile_first(int64_t* tile_first, int64_t lo, int64_t hi, int64_t v, int lane,
-                                                unsigned active) {
-  // short gaps inline
-  bool big = (hi - lo) >= 8;
-  if (!big) for (int64_t T = lo; T <= hi; ++T) tile_first[T] = v;
-  unsigned todo = __ballot_sync(active, big);
-  while (todo) {
-    int src = __ffs(todo) - 1;
-    todo &= todo - 1;
-    int64_t l2 = __shfl_sync(active, lo, src), h2 = __shfl_sync(active, hi, src), v2 = __shfl_sync(active, v, src);
-    for (int64_t T = l2 + lane; T <= h2; T += 32) tile_first[T] = v2;
+__device__ __noinline__ unsigned long long warp_cigar_reflen_call(const uint32_t* cig, uint32_t b0, uint32_t b1, int lane,
+                                                                  int aligned16) {
+  return warp_cigar_reflen(cig, b0, b1, lane, aligned16 != 0);
+}
+
+// Rare path of k_fused_prep: some read of this warp is the first of a new tile.  Entered by the
+// whole warp.  tl[r] = tile of read r (already clamped), prev = tile of the read before this thread's.
+__device__ __noinline__ void prep_tile_boundaries(int64_t* tile_first, int64_t i0, int nv, int64_t prev, int64_t t0,
+                                                  int64_t t1, int64_t t2, int64_t t3, bool is_last, int64_t n,
+                                                  int64_t last_tile, int lane) {
+#pragma unroll 1
+  for (int r = 0; r <= 4; ++r) {
+    int64_t tcur = r == 0 ? t0 : r == 1 ? t1 : r == 2 ? t2 : t3;
+    int64_t lo, hi, v;
+    if (r < 4) {
+      bool need = r < nv && tcur > prev;
+      lo = need ? prev + 1 : 1; hi = need ? tcur : 0; v = i0 + r;
+      if (r < nv && tcur > prev) prev = tcur;
+    } else {                                   // the last read closes the table
+      lo = is_last ? prev + 1 : 1; hi = is_last ? last_tile : 0; v = n;
+    }
+    bool big = (hi - lo) >= 8;
+    if (!big) for (int64_t T = lo; T <= hi; ++T) tile_first[T] = v;
+    unsigned todo = __ballot_sync(0xffffffffu, big);
+    while (todo) {                             // long gaps are written by the whole warp
+      int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      int64_t l2 = __shfl_sync(0xffffffffu, lo, src), h2 = __shfl_sync(0xffffffffu, hi, src);
+      int64_t v2 = __shfl_sync(0xffffffffu, v, src);
+      for (int64_t T = l2 + lane; T <= h2; T += 32) tile_first[T] = v2;
+    }
+  }
+}
+
+// Rare path: the starts / near ends of this warp fall into more than one tile.  pt[k] = tile or
+// 0xffffffff (none), k<4 starts (+1), k>=4 ends (-1).  Entered by the whole warp.
+__device__ __noinline__ void prep_tile_agg_slow(int32_t* tile_agg, uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3,
+                                                uint32_t p4, uint32_t p5, uint32_t p6, uint32_t p7, int lane) {
+  uint32_t pt[8] = {p0, p1, p2, p3, p4, p5, p6, p7};
+#pragma unroll 1
+  for (int iter = 0; iter < 6; ++iter) {
+    uint32_t m = 0xffffffffu;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m = min(m, pt[k]);
+    uint32_t Tm = __reduce_min_sync(0xffffffffu, m);
+    if (Tm == 0xffffffffu) return;
+    int local = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) if (pt[k] == Tm) { local += (k < 4) ? 1 : -1; pt[k] = 0xffffffffu; }
+    int v = __reduce_add_sync(0xffffffffu, local);
+    if (lane == 0 && v != 0) atomicAdd(tile_agg + Tm, v);
+  }
+  // reads of this warp spread over many tiles (sparse data): direct updates
+#pragma unroll
+  for (int k = 0; k < 8; ++k) if (pt[k] != 0xffffffffu) atomicAdd(tile_agg + pt[k], (k < 4) ? 1 : -1);
+}
+
+// Rare path: some read of this warp spans more than kNearSpan slots.  Entered by the whole warp.
+__device__ __noinline__ void prep_far(const FusedArgs& f, int64_t e0, int64_t e1, int64_t e2, int64_t e3, unsigned farmask,
+                                      int lane) {
+  int nfar = __popc(farmask);
+  int incl = nfar;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  int total = __shfl_sync(0xffffffffu, incl, 31);
+  uint32_t base = 0;
+  if (lane == 0) base = atomicAdd(&f.e.pc->n_far, (uint32_t)total);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  uint32_t idx = base + (uint32_t)(incl - nfar);
+#pragma unroll 1
+  for (int r = 0; r < 4; ++r) {
+    if (farmask & (1u << r)) {
+      int64_t e = r == 0 ? e0 : r == 1 ? e1 : r == 2 ? e2 : e3;
+      if (idx < f.far_cap) {
+        f.far_end[idx] = e;
+        atomicAdd(f.tile_cnt + (e >> kTileShift), 1u);
+        atomicAdd(f.tile_agg + (e >> kTileShift), -1);
+      }
+      ++idx;
+    }
   }
 }
 
@@ -103,11 +172,12 @@ k_fused_prep(FusedArgs f) {
   const int64_t g_stride = (int64_t)gridDim.x * kPrepThreads;
   const int64_t last_tile = f.n_tiles;                        // tile_first has n_tiles+1 entries
 
+#pragma unroll 1
   for (int64_t g = (int64_t)blockIdx.x * kPrepThreads + threadIdx.x; g < g_round; g += g_stride) {
     const int64_t i0 = g * kPrepPer;
     int32_t T[4], P[4];
     uint32_t F[4], Q[4], O[5];
-    int nv = (int)min((int64_t)kPrepPer, max((int64_t)0, n - i0));     // valid reads of this thread
+    const int nv = (int)min((int64_t)kPrepPer, max((int64_t)0, n - i0));     // valid reads of this thread
     if (nv == kPrepPer && f.vec_ok) {
       int4 t4 = *reinterpret_cast<const int4*>(a.tid + i0);
       int4 p4 = *reinterpret_cast<const int4*>(a.pos + i0);
@@ -133,61 +203,64 @@ k_fused_prep(FusedArgs f) {
 #pragma unroll
       for (int r = 0; r <= 4; ++r) O[r] = (i0 <= n) ? a.cig_off[min(i0 + r, n)] : 0u;
     }
-    // previous read's (tid,pos): from the neighbouring lane, lane 0 reloads
-    int32_t pt = __shfl_up_sync(0xffffffffu, T[3], 1), pp = __shfl_up_sync(0xffffffffu, P[3], 1);
-    if (lane == 0) {
-      if (i0 > 0 && i0 - 1 < n) { pt = a.tid[i0 - 1]; pp = a.pos[i0 - 1]; }
-      else { pt = INT_MIN; pp = INT_MIN; }                        // INT_MIN: "no previous read"
-    }
 
+    // ---- filter + CIGAR reduction ------------------------------------------------------------
     bool pass[4];
-    unsigned long long reflen[4];
-    bool coop[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      pass[r] = r < nv && read_passes(F[r], Q[r], a.filt) && T[r] >= 0 && T[r] < a.n_contigs;
-      uint32_t nc = O[r + 1] - O[r];
-      coop[r] = pass[r] && nc > kThreadOps;
-      reflen[r] = 0;
-    }
-    // first op of every short CIGAR: four independent loads
+    uint32_t reflen[4];                 // a read's reference length fits 32 bits (BAM positions are int32)
+    unsigned coop = 0;
     uint32_t op0[4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) op0[r] = (pass[r] && !coop[r] && O[r + 1] > O[r]) ? __ldg(a.cig + O[r]) : 0u;
+    for (int r = 0; r < 4; ++r) {
+      pass[r] = r < nv && read_passes(F[r], Q[r], a.filt) && (uint32_t)T[r] < (uint32_t)a.n_contigs;
+      uint32_t nc = O[r + 1] - O[r];
+      bool c = pass[r] && nc > kThreadOps;
+      coop |= c ? (1u << r) : 0u;
+      op0[r] = (pass[r] && !c && nc > 0) ? __ldg(a.cig + O[r]) : 0u;     // four independent loads
+    }
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       reflen[r] = cigar_ref_len(op0[r]);
-      if (pass[r] && !coop[r])
+      if (pass[r] && !((coop >> r) & 1u) && O[r + 1] - O[r] > 1) {
+#pragma unroll 1
         for (uint32_t k = O[r] + 1; k < O[r + 1]; ++k) reflen[r] += cigar_ref_len(__ldg(a.cig + k));
+      }
     }
     // long CIGARs: the whole warp reduces one read at a time with 128-bit loads
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      unsigned todo = __ballot_sync(0xffffffffu, coop[r]);
-      while (todo) {
-        int src = __ffs(todo) - 1;
-        todo &= todo - 1;
-        uint32_t b0 = __shfl_sync(0xffffffffu, O[r], src), b1 = __shfl_sync(0xffffffffu, O[r + 1], src);
-        unsigned long long v = warp_cigar_reflen(a.cig, b0, b1, lane, a.cig_aligned16 != 0);
-        if (lane == src) reflen[r] = v;
+    while (__any_sync(0xffffffffu, coop != 0)) {
+      unsigned lanes = __ballot_sync(0xffffffffu, coop != 0);
+      int src = __ffs(lanes) - 1;
+      int r = __ffs(__shfl_sync(0xffffffffu, coop, src)) - 1;
+      uint32_t ob = r == 0 ? O[0] : r == 1 ? O[1] : r == 2 ? O[2] : O[3];
+      uint32_t oe = r == 0 ? O[1] : r == 1 ? O[2] : r == 2 ? O[3] : O[4];
+      ob = __shfl_sync(0xffffffffu, ob, src);
+      oe = __shfl_sync(0xffffffffu, oe, src);
+      unsigned long long v = warp_cigar_reflen_call(a.cig, ob, oe, lane, a.cig_aligned16);
+      if (lane == src) {
+        uint32_t v32 = v > 0x7fffffffull ? 0x7fffffffu : (uint32_t)v;
+        if (r == 0) reflen[0] = v32; else if (r == 1) reflen[1] = v32; else if (r == 2) reflen[2] = v32; else reflen[3] = v32;
+        coop &= ~(1u << r);
       }
     }
 
-    // slot keys, clipped intervals, records
+    // ---- slot keys, clipped intervals, records --------------------------------------------------
     int64_t key[4], endk[4];
     uint32_t span[4];
-    int64_t c_len = 0, c_base = 0; int32_t c_tid = INT_MIN;
+    int64_t c_len = 0, c_base = f.n_slots;
+    int32_t c_tid = -1;
+    unsigned farmask = 0;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       if (T[r] != c_tid) { c_tid = T[r]; (void)slot_key(a, T[r], 0, f.n_slots, c_len, c_base); }
-      bool valid_t = T[r] >= 0 && T[r] < a.n_contigs;
       int64_t q = P[r] < 0 ? 0 : (P[r] > c_len ? c_len : (int64_t)P[r]);
-      key[r] = valid_t ? c_base + q : f.n_slots;
+      key[r] = c_base + q;                       // invalid contig: c_base = n_slots, c_len = 0
       span[r] = 0; endk[r] = key[r];
       if (pass[r]) {
         int64_t e = (int64_t)P[r] + (int64_t)reflen[r];
         e = e < 0 ? 0 : (e > c_len ? c_len : e);
-        if (e > q) { span[r] = (uint32_t)(e - q); endk[r] = c_base + e; n_pass += 1; aligned += reflen[r]; }
+        if (e > q) {
+          span[r] = (uint32_t)(e - q); endk[r] = c_base + e; n_pass += 1; aligned += reflen[r];
+          if (span[r] > kNearSpan) farmask |= 1u << r; else max_span = max(max_span, span[r]);
+        }
       }
     }
     if (nv == kPrepPer) {
@@ -198,97 +271,63 @@ k_fused_prep(FusedArgs f) {
       for (int r = 0; r < nv; ++r) f.rec[i0 + r] = make_uint2((uint32_t)key[r], span[r]);
     }
 
-    // sortedness + tile boundaries (tile_first)
+    // ---- sortedness + tile boundaries (tile_first) -------------------------------------------------
     {
-      int32_t qt = pt, qp = pp;
-      int64_t plen, pbase;
-      int64_t prev_tile = (pt == INT_MIN) ? -1 : (slot_key(a, pt, pp, f.n_slots, plen, pbase) >> kTileShift);
-      // per-thread pending fill (at most one long gap per read; short ones inline)
+      int64_t tl[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) tl[r] = min(key[r] >> kTileShift, last_tile);
+      // the read before this thread's: tile and (tid,pos) from the neighbouring lane, lane 0 reloads
+      int64_t prev_tile = __shfl_up_sync(0xffffffffu, tl[3], 1);
+      int32_t pt = __shfl_up_sync(0xffffffffu, T[3], 1), pp = __shfl_up_sync(0xffffffffu, P[3], 1);
+      bool has_prev = true;
+      if (lane == 0) {
+        if (i0 > 0 && i0 - 1 < n) {
+          pt = a.tid[i0 - 1]; pp = a.pos[i0 - 1];
+          int64_t l_, b_;
+          prev_tile = min(slot_key(a, pt, pp, f.n_slots, l_, b_) >> kTileShift, last_tile);
+        } else { has_prev = false; prev_tile = -1; }
+      }
+      bool bnd = false;
+      int64_t run = prev_tile;
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
-        bool v = r < nv;
-        if (v && qt != INT_MIN) {
-          uint32_t u0 = (uint32_t)qt, u1 = (uint32_t)T[r];
-          if (u1 < u0 || (u1 == u0 && P[r] < qp)) unsorted = 1;
+        if (r < nv) {
+          uint32_t u0 = (uint32_t)pt, u1 = (uint32_t)T[r];
+          if (has_prev && (u1 < u0 || (u1 == u0 && P[r] < pp))) unsorted = 1;
+          bnd |= tl[r] > run;
+          run = max(run, tl[r]);
+          pt = T[r]; pp = P[r]; has_prev = true;
         }
-        int64_t t_cur = v ? min(key[r] >> kTileShift, last_tile) : prev_tile;
-        int64_t lo = prev_tile + 1, hi = t_cur;
-        bool need = v && hi >= lo;
-        unsigned active = 0xffffffffu;
-        fill_tile_first(f.tile_first, need ? lo : 1, need ? hi : 0, i0 + r, lane, active);
-        if (v) { prev_tile = max(prev_tile, t_cur); qt = T[r]; qp = P[r]; }
       }
-      // the last read closes the table
-      bool is_last = nv > 0 && (i0 + nv == n);
-      fill_tile_first(f.tile_first, is_last ? prev_tile + 1 : 1, is_last ? last_tile : 0, n, lane, 0xffffffffu);
+      const bool is_last = nv > 0 && (i0 + nv == n);
+      if (__any_sync(0xffffffffu, bnd || is_last))
+        prep_tile_boundaries(f.tile_first, i0, nv, prev_tile, tl[0], tl[1], tl[2], tl[3], is_last, n, last_tile, lane);
     }
 
-    // far reads: end list + per-tile far counts (warp-aggregated slot claim); near: max span
+    // ---- tile_agg: +1 per start, -1 per near end (far ends are handled with the far list) ----------
     {
-      int nfar = 0;
+      uint32_t ptl[8];
+      uint32_t mn = 0xffffffffu, mx = 0u;
+      int net = 0;
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
-        if (span[r] > kNearSpan) ++nfar;
-        else max_span = max(max_span, span[r]);
+        bool c = span[r] > 0, nr = c && span[r] <= kNearSpan;
+        ptl[r] = c ? (uint32_t)(key[r] >> kTileShift) : 0xffffffffu;
+        ptl[4 + r] = nr ? (uint32_t)(endk[r] >> kTileShift) : 0xffffffffu;
+        if (c) { mn = min(mn, ptl[r]); mx = max(mx, ptl[r]); net += 1; }
+        if (nr) { mn = min(mn, ptl[4 + r]); mx = max(mx, ptl[4 + r]); net -= 1; }
       }
-      int incl = nfar;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int y = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += y;
-      }
-      int total = __shfl_sync(0xffffffffu, incl, 31);
-      if (total) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&a.pc->n_far, (uint32_t)total);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        uint32_t idx = base + (uint32_t)(incl - nfar);
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          if (span[r] > kNearSpan) {
-            if (idx < f.far_cap) {
-              f.far_end[idx] = endk[r];
-              atomicAdd(f.tile_cnt + (endk[r] >> kTileShift), 1u);
-              atomicAdd(f.tile_agg + (endk[r] >> kTileShift), -1);
-            }
-            ++idx;
-          }
+      uint32_t wmin = __reduce_min_sync(0xffffffffu, mn), wmax = __reduce_max_sync(0xffffffffu, mx);
+      if (wmin != 0xffffffffu) {
+        if (wmin == wmax) {                       // every start and end of this warp in one tile
+          int v = __reduce_add_sync(0xffffffffu, net);
+          if (lane == 0 && v != 0) atomicAdd(f.tile_agg + wmin, v);
+        } else {
+          prep_tile_agg_slow(f.tile_agg, ptl[0], ptl[1], ptl[2], ptl[3], ptl[4], ptl[5], ptl[6], ptl[7], lane);
         }
       }
     }
-
-    // tile_agg: +1 per start, -1 per near end, aggregated across the warp per distinct tile
-    {
-      int64_t pend_t[8];
-      int pend_v[8];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        bool c = span[r] > 0;
-        pend_t[r] = c ? (key[r] >> kTileShift) : INT64_MAX;
-        pend_v[r] = 1;
-        bool nearr = c && span[r] <= kNearSpan;
-        pend_t[4 + r] = nearr ? (endk[r] >> kTileShift) : INT64_MAX;
-        pend_v[4 + r] = -1;
-      }
-      for (int iter = 0; iter < 4; ++iter) {
-        int64_t m = INT64_MAX;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) m = min(m, pend_t[k]);
-        // warp minimum of a 64-bit value: high then low word
-        unsigned hi = __reduce_min_sync(0xffffffffu, (unsigned)((unsigned long long)m >> 32));
-        unsigned lo = __reduce_min_sync(0xffffffffu, ((unsigned)((unsigned long long)m >> 32) == hi) ? (unsigned)m : 0xffffffffu);
-        int64_t Tm = (int64_t)(((unsigned long long)hi << 32) | lo);
-        if (Tm == INT64_MAX) break;
-        int local = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) if (pend_t[k] == Tm) { local += pend_v[k]; pend_t[k] = INT64_MAX; }
-        int v = __reduce_add_sync(0xffffffffu, local);
-        if (lane == 0 && v != 0) atomicAdd(f.tile_agg + Tm, v);
-      }
-      // anything still pending (reads of this warp spread over many tiles): direct updates
-#pragma unroll
-      for (int k = 0; k < 8; ++k) if (pend_t[k] != INT64_MAX) atomicAdd(f.tile_agg + pend_t[k], pend_v[k]);
-    }
+    if (__any_sync(0xffffffffu, farmask != 0)) prep_far(f, endk[0], endk[1], endk[2], endk[3], farmask, lane);
   }
 
   // block-level reduction of the pass counters
@@ -325,115 +364,178 @@ __global__ void k_far_scatter(FusedArgs f) {
   }
 }
 
-__global__ void __launch_bounds__(kFusedThreads, 5)
+struct TileMeta {
+  int64_t r0, r1, jmin;    // own reads [r0,r1); walk-back candidates [jmin,r0)
+  int carry;               // depth entering the tile
+  uint32_t k0, k1;         // far-end bucket [k0,k1)
+};
+
+__device__ __forceinline__ TileMeta load_tile_meta(const FusedArgs& f, int64_t tile) {
+  TileMeta m;
+  m.r0 = m.r1 = m.jmin = 0; m.carry = 0; m.k0 = m.k1 = 0;
+  if (tile < f.n_tiles) {
+    m.r0 = f.tile_first[tile]; m.r1 = f.tile_first[tile + 1];
+    m.jmin = tile > 0 ? f.tile_first[tile - 1] : 0;
+    m.carry = tile > 0 ? f.tile_agg[tile - 1] : 0;
+    m.k0 = tile > 0 ? f.tile_cnt[tile - 1] : 0u; m.k1 = f.tile_cnt[tile];
+  }
+  return m;
+}
+
+constexpr int kPreOwn = 4;     // own records prefetched per thread (kPreOwn*kFusedThreads per tile)
+
+__device__ __forceinline__ void prefetch_recs(const FusedArgs& f, const TileMeta& m, uint2 (&own)[kPreOwn], uint2& back) {
+#pragma unroll
+  for (int u = 0; u < kPreOwn; ++u) {
+    int64_t j = m.r0 + threadIdx.x + u * kFusedThreads;
+    own[u] = (j < m.r1) ? f.rec[j] : make_uint2(0u, 0u);
+  }
+  int64_t jb = m.r0 - 1 - threadIdx.x;
+  back = (jb >= m.jmin) ? f.rec[jb] : make_uint2(0u, 0u);
+}
+
+// Persistent, software-pipelined: while tile k is accumulated in shared memory, scanned and
+// stored, the records of tile k+1 and the metadata of tile k+2 are already in flight.
+__global__ void __launch_bounds__(kFusedThreads, 4)
 k_fused_tile(FusedArgs f) {
   __shared__ __align__(16) int s_start[kTile];
   __shared__ __align__(16) int s_end[kTile];
   __shared__ int s_warp[kFusedThreads / 32];
   __shared__ int s_warp2[kFusedThreads / 32];
   PassCounters* pc = f.e.pc;
-  const int64_t tile = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // tile metadata: independent loads issued before the shared memory is cleared
-  const int64_t r0 = f.tile_first[tile], r1 = f.tile_first[tile + 1];
-  const int64_t jmin = tile > 0 ? f.tile_first[tile - 1] : 0;
-  const int carry = tile > 0 ? f.tile_agg[tile - 1] : 0;           // depth entering the tile
-  const uint32_t k0 = tile > 0 ? f.tile_cnt[tile - 1] : 0u, k1 = f.tile_cnt[tile];
-  const uint32_t reach = pc->max_span;
-  {
-    int4* z0 = reinterpret_cast<int4*>(s_start);
-    int4* z1 = reinterpret_cast<int4*>(s_end);
-    for (int k = threadIdx.x; k < kTile / 4; k += kFusedThreads) { z0[k] = make_int4(0, 0, 0, 0); z1[k] = make_int4(0, 0, 0, 0); }
-  }
-  __syncthreads();
-  const int64_t base = tile << kTileShift;
-  const uint32_t base_lo = (uint32_t)base;
+  const int64_t stride = gridDim.x;
+  const uint32_t reach = pc->max_span;                  // written by k_fused_prep
+  int64_t tile = blockIdx.x;
+  TileMeta m_cur = load_tile_meta(f, tile);
+  TileMeta m_next = load_tile_meta(f, tile + stride);
+  uint2 own[kPreOwn], back;
+  prefetch_recs(f, m_cur, own, back);
+  int mx = 0, cap = 0;
 
-  // reads that start in this tile
-  for (int64_t j = r0 + threadIdx.x; j < r1; j += kFusedThreads) {
-    uint2 r = f.rec[j];
-    if (r.y) {
-      uint32_t local = r.x - base_lo;                  // < kTile for sorted input (tile_first)
-      if (local < (uint32_t)kTile) {                   // guard: unsorted input must not corrupt smem
-        atomicAdd(&s_start[local], 1);
-        uint32_t el = local + r.y;
-        if (r.y <= kNearSpan && el < (uint32_t)kTile) atomicAdd(&s_end[el], 1);
+#pragma unroll 1
+  for (; tile < f.n_tiles; tile += stride) {
+    // prefetch for the following tiles first: these loads stay in flight during the whole body
+    uint2 n_own[kPreOwn], n_back;
+    prefetch_recs(f, m_next, n_own, n_back);            // empty ranges when tile+stride is past the end
+    TileMeta m_nn = load_tile_meta(f, tile + 2 * stride);
+    {
+      int4* z0 = reinterpret_cast<int4*>(s_start);
+      int4* z1 = reinterpret_cast<int4*>(s_end);
+      for (int k = threadIdx.x; k < kTile / 4; k += kFusedThreads) { z0[k] = make_int4(0, 0, 0, 0); z1[k] = make_int4(0, 0, 0, 0); }
+    }
+    __syncthreads();
+    const int64_t base = tile << kTileShift;
+    const uint32_t base_lo = (uint32_t)base;
+
+    // reads that start in this tile
+#pragma unroll
+    for (int u = 0; u < kPreOwn; ++u) {
+      uint2 r = own[u];
+      if (r.y) {
+        uint32_t local = r.x - base_lo;                  // < kTile for sorted input (tile_first)
+        if (local < (uint32_t)kTile) {                   // guard: unsorted input must not corrupt smem
+          atomicAdd(&s_start[local], 1);
+          uint32_t el = local + r.y;
+          if (r.y <= kNearSpan && el < (uint32_t)kTile) atomicAdd(&s_end[el], 1);
+        }
       }
     }
-  }
-  // near reads that started before the tile and end inside it: walk back while the start is within
-  // max_span of the tile (sorted order => monotone distance).  reach <= kNearSpan = kTile, so every
-  // candidate started in the previous tile; staying inside it keeps the 32-bit distance from wrapping.
-  for (int64_t j = r0 - 1 - threadIdx.x; j >= jmin; j -= kFusedThreads) {
-    uint2 r = f.rec[j];
-    uint32_t d = base_lo - r.x;                        // distance behind the tile start (>= 1)
-    if (d > reach) break;
-    if (r.y >= d && r.y <= kNearSpan) {
-      uint32_t el = r.y - d;
-      if (el < (uint32_t)kTile) atomicAdd(&s_end[el], 1);
+    for (int64_t j = m_cur.r0 + threadIdx.x + kPreOwn * kFusedThreads; j < m_cur.r1; j += kFusedThreads) {
+      uint2 r = f.rec[j];                                // dense tiles: the rest straight from global
+      if (r.y) {
+        uint32_t local = r.x - base_lo;
+        if (local < (uint32_t)kTile) {
+          atomicAdd(&s_start[local], 1);
+          uint32_t el = local + r.y;
+          if (r.y <= kNearSpan && el < (uint32_t)kTile) atomicAdd(&s_end[el], 1);
+        }
+      }
     }
-  }
-  // far ends bucketed for this tile
-  for (uint32_t k = k0 + threadIdx.x; k < k1; k += kFusedThreads) atomicAdd(&s_end[f.far_sorted[k] & (kTile - 1)], 1);
-  __syncthreads();
+    // near reads that started before the tile and end inside it: walk back while the start is
+    // within max_span of the tile (sorted order => monotone distance).  reach <= kNearSpan = kTile,
+    // so every candidate started in the previous tile (>= jmin), which also keeps the 32-bit
+    // distance from wrapping.
+    {
+      uint2 r = back;
+      int64_t j = m_cur.r0 - 1 - threadIdx.x;
+      while (j >= m_cur.jmin) {
+        uint32_t d = base_lo - r.x;                      // distance behind the tile start (>= 1)
+        if (d > reach) break;
+        if (r.y >= d && r.y <= kNearSpan) {
+          uint32_t el = r.y - d;
+          if (el < (uint32_t)kTile) atomicAdd(&s_end[el], 1);
+        }
+        j -= kFusedThreads;
+        if (j >= m_cur.jmin) r = f.rec[j];
+      }
+    }
+    // far ends bucketed for this tile
+    for (uint32_t k = m_cur.k0 + threadIdx.x; k < m_cur.k1; k += kFusedThreads)
+      atomicAdd(&s_end[f.far_sorted[k] & (kTile - 1)], 1);
+    __syncthreads();
 
-  // block scan of (starts - ends), warp-striped like k_scan_inplace
-  const int4* vs = reinterpret_cast<const int4*>(s_start);
-  const int4* ve = reinterpret_cast<const int4*>(s_end);
-  int4 v[kScanVec], en[kScanVec];
-  int run[kScanVec];
+    // block scan of (starts - ends), warp-striped like k_scan_inplace
+    const int4* vs = reinterpret_cast<const int4*>(s_start);
+    const int4* ve = reinterpret_cast<const int4*>(s_end);
+    int4 v[kScanVec], en[kScanVec];
+    int run[kScanVec];
 #pragma unroll
-  for (int j = 0; j < kScanVec; ++j) {
-    int idx = (warp * kScanVec + j) * 32 + lane;
-    int4 st = vs[idx];
-    en[j] = ve[idx];
-    v[j].x = st.x - en[j].x;
-    v[j].y = v[j].x + st.y - en[j].y;
-    v[j].z = v[j].y + st.z - en[j].z;
-    v[j].w = v[j].z + st.w - en[j].w;
-    run[j] = v[j].w;
-  }
-  int acc = 0;
-#pragma unroll
-  for (int j = 0; j < kScanVec; ++j) {
-    int x = run[j];
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x += y;
+    for (int j = 0; j < kScanVec; ++j) {
+      int idx = (warp * kScanVec + j) * 32 + lane;
+      int4 st = vs[idx];
+      en[j] = ve[idx];
+      v[j].x = st.x - en[j].x;
+      v[j].y = v[j].x + st.y - en[j].y;
+      v[j].z = v[j].y + st.z - en[j].z;
+      v[j].w = v[j].z + st.w - en[j].w;
+      run[j] = v[j].w;
     }
-    int total = __shfl_sync(0xffffffffu, x, 31);
-    run[j] = x - run[j] + acc;
-    acc += total;
-  }
-  if (lane == 31) s_warp[warp] = acc;
-  __syncthreads();
-  int off = carry;
+    int acc = 0;
 #pragma unroll
-  for (int k = 0; k < kFusedThreads / 32; ++k) off += (k < warp) ? s_warp[k] : 0;
-  int4* out = reinterpret_cast<int4*>(f.depth + base);
-  const int64_t n_vec = (f.n_slots - base) >> 2;
-  int mx = 0, cap = 0;
+    for (int j = 0; j < kScanVec; ++j) {
+      int x = run[j];
 #pragma unroll
-  for (int j = 0; j < kScanVec; ++j) {
-    int idx = (warp * kScanVec + j) * 32 + lane;
-    int o = off + run[j];
-    v[j].x += o; v[j].y += o; v[j].z += o; v[j].w += o;
-    mx = max(mx, max(max(v[j].x, v[j].y), max(v[j].z, v[j].w)));
-    cap = max(cap, max(max(v[j].x + en[j].x, v[j].y + en[j].y), max(v[j].z + en[j].z, v[j].w + en[j].w)));
-    if (idx < n_vec) st_stream_int4(out + idx, v[j]);
+      for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      int total = __shfl_sync(0xffffffffu, x, 31);
+      run[j] = x - run[j] + acc;
+      acc += total;
+    }
+    if (lane == 31) s_warp[warp] = acc;
+    __syncthreads();                                     // also: every warp has read s_start/s_end
+    int off = m_cur.carry;
+#pragma unroll
+    for (int k = 0; k < kFusedThreads / 32; ++k) off += (k < warp) ? s_warp[k] : 0;
+    int4* out = reinterpret_cast<int4*>(f.depth + base);
+    const int64_t n_vec = (f.n_slots - base) >> 2;
+#pragma unroll
+    for (int j = 0; j < kScanVec; ++j) {
+      int idx = (warp * kScanVec + j) * 32 + lane;
+      int o = off + run[j];
+      v[j].x += o; v[j].y += o; v[j].z += o; v[j].w += o;
+      mx = max(mx, max(max(v[j].x, v[j].y), max(v[j].z, v[j].w)));
+      cap = max(cap, max(max(v[j].x + en[j].x, v[j].y + en[j].y), max(v[j].z + en[j].z, v[j].w + en[j].w)));
+      if (idx < n_vec) st_stream_int4(out + idx, v[j]);
+    }
+    __syncthreads();                                     // s_warp is rewritten by the next tile
+    m_cur = m_next; m_next = m_nn;
+#pragma unroll
+    for (int u = 0; u < kPreOwn; ++u) own[u] = n_own[u];
+    back = n_back;
   }
+
   mx = warp_max(mx);
   cap = warp_max(cap);
-  __syncthreads();
   if (lane == 0) { s_warp[warp] = mx; s_warp2[warp] = cap; }
   __syncthreads();
   if (threadIdx.x == 0) {
     int m = 0, c2 = 0;
     for (int k = 0; k < kFusedThreads / 32; ++k) { m = max(m, s_warp[k]); c2 = max(c2, s_warp2[k]); }
-    // only touch the global maxima when this tile can raise them (stale reads only cost an extra atomic)
-    if (m > *((volatile int*)&pc->max_depth_seen)) atomicMax(&pc->max_depth_seen, m);
-    if (c2 > *((volatile int*)&pc->cap_metric)) atomicMax(&pc->cap_metric, c2);
+    if (m > 0) atomicMax(&pc->max_depth_seen, m);
+    if (c2 > 0) atomicMax(&pc->cap_metric, c2);
   }
 }
 

@@ -146,6 +146,33 @@ __device__ __forceinline__ void write_stats(mcov_region_stats* out, const WalkOu
   *out = r;
 }
 
+// one aligned vector of four depths -> histogram, equal neighbours merged first
+__device__ __forceinline__ void hist_vec(uint32_t* s_hist, const int4& q) {
+  int b0 = hist_bin(q.x), b1 = hist_bin(q.y), b2 = hist_bin(q.z), b3 = hist_bin(q.w);
+  if (b0 == b1 && b2 == b3) {
+    if (b0 == b2) atomicAdd(&s_hist[b0], 4u);
+    else { atomicAdd(&s_hist[b0], 2u); atomicAdd(&s_hist[b2], 2u); }
+  } else {
+    uint32_t c0 = 1;
+    if (b1 == b0) ++c0; else { atomicAdd(&s_hist[b0], c0); b0 = b1; c0 = 1; }
+    if (b2 == b0) ++c0; else { atomicAdd(&s_hist[b0], c0); b0 = b2; c0 = 1; }
+    if (b3 == b0) ++c0; else { atomicAdd(&s_hist[b0], c0); b0 = b3; c0 = 1; }
+    atomicAdd(&s_hist[b0], c0);
+  }
+}
+
+__device__ __forceinline__ void hist_partial(uint32_t* s_hist, const int4& q, int lo, int hi) {
+  int v[4] = {q.x, q.y, q.z, q.w};
+  for (int k = lo; k < hi; ++k) atomicAdd(&s_hist[hist_bin(v[k])], 1u);
+}
+
+struct RegionScratch {          // per multi-chunk region, zeroed before every run
+  uint32_t done;                // chunks that have merged their histogram
+  uint32_t max_bin;             // highest non-empty bin
+  uint32_t min_bin_inv;         // kHistBins-1 - lowest non-empty bin
+  uint32_t pad;
+};
+
 __global__ void __launch_bounds__(kStatThreads, 3)
 k_region_stats(StatArgs a) {
   __shared__ __align__(16) uint32_t s_hist[kHistBins];
@@ -173,57 +200,58 @@ k_region_stats(StatArgs a) {
   const int4* vp = reinterpret_cast<const int4*>(a.depth + a0);
   const int head = (int)(s0 - a0);                      // elements to skip in the first vector
   const int tail = (int)((a0 + (nvec << 2)) - s1);      // elements to skip in the last vector
-  for (int64_t j = t; j < nvec; j += kStatThreads) {
-    int4 q = ld_stream_int4(vp + j);
-    int b[4] = {hist_bin(q.x), hist_bin(q.y), hist_bin(q.z), hist_bin(q.w)};
-    int lo = (j == 0) ? head : 0, hi = (j == nvec - 1) ? 4 - tail : 4;
-    if (lo == 0 && hi == 4) {
-      // interior vector: merge equal neighbours before touching shared memory
-      if (b[0] == b[1] && b[1] == b[2] && b[2] == b[3]) atomicAdd(&s_hist[b[0]], 4u);
-      else {
-        int run_v = b[0]; uint32_t run_c = 1;
-#pragma unroll
-        for (int k = 1; k < 4; ++k) {
-          if (b[k] == run_v) ++run_c;
-          else { atomicAdd(&s_hist[run_v], run_c); run_v = b[k]; run_c = 1; }
-        }
-        atomicAdd(&s_hist[run_v], run_c);
-      }
-    } else {
-      for (int k = lo; k < hi; ++k) atomicAdd(&s_hist[b[k]], 1u);
+  const int64_t jf0 = head ? 1 : 0, jf1 = nvec - (tail ? 1 : 0);   // full vectors [jf0, jf1)
+  // four independent 128-bit loads in flight per thread
+  for (int64_t j = jf0 + t; j < jf1; j += 4 * kStatThreads) {
+    int4 q0 = __ldcs(vp + j), q1, q2, q3;
+    const bool v1 = j + kStatThreads < jf1, v2 = j + 2 * kStatThreads < jf1, v3 = j + 3 * kStatThreads < jf1;
+    if (v1) q1 = __ldcs(vp + j + kStatThreads);
+    if (v2) q2 = __ldcs(vp + j + 2 * kStatThreads);
+    if (v3) q3 = __ldcs(vp + j + 3 * kStatThreads);
+    hist_vec(s_hist, q0);
+    if (v1) hist_vec(s_hist, q1);
+    if (v2) hist_vec(s_hist, q2);
+    if (v3) hist_vec(s_hist, q3);
+  }
+  if (nvec > 0) {
+    if (nvec == 1) { if (t == 0 && (head || tail)) hist_partial(s_hist, __ldcs(vp), head, 4 - tail); }
+    else {
+      if (t == 0 && head) hist_partial(s_hist, __ldcs(vp), head, 4);
+      if (t == 32 && tail) hist_partial(s_hist, __ldcs(vp + nvec - 1), 0, 4 - tail);
     }
   }
   __syncthreads();
   mcov_region_stats* out = a.out + g;
 
-  if (n_chunks == 1) {
-    if (pad > 0 && t == 0) s_hist[0] += (uint32_t)pad;   // zeros beyond the contig end join the multiset
-    if (pad > 0) __syncthreads();
-    WalkOut w = hist_walk(s_hist, n_region, a.breadth_n, s_u64, s_i32, s_med);
-    if (t == 0) write_stats(out, w);
-    return;
+  if (n_chunks > 1) {
+    // ---- multi-chunk region: merge the non-empty bins into the region's global histogram ----
+    uint32_t* gh = a.hist_pool + (int64_t)a.region_hist[g] * kHistBins;
+    RegionScratch* rs = reinterpret_cast<RegionScratch*>(a.region_done) + a.region_hist[g];
+    uint32_t bmax = 0, bmin_inv = 0;
+    for (int b = t; b < kHistBins; b += kStatThreads) {
+      uint32_t c = s_hist[b];
+      if (c) { atomicAdd(gh + b, c); bmax = max(bmax, (uint32_t)b); bmin_inv = max(bmin_inv, (uint32_t)(kHistBins - 1 - b)); }
+    }
+    bmax = (uint32_t)warp_max((int)bmax); bmin_inv = (uint32_t)warp_max((int)bmin_inv);
+    if ((t & 31) == 0) { atomicMax(&rs->max_bin, bmax); atomicMax(&rs->min_bin_inv, bmin_inv); }
+    __threadfence();
+    __syncthreads();
+    if (t == 0) {
+      unsigned prev = atomicAdd(&rs->done, 1u);
+      s_last = (prev == (unsigned)(n_chunks - 1));
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // last chunk of the region: pull the merged histogram (only the populated range) and finish
+    const int glo = kHistBins - 1 - (int)*((volatile uint32_t*)&rs->min_bin_inv), ghi = (int)*((volatile uint32_t*)&rs->max_bin);
+    for (int b = glo + t; b <= ghi; b += kStatThreads) s_hist[b] = __ldcg(gh + b);
+    __syncthreads();
   }
-
-  // ---- multi-chunk region: merge the non-empty bins into the region's global histogram ----
-  uint32_t* gh = a.hist_pool + (int64_t)a.region_hist[g] * kHistBins;
-  for (int b = t; b < kHistBins; b += kStatThreads) {
-    uint32_t c = s_hist[b];
-    if (c) atomicAdd(gh + b, c);
+  if (pad > 0) {                       // zeros beyond the contig end join the multiset
+    if (t == 0) s_hist[0] += (uint32_t)pad;
+    __syncthreads();
   }
-  __threadfence();
-  __syncthreads();
-  if (t == 0) {
-    unsigned prev = atomicAdd(a.region_done + g, 1u);
-    s_last = (prev == (unsigned)(n_chunks - 1));
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  // last chunk of the region: pull the merged histogram and finish
-  for (int b = t; b < kHistBins; b += kStatThreads) s_hist[b] = __ldcg(gh + b);
-  __syncthreads();
-  if (pad > 0 && t == 0) s_hist[0] += (uint32_t)pad;
-  if (pad > 0) __syncthreads();
   WalkOut w = hist_walk(s_hist, n_region, a.breadth_n, s_u64, s_i32, s_med);
   if (t == 0) write_stats(out, w);
 }

@@ -152,7 +152,10 @@ int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a) {
   CU(cudaGetLastError());
   MCOV_LAUNCH(ctx, kKFarScatter, (k_far_scatter<<<kNumSMsB200 * 2, 256, 0, s>>>(f)));
   CU(cudaGetLastError());
-  MCOV_LAUNCH(ctx, kKFusedTile, (k_fused_tile<<<(unsigned)n_tiles, kFusedThreads, 0, s>>>(f)));
+  {
+    const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)kNumSMsB200 * 4);   // persistent: 4 CTAs per SM
+    MCOV_LAUNCH(ctx, kKFusedTile, (k_fused_tile<<<grid, kFusedThreads, 0, s>>>(f)));
+  }
   CU(cudaGetLastError());
   return MCOV_OK;
 }
@@ -504,8 +507,8 @@ int mcov_region_stats_run(mcov_ctx* ctx, int64_t g, const int32_t* tid, const in
     CU(ctx->d_out.ensure((size_t)g * sizeof(mcov_region_stats)));
     CU(ctx->d_tasks.ensure(std::max<size_t>(tasks.size(), 1) * sizeof(StatTask)));
     CU(ctx->d_rlen.ensure((size_t)g * 8)); CU(ctx->d_rchunks.ensure((size_t)g * 4)); CU(ctx->d_rhist.ensure((size_t)g * 4));
-    // [region_done | hist_pool] are cleared together before every run
-    CU(ctx->d_pool.ensure((size_t)g * 4 + (size_t)std::max(n_multi, 1) * kHistBins * 4 + 16));
+    // [RegionScratch per multi-chunk region | hist_pool] are cleared together before every run
+    CU(ctx->d_pool.ensure((size_t)std::max(n_multi, 1) * (sizeof(RegionScratch) + (size_t)kHistBins * 4) + 16));
     int32_t* d_rlen = ctx->d_rlen.as<int32_t>();
     if (!tasks.empty()) CU(cudaMemcpyAsync(ctx->d_tasks.p, tasks.data(), tasks.size() * sizeof(StatTask), cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(d_rlen, rp.rlen.data(), (size_t)g * 4, cudaMemcpyHostToDevice, s));
@@ -517,7 +520,7 @@ int mcov_region_stats_run(mcov_ctx* ctx, int64_t g, const int32_t* tid, const in
     rp.g = g; rp.n_contigs_epoch = ctx->contig_epoch; rp.valid = true;
   }
   if (g > 0) {
-    const size_t done_bytes = ((size_t)g * 4 + 15) & ~(size_t)15;
+    const size_t done_bytes = (size_t)rp.n_multi * sizeof(RegionScratch);
     if (rp.n_multi) CU(cudaMemsetAsync(ctx->d_pool.p, 0, done_bytes + (size_t)rp.n_multi * kHistBins * 4, s));
     if (rp.n_tasks) {
       StatArgs a;
