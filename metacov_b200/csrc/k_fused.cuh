@@ -159,7 +159,7 @@ __device__ __noinline__ void prep_far(const FusedArgs& f, int64_t e0, int64_t e1
   }
 }
 
-__global__ void __launch_bounds__(kPrepThreads)
+__global__ void __launch_bounds__(kPrepThreads, 4)
 k_fused_prep(FusedArgs f) {
   const ExpandArgs& a = f.e;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -272,50 +272,43 @@ k_fused_prep(FusedArgs f) {
     }
 
     // ---- sortedness + tile boundaries (tile_first) -------------------------------------------------
+    // "sorted" is judged on the slot keys: that is the order the tile kernel relies on.
     {
-      int64_t tl[4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) tl[r] = min(key[r] >> kTileShift, last_tile);
-      // the read before this thread's: tile and (tid,pos) from the neighbouring lane, lane 0 reloads
-      int64_t prev_tile = __shfl_up_sync(0xffffffffu, tl[3], 1);
-      int32_t pt = __shfl_up_sync(0xffffffffu, T[3], 1), pp = __shfl_up_sync(0xffffffffu, P[3], 1);
-      bool has_prev = true;
+      int64_t prev_key = __shfl_up_sync(0xffffffffu, key[3], 1);
       if (lane == 0) {
-        if (i0 > 0 && i0 - 1 < n) {
-          pt = a.tid[i0 - 1]; pp = a.pos[i0 - 1];
-          int64_t l_, b_;
-          prev_tile = min(slot_key(a, pt, pp, f.n_slots, l_, b_) >> kTileShift, last_tile);
-        } else { has_prev = false; prev_tile = -1; }
+        prev_key = -1;
+        if (i0 > 0 && i0 - 1 < n) { int64_t l_, b_; prev_key = slot_key(a, a.tid[i0 - 1], a.pos[i0 - 1], f.n_slots, l_, b_); }
       }
-      bool bnd = false;
-      int64_t run = prev_tile;
+      const int64_t prev_tile = prev_key < 0 ? -1 : min(prev_key >> kTileShift, last_tile);
+      int64_t tl3 = min(key[3] >> kTileShift, last_tile);
+      bool bnd;
+      if (nv == kPrepPer) {
+        unsorted |= (key[0] < prev_key) | (key[1] < key[0]) | (key[2] < key[1]) | (key[3] < key[2]);
+        bnd = tl3 > prev_tile;                       // keys are monotone: any boundary shows up at the last read
+      } else {
+        int64_t run = prev_key;
+        bnd = false;
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        if (r < nv) {
-          uint32_t u0 = (uint32_t)pt, u1 = (uint32_t)T[r];
-          if (has_prev && (u1 < u0 || (u1 == u0 && P[r] < pp))) unsorted = 1;
-          bnd |= tl[r] > run;
-          run = max(run, tl[r]);
-          pt = T[r]; pp = P[r]; has_prev = true;
-        }
+        for (int r = 0; r < 4; ++r) if (r < nv) { unsorted |= key[r] < run; bnd |= min(key[r] >> kTileShift, last_tile) > prev_tile; run = key[r]; }
       }
       const bool is_last = nv > 0 && (i0 + nv == n);
       if (__any_sync(0xffffffffu, bnd || is_last))
-        prep_tile_boundaries(f.tile_first, i0, nv, prev_tile, tl[0], tl[1], tl[2], tl[3], is_last, n, last_tile, lane);
+        prep_tile_boundaries(f.tile_first, i0, nv, prev_tile, min(key[0] >> kTileShift, last_tile),
+                             min(key[1] >> kTileShift, last_tile), min(key[2] >> kTileShift, last_tile), tl3, is_last, n,
+                             last_tile, lane);
     }
 
     // ---- tile_agg: +1 per start, -1 per near end (far ends are handled with the far list) ----------
     {
-      uint32_t ptl[8];
       uint32_t mn = 0xffffffffu, mx = 0u;
       int net = 0;
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
-        bool c = span[r] > 0, nr = c && span[r] <= kNearSpan;
-        ptl[r] = c ? (uint32_t)(key[r] >> kTileShift) : 0xffffffffu;
-        ptl[4 + r] = nr ? (uint32_t)(endk[r] >> kTileShift) : 0xffffffffu;
-        if (c) { mn = min(mn, ptl[r]); mx = max(mx, ptl[r]); net += 1; }
-        if (nr) { mn = min(mn, ptl[4 + r]); mx = max(mx, ptl[4 + r]); net -= 1; }
+        if (span[r] > 0) {
+          uint32_t ts = (uint32_t)(key[r] >> kTileShift);
+          mn = min(mn, ts); mx = max(mx, ts); net += 1;
+          if (span[r] <= kNearSpan) { uint32_t te = (uint32_t)(endk[r] >> kTileShift); mx = max(mx, te); net -= 1; }
+        }
       }
       uint32_t wmin = __reduce_min_sync(0xffffffffu, mn), wmax = __reduce_max_sync(0xffffffffu, mx);
       if (wmin != 0xffffffffu) {
@@ -323,6 +316,13 @@ k_fused_prep(FusedArgs f) {
           int v = __reduce_add_sync(0xffffffffu, net);
           if (lane == 0 && v != 0) atomicAdd(f.tile_agg + wmin, v);
         } else {
+          uint32_t ptl[8];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            bool c = span[r] > 0, nr = c && span[r] <= kNearSpan;
+            ptl[r] = c ? (uint32_t)(key[r] >> kTileShift) : 0xffffffffu;
+            ptl[4 + r] = nr ? (uint32_t)(endk[r] >> kTileShift) : 0xffffffffu;
+          }
           prep_tile_agg_slow(f.tile_agg, ptl[0], ptl[1], ptl[2], ptl[3], ptl[4], ptl[5], ptl[6], ptl[7], lane);
         }
       }
