@@ -1,0 +1,124 @@
+"""The drop-in Python API and CLI on the GPU, against the committed golden vectors (reference
+tests/test_cli.py runs the same commands but only asserts exit_code == 0)."""
+import csv
+import io
+import os
+
+import numpy as np
+import pytest
+from click.testing import CliRunner
+
+from helpers import load_json, load_soa
+from oracle import bamio, cport
+from test_dropin_surface import BLAST7
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fixture_bam(tmp_path_factory):
+    """The reference fixture re-encoded from tests/golden/fixture_soa.npz (the GPU box has no /root/reference)."""
+    z, b = load_soa("fixture_soa.npz")
+    d = tmp_path_factory.mktemp("bam")
+    path = str(d / "fixture.bam")
+    so = z["seq_off"]
+    seqs = [z["seq"][so[i]:so[i + 1]] for i in range(len(b.tid))]
+    bamio.write_bam(path, [str(x) for x in z["references"]], z["lengths"].tolist(), b.tid, b.pos, b.flag, b.mapq,
+                    b.cig_off, b.cig, isize=z["isize"], names=[str(x) for x in z["names"]], seqs=seqs)
+    return path
+
+
+def test_classic_api_matches_golden(fixture_bam):
+    from metacov_b200 import AlignmentFile, pileup
+    gold = load_json("fixture_classic.json")
+    with AlignmentFile(fixture_bam) as bam:
+        assert bam.mapped == gold["mapped"] and bam.unmapped == gold["unmapped"]
+        for row in gold["classic"]:
+            got = pileup.classic(bam, row["ref"], row["start"], row["end"])
+            assert got == row["result"], row
+            assert list(got) == ["min", "max", "med", "std", "avg", "q23", "sum"]
+            assert isinstance(got["min"], int) and isinstance(got["sum"], int) and isinstance(got["std"], np.floating)
+        with pytest.raises(ValueError):
+            pileup.classic(bam, "ref1", 5, 5)                  # np.amin of an empty vector (pileup.py:19)
+        # pysam protocol: columns of a region
+        cols = {c.pos: c.n for c in bam.pileup("ref1", 0, 425)}
+        want = np.load(os.path.join(os.path.dirname(__file__), "golden", "fixture_depth_ref1.npy"))
+        assert all(cols.get(p, 0) == want[p] for p in range(425))
+    with pytest.raises(TypeError):
+        pileup.classic(object(), "ref1", 0, 5)                 # foreign bam objects: no CPU fallback
+
+
+def run_pileup(args):
+    from metacov_b200.cli import pileup
+    res = CliRunner().invoke(pileup, args)
+    assert res.exit_code == 0, res.output
+    return res
+
+
+def test_cli_pileup_blast7_and_header_regions(fixture_bam, tmp_path):
+    gold = load_json("fixture_classic.json")["classic"]
+    rb = tmp_path / "regions.blast7"
+    rb.write_text(BLAST7)
+    out = tmp_path / "out.csv"
+    run_pileup(["-b", fixture_bam, "-rb", str(rb), "-o", str(out)])
+    rows = list(csv.DictReader(open(out)))
+    assert list(rows[0]) == ["sacc", "start", "end", "avg", "max", "med", "min", "q23", "std", "sum"]
+    # regions.blast7 rows are golden rows 2..5 (the last one written reversed: 575..301)
+    assert [(r["sacc"], r["start"], r["end"]) for r in rows] == [("ref1", "1", "425"), ("ref2", "1", "575"),
+                                                                  ("ref2", "1", "300"), ("ref2", "575", "301")]
+    for r, g in zip(rows, gold[2:6]):
+        for k, v in g["result"].items():
+            assert float(r[k]) == float(v), (r, g)
+        assert r["sum"] == str(g["result"]["sum"]) and r["avg"] == str(np.float64(g["result"]["avg"]))
+    # regions from the BAM header (reference test_pileup2)
+    out2 = tmp_path / "out2.csv"
+    run_pileup(["-b", fixture_bam, "-o", str(out2)])
+    rows = list(csv.DictReader(open(out2)))
+    assert [(r["sacc"], r["start"], r["end"]) for r in rows] == [("ref1", "0", "425"), ("ref2", "0", "575")]
+    for r, g in zip(rows, gold[0:2]):
+        for k, v in g["result"].items():
+            assert float(r[k]) == float(v)
+    # CSV regions
+    rc = tmp_path / "regions.csv"
+    rc.write_text("sequence_id,start,end\nref2,301,575\n")
+    out3 = tmp_path / "out3.csv"
+    run_pileup(["-b", fixture_bam, "-rc", str(rc), "-o", str(out3)])
+    row = list(csv.DictReader(open(out3)))[0]
+    assert float(row["q23"]) == gold[5]["result"]["q23"] and row["min"] == "5"
+
+
+def test_scan_api_and_cli(fixture_bam, tmp_path):
+    from metacov_b200 import AlignmentFile, scan
+    from metacov_b200.cli import scan as scan_cmd
+    z, _ = load_soa("fixture_soa.npz")
+    # API: ByFlag(IsizeHist) over every record
+    calls = []
+    with AlignmentFile(fixture_bam) as af:
+        counters = scan.ByFlag([scan.IsizeHist()], [scan.Flags["Mapped"], scan.Flags["IsRead1"]])
+        n = scan.scan_reads(af, None, counters, 1000, lambda: calls.append(1))
+    assert n == 4112 and len(calls) == 4
+    rh, rc, rmx = cport.isize_hist(z["flag"], z["isize"], (0x4, 0x40), 1024)
+    for g, p in enumerate(counters.processors):
+        h = p.processors[0]
+        nz = np.nonzero(rh[g])[0]
+        assert h.max_isize == (int(nz[-1]) if len(nz) else 0)
+        assert np.array_equal(h.counts[:h.max_isize + 1], rh[g][:h.max_isize + 1])
+        assert h.counts.dtype == np.uint32 and len(h.counts) in (128, 256, 512)
+    # ungrouped list + maxreads
+    with AlignmentFile(fixture_bam) as af:
+        h = scan.IsizeHist()
+        assert scan.scan_reads(af, None, [h], maxreads=1000) == 1000
+    r1, _, _ = cport.isize_hist(z["flag"][:1000], z["isize"][:1000], (), 1024)
+    assert np.array_equal(h.counts[:h.max_isize + 1], r1[0][:h.max_isize + 1])
+    # CLI
+    out = tmp_path / "isize.csv"
+    res = CliRunner().invoke(scan_cmd, [fixture_bam, "-I", str(out), "-g", "Mapped"])
+    assert res.exit_code == 0, res.output
+    rows = list(csv.reader(open(out)))
+    assert rows[0] == ["n", "count", "Mapped"]
+    r2, _, _ = cport.isize_hist(z["flag"], z["isize"], (0x4,), 1024)
+    mapped_rows = [r for r in rows[1:] if r[2] == "Mapped"]
+    assert len(mapped_rows) == 249 and int(mapped_rows[0][1]) == int(r2[0][0]) and int(mapped_rows[210][1]) == int(r2[0][210])
+    # out-of-scope options fail loudly instead of computing something else
+    res = CliRunner().invoke(scan_cmd, [fixture_bam, "-o", str(tmp_path / "k.csv")])
+    assert res.exit_code != 0 and "scope" in res.output
