@@ -191,6 +191,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -216,12 +217,18 @@ def run_ours(args):
     stream = torch.cuda.current_stream().cuda_stream
     eng = CoverageEngine(lengths, device=local, stream=stream)
 
+    if world > 1:
+        cap = int(np.bincount(owner, minlength=world).max())
+        local_dev = torch.zeros(cap * 64, dtype=torch.uint8, device=dev)
+        out_dev = torch.empty(world * cap * 64, dtype=torch.uint8, device=dev)
+
     def step(batch):
-        eng.depth_sorted(batch, wait=False)       # verdict delivered by region_stats (one sync per step)
-        st = eng.region_stats(reg_tid, reg_start, reg_end)
-        if world > 1:
-            st = sharding.gather_region_stats(st, owner, rank, world, device=dev)
-        return st
+        eng.depth_sorted(batch, wait=False)       # verdict delivered by the next synchronising call
+        if world == 1:
+            return eng.region_stats(reg_tid, reg_start, reg_end)          # one sync per step
+        # N>1: records stay on the device, ONE all-gather over NCCL, one D2H of all records
+        eng.region_stats_enqueue(reg_tid, reg_start, reg_end, local_dev)
+        return sharding.gather_region_stats_device(local_dev, out_dev, owner, world)
 
     for _ in range(max(args.warmup, 3)):
         stats = step(dbatch)
@@ -269,9 +276,11 @@ def run_ours(args):
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
             eng.compute_depth(hbatch)
-            st = eng.region_stats(reg_tid, reg_start, reg_end)
-            if world > 1:
-                st = sharding.gather_region_stats(st, owner, rank, world, device=dev)
+            if world == 1:
+                st = eng.region_stats(reg_tid, reg_start, reg_end)
+            else:
+                eng.region_stats_enqueue(reg_tid, reg_start, reg_end, local_dev)
+                st = sharding.gather_region_stats_device(local_dev, out_dev, owner, world)
         barrier()
         dt = (time.perf_counter() - t0) / args.e2e_steps
         d_t = torch.tensor([dt], dtype=torch.float64, device=dev)

@@ -148,6 +148,16 @@ int  mcov_region_stats_run(mcov_ctx* ctx, int64_t g,
                            const int32_t* tid, const int32_t* start, const int32_t* end,
                            int32_t breadth_n, mcov_region_stats* host_out);
 
+/* Asynchronous variant for multi-GPU pipelines: the g records are written to
+ * DEVICE memory dev_out on the context's stream and the call returns without
+ * synchronising (the records can be handed to a collective on the same
+ * stream).  Regions whose flags carry bit1 (depth beyond the counting
+ * histogram) need mcov_region_stats_run for exact order statistics; zero-length
+ * regions are not zeroed; a pending sortedness verdict is not delivered. */
+int  mcov_region_stats_enqueue(mcov_ctx* ctx, int64_t g,
+                               const int32_t* tid, const int32_t* start, const int32_t* end,
+                               int32_t breadth_n, mcov_region_stats* dev_out);
+
 /* Fixed-window mean depth (additive feature named by north_star; no
  * reference counterpart): for every contig, ceil(len/window) float64 means,
  * concatenated in tid order into host_out (n_out = total windows). */

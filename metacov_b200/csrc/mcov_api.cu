@@ -449,13 +449,10 @@ int mcov_copy_depth(mcov_ctx* ctx, int32_t tid, int32_t start, int32_t end, int3
   return MCOV_OK;
 }
 
-int mcov_region_stats_run(mcov_ctx* ctx, int64_t g, const int32_t* tid, const int32_t* start, const int32_t* end,
-                          int32_t breadth_n, mcov_region_stats* host_out) {
-  if (!ctx) return MCOV_ERR_ARG;
-  if (ctx->state != kDepthReady) return fail(ctx, MCOV_ERR_STATE, "mcov_region_stats_run: depth not ready (finalize first)");
-  if (g < 0 || (g > 0 && (!tid || !start || !end || !host_out))) return fail(ctx, MCOV_ERR_ARG, "mcov_region_stats_run: bad arguments");
-  if (g > INT32_MAX) return fail(ctx, MCOV_ERR_RANGE, "mcov_region_stats_run: more than 2^31-1 regions");
-  CU(cudaSetDevice(ctx->device));
+// Build (or reuse) the chunk table of a region set and enqueue the statistics kernel writing g
+// records to d_out (device memory).
+static int stats_launch(mcov_ctx* ctx, int64_t g, const int32_t* tid, const int32_t* start, const int32_t* end,
+                        int32_t breadth_n, mcov_region_stats* d_out) {
   cudaStream_t s = ctx->stream;
   RegionPlan& rp = ctx->plan;
   // The chunk table of a region set is cached on the device: a caller that asks for the same
@@ -529,10 +526,27 @@ int mcov_region_stats_run(mcov_ctx* ctx, int64_t g, const int32_t* tid, const in
       a.region_chunks = ctx->d_rchunks.as<int32_t>(); a.region_hist = ctx->d_rhist.as<int32_t>();
       a.region_done = ctx->d_pool.as<uint32_t>();
       a.hist_pool = reinterpret_cast<uint32_t*>(ctx->d_pool.as<char>() + done_bytes);
-      a.out = ctx->d_out.as<mcov_region_stats>(); a.breadth_n = breadth_n;
+      a.out = d_out; a.breadth_n = breadth_n;
       MCOV_LAUNCH(ctx, kKRegionStats, (k_region_stats<<<(unsigned)rp.n_tasks, kStatThreads, 0, s>>>(a)));
       CU(cudaGetLastError());
     }
+  }
+  return MCOV_OK;
+}
+
+int mcov_region_stats_run(mcov_ctx* ctx, int64_t g, const int32_t* tid, const int32_t* start, const int32_t* end,
+                          int32_t breadth_n, mcov_region_stats* host_out) {
+  if (!ctx) return MCOV_ERR_ARG;
+  if (ctx->state != kDepthReady) return fail(ctx, MCOV_ERR_STATE, "mcov_region_stats_run: depth not ready (finalize first)");
+  if (g < 0 || (g > 0 && (!tid || !start || !end || !host_out))) return fail(ctx, MCOV_ERR_ARG, "mcov_region_stats_run: bad arguments");
+  if (g > INT32_MAX) return fail(ctx, MCOV_ERR_RANGE, "mcov_region_stats_run: more than 2^31-1 regions");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  RegionPlan& rp = ctx->plan;
+  if (g > 0) {
+    CU(ctx->d_out.ensure((size_t)g * sizeof(mcov_region_stats)));
+    int rc = stats_launch(ctx, g, tid, start, end, breadth_n, ctx->d_out.as<mcov_region_stats>());
+    if (rc) return rc;
     CU(cudaMemcpyAsync(host_out, ctx->d_out.p, (size_t)g * sizeof(mcov_region_stats), cudaMemcpyDeviceToHost, s));
   }
   PassCounters h;
@@ -560,6 +574,17 @@ int mcov_region_stats_run(mcov_ctx* ctx, int64_t g, const int32_t* tid, const in
       if (end[i] != start[i] && (host_out[i].flags & kStatOverflow)) host_out[i] = again[i];
   }
   return MCOV_OK;
+}
+
+int mcov_region_stats_enqueue(mcov_ctx* ctx, int64_t g, const int32_t* tid, const int32_t* start, const int32_t* end,
+                              int32_t breadth_n, mcov_region_stats* dev_out) {
+  if (!ctx) return MCOV_ERR_ARG;
+  if (ctx->state != kDepthReady) return fail(ctx, MCOV_ERR_STATE, "mcov_region_stats_enqueue: depth not ready");
+  if (g < 0 || (g > 0 && (!tid || !start || !end || !dev_out))) return fail(ctx, MCOV_ERR_ARG, "mcov_region_stats_enqueue: bad arguments");
+  if (g > INT32_MAX) return fail(ctx, MCOV_ERR_RANGE, "mcov_region_stats_enqueue: more than 2^31-1 regions");
+  if (g == 0) return MCOV_OK;
+  CU(cudaSetDevice(ctx->device));
+  return stats_launch(ctx, g, tid, start, end, breadth_n, dev_out);
 }
 
 int mcov_window_means(mcov_ctx* ctx, int32_t window, double* host_out, int64_t n_out) {

@@ -197,6 +197,17 @@ class CoverageEngine:
                                               int(breadth_n), _capi.ptr(out)))
         return out
 
+    def region_stats_enqueue(self, tid, start, end, out, breadth_n=1):
+        """Asynchronous: write len(tid) records into the CUDA uint8 tensor ``out`` (>= 64 bytes per
+        region) on the engine's stream; no synchronisation (see mcov_region_stats_enqueue)."""
+        tid = np.ascontiguousarray(tid, dtype=np.int32)
+        start = np.ascontiguousarray(start, dtype=np.int32)
+        end = np.ascontiguousarray(end, dtype=np.int32)
+        if out.numel() * out.element_size() < 64 * len(tid):
+            raise ValueError("output tensor too small")
+        self._check(lib.mcov_region_stats_enqueue(self._ctx, len(tid), _capi.ptr(tid), _capi.ptr(start),
+                                                  _capi.ptr(end), int(breadth_n), out.data_ptr()))
+
     def window_means(self, window):
         n_out = int(sum((int(l) + window - 1) // window for l in self.lengths))
         out = np.empty(n_out, dtype=np.float64)

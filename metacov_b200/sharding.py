@@ -88,3 +88,25 @@ def gather_region_stats(local_stats, owner, rank, world_size, device=None, group
         if len(idx):
             merged[idx] = flat[r, :len(idx) * rec].view(_capi.REGION_STATS_DTYPE)
     return merged
+
+
+def gather_region_stats_device(local_dev, out_dev, owner, world_size, group=None):
+    """Device-resident variant: ``local_dev`` (uint8 CUDA tensor, cap*64 bytes, this rank's records
+    written by ``CoverageEngine.region_stats_enqueue``) is all-gathered into ``out_dev``
+    (world*cap*64 bytes) over NCCL with no host round trip; one D2H copy then delivers all
+    records in region order."""
+    import torch.distributed as dist
+    rec = _capi.REGION_STATS_DTYPE.itemsize
+    if world_size > 1:
+        dist.all_gather_into_tensor(out_dev, local_dev, group=group)
+    else:
+        out_dev.copy_(local_dev)
+    cap = local_dev.numel() // rec
+    flat = out_dev.cpu().numpy().reshape(world_size, cap * rec)
+    owner = np.asarray(owner)
+    merged = np.zeros(len(owner), dtype=_capi.REGION_STATS_DTYPE)
+    for r in range(world_size):
+        idx = np.nonzero(owner == r)[0]
+        if len(idx):
+            merged[idx] = flat[r, :len(idx) * rec].view(_capi.REGION_STATS_DTYPE)
+    return merged
