@@ -168,7 +168,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(args.real_stdout, line)
 
 
 def batch_bytes(b):
@@ -191,7 +191,6 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -363,12 +362,29 @@ def run_ours(args):
         "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "aligned_bases_per_step": aligned_total,
     }
-    print(json.dumps(line))
+    emit(args.real_stdout, line)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
+    # stdout carries exactly ONE JSON line: everything else (NCCL's version banner, library chatter)
+    # goes to stderr until the line is printed
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        _main(real_stdout)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+
+
+def emit(real_stdout, line):
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
+
+def _main(real_stdout):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -380,6 +396,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    args.real_stdout = real_stdout
     if args.impl == "reference":
         run_reference(args)
     else:

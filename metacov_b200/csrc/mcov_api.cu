@@ -543,16 +543,21 @@ int mcov_region_stats_run(mcov_ctx* ctx, int64_t g, const int32_t* tid, const in
   CU(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
   RegionPlan& rp = ctx->plan;
+  // results and the pending verdict come back through one pinned staging buffer (a pageable
+  // destination would make the copy synchronous and slower)
+  const size_t out_bytes = (size_t)g * sizeof(mcov_region_stats);
+  CU(ctx->h_pin.ensure(out_bytes + sizeof(PassCounters)));
   if (g > 0) {
-    CU(ctx->d_out.ensure((size_t)g * sizeof(mcov_region_stats)));
+    CU(ctx->d_out.ensure(out_bytes));
     int rc = stats_launch(ctx, g, tid, start, end, breadth_n, ctx->d_out.as<mcov_region_stats>());
     if (rc) return rc;
-    CU(cudaMemcpyAsync(host_out, ctx->d_out.p, (size_t)g * sizeof(mcov_region_stats), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(ctx->h_pin.p, ctx->d_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
   }
-  PassCounters h;
-  if (ctx->verdict_pending) CU(cudaMemcpyAsync(&h, ctx->d_pc.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+  PassCounters* hp = reinterpret_cast<PassCounters*>(ctx->h_pin.as<char>() + out_bytes);
+  if (ctx->verdict_pending) CU(cudaMemcpyAsync(hp, ctx->d_pc.p, sizeof(PassCounters), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
-  if (ctx->verdict_pending) { int vr = fused_verdict(ctx, h); if (vr) return vr; }
+  if (ctx->verdict_pending) { PassCounters h = *hp; int vr = fused_verdict(ctx, h); if (vr) return vr; }
+  if (g > 0) std::memcpy(host_out, ctx->h_pin.p, out_bytes);
   // regions whose depth left the counting histogram's range: exact statistics by a GPU radix sort
   // of the region (rare: needs max_depth raised above 8190)
   bool redo = false;
