@@ -306,7 +306,8 @@ def run_ours(args):
     alg_bytes = {
         "k_fused_prep": 15 * n_reads + 4 * cig_pass + 8 * n_reads,
         "k_fused_tile": 8 * n_reads + 4 * slots,
-        "k_region_stats": 4 * L_regions + 64 * g,
+        "k_region_stats": 4 * int(lengths[lengths > 8192].astype(np.int64).sum()) + 64 * int((lengths > 8192).sum()),
+        "k_region_stats_small": 4 * int(lengths[lengths <= 8192].astype(np.int64).sum()) + 64 * int((lengths <= 8192).sum()),
         "k_expand": 15 * n_reads + 4 * cig_pass + 8 * n_pass,
         "k_scan_inplace": 8 * slots,
         "memset_depth": 4 * slots,
@@ -325,7 +326,7 @@ def run_ours(args):
             "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes"], "kernels": kernels,
             "timing": "CUDA-event pair around every launch on the launching stream, K steps run right after the timed region"}
-    whole_bytes = alg_bytes["k_fused_prep"] + alg_bytes["k_fused_tile"] + alg_bytes["k_region_stats"]
+    whole_bytes = alg_bytes["k_fused_prep"] + alg_bytes["k_fused_tile"] + 4 * L_regions + 64 * g
     roof["whole_step"] = {"algorithmic_bytes": whole_bytes, "gbs": whole_bytes / ms_step / 1e6,
                           "frac": whole_bytes / ms_step / 1e6 / peak}
 

@@ -44,7 +44,8 @@ enum PassState { kIdle = 0, kAccumulating = 1, kDepthReady = 2 };
 // kernel ids for the optional per-kernel CUDA-event timing (mcov_profile_*)
 enum KernelId {
   kKExpand = 0, kKScan, kKFusedPrep, kKTileFirst, kKScanCounts, kKFarScatter, kKFusedTile,
-  kKInitStats, kKRegionStats, kKWindowSums, kKIsizeHist, kKGroupCount, kKSortedStats, kKClear, kKernelCount
+  kKInitStats, kKRegionStats, kKWindowSums, kKIsizeHist, kKGroupCount, kKSortedStats, kKClear, kKRegionStatsSmall,
+  kKernelCount
 };
 
 struct ProfRec { int id; cudaEvent_t a, b; };
@@ -52,7 +53,7 @@ struct ProfRec { int id; cudaEvent_t a, b; };
 // cached chunk table of the last region set (mcov_region_stats_run)
 struct RegionPlan {
   bool valid = false;
-  int64_t g = 0, n_tasks = 0;
+  int64_t g = 0, n_tasks = 0, n_small = 0;
   int32_t n_multi = 0;
   int64_t n_contigs_epoch = -1;
   std::vector<int32_t> tid, start, end, rlen, rpad;

@@ -58,26 +58,21 @@ struct WalkOut {
   int mn, mx, med_lo, med_hi;
 };
 
-// Walk a kHistBins histogram held in shared memory; all threads participate, the result is valid
-// on thread 0.  n = number of values the histogram describes.
-__device__ __forceinline__ WalkOut hist_walk(const uint32_t* hist, long long n, int breadth_n,
-                                             unsigned long long* s_u64 /* [6][kStatThreads/32] */,
-                                             int* s_i32 /* [4][kStatThreads/32] */, int* s_med /* 2 */) {
-  constexpr int kW = kStatThreads / 32;
-  constexpr int kPer = kHistBins / kStatThreads;             // 16 bins per thread
+// Walk the bins [lo, hi] of a counting histogram held in shared memory (bins outside the range are
+// not touched and may hold garbage); all THREADS threads participate, the result is valid on thread
+// 0.  n = number of values the histogram describes.
+template <int THREADS>
+__device__ __forceinline__ WalkOut hist_walk(const uint32_t* hist, long long n, int breadth_n, int lo, int hi,
+                                             unsigned long long* s_u64 /* [6][THREADS/32] */,
+                                             int* s_i32 /* [4][THREADS/32] */, int* s_med /* 2 */) {
+  constexpr int kW = THREADS / 32;
   const long long k1 = n / 4, k2 = n - n / 4;                // interquartile ranks [k1, k2)
   const long long m1 = (n - 1) / 2, m2 = n / 2;              // median pair
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int b0 = t * kPer;
+  const int per = (hi - lo + THREADS) / THREADS;             // bins per thread (>= 1)
+  const int b0 = lo + t * per, b1 = min(b0 + per, hi + 1);   // this thread's bins [b0, b1)
   unsigned long long local = 0;
-  {
-    const uint4* h4 = reinterpret_cast<const uint4*>(hist + b0);
-#pragma unroll
-    for (int k = 0; k < kPer / 4; ++k) {
-      uint4 q = h4[k];
-      local += (unsigned long long)q.x + q.y + q.z + q.w;
-    }
-  }
+  for (int b = b0; b < b1; ++b) local += hist[b];
   // block exclusive scan of `local`
   unsigned long long x = local;
 #pragma unroll
@@ -95,20 +90,19 @@ __device__ __forceinline__ WalkOut hist_walk(const uint32_t* hist, long long n, 
   unsigned long long sumsq = 0;
   int mn = INT_MAX, mx = INT_MIN;
   if (local) {
-#pragma unroll
-    for (int k = 0; k < kPer; ++k) {
-      long long cn = hist[b0 + k];
+    for (int bb = b0; bb < b1; ++bb) {
+      long long cn = hist[bb];
       if (cn) {
-        long long b = b0 + k;
+        long long b = bb;
         sum += b * cn;
         sumsq += (unsigned long long)(b * b) * (unsigned long long)cn;
         ge1 += b >= 1 ? cn : 0;
         geN += b >= breadth_n ? cn : 0;
-        mn = min(mn, (int)b); mx = max(mx, (int)b);
-        long long lo = c > k1 ? c : k1, hi = (c + cn) < k2 ? (c + cn) : k2;
-        if (hi > lo) iq += (hi - lo) * b;
-        if (c <= m1 && m1 < c + cn) s_med[0] = (int)b;
-        if (c <= m2 && m2 < c + cn) s_med[1] = (int)b;
+        mn = min(mn, bb); mx = max(mx, bb);
+        long long l2 = c > k1 ? c : k1, h2 = (c + cn) < k2 ? (c + cn) : k2;
+        if (h2 > l2) iq += (h2 - l2) * b;
+        if (c <= m1 && m1 < c + cn) s_med[0] = bb;
+        if (c <= m2 && m2 < c + cn) s_med[1] = bb;
         c += cn;
       }
     }
@@ -146,19 +140,14 @@ __device__ __forceinline__ void write_stats(mcov_region_stats* out, const WalkOu
   *out = r;
 }
 
-// one aligned vector of four depths -> histogram, equal neighbours merged first
+// One aligned vector of four depths -> four increments.  Plain +1 updates compile to
+// ATOMS.POPC.INC, which the shared-memory unit sustains at a far higher rate than value-carrying
+// ATOMS.ADD (measured: tools/ubench_hist.cu) -- so neighbours are deliberately NOT merged first.
 __device__ __forceinline__ void hist_vec(uint32_t* s_hist, const int4& q) {
-  int b0 = hist_bin(q.x), b1 = hist_bin(q.y), b2 = hist_bin(q.z), b3 = hist_bin(q.w);
-  if (b0 == b1 && b2 == b3) {
-    if (b0 == b2) atomicAdd(&s_hist[b0], 4u);
-    else { atomicAdd(&s_hist[b0], 2u); atomicAdd(&s_hist[b2], 2u); }
-  } else {
-    uint32_t c0 = 1;
-    if (b1 == b0) ++c0; else { atomicAdd(&s_hist[b0], c0); b0 = b1; c0 = 1; }
-    if (b2 == b0) ++c0; else { atomicAdd(&s_hist[b0], c0); b0 = b2; c0 = 1; }
-    if (b3 == b0) ++c0; else { atomicAdd(&s_hist[b0], c0); b0 = b3; c0 = 1; }
-    atomicAdd(&s_hist[b0], c0);
-  }
+  atomicAdd(&s_hist[hist_bin(q.x)], 1u);
+  atomicAdd(&s_hist[hist_bin(q.y)], 1u);
+  atomicAdd(&s_hist[hist_bin(q.z)], 1u);
+  atomicAdd(&s_hist[hist_bin(q.w)], 1u);
 }
 
 __device__ __forceinline__ void hist_partial(uint32_t* s_hist, const int4& q, int lo, int hi) {
@@ -252,8 +241,64 @@ k_region_stats(StatArgs a) {
     if (t == 0) s_hist[0] += (uint32_t)pad;
     __syncthreads();
   }
-  WalkOut w = hist_walk(s_hist, n_region, a.breadth_n, s_u64, s_i32, s_med);
+  WalkOut w = hist_walk<kStatThreads>(s_hist, n_region, a.breadth_n, 0, kHistBins - 1, s_u64, s_i32, s_med);
   if (t == 0) write_stats(out, w);
+}
+
+// ---- small regions (<= kSmallRegion slots): one 256-thread CTA per region ---------------------------
+// Hundreds of thousands of short contigs (config C3) make the fixed cost of clearing and walking
+// 8192 bins dominate.  Here a first pass finds the region's min / max, only that bin range is cleared
+// and walked, and the second pass (served by L1/L2) does the increments.
+constexpr int kSmallThreads = 256;
+constexpr int kSmallRegion = 8192;
+
+__global__ void __launch_bounds__(kSmallThreads, 6)
+k_region_stats_small(StatArgs a) {
+  __shared__ __align__(16) uint32_t s_hist[kHistBins];
+  __shared__ unsigned long long s_u64[6 * (kSmallThreads / 32)];
+  __shared__ int s_i32[4 * (kSmallThreads / 32)];
+  __shared__ int s_med[2];
+  const StatTask task = a.tasks[blockIdx.x];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int g = task.region;
+  const int pad = a.region_pad[g];
+  const long long n_region = (long long)a.region_len[g] + pad;
+  const int64_t s0 = task.slot, s1 = task.slot + task.n;
+  const int64_t a0 = s0 & ~(int64_t)3;
+  const int64_t nvec = ((s1 - a0) + 3) >> 2;
+  const int4* vp = reinterpret_cast<const int4*>(a.depth + a0);
+  // pass 1: min / max bin of the region
+  int lo = pad > 0 ? 0 : kHistBins - 1, hi = 0;
+  for (int64_t j = t; j < nvec; j += kSmallThreads) {
+    int4 q = __ldg(vp + j);
+    int v[4] = {q.x, q.y, q.z, q.w};
+    int64_t e0 = a0 + (j << 2);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (e0 + k >= s0 && e0 + k < s1) { int b = hist_bin(v[k]); lo = min(lo, b); hi = max(hi, b); }
+  }
+  lo = warp_min(lo); hi = warp_max(hi);
+  if (lane == 0) { s_i32[warp] = lo; s_i32[kSmallThreads / 32 + warp] = hi; }
+  __syncthreads();
+  lo = kHistBins - 1; hi = 0;
+#pragma unroll
+  for (int k = 0; k < kSmallThreads / 32; ++k) { lo = min(lo, s_i32[k]); hi = max(hi, s_i32[kSmallThreads / 32 + k]); }
+  if (hi < lo) hi = lo;
+  for (int b = lo + t; b <= hi; b += kSmallThreads) s_hist[b] = 0;
+  __syncthreads();
+  // pass 2: increments
+  for (int64_t j = t; j < nvec; j += kSmallThreads) {
+    int4 q = __ldg(vp + j);
+    int v[4] = {q.x, q.y, q.z, q.w};
+    int64_t e0 = a0 + (j << 2);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (e0 + k >= s0 && e0 + k < s1) atomicAdd(&s_hist[hist_bin(v[k])], 1u);
+  }
+  if (pad > 0 && t == 0) atomicAdd(&s_hist[0], (uint32_t)pad);
+  __syncthreads();
+  WalkOut w = hist_walk<kSmallThreads>(s_hist, n_region, a.breadth_n, lo, hi, s_u64, s_i32, s_med);
+  if (t == 0) write_stats(a.out + g, w);
 }
 
 // Fixed-window mean depth: one warp per window.

@@ -401,7 +401,7 @@ int mcov_pass_info_get(mcov_ctx* ctx, mcov_pass_info* out) {
 static const char* kKernelNames[kKernelCount] = {
     "k_expand", "k_scan_inplace", "k_fused_prep", "k_tile_first", "k_scan_counts", "k_far_scatter", "k_fused_tile",
     "k_init_region_stats", "k_region_stats", "k_window_sums", "k_isize_hist", "k_group_count", "k_sorted_stats",
-    "memset_depth"};
+    "memset_depth", "k_region_stats_small"};
 
 int64_t mcov_launch_count(const mcov_ctx* ctx) { return ctx ? ctx->n_launches : 0; }
 
@@ -475,8 +475,8 @@ static int stats_launch(mcov_ctx* ctx, int64_t g, const int32_t* tid, const int3
     // chunk length: enough chunks to fill the machine several times over; a region is split evenly
     int64_t chunk_max = (total / ((int64_t)kNumSMsB200 * 24) + 4095) / 4096 * 4096;
     chunk_max = std::max<int64_t>(8192, std::min<int64_t>(32768, chunk_max));
-    std::vector<StatTask> tasks;
-    tasks.reserve((size_t)(g + total / chunk_max + 1));
+    std::vector<StatTask> tasks, small;
+    tasks.reserve((size_t)(total / chunk_max + 1024));
     rp.rlen.assign((size_t)g, 0); rp.rpad.assign((size_t)g, 0);
     std::vector<int32_t> rchunks((size_t)g), rhist((size_t)g);
     int32_t n_multi = 0;
@@ -487,6 +487,13 @@ static int stats_launch(mcov_ctx* ctx, int64_t g, const int32_t* tid, const int3
       int32_t pad = (int32_t)((int64_t)end[i] - start[i] - n);
       int32_t nch = (int32_t)((n + chunk_max - 1) / chunk_max);
       if (nch == 0 && pad > 0) nch = 1;             // nothing but zeros: one empty chunk finishes it
+      if (nch == 1 && n <= kSmallRegion) {          // short region: the range-limited kernel
+        StatTask t;
+        t.slot = ctx->off[tid[i]] + cs; t.n = (int32_t)n; t.region = (int32_t)i;
+        small.push_back(t);
+        rp.rlen[i] = (int32_t)n; rp.rpad[i] = pad; rchunks[i] = 1; rhist[i] = -1;
+        continue;
+      }
       int64_t per = nch > 0 ? (((n + nch - 1) / nch + 3) & ~(int64_t)3) : 0;     // even split, 16-byte multiple
       rp.rlen[i] = (int32_t)n; rp.rpad[i] = pad; rchunks[i] = nch;
       rhist[i] = nch > 1 ? n_multi++ : -1;
@@ -500,7 +507,9 @@ static int stats_launch(mcov_ctx* ctx, int64_t g, const int32_t* tid, const int3
       }
     }
     rp.n_tasks = (int64_t)tasks.size();
+    rp.n_small = (int64_t)small.size();
     rp.n_multi = n_multi;
+    tasks.insert(tasks.end(), small.begin(), small.end());     // [chunk tasks | small-region tasks]
     CU(ctx->d_out.ensure((size_t)g * sizeof(mcov_region_stats)));
     CU(ctx->d_tasks.ensure(std::max<size_t>(tasks.size(), 1) * sizeof(StatTask)));
     CU(ctx->d_rlen.ensure((size_t)g * 8)); CU(ctx->d_rchunks.ensure((size_t)g * 4)); CU(ctx->d_rhist.ensure((size_t)g * 4));
@@ -528,6 +537,16 @@ static int stats_launch(mcov_ctx* ctx, int64_t g, const int32_t* tid, const int3
       a.hist_pool = reinterpret_cast<uint32_t*>(ctx->d_pool.as<char>() + done_bytes);
       a.out = d_out; a.breadth_n = breadth_n;
       MCOV_LAUNCH(ctx, kKRegionStats, (k_region_stats<<<(unsigned)rp.n_tasks, kStatThreads, 0, s>>>(a)));
+      CU(cudaGetLastError());
+    }
+    if (rp.n_small) {
+      StatArgs a;
+      int32_t* d_rlen = ctx->d_rlen.as<int32_t>();
+      a.depth = ctx->depth; a.tasks = ctx->d_tasks.as<StatTask>() + rp.n_tasks; a.region_len = d_rlen; a.region_pad = d_rlen + g;
+      a.region_chunks = ctx->d_rchunks.as<int32_t>(); a.region_hist = ctx->d_rhist.as<int32_t>();
+      a.region_done = nullptr; a.hist_pool = nullptr;
+      a.out = d_out; a.breadth_n = breadth_n;
+      MCOV_LAUNCH(ctx, kKRegionStatsSmall, (k_region_stats_small<<<(unsigned)rp.n_small, kSmallThreads, 0, s>>>(a)));
       CU(cudaGetLastError());
     }
   }
