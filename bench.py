@@ -41,7 +41,7 @@ def peaks():
 class ClockSampler(threading.Thread):
     """SM clock and throttle reasons sampled during the timed region (NVML)."""
 
-    def __init__(self, index, period=0.002):
+    def __init__(self, index, period=0.01):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -231,6 +231,21 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         stats = step(dbatch)
+    if args.breakdown:
+        def tt(fn, n=30):
+            barrier(); t0 = time.perf_counter()
+            for _ in range(n):
+                fn()
+            torch.cuda.synchronize(); return (time.perf_counter() - t0) / n * 1e6
+        parts = {"depth_only": tt(lambda: eng.depth_sorted(dbatch, wait=False))}
+        if world > 1:
+            parts["stats_enqueue"] = tt(lambda: eng.region_stats_enqueue(reg_tid, reg_start, reg_end, local_dev))
+            parts["all_gather"] = tt(lambda: dist.all_gather_into_tensor(out_dev, local_dev))
+            parts["gather+d2h+merge"] = tt(lambda: sharding.gather_region_stats_device(local_dev, out_dev, owner, world))
+        else:
+            parts["stats"] = tt(lambda: eng.region_stats(reg_tid, reg_start, reg_end))
+        parts["step"] = tt(lambda: step(dbatch))
+        print("rank %d breakdown us: %s" % (rank, {k: round(v, 1) for k, v in parts.items()}), file=sys.stderr)
     info = eng.pass_info()
     aligned_local = info["aligned_bases"]
     aligned_t = torch.tensor([aligned_local], dtype=torch.int64, device=dev)
@@ -239,17 +254,19 @@ def run_ours(args):
     aligned_total = int(aligned_t.item())
 
     # ---- timed region: device-resident inputs ---------------------------------------------------
-    sampler = ClockSampler(local)
+    # NVML is a shared, lock-protected service: only rank 0 samples (its GPU runs the same kernels)
+    sampler = ClockSampler(local) if rank == 0 else None
     l0 = eng.launch_count()
     barrier()
-    sampler.start()
+    if sampler:
+        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
         step(dbatch)
     ev1.record()
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     ms_total = ev0.elapsed_time(ev1)
     t_t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -396,6 +413,7 @@ def _main(real_stdout):
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="print a host-side time breakdown of one step to stderr")
     args = ap.parse_args()
     args.real_stdout = real_stdout
     if args.impl == "reference":
