@@ -217,9 +217,8 @@ def run_ours(args):
     eng = CoverageEngine(lengths, device=local, stream=stream)
 
     if world > 1:
-        cap = int(np.bincount(owner, minlength=world).max())
-        local_dev = torch.zeros(cap * 64, dtype=torch.uint8, device=dev)
-        out_dev = torch.empty(world * cap * 64, dtype=torch.uint8, device=dev)
+        dg = sharding.DeviceGather(owner, world, dev)
+        local_dev, out_dev = dg.local_dev, dg.out_dev
 
     def step(batch):
         eng.depth_sorted(batch, wait=False)       # verdict delivered by the next synchronising call
@@ -227,7 +226,7 @@ def run_ours(args):
             return eng.region_stats(reg_tid, reg_start, reg_end)          # one sync per step
         # N>1: records stay on the device, ONE all-gather over NCCL, one D2H of all records
         eng.region_stats_enqueue(reg_tid, reg_start, reg_end, local_dev)
-        return sharding.gather_region_stats_device(local_dev, out_dev, owner, world)
+        return dg.gather()
 
     for _ in range(max(args.warmup, 3)):
         stats = step(dbatch)
@@ -241,7 +240,7 @@ def run_ours(args):
         if world > 1:
             parts["stats_enqueue"] = tt(lambda: eng.region_stats_enqueue(reg_tid, reg_start, reg_end, local_dev))
             parts["all_gather"] = tt(lambda: dist.all_gather_into_tensor(out_dev, local_dev))
-            parts["gather+d2h+merge"] = tt(lambda: sharding.gather_region_stats_device(local_dev, out_dev, owner, world))
+            parts["gather+d2h+merge"] = tt(lambda: dg.gather())
         else:
             parts["stats"] = tt(lambda: eng.region_stats(reg_tid, reg_start, reg_end))
         parts["step"] = tt(lambda: step(dbatch))
@@ -296,7 +295,7 @@ def run_ours(args):
                 st = eng.region_stats(reg_tid, reg_start, reg_end)
             else:
                 eng.region_stats_enqueue(reg_tid, reg_start, reg_end, local_dev)
-                st = sharding.gather_region_stats_device(local_dev, out_dev, owner, world)
+                st = dg.gather()
         barrier()
         dt = (time.perf_counter() - t0) / args.e2e_steps
         d_t = torch.tensor([dt], dtype=torch.float64, device=dev)

@@ -31,6 +31,7 @@ def test_partition_balances_and_covers():
     b = sharding.partition_contigs([10, 10], [1, 1], 4)
     assert b[0] == 0 and b[-1] == 2 and np.all(np.diff(b) >= 0)
     owner = sharding.assign_regions([0, 1, 1, 0], b)
+    assert hasattr(sharding, "DeviceGather")
     assert all(b[o] <= t < b[o + 1] for o, t in zip(owner, [0, 1, 1, 0]))
     tid = np.array([0, 0, 2, 2, 2, -1])
     assert sharding.reads_per_contig_from_tid(tid, 3).tolist() == [2, 0, 3]
