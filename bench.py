@@ -213,8 +213,13 @@ def run_ours(args):
     reg_end = lengths.astype(np.int32)
     owner = sharding.assign_regions(np.arange(w.n_contigs), bounds)
 
-    stream = torch.cuda.current_stream().cuda_stream
-    eng = CoverageEngine(lengths, device=local, stream=stream)
+    # One explicit (non-default) torch stream carries everything: the engine's kernels, the NCCL
+    # gather (which orders itself against torch's *current* stream) and the timing events.  The
+    # legacy default stream has handle 0, which mcov_create would take as "make your own stream".
+    work_stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(work_stream)
+    eng = CoverageEngine(lengths, device=local, stream=work_stream.cuda_stream)
+    assert work_stream.cuda_stream != 0
 
     if world > 1:
         dg = sharding.DeviceGather(owner, world, dev)
