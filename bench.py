@@ -231,7 +231,7 @@ def run_ours(args):
             return eng.region_stats(reg_tid, reg_start, reg_end)          # one sync per step
         # N>1: records stay on the device, ONE all-gather over NCCL, one D2H of all records
         eng.region_stats_enqueue(reg_tid, reg_start, reg_end, local_dev)
-        return dg.gather()
+        return dg.gather(want_host=(rank == 0))
 
     for _ in range(max(args.warmup, 3)):
         stats = step(dbatch)
@@ -300,7 +300,7 @@ def run_ours(args):
                 st = eng.region_stats(reg_tid, reg_start, reg_end)
             else:
                 eng.region_stats_enqueue(reg_tid, reg_start, reg_end, local_dev)
-                st = dg.gather()
+                st = dg.gather(want_host=(rank == 0))
         barrier()
         dt = (time.perf_counter() - t0) / args.e2e_steps
         d_t = torch.tensor([dt], dtype=torch.float64, device=dev)

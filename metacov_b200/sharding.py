@@ -117,25 +117,33 @@ class DeviceGather:
         self.out_host = torch.empty(self.world * self.cap * self.rec, dtype=torch.uint8).pin_memory()
         self.merged = np.zeros(self.n_regions, dtype=_capi.REGION_STATS_DTYPE)
 
-    def gather(self):
+    def gather(self, want_host=True):
+        """All-gather the records; with want_host (rank 0: it writes the CSV) copy them to pinned
+        host memory and return them in region order, else only wait for the collective."""
         import torch
         import torch.distributed as dist
         if self.world > 1:
             dist.all_gather_into_tensor(self.out_dev, self.local_dev, group=self.group)
         else:
             self.out_dev.copy_(self.local_dev)
+        if not want_host:
+            torch.cuda.current_stream().synchronize()
+            return None
         self.out_host.copy_(self.out_dev, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         flat = self.out_host.numpy().reshape(self.world, self.cap * self.rec)
+        if self.monotone and np.all(self.counts == self.cap):
+            return flat.reshape(-1).view(_capi.REGION_STATS_DTYPE)       # zero-copy: already in region order
+        out_u8 = self.merged.view(np.uint8).reshape(-1, self.rec)
         pos = 0
         for r in range(self.world):
             k = int(self.counts[r])
             if not k:
                 continue
-            part = flat[r, :k * self.rec].view(_capi.REGION_STATS_DTYPE)
+            part = flat[r, :k * self.rec].reshape(k, self.rec)          # plain byte rows: memcpy speed
             if self.monotone:
-                self.merged[pos:pos + k] = part
+                out_u8[pos:pos + k] = part
                 pos += k
             else:
-                self.merged[self.index[r]] = part
+                out_u8[self.index[r]] = part
         return self.merged
