@@ -159,18 +159,35 @@ __device__ __noinline__ void prep_far(const FusedArgs& f, int64_t e0, int64_t e1
   }
 }
 
+// Hot loop of the fused path's first kernel.  All per-read arithmetic is 32-bit and contig
+// relative: with base = contig offset, tb = base >> 12 and bo = base & 4095 the tile of position q
+// is tb + ((bo + q) >> 12) and the low 32 bits of the slot key are (uint32)base + q; 64-bit slot
+// numbers are only formed on the rare paths (tile boundaries, far reads).
 __global__ void __launch_bounds__(kPrepThreads, 4)
 k_fused_prep(FusedArgs f) {
   const ExpandArgs& a = f.e;
+  const int32_t* __restrict__ g_tid = a.tid;
+  const int32_t* __restrict__ g_pos = a.pos;
+  const uint16_t* __restrict__ g_flag = a.flag;
+  const uint8_t* __restrict__ g_mapq = a.mapq;
+  const uint32_t* __restrict__ g_off = a.cig_off;
+  const uint32_t* __restrict__ g_cig = a.cig;
+  const int64_t* __restrict__ g_coff = a.contig_off;
+  const int32_t* __restrict__ g_clen = a.contig_len;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned long long n_pass = 0, aligned = 0;
-  int unsorted = 0;
-  uint32_t max_span = 0;
+  const uint32_t n_contigs = (uint32_t)a.n_contigs;
+  const uint32_t drop = (uint32_t)a.filt.flag_filter | 0x4u, req = a.filt.flag_require, minq = a.filt.min_mapq;
+  const bool orph = a.filt.ignore_orphans != 0;
+  const int vec_ok = f.vec_ok;
   const int64_t n = a.n;
   const int64_t n_groups = (n + kPrepPer - 1) / kPrepPer;
   const int64_t g_round = (n_groups + 31) & ~(int64_t)31;     // whole warps iterate together
   const int64_t g_stride = (int64_t)gridDim.x * kPrepThreads;
-  const int64_t last_tile = f.n_tiles;                        // tile_first has n_tiles+1 entries
+  const uint32_t last_tile = (uint32_t)f.n_tiles;             // tile_first has n_tiles+1 entries
+  const uint32_t nslot_tb = (uint32_t)(f.n_slots >> kTileShift), nslot_bo = (uint32_t)(f.n_slots & (kTile - 1));
+  unsigned long long aligned = 0;
+  uint32_t n_pass = 0, max_span = 0;
+  int unsorted = 0;
 
 #pragma unroll 1
   for (int64_t g = (int64_t)blockIdx.x * kPrepThreads + threadIdx.x; g < g_round; g += g_stride) {
@@ -178,13 +195,13 @@ k_fused_prep(FusedArgs f) {
     int32_t T[4], P[4];
     uint32_t F[4], Q[4], O[5];
     const int nv = (int)min((int64_t)kPrepPer, max((int64_t)0, n - i0));     // valid reads of this thread
-    if (nv == kPrepPer && f.vec_ok) {
-      int4 t4 = *reinterpret_cast<const int4*>(a.tid + i0);
-      int4 p4 = *reinterpret_cast<const int4*>(a.pos + i0);
-      ushort4 f4 = *reinterpret_cast<const ushort4*>(a.flag + i0);
-      uchar4 q4 = *reinterpret_cast<const uchar4*>(a.mapq + i0);
-      uint4 o4 = *reinterpret_cast<const uint4*>(a.cig_off + i0);
-      O[4] = a.cig_off[i0 + 4];
+    if (nv == kPrepPer && vec_ok) {
+      int4 t4 = *reinterpret_cast<const int4*>(g_tid + i0);
+      int4 p4 = *reinterpret_cast<const int4*>(g_pos + i0);
+      ushort4 f4 = *reinterpret_cast<const ushort4*>(g_flag + i0);
+      uchar4 q4 = *reinterpret_cast<const uchar4*>(g_mapq + i0);
+      uint4 o4 = *reinterpret_cast<const uint4*>(g_off + i0);
+      O[4] = g_off[i0 + 4];
       T[0] = t4.x; T[1] = t4.y; T[2] = t4.z; T[3] = t4.w;
       P[0] = p4.x; P[1] = p4.y; P[2] = p4.z; P[3] = p4.w;
       F[0] = f4.x; F[1] = f4.y; F[2] = f4.z; F[3] = f4.w;
@@ -194,35 +211,37 @@ k_fused_prep(FusedArgs f) {
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         bool v = r < nv;
-        T[r] = v ? a.tid[i0 + r] : -1;
-        P[r] = v ? a.pos[i0 + r] : 0;
-        F[r] = v ? (uint32_t)a.flag[i0 + r] : 0x4u;
-        Q[r] = v ? (uint32_t)a.mapq[i0 + r] : 0u;
+        T[r] = v ? g_tid[i0 + r] : -1;
+        P[r] = v ? g_pos[i0 + r] : 0;
+        F[r] = v ? (uint32_t)g_flag[i0 + r] : 0x4u;
+        Q[r] = v ? (uint32_t)g_mapq[i0 + r] : 0u;
       }
       // padding reads get an empty CIGAR: their offsets all equal cig_off[n]
 #pragma unroll
-      for (int r = 0; r <= 4; ++r) O[r] = (i0 <= n) ? a.cig_off[min(i0 + r, n)] : 0u;
+      for (int r = 0; r <= 4; ++r) O[r] = (i0 <= n) ? g_off[min(i0 + r, n)] : 0u;
     }
 
     // ---- filter + CIGAR reduction ------------------------------------------------------------
-    bool pass[4];
+    unsigned passm = 0, coop = 0;
     uint32_t reflen[4];                 // a read's reference length fits 32 bits (BAM positions are int32)
-    unsigned coop = 0;
     uint32_t op0[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      pass[r] = r < nv && read_passes(F[r], Q[r], a.filt) && (uint32_t)T[r] < (uint32_t)a.n_contigs;
+      // pysam __advance_samtools + bam_plp_push's UNMAP drop
+      bool p = r < nv && !(F[r] & drop) && (!req || (F[r] & req)) && Q[r] >= minq && !(orph && (F[r] & 3u) == 1u) &&
+               (uint32_t)T[r] < n_contigs;
       uint32_t nc = O[r + 1] - O[r];
-      bool c = pass[r] && nc > kThreadOps;
+      bool c = p && nc > kThreadOps;
+      passm |= p ? (1u << r) : 0u;
       coop |= c ? (1u << r) : 0u;
-      op0[r] = (pass[r] && !c && nc > 0) ? __ldg(a.cig + O[r]) : 0u;     // four independent loads
+      op0[r] = (p && !c && nc > 0) ? __ldg(g_cig + O[r]) : 0u;          // four independent loads
     }
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       reflen[r] = cigar_ref_len(op0[r]);
-      if (pass[r] && !((coop >> r) & 1u) && O[r + 1] - O[r] > 1) {
+      if (((passm & ~coop) >> r) & 1u) {
 #pragma unroll 1
-        for (uint32_t k = O[r] + 1; k < O[r + 1]; ++k) reflen[r] += cigar_ref_len(__ldg(a.cig + k));
+        for (uint32_t k = O[r] + 1; k < O[r + 1]; ++k) reflen[r] += cigar_ref_len(__ldg(g_cig + k));
       }
     }
     // long CIGARs: the whole warp reduces one read at a time with 128-bit loads
@@ -234,7 +253,7 @@ k_fused_prep(FusedArgs f) {
       uint32_t oe = r == 0 ? O[1] : r == 1 ? O[2] : r == 2 ? O[3] : O[4];
       ob = __shfl_sync(0xffffffffu, ob, src);
       oe = __shfl_sync(0xffffffffu, oe, src);
-      unsigned long long v = warp_cigar_reflen_call(a.cig, ob, oe, lane, a.cig_aligned16);
+      unsigned long long v = warp_cigar_reflen_call(g_cig, ob, oe, lane, a.cig_aligned16);
       if (lane == src) {
         uint32_t v32 = v > 0x7fffffffull ? 0x7fffffffu : (uint32_t)v;
         if (r == 0) reflen[0] = v32; else if (r == 1) reflen[1] = v32; else if (r == 2) reflen[2] = v32; else reflen[3] = v32;
@@ -242,59 +261,85 @@ k_fused_prep(FusedArgs f) {
       }
     }
 
-    // ---- slot keys, clipped intervals, records --------------------------------------------------
-    int64_t key[4], endk[4];
-    uint32_t span[4];
-    int64_t c_len = 0, c_base = f.n_slots;
-    int32_t c_tid = -1;
+    // ---- clipped intervals, records, tiles: 32-bit, contig relative ------------------------------
+    uint32_t klo[4], span[4], tls[4], tle[4];     // key low bits, span, start tile, end tile
+    uint32_t qq[4];                               // clamped start inside the contig
+    int32_t c_tid = INT_MIN;
+    uint32_t c_len = 0, c_blo = (uint32_t)f.n_slots, c_tb = nslot_tb, c_bo = nslot_bo;
     unsigned farmask = 0;
+    uint32_t al32 = 0;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      if (T[r] != c_tid) { c_tid = T[r]; (void)slot_key(a, T[r], 0, f.n_slots, c_len, c_base); }
-      int64_t q = P[r] < 0 ? 0 : (P[r] > c_len ? c_len : (int64_t)P[r]);
-      key[r] = c_base + q;                       // invalid contig: c_base = n_slots, c_len = 0
-      span[r] = 0; endk[r] = key[r];
-      if (pass[r]) {
-        int64_t e = (int64_t)P[r] + (int64_t)reflen[r];
-        e = e < 0 ? 0 : (e > c_len ? c_len : e);
+      if (T[r] != c_tid) {                        // contig change (once per thread in the common case)
+        c_tid = T[r];
+        if ((uint32_t)T[r] < n_contigs) {
+          int64_t base = g_coff[T[r]];
+          c_len = (uint32_t)g_clen[T[r]];
+          c_blo = (uint32_t)base; c_tb = (uint32_t)(base >> kTileShift); c_bo = (uint32_t)base & (kTile - 1);
+        } else { c_len = 0; c_blo = (uint32_t)f.n_slots; c_tb = nslot_tb; c_bo = nslot_bo; }
+      }
+      uint32_t q = P[r] < 0 ? 0u : min((uint32_t)P[r], c_len);
+      qq[r] = q;
+      klo[r] = c_blo + q;
+      tls[r] = min(c_tb + ((c_bo + q) >> kTileShift), last_tile);
+      span[r] = 0; tle[r] = tls[r];
+      if ((passm >> r) & 1u) {
+        // end = clamp(pos + reflen, 0, len), in 64 bits only for the (never negative in practice) sum
+        int64_t e64 = (int64_t)P[r] + (int64_t)reflen[r];
+        uint32_t e = e64 < 0 ? 0u : (e64 > (int64_t)c_len ? c_len : (uint32_t)e64);
         if (e > q) {
-          span[r] = (uint32_t)(e - q); endk[r] = c_base + e; n_pass += 1; aligned += reflen[r];
+          span[r] = e - q; tle[r] = c_tb + ((c_bo + e) >> kTileShift);
+          n_pass += 1; al32 += reflen[r];
           if (span[r] > kNearSpan) farmask |= 1u << r; else max_span = max(max_span, span[r]);
         }
       }
     }
+    aligned += al32;
     if (nv == kPrepPer) {
       uint4* out = reinterpret_cast<uint4*>(f.rec + i0);
-      out[0] = make_uint4((uint32_t)key[0], span[0], (uint32_t)key[1], span[1]);
-      out[1] = make_uint4((uint32_t)key[2], span[2], (uint32_t)key[3], span[3]);
+      out[0] = make_uint4(klo[0], span[0], klo[1], span[1]);
+      out[1] = make_uint4(klo[2], span[2], klo[3], span[3]);
     } else {
-      for (int r = 0; r < nv; ++r) f.rec[i0 + r] = make_uint2((uint32_t)key[r], span[r]);
+      for (int r = 0; r < nv; ++r) f.rec[i0 + r] = make_uint2(klo[r], span[r]);
     }
 
     // ---- sortedness + tile boundaries (tile_first) -------------------------------------------------
-    // "sorted" is judged on the slot keys: that is the order the tile kernel relies on.
+    // "sorted" is judged on (contig, clamped position), i.e. on the slot keys the tile kernel relies on
     {
-      int64_t prev_key = __shfl_up_sync(0xffffffffu, key[3], 1);
+      uint32_t pt = __shfl_up_sync(0xffffffffu, (uint32_t)T[3], 1), pq = __shfl_up_sync(0xffffffffu, qq[3], 1);
+      uint32_t ptile = __shfl_up_sync(0xffffffffu, tls[3], 1);
+      bool has_prev = true;
       if (lane == 0) {
-        prev_key = -1;
-        if (i0 > 0 && i0 - 1 < n) { int64_t l_, b_; prev_key = slot_key(a, a.tid[i0 - 1], a.pos[i0 - 1], f.n_slots, l_, b_); }
+        has_prev = i0 > 0 && i0 - 1 < n;
+        if (has_prev) {
+          int32_t t0 = g_tid[i0 - 1], p0 = g_pos[i0 - 1];
+          pt = (uint32_t)t0;
+          if ((uint32_t)t0 < n_contigs) {
+            int64_t base = g_coff[t0]; uint32_t len = (uint32_t)g_clen[t0];
+            pq = p0 < 0 ? 0u : min((uint32_t)p0, len);
+            ptile = min((uint32_t)(base >> kTileShift) + ((((uint32_t)base & (kTile - 1)) + pq) >> kTileShift), last_tile);
+          } else { pq = 0; ptile = min(nslot_tb, last_tile); }
+        }
       }
-      const int64_t prev_tile = prev_key < 0 ? -1 : min(prev_key >> kTileShift, last_tile);
-      int64_t tl3 = min(key[3] >> kTileShift, last_tile);
-      bool bnd;
-      if (nv == kPrepPer) {
-        unsorted |= (key[0] < prev_key) | (key[1] < key[0]) | (key[2] < key[1]) | (key[3] < key[2]);
-        bnd = tl3 > prev_tile;                       // keys are monotone: any boundary shows up at the last read
-      } else {
-        int64_t run = prev_key;
-        bnd = false;
+      // invalid contigs compare as the largest id (they sort last, like tid -1 in a BAM)
+      uint32_t ut[4];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) if (r < nv) { unsorted |= key[r] < run; bnd |= min(key[r] >> kTileShift, last_tile) > prev_tile; run = key[r]; }
+      for (int r = 0; r < 4; ++r) ut[r] = (uint32_t)T[r] < n_contigs ? (uint32_t)T[r] : 0xffffffffu;
+      if (pt >= n_contigs) pt = 0xffffffffu;
+      bool bnd = false;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        if (r < nv) {
+          uint32_t t0 = r ? ut[r - 1] : pt, q0 = r ? qq[r - 1] : pq;
+          bool ok = (r == 0 && !has_prev) || ut[r] > t0 || (ut[r] == t0 && (ut[r] == 0xffffffffu || qq[r] >= q0));
+          unsorted |= !ok;
+        }
       }
+      const uint32_t tl_last = nv > 0 ? (nv == 4 ? tls[3] : nv == 3 ? tls[2] : nv == 2 ? tls[1] : tls[0]) : 0u;
+      bnd = nv > 0 && (!has_prev || tl_last > ptile);
       const bool is_last = nv > 0 && (i0 + nv == n);
       if (__any_sync(0xffffffffu, bnd || is_last))
-        prep_tile_boundaries(f.tile_first, i0, nv, prev_tile, min(key[0] >> kTileShift, last_tile),
-                             min(key[1] >> kTileShift, last_tile), min(key[2] >> kTileShift, last_tile), tl3, is_last, n,
+        prep_tile_boundaries(f.tile_first, i0, nv, has_prev ? (int64_t)ptile : -1, tls[0], tls[1], tls[2], tls[3], is_last, n,
                              last_tile, lane);
     }
 
@@ -305,9 +350,8 @@ k_fused_prep(FusedArgs f) {
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         if (span[r] > 0) {
-          uint32_t ts = (uint32_t)(key[r] >> kTileShift);
-          mn = min(mn, ts); mx = max(mx, ts); net += 1;
-          if (span[r] <= kNearSpan) { uint32_t te = (uint32_t)(endk[r] >> kTileShift); mx = max(mx, te); net -= 1; }
+          mn = min(mn, tls[r]); mx = max(mx, tls[r]); net += 1;
+          if (span[r] <= kNearSpan) { mx = max(mx, tle[r]); net -= 1; }
         }
       }
       uint32_t wmin = __reduce_min_sync(0xffffffffu, mn), wmax = __reduce_max_sync(0xffffffffu, mx);
@@ -320,25 +364,34 @@ k_fused_prep(FusedArgs f) {
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
             bool c = span[r] > 0, nr = c && span[r] <= kNearSpan;
-            ptl[r] = c ? (uint32_t)(key[r] >> kTileShift) : 0xffffffffu;
-            ptl[4 + r] = nr ? (uint32_t)(endk[r] >> kTileShift) : 0xffffffffu;
+            ptl[r] = c ? tls[r] : 0xffffffffu;
+            ptl[4 + r] = nr ? tle[r] : 0xffffffffu;
           }
           prep_tile_agg_slow(f.tile_agg, ptl[0], ptl[1], ptl[2], ptl[3], ptl[4], ptl[5], ptl[6], ptl[7], lane);
         }
       }
     }
-    if (__any_sync(0xffffffffu, farmask != 0)) prep_far(f, endk[0], endk[1], endk[2], endk[3], farmask, lane);
+    if (__any_sync(0xffffffffu, farmask != 0)) {
+      // 64-bit end slots only here
+      int64_t e64[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        int64_t base = ((farmask >> r) & 1u) ? g_coff[T[r]] : 0;
+        e64[r] = base + qq[r] + span[r];
+      }
+      prep_far(f, e64[0], e64[1], e64[2], e64[3], farmask, lane);
+    }
   }
 
   // block-level reduction of the pass counters
-  n_pass = warp_sum(n_pass);
+  unsigned long long np64 = warp_sum((unsigned long long)n_pass);
   aligned = warp_sum(aligned);
   unsorted = __any_sync(0xffffffffu, unsorted);
   max_span = (uint32_t)warp_max((int)max_span);
   __shared__ unsigned long long s_np[kPrepThreads / 32], s_al[kPrepThreads / 32];
   __shared__ int s_un[kPrepThreads / 32];
   __shared__ uint32_t s_ms[kPrepThreads / 32];
-  if (lane == 0) { s_np[warp] = n_pass; s_al[warp] = aligned; s_un[warp] = unsorted; s_ms[warp] = max_span; }
+  if (lane == 0) { s_np[warp] = np64; s_al[warp] = aligned; s_un[warp] = unsorted; s_ms[warp] = max_span; }
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned long long np = 0, al = 0; int un = 0; uint32_t ms = 0;
