@@ -173,11 +173,12 @@ typedef struct mcov_pass_info {
   int64_t n_reads;        /* records pushed                                   */
   int64_t n_pass;         /* records that passed the filter with reflen > 0   */
   int64_t aligned_bases;  /* sum of reflen over passing reads (unclipped)     */
-  int32_t max_depth_seen; /* max depth over all contigs                       */
+  int32_t max_depth_seen; /* max depth over all contigs (before the cap)      */
   int32_t cap_metric;     /* max_p depth[p-1]+starts[p] (fused path) or an
                              upper bound of it (push path)                    */
   int32_t sorted;         /* 1 if the input was coordinate-sorted             */
-  int32_t reserved;
+  int32_t cap_contigs;    /* contigs whose depth was replayed under the max_depth
+                             cap (fused path; 0 = the cap never fired)        */
 } mcov_pass_info;
 int  mcov_pass_info_get(mcov_ctx* ctx, mcov_pass_info* out);
 

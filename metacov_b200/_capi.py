@@ -57,7 +57,7 @@ assert REGION_STATS_DTYPE.itemsize == C.sizeof(RegionStats) == 64
 class PassInfo(C.Structure):
     _fields_ = [("n_reads", C.c_int64), ("n_pass", C.c_int64), ("aligned_bases", C.c_int64),
                 ("max_depth_seen", C.c_int32), ("cap_metric", C.c_int32), ("sorted", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("cap_contigs", C.c_int32)]
 
 
 class KernelTime(C.Structure):

@@ -151,10 +151,12 @@ class AlignmentFile:
         if self._engine is None:
             s = self.soa()
             eng = CoverageEngine(self.lengths, device=self._device, filt=self._filter_kw)
-            eng.compute_depth(ReadBatch(s["tid"], s["pos"], s["flag"], s["mapq"], s["cig_off"], s["cig"]))
+            path = eng.compute_depth(ReadBatch(s["tid"], s["pos"], s["flag"], s["mapq"], s["cig_off"], s["cig"]))
             info = eng.pass_info()
             md = eng.filter.max_depth
-            if md > 0 and info["cap_metric"] > md:
+            # the fused (sorted) path replays htslib's cap exactly on the GPU; the any-order path cannot
+            # (the cap is only defined for sorted input), so it refuses rather than return uncapped numbers
+            if path != "fused" and md > 0 and info["cap_metric"] > md:
                 eng.close()
                 from .pileup import DepthCapError
                 raise DepthCapError(

@@ -44,7 +44,7 @@ enum PassState { kIdle = 0, kAccumulating = 1, kDepthReady = 2 };
 // kernel ids for the optional per-kernel CUDA-event timing (mcov_profile_*)
 enum KernelId {
   kKExpand = 0, kKScan, kKFusedPrep, kKTileFirst, kKScanCounts, kKFarScatter, kKFusedTile,
-  kKInitStats, kKRegionStats, kKWindowSums, kKIsizeHist, kKGroupCount, kKSortedStats, kKClear, kKRegionStatsSmall,
+  kKInitStats, kKRegionStats, kKWindowSums, kKIsizeHist, kKGroupCount, kKSortedStats, kKClear, kKRegionStatsSmall, kKCapReplay,
   kKernelCount
 };
 
@@ -96,6 +96,8 @@ struct mcov_ctx {
   bool verdict_pending = false;   // an asynchronous fused pass has not been checked for sortedness yet
   int64_t contig_epoch = 0;
   mcov::RegionPlan plan;
+  int32_t cap_contigs = 0;        // contigs replayed under htslib's max_depth cap in the last fused pass
+  std::vector<unsigned char> fused_blob;   // FusedArgs of the last fused pass (k_fused.cuh), for the cap replay
 
   // fused (sorted) path scratch
   mcov::DevBuf d_end_slot, d_start_slot, d_far_list, d_tile_cnt, d_tile_off, d_far_sorted;

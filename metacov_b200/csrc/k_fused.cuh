@@ -59,6 +59,8 @@ struct FusedArgs {
   uint32_t* far_sorted;       // [far_cap] in-tile offsets bucketed by tile
   int64_t* tile_first;        // [n_tiles+1]
   int32_t* depth;
+  int32_t* tile_cap;          // [n_tiles] max of depth[p-1]+starts[p] in the tile, written only when > max_depth
+  int32_t max_depth;          // htslib maxcnt (<= 0: cap disabled)
   int vec_ok;                 // SoA base pointers aligned for 128-bit loads
 };
 
@@ -564,15 +566,19 @@ k_fused_tile(FusedArgs f) {
     for (int k = 0; k < kFusedThreads / 32; ++k) off += (k < warp) ? s_warp[k] : 0;
     int4* out = reinterpret_cast<int4*>(f.depth + base);
     const int64_t n_vec = (f.n_slots - base) >> 2;
+    int cap_t = 0;
 #pragma unroll
     for (int j = 0; j < kScanVec; ++j) {
       int idx = (warp * kScanVec + j) * 32 + lane;
       int o = off + run[j];
       v[j].x += o; v[j].y += o; v[j].z += o; v[j].w += o;
       mx = max(mx, max(max(v[j].x, v[j].y), max(v[j].z, v[j].w)));
-      cap = max(cap, max(max(v[j].x + en[j].x, v[j].y + en[j].y), max(v[j].z + en[j].z, v[j].w + en[j].w)));
+      cap_t = max(cap_t, max(max(v[j].x + en[j].x, v[j].y + en[j].y), max(v[j].z + en[j].z, v[j].w + en[j].w)));
       if (idx < n_vec) st_stream_int4(out + idx, v[j]);
     }
+    cap = max(cap, cap_t);
+    // htslib's cap could fire somewhere in this tile (rare): remember the tile for the exact replay
+    if (f.max_depth > 0 && cap_t > f.max_depth) atomicMax(f.tile_cap + tile, cap_t);
     __syncthreads();                                     // s_warp is rewritten by the next tile
     m_cur = m_next; m_next = m_nn;
 #pragma unroll
@@ -590,6 +596,59 @@ k_fused_tile(FusedArgs f) {
     if (m > 0) atomicMax(&pc->max_depth_seen, m);
     if (c2 > 0) atomicMax(&pc->cap_metric, c2);
   }
+}
+
+// Exact replay of htslib's max_depth cap for the contigs where it can fire (SURVEY.md Appendix
+// A-6; restated sequentially in oracle/coverage.c::orc_depth_plp).  For a whole-contig iterator the
+// machine reduces to a recurrence over positions: with m(p) passing reads starting at p (file
+// order) and D[p-1] the capped depth just before, the first
+//     K(p) = max(1, min(m(p), max_depth - D[p-1]))
+// of them are kept (the first read at a position is pushed while the iterator is still behind it
+// and is never dropped; every later one is dropped once max_depth reads are buffered).  D depends
+// on earlier decisions, so a contig is replayed by ONE thread, in place: the contig's slots are
+// first cleared, kept reads add +1 at their end slot, and the running depth overwrites each slot
+// as the walk passes it.  Only contigs flagged through tile_cap are replayed.
+__global__ void k_cap_replay(FusedArgs f, const int32_t* __restrict__ contigs, int n_flagged) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_flagged) return;
+  const int c = contigs[k];
+  const int64_t base = f.e.contig_off[c];
+  const int32_t len = f.e.contig_len[c];
+  const uint32_t base_lo = (uint32_t)base;
+  int32_t* d = f.depth + base;
+  for (int32_t p = 0; p <= len; ++p) d[p] = 0;
+  // first read of the contig: start at the first read of the tile holding the contig's first slot
+  int64_t j = f.tile_first[base >> kTileShift];
+  const int64_t n = f.e.n;
+  while (j < n && (int32_t)(f.rec[j].x - base_lo) < 0) ++j;
+  int depth = 0;
+  const int maxcnt = f.max_depth;
+  int32_t p = 0;
+  while (p < len) {
+    // reads starting at p (sorted keys): keep the first K
+    int kept = 0;
+    bool first = true;
+    while (j < n) {
+      uint2 r = f.rec[j];
+      int32_t q = (int32_t)(r.x - base_lo);
+      if (q != p || q > len) break;
+      ++j;
+      if (r.y == 0) continue;                       // filtered / empty read
+      bool keep = first || (depth + kept) < maxcnt; // depth = D[p-1] = reads buffered from earlier positions
+      first = false;
+      if (keep) { ++kept; d[p + (int32_t)r.y] += 1; }
+    }
+    int32_t ends = d[p];
+    depth += kept - ends;
+    d[p] = depth;
+    ++p;
+    // skip ahead over positions without starts while nothing changes: still must fold the ends in
+    if (j >= n || (int32_t)(f.rec[j].x - base_lo) > len || (int32_t)(f.rec[j].x - base_lo) < 0) {
+      for (; p < len; ++p) { depth -= d[p]; d[p] = depth; }
+      break;
+    }
+  }
+  d[len] = 0;                                       // sentinel slot
 }
 
 }  // namespace mcov

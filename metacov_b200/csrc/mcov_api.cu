@@ -115,9 +115,10 @@ int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a) {
   const int64_t scan_len = 2 * cnt_pad;                                // [tile_agg | tile_cnt]
   const int64_t scan_tiles = (scan_len + kScanTile - 1) / kScanTile;
   const uint32_t far_cap = (uint32_t)std::min<int64_t>(std::max<int64_t>(n, 1), kFarCapDefault);
-  // one zeroed scratch block: [tile_agg | tile_cnt | tile_cursor | scan status]
+  // one zeroed scratch block: [tile_agg | tile_cnt | tile_cursor | tile_cap | scan status]
   const size_t o_agg = 0, o_cnt = o_agg + (size_t)cnt_pad * 4, o_cur = o_cnt + (size_t)cnt_pad * 4,
-               o_st = (o_cur + (size_t)n_tiles * 4 + 7) & ~(size_t)7, z_bytes = o_st + (size_t)scan_tiles * 8;
+               o_cap = o_cur + (size_t)n_tiles * 4, o_st = (o_cap + (size_t)n_tiles * 4 + 7) & ~(size_t)7,
+               z_bytes = o_st + (size_t)scan_tiles * 8;
   CU(ctx->d_status.ensure(z_bytes));
   CU(ctx->d_start_slot.ensure((size_t)(std::max<int64_t>(n, 1) + 4) * sizeof(uint2)));   // rec
   CU(ctx->d_tile_off.ensure((size_t)(n_tiles + 1) * 8));                                 // tile_first
@@ -139,6 +140,8 @@ int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a) {
   f.far_sorted = ctx->d_far_sorted.as<uint32_t>();
   f.tile_first = ctx->d_tile_off.as<int64_t>();
   f.depth = ctx->depth;
+  f.tile_cap = reinterpret_cast<int32_t*>(z + o_cap);
+  f.max_depth = ctx->filt.max_depth;
   auto al = [](const void* p, uintptr_t m) { return (reinterpret_cast<uintptr_t>(p) & (m - 1)) == 0; };
   f.vec_ok = (n > 0 && al(a.tid, 16) && al(a.pos, 16) && al(a.cig_off, 16) && al(a.flag, 8) && al(a.mapq, 4)) ? 1 : 0;
   if (n > 0) {
@@ -153,6 +156,7 @@ int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a) {
   CU(cudaGetLastError());
   MCOV_LAUNCH(ctx, kKFarScatter, (k_far_scatter<<<kNumSMsB200 * 2, 256, 0, s>>>(f)));
   CU(cudaGetLastError());
+  ctx->fused_blob.assign(reinterpret_cast<const unsigned char*>(&f), reinterpret_cast<const unsigned char*>(&f) + sizeof(f));
   {
     const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)kNumSMsB200 * 4);   // persistent: 4 CTAs per SM
     MCOV_LAUNCH(ctx, kKFusedTile, (k_fused_tile<<<grid, kFusedThreads, 0, s>>>(f)));
@@ -173,6 +177,35 @@ int fused_verdict(mcov_ctx* ctx, const PassCounters& h) {
   if ((int64_t)h.n_far > std::min<int64_t>(std::max<int64_t>(ctx->n_reads_pushed, 1), kFarCapDefault)) {
     ctx->state = kIdle;
     return fail(ctx, MCOV_ERR_RANGE, "mcov_depth_sorted: too many long-span reads for the bucket list; use mcov_begin/push/finalize");
+  }
+  ctx->cap_contigs = 0;
+  if (ctx->filt.max_depth > 0 && h.cap_metric > ctx->filt.max_depth) {
+    // htslib's max_depth cap fires somewhere: replay the affected contigs exactly (k_cap_replay)
+    FusedArgs f;
+    std::memcpy(&f, ctx->fused_blob.data(), sizeof(f));
+    std::vector<int32_t> tc((size_t)f.n_tiles);
+    CU(cudaMemcpyAsync(tc.data(), f.tile_cap, (size_t)f.n_tiles * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    std::vector<int32_t> flagged;
+    for (int64_t T = 0; T < f.n_tiles; ++T) {
+      if (tc[T] <= ctx->filt.max_depth) continue;
+      // contigs with a slot in tile T
+      int64_t lo = T * kTile, hi = std::min<int64_t>(lo + kTile, ctx->n_slots);
+      int32_t c = (int32_t)(std::upper_bound(ctx->off.begin(), ctx->off.begin() + ctx->n_contigs, lo) - ctx->off.begin()) - 1;
+      for (; c < ctx->n_contigs && ctx->off[c] < hi; ++c)
+        if (c >= 0 && (flagged.empty() || flagged.back() != c)) flagged.push_back(c);
+    }
+    std::sort(flagged.begin(), flagged.end());
+    flagged.erase(std::unique(flagged.begin(), flagged.end()), flagged.end());
+    if (!flagged.empty()) {
+      CU(ctx->d_win_n.ensure(flagged.size() * 4));
+      CU(cudaMemcpyAsync(ctx->d_win_n.p, flagged.data(), flagged.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+      MCOV_LAUNCH(ctx, kKCapReplay, (k_cap_replay<<<(unsigned)((flagged.size() + 31) / 32), 32, 0, ctx->stream>>>(
+          f, ctx->d_win_n.as<int32_t>(), (int)flagged.size())));
+      CU(cudaGetLastError());
+      CU(cudaStreamSynchronize(ctx->stream));
+      ctx->cap_contigs = (int32_t)flagged.size();
+    }
   }
   return MCOV_OK;
 }
@@ -395,14 +428,14 @@ int mcov_pass_info_get(mcov_ctx* ctx, mcov_pass_info* out) {
   out->max_depth_seen = h.max_depth_seen;
   out->cap_metric = h.cap_metric;
   out->sorted = h.unsorted ? 0 : 1;
-  out->reserved = 0;
+  out->cap_contigs = ctx->cap_contigs;
   return MCOV_OK;
 }
 
 static const char* kKernelNames[kKernelCount] = {
     "k_expand", "k_scan_inplace", "k_fused_prep", "k_tile_first", "k_scan_counts", "k_far_scatter", "k_fused_tile",
     "k_init_region_stats", "k_region_stats", "k_window_sums", "k_isize_hist", "k_group_count", "k_sorted_stats",
-    "memset_depth", "k_region_stats_small"};
+    "memset_depth", "k_region_stats_small", "k_cap_replay"};
 
 int64_t mcov_launch_count(const mcov_ctx* ctx) { return ctx ? ctx->n_launches : 0; }
 

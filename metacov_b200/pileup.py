@@ -12,8 +12,9 @@ from . import _capi
 
 
 class DepthCapError(RuntimeError):
-    """htslib's max_depth cap (pysam default 8000) would have dropped reads in
-    this BAM; the capped pileup is order-dependent and is not reproduced."""
+    """htslib's max_depth cap (pysam default 8000) would have dropped reads but the
+    reads are not coordinate-sorted, so the (order-dependent) capped pileup is undefined.
+    For sorted input the cap is replayed exactly on the GPU (k_cap_replay)."""
 
 
 def finish_classic(st, n):

@@ -265,3 +265,43 @@ def test_device_resident_inputs_match_host_inputs():
         torch.cuda.synchronize()
         o = eng.contig_offset(3)
         assert np.array_equal(buf[o:o + int(w.contig_len[3])].cpu().numpy(), want[3])
+
+
+def test_max_depth_cap_replayed_exactly():
+    """Where htslib's maxcnt fires, the fused path replays the affected contigs and must equal the
+    sequential htslib machine (oracle orc_depth_plp), statistics included."""
+    from metacov_b200 import ReadBatch
+    rng = np.random.default_rng(9)
+    lengths = np.array([3000, 1500, 2500], np.int32)
+    tid, pos = [], []
+    # contig 0: a 12 000-deep stack at 300 plus background and a second pile at 310; contig 1: shallow;
+    # contig 2: ramp that crosses 8000 gradually (never capped: reads arrive at distinct positions)
+    for c, ps in ((0, np.r_[np.full(12000, 300), np.full(3000, 310), rng.integers(0, 2800, 4000)]),
+                  (1, rng.integers(0, 1400, 2000)),
+                  (2, np.r_[np.repeat(np.arange(100, 1100), 9), rng.integers(0, 2300, 500)])):
+        ps = np.sort(ps)
+        tid += [c] * len(ps); pos += ps.tolist()
+    n = len(tid)
+    rl = rng.integers(60, 140, n)
+    rl[np.array(tid) == 2] = 1200
+    b = ReadBatch(np.array(tid, np.int32), np.array(pos, np.int32), np.zeros(n, np.uint16), np.full(n, 30, np.uint8),
+                  np.arange(n + 1, dtype=np.uint32), (rl.astype(np.uint32) << 4))
+    want, off, info = cport.depth(b, lengths, mode="plp")
+    assert info["dropped_by_cap"] > 0
+    with engine_for(lengths) as eng:
+        eng.depth_sorted(b)
+        pi = eng.pass_info()
+        assert pi["cap_metric"] > 8000 and pi["cap_contigs"] >= 1
+        for c in range(3):
+            assert np.array_equal(eng.copy_depth(c), want[off[c]:off[c] + lengths[c]]), c
+        t, a, e = [0, 1, 2, 0], [0, 0, 0, 250], [3000, 1500, 2500, 400]
+        got = eng.region_stats(t, a, e)
+        ref = cport.region_stats(want, off, lengths, t, a, e)
+        for k in ("sum", "sumsq", "iq_sum", "min", "max", "med_lo", "med_hi"):
+            assert np.array_equal(got[k], ref[k]), k
+    # cap disabled: plain difference-array depth again
+    with engine_for(lengths, max_depth=0) as eng:
+        eng.depth_sorted(b)
+        assert eng.pass_info()["cap_contigs"] == 0
+        free, _, _ = cport.depth(b, lengths, mode="diff")
+        assert np.array_equal(eng.copy_depth(0), free[off[0]:off[0] + lengths[0]])
