@@ -467,6 +467,12 @@ k_fused_tile(FusedArgs f) {
   uint2 own[kPreOwn], back;
   prefetch_recs(f, m_cur, own, back);
   int mx = 0, cap = 0;
+  {
+    int4* z0 = reinterpret_cast<int4*>(s_start);
+    int4* z1 = reinterpret_cast<int4*>(s_end);
+    for (int k = threadIdx.x; k < kTile / 4; k += kFusedThreads) { z0[k] = make_int4(0, 0, 0, 0); z1[k] = make_int4(0, 0, 0, 0); }
+  }
+  __syncthreads();
 
 #pragma unroll 1
   for (; tile < f.n_tiles; tile += stride) {
@@ -474,12 +480,6 @@ k_fused_tile(FusedArgs f) {
     uint2 n_own[kPreOwn], n_back;
     prefetch_recs(f, m_next, n_own, n_back);            // empty ranges when tile+stride is past the end
     TileMeta m_nn = load_tile_meta(f, tile + 2 * stride);
-    {
-      int4* z0 = reinterpret_cast<int4*>(s_start);
-      int4* z1 = reinterpret_cast<int4*>(s_end);
-      for (int k = threadIdx.x; k < kTile / 4; k += kFusedThreads) { z0[k] = make_int4(0, 0, 0, 0); z1[k] = make_int4(0, 0, 0, 0); }
-    }
-    __syncthreads();
     const int64_t base = tile << kTileShift;
     const uint32_t base_lo = (uint32_t)base;
 
@@ -561,6 +561,12 @@ k_fused_tile(FusedArgs f) {
     }
     if (lane == 31) s_warp[warp] = acc;
     __syncthreads();                                     // also: every warp has read s_start/s_end
+    {
+      // clear the counters for the next tile now; the barrier at the end of the body publishes it
+      int4* z0 = reinterpret_cast<int4*>(s_start);
+      int4* z1 = reinterpret_cast<int4*>(s_end);
+      for (int k = threadIdx.x; k < kTile / 4; k += kFusedThreads) { z0[k] = make_int4(0, 0, 0, 0); z1[k] = make_int4(0, 0, 0, 0); }
+    }
     int off = m_cur.carry;
 #pragma unroll
     for (int k = 0; k < kFusedThreads / 32; ++k) off += (k < warp) ? s_warp[k] : 0;
@@ -579,7 +585,7 @@ k_fused_tile(FusedArgs f) {
     cap = max(cap, cap_t);
     // htslib's cap could fire somewhere in this tile (rare): remember the tile for the exact replay
     if (f.max_depth > 0 && cap_t > f.max_depth) atomicMax(f.tile_cap + tile, cap_t);
-    __syncthreads();                                     // s_warp is rewritten by the next tile
+    __syncthreads();                                     // counters cleared; s_warp is rewritten by the next tile
     m_cur = m_next; m_next = m_nn;
 #pragma unroll
     for (int u = 0; u < kPreOwn; ++u) own[u] = n_own[u];

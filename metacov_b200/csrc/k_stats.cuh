@@ -162,7 +162,7 @@ struct RegionScratch {          // per multi-chunk region, zeroed before every r
   uint32_t pad;
 };
 
-__global__ void __launch_bounds__(kStatThreads, 3)
+__global__ void __launch_bounds__(kStatThreads, 4)
 k_region_stats(StatArgs a) {
   __shared__ __align__(16) uint32_t s_hist[kHistBins];
   __shared__ unsigned long long s_u64[6 * (kStatThreads / 32)];
