@@ -139,6 +139,19 @@ int  mcov_depth_sorted_async(mcov_ctx* ctx, int64_t n,
                              const uint32_t* cig_off, const uint32_t* cig,
                              int mem_kind);
 
+/* Compact HOST transport of a coordinate-sorted batch (the PCIe link bounds the
+ * end-to-end rate): instead of tid[n] the per-contig read prefix
+ * contig_read_start[n_contigs+1] (reads [crs[c], crs[c+1]) belong to contig c,
+ * reads from crs[n_contigs] on are unplaced); instead of cig_off[n+1] the u16 op
+ * counts n_cigar[n] (BAM's own limit); mapq may be NULL when min_mapq == 0.  The
+ * SoA columns are rebuilt on the device (k_unpack_reads + scan).  All arrays are
+ * host memory.  wait=0 defers the sortedness verdict like _async. */
+int  mcov_depth_sorted_packed(mcov_ctx* ctx, int64_t n,
+                              const int64_t* contig_read_start, const int32_t* pos,
+                              const uint16_t* flag, const uint8_t* mapq /* nullable */,
+                              const uint16_t* n_cigar, const uint32_t* cig, int64_t n_cig_total,
+                              int wait);
+
 /* Replaces the seven reductions of `classic` (reference
  * metacov/pileup.py:18-26) for g regions at once (the loop at cli.py:85-95).
  * tid/start/end are host arrays; 0 <= start <= end.  Positions >= len[tid]

@@ -657,4 +657,26 @@ __global__ void k_cap_replay(FusedArgs f, const int32_t* __restrict__ contigs, i
   d[len] = 0;                                       // sentinel slot
 }
 
+// ---- compact host transport (mcov_depth_sorted_packed) ---------------------------------------------
+// The PCIe link, not the GPU, bounds the end-to-end rate, so the host may ship a coordinate-sorted
+// batch without the redundant columns: the contig of read i follows from a per-contig read-count
+// prefix (instead of tid[R]), CIGAR offsets follow from u16 op counts (instead of u32 offsets), and
+// mapq may be omitted when the filter does not look at it.  This kernel rebuilds tid[] and seeds the
+// offset scan; k_scan_inplace turns the counts into cig_off[].
+__global__ void k_unpack_reads(int64_t n, const int64_t* __restrict__ contig_read_start, int32_t n_contigs,
+                               const uint16_t* __restrict__ ncig, int32_t* __restrict__ tid, uint32_t* __restrict__ cig_off,
+                               int64_t off_len) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < off_len) cig_off[i] = (i >= 1 && i <= n) ? (uint32_t)ncig[i - 1] : 0u;      // entry 0 and the padding are 0
+  if (i >= n) return;
+  // contig of read i: largest c with contig_read_start[c] <= i; reads past the last contig are unplaced
+  int32_t lo = 0, hi = n_contigs;
+  if (i >= contig_read_start[n_contigs]) { tid[i] = -1; return; }
+  while (hi - lo > 1) {
+    int32_t mid = lo + ((hi - lo) >> 1);
+    if (contig_read_start[mid] <= i) lo = mid; else hi = mid;
+  }
+  tid[i] = lo;
+}
+
 }  // namespace mcov

@@ -414,6 +414,79 @@ int mcov_depth_sorted_async(mcov_ctx* ctx, int64_t n, const int32_t* tid, const 
   return depth_sorted_impl(ctx, n, tid, pos, flag, mapq, cig_off, cig, mem_kind, false);
 }
 
+int mcov_depth_sorted_packed(mcov_ctx* ctx, int64_t n, const int64_t* contig_read_start, const int32_t* pos,
+                             const uint16_t* flag, const uint8_t* mapq, const uint16_t* n_cigar, const uint32_t* cig,
+                             int64_t n_cig_total, int wait) {
+  if (!ctx) return MCOV_ERR_ARG;
+  if (n < 0 || n_cig_total < 0 || n_cig_total > 0xFFFFFFFFll) return fail(ctx, MCOV_ERR_ARG, "mcov_depth_sorted_packed: bad sizes");
+  if (!contig_read_start || (n > 0 && (!pos || !flag || !n_cigar)) || (n_cig_total > 0 && !cig))
+    return fail(ctx, MCOV_ERR_ARG, "mcov_depth_sorted_packed: null array");
+  if (!mapq && ctx->filt.min_mapq > 0) return fail(ctx, MCOV_ERR_ARG, "mcov_depth_sorted_packed: mapq is required when min_mapq > 0");
+  CU(cudaSetDevice(ctx->device));
+  int rc = ensure_depth(ctx);
+  if (rc) return rc;
+  if (contig_read_start[0] != 0 || contig_read_start[ctx->n_contigs] > n)
+    return fail(ctx, MCOV_ERR_ARG, "mcov_depth_sorted_packed: contig_read_start must start at 0 and end <= n");
+  CU(cudaMemsetAsync(ctx->d_pc.p, 0, sizeof(PassCounters), ctx->stream));
+  ReadStage& st = ctx->stage[ctx->stage_next];
+  ctx->stage_next ^= 1;
+  if (st.in_flight) { CU(cudaEventSynchronize(st.consumed)); st.in_flight = false; }
+  const int64_t off_len = (n + 1 + 3) & ~(int64_t)3;                    // scanned in place: multiple of 4
+  const size_t crs_bytes = ((size_t)ctx->n_contigs + 1) * 8;
+  CU(st.tid.ensure((size_t)std::max<int64_t>(n, 1) * 4)); CU(st.pos.ensure((size_t)std::max<int64_t>(n, 1) * 4));
+  CU(st.flag.ensure((size_t)std::max<int64_t>(n, 1) * 2)); CU(st.mapq.ensure((size_t)std::max<int64_t>(n, 1)));
+  CU(st.cig_off.ensure((size_t)off_len * 4)); CU(st.cig.ensure((size_t)n_cig_total * 4 + 16));
+  CU(ctx->d_end_slot.ensure((size_t)std::max<int64_t>(n, 1) * 2 + crs_bytes + 16));     // [contig_read_start | n_cigar]
+  cudaStream_t cs = ctx->copy_stream;
+  char* extra = ctx->d_end_slot.as<char>();
+  CU(cudaMemcpyAsync(extra, contig_read_start, crs_bytes, cudaMemcpyHostToDevice, cs));
+  if (n > 0) {
+    CU(cudaMemcpyAsync(extra + crs_bytes, n_cigar, (size_t)n * 2, cudaMemcpyHostToDevice, cs));
+    CU(cudaMemcpyAsync(st.pos.p, pos, (size_t)n * 4, cudaMemcpyHostToDevice, cs));
+    CU(cudaMemcpyAsync(st.flag.p, flag, (size_t)n * 2, cudaMemcpyHostToDevice, cs));
+    if (mapq) CU(cudaMemcpyAsync(st.mapq.p, mapq, (size_t)n, cudaMemcpyHostToDevice, cs));
+    else CU(cudaMemsetAsync(st.mapq.p, 0xff, (size_t)n, cs));
+    if (n_cig_total) CU(cudaMemcpyAsync(st.cig.p, cig, (size_t)n_cig_total * 4, cudaMemcpyHostToDevice, cs));
+  }
+  CU(cudaEventRecord(ctx->copied, cs));
+  CU(cudaStreamWaitEvent(ctx->stream, ctx->copied, 0));
+  cudaStream_t s = ctx->stream;
+  // rebuild tid[] and cig_off[] on the device
+  MCOV_LAUNCH(ctx, kKUnpack, (k_unpack_reads<<<(unsigned)((off_len + 255) / 256), 256, 0, s>>>(
+      n, reinterpret_cast<const int64_t*>(extra), ctx->n_contigs, reinterpret_cast<const uint16_t*>(extra + crs_bytes),
+      st.tid.as<int32_t>(), st.cig_off.as<uint32_t>(), off_len)));
+  CU(cudaGetLastError());
+  {
+    const int64_t tiles = (off_len + kScanTile - 1) / kScanTile;
+    CU(ctx->d_tile_cnt.ensure((size_t)tiles * 8));
+    CU(cudaMemsetAsync(ctx->d_tile_cnt.p, 0, (size_t)tiles * 8, s));
+    MCOV_LAUNCH(ctx, kKScanCounts, (k_scan_inplace<false><<<(unsigned)tiles, kScanThreads, 0, s>>>(
+        st.cig_off.as<int32_t>(), off_len, ctx->d_tile_cnt.as<unsigned long long>(), pc_of(ctx))));
+    CU(cudaGetLastError());
+    CU(cudaMemsetAsync(&pc_of(ctx)->ticket, 0, sizeof(unsigned int), s));      // the fused pass scans again
+  }
+  ExpandArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.n = n;
+  a.tid = st.tid.as<int32_t>(); a.pos = st.pos.as<int32_t>(); a.flag = st.flag.as<uint16_t>();
+  a.mapq = st.mapq.as<uint8_t>(); a.cig_off = st.cig_off.as<uint32_t>(); a.cig = st.cig.as<uint32_t>();
+  a.contig_off = ctx->d_off.as<int64_t>(); a.contig_len = ctx->d_len.as<int32_t>(); a.n_contigs = ctx->n_contigs;
+  a.filt = ctx->filt; a.delta = ctx->depth; a.pc = pc_of(ctx);
+  a.cig_aligned16 = 1;
+  rc = fused_depth_sorted(ctx, a);
+  if (rc) return rc;
+  ctx->n_reads_pushed = n;
+  rc = finish_stage(ctx, &st);
+  if (rc) return rc;
+  ctx->state = kDepthReady;
+  ctx->verdict_pending = true;
+  if (!wait) return MCOV_OK;
+  PassCounters h;
+  CU(cudaMemcpyAsync(&h, ctx->d_pc.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return fused_verdict(ctx, h);
+}
+
 int mcov_pass_info_get(mcov_ctx* ctx, mcov_pass_info* out) {
   if (!ctx || !out) return fail(ctx, MCOV_ERR_ARG, "mcov_pass_info_get: null argument");
   if (ctx->state == kIdle) return fail(ctx, MCOV_ERR_STATE, "mcov_pass_info_get: no pass has run");
@@ -435,7 +508,7 @@ int mcov_pass_info_get(mcov_ctx* ctx, mcov_pass_info* out) {
 static const char* kKernelNames[kKernelCount] = {
     "k_expand", "k_scan_inplace", "k_fused_prep", "k_tile_first", "k_scan_counts", "k_far_scatter", "k_fused_tile",
     "k_init_region_stats", "k_region_stats", "k_window_sums", "k_isize_hist", "k_group_count", "k_sorted_stats",
-    "memset_depth", "k_region_stats_small", "k_cap_replay"};
+    "memset_depth", "k_region_stats_small", "k_cap_replay", "k_unpack_reads"};
 
 int64_t mcov_launch_count(const mcov_ctx* ctx) { return ctx ? ctx->n_launches : 0; }
 

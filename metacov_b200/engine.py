@@ -137,6 +137,13 @@ class CoverageEngine:
         fn = lib.mcov_depth_sorted if wait else lib.mcov_depth_sorted_async
         self._check(fn(self._ctx, n, *[_capi.ptr(x) for x in b], _mem_kind(b)))
 
+    def depth_sorted_packed(self, packed, wait=True):
+        """Fused path from the compact host transport (see ``pack_batch``)."""
+        self._check(lib.mcov_depth_sorted_packed(
+            self._ctx, packed["n"], _capi.ptr(packed["contig_read_start"]), _capi.ptr(packed["pos"]),
+            _capi.ptr(packed["flag"]), _capi.ptr(packed["mapq"]) if packed.get("mapq") is not None else None,
+            _capi.ptr(packed["n_cigar"]), _capi.ptr(packed["cig"]), packed["n_cig_total"], 1 if wait else 0))
+
     def compute_depth(self, batch):
         """Per-base depth of all contigs from one batch: the fused sorted path,
         or clear + expand + scan when the reads are not coordinate-sorted (or
@@ -237,3 +244,44 @@ class CoverageEngine:
                 return hist, cnt, mx.value
             while n_bins <= mx.value:
                 n_bins *= 2
+
+
+def pack_batch(batch, n_contigs, with_mapq=False, pinned=False):
+    """Compact host transport of a coordinate-sorted ``ReadBatch`` (numpy or CPU torch members):
+    per-contig read prefix instead of ``tid``, u16 op counts instead of u32 offsets, ``mapq`` only
+    on request.  Raises ValueError if the batch is not grouped by contig.  With ``pinned`` the
+    arrays are torch pinned tensors (true asynchronous H2D)."""
+    def as_np(a, dt):
+        if _is_torch(a):
+            a = a.cpu().numpy()
+        return np.ascontiguousarray(a).view(dt) if np.dtype(a.dtype).itemsize == np.dtype(dt).itemsize else np.ascontiguousarray(a, dtype=dt)
+    tid = as_np(batch.tid, np.int32)
+    n = len(tid)
+    placed = tid[(tid >= 0) & (tid < n_contigs)]
+    if len(placed) and (np.any(np.diff(placed) < 0) or np.any(tid[:len(placed)] != placed)):
+        raise ValueError("pack_batch: reads are not grouped by contig (unplaced reads must come last)")
+    crs = np.zeros(n_contigs + 1, dtype=np.int64)
+    np.cumsum(np.bincount(placed, minlength=n_contigs), out=crs[1:])
+    off = as_np(batch.cig_off, np.uint32).astype(np.int64)
+    ncig = np.diff(off)
+    if len(ncig) and ncig.max() > 65535:
+        raise ValueError("pack_batch: a CIGAR has more than 65535 ops")
+    out = {"n": n, "contig_read_start": crs, "pos": as_np(batch.pos, np.int32), "flag": as_np(batch.flag, np.uint16),
+           "mapq": as_np(batch.mapq, np.uint8) if with_mapq else None, "n_cigar": ncig.astype(np.uint16),
+           "cig": as_np(batch.cig, np.uint32), "n_cig_total": int(off[-1]) if len(off) else 0}
+    if pinned:
+        import torch
+        for k in ("contig_read_start", "pos", "flag", "mapq", "n_cigar", "cig"):
+            if out[k] is not None:
+                t = torch.from_numpy(out[k].view({8: np.int64, 4: np.int32, 2: np.int16, 1: np.uint8}[out[k].dtype.itemsize]))
+                out[k] = t.pin_memory()
+    return out
+
+
+def packed_bytes(packed):
+    tot = 0
+    for k in ("contig_read_start", "pos", "flag", "mapq", "n_cigar", "cig"):
+        a = packed[k]
+        if a is not None:
+            tot += a.numel() * a.element_size() if _is_torch(a) else a.nbytes
+    return int(tot)

@@ -305,3 +305,34 @@ def test_max_depth_cap_replayed_exactly():
         assert eng.pass_info()["cap_contigs"] == 0
         free, _, _ = cport.depth(b, lengths, mode="diff")
         assert np.array_equal(eng.copy_depth(0), free[off[0]:off[0] + lengths[0]])
+
+
+@pytest.mark.parametrize("wl,scale", [("c2", 0.01), ("c5", 0.002)])
+def test_packed_host_transport_equals_soa_path(wl, scale):
+    """mcov_depth_sorted_packed (contig prefix + u16 op counts, no mapq) rebuilds the SoA on the device."""
+    from metacov_b200 import McovError, synth
+    from metacov_b200.engine import pack_batch, packed_bytes
+    w = synth.WORKLOADS[wl](scale)
+    b, _ = synth.generate_host(w)
+    packed = pack_batch(b, w.n_contigs)
+    assert packed_bytes(packed) < sum(np.asarray(x).nbytes for x in b)
+    with engine_for(w.contig_len) as eng:
+        eng.depth_sorted_packed(packed)
+        want, dflat, off, info = oracle_depth(b, w.contig_len)
+        for c, d in enumerate(full_depth(eng)):
+            assert np.array_equal(d, want[c]), c
+        pi = eng.pass_info()
+        assert pi["n_pass"] == info["n_pass"] and pi["aligned_bases"] == info["aligned_bases"] and pi["sorted"] == 1
+        # with mapq shipped and a mapq filter
+        eng.set_filter(min_mapq=30)
+        with pytest.raises(McovError):
+            eng.depth_sorted_packed(packed)                     # mapq required when min_mapq > 0
+        eng.depth_sorted_packed(pack_batch(b, w.n_contigs, with_mapq=True))
+        want30, _, _, _ = oracle_depth(b, w.contig_len, min_mapq=30)
+        assert np.array_equal(eng.copy_depth(0), want30[0])
+    # unplaced reads at the end and pinned tensors
+    z, fb = load_soa("fixture_soa.npz")
+    with engine_for(z["lengths"]) as eng:
+        eng.depth_sorted_packed(pack_batch(fb, 2, pinned=True))
+        wantf, _, _, _ = oracle_depth(fb, z["lengths"])
+        assert np.array_equal(eng.copy_depth(1), wantf[1]) and eng.pass_info()["n_pass"] == 3350
