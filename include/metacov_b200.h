@@ -226,6 +226,18 @@ int  mcov_isize_hist(mcov_ctx* ctx, int64_t n,
                      int32_t n_bins, uint32_t* hist_out,
                      uint64_t* group_counts_out, int32_t* max_isize_out);
 
+/* Replaces `KmerHist.process_read` over every record (reference
+ * metacov/scan.pyx:503-522 with the sequence decoding of scan.pyx:240-259): reads
+ * shorter than OFFSET+STEP*NK are skipped; for i < NK the k-mer at read position
+ * OFFSET+i*STEP (first base in the low bits, any non-ACGT base -> bin 4^K) is
+ * counted in hist[group][kmer][i].  seq_win = per-read windows from
+ * mcov_bam_seq_windows (win_bases >= OFFSET+(NK-1)*STEP+K).  Host arrays;
+ * hist_out: u32[2^n_group_flags][4^K+1][NK].  K <= 12, OFFSET >= 0. */
+int  mcov_kmer_hist(mcov_ctx* ctx, int64_t n, const uint16_t* flag, const int32_t* l_seq,
+                    const uint8_t* seq_win, int32_t win_bytes, int32_t win_bases,
+                    int32_t K, int32_t NK, int32_t STEP, int32_t OFFSET,
+                    int32_t n_group_flags, const uint16_t* group_flags, uint32_t* hist_out);
+
 /* ---- host BAM decoding (replaces pysam.AlignmentFile, cli.py:56, 211) ---- */
 
 typedef struct mcov_bam mcov_bam;
@@ -252,6 +264,11 @@ const int32_t*  mcov_bam_lseq(const mcov_bam* b);
 const int32_t*  mcov_bam_isize(const mcov_bam* b);
 const uint32_t* mcov_bam_cig_off(const mcov_bam* b);
 const uint32_t* mcov_bam_cig(const mcov_bam* b);
+/* Packed SEQ (only the k-mer histogram needs it) and the per-read windows it is
+ * cut into: out[n][(win_bases+1)/2], forward reads their first win_bases bases,
+ * reverse reads their last win_bases (nt16, high nibble first, missing = 15). */
+int  mcov_bam_load_seq(mcov_bam* b);
+int  mcov_bam_seq_windows(const mcov_bam* b, int32_t win_bases, uint8_t* out);
 
 /* ---- synthetic workloads (bench / test support; include/mcov_synth.h) ---- */
 

@@ -101,6 +101,9 @@ SIGNATURES = {
     "mcov_profile_enable": (C.c_int, [_vp, C.c_int]),
     "mcov_profile_read": (C.c_int, [_vp, C.POINTER(KernelTime), C.c_int]),
     "mcov_isize_hist": (C.c_int, [_vp, _i64, _vp, _vp, C.c_int, _i32, _vp, _i32, _vp, _vp, _vp]),
+    "mcov_kmer_hist": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "mcov_bam_load_seq": (C.c_int, [_vp]),
+    "mcov_bam_seq_windows": (C.c_int, [_vp, _i32, _vp]),
     "mcov_bam_open": (C.c_int, [C.POINTER(_vp), C.c_char_p, C.c_char_p, C.c_int]),
     "mcov_bam_close": (None, [_vp]),
     "mcov_bam_n_ref": (_i32, [_vp]),

@@ -134,6 +134,19 @@ class AlignmentFile:
             )
         return self._soa
 
+    def seq_windows(self, win_bases):
+        """uint8[n, (win_bases+1)//2]: per read the first (forward) / last (reverse) win_bases bases,
+        nt16 two per byte -- the part of SEQ the k-mer histogram looks at."""
+        n = len(self.soa()["tid"])
+        rc = lib.mcov_bam_load_seq(self._h)
+        if rc != 0:
+            raise McovError(rc, "BAM SEQ decode failed")
+        out = np.empty((n, (win_bases + 1) // 2), dtype=np.uint8)
+        rc = lib.mcov_bam_seq_windows(self._h, int(win_bases), _capi.ptr(out))
+        if rc != 0:
+            raise McovError(rc, "mcov_bam_seq_windows failed")
+        return out
+
     def __len__(self):
         return len(self.soa()["tid"])
 

@@ -138,9 +138,6 @@ def scan(readfile, readfile_type, out_basehist, boffset, out_kmerhist, k, number
     for opt, name in ((out_basehist, "-b/--out-basehist"), (out_mirrorhist, "-M/--out-mirrorhist")):
         if opt:
             raise click.UsageError(name + " needs the reference FASTA and is outside the GPU hot path of this build")
-    if out_kmerhist:
-        raise click.UsageError("-o/--out-kmerhist: the k-mer histogram kernel is the next row of the scope "
-                               "table and not in this build")
 
     update_every = 100000
     if max_reads and max_reads > 0 and max_reads / 100 < update_every:
@@ -154,6 +151,8 @@ def scan(readfile, readfile_type, out_basehist, boffset, out_kmerhist, k, number
         length = max_reads
 
     counters = []
+    if out_kmerhist:
+        counters.append(_scan.KmerHist(k, number, step, offset))
     if out_isizehist:
         counters.append(_scan.IsizeHist())
     counters = _scan.ByFlag(counters, [_scan.Flags[flag] for flag in group_by])
@@ -166,6 +165,9 @@ def scan(readfile, readfile_type, out_basehist, boffset, out_kmerhist, k, number
     log.info("Processed {} reads".format(nreads))
 
     n = 0
+    if out_kmerhist:
+        csv.writer(out_kmerhist).writerows(counters.get_rows(n))
+        n += 1       # (the reference forgets this increment, cli.py:273-280; harmless there without -M)
     if out_isizehist:
         csv.writer(out_isizehist).writerows(counters.get_rows(n))
         n += 1

@@ -9,6 +9,7 @@
 // deflate streams, so they are inflated in parallel by a few host threads.
 #include <zlib.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -31,6 +32,9 @@ struct mcov_bam {
   std::vector<uint16_t> flag;
   std::vector<uint8_t> mapq;
   std::vector<uint32_t> cig_off, cig;
+  bool has_seq = false;
+  std::vector<uint64_t> seq_off;     // byte offset of each record's packed SEQ
+  std::vector<uint8_t> seq;          // nt16, two bases per byte, high nibble first (BAM encoding)
 };
 
 namespace {
@@ -146,26 +150,36 @@ bool parse_header(mcov_bam* b) {
 
 }  // namespace
 
-extern "C" {
-
-int mcov_bam_open(mcov_bam** out, const char* path, char* err, int errlen) {
-  if (!out || !path) return set_err(err, errlen, "mcov_bam_open: null argument");
-  *out = nullptr;
-  FILE* fh = std::fopen(path, "rb");
-  if (!fh) return set_err(err, errlen, "mcov_bam_open: cannot open file");
-  mcov_bam* b = new mcov_bam();
-  b->path = path;
+static int read_inflate(mcov_bam* b);
+// read the file and inflate it into b->data; 0 ok, 1 cannot open, 2 short read, 3 bad BGZF, 4 bad BAM
+static int read_inflate(mcov_bam* b) {
+  FILE* fh = std::fopen(b->path.c_str(), "rb");
+  if (!fh) return 1;
   std::fseek(fh, 0, SEEK_END);
   long sz = std::ftell(fh);
   std::fseek(fh, 0, SEEK_SET);
   b->raw.resize(sz > 0 ? (size_t)sz : 0);
   size_t got = b->raw.empty() ? 0 : std::fread(b->raw.data(), 1, b->raw.size(), fh);
   std::fclose(fh);
-  if (got != b->raw.size()) { delete b; return set_err(err, errlen, "mcov_bam_open: short read"); }
+  if (got != b->raw.size()) return 2;
   unsigned hw = std::thread::hardware_concurrency();
-  if (!inflate_all(b, hw ? (int)hw : 4)) { delete b; return set_err(err, errlen, "mcov_bam_open: not a valid BGZF file"); }
-  if (!parse_header(b)) { delete b; return set_err(err, errlen, "mcov_bam_open: not a valid BAM file"); }
+  if (!inflate_all(b, hw ? (int)hw : 4)) return 3;
+  if (!parse_header(b)) return 4;
   std::vector<uint8_t>().swap(b->raw);
+  return 0;
+}
+
+extern "C" {
+
+int mcov_bam_open(mcov_bam** out, const char* path, char* err, int errlen) {
+  if (!out || !path) return set_err(err, errlen, "mcov_bam_open: null argument");
+  *out = nullptr;
+  mcov_bam* b = new mcov_bam();
+  b->path = path;
+  static const char* msg[] = {"", "mcov_bam_open: cannot open file", "mcov_bam_open: short read",
+                              "mcov_bam_open: not a valid BGZF file", "mcov_bam_open: not a valid BAM file"};
+  int rc = read_inflate(b);
+  if (rc) { delete b; return set_err(err, errlen, msg[rc]); }
   *out = b;
   return MCOV_OK;
 }
@@ -272,5 +286,80 @@ const int32_t* mcov_bam_lseq(const mcov_bam* b) { return (b && b->loaded) ? b->l
 const int32_t* mcov_bam_isize(const mcov_bam* b) { return (b && b->loaded) ? b->isize.data() : nullptr; }
 const uint32_t* mcov_bam_cig_off(const mcov_bam* b) { return (b && b->loaded) ? b->cig_off.data() : nullptr; }
 const uint32_t* mcov_bam_cig(const mcov_bam* b) { return (b && b->loaded) ? b->cig.data() : nullptr; }
+
+// Packed SEQ of every record (needed by the k-mer histogram only).  Re-inflates the file when the
+// record pass has already released it.
+int mcov_bam_load_seq(mcov_bam* b) {
+  if (!b) return MCOV_ERR_ARG;
+  if (b->has_seq) return MCOV_OK;
+  if (b->data.empty()) { if (read_inflate(b)) return MCOV_ERR_IO; }
+  const uint8_t* d = b->data.data();
+  const size_t n = b->data.size();
+  size_t p = b->rec_begin, n_rec = 0, bytes = 0;
+  while (p + 4 <= n) {
+    uint32_t bs = rd32(d + p);
+    if (bs < 32 || p + 4 + bs > n) return MCOV_ERR_IO;
+    bytes += ((size_t)rd32(d + p + 4 + 16) + 1) / 2;
+    ++n_rec;
+    p += 4 + bs;
+  }
+  b->seq_off.resize(n_rec + 1);
+  b->seq.resize(bytes);
+  p = b->rec_begin;
+  size_t so = 0;
+  for (size_t i = 0; i < n_rec; ++i) {
+    uint32_t bs = rd32(d + p);
+    const uint8_t* r = d + p + 4;
+    uint8_t l_read_name = r[8];
+    uint16_t n_op = rd16(r + 12);
+    size_t l_seq = rd32(r + 16), nb = (l_seq + 1) / 2;
+    if (32u + l_read_name + 4u * n_op + nb > bs) return MCOV_ERR_IO;
+    b->seq_off[i] = so;
+    std::memcpy(b->seq.data() + so, r + 32 + l_read_name + 4u * n_op, nb);
+    so += nb;
+    p += 4 + bs;
+  }
+  b->seq_off[n_rec] = so;
+  b->has_seq = true;
+  if (b->loaded) std::vector<uint8_t>().swap(b->data);
+  return MCOV_OK;
+}
+
+// Per read a window of `win_bases` bases, re-packed two per byte (high nibble first) into
+// out[n][(win_bases+1)/2]: forward reads contribute their FIRST win_bases bases, reverse reads
+// (flag 0x10) their LAST win_bases, so that window base j is absolute base (l_seq - win_bases + j);
+// missing bases are 'N' (15).  This is all the k-mer histogram needs (reference scan.pyx:240-259
+// decodes the whole SEQ and undoes the mapper's reverse complement; only the read's first
+// OFFSET+STEP*(NK-1)+K bases are ever looked at, scan.pyx:513-520).
+int mcov_bam_seq_windows(const mcov_bam* b, int32_t win_bases, uint8_t* out) {
+  if (!b || !out || win_bases <= 0) return MCOV_ERR_ARG;
+  if (!b->has_seq || !b->loaded) return MCOV_ERR_ARG;
+  const size_t n = b->tid.size(), W = ((size_t)win_bases + 1) / 2;
+  unsigned hw = std::thread::hardware_concurrency();
+  int nt = (int)std::max(1u, std::min(hw ? hw : 4u, 32u));
+  if (n < 4096) nt = 1;
+  auto work = [&](size_t lo, size_t hi) {
+    for (size_t i = lo; i < hi; ++i) {
+      const uint8_t* s = b->seq.data() + b->seq_off[i];
+      const int64_t l = b->lseq[i];
+      const bool rev = (b->flag[i] & 0x10) != 0;
+      uint8_t* o = out + i * W;
+      std::memset(o, 0xff, W);
+      for (int32_t j = 0; j < win_bases; ++j) {
+        int64_t a = rev ? l - win_bases + j : j;
+        uint8_t c = 15;
+        if (a >= 0 && a < l) c = (a & 1) ? (s[a >> 1] & 15) : (s[a >> 1] >> 4);
+        if (j & 1) o[j >> 1] = (uint8_t)((o[j >> 1] & 0xf0) | c);
+        else o[j >> 1] = (uint8_t)((o[j >> 1] & 0x0f) | (c << 4));
+      }
+    }
+  };
+  std::vector<std::thread> th;
+  size_t per = (n + nt - 1) / nt;
+  for (int t = 1; t < nt; ++t) { size_t lo = t * per, hi = std::min(n, lo + per); if (lo < hi) th.emplace_back(work, lo, hi); }
+  work(0, std::min(n, per));
+  for (auto& t : th) t.join();
+  return MCOV_OK;
+}
 
 }  // extern "C"

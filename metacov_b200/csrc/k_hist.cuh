@@ -90,4 +90,61 @@ k_group_count(IsizeArgs a) {
   }
 }
 
+// ---- k-mer histogram (KmerHist, reference metacov/scan.pyx:491-533) -------------------------------
+// For each read with rlen >= OFFSET + STEP*NK (scan.pyx:510) and each i < NK: the k-mer starting at
+// read position OFFSET + i*STEP, 2 bits per base with the FIRST base in the low bits (scan.pyx:520);
+// a base that is not A/C/G/T sends the k-mer to bin 4^K (scan.pyx:517-519); counts[k][i] += 1.
+// "Read position" is in the sequenced orientation: for reverse-strand records the stored SEQ is
+// reverse-complemented back (scan.pyx:251-257).  The input is the per-read window of
+// win_bases = OFFSET + (NK-1)*STEP + K bases produced by mcov_bam_seq_windows: window base j of a
+// forward read is read base j; of a reverse read it is stored base (l_seq - win_bases + j), i.e. read
+// base x = complement(window[win_bases-1-x]).
+struct KmerArgs {
+  int64_t n;
+  const uint16_t* flag;
+  const int32_t* l_seq;
+  const uint8_t* win;       // [n][win_bytes]
+  int32_t win_bytes, win_bases;
+  int32_t K, NK, STEP, OFFSET;
+  int32_t n_group_flags;
+  uint16_t group_flags[kMaxGroupFlags];
+  uint32_t* hist;           // [groups][4^K + 1][NK]
+};
+
+__device__ __forceinline__ int nt16_to_nt4(int c) {      // "=ACMGRSVTWYHKDBN" -> A0 C1 G2 T3, everything else 4
+  return c == 1 ? 0 : c == 2 ? 1 : c == 4 ? 2 : c == 8 ? 3 : 4;
+}
+
+__global__ void __launch_bounds__(kHistThreads)
+k_kmer_hist(KmerArgs a) {
+  const int64_t stride = (int64_t)gridDim.x * kHistThreads;
+  const int64_t table = ((int64_t)1 << (2 * a.K)) + 1;
+  for (int64_t i = (int64_t)blockIdx.x * kHistThreads + threadIdx.x; i < a.n; i += stride) {
+    const int rlen = a.l_seq[i];
+    if (rlen < a.OFFSET + a.STEP * a.NK) continue;
+    const uint32_t f = a.flag[i];
+    int g = 0;
+    for (int k = 0; k < a.n_group_flags; ++k) g = (g << 1) | ((f & a.group_flags[k]) ? 1 : 0);
+    const bool rev = (f & 0x10u) != 0;
+    const uint8_t* w = a.win + i * a.win_bytes;
+    uint32_t* h = a.hist + (int64_t)g * table * a.NK;
+    for (int s = 0; s < a.NK; ++s) {
+      int64_t kmer = 0;
+      for (int j = 0; j < a.K; ++j) {
+        int x = a.OFFSET + s * a.STEP + j;                 // read position (sequenced orientation)
+        int c = 4;
+        if (x < rlen && x < a.win_bases) {
+          int wj = rev ? a.win_bases - 1 - x : x;
+          int nib = (wj & 1) ? (w[wj >> 1] & 15) : (w[wj >> 1] >> 4);
+          c = nt16_to_nt4(nib);
+          if (rev && c < 4) c = 3 - c;                     // nt4_comp (scan.pyx:61-62); N stays N
+        }
+        if (c > 3) { kmer = table - 1; break; }
+        kmer |= (int64_t)c << (2 * j);
+      }
+      atomicAdd(h + kmer * a.NK + s, 1u);
+    }
+  }
+}
+
 }  // namespace mcov

@@ -508,7 +508,7 @@ int mcov_pass_info_get(mcov_ctx* ctx, mcov_pass_info* out) {
 static const char* kKernelNames[kKernelCount] = {
     "k_expand", "k_scan_inplace", "k_fused_prep", "k_tile_first", "k_scan_counts", "k_far_scatter", "k_fused_tile",
     "k_init_region_stats", "k_region_stats", "k_window_sums", "k_isize_hist", "k_group_count", "k_sorted_stats",
-    "memset_depth", "k_region_stats_small", "k_cap_replay", "k_unpack_reads"};
+    "memset_depth", "k_region_stats_small", "k_cap_replay", "k_unpack_reads", "k_kmer_hist"};
 
 int64_t mcov_launch_count(const mcov_ctx* ctx) { return ctx ? ctx->n_launches : 0; }
 
@@ -798,6 +798,41 @@ int mcov_isize_hist(mcov_ctx* ctx, int64_t n, const uint16_t* flag, const int32_
   CU(cudaMemcpyAsync(hist_out, a.hist, hist_bytes, cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(group_counts_out, a.group_cnt, (size_t)groups * 8, cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(max_isize_out, a.max_isize, 4, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return MCOV_OK;
+}
+
+int mcov_kmer_hist(mcov_ctx* ctx, int64_t n, const uint16_t* flag, const int32_t* l_seq, const uint8_t* seq_win,
+                   int32_t win_bytes, int32_t win_bases, int32_t K, int32_t NK, int32_t STEP, int32_t OFFSET,
+                   int32_t n_group_flags, const uint16_t* group_flags, uint32_t* hist_out) {
+  if (!ctx) return MCOV_ERR_ARG;
+  if (n < 0 || K < 1 || K > 12 || NK < 1 || STEP < 1 || OFFSET < 0 || n_group_flags < 0 || n_group_flags > kMaxGroupFlags ||
+      win_bases < OFFSET + (NK - 1) * STEP + K || win_bytes < (win_bases + 1) / 2 || !hist_out ||
+      (n > 0 && (!flag || !l_seq || !seq_win)) || (n_group_flags > 0 && !group_flags))
+    return fail(ctx, MCOV_ERR_ARG, "mcov_kmer_hist: bad arguments (K in 1..12, OFFSET >= 0, window must cover OFFSET+(NK-1)*STEP+K bases)");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const int64_t table = ((int64_t)1 << (2 * K)) + 1;
+  const size_t hist_bytes = (size_t)(1 << n_group_flags) * table * NK * 4;
+  CU(ctx->d_win_out.ensure(hist_bytes));
+  CU(cudaMemsetAsync(ctx->d_win_out.p, 0, hist_bytes, s));
+  if (n > 0) {
+    ReadStage& st = ctx->stage[0];
+    if (st.in_flight) { CU(cudaEventSynchronize(st.consumed)); st.in_flight = false; }
+    CU(st.flag.ensure((size_t)n * 2)); CU(st.pos.ensure((size_t)n * 4)); CU(st.cig.ensure((size_t)n * win_bytes));
+    CU(cudaMemcpyAsync(st.flag.p, flag, (size_t)n * 2, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(st.pos.p, l_seq, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(st.cig.p, seq_win, (size_t)n * win_bytes, cudaMemcpyHostToDevice, s));
+    KmerArgs a;
+    a.n = n; a.flag = st.flag.as<uint16_t>(); a.l_seq = st.pos.as<int32_t>(); a.win = st.cig.as<uint8_t>();
+    a.win_bytes = win_bytes; a.win_bases = win_bases; a.K = K; a.NK = NK; a.STEP = STEP; a.OFFSET = OFFSET;
+    a.n_group_flags = n_group_flags;
+    for (int k = 0; k < kMaxGroupFlags; ++k) a.group_flags[k] = k < n_group_flags ? group_flags[k] : 0;
+    a.hist = ctx->d_win_out.as<uint32_t>();
+    MCOV_LAUNCH(ctx, kKKmerHist, (k_kmer_hist<<<grid_for(n, kHistThreads, 8), kHistThreads, 0, s>>>(a)));
+    CU(cudaGetLastError());
+  }
+  CU(cudaMemcpyAsync(hist_out, ctx->d_win_out.p, hist_bytes, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
   return MCOV_OK;
 }

@@ -215,6 +215,20 @@ class CoverageEngine:
         self._check(lib.mcov_region_stats_enqueue(self._ctx, len(tid), _capi.ptr(tid), _capi.ptr(start),
                                                   _capi.ptr(end), int(breadth_n), out.data_ptr()))
 
+    def kmer_hist(self, flag, l_seq, seq_win, win_bases, K, NK, STEP, OFFSET, group_flags=()):
+        """ByFlag-grouped k-mer histogram -> uint32[groups, 4**K + 1, NK] (see mcov_kmer_hist)."""
+        gf = np.ascontiguousarray(group_flags, dtype=np.uint16)
+        flag = np.ascontiguousarray(flag, dtype=np.uint16)
+        l_seq = np.ascontiguousarray(l_seq, dtype=np.int32)
+        seq_win = np.ascontiguousarray(seq_win, dtype=np.uint8)
+        n = len(flag)
+        win_bytes = seq_win.shape[1] if seq_win.ndim == 2 else (win_bases + 1) // 2
+        hist = np.zeros((1 << len(gf), 4 ** K + 1, NK), dtype=np.uint32)
+        self._check(lib.mcov_kmer_hist(self._ctx, n, _capi.ptr(flag), _capi.ptr(l_seq), _capi.ptr(seq_win), win_bytes,
+                                       win_bases, K, NK, STEP, OFFSET, len(gf), _capi.ptr(gf) if len(gf) else None,
+                                       _capi.ptr(hist)))
+        return hist
+
     def window_means(self, window):
         n_out = int(sum((int(l) + window - 1) // window for l in self.lengths))
         out = np.empty(n_out, dtype=np.float64)

@@ -9,10 +9,10 @@ Mirrors the surface of reference metacov/scan.pyx: ``Flag`` / ``Flags`` /
 The reference walks the file one record at a time under the GIL
 (scan.pyx:653-667); here the records are decoded once into SoA arrays and every
 accumulator is filled by one CUDA kernel over all records (order does not
-matter for a histogram).  GPU-backed in this build: ``ByFlag`` grouping and
-``IsizeHist`` (they need only flag and isize).  ``KmerHist`` is the next row of
-the scope table; ``BaseHist`` / ``MirrorHist`` need a reference FASTA and are
-out of scope.
+matter for a histogram).  GPU-backed: ``ByFlag`` grouping, ``IsizeHist`` (flag
+and isize only) and ``KmerHist`` (per-read SEQ windows).  ``BaseHist`` /
+``MirrorHist`` need a reference FASTA and are out of scope (SURVEY.md 2 /
+Appendix C-9).
 """
 from copy import copy
 from itertools import islice
@@ -160,8 +160,9 @@ class IsizeHist(ReadProcessor):
 
 
 class KmerHist(ReadProcessor):
-    """k-mer histogram at NK sampled read positions (scan.pyx:491-533).  Surface only in this
-    build: the GPU kernel over packed SEQ prefixes is the next row of the scope table."""
+    """k-mer histogram at NK sampled read positions (scan.pyx:491-533): reads shorter than
+    OFFSET+STEP*NK are skipped; the k-mer at read position OFFSET+i*STEP is counted in
+    counts[kmer, i], first base in the low bits, any N -> row 4**K."""
 
     def __init__(self, K, NK, STEP, OFFSET):
         self.K, self.NK, self.STEP, self.OFFSET = K, NK, STEP, OFFSET
@@ -179,6 +180,17 @@ class KmerHist(ReadProcessor):
         yield ["N" * self.K] + list(self.counts[4 ** self.K])
         for i in range(4 ** self.K):
             yield [kmer_base2_to_ascii(i, self.K)] + list(self._counts_data[i])
+
+    def _accumulate(self, ctx, group_flags, targets):
+        if self.OFFSET < 0:
+            raise ValueError("KmerHist: a negative OFFSET reads outside the read in the reference "
+                             "(SURVEY.md Appendix C-9); not supported")
+        win_bases = self.OFFSET + (self.NK - 1) * self.STEP + self.K
+        win = ctx["infile"].seq_windows(win_bases)[:len(ctx["flag"])]
+        hist = ctx["engine"].kmer_hist(ctx["flag"], ctx["l_seq"], win, win_bases, self.K, self.NK, self.STEP,
+                                       self.OFFSET, group_flags)
+        for g, t in enumerate(targets):
+            t._counts_data = hist[g].copy()
 
 
 class BaseHist(ReadProcessor):
@@ -227,7 +239,8 @@ def scan_reads(infile, fasta, counters, progress_interval=10000000, progress_cb=
         n = int(maxreads)
     lengths = infile.lengths if len(infile.lengths) else (1,)
     with CoverageEngine(lengths, device=getattr(infile, "_device", 0)) as engine:
-        ctx = {"engine": engine, "flag": soa["flag"][:n], "isize": soa["isize"][:n]}
+        ctx = {"engine": engine, "infile": infile, "flag": soa["flag"][:n], "isize": soa["isize"][:n],
+               "l_seq": soa["l_seq"][:n]}
         processor._accumulate(ctx, [], [processor])
     if n:
         processor.set_max_readlen(max(50, int(soa["l_seq"][:n].max())))

@@ -120,5 +120,36 @@ def test_scan_api_and_cli(fixture_bam, tmp_path):
     mapped_rows = [r for r in rows[1:] if r[2] == "Mapped"]
     assert len(mapped_rows) == 249 and int(mapped_rows[0][1]) == int(r2[0][0]) and int(mapped_rows[210][1]) == int(r2[0][210])
     # out-of-scope options fail loudly instead of computing something else
-    res = CliRunner().invoke(scan_cmd, [fixture_bam, "-o", str(tmp_path / "k.csv")])
-    assert res.exit_code != 0 and "scope" in res.output
+    res = CliRunner().invoke(scan_cmd, [fixture_bam, "-b", str(tmp_path / "b.csv")])
+    assert res.exit_code != 0 and "outside the GPU hot path" in res.output
+
+
+def test_kmer_hist_api_and_cli(fixture_bam, tmp_path):
+    """KmerHist on the GPU against the restated scan.pyx:491-533 (oracle/scanstats.py)."""
+    from metacov_b200 import AlignmentFile, scan
+    from metacov_b200.cli import scan as scan_cmd
+    from oracle import scanstats
+    z, _ = load_soa("fixture_soa.npz")
+    so = z["seq_off"]
+    seqs = [z["seq"][so[i]:so[i + 1]] for i in range(len(z["tid"]))]
+    for K, NK, STEP, OFFSET, gf in ((7, 8, 7, 0, ()), (3, 5, 2, 4, (0x10, 0x40)), (5, 3, 9, 1, (0x4,))):
+        with AlignmentFile(fixture_bam) as af:
+            flags = [f for f in scan.Flags.values() if f.flag in gf]
+            flags.sort(key=lambda f: gf.index(f.flag))
+            counters = scan.ByFlag([scan.KmerHist(K, NK, STEP, OFFSET), scan.IsizeHist()], flags)
+            assert scan.scan_reads(af, None, counters) == 4112
+        want = scanstats.kmer_hist(z["flag"], seqs, K, NK, STEP, OFFSET, gf)
+        for g, p in enumerate(counters.processors):
+            assert np.array_equal(p.processors[0].counts, want[g]), (K, NK, STEP, OFFSET, g)
+    # CLI: reference tests/test_cli.py:22-29 runs `scan X.bam -o out1.csv`
+    out = tmp_path / "kmers.csv"
+    res = CliRunner().invoke(scan_cmd, [fixture_bam, "-o", str(out), "-I", str(tmp_path / "i.csv")])
+    assert res.exit_code == 0, res.output
+    rows = list(csv.reader(open(out)))
+    want = scanstats.kmer_hist(z["flag"], seqs, 7, 8, 7, 0)[0]
+    assert rows[0] == ["kmer"] + ["n%d" % i for i in range(8)] and rows[1][0] == "NNNNNNN" and len(rows) == 4 ** 7 + 2
+    assert [int(x) for x in rows[1][1:]] == want[4 ** 7].tolist()
+    assert rows[2][0] == "AAAAAAA" and [int(x) for x in rows[2][1:]] == want[0].tolist()
+    k = 0b01_00_11_10_00_01_11                      # low bits first: T C A G T A C  (11 01 00 10 11 00 01)
+    assert rows[2 + k][0] == scan.kmer_base2_to_ascii(k, 7) and [int(x) for x in rows[2 + k][1:]] == want[k].tolist()
+    assert sum(1 for _ in open(tmp_path / "i.csv")) == 250

@@ -1,6 +1,8 @@
 """Parity of the CUDA path (through the C-ABI) against the oracle and the committed golden
 vectors.  Integer results bit-exact; floats to the cent after the reference's round(.,2)
 (1e-6 relative before rounding is checked in test_host_logic)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -336,3 +338,40 @@ def test_packed_host_transport_equals_soa_path(wl, scale):
         eng.depth_sorted_packed(pack_batch(fb, 2, pinned=True))
         wantf, _, _, _ = oracle_depth(fb, z["lengths"])
         assert np.array_equal(eng.copy_depth(1), wantf[1]) and eng.pass_info()["n_pass"] == 3350
+
+
+def test_full_size_c2_bit_exact_and_properties():
+    """BASELINE config C2 at full size (10 M x 150 bp, 1 000 contigs): bit-exact against the C
+    oracle, plus size-independent properties (mass conservation, idempotence, path equivalence)."""
+    import torch
+    from metacov_b200 import ReadBatch, synth
+    w = synth.c2(1.0)
+    db, _, drl = synth.generate_device(w, 0, want_reflen=True)
+    hb = ReadBatch(*[np.ascontiguousarray(t.cpu().numpy()) for t in db])
+    hb = ReadBatch(hb.tid, hb.pos, hb.flag.view(np.uint16), hb.mapq, hb.cig_off.view(np.uint32), hb.cig.view(np.uint32))
+    want, off, info = cport.depth(hb, w.contig_len, mode="par", threads=os.cpu_count() or 4)
+    with engine_for(w.contig_len) as eng:
+        eng.depth_sorted(db)
+        pi = eng.pass_info()
+        assert pi["n_pass"] == info["n_pass"] and pi["aligned_bases"] == info["aligned_bases"]
+        assert pi["max_depth_seen"] == int(want.max()) and pi["cap_contigs"] == 0
+        # whole depth array, bit for bit (slot layout of the oracle = slot layout of the engine)
+        assert eng.n_slots == len(want)
+        buf = torch.empty(eng.n_slots, dtype=torch.int32, device="cuda")
+        eng.bind_depth(buf)
+        eng.depth_sorted(db)
+        got = buf.cpu().numpy()
+        assert np.array_equal(got, want)
+        # mass conservation: sum(depth) == aligned bases (no read is clipped in this workload)
+        assert int(got.astype(np.int64).sum()) == info["aligned_bases"]
+        # idempotence and path equivalence (push path on the same buffer)
+        eng.begin(); eng.push(db); eng.finalize()
+        torch.cuda.synchronize()
+        assert torch.equal(buf, torch.from_numpy(want).cuda())
+        # statistics of every contig
+        tid = np.arange(w.n_contigs, dtype=np.int32)
+        st = eng.region_stats(tid, np.zeros_like(tid), w.contig_len)
+        ref = cport.region_stats(want, off, w.contig_len, tid, np.zeros_like(tid), w.contig_len, threads=os.cpu_count() or 4)
+        for k in ("sum", "sumsq", "iq_sum", "min", "max", "med_lo", "med_hi", "n_ge1"):
+            assert np.array_equal(st[k], ref[k]), k
+        assert int(st["sum"].sum()) == info["aligned_bases"]

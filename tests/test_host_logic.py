@@ -100,3 +100,32 @@ def test_synth_generator_shapes_and_sortedness():
         assert np.array_equal(b2.pos, b.pos[lo:lo + n]) and np.array_equal(b2.flag, b.flag[lo:lo + n])
         o = b.cig_off.astype(np.int64)
         assert np.array_equal(b2.cig, b.cig[o[lo]:o[lo + n]])
+
+
+def test_native_seq_windows(tmp_path):
+    """csrc/bamio.cpp: packed SEQ and the per-read k-mer windows (first bases of forward reads,
+    last bases of reverse reads)."""
+    from metacov_b200 import AlignmentFile
+    z, b = load_soa("fixture_soa.npz")
+    so = z["seq_off"]
+    n = 300
+    seqs = [z["seq"][so[i]:so[i + 1]] for i in range(n)]
+    path = str(tmp_path / "s.bam")
+    o = b.cig_off.astype(np.int64)
+    bamio.write_bam(path, ["ref1", "ref2"], [425, 575], b.tid[:n], b.pos[:n], b.flag[:n], b.mapq[:n],
+                    (o[:n + 1] - o[0]).astype(np.uint32), b.cig[o[0]:o[n]], seqs=seqs)
+    P = 23
+    with AlignmentFile(path) as af:
+        win = af.seq_windows(P)
+        assert win.shape == (n, (P + 1) // 2)
+        assert np.array_equal(af.soa()["l_seq"], np.array([len(s) for s in seqs]))
+        for i in range(n):
+            nib = np.empty(2 * win.shape[1], np.uint8)
+            nib[0::2] = win[i] >> 4
+            nib[1::2] = win[i] & 15
+            s = seqs[i]
+            if b.flag[i] & 0x10:
+                want = [s[len(s) - P + j] if len(s) - P + j >= 0 else 15 for j in range(P)]
+            else:
+                want = [s[j] if j < len(s) else 15 for j in range(P)]
+            assert nib[:P].tolist() == [int(x) for x in want], i

@@ -115,3 +115,24 @@ def test_bam_reader_on_reference_fixture():
     assert np.array_equal(recs.tid, b.tid) and np.array_equal(recs.cig, b.cig)
     per_ref, n_no_coor = bamio.read_bai_stats(os.path.join(REF_DATA, "bbmap.sorted.bam.bai"))
     assert per_ref == [(1694, 38), (2285, 91)] and n_no_coor == 4
+
+
+def test_kmer_hist_known_answers():
+    """scan.pyx:491-533 restated; Appendix B: 3666 fixture reads are long enough for the default
+    KmerHist (K=7, NK=8, STEP=7, OFFSET=0)."""
+    from oracle import scanstats
+    z, _ = load_soa("fixture_soa.npz")
+    so = z["seq_off"]
+    seqs = [z["seq"][so[i]:so[i + 1]] for i in range(len(z["tid"]))]
+    h = scanstats.kmer_hist(z["flag"], seqs, 7, 8, 7, 0)
+    assert h.shape == (1, 4 ** 7 + 1, 8)
+    assert (h[0].sum(axis=0) == 3666).all()
+    assert hashlib.sha1(h.tobytes()).hexdigest() == "ed8186021fd049fba4cb4cfadadff9103651b2d9"
+    # a reverse-strand read is reverse-complemented back before its k-mers are taken
+    fwd = np.array([1, 2, 4, 8, 1, 1, 2, 2], np.uint8)            # ACGTAACC
+    hf = scanstats.kmer_hist([0], [fwd], 2, 2, 3, 0)
+    assert hf[0, 0 | (1 << 2), 0] == 1 and hf[0, 3 | (0 << 2), 1] == 1          # "AC" at 0, "TA" at 3
+    hr = scanstats.kmer_hist([16], [fwd], 2, 2, 3, 0)             # read = revcomp = GGTTACGT
+    assert hr[0, 2 | (2 << 2), 0] == 1 and hr[0, 3 | (0 << 2), 1] == 1          # "GG" at 0, "TA" at 3
+    hn = scanstats.kmer_hist([0], [np.array([1, 15, 1, 1, 1, 1], np.uint8)], 2, 2, 3, 0)
+    assert hn[0, 16, 0] == 1 and hn[0, 0, 1] == 1                # an N sends the k-mer to row 4**K
