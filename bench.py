@@ -368,8 +368,15 @@ def run_ours(args):
             ent["frac"] = ent["gbs"] / peak
         kernels[name] = ent
     dom = max((k for k in kernels if "gbs" in kernels[k]), key=lambda k: kernels[k]["ms_per_launch"] * kernels[k]["launches"])
+    # measured DRAM traffic of the dominant kernel (dram__bytes_read+write from the committed ncu capture);
+    # only quoted for the workload it was captured on
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic_c2.json")
+    if args.workload == "c2" and args.scale == 1.0 and os.path.exists(tpath):
+        with open(tpath) as fh:
+            traffic = json.load(fh)["dram_bytes_per_launch"].get(dom)
     roof = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
-            "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+            "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes"], "kernels": kernels,
             "timing": "CUDA-event pair around every launch on the launching stream, K steps run right after the timed region"}
     whole_bytes = alg_bytes["k_fused_prep"] + alg_bytes["k_fused_tile"] + 4 * L_regions + 64 * g
