@@ -353,7 +353,7 @@ def run_ours(args):
         "k_fused_prep": 15 * n_reads + 4 * cig_pass + 8 * n_reads,
         "k_fused_tile": 8 * n_reads + 4 * slots,
         "k_region_stats": 4 * int(lengths[lengths > 8192].astype(np.int64).sum()) + 64 * int((lengths > 8192).sum()),
-        "k_region_stats_small": 4 * int(lengths[lengths <= 8192].astype(np.int64).sum()) + 64 * int((lengths <= 8192).sum()),
+        "k_region_stats_warp": 4 * int(lengths[lengths <= 8192].astype(np.int64).sum()) + 64 * int((lengths <= 8192).sum()),
         "k_expand": 15 * n_reads + 4 * cig_pass + 8 * n_pass,
         "k_scan_inplace": 8 * slots,
         "memset_depth": 4 * slots,

@@ -252,13 +252,17 @@ k_region_stats(StatArgs a) {
 constexpr int kSmallThreads = 256;
 constexpr int kSmallRegion = 8192;
 
+// Runs over the retry list written by k_region_stats_warp (regions whose depth range does not fit
+// a warp's window): retry[0] = count, retry[1..] = task indices.  Persistent: blocks stride over the list.
 __global__ void __launch_bounds__(kSmallThreads, 6)
-k_region_stats_small(StatArgs a) {
+k_region_stats_small(StatArgs a, const uint32_t* __restrict__ retry) {
   __shared__ __align__(16) uint32_t s_hist[kHistBins];
   __shared__ unsigned long long s_u64[6 * (kSmallThreads / 32)];
   __shared__ int s_i32[4 * (kSmallThreads / 32)];
   __shared__ int s_med[2];
-  const StatTask task = a.tasks[blockIdx.x];
+  const uint32_t n_retry = retry[0];
+  for (uint32_t item = blockIdx.x; item < n_retry; item += gridDim.x) {
+  const StatTask task = a.tasks[retry[1 + item]];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int g = task.region;
   const int pad = a.region_pad[g];
@@ -299,6 +303,101 @@ k_region_stats_small(StatArgs a) {
   __syncthreads();
   WalkOut w = hist_walk<kSmallThreads>(s_hist, n_region, a.breadth_n, lo, hi, s_u64, s_i32, s_med);
   if (t == 0) write_stats(a.out + g, w);
+  __syncthreads();
+  }
+}
+
+// ---- small regions, first attempt: ONE WARP per region ------------------------------------------------
+// 8 regions per CTA, each warp with a private window of kWarpBins one-value bins anchored at the
+// region's minimum depth.  Everything is warp-synchronous (no block barrier).  A region whose depth
+// range does not fit the window is appended to the retry list for k_region_stats_small.
+constexpr int kWarpBins = 1024;
+constexpr int kWarpsPerCta = 8;
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_region_stats_warp(StatArgs a, int64_t task0, int64_t n_tasks, uint32_t* __restrict__ retry) {
+  __shared__ uint32_t s_win[kWarpsPerCta][kWarpBins];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t wi = (int64_t)blockIdx.x * kWarpsPerCta + warp;
+  if (wi >= n_tasks) return;
+  const StatTask task = a.tasks[task0 + wi];
+  const int g = task.region;
+  const int pad = a.region_pad[g];
+  const long long n = (long long)a.region_len[g] + pad;
+  const int64_t s0 = task.slot, s1 = task.slot + task.n;
+  const int64_t a0 = s0 & ~(int64_t)3;
+  const int64_t nvec = ((s1 - a0) + 3) >> 2;
+  const int4* vp = reinterpret_cast<const int4*>(a.depth + a0);
+  uint32_t* win = s_win[warp];
+  // pass 1: min / max bin
+  int lo = pad > 0 ? 0 : kHistBins - 1, hi = 0;
+  for (int64_t j = lane; j < nvec; j += 32) {
+    int4 q = __ldg(vp + j);
+    int v[4] = {q.x, q.y, q.z, q.w};
+    int64_t e0 = a0 + (j << 2);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (e0 + k >= s0 && e0 + k < s1) { int b = hist_bin(v[k]); lo = min(lo, b); hi = max(hi, b); }
+  }
+  lo = warp_min(lo); hi = warp_max(hi);
+  if (hi < lo) hi = lo;
+  const int nb = hi - lo + 1;
+  if (nb > kWarpBins || hi >= kHistBins - 1) {          // does not fit (or overflows the bin range): retry path
+    if (lane == 0) { uint32_t k = atomicAdd(retry, 1u); retry[1 + k] = (uint32_t)(task0 + wi); }
+    return;
+  }
+  for (int b = lane; b < nb; b += 32) win[b] = 0;
+  __syncwarp();
+  // pass 2: increments (served by L1/L2)
+  for (int64_t j = lane; j < nvec; j += 32) {
+    int4 q = __ldg(vp + j);
+    int v[4] = {q.x, q.y, q.z, q.w};
+    int64_t e0 = a0 + (j << 2);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (e0 + k >= s0 && e0 + k < s1) atomicAdd(&win[hist_bin(v[k]) - lo], 1u);
+  }
+  if (pad > 0 && lane == 0) atomicAdd(&win[0], (uint32_t)pad);      // pad > 0 => lo == 0
+  __syncwarp();
+  // walk the window: each lane a contiguous run of bins
+  const long long k1 = n / 4, k2 = n - n / 4, m1 = (n - 1) / 2, m2 = n / 2;
+  const int per = (nb + 31) / 32;
+  const int b0 = lane * per, b1 = min(b0 + per, nb);
+  unsigned long long local = 0;
+  for (int b = b0; b < b1; ++b) local += win[b];
+  unsigned long long x = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  long long c = (long long)(x - local);
+  long long sum = 0, iq = 0, ge1 = 0, geN = 0;
+  unsigned long long sumsq = 0;
+  int mn = INT_MAX, mx = INT_MIN, ml = -1, mh = -1;
+  for (int bb = b0; bb < b1; ++bb) {
+    long long cn = win[bb];
+    if (cn) {
+      long long b = bb + lo;
+      sum += b * cn;
+      sumsq += (unsigned long long)(b * b) * (unsigned long long)cn;
+      ge1 += b >= 1 ? cn : 0;
+      geN += b >= a.breadth_n ? cn : 0;
+      mn = min(mn, (int)b); mx = max(mx, (int)b);
+      long long l2 = c > k1 ? c : k1, h2 = (c + cn) < k2 ? (c + cn) : k2;
+      if (h2 > l2) iq += (h2 - l2) * b;
+      if (c <= m1 && m1 < c + cn) ml = (int)b;
+      if (c <= m2 && m2 < c + cn) mh = (int)b;
+      c += cn;
+    }
+  }
+  sum = warp_sum(sum); iq = warp_sum(iq); ge1 = warp_sum(ge1); geN = warp_sum(geN); sumsq = warp_sum(sumsq);
+  mn = warp_min(mn); mx = warp_max(mx); ml = warp_max(ml); mh = warp_max(mh);
+  if (lane == 0) {
+    WalkOut w;
+    w.sum = sum; w.iq_sum = iq; w.ge1 = ge1; w.geN = geN; w.sumsq = sumsq; w.mn = mn; w.mx = mx; w.med_lo = ml; w.med_hi = mh;
+    write_stats(a.out + g, w);
+  }
 }
 
 // Fixed-window mean depth: one warp per window.

@@ -508,7 +508,7 @@ int mcov_pass_info_get(mcov_ctx* ctx, mcov_pass_info* out) {
 static const char* kKernelNames[kKernelCount] = {
     "k_expand", "k_scan_inplace", "k_fused_prep", "k_tile_first", "k_scan_counts", "k_far_scatter", "k_fused_tile",
     "k_init_region_stats", "k_region_stats", "k_window_sums", "k_isize_hist", "k_group_count", "k_sorted_stats",
-    "memset_depth", "k_region_stats_small", "k_cap_replay", "k_unpack_reads", "k_kmer_hist"};
+    "memset_depth", "k_region_stats_small", "k_cap_replay", "k_unpack_reads", "k_kmer_hist", "k_region_stats_warp"};
 
 int64_t mcov_launch_count(const mcov_ctx* ctx) { return ctx ? ctx->n_launches : 0; }
 
@@ -656,11 +656,20 @@ static int stats_launch(mcov_ctx* ctx, int64_t g, const int32_t* tid, const int3
     if (rp.n_small) {
       StatArgs a;
       int32_t* d_rlen = ctx->d_rlen.as<int32_t>();
-      a.depth = ctx->depth; a.tasks = ctx->d_tasks.as<StatTask>() + rp.n_tasks; a.region_len = d_rlen; a.region_pad = d_rlen + g;
+      a.depth = ctx->depth; a.tasks = ctx->d_tasks.as<StatTask>(); a.region_len = d_rlen; a.region_pad = d_rlen + g;
       a.region_chunks = ctx->d_rchunks.as<int32_t>(); a.region_hist = ctx->d_rhist.as<int32_t>();
       a.region_done = nullptr; a.hist_pool = nullptr;
       a.out = d_out; a.breadth_n = breadth_n;
-      MCOV_LAUNCH(ctx, kKRegionStatsSmall, (k_region_stats_small<<<(unsigned)rp.n_small, kSmallThreads, 0, s>>>(a)));
+      // one warp per region first; regions whose depth range does not fit a warp's window are
+      // collected in a retry list (device side) and finished by the CTA-per-region kernel
+      CU(ctx->d_done.ensure(((size_t)rp.n_small + 1) * 4));
+      uint32_t* retry = ctx->d_done.as<uint32_t>();
+      CU(cudaMemsetAsync(retry, 0, 4, s));
+      const unsigned wgrid = (unsigned)((rp.n_small + kWarpsPerCta - 1) / kWarpsPerCta);
+      MCOV_LAUNCH(ctx, kKRegionStatsWarp, (k_region_stats_warp<<<wgrid, kWarpsPerCta * 32, 0, s>>>(a, rp.n_tasks, rp.n_small, retry)));
+      CU(cudaGetLastError());
+      const unsigned rgrid = (unsigned)std::min<int64_t>(rp.n_small, (int64_t)kNumSMsB200 * 6);
+      MCOV_LAUNCH(ctx, kKRegionStatsSmall, (k_region_stats_small<<<rgrid, kSmallThreads, 0, s>>>(a, retry)));
       CU(cudaGetLastError());
     }
   }
