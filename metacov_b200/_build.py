@@ -48,11 +48,12 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
     nvcc = _nvcc()
+    extra = os.environ.get("MCOV_NVCC_EXTRA", "").split()      # tuning hook, e.g. -DMCOV_TILE_MIN_CTAS=5
     os.makedirs(BUILD_DIR, exist_ok=True)
     objs = []
     for src in CUDA_SOURCES + CXX_SOURCES:
         obj = os.path.join(BUILD_DIR, os.path.splitext(src)[0] + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd), file=sys.stderr)
         subprocess.run(cmd, check=True)

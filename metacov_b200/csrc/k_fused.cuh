@@ -6,8 +6,8 @@
 // L2 per read, and no CTA waits on another:
 //
 //   k_fused_prep   one pass over the reads, 4 consecutive reads per thread with
-//                  128-bit loads: filter + CIGAR reduce, emits
-//                  rec[i] = {low 32 bits of the start slot, clipped span}
+//                  128-bit loads: filter + CIGAR reduce, emits the 4-byte record
+//                  rec[i] = {offset of the start slot in its tile, clipped span}
 //                  (span 0 = read contributes nothing).  Because the reads are
 //                  sorted it also produces, with warp-aggregated updates,
 //                    tile_first[T]  first read whose start slot >= T*kTile
@@ -29,8 +29,8 @@
 //                  condition exactly: cap[p] = depth[p-1] + starts[p]
 //                  = depth[p] + ends[p].
 //
-// HBM bytes (algorithmic): prep 15R + 4*sum(n_cigar of passing reads) + 8R;
-// tile 8R + 4(L+C).
+// HBM bytes (algorithmic): prep 15R + 4*sum(n_cigar of passing reads) + 4R;
+// tile 4R + 4(L+C).
 #pragma once
 #include "ctx.cuh"
 #include "k_expand.cuh"
@@ -48,7 +48,7 @@ constexpr uint32_t kFarCapDefault = 1u << 26;
 
 struct FusedArgs {
   ExpandArgs e;
-  uint2* rec;                 // [n] {key_lo, span}
+  uint32_t* rec;              // [n] 4-byte records, see make_rec
   int64_t n_slots;
   int64_t n_tiles;
   int64_t* far_end;           // [far_cap] end slots of far reads
@@ -62,6 +62,8 @@ struct FusedArgs {
   int32_t* tile_cap;          // [n_tiles] max of depth[p-1]+starts[p] in the tile, written only when > max_depth
   int32_t max_depth;          // htslib maxcnt (<= 0: cap disabled)
   int vec_ok;                 // SoA base pointers aligned for 128-bit loads
+  uint32_t* slow_list;        // warp iterations (group index >> 5) left to k_fused_prep_slow
+  uint32_t* slow_count;
 };
 
 // slot key of a read: contig offset + clamped position; reads without a valid
@@ -161,12 +163,160 @@ __device__ __noinline__ void prep_far(const FusedArgs& f, int64_t e0, int64_t e1
   }
 }
 
-// Hot loop of the fused path's first kernel.  All per-read arithmetic is 32-bit and contig
-// relative: with base = contig offset, tb = base >> 12 and bo = base & 4095 the tile of position q
-// is tb + ((bo + q) >> 12) and the low 32 bits of the slot key are (uint32)base + q; 64-bit slot
-// numbers are only formed on the rare paths (tile boundaries, far reads).
-__global__ void __launch_bounds__(kPrepThreads, 4)
-k_fused_prep(FusedArgs f) {
+// Record written by k_fused_prep for the tile kernel, 4 bytes per read:
+//   bits  0..11  offset of the start slot inside its tile (the tile itself follows from tile_first)
+//   bits 12..24  span code: 0 = contributes nothing (filtered / empty), 1..kNearSpan = clipped span,
+//                kRecFar = span above kNearSpan (its end comes from the far-end buckets)
+constexpr uint32_t kRecFar = 0x1FFFu;
+__device__ __forceinline__ uint32_t make_rec(uint32_t local, uint32_t span) {
+  return local | ((span > kNearSpan ? kRecFar : span) << kTileShift);
+}
+
+struct PrepAcc { uint32_t n_pass, al32, max_span, unsorted; };
+
+// General path of k_fused_prep for one warp iteration: contig changes inside the warp, negative
+// positions, reads without a valid contig, the ragged tail, the first reads of the batch.  Entered
+// by the whole warp.  All per-read arithmetic is 32-bit and contig relative: with base = contig
+// offset, tb = base >> 12 and bo = base & 4095 the tile of position q is tb + ((bo + q) >> 12);
+// 64-bit slot numbers are only formed for far reads.
+__device__ __forceinline__ PrepAcc prep_general(const FusedArgs& f, int64_t i0, int nv, int32_t T0, int32_t T1, int32_t T2,
+                                             int32_t T3, int32_t P0, int32_t P1, int32_t P2, int32_t P3, uint32_t R0,
+                                             uint32_t R1, uint32_t R2, uint32_t R3, unsigned passm, int lane) {
+  const ExpandArgs& a = f.e;
+  const int64_t* __restrict__ g_coff = a.contig_off;
+  const int32_t* __restrict__ g_clen = a.contig_len;
+  const uint32_t n_contigs = (uint32_t)a.n_contigs;
+  const int64_t n = a.n;
+  const uint32_t last_tile = (uint32_t)f.n_tiles;             // tile_first has n_tiles+1 entries
+  const uint32_t nslot_tb = (uint32_t)(f.n_slots >> kTileShift), nslot_bo = (uint32_t)(f.n_slots & (kTile - 1));
+  const int32_t T[4] = {T0, T1, T2, T3}, P[4] = {P0, P1, P2, P3};
+  const uint32_t reflen[4] = {R0, R1, R2, R3};
+  PrepAcc acc = {0u, 0u, 0u, 0u};
+  uint32_t span[4], tls[4], tle[4], qq[4], loc[4];
+  int32_t c_tid = INT_MIN;
+  uint32_t c_len = 0, c_tb = nslot_tb, c_bo = nslot_bo;
+  unsigned farmask = 0;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    if (T[r] != c_tid) {                        // contig change
+      c_tid = T[r];
+      if ((uint32_t)T[r] < n_contigs) {
+        int64_t base = g_coff[T[r]];
+        c_len = (uint32_t)g_clen[T[r]];
+        c_tb = (uint32_t)(base >> kTileShift); c_bo = (uint32_t)base & (kTile - 1);
+      } else { c_len = 0; c_tb = nslot_tb; c_bo = nslot_bo; }
+    }
+    uint32_t q = P[r] < 0 ? 0u : min((uint32_t)P[r], c_len);
+    qq[r] = q;
+    loc[r] = (c_bo + q) & (kTile - 1);
+    tls[r] = min(c_tb + ((c_bo + q) >> kTileShift), last_tile);
+    span[r] = 0; tle[r] = tls[r];
+    if ((passm >> r) & 1u) {
+      // end = clamp(pos + reflen, 0, len), in 64 bits only for the (never negative in practice) sum
+      int64_t e64 = (int64_t)P[r] + (int64_t)reflen[r];
+      uint32_t e = e64 < 0 ? 0u : (e64 > (int64_t)c_len ? c_len : (uint32_t)e64);
+      if (e > q) {
+        span[r] = e - q; tle[r] = c_tb + ((c_bo + e) >> kTileShift);
+        acc.n_pass += 1; acc.al32 += reflen[r];
+        if (span[r] > kNearSpan) farmask |= 1u << r; else acc.max_span = max(acc.max_span, span[r]);
+      }
+    }
+  }
+  if (nv == kPrepPer) {
+    *reinterpret_cast<uint4*>(f.rec + i0) =
+        make_uint4(make_rec(loc[0], span[0]), make_rec(loc[1], span[1]), make_rec(loc[2], span[2]), make_rec(loc[3], span[3]));
+  } else {
+    for (int r = 0; r < nv; ++r) f.rec[i0 + r] = make_rec(loc[r], span[r]);
+  }
+
+  // ---- sortedness + tile boundaries (tile_first) -------------------------------------------------
+  // "sorted" is judged on (contig, clamped position), i.e. on the slot keys the tile kernel relies on
+  {
+    uint32_t pt = __shfl_up_sync(0xffffffffu, (uint32_t)T[3], 1), pq = __shfl_up_sync(0xffffffffu, qq[3], 1);
+    uint32_t ptile = __shfl_up_sync(0xffffffffu, tls[3], 1);
+    bool has_prev = true;
+    if (lane == 0) {
+      has_prev = i0 > 0 && i0 - 1 < n;
+      if (has_prev) {
+        int32_t t0 = a.tid[i0 - 1], p0 = a.pos[i0 - 1];
+        pt = (uint32_t)t0;
+        if ((uint32_t)t0 < n_contigs) {
+          int64_t base = g_coff[t0]; uint32_t len = (uint32_t)g_clen[t0];
+          pq = p0 < 0 ? 0u : min((uint32_t)p0, len);
+          ptile = min((uint32_t)(base >> kTileShift) + ((((uint32_t)base & (kTile - 1)) + pq) >> kTileShift), last_tile);
+        } else { pq = 0; ptile = min(nslot_tb, last_tile); }
+      }
+    }
+    // invalid contigs compare as the largest id (they sort last, like tid -1 in a BAM)
+    uint32_t ut[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) ut[r] = (uint32_t)T[r] < n_contigs ? (uint32_t)T[r] : 0xffffffffu;
+    if (pt >= n_contigs) pt = 0xffffffffu;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (r < nv) {
+        uint32_t t0 = r ? ut[r - 1] : pt, q0 = r ? qq[r - 1] : pq;
+        bool ok = (r == 0 && !has_prev) || ut[r] > t0 || (ut[r] == t0 && (ut[r] == 0xffffffffu || qq[r] >= q0));
+        acc.unsorted |= ok ? 0u : 1u;
+      }
+    }
+    const uint32_t tl_last = nv > 0 ? (nv == 4 ? tls[3] : nv == 3 ? tls[2] : nv == 2 ? tls[1] : tls[0]) : 0u;
+    const bool bnd = nv > 0 && (!has_prev || tl_last > ptile);
+    const bool is_last = nv > 0 && (i0 + nv == n);
+    if (__any_sync(0xffffffffu, bnd || is_last))
+      prep_tile_boundaries(f.tile_first, i0, nv, has_prev ? (int64_t)ptile : -1, tls[0], tls[1], tls[2], tls[3], is_last, n,
+                           last_tile, lane);
+  }
+
+  // ---- tile_agg: +1 per start, -1 per near end (far ends are handled with the far list) ----------
+  {
+    uint32_t mn = 0xffffffffu, mx = 0u;
+    int net = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (span[r] > 0) {
+        mn = min(mn, tls[r]); mx = max(mx, tls[r]); net += 1;
+        if (span[r] <= kNearSpan) { mx = max(mx, tle[r]); net -= 1; }
+      }
+    }
+    uint32_t wmin = __reduce_min_sync(0xffffffffu, mn), wmax = __reduce_max_sync(0xffffffffu, mx);
+    if (wmin != 0xffffffffu) {
+      if (wmin == wmax) {                       // every start and end of this warp in one tile
+        int v = __reduce_add_sync(0xffffffffu, net);
+        if (lane == 0 && v != 0) atomicAdd(f.tile_agg + wmin, v);
+      } else {
+        uint32_t ptl[8];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          bool c = span[r] > 0, nr = c && span[r] <= kNearSpan;
+          ptl[r] = c ? tls[r] : 0xffffffffu;
+          ptl[4 + r] = nr ? tle[r] : 0xffffffffu;
+        }
+        prep_tile_agg_slow(f.tile_agg, ptl[0], ptl[1], ptl[2], ptl[3], ptl[4], ptl[5], ptl[6], ptl[7], lane);
+      }
+    }
+  }
+  if (__any_sync(0xffffffffu, farmask != 0)) {
+    int64_t e64[4];                               // 64-bit end slots only here
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      int64_t base = ((farmask >> r) & 1u) ? g_coff[T[r]] : 0;
+      e64[r] = base + qq[r] + span[r];
+    }
+    prep_far(f, e64[0], e64[1], e64[2], e64[3], farmask, lane);
+  }
+  return acc;
+}
+
+// Loads + filter + CIGAR reduction of the 4 reads of one thread (shared by both prep kernels).
+struct PrepReads {
+  int32_t T[4], P[4];
+  uint32_t reflen[4];     // a read's reference length fits 32 bits (BAM positions are int32)
+  unsigned passm;
+  int nv;                 // valid reads of this thread
+};
+
+__device__ __forceinline__ PrepReads prep_load_reduce(const FusedArgs& f, int64_t i0, int lane) {
   const ExpandArgs& a = f.e;
   const int32_t* __restrict__ g_tid = a.tid;
   const int32_t* __restrict__ g_pos = a.pos;
@@ -174,235 +324,231 @@ k_fused_prep(FusedArgs f) {
   const uint8_t* __restrict__ g_mapq = a.mapq;
   const uint32_t* __restrict__ g_off = a.cig_off;
   const uint32_t* __restrict__ g_cig = a.cig;
-  const int64_t* __restrict__ g_coff = a.contig_off;
-  const int32_t* __restrict__ g_clen = a.contig_len;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t n_contigs = (uint32_t)a.n_contigs;
+  // pysam __advance_samtools + bam_plp_push's UNMAP drop, branch-free:
+  // pass <=> no dropped bit, a required bit (if any are required), mapq, not (paired and not proper)
   const uint32_t drop = (uint32_t)a.filt.flag_filter | 0x4u, req = a.filt.flag_require, minq = a.filt.min_mapq;
-  const bool orph = a.filt.ignore_orphans != 0;
-  const int vec_ok = f.vec_ok;
+  const uint32_t req_none = req == 0 ? 1u : 0u, orph_mask = a.filt.ignore_orphans ? 3u : 0u;
   const int64_t n = a.n;
-  const int64_t n_groups = (n + kPrepPer - 1) / kPrepPer;
-  const int64_t g_round = (n_groups + 31) & ~(int64_t)31;     // whole warps iterate together
-  const int64_t g_stride = (int64_t)gridDim.x * kPrepThreads;
-  const uint32_t last_tile = (uint32_t)f.n_tiles;             // tile_first has n_tiles+1 entries
-  const uint32_t nslot_tb = (uint32_t)(f.n_slots >> kTileShift), nslot_bo = (uint32_t)(f.n_slots & (kTile - 1));
-  unsigned long long aligned = 0;
-  uint32_t n_pass = 0, max_span = 0;
-  int unsorted = 0;
-
+  PrepReads R;
+  uint32_t F[4], Q[4], O[5];
+  R.nv = (int)min((int64_t)kPrepPer, max((int64_t)0, n - i0));
+  if (R.nv == kPrepPer && f.vec_ok) {
+    int4 t4 = *reinterpret_cast<const int4*>(g_tid + i0);
+    int4 p4 = *reinterpret_cast<const int4*>(g_pos + i0);
+    ushort4 f4 = *reinterpret_cast<const ushort4*>(g_flag + i0);
+    uchar4 q4 = *reinterpret_cast<const uchar4*>(g_mapq + i0);
+    uint4 o4 = *reinterpret_cast<const uint4*>(g_off + i0);
+    O[4] = g_off[i0 + 4];
+    R.T[0] = t4.x; R.T[1] = t4.y; R.T[2] = t4.z; R.T[3] = t4.w;
+    R.P[0] = p4.x; R.P[1] = p4.y; R.P[2] = p4.z; R.P[3] = p4.w;
+    F[0] = f4.x; F[1] = f4.y; F[2] = f4.z; F[3] = f4.w;
+    Q[0] = q4.x; Q[1] = q4.y; Q[2] = q4.z; Q[3] = q4.w;
+    O[0] = o4.x; O[1] = o4.y; O[2] = o4.z; O[3] = o4.w;
+  } else {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      bool v = r < R.nv;
+      R.T[r] = v ? g_tid[i0 + r] : -1;
+      R.P[r] = v ? g_pos[i0 + r] : 0;
+      F[r] = v ? (uint32_t)g_flag[i0 + r] : 0x4u;
+      Q[r] = v ? (uint32_t)g_mapq[i0 + r] : 0u;
+    }
+    // padding reads get an empty CIGAR: their offsets all equal cig_off[n]
+#pragma unroll
+    for (int r = 0; r <= 4; ++r) O[r] = (i0 <= n) ? g_off[min(i0 + r, n)] : 0u;
+  }
+  unsigned passm = 0, coop = 0;
+  uint32_t op0[4], nc[4];
+  uint32_t nc_max = 0;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const bool p = (r < R.nv) & ((F[r] & drop) == 0u) & (((F[r] & req) | req_none) != 0u) & (Q[r] >= minq) &
+                   ((F[r] & orph_mask) != 1u) & ((uint32_t)R.T[r] < n_contigs);
+    nc[r] = O[r + 1] - O[r];
+    bool c = p && nc[r] > kThreadOps;
+    passm |= p ? (1u << r) : 0u;
+    coop |= c ? (1u << r) : 0u;
+    if (!p || c) nc[r] = 0;                                           // ops this thread reduces itself
+    nc_max = max(nc_max, nc[r]);
+    op0[r] = nc[r] > 0 ? __ldg(g_cig + O[r]) : 0u;                    // four independent loads
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) R.reflen[r] = cigar_ref_len(op0[r]);
 #pragma unroll 1
-  for (int64_t g = (int64_t)blockIdx.x * kPrepThreads + threadIdx.x; g < g_round; g += g_stride) {
-    const int64_t i0 = g * kPrepPer;
-    int32_t T[4], P[4];
-    uint32_t F[4], Q[4], O[5];
-    const int nv = (int)min((int64_t)kPrepPer, max((int64_t)0, n - i0));     // valid reads of this thread
-    if (nv == kPrepPer && vec_ok) {
-      int4 t4 = *reinterpret_cast<const int4*>(g_tid + i0);
-      int4 p4 = *reinterpret_cast<const int4*>(g_pos + i0);
-      ushort4 f4 = *reinterpret_cast<const ushort4*>(g_flag + i0);
-      uchar4 q4 = *reinterpret_cast<const uchar4*>(g_mapq + i0);
-      uint4 o4 = *reinterpret_cast<const uint4*>(g_off + i0);
-      O[4] = g_off[i0 + 4];
-      T[0] = t4.x; T[1] = t4.y; T[2] = t4.z; T[3] = t4.w;
-      P[0] = p4.x; P[1] = p4.y; P[2] = p4.z; P[3] = p4.w;
-      F[0] = f4.x; F[1] = f4.y; F[2] = f4.z; F[3] = f4.w;
-      Q[0] = q4.x; Q[1] = q4.y; Q[2] = q4.z; Q[3] = q4.w;
-      O[0] = o4.x; O[1] = o4.y; O[2] = o4.z; O[3] = o4.w;
-    } else {
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        bool v = r < nv;
-        T[r] = v ? g_tid[i0 + r] : -1;
-        P[r] = v ? g_pos[i0 + r] : 0;
-        F[r] = v ? (uint32_t)g_flag[i0 + r] : 0x4u;
-        Q[r] = v ? (uint32_t)g_mapq[i0 + r] : 0u;
-      }
-      // padding reads get an empty CIGAR: their offsets all equal cig_off[n]
-#pragma unroll
-      for (int r = 0; r <= 4; ++r) O[r] = (i0 <= n) ? g_off[min(i0 + r, n)] : 0u;
-    }
-
-    // ---- filter + CIGAR reduction ------------------------------------------------------------
-    unsigned passm = 0, coop = 0;
-    uint32_t reflen[4];                 // a read's reference length fits 32 bits (BAM positions are int32)
-    uint32_t op0[4];
+  for (uint32_t k = 1; k < nc_max; ++k) {                             // ops 2..4 (about 10 % of short reads)
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      // pysam __advance_samtools + bam_plp_push's UNMAP drop
-      bool p = r < nv && !(F[r] & drop) && (!req || (F[r] & req)) && Q[r] >= minq && !(orph && (F[r] & 3u) == 1u) &&
-               (uint32_t)T[r] < n_contigs;
-      uint32_t nc = O[r + 1] - O[r];
-      bool c = p && nc > kThreadOps;
-      passm |= p ? (1u << r) : 0u;
-      coop |= c ? (1u << r) : 0u;
-      op0[r] = (p && !c && nc > 0) ? __ldg(g_cig + O[r]) : 0u;          // four independent loads
-    }
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      reflen[r] = cigar_ref_len(op0[r]);
-      if (((passm & ~coop) >> r) & 1u) {
-#pragma unroll 1
-        for (uint32_t k = O[r] + 1; k < O[r + 1]; ++k) reflen[r] += cigar_ref_len(__ldg(g_cig + k));
-      }
-    }
-    // long CIGARs: the whole warp reduces one read at a time with 128-bit loads
-    while (__any_sync(0xffffffffu, coop != 0)) {
-      unsigned lanes = __ballot_sync(0xffffffffu, coop != 0);
-      int src = __ffs(lanes) - 1;
-      int r = __ffs(__shfl_sync(0xffffffffu, coop, src)) - 1;
-      uint32_t ob = r == 0 ? O[0] : r == 1 ? O[1] : r == 2 ? O[2] : O[3];
-      uint32_t oe = r == 0 ? O[1] : r == 1 ? O[2] : r == 2 ? O[3] : O[4];
-      ob = __shfl_sync(0xffffffffu, ob, src);
-      oe = __shfl_sync(0xffffffffu, oe, src);
-      unsigned long long v = warp_cigar_reflen_call(g_cig, ob, oe, lane, a.cig_aligned16);
-      if (lane == src) {
-        uint32_t v32 = v > 0x7fffffffull ? 0x7fffffffu : (uint32_t)v;
-        if (r == 0) reflen[0] = v32; else if (r == 1) reflen[1] = v32; else if (r == 2) reflen[2] = v32; else reflen[3] = v32;
-        coop &= ~(1u << r);
-      }
-    }
-
-    // ---- clipped intervals, records, tiles: 32-bit, contig relative ------------------------------
-    uint32_t klo[4], span[4], tls[4], tle[4];     // key low bits, span, start tile, end tile
-    uint32_t qq[4];                               // clamped start inside the contig
-    int32_t c_tid = INT_MIN;
-    uint32_t c_len = 0, c_blo = (uint32_t)f.n_slots, c_tb = nslot_tb, c_bo = nslot_bo;
-    unsigned farmask = 0;
-    uint32_t al32 = 0;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      if (T[r] != c_tid) {                        // contig change (once per thread in the common case)
-        c_tid = T[r];
-        if ((uint32_t)T[r] < n_contigs) {
-          int64_t base = g_coff[T[r]];
-          c_len = (uint32_t)g_clen[T[r]];
-          c_blo = (uint32_t)base; c_tb = (uint32_t)(base >> kTileShift); c_bo = (uint32_t)base & (kTile - 1);
-        } else { c_len = 0; c_blo = (uint32_t)f.n_slots; c_tb = nslot_tb; c_bo = nslot_bo; }
-      }
-      uint32_t q = P[r] < 0 ? 0u : min((uint32_t)P[r], c_len);
-      qq[r] = q;
-      klo[r] = c_blo + q;
-      tls[r] = min(c_tb + ((c_bo + q) >> kTileShift), last_tile);
-      span[r] = 0; tle[r] = tls[r];
-      if ((passm >> r) & 1u) {
-        // end = clamp(pos + reflen, 0, len), in 64 bits only for the (never negative in practice) sum
-        int64_t e64 = (int64_t)P[r] + (int64_t)reflen[r];
-        uint32_t e = e64 < 0 ? 0u : (e64 > (int64_t)c_len ? c_len : (uint32_t)e64);
-        if (e > q) {
-          span[r] = e - q; tle[r] = c_tb + ((c_bo + e) >> kTileShift);
-          n_pass += 1; al32 += reflen[r];
-          if (span[r] > kNearSpan) farmask |= 1u << r; else max_span = max(max_span, span[r]);
-        }
-      }
-    }
-    aligned += al32;
-    if (nv == kPrepPer) {
-      uint4* out = reinterpret_cast<uint4*>(f.rec + i0);
-      out[0] = make_uint4(klo[0], span[0], klo[1], span[1]);
-      out[1] = make_uint4(klo[2], span[2], klo[3], span[3]);
-    } else {
-      for (int r = 0; r < nv; ++r) f.rec[i0 + r] = make_uint2(klo[r], span[r]);
-    }
-
-    // ---- sortedness + tile boundaries (tile_first) -------------------------------------------------
-    // "sorted" is judged on (contig, clamped position), i.e. on the slot keys the tile kernel relies on
-    {
-      uint32_t pt = __shfl_up_sync(0xffffffffu, (uint32_t)T[3], 1), pq = __shfl_up_sync(0xffffffffu, qq[3], 1);
-      uint32_t ptile = __shfl_up_sync(0xffffffffu, tls[3], 1);
-      bool has_prev = true;
-      if (lane == 0) {
-        has_prev = i0 > 0 && i0 - 1 < n;
-        if (has_prev) {
-          int32_t t0 = g_tid[i0 - 1], p0 = g_pos[i0 - 1];
-          pt = (uint32_t)t0;
-          if ((uint32_t)t0 < n_contigs) {
-            int64_t base = g_coff[t0]; uint32_t len = (uint32_t)g_clen[t0];
-            pq = p0 < 0 ? 0u : min((uint32_t)p0, len);
-            ptile = min((uint32_t)(base >> kTileShift) + ((((uint32_t)base & (kTile - 1)) + pq) >> kTileShift), last_tile);
-          } else { pq = 0; ptile = min(nslot_tb, last_tile); }
-        }
-      }
-      // invalid contigs compare as the largest id (they sort last, like tid -1 in a BAM)
-      uint32_t ut[4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) ut[r] = (uint32_t)T[r] < n_contigs ? (uint32_t)T[r] : 0xffffffffu;
-      if (pt >= n_contigs) pt = 0xffffffffu;
-      bool bnd = false;
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        if (r < nv) {
-          uint32_t t0 = r ? ut[r - 1] : pt, q0 = r ? qq[r - 1] : pq;
-          bool ok = (r == 0 && !has_prev) || ut[r] > t0 || (ut[r] == t0 && (ut[r] == 0xffffffffu || qq[r] >= q0));
-          unsorted |= !ok;
-        }
-      }
-      const uint32_t tl_last = nv > 0 ? (nv == 4 ? tls[3] : nv == 3 ? tls[2] : nv == 2 ? tls[1] : tls[0]) : 0u;
-      bnd = nv > 0 && (!has_prev || tl_last > ptile);
-      const bool is_last = nv > 0 && (i0 + nv == n);
-      if (__any_sync(0xffffffffu, bnd || is_last))
-        prep_tile_boundaries(f.tile_first, i0, nv, has_prev ? (int64_t)ptile : -1, tls[0], tls[1], tls[2], tls[3], is_last, n,
-                             last_tile, lane);
-    }
-
-    // ---- tile_agg: +1 per start, -1 per near end (far ends are handled with the far list) ----------
-    {
-      uint32_t mn = 0xffffffffu, mx = 0u;
-      int net = 0;
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        if (span[r] > 0) {
-          mn = min(mn, tls[r]); mx = max(mx, tls[r]); net += 1;
-          if (span[r] <= kNearSpan) { mx = max(mx, tle[r]); net -= 1; }
-        }
-      }
-      uint32_t wmin = __reduce_min_sync(0xffffffffu, mn), wmax = __reduce_max_sync(0xffffffffu, mx);
-      if (wmin != 0xffffffffu) {
-        if (wmin == wmax) {                       // every start and end of this warp in one tile
-          int v = __reduce_add_sync(0xffffffffu, net);
-          if (lane == 0 && v != 0) atomicAdd(f.tile_agg + wmin, v);
-        } else {
-          uint32_t ptl[8];
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            bool c = span[r] > 0, nr = c && span[r] <= kNearSpan;
-            ptl[r] = c ? tls[r] : 0xffffffffu;
-            ptl[4 + r] = nr ? tle[r] : 0xffffffffu;
-          }
-          prep_tile_agg_slow(f.tile_agg, ptl[0], ptl[1], ptl[2], ptl[3], ptl[4], ptl[5], ptl[6], ptl[7], lane);
-        }
-      }
-    }
-    if (__any_sync(0xffffffffu, farmask != 0)) {
-      // 64-bit end slots only here
-      int64_t e64[4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        int64_t base = ((farmask >> r) & 1u) ? g_coff[T[r]] : 0;
-        e64[r] = base + qq[r] + span[r];
-      }
-      prep_far(f, e64[0], e64[1], e64[2], e64[3], farmask, lane);
+      uint32_t op = k < nc[r] ? __ldg(g_cig + O[r] + k) : 0u;
+      R.reflen[r] += cigar_ref_len(op);
     }
   }
+  // long CIGARs: the whole warp reduces one read at a time with 128-bit loads
+  while (__any_sync(0xffffffffu, coop != 0)) {
+    unsigned lanes = __ballot_sync(0xffffffffu, coop != 0);
+    int src = __ffs(lanes) - 1;
+    int r = __ffs(__shfl_sync(0xffffffffu, coop, src)) - 1;
+    uint32_t ob = r == 0 ? O[0] : r == 1 ? O[1] : r == 2 ? O[2] : O[3];
+    uint32_t oe = r == 0 ? O[1] : r == 1 ? O[2] : r == 2 ? O[3] : O[4];
+    ob = __shfl_sync(0xffffffffu, ob, src);
+    oe = __shfl_sync(0xffffffffu, oe, src);
+    unsigned long long v = warp_cigar_reflen_call(g_cig, ob, oe, lane, a.cig_aligned16);
+    if (lane == src) {
+      uint32_t v32 = v > 0x7fffffffull ? 0x7fffffffu : (uint32_t)v;
+      if (r == 0) R.reflen[0] = v32; else if (r == 1) R.reflen[1] = v32; else if (r == 2) R.reflen[2] = v32; else R.reflen[3] = v32;
+      coop &= ~(1u << r);
+    }
+  }
+  R.passm = passm;
+  return R;
+}
 
-  // block-level reduction of the pass counters
+// block-level reduction of the pass counters of a prep kernel
+__device__ __forceinline__ void prep_flush_counters(PassCounters* pc, uint32_t n_pass, unsigned long long aligned,
+                                                    uint32_t unsorted, uint32_t max_span) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned long long np64 = warp_sum((unsigned long long)n_pass);
   aligned = warp_sum(aligned);
-  unsorted = __any_sync(0xffffffffu, unsorted);
+  unsorted = __any_sync(0xffffffffu, unsorted != 0);
   max_span = (uint32_t)warp_max((int)max_span);
   __shared__ unsigned long long s_np[kPrepThreads / 32], s_al[kPrepThreads / 32];
   __shared__ int s_un[kPrepThreads / 32];
   __shared__ uint32_t s_ms[kPrepThreads / 32];
-  if (lane == 0) { s_np[warp] = np64; s_al[warp] = aligned; s_un[warp] = unsorted; s_ms[warp] = max_span; }
+  if (lane == 0) { s_np[warp] = np64; s_al[warp] = aligned; s_un[warp] = (int)unsorted; s_ms[warp] = max_span; }
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned long long np = 0, al = 0; int un = 0; uint32_t ms = 0;
     for (int k = 0; k < kPrepThreads / 32; ++k) { np += s_np[k]; al += s_al[k]; un |= s_un[k]; ms = max(ms, s_ms[k]); }
-    if (np) atomicAdd(&a.pc->n_pass, np);
-    if (al) atomicAdd(&a.pc->aligned_bases, al);
-    if (un) atomicOr(&a.pc->unsorted, 1);
-    if (ms) atomicMax(&a.pc->max_span, ms);
+    if (np) atomicAdd(&pc->n_pass, np);
+    if (al) atomicAdd(&pc->aligned_bases, al);
+    if (un) atomicOr(&pc->unsorted, 1);
+    if (ms) atomicMax(&pc->max_span, ms);
   }
+}
+
+// First kernel of the fused path.  4 consecutive reads per thread, 128-bit SoA loads.  This kernel
+// is the warp-uniform FAST PATH for the overwhelmingly common case -- all 128 reads of the warp (and
+// the read before them) lie in one valid contig at non-negative positions -- where the contig's
+// constants live in uniform registers, a near read's +1/-1 cancel inside one tile (no tile_agg
+// update at all unless the warp straddles a tile border) and nothing is 64-bit.  A warp iteration
+// that does not qualify is appended to f.slow_list and done by k_fused_prep_slow (prep_general).
+__global__ void __launch_bounds__(kPrepThreads, 4)
+k_fused_prep(const __grid_constant__ FusedArgs f) {
+  const ExpandArgs& a = f.e;
+  const int lane = threadIdx.x & 31;
+  const uint32_t n_contigs = (uint32_t)a.n_contigs;
+  const int64_t n = a.n;
+  const int64_t n_groups = (n + kPrepPer - 1) / kPrepPer;
+  const int64_t g_round = (n_groups + 31) & ~(int64_t)31;     // whole warps iterate together
+  const int64_t g_stride = (int64_t)gridDim.x * kPrepThreads;
+  unsigned long long aligned = 0;
+  uint32_t n_pass = 0, max_span = 0;
+  uint32_t unsorted = 0;
+  // constants of the warp's current contig, reloaded only when the contig changes
+  int32_t w_tid = -1;
+  uint32_t w_len = 0, w_tb = 0, w_bo = 0;
+
+#pragma unroll 1
+  for (int64_t g = (int64_t)blockIdx.x * kPrepThreads + threadIdx.x; g < g_round; g += g_stride) {
+    const int64_t i0 = g * kPrepPer;
+    // the read before this warp's first one (lane 0 only): sortedness and tile border across warps
+    int32_t pvT = -1, pvP = -1;
+    if (lane == 0 && i0 > 0 && i0 - 1 < n) { pvT = a.tid[i0 - 1]; pvP = a.pos[i0 - 1]; }
+    const PrepReads R = prep_load_reduce(f, i0, lane);
+    const int32_t* T = R.T;
+    const int32_t* P = R.P;
+    const uint32_t* reflen = R.reflen;
+    const unsigned passm = R.passm;
+
+    const int32_t Tw = __shfl_sync(0xffffffffu, T[0], 0);
+    bool simple = R.nv == kPrepPer && T[0] == Tw && T[1] == Tw && T[2] == Tw && T[3] == Tw && (P[0] | P[1] | P[2] | P[3]) >= 0;
+    if (lane == 0) simple = simple && pvT == Tw && pvP >= 0;
+    if (!(__all_sync(0xffffffffu, simple) && (uint32_t)Tw < n_contigs)) {
+      if (lane == 0) f.slow_list[atomicAdd(f.slow_count, 1u)] = (uint32_t)(g >> 5);
+      continue;
+    }
+    if (Tw != w_tid) {                               // warp-uniform
+      w_tid = Tw;
+      const int64_t base = a.contig_off[Tw];
+      w_len = (uint32_t)a.contig_len[Tw];
+      w_tb = (uint32_t)(base >> kTileShift); w_bo = (uint32_t)base & (kTile - 1);
+    }
+    uint32_t q[4], sq[4], rc[4];
+    uint32_t emax = 0, al32 = 0;
+    unsigned farmask = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      q[r] = min((uint32_t)P[r], w_len);
+      const uint32_t e = min((uint32_t)P[r] + reflen[r], w_len);     // P >= 0 and reflen < 2^31: no wrap
+      const uint32_t sp = ((passm >> r) & 1u) ? e - q[r] : 0u;
+      sq[r] = w_bo + q[r];
+      const bool far = sp > kNearSpan;
+      rc[r] = (sq[r] & (kTile - 1)) | ((far ? kRecFar : sp) << kTileShift);
+      n_pass += sp ? 1u : 0u;
+      al32 += sp ? reflen[r] : 0u;
+      farmask |= far ? (1u << r) : 0u;
+      max_span = max(max_span, far ? 0u : sp);
+      emax = max(emax, (sp && !far) ? (w_bo + e) >> kTileShift : 0u);
+    }
+    aligned += al32;
+    *reinterpret_cast<uint4*>(f.rec + i0) = make_uint4(rc[0], rc[1], rc[2], rc[3]);
+    // sorted inside the contig <=> clamped positions never decrease
+    uint32_t pq = __shfl_up_sync(0xffffffffu, q[3], 1);
+    if (lane == 0) pq = min((uint32_t)pvP, w_len);
+    unsorted |= (q[0] < pq || q[1] < q[0] || q[2] < q[1] || q[3] < q[2]) ? 1u : 0u;
+    // tiles relative to the contig's first tile
+    const uint32_t t0 = sq[0] >> kTileShift, t3 = sq[3] >> kTileShift;
+    uint32_t ptile = __shfl_up_sync(0xffffffffu, t3, 1);
+    if (lane == 0) ptile = (w_bo + pq) >> kTileShift;
+    const bool is_last = i0 + kPrepPer == n;
+    if (__any_sync(0xffffffffu, t3 > ptile || is_last))
+      prep_tile_boundaries(f.tile_first, i0, kPrepPer, (int64_t)(w_tb + ptile), w_tb + t0, w_tb + (sq[1] >> kTileShift),
+                           w_tb + (sq[2] >> kTileShift), w_tb + t3, is_last, n, (uint32_t)f.n_tiles, lane);
+    // tile_agg: the +1 and -1 of a near read cancel when both fall in the warp's first tile
+    const uint32_t wmax = __reduce_max_sync(0xffffffffu, max(t3, emax));
+    const uint32_t wmin = __shfl_sync(0xffffffffu, t0, 0);
+    const bool anyfar = __any_sync(0xffffffffu, farmask != 0);
+    if (wmax != wmin || anyfar) {
+      uint32_t ptl[8];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const uint32_t code = rc[r] >> kTileShift;
+        const bool c = code != 0, nr = c && code != kRecFar;
+        ptl[r] = c ? w_tb + (sq[r] >> kTileShift) : 0xffffffffu;
+        ptl[4 + r] = nr ? w_tb + ((sq[r] + code) >> kTileShift) : 0xffffffffu;
+      }
+      prep_tile_agg_slow(f.tile_agg, ptl[0], ptl[1], ptl[2], ptl[3], ptl[4], ptl[5], ptl[6], ptl[7], lane);
+      if (anyfar) {
+        const int64_t base = a.contig_off[Tw];
+        int64_t e64[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) e64[r] = base + min((uint32_t)P[r] + reflen[r], w_len);
+        prep_far(f, e64[0], e64[1], e64[2], e64[3], farmask, lane);
+      }
+    }
+  }
+  prep_flush_counters(a.pc, n_pass, aligned, unsorted, max_span);
+}
+
+// The warp iterations k_fused_prep set aside: contig changes inside the warp, the first and the
+// ragged last reads of the batch, reads without a valid contig, negative positions.
+__global__ void __launch_bounds__(kPrepThreads, 4)
+k_fused_prep_slow(const __grid_constant__ FusedArgs f) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t n_list = *f.slow_count;
+  const uint32_t w_stride = gridDim.x * (kPrepThreads / 32);
+  unsigned long long aligned = 0;
+  uint32_t n_pass = 0, max_span = 0, unsorted = 0;
+#pragma unroll 1
+  for (uint32_t w = blockIdx.x * (kPrepThreads / 32) + (threadIdx.x >> 5); w < n_list; w += w_stride) {
+    const int64_t g = ((int64_t)f.slow_list[w] << 5) + lane;
+    const int64_t i0 = g * kPrepPer;
+    const PrepReads R = prep_load_reduce(f, i0, lane);
+    PrepAcc pa = prep_general(f, i0, R.nv, R.T[0], R.T[1], R.T[2], R.T[3], R.P[0], R.P[1], R.P[2], R.P[3], R.reflen[0],
+                              R.reflen[1], R.reflen[2], R.reflen[3], R.passm, lane);
+    n_pass += pa.n_pass; aligned += pa.al32; max_span = max(max_span, pa.max_span); unsorted |= pa.unsorted;
+  }
+  prep_flush_counters(f.e.pc, n_pass, aligned, unsorted, max_span);
 }
 
 // bucket far ends by tile; tile_cnt holds the INCLUSIVE scan of the per-tile counts.  Because the
@@ -437,22 +583,46 @@ __device__ __forceinline__ TileMeta load_tile_meta(const FusedArgs& f, int64_t t
   return m;
 }
 
-constexpr int kPreOwn = 4;     // own records prefetched per thread (kPreOwn*kFusedThreads per tile)
+#ifndef MCOV_TILE_MIN_CTAS
+#define MCOV_TILE_MIN_CTAS 4
+#endif
+constexpr int kPreOwn = 4;     // own records prefetched per thread: one aligned 128-bit load
 
-__device__ __forceinline__ void prefetch_recs(const FusedArgs& f, const TileMeta& m, uint2 (&own)[kPreOwn], uint2& back) {
-#pragma unroll
-  for (int u = 0; u < kPreOwn; ++u) {
-    int64_t j = m.r0 + threadIdx.x + u * kFusedThreads;
-    own[u] = (j < m.r1) ? f.rec[j] : make_uint2(0u, 0u);
+// Records of the tile's own reads [r0,r1), four per thread from the 16-byte aligned index below r0
+// (entries outside the range are zeroed = "contributes nothing"), and one walk-back candidate.
+__device__ __forceinline__ void prefetch_recs(const FusedArgs& f, const TileMeta& m, uint4& own, uint32_t& back) {
+  const int64_t j = (m.r0 & ~(int64_t)3) + 4 * (int64_t)threadIdx.x;
+  own = make_uint4(0u, 0u, 0u, 0u);
+  if (j < m.r1) {
+    own = *reinterpret_cast<const uint4*>(f.rec + j);       // the buffer is padded past n
+    const int64_t lo = m.r0 - j, hi = m.r1 - j;               // valid lanes of the vector: [lo, hi)
+    if (lo > 0 || hi < 4) {
+      if (0 < lo || 0 >= hi) own.x = 0u;
+      if (1 < lo || 1 >= hi) own.y = 0u;
+      if (2 < lo || 2 >= hi) own.z = 0u;
+      if (3 < lo || 3 >= hi) own.w = 0u;
+    }
   }
-  int64_t jb = m.r0 - 1 - threadIdx.x;
-  back = (jb >= m.jmin) ? f.rec[jb] : make_uint2(0u, 0u);
+  const int64_t jb = m.r0 - 1 - threadIdx.x;
+  back = (jb >= m.jmin) ? f.rec[jb] : 0u;
+}
+
+// +1 at the start of an own read, +1 in the end counters if it ends inside the tile (a far
+// read's code kRecFar lies beyond any in-tile end)
+__device__ __forceinline__ void tile_own(int* s_start, int* s_end, uint32_t r) {
+  const uint32_t code = r >> kTileShift;
+  if (code) {
+    const uint32_t local = r & (kTile - 1);
+    atomicAdd(&s_start[local], 1);
+    const uint32_t el = local + code;
+    if (el < (uint32_t)kTile) atomicAdd(&s_end[el], 1);
+  }
 }
 
 // Persistent, software-pipelined: while tile k is accumulated in shared memory, scanned and
 // stored, the records of tile k+1 and the metadata of tile k+2 are already in flight.
-__global__ void __launch_bounds__(kFusedThreads, 4)
-k_fused_tile(FusedArgs f) {
+__global__ void __launch_bounds__(kFusedThreads, MCOV_TILE_MIN_CTAS)
+k_fused_tile(const __grid_constant__ FusedArgs f) {
   __shared__ __align__(16) int s_start[kTile];
   __shared__ __align__(16) int s_end[kTile];
   __shared__ int s_warp[kFusedThreads / 32];
@@ -464,7 +634,8 @@ k_fused_tile(FusedArgs f) {
   int64_t tile = blockIdx.x;
   TileMeta m_cur = load_tile_meta(f, tile);
   TileMeta m_next = load_tile_meta(f, tile + stride);
-  uint2 own[kPreOwn], back;
+  uint4 own;
+  uint32_t back;
   prefetch_recs(f, m_cur, own, back);
   int mx = 0, cap = 0;
   {
@@ -477,50 +648,30 @@ k_fused_tile(FusedArgs f) {
 #pragma unroll 1
   for (; tile < f.n_tiles; tile += stride) {
     // prefetch for the following tiles first: these loads stay in flight during the whole body
-    uint2 n_own[kPreOwn], n_back;
+    uint4 n_own;
+    uint32_t n_back;
     prefetch_recs(f, m_next, n_own, n_back);            // empty ranges when tile+stride is past the end
     TileMeta m_nn = load_tile_meta(f, tile + 2 * stride);
     const int64_t base = tile << kTileShift;
-    const uint32_t base_lo = (uint32_t)base;
 
-    // reads that start in this tile
-#pragma unroll
-    for (int u = 0; u < kPreOwn; ++u) {
-      uint2 r = own[u];
-      if (r.y) {
-        uint32_t local = r.x - base_lo;                  // < kTile for sorted input (tile_first)
-        if (local < (uint32_t)kTile) {                   // guard: unsorted input must not corrupt smem
-          atomicAdd(&s_start[local], 1);
-          uint32_t el = local + r.y;
-          if (r.y <= kNearSpan && el < (uint32_t)kTile) atomicAdd(&s_end[el], 1);
-        }
-      }
-    }
-    for (int64_t j = m_cur.r0 + threadIdx.x + kPreOwn * kFusedThreads; j < m_cur.r1; j += kFusedThreads) {
-      uint2 r = f.rec[j];                                // dense tiles: the rest straight from global
-      if (r.y) {
-        uint32_t local = r.x - base_lo;
-        if (local < (uint32_t)kTile) {
-          atomicAdd(&s_start[local], 1);
-          uint32_t el = local + r.y;
-          if (r.y <= kNearSpan && el < (uint32_t)kTile) atomicAdd(&s_end[el], 1);
-        }
-      }
-    }
+    // reads that start in this tile (tile_first ranges: every record in [r0,r1) belongs here)
+    tile_own(s_start, s_end, own.x);
+    tile_own(s_start, s_end, own.y);
+    tile_own(s_start, s_end, own.z);
+    tile_own(s_start, s_end, own.w);
+    for (int64_t j = (m_cur.r0 & ~(int64_t)3) + kPreOwn * kFusedThreads + threadIdx.x; j < m_cur.r1; j += kFusedThreads)
+      tile_own(s_start, s_end, f.rec[j]);                // dense tiles: the rest straight from global
     // near reads that started before the tile and end inside it: walk back while the start is
     // within max_span of the tile (sorted order => monotone distance).  reach <= kNearSpan = kTile,
-    // so every candidate started in the previous tile (>= jmin), which also keeps the 32-bit
-    // distance from wrapping.
+    // so every candidate started in the previous tile: exactly the records [jmin, r0).
     {
-      uint2 r = back;
+      uint32_t r = back;
       int64_t j = m_cur.r0 - 1 - threadIdx.x;
       while (j >= m_cur.jmin) {
-        uint32_t d = base_lo - r.x;                      // distance behind the tile start (>= 1)
+        const uint32_t d = (uint32_t)kTile - (r & (kTile - 1));     // distance behind the tile start (>= 1)
         if (d > reach) break;
-        if (r.y >= d && r.y <= kNearSpan) {
-          uint32_t el = r.y - d;
-          if (el < (uint32_t)kTile) atomicAdd(&s_end[el], 1);
-        }
+        const uint32_t code = r >> kTileShift;
+        if (code >= d && code <= kNearSpan) atomicAdd(&s_end[code - d], 1);
         j -= kFusedThreads;
         if (j >= m_cur.jmin) r = f.rec[j];
       }
@@ -587,8 +738,7 @@ k_fused_tile(FusedArgs f) {
     if (f.max_depth > 0 && cap_t > f.max_depth) atomicMax(f.tile_cap + tile, cap_t);
     __syncthreads();                                     // counters cleared; s_warp is rewritten by the next tile
     m_cur = m_next; m_next = m_nn;
-#pragma unroll
-    for (int u = 0; u < kPreOwn; ++u) own[u] = n_own[u];
+    own = n_own;
     back = n_back;
   }
 
@@ -620,13 +770,19 @@ __global__ void k_cap_replay(FusedArgs f, const int32_t* __restrict__ contigs, i
   const int c = contigs[k];
   const int64_t base = f.e.contig_off[c];
   const int32_t len = f.e.contig_len[c];
-  const uint32_t base_lo = (uint32_t)base;
   int32_t* d = f.depth + base;
   for (int32_t p = 0; p <= len; ++p) d[p] = 0;
-  // first read of the contig: start at the first read of the tile holding the contig's first slot
-  int64_t j = f.tile_first[base >> kTileShift];
+  // Reads in file order from the first read of the tile holding the contig's first slot.  A
+  // record stores its start relative to its tile; the tile follows from tile_first.
+  int64_t T = base >> kTileShift;
+  int64_t j = f.tile_first[T];
   const int64_t n = f.e.n;
-  while (j < n && (int32_t)(f.rec[j].x - base_lo) < 0) ++j;
+  // contig-relative start of read j (advances T as j crosses tile borders); > len = past the contig
+  auto rel = [&](int64_t jj) -> int64_t {
+    while (T + 1 <= f.n_tiles && jj >= f.tile_first[T + 1]) ++T;
+    return (T << kTileShift) + (int64_t)(f.rec[jj] & (kTile - 1)) - base;
+  };
+  while (j < n && rel(j) < 0) ++j;                  // reads of the previous contig sharing the tile
   int depth = 0;
   const int maxcnt = f.max_depth;
   int32_t p = 0;
@@ -635,21 +791,31 @@ __global__ void k_cap_replay(FusedArgs f, const int32_t* __restrict__ contigs, i
     int kept = 0;
     bool first = true;
     while (j < n) {
-      uint2 r = f.rec[j];
-      int32_t q = (int32_t)(r.x - base_lo);
+      int64_t q = rel(j);
       if (q != p || q > len) break;
+      uint32_t code = f.rec[j] >> kTileShift;
       ++j;
-      if (r.y == 0) continue;                       // filtered / empty read
+      if (code == 0) continue;                      // filtered / empty read
       bool keep = first || (depth + kept) < maxcnt; // depth = D[p-1] = reads buffered from earlier positions
       first = false;
-      if (keep) { ++kept; d[p + (int32_t)r.y] += 1; }
+      if (keep) {
+        ++kept;
+        int64_t span = code;
+        if (code == kRecFar) {                      // long span: not in the record, reduce the CIGAR again
+          int64_t rl = 0;
+          for (uint32_t o = f.e.cig_off[j - 1]; o < f.e.cig_off[j]; ++o) rl += cigar_ref_len(f.e.cig[o]);
+          int64_t e = (int64_t)p + rl;
+          span = (e > len ? len : e) - p;
+        }
+        d[p + span] += 1;
+      }
     }
     int32_t ends = d[p];
     depth += kept - ends;
     d[p] = depth;
     ++p;
-    // skip ahead over positions without starts while nothing changes: still must fold the ends in
-    if (j >= n || (int32_t)(f.rec[j].x - base_lo) > len || (int32_t)(f.rec[j].x - base_lo) < 0) {
+    // no more reads in this contig: only the ends remain to be folded in
+    if (j >= n || rel(j) > len) {
       for (; p < len; ++p) { depth -= d[p]; d[p] = depth; }
       break;
     }

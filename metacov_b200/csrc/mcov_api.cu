@@ -118,9 +118,11 @@ int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a) {
   // one zeroed scratch block: [tile_agg | tile_cnt | tile_cursor | tile_cap | scan status]
   const size_t o_agg = 0, o_cnt = o_agg + (size_t)cnt_pad * 4, o_cur = o_cnt + (size_t)cnt_pad * 4,
                o_cap = o_cur + (size_t)n_tiles * 4, o_st = (o_cap + (size_t)n_tiles * 4 + 7) & ~(size_t)7,
-               z_bytes = o_st + (size_t)scan_tiles * 8;
+               o_slow = o_st + (size_t)scan_tiles * 8, z_bytes = o_slow + 8;
+  const int64_t n_warp_iters = ((n + kPrepPer - 1) / kPrepPer + 31) / 32;
   CU(ctx->d_status.ensure(z_bytes));
-  CU(ctx->d_start_slot.ensure((size_t)(std::max<int64_t>(n, 1) + 4) * sizeof(uint2)));   // rec
+  CU(ctx->d_slow.ensure((size_t)(n_warp_iters + 1) * 4));
+  CU(ctx->d_start_slot.ensure((size_t)(std::max<int64_t>(n, 1) + 8) * sizeof(uint32_t)));   // rec (+ vector-load padding)
   CU(ctx->d_tile_off.ensure((size_t)(n_tiles + 1) * 8));                                 // tile_first
   CU(ctx->d_far_list.ensure((size_t)far_cap * 8));
   CU(ctx->d_far_sorted.ensure((size_t)far_cap * 4));
@@ -129,7 +131,7 @@ int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a) {
   CU(cudaMemsetAsync(z, 0, z_bytes, s));
   FusedArgs f;
   f.e = a;
-  f.rec = ctx->d_start_slot.as<uint2>();
+  f.rec = ctx->d_start_slot.as<uint32_t>();
   f.n_slots = ctx->n_slots;
   f.n_tiles = n_tiles;
   f.far_end = ctx->d_far_list.as<int64_t>();
@@ -144,9 +146,14 @@ int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a) {
   f.max_depth = ctx->filt.max_depth;
   auto al = [](const void* p, uintptr_t m) { return (reinterpret_cast<uintptr_t>(p) & (m - 1)) == 0; };
   f.vec_ok = (n > 0 && al(a.tid, 16) && al(a.pos, 16) && al(a.cig_off, 16) && al(a.flag, 8) && al(a.mapq, 4)) ? 1 : 0;
+  f.slow_list = ctx->d_slow.as<uint32_t>();
+  f.slow_count = reinterpret_cast<uint32_t*>(z + o_slow);
   if (n > 0) {
     const int64_t groups = (n + kPrepPer - 1) / kPrepPer;
     MCOV_LAUNCH(ctx, kKFusedPrep, (k_fused_prep<<<grid_for(groups, kPrepThreads, 8), kPrepThreads, 0, s>>>(f)));
+    CU(cudaGetLastError());
+    // the warp iterations the fast path set aside (contig changes, batch ends, unplaced reads)
+    MCOV_LAUNCH(ctx, kKFusedPrepSlow, (k_fused_prep_slow<<<grid_for(n_warp_iters * 32, kPrepThreads, 4), kPrepThreads, 0, s>>>(f)));
     CU(cudaGetLastError());
   } else {
     CU(cudaMemsetAsync(f.tile_first, 0, (size_t)(n_tiles + 1) * 8, s));
@@ -158,7 +165,7 @@ int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a) {
   CU(cudaGetLastError());
   ctx->fused_blob.assign(reinterpret_cast<const unsigned char*>(&f), reinterpret_cast<const unsigned char*>(&f) + sizeof(f));
   {
-    const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)kNumSMsB200 * 4);   // persistent: 4 CTAs per SM
+    const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)kNumSMsB200 * MCOV_TILE_MIN_CTAS);   // persistent
     MCOV_LAUNCH(ctx, kKFusedTile, (k_fused_tile<<<grid, kFusedThreads, 0, s>>>(f)));
   }
   CU(cudaGetLastError());
@@ -262,7 +269,7 @@ void mcov_destroy(mcov_ctx* ctx) {
     s.tid.release(); s.pos.release(); s.flag.release(); s.mapq.release(); s.cig_off.release(); s.cig.release();
   }
   DevBuf* bufs[] = {&ctx->d_len, &ctx->d_off, &ctx->depth_own, &ctx->d_pc, &ctx->d_status, &ctx->d_end_slot,
-                    &ctx->d_start_slot, &ctx->d_far_list, &ctx->d_tile_cnt, &ctx->d_tile_off, &ctx->d_far_sorted,
+                    &ctx->d_start_slot, &ctx->d_slow, &ctx->d_far_list, &ctx->d_tile_cnt, &ctx->d_tile_off, &ctx->d_far_sorted,
                     &ctx->d_tasks, &ctx->d_rlen, &ctx->d_rchunks, &ctx->d_rhist, &ctx->d_pool, &ctx->d_done,
                     &ctx->d_out, &ctx->d_win_slot, &ctx->d_win_n, &ctx->d_win_out};
   for (DevBuf* b : bufs) b->release();
@@ -508,7 +515,8 @@ int mcov_pass_info_get(mcov_ctx* ctx, mcov_pass_info* out) {
 static const char* kKernelNames[kKernelCount] = {
     "k_expand", "k_scan_inplace", "k_fused_prep", "k_tile_first", "k_scan_counts", "k_far_scatter", "k_fused_tile",
     "k_init_region_stats", "k_region_stats", "k_window_sums", "k_isize_hist", "k_group_count", "k_sorted_stats",
-    "memset_depth", "k_region_stats_small", "k_cap_replay", "k_unpack_reads", "k_kmer_hist", "k_region_stats_warp"};
+    "memset_depth", "k_region_stats_small", "k_cap_replay", "k_unpack_reads", "k_kmer_hist", "k_region_stats_warp",
+    "k_fused_prep_slow"};
 
 int64_t mcov_launch_count(const mcov_ctx* ctx) { return ctx ? ctx->n_launches : 0; }
 
@@ -685,21 +693,29 @@ int mcov_region_stats_run(mcov_ctx* ctx, int64_t g, const int32_t* tid, const in
   CU(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
   RegionPlan& rp = ctx->plan;
-  // results and the pending verdict come back through one pinned staging buffer (a pageable
-  // destination would make the copy synchronous and slower)
+  // Results and the pending verdict come back through pinned memory (a pageable destination would
+  // make the copy synchronous and slow): straight into host_out when the caller's buffer is itself
+  // pinned, else through the context's staging buffer.
   const size_t out_bytes = (size_t)g * sizeof(mcov_region_stats);
-  CU(ctx->h_pin.ensure(out_bytes + sizeof(PassCounters)));
+  bool direct = false;
+  if (g > 0) {
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, host_out) == cudaSuccess) direct = (pa.type == cudaMemoryTypeHost);
+    else (void)cudaGetLastError();
+  }
+  CU(ctx->h_pin.ensure((direct ? 0 : out_bytes) + sizeof(PassCounters)));
+  char* stage = ctx->h_pin.as<char>();
   if (g > 0) {
     CU(ctx->d_out.ensure(out_bytes));
     int rc = stats_launch(ctx, g, tid, start, end, breadth_n, ctx->d_out.as<mcov_region_stats>());
     if (rc) return rc;
-    CU(cudaMemcpyAsync(ctx->h_pin.p, ctx->d_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(direct ? (void*)host_out : (void*)stage, ctx->d_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
   }
-  PassCounters* hp = reinterpret_cast<PassCounters*>(ctx->h_pin.as<char>() + out_bytes);
+  PassCounters* hp = reinterpret_cast<PassCounters*>(stage + (direct ? 0 : out_bytes));
   if (ctx->verdict_pending) CU(cudaMemcpyAsync(hp, ctx->d_pc.p, sizeof(PassCounters), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
   if (ctx->verdict_pending) { PassCounters h = *hp; int vr = fused_verdict(ctx, h); if (vr) return vr; }
-  if (g > 0) std::memcpy(host_out, ctx->h_pin.p, out_bytes);
+  if (g > 0 && !direct) std::memcpy(host_out, stage, out_bytes);
   // regions whose depth left the counting histogram's range: exact statistics by a GPU radix sort
   // of the region (rare: needs max_depth raised above 8190)
   bool redo = false;

@@ -74,6 +74,7 @@ class CoverageEngine:
         if filt is not None:
             self.set_filter(**filt)
         self._keep = None
+        self._pinned = None
 
     # -- plumbing ---------------------------------------------------------
     def _check(self, rc):
@@ -199,10 +200,20 @@ class CoverageEngine:
         g = len(tid)
         if not (len(start) == len(end) == g):
             raise ValueError("tid/start/end lengths differ")
-        out = np.zeros(g, dtype=_capi.REGION_STATS_DTYPE)
+        out = self._stats_buffer(g)
         self._check(lib.mcov_region_stats_run(self._ctx, g, _capi.ptr(tid), _capi.ptr(start), _capi.ptr(end),
                                               int(breadth_n), _capi.ptr(out)))
         return out
+
+    def _stats_buffer(self, g):
+        """Result records land in a pinned host buffer owned by the engine and reused between calls
+        (the returned array is a view: copy it to keep it across the next region_stats call)."""
+        if g <= 1024:
+            return np.zeros(g, dtype=_capi.REGION_STATS_DTYPE)
+        if self._pinned is None or self._pinned.numel() < g * 64:
+            import torch
+            self._pinned = torch.empty(g * 64 + 64, dtype=torch.uint8).pin_memory()
+        return self._pinned.numpy()[:g * 64].view(_capi.REGION_STATS_DTYPE)
 
     def region_stats_enqueue(self, tid, start, end, out, breadth_n=1):
         """Asynchronous: write len(tid) records into the CUDA uint8 tensor ``out`` (>= 64 bytes per
