@@ -359,13 +359,8 @@ def run_ours(args):
         "memset_depth": 4 * slots,
     }
     kernels = {}
-    # the prep pass is two launches (fast path + the warp iterations it sets aside): its bytes are
-    # counted once, against the sum of both times
-    prep_extra = kt["k_fused_prep_slow"][1] / max(kt["k_fused_prep_slow"][0], 1) if "k_fused_prep_slow" in kt else 0.0
     for name, (n_l, tot) in kt.items():
         per = tot / max(n_l, 1)
-        if name == "k_fused_prep":
-            per += prep_extra
         ent = {"launches": int(n_l), "ms_per_launch": per, "share_of_step": per * (n_l / args.steps) / ms_step}
         if name in alg_bytes and per > 0:
             ent["algorithmic_bytes"] = alg_bytes[name]

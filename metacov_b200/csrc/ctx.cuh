@@ -45,7 +45,6 @@ enum PassState { kIdle = 0, kAccumulating = 1, kDepthReady = 2 };
 enum KernelId {
   kKExpand = 0, kKScan, kKFusedPrep, kKTileFirst, kKScanCounts, kKFarScatter, kKFusedTile,
   kKInitStats, kKRegionStats, kKWindowSums, kKIsizeHist, kKGroupCount, kKSortedStats, kKClear, kKRegionStatsSmall, kKCapReplay, kKUnpack, kKKmerHist, kKRegionStatsWarp,
-  kKFusedPrepSlow,
   kKernelCount
 };
 
@@ -101,7 +100,7 @@ struct mcov_ctx {
   std::vector<unsigned char> fused_blob;   // FusedArgs of the last fused pass (k_fused.cuh), for the cap replay
 
   // fused (sorted) path scratch
-  mcov::DevBuf d_end_slot, d_start_slot, d_slow, d_far_list, d_tile_cnt, d_tile_off, d_far_sorted;
+  mcov::DevBuf d_end_slot, d_start_slot, d_far_list, d_tile_cnt, d_tile_off, d_far_sorted;
 
   // stats scratch
   mcov::DevBuf d_tasks, d_rlen, d_rchunks, d_rhist, d_pool, d_done, d_out, d_win_slot, d_win_n, d_win_out;

@@ -9,25 +9,28 @@
 //                  128-bit loads: filter + CIGAR reduce, emits the 4-byte record
 //                  rec[i] = {offset of the start slot in its tile, clipped span}
 //                  (span 0 = read contributes nothing).  Because the reads are
-//                  sorted it also produces, with warp-aggregated updates,
+//                  sorted it also produces
 //                    tile_first[T]  first read whose start slot >= T*kTile
-//                    tile_agg[T]    (#starts - #ends) falling in tile T
 //                  and, for reads whose span exceeds kNearSpan ("far" reads:
-//                  long reads, spliced reads), the end slot list + per-tile
-//                  far-end counts.
+//                  long reads, spliced reads), the end slot list, per-tile
+//                  far-end counts and tile_agg[T] = (#far starts - #far ends) in T.
 //   k_scan_inplace one small scan over [tile_agg | far counts]: the inclusive
-//                  sum of tile_agg up to T-1 IS the depth entering tile T, so
-//                  the tile kernel needs no look-back and no ordering.
+//                  sum of tile_agg up to T-1 is the number of FAR reads open at
+//                  the start of tile T.
 //   k_far_scatter  bucket the far ends by tile (counting sort).
 //   k_fused_tile   one CTA per tile of kTile slots: +1/-1 of the tile's reads
 //                  go to SHARED-memory counters (starts and ends kept apart),
 //                  the ends of near reads that started before the tile are
 //                  found by walking back at most max_span slots in the sorted
-//                  order, far ends come from the tile's bucket; block scan
-//                  from the known carry; 128-bit streaming stores.  Keeping
-//                  starts and ends apart gives htslib's max_depth no-op
-//                  condition exactly: cap[p] = depth[p-1] + starts[p]
-//                  = depth[p] + ends[p].
+//                  order -- and because kNearSpan = kTile every near read that
+//                  is open at the tile border ends inside the tile, so THE
+//                  NUMBER OF WALK-BACK HITS IS THE NEAR DEPTH ENTERING THE TILE:
+//                  no look-back, no ordering between CTAs, and no per-tile
+//                  aggregate for near reads at all.  Far ends come from the
+//                  tile's bucket; block scan from the carry; 128-bit streaming
+//                  stores.  Keeping starts and ends apart gives htslib's
+//                  max_depth no-op condition exactly: cap[p] = depth[p-1] +
+//                  starts[p] = depth[p] + ends[p].
 //
 // HBM bytes (algorithmic): prep 15R + 4*sum(n_cigar of passing reads) + 4R;
 // tile 4R + 4(L+C).
@@ -53,7 +56,7 @@ struct FusedArgs {
   int64_t n_tiles;
   int64_t* far_end;           // [far_cap] end slots of far reads
   uint32_t far_cap;
-  int32_t* tile_agg;          // [cnt_pad] (#starts - #ends) per tile -> inclusive scan in place
+  int32_t* tile_agg;          // [cnt_pad] (#far starts - #far ends) per tile -> inclusive scan in place
   uint32_t* tile_cnt;         // [cnt_pad] far ends per tile -> inclusive scan in place (follows tile_agg)
   uint32_t* tile_cursor;      // [n_tiles] scatter cursors
   uint32_t* far_sorted;       // [far_cap] in-tile offsets bucketed by tile
@@ -62,8 +65,6 @@ struct FusedArgs {
   int32_t* tile_cap;          // [n_tiles] max of depth[p-1]+starts[p] in the tile, written only when > max_depth
   int32_t max_depth;          // htslib maxcnt (<= 0: cap disabled)
   int vec_ok;                 // SoA base pointers aligned for 128-bit loads
-  uint32_t* slow_list;        // warp iterations (group index >> 5) left to k_fused_prep_slow
-  uint32_t* slow_count;
 };
 
 // slot key of a read: contig offset + clamped position; reads without a valid
@@ -111,32 +112,9 @@ __device__ __noinline__ void prep_tile_boundaries(int64_t* tile_first, int64_t i
   }
 }
 
-// Rare path: the starts / near ends of this warp fall into more than one tile.  pt[k] = tile or
-// 0xffffffff (none), k<4 starts (+1), k>=4 ends (-1).  Entered by the whole warp.
-__device__ __noinline__ void prep_tile_agg_slow(int32_t* tile_agg, uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3,
-                                                uint32_t p4, uint32_t p5, uint32_t p6, uint32_t p7, int lane) {
-  uint32_t pt[8] = {p0, p1, p2, p3, p4, p5, p6, p7};
-#pragma unroll 1
-  for (int iter = 0; iter < 6; ++iter) {
-    uint32_t m = 0xffffffffu;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) m = min(m, pt[k]);
-    uint32_t Tm = __reduce_min_sync(0xffffffffu, m);
-    if (Tm == 0xffffffffu) return;
-    int local = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) if (pt[k] == Tm) { local += (k < 4) ? 1 : -1; pt[k] = 0xffffffffu; }
-    int v = __reduce_add_sync(0xffffffffu, local);
-    if (lane == 0 && v != 0) atomicAdd(tile_agg + Tm, v);
-  }
-  // reads of this warp spread over many tiles (sparse data): direct updates
-#pragma unroll
-  for (int k = 0; k < 8; ++k) if (pt[k] != 0xffffffffu) atomicAdd(tile_agg + pt[k], (k < 4) ? 1 : -1);
-}
-
 // Rare path: some read of this warp spans more than kNearSpan slots.  Entered by the whole warp.
-__device__ __noinline__ void prep_far(const FusedArgs& f, int64_t e0, int64_t e1, int64_t e2, int64_t e3, unsigned farmask,
-                                      int lane) {
+__device__ __noinline__ void prep_far(const FusedArgs& f, uint32_t st0, uint32_t st1, uint32_t st2, uint32_t st3, int64_t e0,
+                                      int64_t e1, int64_t e2, int64_t e3, unsigned farmask, int lane) {
   int nfar = __popc(farmask);
   int incl = nfar;
 #pragma unroll
@@ -153,10 +131,12 @@ __device__ __noinline__ void prep_far(const FusedArgs& f, int64_t e0, int64_t e1
   for (int r = 0; r < 4; ++r) {
     if (farmask & (1u << r)) {
       int64_t e = r == 0 ? e0 : r == 1 ? e1 : r == 2 ? e2 : e3;
-      if (idx < f.far_cap) {
+      uint32_t st = r == 0 ? st0 : r == 1 ? st1 : r == 2 ? st2 : st3;
+      if (idx < f.far_cap) {                      // (past the cap the pass is rejected: MCOV_ERR_RANGE)
         f.far_end[idx] = e;
         atomicAdd(f.tile_cnt + (e >> kTileShift), 1u);
-        atomicAdd(f.tile_agg + (e >> kTileShift), -1);
+        atomicAdd(f.tile_agg + st, 1);            // a far read is open from its start tile ...
+        atomicAdd(f.tile_agg + (e >> kTileShift), -1);   // ... to its end tile
       }
       ++idx;
     }
@@ -192,7 +172,7 @@ __device__ __forceinline__ PrepAcc prep_general(const FusedArgs& f, int64_t i0, 
   const int32_t T[4] = {T0, T1, T2, T3}, P[4] = {P0, P1, P2, P3};
   const uint32_t reflen[4] = {R0, R1, R2, R3};
   PrepAcc acc = {0u, 0u, 0u, 0u};
-  uint32_t span[4], tls[4], tle[4], qq[4], loc[4];
+  uint32_t span[4], tls[4], qq[4], loc[4];
   int32_t c_tid = INT_MIN;
   uint32_t c_len = 0, c_tb = nslot_tb, c_bo = nslot_bo;
   unsigned farmask = 0;
@@ -210,13 +190,13 @@ __device__ __forceinline__ PrepAcc prep_general(const FusedArgs& f, int64_t i0, 
     qq[r] = q;
     loc[r] = (c_bo + q) & (kTile - 1);
     tls[r] = min(c_tb + ((c_bo + q) >> kTileShift), last_tile);
-    span[r] = 0; tle[r] = tls[r];
+    span[r] = 0;
     if ((passm >> r) & 1u) {
       // end = clamp(pos + reflen, 0, len), in 64 bits only for the (never negative in practice) sum
       int64_t e64 = (int64_t)P[r] + (int64_t)reflen[r];
       uint32_t e = e64 < 0 ? 0u : (e64 > (int64_t)c_len ? c_len : (uint32_t)e64);
       if (e > q) {
-        span[r] = e - q; tle[r] = c_tb + ((c_bo + e) >> kTileShift);
+        span[r] = e - q;
         acc.n_pass += 1; acc.al32 += reflen[r];
         if (span[r] > kNearSpan) farmask |= 1u << r; else acc.max_span = max(acc.max_span, span[r]);
       }
@@ -268,34 +248,7 @@ __device__ __forceinline__ PrepAcc prep_general(const FusedArgs& f, int64_t i0, 
                            last_tile, lane);
   }
 
-  // ---- tile_agg: +1 per start, -1 per near end (far ends are handled with the far list) ----------
-  {
-    uint32_t mn = 0xffffffffu, mx = 0u;
-    int net = 0;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      if (span[r] > 0) {
-        mn = min(mn, tls[r]); mx = max(mx, tls[r]); net += 1;
-        if (span[r] <= kNearSpan) { mx = max(mx, tle[r]); net -= 1; }
-      }
-    }
-    uint32_t wmin = __reduce_min_sync(0xffffffffu, mn), wmax = __reduce_max_sync(0xffffffffu, mx);
-    if (wmin != 0xffffffffu) {
-      if (wmin == wmax) {                       // every start and end of this warp in one tile
-        int v = __reduce_add_sync(0xffffffffu, net);
-        if (lane == 0 && v != 0) atomicAdd(f.tile_agg + wmin, v);
-      } else {
-        uint32_t ptl[8];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          bool c = span[r] > 0, nr = c && span[r] <= kNearSpan;
-          ptl[r] = c ? tls[r] : 0xffffffffu;
-          ptl[4 + r] = nr ? tle[r] : 0xffffffffu;
-        }
-        prep_tile_agg_slow(f.tile_agg, ptl[0], ptl[1], ptl[2], ptl[3], ptl[4], ptl[5], ptl[6], ptl[7], lane);
-      }
-    }
-  }
+  // ---- far reads: end list, per-tile far-end counts, far-open aggregate ---------------------------
   if (__any_sync(0xffffffffu, farmask != 0)) {
     int64_t e64[4];                               // 64-bit end slots only here
 #pragma unroll
@@ -303,7 +256,7 @@ __device__ __forceinline__ PrepAcc prep_general(const FusedArgs& f, int64_t i0, 
       int64_t base = ((farmask >> r) & 1u) ? g_coff[T[r]] : 0;
       e64[r] = base + qq[r] + span[r];
     }
-    prep_far(f, e64[0], e64[1], e64[2], e64[3], farmask, lane);
+    prep_far(f, tls[0], tls[1], tls[2], tls[3], e64[0], e64[1], e64[2], e64[3], farmask, lane);
   }
   return acc;
 }
@@ -426,12 +379,12 @@ __device__ __forceinline__ void prep_flush_counters(PassCounters* pc, uint32_t n
   }
 }
 
-// First kernel of the fused path.  4 consecutive reads per thread, 128-bit SoA loads.  This kernel
-// is the warp-uniform FAST PATH for the overwhelmingly common case -- all 128 reads of the warp (and
-// the read before them) lie in one valid contig at non-negative positions -- where the contig's
-// constants live in uniform registers, a near read's +1/-1 cancel inside one tile (no tile_agg
-// update at all unless the warp straddles a tile border) and nothing is 64-bit.  A warp iteration
-// that does not qualify is appended to f.slow_list and done by k_fused_prep_slow (prep_general).
+// First kernel of the fused path.  4 consecutive reads per thread, 128-bit SoA loads; filter and
+// CIGAR reduction are common, then a warp-uniform FAST PATH takes the overwhelmingly common case --
+// all 128 reads of the warp (and the read before them) lie in one valid contig at non-negative
+// positions -- where the contig's constants live in uniform registers and nothing is 64-bit.  Near
+// reads need no per-tile aggregate (see k_fused_tile), so the only cross-thread work is the tile
+// border detection.  Any other warp iteration takes prep_general.
 __global__ void __launch_bounds__(kPrepThreads, 4)
 k_fused_prep(const __grid_constant__ FusedArgs f) {
   const ExpandArgs& a = f.e;
@@ -464,7 +417,9 @@ k_fused_prep(const __grid_constant__ FusedArgs f) {
     bool simple = R.nv == kPrepPer && T[0] == Tw && T[1] == Tw && T[2] == Tw && T[3] == Tw && (P[0] | P[1] | P[2] | P[3]) >= 0;
     if (lane == 0) simple = simple && pvT == Tw && pvP >= 0;
     if (!(__all_sync(0xffffffffu, simple) && (uint32_t)Tw < n_contigs)) {
-      if (lane == 0) f.slow_list[atomicAdd(f.slow_count, 1u)] = (uint32_t)(g >> 5);
+      const PrepAcc pa = prep_general(f, i0, R.nv, T[0], T[1], T[2], T[3], P[0], P[1], P[2], P[3], reflen[0], reflen[1],
+                                      reflen[2], reflen[3], passm, lane);
+      n_pass += pa.n_pass; aligned += pa.al32; max_span = max(max_span, pa.max_span); unsorted |= pa.unsorted;
       continue;
     }
     if (Tw != w_tid) {                               // warp-uniform
@@ -474,7 +429,7 @@ k_fused_prep(const __grid_constant__ FusedArgs f) {
       w_tb = (uint32_t)(base >> kTileShift); w_bo = (uint32_t)base & (kTile - 1);
     }
     uint32_t q[4], sq[4], rc[4];
-    uint32_t emax = 0, al32 = 0;
+    uint32_t al32 = 0;
     unsigned farmask = 0;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -488,7 +443,6 @@ k_fused_prep(const __grid_constant__ FusedArgs f) {
       al32 += sp ? reflen[r] : 0u;
       farmask |= far ? (1u << r) : 0u;
       max_span = max(max_span, far ? 0u : sp);
-      emax = max(emax, (sp && !far) ? (w_bo + e) >> kTileShift : 0u);
     }
     aligned += al32;
     *reinterpret_cast<uint4*>(f.rec + i0) = make_uint4(rc[0], rc[1], rc[2], rc[3]);
@@ -497,58 +451,24 @@ k_fused_prep(const __grid_constant__ FusedArgs f) {
     if (lane == 0) pq = min((uint32_t)pvP, w_len);
     unsorted |= (q[0] < pq || q[1] < q[0] || q[2] < q[1] || q[3] < q[2]) ? 1u : 0u;
     // tiles relative to the contig's first tile
-    const uint32_t t0 = sq[0] >> kTileShift, t3 = sq[3] >> kTileShift;
+    const uint32_t t3 = sq[3] >> kTileShift;
     uint32_t ptile = __shfl_up_sync(0xffffffffu, t3, 1);
     if (lane == 0) ptile = (w_bo + pq) >> kTileShift;
     const bool is_last = i0 + kPrepPer == n;
     if (__any_sync(0xffffffffu, t3 > ptile || is_last))
-      prep_tile_boundaries(f.tile_first, i0, kPrepPer, (int64_t)(w_tb + ptile), w_tb + t0, w_tb + (sq[1] >> kTileShift),
-                           w_tb + (sq[2] >> kTileShift), w_tb + t3, is_last, n, (uint32_t)f.n_tiles, lane);
-    // tile_agg: the +1 and -1 of a near read cancel when both fall in the warp's first tile
-    const uint32_t wmax = __reduce_max_sync(0xffffffffu, max(t3, emax));
-    const uint32_t wmin = __shfl_sync(0xffffffffu, t0, 0);
-    const bool anyfar = __any_sync(0xffffffffu, farmask != 0);
-    if (wmax != wmin || anyfar) {
-      uint32_t ptl[8];
+      prep_tile_boundaries(f.tile_first, i0, kPrepPer, (int64_t)(w_tb + ptile), w_tb + (sq[0] >> kTileShift),
+                           w_tb + (sq[1] >> kTileShift), w_tb + (sq[2] >> kTileShift), w_tb + t3, is_last, n,
+                           (uint32_t)f.n_tiles, lane);
+    if (__any_sync(0xffffffffu, farmask != 0)) {
+      const int64_t base = a.contig_off[Tw];
+      int64_t e64[4];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const uint32_t code = rc[r] >> kTileShift;
-        const bool c = code != 0, nr = c && code != kRecFar;
-        ptl[r] = c ? w_tb + (sq[r] >> kTileShift) : 0xffffffffu;
-        ptl[4 + r] = nr ? w_tb + ((sq[r] + code) >> kTileShift) : 0xffffffffu;
-      }
-      prep_tile_agg_slow(f.tile_agg, ptl[0], ptl[1], ptl[2], ptl[3], ptl[4], ptl[5], ptl[6], ptl[7], lane);
-      if (anyfar) {
-        const int64_t base = a.contig_off[Tw];
-        int64_t e64[4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) e64[r] = base + min((uint32_t)P[r] + reflen[r], w_len);
-        prep_far(f, e64[0], e64[1], e64[2], e64[3], farmask, lane);
-      }
+      for (int r = 0; r < 4; ++r) e64[r] = base + min((uint32_t)P[r] + reflen[r], w_len);
+      prep_far(f, w_tb + (sq[0] >> kTileShift), w_tb + (sq[1] >> kTileShift), w_tb + (sq[2] >> kTileShift), w_tb + t3, e64[0],
+               e64[1], e64[2], e64[3], farmask, lane);
     }
   }
   prep_flush_counters(a.pc, n_pass, aligned, unsorted, max_span);
-}
-
-// The warp iterations k_fused_prep set aside: contig changes inside the warp, the first and the
-// ragged last reads of the batch, reads without a valid contig, negative positions.
-__global__ void __launch_bounds__(kPrepThreads, 4)
-k_fused_prep_slow(const __grid_constant__ FusedArgs f) {
-  const int lane = threadIdx.x & 31;
-  const uint32_t n_list = *f.slow_count;
-  const uint32_t w_stride = gridDim.x * (kPrepThreads / 32);
-  unsigned long long aligned = 0;
-  uint32_t n_pass = 0, max_span = 0, unsorted = 0;
-#pragma unroll 1
-  for (uint32_t w = blockIdx.x * (kPrepThreads / 32) + (threadIdx.x >> 5); w < n_list; w += w_stride) {
-    const int64_t g = ((int64_t)f.slow_list[w] << 5) + lane;
-    const int64_t i0 = g * kPrepPer;
-    const PrepReads R = prep_load_reduce(f, i0, lane);
-    PrepAcc pa = prep_general(f, i0, R.nv, R.T[0], R.T[1], R.T[2], R.T[3], R.P[0], R.P[1], R.P[2], R.P[3], R.reflen[0],
-                              R.reflen[1], R.reflen[2], R.reflen[3], R.passm, lane);
-    n_pass += pa.n_pass; aligned += pa.al32; max_span = max(max_span, pa.max_span); unsorted |= pa.unsorted;
-  }
-  prep_flush_counters(f.e.pc, n_pass, aligned, unsorted, max_span);
 }
 
 // bucket far ends by tile; tile_cnt holds the INCLUSIVE scan of the per-tile counts.  Because the
@@ -627,6 +547,7 @@ k_fused_tile(const __grid_constant__ FusedArgs f) {
   __shared__ __align__(16) int s_end[kTile];
   __shared__ int s_warp[kFusedThreads / 32];
   __shared__ int s_warp2[kFusedThreads / 32];
+  __shared__ int s_open[2];                             // near reads open at the tile border (double-buffered)
   PassCounters* pc = f.e.pc;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t stride = gridDim.x;
@@ -642,11 +563,13 @@ k_fused_tile(const __grid_constant__ FusedArgs f) {
     int4* z0 = reinterpret_cast<int4*>(s_start);
     int4* z1 = reinterpret_cast<int4*>(s_end);
     for (int k = threadIdx.x; k < kTile / 4; k += kFusedThreads) { z0[k] = make_int4(0, 0, 0, 0); z1[k] = make_int4(0, 0, 0, 0); }
+    if (threadIdx.x < 2) s_open[threadIdx.x] = 0;
   }
   __syncthreads();
+  int par = 0;
 
 #pragma unroll 1
-  for (; tile < f.n_tiles; tile += stride) {
+  for (; tile < f.n_tiles; tile += stride, par ^= 1) {
     // prefetch for the following tiles first: these loads stay in flight during the whole body
     uint4 n_own;
     uint32_t n_back;
@@ -664,17 +587,22 @@ k_fused_tile(const __grid_constant__ FusedArgs f) {
     // near reads that started before the tile and end inside it: walk back while the start is
     // within max_span of the tile (sorted order => monotone distance).  reach <= kNearSpan = kTile,
     // so every candidate started in the previous tile: exactly the records [jmin, r0).
+    // Each hit is a read that covers the last slot before the tile, and all of them end in this
+    // tile: their number is the near depth entering the tile.
     {
       uint32_t r = back;
       int64_t j = m_cur.r0 - 1 - threadIdx.x;
+      int open = 0;
       while (j >= m_cur.jmin) {
         const uint32_t d = (uint32_t)kTile - (r & (kTile - 1));     // distance behind the tile start (>= 1)
         if (d > reach) break;
         const uint32_t code = r >> kTileShift;
-        if (code >= d && code <= kNearSpan) atomicAdd(&s_end[code - d], 1);
+        if (code >= d && code <= kNearSpan) { atomicAdd(&s_end[code - d], 1); ++open; }
         j -= kFusedThreads;
         if (j >= m_cur.jmin) r = f.rec[j];
       }
+      open = __reduce_add_sync(0xffffffffu, open);
+      if (lane == 0 && open) atomicAdd(&s_open[par], open);
     }
     // far ends bucketed for this tile
     for (uint32_t k = m_cur.k0 + threadIdx.x; k < m_cur.k1; k += kFusedThreads)
@@ -718,7 +646,8 @@ k_fused_tile(const __grid_constant__ FusedArgs f) {
       int4* z1 = reinterpret_cast<int4*>(s_end);
       for (int k = threadIdx.x; k < kTile / 4; k += kFusedThreads) { z0[k] = make_int4(0, 0, 0, 0); z1[k] = make_int4(0, 0, 0, 0); }
     }
-    int off = m_cur.carry;
+    int off = m_cur.carry + s_open[par];                 // far reads open at the border + near reads open at the border
+    if (threadIdx.x == 0) s_open[par ^ 1] = 0;           // the other buffer: last read before the previous end-of-body barrier
 #pragma unroll
     for (int k = 0; k < kFusedThreads / 32; ++k) off += (k < warp) ? s_warp[k] : 0;
     int4* out = reinterpret_cast<int4*>(f.depth + base);

@@ -118,10 +118,8 @@ int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a) {
   // one zeroed scratch block: [tile_agg | tile_cnt | tile_cursor | tile_cap | scan status]
   const size_t o_agg = 0, o_cnt = o_agg + (size_t)cnt_pad * 4, o_cur = o_cnt + (size_t)cnt_pad * 4,
                o_cap = o_cur + (size_t)n_tiles * 4, o_st = (o_cap + (size_t)n_tiles * 4 + 7) & ~(size_t)7,
-               o_slow = o_st + (size_t)scan_tiles * 8, z_bytes = o_slow + 8;
-  const int64_t n_warp_iters = ((n + kPrepPer - 1) / kPrepPer + 31) / 32;
+               z_bytes = o_st + (size_t)scan_tiles * 8;
   CU(ctx->d_status.ensure(z_bytes));
-  CU(ctx->d_slow.ensure((size_t)(n_warp_iters + 1) * 4));
   CU(ctx->d_start_slot.ensure((size_t)(std::max<int64_t>(n, 1) + 8) * sizeof(uint32_t)));   // rec (+ vector-load padding)
   CU(ctx->d_tile_off.ensure((size_t)(n_tiles + 1) * 8));                                 // tile_first
   CU(ctx->d_far_list.ensure((size_t)far_cap * 8));
@@ -146,14 +144,9 @@ int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a) {
   f.max_depth = ctx->filt.max_depth;
   auto al = [](const void* p, uintptr_t m) { return (reinterpret_cast<uintptr_t>(p) & (m - 1)) == 0; };
   f.vec_ok = (n > 0 && al(a.tid, 16) && al(a.pos, 16) && al(a.cig_off, 16) && al(a.flag, 8) && al(a.mapq, 4)) ? 1 : 0;
-  f.slow_list = ctx->d_slow.as<uint32_t>();
-  f.slow_count = reinterpret_cast<uint32_t*>(z + o_slow);
   if (n > 0) {
     const int64_t groups = (n + kPrepPer - 1) / kPrepPer;
     MCOV_LAUNCH(ctx, kKFusedPrep, (k_fused_prep<<<grid_for(groups, kPrepThreads, 8), kPrepThreads, 0, s>>>(f)));
-    CU(cudaGetLastError());
-    // the warp iterations the fast path set aside (contig changes, batch ends, unplaced reads)
-    MCOV_LAUNCH(ctx, kKFusedPrepSlow, (k_fused_prep_slow<<<grid_for(n_warp_iters * 32, kPrepThreads, 4), kPrepThreads, 0, s>>>(f)));
     CU(cudaGetLastError());
   } else {
     CU(cudaMemsetAsync(f.tile_first, 0, (size_t)(n_tiles + 1) * 8, s));
@@ -269,7 +262,7 @@ void mcov_destroy(mcov_ctx* ctx) {
     s.tid.release(); s.pos.release(); s.flag.release(); s.mapq.release(); s.cig_off.release(); s.cig.release();
   }
   DevBuf* bufs[] = {&ctx->d_len, &ctx->d_off, &ctx->depth_own, &ctx->d_pc, &ctx->d_status, &ctx->d_end_slot,
-                    &ctx->d_start_slot, &ctx->d_slow, &ctx->d_far_list, &ctx->d_tile_cnt, &ctx->d_tile_off, &ctx->d_far_sorted,
+                    &ctx->d_start_slot, &ctx->d_far_list, &ctx->d_tile_cnt, &ctx->d_tile_off, &ctx->d_far_sorted,
                     &ctx->d_tasks, &ctx->d_rlen, &ctx->d_rchunks, &ctx->d_rhist, &ctx->d_pool, &ctx->d_done,
                     &ctx->d_out, &ctx->d_win_slot, &ctx->d_win_n, &ctx->d_win_out};
   for (DevBuf* b : bufs) b->release();
@@ -515,8 +508,7 @@ int mcov_pass_info_get(mcov_ctx* ctx, mcov_pass_info* out) {
 static const char* kKernelNames[kKernelCount] = {
     "k_expand", "k_scan_inplace", "k_fused_prep", "k_tile_first", "k_scan_counts", "k_far_scatter", "k_fused_tile",
     "k_init_region_stats", "k_region_stats", "k_window_sums", "k_isize_hist", "k_group_count", "k_sorted_stats",
-    "memset_depth", "k_region_stats_small", "k_cap_replay", "k_unpack_reads", "k_kmer_hist", "k_region_stats_warp",
-    "k_fused_prep_slow"};
+    "memset_depth", "k_region_stats_small", "k_cap_replay", "k_unpack_reads", "k_kmer_hist", "k_region_stats_warp"};
 
 int64_t mcov_launch_count(const mcov_ctx* ctx) { return ctx ? ctx->n_launches : 0; }
 
