@@ -41,10 +41,14 @@
 
 namespace mcov {
 
-constexpr int kTile = 4096;               // slots per CTA of the tile kernel
-constexpr int kTileShift = 12;
+#ifndef MCOV_TILE_SHIFT
+#define MCOV_TILE_SHIFT 11
+#endif
+constexpr int kTileShift = MCOV_TILE_SHIFT;
+constexpr int kTile = 1 << kTileShift;    // slots per CTA of the tile kernel (2048: 128-thread CTAs, 8 per SM)
 constexpr uint32_t kNearSpan = kTile;     // spans above this take the bucket path
-constexpr int kFusedThreads = 256;
+constexpr int kFusedThreads = kTile / 16; // 16 slots per thread
+static_assert(kTileShift >= 9 && kTileShift <= 12, "record format: 12-bit offset, 13-bit span code");
 constexpr int kPrepThreads = 256;
 constexpr int kPrepPer = 4;               // reads per thread
 constexpr uint32_t kFarCapDefault = 1u << 26;
@@ -455,10 +459,23 @@ k_fused_prep(const __grid_constant__ FusedArgs f) {
     uint32_t ptile = __shfl_up_sync(0xffffffffu, t3, 1);
     if (lane == 0) ptile = (w_bo + pq) >> kTileShift;
     const bool is_last = i0 + kPrepPer == n;
-    if (__any_sync(0xffffffffu, t3 > ptile || is_last))
-      prep_tile_boundaries(f.tile_first, i0, kPrepPer, (int64_t)(w_tb + ptile), w_tb + (sq[0] >> kTileShift),
-                           w_tb + (sq[1] >> kTileShift), w_tb + (sq[2] >> kTileShift), w_tb + t3, is_last, n,
-                           (uint32_t)f.n_tiles, lane);
+    if (__any_sync(0xffffffffu, t3 > ptile || is_last)) {
+      // a tile border inside the warp's reads: the first read of every tile entered writes its index
+      if (__any_sync(0xffffffffu, t3 - ptile > 4u || is_last)) {       // long gaps / end of batch: warp-cooperative
+        prep_tile_boundaries(f.tile_first, i0, kPrepPer, (int64_t)(w_tb + ptile), w_tb + (sq[0] >> kTileShift),
+                             w_tb + (sq[1] >> kTileShift), w_tb + (sq[2] >> kTileShift), w_tb + t3, is_last, n,
+                             (uint32_t)f.n_tiles, lane);
+      } else if (t3 > ptile) {
+        int64_t* __restrict__ tf = f.tile_first + w_tb;
+        uint32_t prev = ptile;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const uint32_t tr = sq[r] >> kTileShift;
+          for (uint32_t T = prev + 1; T <= tr; ++T) tf[T] = i0 + r;
+          prev = max(prev, tr);
+        }
+      }
+    }
     if (__any_sync(0xffffffffu, farmask != 0)) {
       const int64_t base = a.contig_off[Tw];
       int64_t e64[4];
@@ -491,20 +508,24 @@ struct TileMeta {
   uint32_t k0, k1;         // far-end bucket [k0,k1)
 };
 
-__device__ __forceinline__ TileMeta load_tile_meta(const FusedArgs& f, int64_t tile) {
+// has_far: the batch holds reads with a span above kNearSpan (else the far tables are all zero
+// and are not read)
+__device__ __forceinline__ TileMeta load_tile_meta(const FusedArgs& f, int64_t tile, bool has_far) {
   TileMeta m;
   m.r0 = m.r1 = m.jmin = 0; m.carry = 0; m.k0 = m.k1 = 0;
   if (tile < f.n_tiles) {
     m.r0 = f.tile_first[tile]; m.r1 = f.tile_first[tile + 1];
     m.jmin = tile > 0 ? f.tile_first[tile - 1] : 0;
-    m.carry = tile > 0 ? f.tile_agg[tile - 1] : 0;
-    m.k0 = tile > 0 ? f.tile_cnt[tile - 1] : 0u; m.k1 = f.tile_cnt[tile];
+    if (has_far) {
+      m.carry = tile > 0 ? f.tile_agg[tile - 1] : 0;
+      m.k0 = tile > 0 ? f.tile_cnt[tile - 1] : 0u; m.k1 = f.tile_cnt[tile];
+    }
   }
   return m;
 }
 
 #ifndef MCOV_TILE_MIN_CTAS
-#define MCOV_TILE_MIN_CTAS 4
+#define MCOV_TILE_MIN_CTAS (16384 / kTile)   /* 1024 resident threads per SM */
 #endif
 constexpr int kPreOwn = 4;     // own records prefetched per thread: one aligned 128-bit load
 
@@ -552,9 +573,10 @@ k_fused_tile(const __grid_constant__ FusedArgs f) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t stride = gridDim.x;
   const uint32_t reach = pc->max_span;                  // written by k_fused_prep
+  const bool has_far = pc->n_far != 0;
   int64_t tile = blockIdx.x;
-  TileMeta m_cur = load_tile_meta(f, tile);
-  TileMeta m_next = load_tile_meta(f, tile + stride);
+  TileMeta m_cur = load_tile_meta(f, tile, has_far);
+  TileMeta m_next = load_tile_meta(f, tile + stride, has_far);
   uint4 own;
   uint32_t back;
   prefetch_recs(f, m_cur, own, back);
@@ -574,7 +596,7 @@ k_fused_tile(const __grid_constant__ FusedArgs f) {
     uint4 n_own;
     uint32_t n_back;
     prefetch_recs(f, m_next, n_own, n_back);            // empty ranges when tile+stride is past the end
-    TileMeta m_nn = load_tile_meta(f, tile + 2 * stride);
+    TileMeta m_nn = load_tile_meta(f, tile + 2 * stride, has_far);
     const int64_t base = tile << kTileShift;
 
     // reads that start in this tile (tile_first ranges: every record in [r0,r1) belongs here)

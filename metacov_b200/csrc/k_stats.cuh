@@ -140,28 +140,42 @@ __device__ __forceinline__ void write_stats(mcov_region_stats* out, const WalkOu
   *out = r;
 }
 
-// One aligned vector of four depths -> four increments.  Plain +1 updates compile to
-// ATOMS.POPC.INC, which the shared-memory unit sustains at a far higher rate than value-carrying
-// ATOMS.ADD (measured: tools/ubench_hist.cu) -- so neighbours are deliberately NOT merged first.
-__device__ __forceinline__ void hist_vec(uint32_t* s_hist, const int4& q) {
-  atomicAdd(&s_hist[hist_bin(q.x)], 1u);
-  atomicAdd(&s_hist[hist_bin(q.y)], 1u);
-  atomicAdd(&s_hist[hist_bin(q.z)], 1u);
-  atomicAdd(&s_hist[hist_bin(q.w)], 1u);
+// One aligned vector of four depths -> four increments, and the running bin range of the thread.
+// Plain +1 updates compile to ATOMS.POPC.INC, which the shared-memory unit sustains at a far higher
+// rate than value-carrying ATOMS.ADD (measured: tools/ubench_hist.cu) -- so neighbours are
+// deliberately NOT merged first.
+__device__ __forceinline__ void hist_vec(uint32_t* s_hist, const int4& q, int& lo, int& hi) {
+  const int b0 = hist_bin(q.x), b1 = hist_bin(q.y), b2 = hist_bin(q.z), b3 = hist_bin(q.w);
+  atomicAdd(&s_hist[b0], 1u);
+  atomicAdd(&s_hist[b1], 1u);
+  atomicAdd(&s_hist[b2], 1u);
+  atomicAdd(&s_hist[b3], 1u);
+  lo = min(min(lo, b0), min(b1, min(b2, b3)));
+  hi = max(max(hi, b0), max(b1, max(b2, b3)));
 }
 
-__device__ __forceinline__ void hist_partial(uint32_t* s_hist, const int4& q, int lo, int hi) {
+__device__ __forceinline__ void hist_partial(uint32_t* s_hist, const int4& q, int k0, int k1, int& lo, int& hi) {
   int v[4] = {q.x, q.y, q.z, q.w};
-  for (int k = lo; k < hi; ++k) atomicAdd(&s_hist[hist_bin(v[k])], 1u);
+  for (int k = k0; k < k1; ++k) {
+    const int b = hist_bin(v[k]);
+    atomicAdd(&s_hist[b], 1u);
+    lo = min(lo, b); hi = max(hi, b);
+  }
 }
 
-struct RegionScratch {          // per multi-chunk region, zeroed before every run
+struct RegionScratch {          // per multi-chunk region; zero between runs (the last chunk resets it)
   uint32_t done;                // chunks that have merged their histogram
   uint32_t max_bin;             // highest non-empty bin
   uint32_t min_bin_inv;         // kHistBins-1 - lowest non-empty bin
   uint32_t pad;
 };
 
+// One CTA per chunk.  The streaming loop feeds the counting histogram and tracks the range of bins
+// it touched; everything after it (merge, walk) is limited to that range, which for real depth
+// profiles is a few dozen bins -- so a chunk costs little more than its stream and regions can be
+// cut finely enough to keep every SM busy to the end.  Multi-chunk regions merge their bin range
+// into a global per-region histogram; the last chunk to arrive pulls the merged range back, leaves
+// the global copy zeroed for the next run, and finishes the region.
 __global__ void __launch_bounds__(kStatThreads, 4)
 k_region_stats(StatArgs a) {
   __shared__ __align__(16) uint32_t s_hist[kHistBins];
@@ -171,7 +185,7 @@ k_region_stats(StatArgs a) {
   __shared__ int s_last;
 
   const StatTask task = a.tasks[blockIdx.x];
-  const int t = threadIdx.x;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int g = task.region;
   const int n_chunks = a.region_chunks[g];
   const int pad = a.region_pad[g];
@@ -190,6 +204,7 @@ k_region_stats(StatArgs a) {
   const int head = (int)(s0 - a0);                      // elements to skip in the first vector
   const int tail = (int)((a0 + (nvec << 2)) - s1);      // elements to skip in the last vector
   const int64_t jf0 = head ? 1 : 0, jf1 = nvec - (tail ? 1 : 0);   // full vectors [jf0, jf1)
+  int lo = kHistBins, hi = -1;
   // four independent 128-bit loads in flight per thread
   for (int64_t j = jf0 + t; j < jf1; j += 4 * kStatThreads) {
     int4 q0 = __ldcs(vp + j), q1, q2, q3;
@@ -197,51 +212,60 @@ k_region_stats(StatArgs a) {
     if (v1) q1 = __ldcs(vp + j + kStatThreads);
     if (v2) q2 = __ldcs(vp + j + 2 * kStatThreads);
     if (v3) q3 = __ldcs(vp + j + 3 * kStatThreads);
-    hist_vec(s_hist, q0);
-    if (v1) hist_vec(s_hist, q1);
-    if (v2) hist_vec(s_hist, q2);
-    if (v3) hist_vec(s_hist, q3);
+    hist_vec(s_hist, q0, lo, hi);
+    if (v1) hist_vec(s_hist, q1, lo, hi);
+    if (v2) hist_vec(s_hist, q2, lo, hi);
+    if (v3) hist_vec(s_hist, q3, lo, hi);
   }
   if (nvec > 0) {
-    if (nvec == 1) { if (t == 0 && (head || tail)) hist_partial(s_hist, __ldcs(vp), head, 4 - tail); }
+    if (nvec == 1) { if (t == 0 && (head || tail)) hist_partial(s_hist, __ldcs(vp), head, 4 - tail, lo, hi); }
     else {
-      if (t == 0 && head) hist_partial(s_hist, __ldcs(vp), head, 4);
-      if (t == 32 && tail) hist_partial(s_hist, __ldcs(vp + nvec - 1), 0, 4 - tail);
+      if (t == 0 && head) hist_partial(s_hist, __ldcs(vp), head, 4, lo, hi);
+      if (t == 32 && tail) hist_partial(s_hist, __ldcs(vp + nvec - 1), 0, 4 - tail, lo, hi);
     }
   }
-  __syncthreads();
-  mcov_region_stats* out = a.out + g;
+  // bin range of the chunk
+  lo = warp_min(lo); hi = warp_max(hi);
+  if (lane == 0) { s_i32[warp] = lo; s_i32[kStatThreads / 32 + warp] = hi; }
+  __syncthreads();                                      // also: the histogram is complete
+  lo = kHistBins; hi = -1;
+#pragma unroll
+  for (int k = 0; k < kStatThreads / 32; ++k) { lo = min(lo, s_i32[k]); hi = max(hi, s_i32[kStatThreads / 32 + k]); }
+  mcov_region_stats* out = a.out + g;                   // (hist_walk rewrites s_i32 only after its own barriers)
 
   if (n_chunks > 1) {
-    // ---- multi-chunk region: merge the non-empty bins into the region's global histogram ----
+    // ---- multi-chunk region: merge the touched bins into the region's global histogram ----
     uint32_t* gh = a.hist_pool + (int64_t)a.region_hist[g] * kHistBins;
     RegionScratch* rs = reinterpret_cast<RegionScratch*>(a.region_done) + a.region_hist[g];
-    uint32_t bmax = 0, bmin_inv = 0;
-    for (int b = t; b < kHistBins; b += kStatThreads) {
+    for (int b = lo + t; b <= hi; b += kStatThreads) {
       uint32_t c = s_hist[b];
-      if (c) { atomicAdd(gh + b, c); bmax = max(bmax, (uint32_t)b); bmin_inv = max(bmin_inv, (uint32_t)(kHistBins - 1 - b)); }
+      if (c) atomicAdd(gh + b, c);
     }
-    bmax = (uint32_t)warp_max((int)bmax); bmin_inv = (uint32_t)warp_max((int)bmin_inv);
-    if ((t & 31) == 0) { atomicMax(&rs->max_bin, bmax); atomicMax(&rs->min_bin_inv, bmin_inv); }
-    __threadfence();
     __syncthreads();
     if (t == 0) {
+      if (hi >= lo) { atomicMax(&rs->max_bin, (uint32_t)hi); atomicMax(&rs->min_bin_inv, (uint32_t)(kHistBins - 1 - lo)); }
+      __threadfence();                                  // the CTA's merges (ordered by the barrier) before the arrival
       unsigned prev = atomicAdd(&rs->done, 1u);
       s_last = (prev == (unsigned)(n_chunks - 1));
     }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    // last chunk of the region: pull the merged histogram (only the populated range) and finish
-    const int glo = kHistBins - 1 - (int)*((volatile uint32_t*)&rs->min_bin_inv), ghi = (int)*((volatile uint32_t*)&rs->max_bin);
-    for (int b = glo + t; b <= ghi; b += kStatThreads) s_hist[b] = __ldcg(gh + b);
+    // last chunk of the region: pull the merged range, leave the global copy clean for the next run
+    lo = kHistBins - 1 - (int)*((volatile uint32_t*)&rs->min_bin_inv);
+    hi = (int)*((volatile uint32_t*)&rs->max_bin);
+    for (int b = lo + t; b <= hi; b += kStatThreads) { s_hist[b] = __ldcg(gh + b); gh[b] = 0u; }
     __syncthreads();
+    if (t == 0) { rs->done = 0u; rs->max_bin = 0u; rs->min_bin_inv = 0u; }
   }
-  if (pad > 0) {                       // zeros beyond the contig end join the multiset
+  if (pad > 0) {                       // zeros beyond the contig end join the multiset (untouched bins are 0)
     if (t == 0) s_hist[0] += (uint32_t)pad;
+    if (hi < 0) hi = 0;
+    lo = 0;
     __syncthreads();
   }
-  WalkOut w = hist_walk<kStatThreads>(s_hist, n_region, a.breadth_n, 0, kHistBins - 1, s_u64, s_i32, s_med);
+  if (hi < lo) { lo = 0; hi = 0; }     // empty region: hist_walk over one (empty) bin
+  WalkOut w = hist_walk<kStatThreads>(s_hist, n_region, a.breadth_n, lo, hi, s_u64, s_i32, s_med);
   if (t == 0) write_stats(out, w);
 }
 

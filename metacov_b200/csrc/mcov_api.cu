@@ -579,10 +579,11 @@ static int stats_launch(mcov_ctx* ctx, int64_t g, const int32_t* tid, const int3
       int64_t len = ctx->len[tid[i]];
       total += std::max<int64_t>(0, std::min<int64_t>(end[i], len) - std::min<int64_t>(start[i], len));
     }
-    // chunk length: enough chunks to fill the machine several times over; a region is split evenly
-    // Splitting a region costs a global histogram merge per chunk (measured on C2: 90 us with four
-    // chunks per 50 kb contig, 57 us with one), so chunks are as long as possible (64 k slots) and
-    // only shrink when the work would otherwise leave the machine underfilled (~2 waves of 3 CTAs/SM).
+    // Chunk length.  Splitting a region is not free: a short CTA spends most of its life in the
+    // latency chain around the stream (clear, first loads, merge atomics, arrival counter) -- measured
+    // on C2 (1 000 regions of 50 kb): 52 us with one chunk per region, 62 / 73 / 87 us with chunks of
+    // 32 k / 16 k / 8 k slots.  So chunks are as long as possible (64 k slots) and only shrink when
+    // the work would otherwise leave the machine underfilled (~1.5 waves of 4 CTAs/SM).
     int64_t chunk_max = (total / ((int64_t)kNumSMsB200 * 6) + 4095) / 4096 * 4096;
     chunk_max = std::max<int64_t>(8192, std::min<int64_t>(65536, chunk_max));
     if (const char* ov = std::getenv("MCOV_STAT_CHUNK")) {          // tuning hook
@@ -627,7 +628,6 @@ static int stats_launch(mcov_ctx* ctx, int64_t g, const int32_t* tid, const int3
     CU(ctx->d_out.ensure((size_t)g * sizeof(mcov_region_stats)));
     CU(ctx->d_tasks.ensure(std::max<size_t>(tasks.size(), 1) * sizeof(StatTask)));
     CU(ctx->d_rlen.ensure((size_t)g * 8)); CU(ctx->d_rchunks.ensure((size_t)g * 4)); CU(ctx->d_rhist.ensure((size_t)g * 4));
-    // [RegionScratch per multi-chunk region | hist_pool] are cleared together before every run
     CU(ctx->d_pool.ensure((size_t)std::max(n_multi, 1) * (sizeof(RegionScratch) + (size_t)kHistBins * 4) + 16));
     int32_t* d_rlen = ctx->d_rlen.as<int32_t>();
     if (!tasks.empty()) CU(cudaMemcpyAsync(ctx->d_tasks.p, tasks.data(), tasks.size() * sizeof(StatTask), cudaMemcpyHostToDevice, s));
@@ -635,13 +635,14 @@ static int stats_launch(mcov_ctx* ctx, int64_t g, const int32_t* tid, const int3
     CU(cudaMemcpyAsync(d_rlen + g, rp.rpad.data(), (size_t)g * 4, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(ctx->d_rchunks.p, rchunks.data(), (size_t)g * 4, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(ctx->d_rhist.p, rhist.data(), (size_t)g * 4, cudaMemcpyHostToDevice, s));
+    // [RegionScratch per multi-chunk region | hist_pool]: zeroed here once; every run leaves it zeroed
+    if (n_multi) CU(cudaMemsetAsync(ctx->d_pool.p, 0, (size_t)n_multi * (sizeof(RegionScratch) + (size_t)kHistBins * 4), s));
     CU(cudaStreamSynchronize(s));                   // the host vectors above go out of scope
     rp.tid.assign(tid, tid + g); rp.start.assign(start, start + g); rp.end.assign(end, end + g);
     rp.g = g; rp.n_contigs_epoch = ctx->contig_epoch; rp.valid = true;
   }
   if (g > 0) {
     const size_t done_bytes = (size_t)rp.n_multi * sizeof(RegionScratch);
-    if (rp.n_multi) CU(cudaMemsetAsync(ctx->d_pool.p, 0, done_bytes + (size_t)rp.n_multi * kHistBins * 4, s));
     if (rp.n_tasks) {
       StatArgs a;
       int32_t* d_rlen = ctx->d_rlen.as<int32_t>();
