@@ -238,6 +238,52 @@ int  mcov_kmer_hist(mcov_ctx* ctx, int64_t n, const uint16_t* flag, const int32_
                     int32_t K, int32_t NK, int32_t STEP, int32_t OFFSET,
                     int32_t n_group_flags, const uint16_t* group_flags, uint32_t* hist_out);
 
+/* ---- the second coverage definition: pileup.experimental ------------------ */
+
+/* Per-region sums behind the 13 outputs of `experimental` (reference
+ * metacov/pileup.py:150-173).  With L = end-start and the reference's names:
+ *   cov   = cov_sum / L            covc = covw_sum / L
+ *   den   = n_starts / L           denc = cor_sum / L        cf = cor_sum / n_starts
+ *   cov2  = cov2_sum / L           wnf  = wnf_sum / L
+ *   nz    = L - n_starts           allreads = secondary + nreads + improper
+ * no_reflen counts the proper-pair reads whose `reference_length` is None
+ * (the reference raises TypeError on the first one, pileup.py:134-137). */
+typedef struct mcov_exp_stats {
+  double  covw_sum;
+  double  cor_sum;
+  double  wnf_sum;
+  int64_t cov_sum;
+  int64_t cov2_sum;
+  int32_t n_starts;
+  int32_t nreads;
+  int32_t secondary;
+  int32_t improper;
+  int32_t no_reflen;
+  int32_t n_pairs;
+} mcov_exp_stats;
+
+/* Replaces the read loop of `experimental(bam, k_cor, k_len, fasta, ref, start,
+ * end)` (reference metacov/pileup.py:90-146) for g regions of ONE contig set in
+ * a coordinate-sorted file.  Host arrays (file order): pos, flag, cig_off[n+1],
+ * cig as for mcov_push_reads; name_hash = mcov_bam_name_hash (the reference joins
+ * mates through a dict keyed by query_name); kmer_code = mcov_bam_qas_kmer(k_len)
+ * (-1 = the lookup raises KeyError); kcor[2][4^k_len] / kcor_has[2][4^k_len] =
+ * the two dicts of load_kmerhist as tables (index: first base most significant,
+ * A0 C1 G2 T3; kcor_has = key present); k_len <= 12, or kcor == NULL for "no
+ * correction" (every lookup raises KeyError -> rcor = 1).  Region i covers
+ * [r_start[i], r_end[i]) of the contig whose reads are the records
+ * [r_lb[i], r_ub[i]) -- any superset of the records `bam.fetch` would return
+ * (the kernel applies the exact overlap test).  out: host, g records. */
+int  mcov_experimental_run(mcov_ctx* ctx, int64_t n, const int32_t* pos, const uint16_t* flag,
+                           const uint32_t* cig_off, const uint32_t* cig, const uint64_t* name_hash,
+                           const int32_t* kmer_code, int32_t k_len, const double* kcor, const uint8_t* kcor_has,
+                           int32_t g, const int32_t* r_start, const int32_t* r_end,
+                           const int64_t* r_lb, const int64_t* r_ub, mcov_exp_stats* out);
+
+/* cor_revsum of reference metacov/pileup.py:78-83: out[i] = sum over j <
+ * min(L-i, n_w) of w[j] * cor_rev[i+j] (the O(L*900) loop of np.inner calls). */
+int  mcov_exp_revsum(mcov_ctx* ctx, int64_t L, const double* cor_rev, int32_t n_w, const double* w, double* out);
+
 /* ---- host BAM decoding (replaces pysam.AlignmentFile, cli.py:56, 211) ---- */
 
 typedef struct mcov_bam mcov_bam;
@@ -269,6 +315,11 @@ const uint32_t* mcov_bam_cig(const mcov_bam* b);
  * reverse reads their last win_bases (nt16, high nibble first, missing = 15). */
 int  mcov_bam_load_seq(mcov_bam* b);
 int  mcov_bam_seq_windows(const mcov_bam* b, int32_t win_bases, uint8_t* out);
+/* FNV-1a 64 of every read name (`read.query_name`, pileup.py:101); valid after mcov_bam_load_seq. */
+const uint64_t* mcov_bam_name_hash(const mcov_bam* b);
+/* out[n]: 2-bit code of the first k_len bases of `read.query_alignment_sequence` (pileup.py:109,
+ * 123; first base most significant, A0 C1 G2 T3), -1 when shorter or not ACGT.  k_len <= 15. */
+int  mcov_bam_qas_kmer(const mcov_bam* b, int32_t k_len, int32_t* out);
 
 /* ---- synthetic workloads (bench / test support; include/mcov_synth.h) ---- */
 

@@ -60,6 +60,13 @@ class PassInfo(C.Structure):
                 ("cap_contigs", C.c_int32)]
 
 
+EXP_STATS_DTYPE = np.dtype([
+    ("covw_sum", "<f8"), ("cor_sum", "<f8"), ("wnf_sum", "<f8"), ("cov_sum", "<i8"), ("cov2_sum", "<i8"),
+    ("n_starts", "<i4"), ("nreads", "<i4"), ("secondary", "<i4"), ("improper", "<i4"), ("no_reflen", "<i4"),
+    ("n_pairs", "<i4")])
+assert EXP_STATS_DTYPE.itemsize == 64      # mcov_exp_stats
+
+
 class KernelTime(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("launches", C.c_int64), ("total_ms", C.c_double)]
 
@@ -104,6 +111,11 @@ SIGNATURES = {
     "mcov_kmer_hist": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "mcov_bam_load_seq": (C.c_int, [_vp]),
     "mcov_bam_seq_windows": (C.c_int, [_vp, _i32, _vp]),
+    "mcov_bam_name_hash": (_vp, [_vp]),
+    "mcov_bam_qas_kmer": (C.c_int, [_vp, _i32, _vp]),
+    "mcov_experimental_run": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp,
+                                        _i32, _vp, _vp, _vp, _vp, _vp]),
+    "mcov_exp_revsum": (C.c_int, [_vp, _i64, _vp, _i32, _vp, _vp]),
     "mcov_bam_open": (C.c_int, [C.POINTER(_vp), C.c_char_p, C.c_char_p, C.c_int]),
     "mcov_bam_close": (None, [_vp]),
     "mcov_bam_n_ref": (_i32, [_vp]),

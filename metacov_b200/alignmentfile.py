@@ -150,6 +150,75 @@ class AlignmentFile:
     def __len__(self):
         return len(self.soa()["tid"])
 
+    # -- pileup.experimental ------------------------------------------------
+    def name_hashes(self):
+        """uint64[n]: FNV-1a of every read name (the key of the reference's mate dict, pileup.py:101)."""
+        n = len(self.soa()["tid"])
+        rc = lib.mcov_bam_load_seq(self._h)
+        if rc != 0:
+            raise McovError(rc, "BAM SEQ decode failed")
+        return _view(lib.mcov_bam_name_hash(self._h), n, np.uint64)
+
+    def qas_kmer_codes(self, k_len):
+        """int32[n]: code of ``read.query_alignment_sequence[0:k_len]`` (pileup.py:109, 123), -1 = no key."""
+        n = len(self.soa()["tid"])
+        rc = lib.mcov_bam_load_seq(self._h)
+        if rc != 0:
+            raise McovError(rc, "BAM SEQ decode failed")
+        out = np.empty(n, dtype=np.int32)
+        rc = lib.mcov_bam_qas_kmer(self._h, int(k_len), _capi.ptr(out))
+        if rc != 0:
+            raise McovError(rc, "mcov_bam_qas_kmer failed")
+        return out
+
+    def _fetch_index(self):
+        """Per-contig record ranges and the longest reference span: what stands in for the BAI when
+        a region's candidate records are looked up (``bam.fetch`` needs a sorted, indexed file)."""
+        if getattr(self, "_fidx", None) is None:
+            s = self.soa()
+            # (contig, position) as one sortable key; unplaced reads (tid -1 -> 2^32-1) sort last
+            key = (s["tid"].view(np.uint32).astype(np.int64) << 31) | s["pos"].astype(np.int64).clip(0)
+            if len(key) > 1 and np.any(key[1:] < key[:-1]):
+                raise ValueError("fetch called on bamfile without index")          # pysam's message
+            ut = s["tid"].view(np.uint32)
+            cstart = np.searchsorted(ut, np.arange(self.nreferences + 1, dtype=np.uint32), side="left")
+            consumes = np.array([1, 0, 1, 1, 0, 0, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0], dtype=np.int64)   # M D N = X
+            per_op = (s["cig"] >> 4).astype(np.int64) * consumes[s["cig"] & 15]
+            csum = np.concatenate(([0], np.cumsum(per_op)))
+            reflen = csum[s["cig_off"][1:]] - csum[s["cig_off"][:-1]]
+            self._fidx = (cstart, int(max(reflen.max(initial=0), 1)))
+        return self._fidx
+
+    def experimental_stats(self, refs, starts, ends, k_len, kc_val, kc_has):
+        """``mcov_exp_stats`` records of the regions (the read loop of pileup.py:90-146 on the GPU)."""
+        s = self.soa()
+        cstart, max_span = self._fetch_index()
+        pos = s["pos"]
+        g = len(refs)
+        lb = np.zeros(g, dtype=np.int64)
+        ub = np.zeros(g, dtype=np.int64)
+        for i, (ref, s0, e0) in enumerate(zip(refs, starts, ends)):
+            tid = self._tid[ref]                                             # KeyError for unknown contigs, like pysam
+            c0, c1 = int(cstart[tid]), int(cstart[tid + 1])
+            lb[i] = c0 + np.searchsorted(pos[c0:c1], s0 - max_span, side="right")
+            ub[i] = c0 + np.searchsorted(pos[c0:c1], e0, side="left")
+            ub[i] = max(ub[i], lb[i])
+        hashes = self.name_hashes()
+        codes = self.qas_kmer_codes(k_len) if kc_val is not None else np.full(len(pos), -1, dtype=np.int32)
+        eng = self.coverage_engine()
+        out = np.zeros(g, dtype=_capi.EXP_STATS_DTYPE)
+        # batches bounded by the scratch they need: (region, read) entries and last-writer slots
+        i = 0
+        while i < g:
+            j, ent, slots = i, 0, 0
+            while j < g and (j == i or (ent + ub[j] - lb[j] < (1 << 30) and slots + ends[j] - starts[j] < (1 << 29))):
+                ent += int(ub[j] - lb[j]); slots += int(ends[j] - starts[j]); j += 1
+            out[i:j] = eng.experimental_stats(s, hashes, codes, k_len, kc_val, kc_has,
+                                              np.asarray(starts[i:j], dtype=np.int32), np.asarray(ends[i:j], dtype=np.int32),
+                                              lb[i:j], ub[i:j])
+            i = j
+        return out
+
     # -- coverage ---------------------------------------------------------
     def set_pileup_filter(self, **kw):
         """Override pysam's implicit pileup arguments (flag_filter, flag_require,

@@ -35,6 +35,7 @@ struct mcov_bam {
   bool has_seq = false;
   std::vector<uint64_t> seq_off;     // byte offset of each record's packed SEQ
   std::vector<uint8_t> seq;          // nt16, two bases per byte, high nibble first (BAM encoding)
+  std::vector<uint64_t> name_hash;   // FNV-1a 64 of the read name (filled with the SEQ pass)
 };
 
 namespace {
@@ -305,6 +306,7 @@ int mcov_bam_load_seq(mcov_bam* b) {
   }
   b->seq_off.resize(n_rec + 1);
   b->seq.resize(bytes);
+  b->name_hash.resize(n_rec);
   p = b->rec_begin;
   size_t so = 0;
   for (size_t i = 0; i < n_rec; ++i) {
@@ -315,6 +317,11 @@ int mcov_bam_load_seq(mcov_bam* b) {
     size_t l_seq = rd32(r + 16), nb = (l_seq + 1) / 2;
     if (32u + l_read_name + 4u * n_op + nb > bs) return MCOV_ERR_IO;
     b->seq_off[i] = so;
+    {
+      uint64_t h = 1469598103934665603ull;                    // FNV-1a 64 over the name (without the NUL)
+      for (unsigned k = 0; k + 1 < l_read_name; ++k) { h ^= r[32 + k]; h *= 1099511628211ull; }
+      b->name_hash[i] = h == ~0ull ? h - 1 : h;               // ~0 is the "no entry" key of the pair sort
+    }
     std::memcpy(b->seq.data() + so, r + 32 + l_read_name + 4u * n_op, nb);
     so += nb;
     p += 4 + bs;
@@ -359,6 +366,45 @@ int mcov_bam_seq_windows(const mcov_bam* b, int32_t win_bases, uint8_t* out) {
   for (int t = 1; t < nt; ++t) { size_t lo = t * per, hi = std::min(n, lo + per); if (lo < hi) th.emplace_back(work, lo, hi); }
   work(0, std::min(n, per));
   for (auto& t : th) t.join();
+  return MCOV_OK;
+}
+
+// FNV-1a 64 hashes of the read names (`read.query_name`, reference metacov/pileup.py:101-118 joins
+// mates through a dict keyed by it).  Valid after mcov_bam_load_seq.
+const uint64_t* mcov_bam_name_hash(const mcov_bam* b) { return (b && b->has_seq) ? b->name_hash.data() : nullptr; }
+
+// Per read the 2-bit code of the first k_len bases of `query_alignment_sequence` (SEQ as stored,
+// without the soft-clipped ends; reference metacov/pileup.py:109-110, 123): first base most
+// significant, A0 C1 G2 T3; -1 when the aligned part is shorter than k_len or holds another letter
+// (a dict lookup with such a key raises KeyError in the reference).  k_len <= 15.
+int mcov_bam_qas_kmer(const mcov_bam* b, int32_t k_len, int32_t* out) {
+  if (!b || !out || k_len <= 0 || k_len > 15) return MCOV_ERR_ARG;
+  if (!b->has_seq || !b->loaded) return MCOV_ERR_ARG;
+  static const int8_t nt4[16] = {-1, 0, 1, -1, 2, -1, -1, -1, 3, -1, -1, -1, -1, -1, -1, -1};   // "=ACMGRSVTWYHKDBN"
+  const size_t n = b->tid.size();
+  for (size_t i = 0; i < n; ++i) {
+    const uint8_t* s = b->seq.data() + b->seq_off[i];
+    int64_t lo = 0, hi = b->lseq[i];
+    const uint32_t c0 = b->cig_off[i], c1 = b->cig_off[i + 1];
+    for (uint32_t k = c0; k < c1; ++k) {                      // leading soft clips (hard clips hold no bases)
+      uint32_t op = b->cig[k] & 15u;
+      if (op == 5) continue;
+      if (op == 4) lo += b->cig[k] >> 4; else break;
+    }
+    for (uint32_t k = c1; k > c0; --k) {
+      uint32_t op = b->cig[k - 1] & 15u;
+      if (op == 5) continue;
+      if (op == 4) hi -= b->cig[k - 1] >> 4; else break;
+    }
+    int32_t code = 0;
+    if (hi - lo < k_len) code = -1;
+    for (int32_t j = 0; j < k_len && code >= 0; ++j) {
+      int64_t a = lo + j;
+      int8_t c = nt4[(a & 1) ? (s[a >> 1] & 15) : (s[a >> 1] >> 4)];
+      code = c < 0 ? -1 : (code << 2) | c;
+    }
+    out[i] = code;
+  }
   return MCOV_OK;
 }
 

@@ -226,6 +226,35 @@ class CoverageEngine:
         self._check(lib.mcov_region_stats_enqueue(self._ctx, len(tid), _capi.ptr(tid), _capi.ptr(start),
                                                   _capi.ptr(end), int(breadth_n), out.data_ptr()))
 
+    def experimental_stats(self, soa, name_hash, kmer_code, k_len, kc_val, kc_has, r_start, r_end, r_lb, r_ub):
+        """One ``mcov_experimental_run`` call -> EXP_STATS_DTYPE records."""
+        n = len(soa["pos"])
+        g = len(r_start)
+        out = np.zeros(g, dtype=_capi.EXP_STATS_DTYPE)
+        r_start = np.ascontiguousarray(r_start, dtype=np.int32)
+        r_end = np.ascontiguousarray(r_end, dtype=np.int32)
+        r_lb = np.ascontiguousarray(r_lb, dtype=np.int64)
+        r_ub = np.ascontiguousarray(r_ub, dtype=np.int64)
+        name_hash = np.ascontiguousarray(name_hash, dtype=np.uint64)
+        kmer_code = np.ascontiguousarray(kmer_code, dtype=np.int32)
+        if kc_val is not None:
+            kc_val = np.ascontiguousarray(kc_val, dtype=np.float64)
+            kc_has = np.ascontiguousarray(kc_has, dtype=np.uint8)
+        self._check(lib.mcov_experimental_run(
+            self._ctx, n, _capi.ptr(soa["pos"]), _capi.ptr(soa["flag"]), _capi.ptr(soa["cig_off"]), _capi.ptr(soa["cig"]),
+            _capi.ptr(name_hash), _capi.ptr(kmer_code), int(k_len) if kc_val is not None else 0,
+            _capi.ptr(kc_val), _capi.ptr(kc_has), g, _capi.ptr(r_start), _capi.ptr(r_end), _capi.ptr(r_lb), _capi.ptr(r_ub),
+            _capi.ptr(out)))
+        return out
+
+    def exp_revsum(self, cor_rev, w):
+        """cor_revsum of reference pileup.py:78-83 (mcov_exp_revsum)."""
+        cor_rev = np.ascontiguousarray(cor_rev, dtype=np.float64)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        out = np.zeros(len(cor_rev), dtype=np.float64)
+        self._check(lib.mcov_exp_revsum(self._ctx, len(cor_rev), _capi.ptr(cor_rev), len(w), _capi.ptr(w), _capi.ptr(out)))
+        return out
+
     def kmer_hist(self, flag, l_seq, seq_win, win_bases, K, NK, STEP, OFFSET, group_flags=()):
         """ByFlag-grouped k-mer histogram -> uint32[groups, 4**K + 1, NK] (see mcov_kmer_hist)."""
         gf = np.ascontiguousarray(group_flags, dtype=np.uint16)

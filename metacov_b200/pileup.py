@@ -1,5 +1,8 @@
 """Drop-in for ``metacov.pileup`` on the B200 path.
 
+``experimental(bam, k_cor, k_len, fasta, ref, start, end)`` keeps the signature and the 13 keys of
+reference metacov/pileup.py:38-173; its read loop runs on the GPU (``mcov_experimental_run``).
+
 ``classic(bam, ref, start, end)`` keeps the signature, keys, value types and
 rounding of reference metacov/pileup.py:9-26.  The per-base depth is computed
 once per BAM on the GPU (instead of one htslib pileup per region) and every
@@ -82,3 +85,140 @@ def load_kmerhist(f, k_len=7):
     df = df.set_index("kmer")
     cor = df[df.columns[0]] / df[df.columns[1:]].mean(axis=1)
     return [cor[df.R == r].to_dict() for r in ("R1", "R2")]
+
+
+# ---- pileup.experimental -------------------------------------------------------------------------
+
+_NT = {"A": 0, "C": 1, "G": 2, "T": 3}
+
+
+def _kcor_tables(k_cor, k_len):
+    """The two dicts of ``load_kmerhist`` as dense tables (value, key-present) indexed by the
+    2-bit code of the k-mer, first base most significant (mcov_bam_qas_kmer)."""
+    if not k_cor:
+        return None, None
+    n = 4 ** k_len
+    val = np.zeros((2, n), dtype=np.float64)
+    has = np.zeros((2, n), dtype=np.uint8)
+    for r in (0, 1):
+        for kmer, v in k_cor[r].items():
+            if len(kmer) != k_len:
+                continue
+            code = 0
+            for ch in kmer:
+                c = _NT.get(ch)
+                if c is None:
+                    code = -1
+                    break
+                code = code * 4 + c
+            if code >= 0:
+                val[r, code] = v
+                has[r, code] = 1
+    return val, has
+
+
+def _region_kmer_cor(region, k_cor, k_len):
+    """cor_fwd / cor_rev of reference pileup.py:66-77 (missing key -> 0), vectorised."""
+    L = len(region)
+    val, has = _kcor_tables(k_cor, k_len)
+    b = np.frombuffer(region.encode("latin-1"), dtype=np.uint8)
+    code = np.full(L, -1, dtype=np.int64)
+    for ch, c in _NT.items():
+        code[b == ord(ch)] = c
+    cor_fwd = np.zeros(L)
+    cor_rev = np.zeros(L)
+    if L >= k_len:
+        win = np.lib.stride_tricks.sliding_window_view(code, k_len)          # win[j] = codes of region[j:j+k]
+        ok = (win >= 0).all(axis=1)
+        pw = 4 ** np.arange(k_len - 1, -1, -1, dtype=np.int64)
+        fwd_idx = np.where(ok, (win * pw).sum(axis=1), 0)
+        rev_idx = np.where(ok, (win * pw[::-1]).sum(axis=1), 0)              # the same bases read backwards
+        # cor_fwd[i] = k_cor[0][region[i:i+k]] for i in range(L-k)   (the last window is never looked up)
+        n_f = max(L - k_len, 0)
+        cor_fwd[:n_f] = np.where(ok[:n_f] & (has[0, fwd_idx[:n_f]] != 0), val[0, fwd_idx[:n_f]], 0.0)
+        # cor_rev[j] = k_cor[1][reversed(region[j-k+1 .. j])] for j in [k-1, L-1]
+        cor_rev[k_len - 1:] = np.where(ok & (has[1, rev_idx] != 0), val[1, rev_idx], 0.0)
+    return cor_fwd, cor_rev
+
+
+def _insert_model():
+    """norm of reference pileup.py:54-60: N(450, 150) pdf at 0..900 (scipy.stats.norm.pdf)."""
+    insert, sd = 450, 150
+    x = (np.arange(0, 2 * insert + 1, dtype=np.float64) - insert) / sd
+    return np.exp(-x ** 2 / 2.0) / np.sqrt(2 * np.pi) / sd, 2 * insert
+
+
+def finish_experimental(st, length, gc, ecor):
+    """The 13 outputs of ``experimental`` (reference pileup.py:150-173) from one
+    ``mcov_exp_stats`` record; same expressions, types and rounding."""
+    length = int(length)
+    n_starts, nreads = int(st["n_starts"]), int(st["nreads"])
+    secondary, improper = int(st["secondary"]), int(st["improper"])
+    nz = length - n_starts
+    nz_e = length * (1 - 1 / length) ** nreads
+    nzef = nz / nz_e
+    allreads = secondary + nreads + improper
+    wnf = float(st["wnf_sum"])
+    with np.errstate(invalid="ignore", divide="ignore"):
+        cf = np.float64(st["cor_sum"]) / np.float64(n_starts)
+    return {
+        "cov": np.float64(int(st["cov_sum"]) / length),
+        "covc": np.float64(st["covw_sum"]) / length,
+        "den": round(np.float64(n_starts / length), 3),
+        "denc": round(np.float64(st["cor_sum"]) / length, 3),
+        "cov2": round(np.float64(int(st["cov2_sum"]) / length)),
+        "cf": round(cf, 3),
+        "ambig": round(secondary / allreads, 3) if allreads > 0 else 0,
+        "improper": round(improper / allreads, 3) if allreads > 0 else 0,
+        "nzef": round(nzef, 3),
+        "gc": round(gc, 3),
+        "ecor": round(ecor, 3),
+        "wnf": round(wnf / length, 3),
+        "cov3": round(200 * (wnf / ecor) / nzef / length, 3),
+    }
+
+
+def experimental_many(bam, k_cor, k_len, fasta, refs, starts, ends):
+    """``experimental`` for many regions: one GPU pass per batch of regions."""
+    if not hasattr(bam, "experimental_stats"):
+        raise TypeError(
+            "metacov_b200.pileup needs a metacov_b200.AlignmentFile (got %r); the GPU path has no "
+            "CPU fallback for foreign bam objects" % type(bam).__name__)
+    starts = [int(x) for x in starts]
+    ends = [int(x) for x in ends]
+    for s0, e0 in zip(starts, ends):
+        if e0 - s0 == 0:
+            raise Exception("Length must be > 0")                      # pileup.py:40-41
+        if e0 - s0 < 0:
+            raise ValueError("negative dimensions are not allowed")    # np.zeros(length), pileup.py:42
+    kc_val, kc_has = _kcor_tables(k_cor, k_len)
+    st = bam.experimental_stats(refs, starts, ends, k_len, kc_val, kc_has)
+    norm, n_w = _insert_model()
+    out = []
+    for i, (ref, s0, e0) in enumerate(zip(refs, starts, ends)):
+        length = e0 - s0
+        if int(st[i]["no_reflen"]):
+            # rend = rstart + read.reference_length with reference_length None (pileup.py:134-137)
+            raise TypeError("unsupported operand type(s) for +: 'int' and 'NoneType'")
+        if fasta:
+            region = fasta.fetch(ref, s0, e0).upper()                   # pileup.py:62-65
+            gc = region.count("G") + region.count("C")
+            gc = gc / (gc + region.count("A") + region.count("T"))
+            if not k_cor:
+                raise UnboundLocalError("cannot access local variable 'ecor' where it is not associated with a value")
+            cor_fwd, cor_rev = _region_kmer_cor(region, k_cor, k_len)
+            # the reference indexes region with the region length; a FASTA shorter than the region fails there
+            if len(region) != length:
+                raise IndexError("string index out of range")
+            revsum = bam.coverage_engine().exp_revsum(cor_rev, norm[:n_w])   # pileup.py:78-83 on the GPU
+            ecor = np.inner(cor_fwd, revsum) / length
+        else:
+            gc = -1
+            ecor = -1
+        out.append(finish_experimental(st[i], length, gc, ecor))
+    return out
+
+
+def experimental(bam, k_cor, k_len, fasta, ref, start, end):
+    """Drop-in for ``metacov.pileup.experimental`` (reference pileup.py:38)."""
+    return experimental_many(bam, k_cor, k_len, fasta, [ref], [start], [end])[0]

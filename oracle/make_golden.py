@@ -142,10 +142,141 @@ def synthetic():
     return out
 
 
+class _Fasta:
+    """``pysam.FastaFile`` stand-in: fetch(ref, start, end) on in-memory sequences."""
+
+    def __init__(self, seqs):
+        self.seqs = seqs
+
+    def fetch(self, ref, start, end):
+        return self.seqs[ref][start:end]
+
+
+def _exp_rows(ref_mod, bam, k_cor, k_len, fasta, regions):
+    import contextlib
+    import io
+    rows = []
+    for n, s, e, with_fa in regions:
+        row = {"ref": n, "start": s, "end": e, "fasta": bool(with_fa)}
+        try:
+            with contextlib.redirect_stdout(io.StringIO()), np.errstate(all="ignore"):   # "RCOR is ZERO" prints (pileup.py:129)
+                res = ref_mod.experimental(bam, k_cor, k_len, fasta if with_fa else None, n, s, e)
+            # JSON has no nan / inf: stored as strings
+            row["result"] = {k: (float(v) if np.isfinite(v) else repr(float(v))) for k, v in res.items()}
+        except Exception as ex:                                    # the reference's own failure modes are part of the contract
+            row["raises"] = type(ex).__name__
+        rows.append(row)
+    return rows
+
+
+def experimental_fixture():
+    """The reference's ``experimental()`` on the reference fixture BAM + FASTA with the synthetic
+    k-mer ratios of oracle.experimental.synthetic_kcor."""
+    import gzip
+    from oracle.experimental import synthetic_kcor
+    ref = ref_pileup_module()
+    bam_path = os.path.join(REF, "tests", "data", "bbmap.sorted.bam")
+    hdr, recs = bamio.read_bam(bam_path)
+    bam = FakeAlignmentFile(hdr, recs, None)
+    seqs, name = {}, None
+    with gzip.open(os.path.join(REF, "tests", "data", "reference_1K.fa.gz"), "rt") as fh:
+        for line in fh:
+            if line.startswith(">"):
+                name = line[1:].split()[0]
+                seqs[name] = []
+            else:
+                seqs[name].append(line.strip())
+    seqs = {k: "".join(v) for k, v in seqs.items()}
+    k_len = 7
+    k_cor = synthetic_kcor(k_len)
+    regions = [("ref1", 0, 425, True), ("ref2", 0, 575, True), ("ref1", 1, 425, True), ("ref2", 1, 575, False),
+               ("ref2", 1, 300, True), ("ref2", 301, 575, True), ("ref1", 100, 103, False), ("ref1", 10, 11, False),
+               ("ref2", 500, 600, False), ("ref1", 200, 420, True)]
+    out = {"source": "reference tests/data/bbmap.sorted.bam + reference_1K.fa.gz via reference metacov/pileup.py:experimental",
+           "k_len": k_len, "fasta": seqs, "rows": _exp_rows(ref, bam, k_cor, k_len, _Fasta(seqs), regions)}
+    with open(os.path.join(GOLD, "fixture_experimental.json"), "w") as fh:
+        json.dump(out, fh, indent=1)
+    return out
+
+
+def experimental_synthetic():
+    """Paired synthetic reads that reach the corners of ``experimental``: reverse reads whose
+    interval starts before the region, mates on either side of a region border (negative slice
+    indices), names seen three and four times, secondary / improper reads, soft and hard clips,
+    N bases, aligned parts shorter than k_len."""
+    from oracle.experimental import synthetic_kcor
+    ref = ref_pileup_module()
+    rng = np.random.Generator(np.random.PCG64(20261019))
+    lengths = [900, 2500]
+    names = ["pA", "pB second"]
+    rows = []                                    # (tid, pos, flag, cigar ops, name, seq codes)
+    nt = np.array([1, 2, 4, 8], dtype=np.uint8)  # A C G T in nt16
+    serial = 0
+    for c, ln in enumerate(lengths):
+        for _ in range({0: 260, 1: 700}[c]):
+            frag = int(rng.integers(60, 400))
+            p1 = int(rng.integers(0, ln - 50))
+            p2 = min(ln - 30, p1 + frag)
+            rlen = int(rng.integers(4, 101))
+            nm = "q%d" % serial
+            serial += 1
+            fwd_first = rng.random() < 0.5
+            f1, f2 = (99, 147) if fwd_first else (83, 163)
+            kind = rng.random()
+            if kind < 0.08:
+                f1, f2 = f1 & ~2, f2 & ~2                       # improper pair
+            for p, f in ((p1, f1), (p2, f2)):
+                k = rng.integers(0, 5)
+                ops = [(rlen << 4) | 0]
+                lseq = rlen
+                if k == 1:
+                    sc = int(rng.integers(1, 12)); ops = [(sc << 4) | 4, (rlen << 4) | 0]; lseq = rlen + sc
+                elif k == 2:
+                    sc = int(rng.integers(1, 9)); ops = [(3 << 4) | 5, (rlen << 4) | 7, (sc << 4) | 4]; lseq = rlen + sc
+                elif k == 3 and rlen > 20:
+                    a = rlen // 2; ops = [(a << 4) | 0, (2 << 4) | 2, ((rlen - a) << 4) | 0]
+                seq = nt[rng.integers(0, 4, lseq)].copy()
+                if rng.random() < 0.05:
+                    seq[int(rng.integers(0, min(lseq, 8)))] = 15   # an N near the start
+                rows.append((c, p, f, ops, nm, seq))
+                if rng.random() < 0.04:                            # secondary copy of the same read
+                    rows.append((c, p, f | 0x100, ops, nm, seq))
+                if rng.random() < 0.03:                            # supplementary piece: same name, proper-pair flag kept
+                    rows.append((c, min(ln - 20, p + 7), f | 0x800, [(12 << 4) | 0], nm, nt[rng.integers(0, 4, 12)].copy()))
+    rows.sort(key=lambda r: (r[0], r[1]))
+    recs = bamio.BamRecords()
+    recs.tid = np.array([r[0] for r in rows], np.int32); recs.pos = np.array([r[1] for r in rows], np.int32)
+    recs.flag = np.array([r[2] for r in rows], np.uint16); recs.mapq = np.full(len(rows), 30, np.uint8)
+    cigs = [r[3] for r in rows]
+    recs.cig_off = np.concatenate(([0], np.cumsum([len(c) for c in cigs]))).astype(np.int64)
+    recs.cig = np.array([op for c in cigs for op in c], dtype=np.uint32)
+    recs.names = [r[4] for r in rows]; recs.seqs = [r[5] for r in rows]
+    recs.l_seq = np.array([len(s) for s in recs.seqs], np.int32); recs.isize = np.zeros(len(rows), np.int32)
+    recs.mtid = np.full(len(rows), -1, np.int32); recs.mpos = np.full(len(rows), -1, np.int32)
+    recs.reflen = bamio.cigar_reflen(recs.cig_off, recs.cig)
+    hdr = bamio.BamHeader("", tuple(names), tuple(lengths))
+    bam = FakeAlignmentFile(hdr, recs)
+    save_soa(os.path.join(GOLD, "synth_pairs_soa.npz"), hdr, recs)
+    fa = {n: "".join("ACGTN"[int(x)] for x in rng.choice(5, ln, p=[0.24, 0.26, 0.26, 0.23, 0.01])) for n, ln in zip(names, lengths)}
+    k_len = 5
+    k_cor = synthetic_kcor(k_len)
+    regions = [("pA", 0, 900, True), ("pB second", 0, 2500, True), ("pA", 100, 500, False), ("pB second", 1200, 1201, False),
+               ("pB second", 1000, 1400, True), ("pA", 850, 900, False), ("pA", 0, 60, False), ("pB second", 2400, 2600, False),
+               ("pB second", 3, 2497, False), ("pA", 300, 302, False)]
+    out = {"source": "synthetic paired SoA (oracle/make_golden.py:experimental_synthetic) via reference metacov/pileup.py:experimental",
+           "k_len": k_len, "fasta": fa, "rows": _exp_rows(ref, bam, k_cor, k_len, _Fasta(fa), regions)}
+    with open(os.path.join(GOLD, "synth_pairs_experimental.json"), "w") as fh:
+        json.dump(out, fh, indent=1)
+    return out
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     f = fixture()
     s = synthetic()
+    ef = experimental_fixture()
+    es = experimental_synthetic()
+    print("experimental rows:", len(ef["rows"]), len(es["rows"]))
     print("fixture regions:", len(f["classic"]), " synthetic regions:", len(s["classic"]))
     for row in f["classic"][:6]:
         print(row)

@@ -60,3 +60,28 @@ def assert_classic_equal(got, want, where=""):
         assert abs(float(got[k]) - float(want[k])) <= 0.01 + 1e-9, (where, k, got[k], want[k])
     for k in ("avg", "q23"):
         assert float(got[k]) == float(want[k]), (where, k, got[k], want[k])
+
+
+def exp_value(v):
+    """Golden JSON stores nan / inf as strings."""
+    return float(v) if isinstance(v, str) else v
+
+
+def assert_experimental_equal(got, want, where=""):
+    """``experimental`` outputs.  Integer-derived keys must be identical; keys made of float sums
+    (north_star: 1e-6 relative) are compared before rounding where possible, and to one unit of
+    the reference's round(., 3) after it."""
+    import math
+    assert set(got) == set(want), (where, sorted(got), sorted(want))
+    for k in ("den", "ambig", "improper", "nzef", "gc", "cov2"):
+        g, w = float(got[k]), exp_value(want[k])
+        assert g == w or (math.isnan(g) and math.isnan(w)), (where, k, got[k], want[k])
+    for k in ("cov", "covc"):
+        g, w = float(got[k]), exp_value(want[k])
+        assert abs(g - w) <= 1e-9 * max(1.0, abs(w)), (where, k, g, w)
+    for k in ("denc", "cf", "wnf", "ecor", "cov3"):
+        g, w = float(got[k]), exp_value(want[k])
+        if math.isnan(w) or math.isinf(w):
+            assert (math.isnan(g) and math.isnan(w)) or g == w, (where, k, g, w)
+        else:
+            assert abs(g - w) <= 0.001 + 1e-6 * abs(w) + 1e-9, (where, k, g, w)
