@@ -4,9 +4,9 @@ Keeps the commands, options and CSV formats of reference metacov/cli.py
 (`pileup` cli.py:35-109, `scan` cli.py:112-285) so that existing invocations
 keep working; the work behind them runs on the GPU.  What is not carried over
 is out of the hot-path scope and fails with a clear message instead of being
-silently approximated: FASTQ input and `-b/-M` of `scan`, `-k` (the
-`experimental` coverage model) of `pileup`, and the `simulate` command
-(SURVEY.md 2, 8(f)).
+silently approximated: FASTQ input and `-b/-M` of `scan`, and the `simulate`
+command.  `pileup -k` (the `experimental` coverage model,
+reference metacov/pileup.py:38-173) runs on the GPU like `classic`.
 """
 import csv
 import logging
@@ -18,6 +18,7 @@ from . import pileup as _pileup
 from . import scan as _scan
 from . import util
 from .alignmentfile import AlignmentFile
+from .fasta import FastaFile
 
 logging.basicConfig(level=logging.INFO, format="[%(relativeCreated)6.1f %(funcName)s]  %(message)s",
                     datefmt="%I:%M:%S")
@@ -45,10 +46,8 @@ def pileup(bamfile, reference_fasta, regionfile_blast7, regionfile_csv, kmer_his
     """
     Compute fold coverage values
     """
-    if kmer_histogram is not None:
-        raise click.UsageError("-k/--kmer-histogram (the experimental k-mer corrected coverage, reference "
-                               "metacov/pileup.py:38-173) is not part of the GPU hot path in this build")
     bam = AlignmentFile(bamfile.name)
+    fasta = FastaFile(reference_fasta.name) if reference_fasta else None          # cli.py:59
     regions = util.make_region_iterator(regionfile_blast7, regionfile_csv, bam)
     try:
         mapped, unmapped = bam.mapped, bam.unmapped
@@ -70,8 +69,13 @@ def pileup(bamfile, reference_fasta, regionfile_blast7, regionfile_csv, kmer_his
         start, end = sorted((int(hit.sstart), int(hit.send)))
         starts.append(start)
         ends.append(end)
+    # cli.py:81 -- the k-mer length option is not passed on to the loader (its default 7 applies)
+    k_cor = _pileup.load_kmerhist(kmer_histogram) if kmer_histogram else None
     with click.progressbar(file=sys.stderr, length=0, label="Calculating coverages"):
         results = _pileup.classic_many(bam, refs, starts, ends) if hits else []
+        if k_cor is not None and hits:                                            # cli.py:93-95
+            for result, extra in zip(results, _pileup.experimental_many(bam, k_cor, kmer_length, fasta, refs, starts, ends)):
+                result.update(extra)
     writer = None
     for hit, result in zip(hits, results):
         if writer is None:

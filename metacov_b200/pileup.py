@@ -78,13 +78,21 @@ def classic(bam, ref, start, end):
 
 def load_kmerhist(f, k_len=7):
     """Drop-in for ``metacov.pileup.load_kmerhist`` (reference pileup.py:29-35):
-    k-mer -> n0 / mean(n1..) for R1 and R2 from ``metacov scan``'s CSV."""
+    k-mer -> n0 / mean(n1..) for R1 and R2 from ``metacov scan``'s CSV.
+
+    The reference expects the columns ``Mapped`` and ``R`` and averages "all other columns", which
+    only worked while pandas silently skipped the text columns; ``metacov scan`` at the reference's
+    HEAD names the read-number column ``IsRead1`` / ``IsRead2`` instead.
+    Both layouts are read here: the ratio is taken over the numeric columns, and the read number
+    comes from ``R`` if present, else from ``IsRead1`` / ``IsRead2`` (values ``R1`` / ``R2``)."""
     import pandas as pd
     df = pd.read_csv(f)
     df = df[~((df.Mapped == "Unmapped") | (df.kmer == "N" * k_len))]
     df = df.set_index("kmer")
-    cor = df[df.columns[0]] / df[df.columns[1:]].mean(axis=1)
-    return [cor[df.R == r].to_dict() for r in ("R1", "R2")]
+    num = df.select_dtypes("number")
+    cor = num[num.columns[0]] / num[num.columns[1:]].mean(axis=1)
+    rcol = df.R if "R" in df.columns else (df.IsRead1 if "IsRead1" in df.columns else df.IsRead2)
+    return [cor[rcol == r].to_dict() for r in ("R1", "R2")]
 
 
 # ---- pileup.experimental -------------------------------------------------------------------------

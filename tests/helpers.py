@@ -78,7 +78,10 @@ def assert_experimental_equal(got, want, where=""):
         assert g == w or (math.isnan(g) and math.isnan(w)), (where, k, got[k], want[k])
     for k in ("cov", "covc"):
         g, w = float(got[k]), exp_value(want[k])
-        assert abs(g - w) <= 1e-9 * max(1.0, abs(w)), (where, k, g, w)
+        if math.isnan(w) or math.isinf(w):          # k-mer ratios of 0/0 or x/0 propagate (garbage in, same garbage out)
+            assert (math.isnan(g) and math.isnan(w)) or g == w, (where, k, g, w)
+        else:
+            assert abs(g - w) <= 1e-9 * max(1.0, abs(w)), (where, k, g, w)
     for k in ("denc", "cf", "wnf", "ecor", "cov3"):
         g, w = float(got[k]), exp_value(want[k])
         if math.isnan(w) or math.isinf(w):

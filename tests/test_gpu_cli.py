@@ -153,3 +153,40 @@ def test_kmer_hist_api_and_cli(fixture_bam, tmp_path):
     k = 0b01_00_11_10_00_01_11                      # low bits first: T C A G T A C  (11 01 00 10 11 00 01)
     assert rows[2 + k][0] == scan.kmer_base2_to_ascii(k, 7) and [int(x) for x in rows[2 + k][1:]] == want[k].tolist()
     assert sum(1 for _ in open(tmp_path / "i.csv")) == 250
+
+
+def test_cli_pileup_with_kmer_histogram(fixture_bam, tmp_path):
+    """reference tests/test_cli.py:47-56 (`scan X.bam -o k.csv` then `pileup -k k.csv`): the scan CSV
+    feeds load_kmerhist, `experimental` adds its 13 columns to every row (cli.py:93-95)."""
+    from metacov_b200 import pileup
+    from metacov_b200.cli import pileup as pileup_cmd, scan as scan_cmd
+    from oracle import experimental as oexp
+    from helpers import assert_experimental_equal, fake_bam
+    kcsv = tmp_path / "kmers.csv"
+    res = CliRunner().invoke(scan_cmd, [fixture_bam, "-o", str(kcsv), "-g", "Mapped", "-g", "IsRead1"])
+    assert res.exit_code == 0, res.output
+    gold = load_json("fixture_experimental.json")
+    fa = tmp_path / "ref.fa"
+    with open(fa, "w") as fh:
+        for name, seq in gold["fasta"].items():
+            fh.write(">%s some description\n" % name)
+            for i in range(0, len(seq), 60):
+                fh.write(seq[i:i + 60] + "\n")
+    out = tmp_path / "cov.csv"
+    res = CliRunner().invoke(pileup_cmd, ["-b", fixture_bam, "-k", str(kcsv), "-f", str(fa), "-o", str(out)])
+    assert res.exit_code == 0, res.output
+    rows = list(csv.DictReader(open(out)))
+    assert len(rows) == 2 and rows[0]["sacc"] == "ref1"
+    keys = {"cov", "covc", "den", "denc", "cov2", "cf", "ambig", "improper", "nzef", "gc", "ecor", "wnf", "cov3"}
+    assert keys | {"min", "max", "med", "std", "avg", "q23", "sum", "sacc", "start", "end"} == set(rows[0])
+    # the same numbers from the oracle with the k-mer ratios the CSV yields
+    with open(kcsv) as fh:
+        k_cor = pileup.load_kmerhist(fh)
+    assert len(k_cor) == 2 and len(k_cor[0]) > 100
+    z, _ = load_soa("fixture_soa.npz")
+    obam = fake_bam(z)
+    for row, (ref, ln) in zip(rows, zip(obam.references, obam.lengths)):
+        with np.errstate(all="ignore"):
+            _, want = oexp.experimental(obam.recs, obam.references, k_cor, 7, gold["fasta"][ref], ref, 0, ln)
+        got = {k: float(row[k]) for k in keys}
+        assert_experimental_equal(got, {k: float(v) for k, v in want.items()}, ref)
