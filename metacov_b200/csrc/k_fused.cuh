@@ -64,7 +64,7 @@ struct FusedArgs {
   uint32_t* tile_cnt;         // [cnt_pad] far ends per tile -> inclusive scan in place (follows tile_agg)
   uint32_t* tile_cursor;      // [n_tiles] scatter cursors
   uint32_t* far_sorted;       // [far_cap] in-tile offsets bucketed by tile
-  int64_t* tile_first;        // [n_tiles+1]
+  uint32_t* tile_first;       // [n_tiles+1] (a fused batch holds < 2^32 reads)
   int32_t* depth;
   int32_t* tile_cap;          // [n_tiles] max of depth[p-1]+starts[p] in the tile, written only when > max_depth
   int32_t max_depth;          // htslib maxcnt (<= 0: cap disabled)
@@ -89,7 +89,7 @@ __device__ __noinline__ unsigned long long warp_cigar_reflen_call(const uint32_t
 
 // Rare path of k_fused_prep: some read of this warp is the first of a new tile.  Entered by the
 // whole warp.  tl[r] = tile of read r (already clamped), prev = tile of the read before this thread's.
-__device__ __noinline__ void prep_tile_boundaries(int64_t* tile_first, int64_t i0, int nv, int64_t prev, int64_t t0,
+__device__ __noinline__ void prep_tile_boundaries(uint32_t* tile_first, int64_t i0, int nv, int64_t prev, int64_t t0,
                                                   int64_t t1, int64_t t2, int64_t t3, bool is_last, int64_t n,
                                                   int64_t last_tile, int lane) {
 #pragma unroll 1
@@ -104,14 +104,14 @@ __device__ __noinline__ void prep_tile_boundaries(int64_t* tile_first, int64_t i
       lo = is_last ? prev + 1 : 1; hi = is_last ? last_tile : 0; v = n;
     }
     bool big = (hi - lo) >= 8;
-    if (!big) for (int64_t T = lo; T <= hi; ++T) tile_first[T] = v;
+    if (!big) for (int64_t T = lo; T <= hi; ++T) tile_first[T] = (uint32_t)v;
     unsigned todo = __ballot_sync(0xffffffffu, big);
     while (todo) {                             // long gaps are written by the whole warp
       int src = __ffs(todo) - 1;
       todo &= todo - 1;
       int64_t l2 = __shfl_sync(0xffffffffu, lo, src), h2 = __shfl_sync(0xffffffffu, hi, src);
       int64_t v2 = __shfl_sync(0xffffffffu, v, src);
-      for (int64_t T = l2 + lane; T <= h2; T += 32) tile_first[T] = v2;
+      for (int64_t T = l2 + lane; T <= h2; T += 32) tile_first[T] = (uint32_t)v2;
     }
   }
 }
@@ -466,12 +466,12 @@ k_fused_prep(const __grid_constant__ FusedArgs f) {
                              w_tb + (sq[1] >> kTileShift), w_tb + (sq[2] >> kTileShift), w_tb + t3, is_last, n,
                              (uint32_t)f.n_tiles, lane);
       } else if (t3 > ptile) {
-        int64_t* __restrict__ tf = f.tile_first + w_tb;
+        uint32_t* __restrict__ tf = f.tile_first + w_tb;
         uint32_t prev = ptile;
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           const uint32_t tr = sq[r] >> kTileShift;
-          for (uint32_t T = prev + 1; T <= tr; ++T) tf[T] = i0 + r;
+          for (uint32_t T = prev + 1; T <= tr; ++T) tf[T] = (uint32_t)(i0 + r);
           prev = max(prev, tr);
         }
       }
@@ -503,49 +503,46 @@ __global__ void k_far_scatter(FusedArgs f) {
 }
 
 struct TileMeta {
-  int64_t r0, r1, jmin;    // own reads [r0,r1); walk-back candidates [jmin,r0)
-  int carry;               // depth entering the tile
-  uint32_t k0, k1;         // far-end bucket [k0,k1)
+  uint32_t r0, r1, jmin;   // own reads [r0,r1); walk-back candidates [jmin,r0)
 };
 
-// has_far: the batch holds reads with a span above kNearSpan (else the far tables are all zero
-// and are not read)
-__device__ __forceinline__ TileMeta load_tile_meta(const FusedArgs& f, int64_t tile, bool has_far) {
+__device__ __forceinline__ TileMeta load_tile_meta(const FusedArgs& f, int64_t tile) {
   TileMeta m;
-  m.r0 = m.r1 = m.jmin = 0; m.carry = 0; m.k0 = m.k1 = 0;
+  m.r0 = m.r1 = m.jmin = 0;
   if (tile < f.n_tiles) {
     m.r0 = f.tile_first[tile]; m.r1 = f.tile_first[tile + 1];
-    m.jmin = tile > 0 ? f.tile_first[tile - 1] : 0;
-    if (has_far) {
-      m.carry = tile > 0 ? f.tile_agg[tile - 1] : 0;
-      m.k0 = tile > 0 ? f.tile_cnt[tile - 1] : 0u; m.k1 = f.tile_cnt[tile];
-    }
+    m.jmin = tile > 0 ? f.tile_first[tile - 1] : 0u;
   }
   return m;
 }
 
 #ifndef MCOV_TILE_MIN_CTAS
-#define MCOV_TILE_MIN_CTAS (16384 / kTile)   /* 1024 resident threads per SM */
+#define MCOV_TILE_MIN_CTAS (20480 / kTile)   /* 1280 resident threads per SM at <= 51 registers */
 #endif
-constexpr int kPreOwn = 4;     // own records prefetched per thread: one aligned 128-bit load
+constexpr int kPreOwn = 4;     // own records staged per thread: one aligned 16-byte copy
 
-// Records of the tile's own reads [r0,r1), four per thread from the 16-byte aligned index below r0
-// (entries outside the range are zeroed = "contributes nothing"), and one walk-back candidate.
-__device__ __forceinline__ void prefetch_recs(const FusedArgs& f, const TileMeta& m, uint4& own, uint32_t& back) {
-  const int64_t j = (m.r0 & ~(int64_t)3) + 4 * (int64_t)threadIdx.x;
-  own = make_uint4(0u, 0u, 0u, 0u);
-  if (j < m.r1) {
-    own = *reinterpret_cast<const uint4*>(f.rec + j);       // the buffer is padded past n
-    const int64_t lo = m.r0 - j, hi = m.r1 - j;               // valid lanes of the vector: [lo, hi)
-    if (lo > 0 || hi < 4) {
-      if (0 < lo || 0 >= hi) own.x = 0u;
-      if (1 < lo || 1 >= hi) own.y = 0u;
-      if (2 < lo || 2 >= hi) own.z = 0u;
-      if (3 < lo || 3 >= hi) own.w = 0u;
-    }
-  }
-  const int64_t jb = m.r0 - 1 - threadIdx.x;
-  back = (jb >= m.jmin) ? f.rec[jb] : 0u;
+__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem, bool valid) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(s), "l"(gmem), "r"(valid ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* smem, const void* gmem, bool valid) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(s), "l"(gmem), "r"(valid ? 4 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// Stage the records of a tile in shared memory with cp.async (no registers are held while the
+// copy is in flight): four own records per thread from the 16-byte aligned index below r0 and one
+// walk-back candidate.  Every thread later reads back only what it copied itself, so
+// cp.async.wait_group is all the synchronisation this needs.  Out-of-range copies write zeros.
+__device__ __forceinline__ void stage_recs(const FusedArgs& f, const TileMeta& m, uint4* s_own, uint32_t* s_back) {
+  const uint32_t j = (m.r0 & ~3u) + 4u * threadIdx.x;
+  cp_async_16(s_own + threadIdx.x, f.rec + j, j < m.r1);             // the buffer is padded past n
+  const bool vb = m.r0 > m.jmin + threadIdx.x;                        // jb = r0 - 1 - tid >= jmin
+  cp_async_4(s_back + threadIdx.x, f.rec + (vb ? m.r0 - 1u - threadIdx.x : 0u), vb);
+  cp_async_commit();
 }
 
 // +1 at the start of an own read, +1 in the end counters if it ends inside the tile (a far
@@ -561,11 +558,14 @@ __device__ __forceinline__ void tile_own(int* s_start, int* s_end, uint32_t r) {
 }
 
 // Persistent, software-pipelined: while tile k is accumulated in shared memory, scanned and
-// stored, the records of tile k+1 and the metadata of tile k+2 are already in flight.
+// stored, the records of tile k+1 are being copied into shared memory (cp.async) and the
+// metadata of tile k+2 is in flight.
 __global__ void __launch_bounds__(kFusedThreads, MCOV_TILE_MIN_CTAS)
 k_fused_tile(const __grid_constant__ FusedArgs f) {
   __shared__ __align__(16) int s_start[kTile];
   __shared__ __align__(16) int s_end[kTile];
+  __shared__ __align__(16) uint4 s_own[2][kFusedThreads];
+  __shared__ uint32_t s_back[2][kFusedThreads];
   __shared__ int s_warp[kFusedThreads / 32];
   __shared__ int s_warp2[kFusedThreads / 32];
   __shared__ int s_open[2];                             // near reads open at the tile border (double-buffered)
@@ -573,13 +573,11 @@ k_fused_tile(const __grid_constant__ FusedArgs f) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t stride = gridDim.x;
   const uint32_t reach = pc->max_span;                  // written by k_fused_prep
-  const bool has_far = pc->n_far != 0;
+  const bool has_far = pc->n_far != 0;                  // else the far tables are all zero and are not read
   int64_t tile = blockIdx.x;
-  TileMeta m_cur = load_tile_meta(f, tile, has_far);
-  TileMeta m_next = load_tile_meta(f, tile + stride, has_far);
-  uint4 own;
-  uint32_t back;
-  prefetch_recs(f, m_cur, own, back);
+  TileMeta m_cur = load_tile_meta(f, tile);
+  TileMeta m_next = load_tile_meta(f, tile + stride);
+  stage_recs(f, m_cur, s_own[0], s_back[0]);
   int mx = 0, cap = 0;
   {
     int4* z0 = reinterpret_cast<int4*>(s_start);
@@ -592,19 +590,28 @@ k_fused_tile(const __grid_constant__ FusedArgs f) {
 
 #pragma unroll 1
   for (; tile < f.n_tiles; tile += stride, par ^= 1) {
-    // prefetch for the following tiles first: these loads stay in flight during the whole body
-    uint4 n_own;
-    uint32_t n_back;
-    prefetch_recs(f, m_next, n_own, n_back);            // empty ranges when tile+stride is past the end
-    TileMeta m_nn = load_tile_meta(f, tile + 2 * stride, has_far);
+    // the following tiles first: these copies / loads stay in flight during the whole body
+    stage_recs(f, m_next, s_own[par ^ 1], s_back[par ^ 1]);      // empty ranges when tile+stride is past the end
+    const TileMeta m_nn = load_tile_meta(f, tile + 2 * stride);
     const int64_t base = tile << kTileShift;
+    cp_async_wait<1>();                                          // this tile's records have landed
 
     // reads that start in this tile (tile_first ranges: every record in [r0,r1) belongs here)
-    tile_own(s_start, s_end, own.x);
-    tile_own(s_start, s_end, own.y);
-    tile_own(s_start, s_end, own.z);
-    tile_own(s_start, s_end, own.w);
-    for (int64_t j = (m_cur.r0 & ~(int64_t)3) + kPreOwn * kFusedThreads + threadIdx.x; j < m_cur.r1; j += kFusedThreads)
+    {
+      uint4 own = s_own[par][threadIdx.x];
+      const uint32_t j = (m_cur.r0 & ~3u) + 4u * threadIdx.x;   // own.x is record j; valid records: [r0, r1)
+      if (j < m_cur.r0 || j + 4u > m_cur.r1) {
+        if (j + 0u < m_cur.r0 || j + 0u >= m_cur.r1) own.x = 0u;
+        if (j + 1u < m_cur.r0 || j + 1u >= m_cur.r1) own.y = 0u;
+        if (j + 2u < m_cur.r0 || j + 2u >= m_cur.r1) own.z = 0u;
+        if (j + 3u < m_cur.r0 || j + 3u >= m_cur.r1) own.w = 0u;
+      }
+      tile_own(s_start, s_end, own.x);
+      tile_own(s_start, s_end, own.y);
+      tile_own(s_start, s_end, own.z);
+      tile_own(s_start, s_end, own.w);
+    }
+    for (uint32_t j = (m_cur.r0 & ~3u) + kPreOwn * kFusedThreads + threadIdx.x; j < m_cur.r1; j += kFusedThreads)
       tile_own(s_start, s_end, f.rec[j]);                // dense tiles: the rest straight from global
     // near reads that started before the tile and end inside it: walk back while the start is
     // within max_span of the tile (sorted order => monotone distance).  reach <= kNearSpan = kTile,
@@ -612,39 +619,45 @@ k_fused_tile(const __grid_constant__ FusedArgs f) {
     // Each hit is a read that covers the last slot before the tile, and all of them end in this
     // tile: their number is the near depth entering the tile.
     {
-      uint32_t r = back;
-      int64_t j = m_cur.r0 - 1 - threadIdx.x;
+      uint32_t r = s_back[par][threadIdx.x];
+      int64_t j = (int64_t)m_cur.r0 - 1 - threadIdx.x;
       int open = 0;
-      while (j >= m_cur.jmin) {
+      while (j >= (int64_t)m_cur.jmin) {
         const uint32_t d = (uint32_t)kTile - (r & (kTile - 1));     // distance behind the tile start (>= 1)
         if (d > reach) break;
         const uint32_t code = r >> kTileShift;
         if (code >= d && code <= kNearSpan) { atomicAdd(&s_end[code - d], 1); ++open; }
         j -= kFusedThreads;
-        if (j >= m_cur.jmin) r = f.rec[j];
+        if (j >= (int64_t)m_cur.jmin) r = f.rec[j];
       }
       open = __reduce_add_sync(0xffffffffu, open);
       if (lane == 0 && open) atomicAdd(&s_open[par], open);
     }
-    // far ends bucketed for this tile
-    for (uint32_t k = m_cur.k0 + threadIdx.x; k < m_cur.k1; k += kFusedThreads)
-      atomicAdd(&s_end[f.far_sorted[k] & (kTile - 1)], 1);
+    // far reads: ends bucketed for this tile, and how many of them are open at the tile border
+    int carry = 0;
+    if (has_far) {
+      carry = tile > 0 ? f.tile_agg[tile - 1] : 0;
+      const uint32_t k0 = tile > 0 ? f.tile_cnt[tile - 1] : 0u, k1 = f.tile_cnt[tile];
+      for (uint32_t k = k0 + threadIdx.x; k < k1; k += kFusedThreads)
+        atomicAdd(&s_end[f.far_sorted[k] & (kTile - 1)], 1);
+    }
     __syncthreads();
 
-    // block scan of (starts - ends), warp-striped like k_scan_inplace
+    // block scan of (starts - ends), warp-striped like k_scan_inplace.  cap[p] = depth[p-1] +
+    // starts[p] is folded into one value per vector, relative to the vector's incoming depth.
     const int4* vs = reinterpret_cast<const int4*>(s_start);
     const int4* ve = reinterpret_cast<const int4*>(s_end);
-    int4 v[kScanVec], en[kScanVec];
-    int run[kScanVec];
+    int4 v[kScanVec];
+    int run[kScanVec], capv[kScanVec];
 #pragma unroll
     for (int j = 0; j < kScanVec; ++j) {
       int idx = (warp * kScanVec + j) * 32 + lane;
-      int4 st = vs[idx];
-      en[j] = ve[idx];
-      v[j].x = st.x - en[j].x;
-      v[j].y = v[j].x + st.y - en[j].y;
-      v[j].z = v[j].y + st.z - en[j].z;
-      v[j].w = v[j].z + st.w - en[j].w;
+      const int4 st = vs[idx], en = ve[idx];
+      v[j].x = st.x - en.x;
+      v[j].y = v[j].x + st.y - en.y;
+      v[j].z = v[j].y + st.z - en.z;
+      v[j].w = v[j].z + st.w - en.w;
+      capv[j] = max(max(st.x, v[j].x + st.y), max(v[j].y + st.z, v[j].z + st.w));
       run[j] = v[j].w;
     }
     int acc = 0;
@@ -668,7 +681,7 @@ k_fused_tile(const __grid_constant__ FusedArgs f) {
       int4* z1 = reinterpret_cast<int4*>(s_end);
       for (int k = threadIdx.x; k < kTile / 4; k += kFusedThreads) { z0[k] = make_int4(0, 0, 0, 0); z1[k] = make_int4(0, 0, 0, 0); }
     }
-    int off = m_cur.carry + s_open[par];                 // far reads open at the border + near reads open at the border
+    int off = carry + s_open[par];                       // far reads open at the border + near reads open at the border
     if (threadIdx.x == 0) s_open[par ^ 1] = 0;           // the other buffer: last read before the previous end-of-body barrier
 #pragma unroll
     for (int k = 0; k < kFusedThreads / 32; ++k) off += (k < warp) ? s_warp[k] : 0;
@@ -679,9 +692,9 @@ k_fused_tile(const __grid_constant__ FusedArgs f) {
     for (int j = 0; j < kScanVec; ++j) {
       int idx = (warp * kScanVec + j) * 32 + lane;
       int o = off + run[j];
+      cap_t = max(cap_t, o + capv[j]);
       v[j].x += o; v[j].y += o; v[j].z += o; v[j].w += o;
       mx = max(mx, max(max(v[j].x, v[j].y), max(v[j].z, v[j].w)));
-      cap_t = max(cap_t, max(max(v[j].x + en[j].x, v[j].y + en[j].y), max(v[j].z + en[j].z, v[j].w + en[j].w)));
       if (idx < n_vec) st_stream_int4(out + idx, v[j]);
     }
     cap = max(cap, cap_t);
@@ -689,9 +702,8 @@ k_fused_tile(const __grid_constant__ FusedArgs f) {
     if (f.max_depth > 0 && cap_t > f.max_depth) atomicMax(f.tile_cap + tile, cap_t);
     __syncthreads();                                     // counters cleared; s_warp is rewritten by the next tile
     m_cur = m_next; m_next = m_nn;
-    own = n_own;
-    back = n_back;
   }
+  cp_async_wait<0>();
 
   mx = warp_max(mx);
   cap = warp_max(cap);

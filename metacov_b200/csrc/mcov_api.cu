@@ -110,6 +110,7 @@ int finish_stage(mcov_ctx* ctx, ReadStage* s) {
 // Fused depth path for coordinate-sorted reads (k_fused.cuh).  `a` holds device pointers.
 int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a) {
   const int64_t n = a.n;
+  if (n >= (int64_t)0xFFFFFFF0ll) return fail(ctx, MCOV_ERR_RANGE, "mcov_depth_sorted: a batch holds at most 2^32-16 reads (read indices are 32-bit); split it or use mcov_begin/push/finalize");
   const int64_t n_tiles = (ctx->n_slots + kTile - 1) / kTile;
   const int64_t cnt_pad = (n_tiles + 1 + 3) & ~(int64_t)3;             // per-tile arrays, scanned in place as int32
   const int64_t scan_len = 2 * cnt_pad;                                // [tile_agg | tile_cnt]
@@ -121,7 +122,7 @@ int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a) {
                z_bytes = o_st + (size_t)scan_tiles * 8;
   CU(ctx->d_status.ensure(z_bytes));
   CU(ctx->d_start_slot.ensure((size_t)(std::max<int64_t>(n, 1) + 8) * sizeof(uint32_t)));   // rec (+ vector-load padding)
-  CU(ctx->d_tile_off.ensure((size_t)(n_tiles + 1) * 8));                                 // tile_first
+  CU(ctx->d_tile_off.ensure((size_t)(n_tiles + 1) * 4));                                 // tile_first
   CU(ctx->d_far_list.ensure((size_t)far_cap * 8));
   CU(ctx->d_far_sorted.ensure((size_t)far_cap * 4));
   cudaStream_t s = ctx->stream;
@@ -138,7 +139,7 @@ int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a) {
   f.tile_cnt = reinterpret_cast<uint32_t*>(z + o_cnt);
   f.tile_cursor = reinterpret_cast<uint32_t*>(z + o_cur);
   f.far_sorted = ctx->d_far_sorted.as<uint32_t>();
-  f.tile_first = ctx->d_tile_off.as<int64_t>();
+  f.tile_first = ctx->d_tile_off.as<uint32_t>();
   f.depth = ctx->depth;
   f.tile_cap = reinterpret_cast<int32_t*>(z + o_cap);
   f.max_depth = ctx->filt.max_depth;
@@ -149,7 +150,7 @@ int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a) {
     MCOV_LAUNCH(ctx, kKFusedPrep, (k_fused_prep<<<grid_for(groups, kPrepThreads, 8), kPrepThreads, 0, s>>>(f)));
     CU(cudaGetLastError());
   } else {
-    CU(cudaMemsetAsync(f.tile_first, 0, (size_t)(n_tiles + 1) * 8, s));
+    CU(cudaMemsetAsync(f.tile_first, 0, (size_t)(n_tiles + 1) * 4, s));
   }
   MCOV_LAUNCH(ctx, kKScanCounts, (k_scan_inplace<false><<<(unsigned)scan_tiles, kScanThreads, 0, s>>>(
       f.tile_agg, scan_len, reinterpret_cast<unsigned long long*>(z + o_st), pc_of(ctx))));
