@@ -375,3 +375,27 @@ def test_full_size_c2_bit_exact_and_properties():
         for k in ("sum", "sumsq", "iq_sum", "min", "max", "med_lo", "med_hi", "n_ge1"):
             assert np.array_equal(st[k], ref[k]), k
         assert int(st["sum"].sum()) == info["aligned_bases"]
+
+
+def test_dense_tile_takes_unpacked_counters():
+    """A tile touched by >= 65 536 reads leaves the packed (16+16 bit) counters of k_fused_tile for the
+    two-array path; depth stays bit-exact either way (cap disabled: 70 000 reads start at one position)."""
+    from metacov_b200 import ReadBatch
+    rng = np.random.default_rng(21)
+    lengths = np.array([9000, 4000], np.int32)
+    ps0 = np.sort(np.r_[np.full(70000, 2500), np.full(30000, 2600), rng.integers(0, 8800, 20000)])
+    ps1 = np.sort(rng.integers(0, 3900, 3000))
+    tid = np.r_[np.zeros(len(ps0), np.int32), np.ones(len(ps1), np.int32)]
+    pos = np.r_[ps0, ps1].astype(np.int32)
+    n = len(tid)
+    rl = rng.integers(50, 150, n)
+    rl[:5] = 3000                                    # a few far reads across the dense tiles
+    b = ReadBatch(tid, pos, np.zeros(n, np.uint16), np.full(n, 30, np.uint8), np.arange(n + 1, dtype=np.uint32),
+                  (rl.astype(np.uint32) << 4))
+    want, off, _ = cport.depth(b, lengths, mode="diff")
+    with engine_for(lengths, max_depth=0) as eng:
+        eng.depth_sorted(b)
+        pi = eng.pass_info()
+        assert pi["max_depth_seen"] == int(want.max()) and pi["max_depth_seen"] > 65536
+        for c in range(2):
+            assert np.array_equal(eng.copy_depth(c), want[off[c]:off[c] + lengths[c]]), c
