@@ -161,6 +161,22 @@ int  mcov_region_stats_run(mcov_ctx* ctx, int64_t g,
                            const int32_t* tid, const int32_t* start, const int32_t* end,
                            int32_t breadth_n, mcov_region_stats* host_out);
 
+/* Pipelined variant of mcov_region_stats_run for callers that process batch
+ * after batch: `submit` enqueues the statistics kernels, the copy of the g
+ * records into pinned staging slot `slot` (0 or 1) and the copy of the pass
+ * verdict, and returns without synchronising -- the caller may enqueue the next
+ * depth pass right away (same stream: it runs after these kernels).  `collect`
+ * waits for that slot, delivers the verdict of the pass the statistics belong
+ * to and copies the records to host_out.  What cannot be done once a later
+ * pass may have overwritten the depth is reported instead of approximated:
+ * MCOV_ERR_STATE if that pass needs the max_depth replay or a region's depth
+ * left the counting histogram (run the batch again through mcov_depth_sorted +
+ * mcov_region_stats_run). */
+int  mcov_region_stats_submit(mcov_ctx* ctx, int64_t g,
+                              const int32_t* tid, const int32_t* start, const int32_t* end,
+                              int32_t breadth_n, int slot);
+int  mcov_region_stats_collect(mcov_ctx* ctx, int slot, mcov_region_stats* host_out);
+
 /* Asynchronous variant for multi-GPU pipelines: the g records are written to
  * DEVICE memory dev_out on the context's stream and the call returns without
  * synchronising (the records can be handed to a collective on the same

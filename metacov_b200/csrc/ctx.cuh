@@ -106,6 +106,15 @@ struct mcov_ctx {
   // stats scratch
   mcov::DevBuf d_tasks, d_rlen, d_rchunks, d_rhist, d_pool, d_done, d_out, d_win_slot, d_win_n, d_win_out;
   mcov::PinBuf h_pin;
+  // pipelined statistics (mcov_region_stats_submit / collect): two pinned slots
+  struct StatSlot {
+    mcov::PinBuf buf;              // [g records | PassCounters]
+    cudaEvent_t done = nullptr;
+    int64_t g = -1;                // -1 = nothing submitted
+    bool has_verdict = false;
+    int64_t n_reads = 0;
+    std::vector<int32_t> len0;     // regions of length 0 (their records are zeroed, like mcov_region_stats_run)
+  } slot[2];
 
   // launch accounting + optional per-kernel event timing
   int64_t n_launches = 0;

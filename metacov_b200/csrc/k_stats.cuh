@@ -353,15 +353,32 @@ k_region_stats_warp(StatArgs a, int64_t task0, int64_t n_tasks, uint32_t* __rest
   const int64_t nvec = ((s1 - a0) + 3) >> 2;
   const int4* vp = reinterpret_cast<const int4*>(a.depth + a0);
   uint32_t* win = s_win[warp];
-  // pass 1: min / max bin
+  // pass 1: min / max bin.  Four independent 128-bit loads per lane in flight (this pass is the one
+  // that comes from HBM); the first and last vector may hold slots of the neighbouring contigs.
   int lo = pad > 0 ? 0 : kHistBins - 1, hi = 0;
-  for (int64_t j = lane; j < nvec; j += 32) {
-    int4 q = __ldg(vp + j);
-    int v[4] = {q.x, q.y, q.z, q.w};
-    int64_t e0 = a0 + (j << 2);
+  const int64_t jf0 = (s0 != a0) ? 1 : 0, jf1 = ((a0 + (nvec << 2)) != s1) ? nvec - 1 : nvec;   // full vectors [jf0, jf1)
+  for (int64_t j = jf0 + lane; j < jf1; j += 128) {
+    const bool v1 = j + 32 < jf1, v2 = j + 64 < jf1, v3 = j + 96 < jf1;
+    int4 q0 = __ldg(vp + j), q1 = q0, q2 = q0, q3 = q0;
+    if (v1) q1 = __ldg(vp + j + 32);
+    if (v2) q2 = __ldg(vp + j + 64);
+    if (v3) q3 = __ldg(vp + j + 96);
+    int mn = min(min(min(q0.x, q0.y), min(q0.z, q0.w)), min(min(q1.x, q1.y), min(q1.z, q1.w)));
+    mn = min(mn, min(min(min(q2.x, q2.y), min(q2.z, q2.w)), min(min(q3.x, q3.y), min(q3.z, q3.w))));
+    int mxv = max(max(max(q0.x, q0.y), max(q0.z, q0.w)), max(max(q1.x, q1.y), max(q1.z, q1.w)));
+    mxv = max(mxv, max(max(max(q2.x, q2.y), max(q2.z, q2.w)), max(max(q3.x, q3.y), max(q3.z, q3.w))));
+    lo = min(lo, hist_bin(mn)); hi = max(hi, hist_bin(mxv));     // hist_bin is monotone
+  }
+  if (lane < 2 && nvec > 0) {                                     // the (at most two) partial vectors
+    const int64_t j = lane == 0 ? 0 : nvec - 1;
+    if ((lane == 0 && jf0 == 1) || (lane == 1 && jf1 == nvec - 1 && (nvec > 1 || jf0 == 0))) {
+      int4 q = __ldg(vp + j);
+      int v[4] = {q.x, q.y, q.z, q.w};
+      int64_t e0 = a0 + (j << 2);
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (e0 + k >= s0 && e0 + k < s1) { int b = hist_bin(v[k]); lo = min(lo, b); hi = max(hi, b); }
+      for (int k = 0; k < 4; ++k)
+        if (e0 + k >= s0 && e0 + k < s1) { int b = hist_bin(v[k]); lo = min(lo, b); hi = max(hi, b); }
+    }
   }
   lo = warp_min(lo); hi = warp_max(hi);
   if (hi < lo) hi = lo;

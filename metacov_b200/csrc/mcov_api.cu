@@ -268,6 +268,7 @@ void mcov_destroy(mcov_ctx* ctx) {
                     &ctx->d_out, &ctx->d_win_slot, &ctx->d_win_n, &ctx->d_win_out};
   for (DevBuf* b : bufs) b->release();
   ctx->h_pin.release();
+  for (auto& sl : ctx->slot) { sl.buf.release(); if (sl.done) cudaEventDestroy(sl.done); }
   ctx->prof_collect();
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -731,6 +732,66 @@ int mcov_region_stats_run(mcov_ctx* ctx, int64_t g, const int32_t* tid, const in
     for (int64_t i = 0; i < g; ++i)
       if (end[i] != start[i] && (host_out[i].flags & kStatOverflow)) host_out[i] = again[i];
   }
+  return MCOV_OK;
+}
+
+int mcov_region_stats_submit(mcov_ctx* ctx, int64_t g, const int32_t* tid, const int32_t* start, const int32_t* end,
+                             int32_t breadth_n, int slot) {
+  if (!ctx) return MCOV_ERR_ARG;
+  if (ctx->state != kDepthReady) return fail(ctx, MCOV_ERR_STATE, "mcov_region_stats_submit: depth not ready");
+  if (slot < 0 || slot > 1 || g < 0 || (g > 0 && (!tid || !start || !end))) return fail(ctx, MCOV_ERR_ARG, "mcov_region_stats_submit: bad arguments");
+  if (g > INT32_MAX) return fail(ctx, MCOV_ERR_RANGE, "mcov_region_stats_submit: more than 2^31-1 regions");
+  CU(cudaSetDevice(ctx->device));
+  mcov_ctx::StatSlot& sl = ctx->slot[slot];
+  if (sl.g >= 0) return fail(ctx, MCOV_ERR_STATE, "mcov_region_stats_submit: slot not collected yet");
+  cudaStream_t s = ctx->stream;
+  const size_t out_bytes = (size_t)g * sizeof(mcov_region_stats);
+  CU(sl.buf.ensure(out_bytes + sizeof(PassCounters)));
+  if (!sl.done) CU(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+  if (g > 0) {
+    CU(ctx->d_out.ensure(out_bytes));
+    int rc = stats_launch(ctx, g, tid, start, end, breadth_n, ctx->d_out.as<mcov_region_stats>());
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(sl.buf.p, ctx->d_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
+  }
+  sl.has_verdict = ctx->verdict_pending;
+  if (sl.has_verdict) {
+    CU(cudaMemcpyAsync(sl.buf.as<char>() + out_bytes, ctx->d_pc.p, sizeof(PassCounters), cudaMemcpyDeviceToHost, s));
+    ctx->verdict_pending = false;                  // the verdict of this pass now travels with the slot
+  }
+  CU(cudaEventRecord(sl.done, s));
+  sl.g = g;
+  sl.n_reads = ctx->n_reads_pushed;
+  sl.len0.clear();
+  for (int64_t i = 0; i < g; ++i) if (end[i] == start[i]) sl.len0.push_back((int32_t)i);
+  return MCOV_OK;
+}
+
+int mcov_region_stats_collect(mcov_ctx* ctx, int slot, mcov_region_stats* host_out) {
+  if (!ctx) return MCOV_ERR_ARG;
+  if (slot < 0 || slot > 1) return fail(ctx, MCOV_ERR_ARG, "mcov_region_stats_collect: bad slot");
+  mcov_ctx::StatSlot& sl = ctx->slot[slot];
+  if (sl.g < 0) return fail(ctx, MCOV_ERR_STATE, "mcov_region_stats_collect: nothing submitted in this slot");
+  if (sl.g > 0 && !host_out) return fail(ctx, MCOV_ERR_ARG, "mcov_region_stats_collect: null output");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaEventSynchronize(sl.done));
+  const int64_t g = sl.g;
+  sl.g = -1;
+  const size_t out_bytes = (size_t)g * sizeof(mcov_region_stats);
+  if (sl.has_verdict) {
+    PassCounters h;
+    std::memcpy(&h, sl.buf.as<char>() + out_bytes, sizeof(h));
+    if (h.unsorted) return fail(ctx, MCOV_ERR_UNSORTED, "mcov_region_stats_collect: the reads of that pass were not sorted by (tid,pos)");
+    if ((int64_t)h.n_far > std::min<int64_t>(std::max<int64_t>(sl.n_reads, 1), kFarCapDefault))
+      return fail(ctx, MCOV_ERR_RANGE, "mcov_region_stats_collect: too many long-span reads in that pass");
+    if (ctx->filt.max_depth > 0 && h.cap_metric > ctx->filt.max_depth)
+      return fail(ctx, MCOV_ERR_STATE, "mcov_region_stats_collect: that pass needs the max_depth replay; rerun it through mcov_depth_sorted + mcov_region_stats_run");
+  }
+  if (g > 0) std::memcpy(host_out, sl.buf.p, out_bytes);
+  for (int32_t i : sl.len0) std::memset(&host_out[i], 0, sizeof(mcov_region_stats));
+  for (int64_t i = 0; i < g; ++i)
+    if (host_out[i].flags & kStatOverflow)
+      return fail(ctx, MCOV_ERR_STATE, "mcov_region_stats_collect: a region's depth left the counting histogram; rerun it through mcov_region_stats_run");
   return MCOV_OK;
 }
 

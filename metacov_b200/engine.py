@@ -215,6 +215,23 @@ class CoverageEngine:
             self._pinned = torch.empty(g * 64 + 64, dtype=torch.uint8).pin_memory()
         return self._pinned.numpy()[:g * 64].view(_capi.REGION_STATS_DTYPE)
 
+    def region_stats_submit(self, tid, start, end, breadth_n=1, slot=0):
+        """Pipelined statistics: enqueue the kernels and the copy-back into staging slot 0/1 and
+        return at once, so that the next depth pass can be enqueued before these results are
+        waited for.  ``region_stats_collect(ticket)`` returns the records."""
+        tid = np.ascontiguousarray(tid, dtype=np.int32)
+        start = np.ascontiguousarray(start, dtype=np.int32)
+        end = np.ascontiguousarray(end, dtype=np.int32)
+        self._check(lib.mcov_region_stats_submit(self._ctx, len(tid), _capi.ptr(tid), _capi.ptr(start), _capi.ptr(end),
+                                                 int(breadth_n), int(slot)))
+        return (int(slot), len(tid))
+
+    def region_stats_collect(self, ticket):
+        slot, g = ticket
+        out = np.zeros(g, dtype=_capi.REGION_STATS_DTYPE)
+        self._check(lib.mcov_region_stats_collect(self._ctx, slot, _capi.ptr(out)))
+        return out
+
     def region_stats_enqueue(self, tid, start, end, out, breadth_n=1):
         """Asynchronous: write len(tid) records into the CUDA uint8 tensor ``out`` (>= 64 bytes per
         region) on the engine's stream; no synchronisation (see mcov_region_stats_enqueue)."""

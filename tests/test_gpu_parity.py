@@ -399,3 +399,49 @@ def test_dense_tile_takes_unpacked_counters():
         assert pi["max_depth_seen"] == int(want.max()) and pi["max_depth_seen"] > 65536
         for c in range(2):
             assert np.array_equal(eng.copy_depth(c), want[off[c]:off[c] + lengths[c]]), c
+
+
+def test_pipelined_statistics_equal_synchronous():
+    """mcov_region_stats_submit / collect: two slots in flight across depth passes, records identical to
+    mcov_region_stats_run; error reporting for what cannot be completed after the fact."""
+    from metacov_b200 import McovError, _capi, synth
+    w = synth.c2(0.01)
+    b, _ = synth.generate_host(w)
+    g = w.n_contigs
+    tid = np.arange(g, dtype=np.int32)
+    start = np.zeros(g, np.int32)
+    end = w.contig_len.astype(np.int32).copy()
+    end[3] = 0                                          # a zero-length region: zeroed record
+    with engine_for(w.contig_len) as eng:
+        eng.depth_sorted(b)
+        want = eng.region_stats(tid, start, end).copy()
+        tickets = []
+        for k in range(4):
+            eng.depth_sorted(b, wait=False)
+            tickets.append(eng.region_stats_submit(tid, start, end, slot=k & 1))
+            if len(tickets) == 2:
+                got = eng.region_stats_collect(tickets.pop(0))
+                assert got.tobytes() == want.tobytes(), k
+        assert eng.region_stats_collect(tickets.pop(0)).tobytes() == want.tobytes()
+        # a slot cannot be submitted twice, nor collected twice
+        eng.depth_sorted(b, wait=False)
+        t = eng.region_stats_submit(tid, start, end, slot=0)
+        with pytest.raises(McovError) as ei:
+            eng.region_stats_submit(tid, start, end, slot=0)
+        assert ei.value.code == _capi.MCOV_ERR_STATE
+        eng.region_stats_collect(t)
+        with pytest.raises(McovError):
+            eng.region_stats_collect(t)
+        # unsorted input: the verdict travels with the slot
+        perm = np.random.default_rng(1).permutation(len(b.tid))
+        from metacov_b200 import ReadBatch
+        off = b.cig_off.astype(np.int64)
+        nc = (off[1:] - off[:-1])[perm]
+        cig = np.concatenate([b.cig[off[i]:off[i + 1]] for i in perm]) if len(perm) else b.cig
+        ub = ReadBatch(b.tid[perm], b.pos[perm], b.flag[perm], b.mapq[perm],
+                       np.concatenate(([0], np.cumsum(nc))).astype(np.uint32), cig)
+        eng.depth_sorted(ub, wait=False)
+        t = eng.region_stats_submit(tid, start, end, slot=1)
+        with pytest.raises(McovError) as ei:
+            eng.region_stats_collect(t)
+        assert ei.value.code == _capi.MCOV_ERR_UNSORTED
