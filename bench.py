@@ -263,15 +263,23 @@ def run_ours(args):
     barrier()
     if sampler:
         sampler.start()
-    # N=1: the K steps are pipelined the way a caller with batch after batch would run them --
+    # The K steps are pipelined the way a caller with batch after batch would run them --
     # the statistics of step k are collected from a pinned slot after step k+1 has been enqueued
     # (mcov_region_stats_submit / collect), so the GPU never waits for the host between steps.
     # Every step's records still reach the host inside the timed region.
     def run_steps(k, depth_call):
         if world > 1:
-            for _ in range(k):
-                step(dbatch)
-            return
+            # same pipelining with the collective in it: records of step k+1, their all-gather and the
+            # copy-back are enqueued before step k's are waited for (two DeviceGather slots)
+            prev, out = None, None
+            for i in range(k):
+                depth_call()
+                eng.region_stats_enqueue(reg_tid, reg_start, reg_end, dg.local[i & 1])
+                dg.submit(i & 1, want_host=(rank == 0))
+                if prev is not None:
+                    out = dg.collect(prev, want_host=(rank == 0))
+                prev = i & 1
+            return dg.collect(prev, want_host=(rank == 0))
         prev = None
         for i in range(k):
             depth_call()
@@ -300,15 +308,17 @@ def run_ours(args):
     ms_step = float(t_t.item()) / args.steps
     launches = eng.launch_count() - l0
     # the same K steps with one synchronising call per step (no pipelining), for comparison
-    ms_sync = None
-    if world == 1:
-        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e2.record()
-        for _ in range(args.steps):
-            step(dbatch)
-        e3.record()
-        torch.cuda.synchronize()
-        ms_sync = e2.elapsed_time(e3) / args.steps
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        step(dbatch)
+    e3.record()
+    barrier()
+    t_s = torch.tensor([e2.elapsed_time(e3)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_s, op=dist.ReduceOp.MAX)
+    ms_sync = float(t_s.item()) / args.steps
     # per-kernel durations: the same K steps once more with a CUDA-event pair around every launch
     # (the events cost ~8 % of a 0.4 ms step, so they stay out of the pass that produces `value`)
     eng.profile(True)
@@ -348,18 +358,10 @@ def run_ours(args):
 
         for _ in range(2):
             e2e_step()
-        if world == 1:
-            # pipelined like the device-resident run: the copy of batch k+1 overlaps the kernels of batch k
-            run_steps(2, lambda: eng.depth_sorted_packed(packed, wait=False))
-            barrier()
-            t0 = time.perf_counter()
-            run_steps(args.e2e_steps, lambda: eng.depth_sorted_packed(packed, wait=False))
-            barrier()
-            dt = (time.perf_counter() - t0) / args.e2e_steps
-            dt_sync = timed(e2e_step, args.e2e_steps)
-        else:
-            dt = timed(e2e_step, args.e2e_steps)
-            dt_sync = dt
+        # pipelined like the device-resident run: the copy of batch k+1 overlaps the kernels of batch k
+        run_steps(2, lambda: eng.depth_sorted_packed(packed, wait=False))
+        dt = timed(lambda: run_steps(args.e2e_steps, lambda: eng.depth_sorted_packed(packed, wait=False)), 1) / args.e2e_steps
+        dt_sync = timed(e2e_step, args.e2e_steps)
         # for comparison: the plain SoA columns (tid[], u32 offsets, mapq) from pinned memory
         pbatch = ReadBatch(*[t.pin_memory() for t in hbatch])
 
@@ -459,7 +461,8 @@ def run_ours(args):
                    "parallelism": "contig-range shards, 1 all-gather of 64 B/region" if world > 1 else "single GPU",
                    "pipelining": ("steps overlap on the host side only: step k's records are collected from a pinned slot "
                                   "after step k+1 is enqueued (mcov_region_stats_submit/collect); unpipelined_ms_per_step = "
-                                  "one synchronising call per step") if world == 1 else "none"},
+                                  "one synchronising call per step") if world == 1 else
+                                  "as N=1, with the NCCL all-gather of the records inside the pipeline (two DeviceGather slots)"},
         "unpipelined_ms_per_step": ms_sync,
         "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "aligned_bases_per_step": aligned_total,

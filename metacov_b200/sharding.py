@@ -112,26 +112,33 @@ class DeviceGather:
         # contiguous contig ranges => regions listed in contig order are already grouped by rank
         self.monotone = bool(np.all(np.diff(owner) >= 0)) if len(owner) else True
         self.index = None if self.monotone else [np.nonzero(owner == r)[0] for r in range(self.world)]
-        self.local_dev = torch.zeros(self.cap * self.rec, dtype=torch.uint8, device=device)
-        self.out_dev = torch.empty(self.world * self.cap * self.rec, dtype=torch.uint8, device=device)
-        self.out_host = torch.empty(self.world * self.cap * self.rec, dtype=torch.uint8).pin_memory()
+        # two slots: step k+1 can be enqueued (records, all-gather, copy-back) before step k is waited for
+        self.local = [torch.zeros(self.cap * self.rec, dtype=torch.uint8, device=device) for _ in range(2)]
+        self.out = [torch.empty(self.world * self.cap * self.rec, dtype=torch.uint8, device=device) for _ in range(2)]
+        self.host = [torch.empty(self.world * self.cap * self.rec, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self.done = [torch.cuda.Event() for _ in range(2)]
+        self.local_dev, self.out_dev, self.out_host = self.local[0], self.out[0], self.host[0]
         self.merged = np.zeros(self.n_regions, dtype=_capi.REGION_STATS_DTYPE)
 
-    def gather(self, want_host=True):
-        """All-gather the records; with want_host (rank 0: it writes the CSV) copy them to pinned
-        host memory and return them in region order, else only wait for the collective."""
+    def submit(self, slot=0, want_host=True):
+        """Enqueue (current stream) the all-gather of ``local[slot]`` and, with want_host, the copy of
+        all records to pinned memory; returns without waiting."""
         import torch
         import torch.distributed as dist
         if self.world > 1:
-            dist.all_gather_into_tensor(self.out_dev, self.local_dev, group=self.group)
+            dist.all_gather_into_tensor(self.out[slot], self.local[slot], group=self.group)
         else:
-            self.out_dev.copy_(self.local_dev)
+            self.out[slot].copy_(self.local[slot])
+        if want_host:
+            self.host[slot].copy_(self.out[slot], non_blocking=True)
+        self.done[slot].record(torch.cuda.current_stream())
+
+    def collect(self, slot=0, want_host=True):
+        """Wait for ``submit(slot)``; with want_host return the records in region order."""
+        self.done[slot].synchronize()
         if not want_host:
-            torch.cuda.current_stream().synchronize()
             return None
-        self.out_host.copy_(self.out_dev, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        flat = self.out_host.numpy().reshape(self.world, self.cap * self.rec)
+        flat = self.host[slot].numpy().reshape(self.world, self.cap * self.rec)
         if self.monotone and np.all(self.counts == self.cap):
             return flat.reshape(-1).view(_capi.REGION_STATS_DTYPE)       # zero-copy: already in region order
         out_u8 = self.merged.view(np.uint8).reshape(-1, self.rec)
@@ -147,3 +154,9 @@ class DeviceGather:
             else:
                 out_u8[self.index[r]] = part
         return self.merged
+
+    def gather(self, want_host=True):
+        """All-gather the records (slot 0) and wait; with want_host (rank 0: it writes the CSV) return
+        them in region order from pinned host memory."""
+        self.submit(0, want_host)
+        return self.collect(0, want_host)
