@@ -225,8 +225,17 @@ def run_ours(args):
         dg = sharding.DeviceGather(owner, world, dev)
         local_dev, out_dev = dg.local_dev, dg.out_dev
 
+    def depth_dev(batch):
+        """Per-base depth of the rank's contigs from a device-resident batch."""
+        if args.path == "push":                   # any-order formulation: clear + k_expand (red.global) + look-back scan
+            eng.begin()
+            eng.push(batch)
+            eng.finalize()
+        else:                                     # default for sorted input: k_fused_prep + k_fused_tile
+            eng.depth_sorted(batch, wait=False)   # verdict delivered by the next synchronising call
+
     def step(batch):
-        eng.depth_sorted(batch, wait=False)       # verdict delivered by the next synchronising call
+        depth_dev(batch)
         if world == 1:
             return eng.region_stats(reg_tid, reg_start, reg_end)          # one sync per step
         # N>1: records stay on the device, ONE all-gather over NCCL, one D2H of all records
@@ -241,7 +250,7 @@ def run_ours(args):
             for _ in range(n):
                 fn()
             torch.cuda.synchronize(); return (time.perf_counter() - t0) / n * 1e6
-        parts = {"depth_only": tt(lambda: eng.depth_sorted(dbatch, wait=False))}
+        parts = {"depth_only": tt(lambda: depth_dev(dbatch))}
         if world > 1:
             parts["stats_enqueue"] = tt(lambda: eng.region_stats_enqueue(reg_tid, reg_start, reg_end, local_dev))
             parts["all_gather"] = tt(lambda: dist.all_gather_into_tensor(out_dev, local_dev))
@@ -289,7 +298,7 @@ def run_ours(args):
             prev = t
         return eng.region_stats_collect(prev)
 
-    piped = run_steps(3, lambda: eng.depth_sorted(dbatch, wait=False))
+    piped = run_steps(3, lambda: depth_dev(dbatch))
     if world == 1:
         ref_stats = step(dbatch)
         assert piped.tobytes() == ref_stats.tobytes(), "pipelined statistics differ from the synchronous call"
@@ -297,7 +306,7 @@ def run_ours(args):
     l0 = eng.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    run_steps(args.steps, lambda: eng.depth_sorted(dbatch, wait=False))
+    run_steps(args.steps, lambda: depth_dev(dbatch))
     ev1.record()
     barrier()
     clocks = sampler.stop() if sampler else None
@@ -425,7 +434,10 @@ def run_ours(args):
             "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes"], "kernels": kernels,
             "timing": "CUDA-event pair around every launch on the launching stream, K steps run right after the timed region"}
-    whole_bytes = alg_bytes["k_fused_prep"] + alg_bytes["k_fused_tile"] + 4 * L_regions + 64 * g
+    if args.path == "push":
+        whole_bytes = alg_bytes["memset_depth"] + alg_bytes["k_expand"] + alg_bytes["k_scan_inplace"] + 4 * L_regions + 64 * g
+    else:
+        whole_bytes = alg_bytes["k_fused_prep"] + alg_bytes["k_fused_tile"] + 4 * L_regions + 64 * g
     roof["whole_step"] = {"algorithmic_bytes": whole_bytes, "gbs": whole_bytes / ms_step / 1e6,
                           "frac": whole_bytes / ms_step / 1e6 / peak}
 
@@ -454,6 +466,8 @@ def run_ours(args):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": {"workload": "%s x%d ranks: %s" % (args.workload, world, w.describe()), "scale": args.scale,
+                   "path": ("fused sorted path (k_fused_prep, k_fused_tile)" if args.path == "fused" else
+                            "push path (memset, k_expand, k_scan_inplace): the any-order formulation"),
                    "per_gpu": {"reads": n_reads, "contigs": g, "slots": int(slots)},
                    "regions": "one whole-contig region per contig (reference util.py:64-69)",
                    "l2": "inputs+depth (%d MB per GPU) exceed the 126 MB L2; no explicit flush" %
@@ -496,6 +510,9 @@ def _main(real_stdout):
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--path", default="fused", choices=["fused", "push"],
+                    help="depth formulation of the device-resident step: fused sorted path (default, what sorted BAM input takes) "
+                         "or the any-order push path (clear + atomics + decoupled look-back scan)")
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the named workload per GPU")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")
