@@ -265,6 +265,11 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(aligned_t)
     aligned_total = int(aligned_t.item())
+    # sanity of what is being timed (size-independent property, any workload size): no synthetic read is
+    # clipped at a contig end, so the per-contig `sum` records must add up to the aligned bases
+    if rank == 0 or world == 1:
+        got_sum = int(np.asarray(stats["sum"], dtype=np.int64).sum())
+        assert got_sum == aligned_total, "mass conservation violated: sum(records.sum)=%d, aligned bases=%d" % (got_sum, aligned_total)
 
     # ---- timed region: device-resident inputs ---------------------------------------------------
     # NVML is a shared, lock-protected service: only rank 0 samples (its GPU runs the same kernels)
@@ -294,9 +299,9 @@ def run_ours(args):
             depth_call()
             t = eng.region_stats_submit(reg_tid, reg_start, reg_end, slot=i & 1)
             if prev is not None:
-                eng.region_stats_collect(prev)
+                eng.region_stats_collect(prev, copy=False)     # records: a view of the pinned slot
             prev = t
-        return eng.region_stats_collect(prev)
+        return eng.region_stats_collect(prev, copy=False)
 
     piped = run_steps(3, lambda: depth_dev(dbatch))
     if world == 1:

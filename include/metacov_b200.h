@@ -176,6 +176,11 @@ int  mcov_region_stats_submit(mcov_ctx* ctx, int64_t g,
                               const int32_t* tid, const int32_t* start, const int32_t* end,
                               int32_t breadth_n, int slot);
 int  mcov_region_stats_collect(mcov_ctx* ctx, int slot, mcov_region_stats* host_out);
+/* Same, without the copy: *view points at the g records in the slot's pinned
+ * staging buffer (owned by the context, valid until the next submit on that
+ * slot).  The records are copied back on a stream of their own, so the kernels
+ * of the next pass do not queue behind a large copy (500 k regions = 32 MB). */
+int  mcov_region_stats_collect_view(mcov_ctx* ctx, int slot, const mcov_region_stats** view, int64_t* g_out);
 
 /* Asynchronous variant for multi-GPU pipelines: the g records are written to
  * DEVICE memory dev_out on the context's stream and the call returns without
@@ -186,6 +191,24 @@ int  mcov_region_stats_collect(mcov_ctx* ctx, int slot, mcov_region_stats* host_
 int  mcov_region_stats_enqueue(mcov_ctx* ctx, int64_t g,
                                const int32_t* tid, const int32_t* start, const int32_t* end,
                                int32_t breadth_n, mcov_region_stats* dev_out);
+
+/* Regions cut across devices (a contig split between ranks at
+ * position p; the boundary reads are given to both sides and clipped there, see
+ * metacov_b200/sharding.py).  A region that straddles the cut cannot be finished
+ * from 64-byte records -- `med` and `q23` (reference pileup.py:21,24) need the
+ * merged multiset -- so each rank ADDS the exact counting histogram of its part
+ * of every such region to dev_hist[g][MCOV_HIST_BINS] (device memory, zeroed by
+ * the caller; last bin = overflow), the tables are summed across ranks (one
+ * all-reduce) and mcov_hist_stats_enqueue walks the merged histograms into the
+ * same records mcov_region_stats_run produces (flags bit1 set if the overflow
+ * bin is populated).  Both are enqueued on the context's stream;
+ * mcov_region_hist_enqueue returns after its task table has been consumed. */
+#define MCOV_HIST_BINS 8192
+int  mcov_region_hist_enqueue(mcov_ctx* ctx, int64_t g,
+                              const int32_t* tid, const int32_t* start, const int32_t* end,
+                              uint32_t* dev_hist);
+int  mcov_hist_stats_enqueue(mcov_ctx* ctx, int64_t g, const uint32_t* dev_hist,
+                             int32_t breadth_n, mcov_region_stats* dev_out);
 
 /* Fixed-window mean depth (additive feature named by north_star; no
  * reference counterpart): for every contig, ceil(len/window) float64 means,
@@ -218,6 +241,10 @@ typedef struct mcov_kernel_time {
   int64_t launches;
   double  total_ms;   /* CUDA-event time summed over the launches, on the ctx's stream */
 } mcov_kernel_time;
+
+/* Wait for everything enqueued on the context's stream (for callers that mix the *_enqueue entry
+ * points with work on other streams). */
+int  mcov_sync(mcov_ctx* ctx);
 
 /* kernels (and clears) enqueued by this context since it was created */
 int64_t mcov_launch_count(const mcov_ctx* ctx);

@@ -48,6 +48,8 @@ class RegionStats(C.Structure):
                 ("med_hi", C.c_int32), ("reserved", C.c_int32), ("flags", C.c_int32)]
 
 
+HIST_BINS = 8192        # MCOV_HIST_BINS
+
 REGION_STATS_DTYPE = np.dtype([
     ("sum", "<i8"), ("sumsq", "<u8"), ("iq_sum", "<i8"), ("n_ge1", "<i8"), ("n_geN", "<i8"),
     ("min", "<i4"), ("max", "<i4"), ("med_lo", "<i4"), ("med_hi", "<i4"), ("reserved", "<i4"), ("flags", "<i4")])
@@ -101,6 +103,10 @@ SIGNATURES = {
     "mcov_region_stats_run": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i32, _vp]),
     "mcov_region_stats_submit": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i32, C.c_int]),
     "mcov_region_stats_collect": (C.c_int, [_vp, C.c_int, _vp]),
+    "mcov_sync": (C.c_int, [_vp]),
+    "mcov_region_hist_enqueue": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp]),
+    "mcov_hist_stats_enqueue": (C.c_int, [_vp, C.c_int64, _vp, C.c_int32, _vp]),
+    "mcov_region_stats_collect_view": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "mcov_region_stats_enqueue": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i32, _vp]),
     "mcov_window_means": (C.c_int, [_vp, _i32, _vp, _i64]),
     "mcov_copy_depth": (C.c_int, [_vp, _i32, _i32, _i32, _vp]),

@@ -45,7 +45,7 @@ enum PassState { kIdle = 0, kAccumulating = 1, kDepthReady = 2 };
 enum KernelId {
   kKExpand = 0, kKScan, kKFusedPrep, kKTileFirst, kKScanCounts, kKFarScatter, kKFusedTile,
   kKInitStats, kKRegionStats, kKWindowSums, kKIsizeHist, kKGroupCount, kKSortedStats, kKClear, kKRegionStatsSmall, kKCapReplay, kKUnpack, kKKmerHist, kKRegionStatsWarp,
-  kKExpPrep, kKExpEntries, kKExpRegion, kKExpRevsum,
+  kKExpPrep, kKExpEntries, kKExpRegion, kKExpRevsum, kKRegionHist, kKHistFinish,
   kKernelCount
 };
 
@@ -73,6 +73,7 @@ struct mcov_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t d2h_stream = nullptr;   // copy-back of pipelined statistics records (overlaps the next pass)
   cudaEvent_t copied = nullptr;
   std::string err;
 
@@ -104,12 +105,14 @@ struct mcov_ctx {
   mcov::DevBuf d_end_slot, d_start_slot, d_far_list, d_tile_cnt, d_tile_off, d_far_sorted;
 
   // stats scratch
-  mcov::DevBuf d_tasks, d_rlen, d_rchunks, d_rhist, d_pool, d_done, d_out, d_win_slot, d_win_n, d_win_out;
+  mcov::DevBuf d_tasks, d_rlen, d_rchunks, d_rhist, d_pool, d_done, d_out, d_win_slot, d_win_n, d_win_out, d_htasks;
   mcov::PinBuf h_pin;
   // pipelined statistics (mcov_region_stats_submit / collect): two pinned slots
   struct StatSlot {
     mcov::PinBuf buf;              // [g records | PassCounters]
-    cudaEvent_t done = nullptr;
+    mcov::DevBuf d_rec;            // the slot's records on the device (copied back on d2h_stream)
+    cudaEvent_t ready = nullptr;   // records written (main stream)
+    cudaEvent_t done = nullptr;    // records in `buf` (d2h_stream)
     int64_t g = -1;                // -1 = nothing submitted
     bool has_verdict = false;
     int64_t n_reads = 0;

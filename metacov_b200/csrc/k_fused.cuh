@@ -48,6 +48,8 @@ constexpr int kTileShift = MCOV_TILE_SHIFT;
 constexpr int kTile = 1 << kTileShift;    // slots per CTA of the tile kernel (2048: 128-thread CTAs, 8 per SM)
 constexpr uint32_t kNearSpan = kTile;     // spans above this take the bucket path
 constexpr int kFusedThreads = kTile / 16; // 16 slots per thread
+constexpr int kTileVec = 4;               // = four int4 per thread (independent of the push path's scan shape)
+static_assert(kFusedThreads * kTileVec * 4 == kTile, "tile kernel: threads x vectors x 4 slots must cover the tile");
 static_assert(kTileShift >= 9 && kTileShift <= 12, "record format: 12-bit offset, 13-bit span code");
 constexpr int kPrepThreads = 256;
 constexpr int kPrepPer = 4;               // reads per thread
@@ -383,28 +385,169 @@ __device__ __forceinline__ void prep_flush_counters(PassCounters* pc, uint32_t n
   }
 }
 
-// First kernel of the fused path.  4 consecutive reads per thread, 128-bit SoA loads; filter and
-// CIGAR reduction are common, then a warp-uniform FAST PATH takes the overwhelmingly common case --
-// all 128 reads of the warp (and the read before them) lie in one valid contig at non-negative
-// positions -- where the contig's constants live in uniform registers and nothing is 64-bit.  Near
-// reads need no per-tile aggregate (see k_fused_tile), so the only cross-thread work is the tile
-// border detection.  Any other warp iteration takes prep_general.
+// K1 of the push path (any read order): filter + CIGAR reduce + difference-array deltas, see
+// k_expand.cuh.  Shares prep_load_reduce with the fused path (only f.e and f.vec_ok are read).
 __global__ void __launch_bounds__(kPrepThreads, 4)
-k_fused_prep(const __grid_constant__ FusedArgs f) {
+k_expand(const __grid_constant__ FusedArgs f) {
   const ExpandArgs& a = f.e;
   const int lane = threadIdx.x & 31;
-  const uint32_t n_contigs = (uint32_t)a.n_contigs;
   const int64_t n = a.n;
   const int64_t n_groups = (n + kPrepPer - 1) / kPrepPer;
   const int64_t g_round = (n_groups + 31) & ~(int64_t)31;     // whole warps iterate together
   const int64_t g_stride = (int64_t)gridDim.x * kPrepThreads;
+  const int64_t* __restrict__ g_coff = a.contig_off;
+  const int32_t* __restrict__ g_clen = a.contig_len;
+  int32_t* __restrict__ delta = a.delta;
   unsigned long long aligned = 0;
-  uint32_t n_pass = 0, max_span = 0;
-  uint32_t unsorted = 0;
-  // constants of the warp's current contig, reloaded only when the contig changes
-  int32_t w_tid = -1;
-  uint32_t w_len = 0, w_tb = 0, w_bo = 0;
+  uint32_t n_pass = 0, unsorted = 0;
+  int32_t c_tid = -1;                                         // contig constants, reloaded on change
+  int64_t c_len = 0, c_base = 0;
+#pragma unroll 1
+  for (int64_t g = (int64_t)blockIdx.x * kPrepThreads + threadIdx.x; g < g_round; g += g_stride) {
+    const int64_t i0 = g * kPrepPer;
+    int32_t pvT = 0, pvP = 0;
+    const bool has_prev = lane == 0 && i0 > 0 && i0 - 1 < n;
+    if (has_prev) { pvT = a.tid[i0 - 1]; pvP = a.pos[i0 - 1]; }
+    const PrepReads R = prep_load_reduce(f, i0, lane);
+    // sortedness by (tid as unsigned: unplaced reads sort last, pos) -- informational (mcov_pass_info.sorted)
+    {
+      uint32_t pt = __shfl_up_sync(0xffffffffu, (uint32_t)R.T[3], 1);
+      int32_t pp = __shfl_up_sync(0xffffffffu, R.P[3], 1);
+      bool prev_ok = lane > 0 && i0 > 0;
+      if (lane == 0) { pt = (uint32_t)pvT; pp = pvP; prev_ok = has_prev; }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        if (r < R.nv) {
+          const uint32_t u1 = (uint32_t)R.T[r];
+          if (prev_ok && (u1 < pt || (u1 == pt && R.P[r] < pp))) unsorted = 1;
+          pt = u1; pp = R.P[r]; prev_ok = true;
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if ((R.passm >> r) & 1u) {                              // (passing reads have a valid contig)
+        if (R.T[r] != c_tid) { c_tid = R.T[r]; c_len = g_clen[c_tid]; c_base = g_coff[c_tid]; }
+        int64_t s = R.P[r], e = (int64_t)R.P[r] + (int64_t)R.reflen[r];
+        s = s < 0 ? 0 : (s > c_len ? c_len : s);
+        e = e < 0 ? 0 : (e > c_len ? c_len : e);
+        if (e > s) {                                          // reflen == 0 or entirely outside the contig: nothing
+          atomicAdd(delta + c_base + s, 1);
+          atomicAdd(delta + c_base + e, -1);
+          n_pass += 1;
+          aligned += R.reflen[r];
+        }
+      }
+    }
+  }
+  prep_flush_counters(a.pc, n_pass, aligned, unsorted, 0u);
+}
 
+// Per-warp state of a prep kernel: pass counters and the constants of the warp's current contig
+// (reloaded only when the contig changes).
+struct PrepWarp {
+  unsigned long long aligned;
+  uint32_t n_pass, max_span, unsorted;
+  int32_t w_tid;
+  uint32_t w_len, w_tb, w_bo;
+};
+
+// Everything after the loads + filter + CIGAR reduction of one warp iteration (shared by both prep
+// kernels): a warp-uniform FAST PATH takes the overwhelmingly common case -- all 128 reads of the
+// warp (and the read before them, pvT/pvP on lane 0) lie in one valid contig at non-negative
+// positions -- where the contig's constants live in uniform registers and nothing is 64-bit.  Near
+// reads need no per-tile aggregate (see k_fused_tile), so the only cross-thread work is the tile
+// border detection.  Any other warp iteration takes prep_general.
+__device__ __forceinline__ void prep_emit(const FusedArgs& f, const int64_t i0, const PrepReads& R, const int32_t pvT,
+                                          const int32_t pvP, const int lane, PrepWarp& W) {
+  const ExpandArgs& a = f.e;
+  const uint32_t n_contigs = (uint32_t)a.n_contigs;
+  const int64_t n = a.n;
+  const int32_t* T = R.T;
+  const int32_t* P = R.P;
+  const uint32_t* reflen = R.reflen;
+  const unsigned passm = R.passm;
+
+  const int32_t Tw = __shfl_sync(0xffffffffu, T[0], 0);
+  bool simple = R.nv == kPrepPer && T[0] == Tw && T[1] == Tw && T[2] == Tw && T[3] == Tw && (P[0] | P[1] | P[2] | P[3]) >= 0;
+  if (lane == 0) simple = simple && pvT == Tw && pvP >= 0;
+  if (!(__all_sync(0xffffffffu, simple) && (uint32_t)Tw < n_contigs)) {
+    const PrepAcc pa = prep_general(f, i0, R.nv, T[0], T[1], T[2], T[3], P[0], P[1], P[2], P[3], reflen[0], reflen[1],
+                                    reflen[2], reflen[3], passm, lane);
+    W.n_pass += pa.n_pass; W.aligned += pa.al32; W.max_span = max(W.max_span, pa.max_span); W.unsorted |= pa.unsorted;
+    return;
+  }
+  if (Tw != W.w_tid) {                               // warp-uniform
+    W.w_tid = Tw;
+    const int64_t base = a.contig_off[Tw];
+    W.w_len = (uint32_t)a.contig_len[Tw];
+    W.w_tb = (uint32_t)(base >> kTileShift); W.w_bo = (uint32_t)base & (kTile - 1);
+  }
+  const uint32_t w_len = W.w_len, w_tb = W.w_tb, w_bo = W.w_bo;
+  uint32_t q[4], sq[4], rc[4];
+  uint32_t al32 = 0, n_pass = 0, max_span = W.max_span;
+  unsigned farmask = 0;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    q[r] = min((uint32_t)P[r], w_len);
+    const uint32_t e = min((uint32_t)P[r] + reflen[r], w_len);     // P >= 0 and reflen < 2^31: no wrap
+    const uint32_t sp = ((passm >> r) & 1u) ? e - q[r] : 0u;
+    sq[r] = w_bo + q[r];
+    const bool far = sp > kNearSpan;
+    rc[r] = (sq[r] & (kTile - 1)) | ((far ? kRecFar : sp) << kTileShift);
+    n_pass += sp ? 1u : 0u;
+    al32 += sp ? reflen[r] : 0u;
+    farmask |= far ? (1u << r) : 0u;
+    max_span = max(max_span, far ? 0u : sp);
+  }
+  W.aligned += al32; W.n_pass += n_pass; W.max_span = max_span;
+  *reinterpret_cast<uint4*>(f.rec + i0) = make_uint4(rc[0], rc[1], rc[2], rc[3]);
+  // sorted inside the contig <=> clamped positions never decrease
+  uint32_t pq = __shfl_up_sync(0xffffffffu, q[3], 1);
+  if (lane == 0) pq = min((uint32_t)pvP, w_len);
+  W.unsorted |= (q[0] < pq || q[1] < q[0] || q[2] < q[1] || q[3] < q[2]) ? 1u : 0u;
+  // tiles relative to the contig's first tile
+  const uint32_t t3 = sq[3] >> kTileShift;
+  uint32_t ptile = __shfl_up_sync(0xffffffffu, t3, 1);
+  if (lane == 0) ptile = (w_bo + pq) >> kTileShift;
+  const bool is_last = i0 + kPrepPer == n;
+  if (__any_sync(0xffffffffu, t3 > ptile || is_last)) {
+    // a tile border inside the warp's reads: the first read of every tile entered writes its index
+    if (__any_sync(0xffffffffu, t3 - ptile > 4u || is_last)) {       // long gaps / end of batch: warp-cooperative
+      prep_tile_boundaries(f.tile_first, i0, kPrepPer, (int64_t)(w_tb + ptile), w_tb + (sq[0] >> kTileShift),
+                           w_tb + (sq[1] >> kTileShift), w_tb + (sq[2] >> kTileShift), w_tb + t3, is_last, n,
+                           (uint32_t)f.n_tiles, lane);
+    } else if (t3 > ptile) {
+      uint32_t* __restrict__ tf = f.tile_first + w_tb;
+      uint32_t prev = ptile;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const uint32_t tr = sq[r] >> kTileShift;
+        for (uint32_t T2 = prev + 1; T2 <= tr; ++T2) tf[T2] = (uint32_t)(i0 + r);
+        prev = max(prev, tr);
+      }
+    }
+  }
+  if (__any_sync(0xffffffffu, farmask != 0)) {
+    const int64_t base = a.contig_off[Tw];
+    int64_t e64[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) e64[r] = base + min((uint32_t)P[r] + reflen[r], w_len);
+    prep_far(f, w_tb + (sq[0] >> kTileShift), w_tb + (sq[1] >> kTileShift), w_tb + (sq[2] >> kTileShift), w_tb + t3, e64[0],
+             e64[1], e64[2], e64[3], farmask, lane);
+  }
+}
+
+// First kernel of the fused path: 4 consecutive reads per thread, 128-bit SoA loads.
+__global__ void __launch_bounds__(kPrepThreads, 4)
+k_fused_prep(const __grid_constant__ FusedArgs f) {
+  const ExpandArgs& a = f.e;
+  const int lane = threadIdx.x & 31;
+  const int64_t n = a.n;
+  const int64_t n_groups = (n + kPrepPer - 1) / kPrepPer;
+  const int64_t g_round = (n_groups + 31) & ~(int64_t)31;     // whole warps iterate together
+  const int64_t g_stride = (int64_t)gridDim.x * kPrepThreads;
+  PrepWarp W = {0ull, 0u, 0u, 0u, -1, 0u, 0u, 0u};
 #pragma unroll 1
   for (int64_t g = (int64_t)blockIdx.x * kPrepThreads + threadIdx.x; g < g_round; g += g_stride) {
     const int64_t i0 = g * kPrepPer;
@@ -412,81 +555,16 @@ k_fused_prep(const __grid_constant__ FusedArgs f) {
     int32_t pvT = -1, pvP = -1;
     if (lane == 0 && i0 > 0 && i0 - 1 < n) { pvT = a.tid[i0 - 1]; pvP = a.pos[i0 - 1]; }
     const PrepReads R = prep_load_reduce(f, i0, lane);
-    const int32_t* T = R.T;
-    const int32_t* P = R.P;
-    const uint32_t* reflen = R.reflen;
-    const unsigned passm = R.passm;
-
-    const int32_t Tw = __shfl_sync(0xffffffffu, T[0], 0);
-    bool simple = R.nv == kPrepPer && T[0] == Tw && T[1] == Tw && T[2] == Tw && T[3] == Tw && (P[0] | P[1] | P[2] | P[3]) >= 0;
-    if (lane == 0) simple = simple && pvT == Tw && pvP >= 0;
-    if (!(__all_sync(0xffffffffu, simple) && (uint32_t)Tw < n_contigs)) {
-      const PrepAcc pa = prep_general(f, i0, R.nv, T[0], T[1], T[2], T[3], P[0], P[1], P[2], P[3], reflen[0], reflen[1],
-                                      reflen[2], reflen[3], passm, lane);
-      n_pass += pa.n_pass; aligned += pa.al32; max_span = max(max_span, pa.max_span); unsorted |= pa.unsorted;
-      continue;
-    }
-    if (Tw != w_tid) {                               // warp-uniform
-      w_tid = Tw;
-      const int64_t base = a.contig_off[Tw];
-      w_len = (uint32_t)a.contig_len[Tw];
-      w_tb = (uint32_t)(base >> kTileShift); w_bo = (uint32_t)base & (kTile - 1);
-    }
-    uint32_t q[4], sq[4], rc[4];
-    uint32_t al32 = 0;
-    unsigned farmask = 0;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      q[r] = min((uint32_t)P[r], w_len);
-      const uint32_t e = min((uint32_t)P[r] + reflen[r], w_len);     // P >= 0 and reflen < 2^31: no wrap
-      const uint32_t sp = ((passm >> r) & 1u) ? e - q[r] : 0u;
-      sq[r] = w_bo + q[r];
-      const bool far = sp > kNearSpan;
-      rc[r] = (sq[r] & (kTile - 1)) | ((far ? kRecFar : sp) << kTileShift);
-      n_pass += sp ? 1u : 0u;
-      al32 += sp ? reflen[r] : 0u;
-      farmask |= far ? (1u << r) : 0u;
-      max_span = max(max_span, far ? 0u : sp);
-    }
-    aligned += al32;
-    *reinterpret_cast<uint4*>(f.rec + i0) = make_uint4(rc[0], rc[1], rc[2], rc[3]);
-    // sorted inside the contig <=> clamped positions never decrease
-    uint32_t pq = __shfl_up_sync(0xffffffffu, q[3], 1);
-    if (lane == 0) pq = min((uint32_t)pvP, w_len);
-    unsorted |= (q[0] < pq || q[1] < q[0] || q[2] < q[1] || q[3] < q[2]) ? 1u : 0u;
-    // tiles relative to the contig's first tile
-    const uint32_t t3 = sq[3] >> kTileShift;
-    uint32_t ptile = __shfl_up_sync(0xffffffffu, t3, 1);
-    if (lane == 0) ptile = (w_bo + pq) >> kTileShift;
-    const bool is_last = i0 + kPrepPer == n;
-    if (__any_sync(0xffffffffu, t3 > ptile || is_last)) {
-      // a tile border inside the warp's reads: the first read of every tile entered writes its index
-      if (__any_sync(0xffffffffu, t3 - ptile > 4u || is_last)) {       // long gaps / end of batch: warp-cooperative
-        prep_tile_boundaries(f.tile_first, i0, kPrepPer, (int64_t)(w_tb + ptile), w_tb + (sq[0] >> kTileShift),
-                             w_tb + (sq[1] >> kTileShift), w_tb + (sq[2] >> kTileShift), w_tb + t3, is_last, n,
-                             (uint32_t)f.n_tiles, lane);
-      } else if (t3 > ptile) {
-        uint32_t* __restrict__ tf = f.tile_first + w_tb;
-        uint32_t prev = ptile;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const uint32_t tr = sq[r] >> kTileShift;
-          for (uint32_t T = prev + 1; T <= tr; ++T) tf[T] = (uint32_t)(i0 + r);
-          prev = max(prev, tr);
-        }
-      }
-    }
-    if (__any_sync(0xffffffffu, farmask != 0)) {
-      const int64_t base = a.contig_off[Tw];
-      int64_t e64[4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) e64[r] = base + min((uint32_t)P[r] + reflen[r], w_len);
-      prep_far(f, w_tb + (sq[0] >> kTileShift), w_tb + (sq[1] >> kTileShift), w_tb + (sq[2] >> kTileShift), w_tb + t3, e64[0],
-               e64[1], e64[2], e64[3], farmask, lane);
-    }
+    prep_emit(f, i0, R, pvT, pvP, lane, W);
   }
-  prep_flush_counters(a.pc, n_pass, aligned, unsorted, max_span);
+  prep_flush_counters(a.pc, W.n_pass, W.aligned, W.unsorted, W.max_span);
 }
+
+// (A cp.async-staged version of this kernel -- every hot-loop load issued one to two iterations
+// ahead into shared memory, 3+2 buffers, 54 KB per CTA -- was measured on B200 and is SLOWER:
+// 79.3 vs 69.8 us on C2, 689 vs 570 us on C4 x0.1.  The kernel is bound by instruction issue and
+// dependent-instruction latency (about 130 thread instructions per read), not by exposed HBM
+// latency; the extra LDGSTS/LDS/DEPBAR instructions cost more than the overlap gains.  DESIGN.md 5.)
 
 // bucket far ends by tile; tile_cnt holds the INCLUSIVE scan of the per-tile counts.  Because the
 // scan runs over [tile_agg | tile_cnt] as one array and tile_agg sums to zero, tile_cnt's running
@@ -520,18 +598,6 @@ __device__ __forceinline__ TileMeta load_tile_meta(const FusedArgs& f, int64_t t
 #define MCOV_TILE_MIN_CTAS (20480 / kTile)   /* 1280 resident threads per SM at <= 51 registers */
 #endif
 constexpr int kPreOwn = 4;     // own records staged per thread: one aligned 16-byte copy
-
-__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem, bool valid) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(s), "l"(gmem), "r"(valid ? 16 : 0) : "memory");
-}
-__device__ __forceinline__ void cp_async_4(void* smem, const void* gmem, bool valid) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(s), "l"(gmem), "r"(valid ? 4 : 0) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
 // Stage the records of a tile in shared memory with cp.async (no registers are held while the
 // copy is in flight): four own records per thread from the 16-byte aligned index below r0 and one
@@ -637,11 +703,11 @@ __device__ __forceinline__ void tile_body(const FusedArgs& f, const TileCtx& c, 
   // starts[p] is folded into one value per vector, relative to the vector's incoming depth.
   const int4* vs = reinterpret_cast<const int4*>(s_cnt);
   const int4* ve = reinterpret_cast<const int4*>(s_end);
-  int4 v[kScanVec];
-  int run[kScanVec], capv[kScanVec];
+  int4 v[kTileVec];
+  int run[kTileVec], capv[kTileVec];
 #pragma unroll
-  for (int j = 0; j < kScanVec; ++j) {
-    int idx = (warp * kScanVec + j) * 32 + lane;
+  for (int j = 0; j < kTileVec; ++j) {
+    int idx = (warp * kTileVec + j) * 32 + lane;
     int4 st = vs[idx], en;
     if (PACKED) {
       en = make_int4((int)((unsigned)st.x >> 16), (int)((unsigned)st.y >> 16), (int)((unsigned)st.z >> 16), (int)((unsigned)st.w >> 16));
@@ -658,7 +724,7 @@ __device__ __forceinline__ void tile_body(const FusedArgs& f, const TileCtx& c, 
   }
   int acc = 0;
 #pragma unroll
-  for (int j = 0; j < kScanVec; ++j) {
+  for (int j = 0; j < kTileVec; ++j) {
     int x = run[j];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -685,8 +751,8 @@ __device__ __forceinline__ void tile_body(const FusedArgs& f, const TileCtx& c, 
   const int64_t n_vec = (f.n_slots - base) >> 2;
   int cap_t = 0;
 #pragma unroll
-  for (int j = 0; j < kScanVec; ++j) {
-    int idx = (warp * kScanVec + j) * 32 + lane;
+  for (int j = 0; j < kTileVec; ++j) {
+    int idx = (warp * kTileVec + j) * 32 + lane;
     int o = off + run[j];
     cap_t = max(cap_t, o + capv[j]);
     v[j].x += o; v[j].y += o; v[j].z += o; v[j].w += o;

@@ -7,17 +7,32 @@
 // start and one plain scan over the concatenation is the segmented scan.
 //
 // Decoupled look-back (one pass, 4 B read + 4 B write per slot = 8*(L+C)
-// algorithmic bytes).  Tile = 256 threads x 16 slots, warp-striped 128-bit
-// loads/stores; tile ids come from an atomic ticket so a tile's predecessors
-// are always already running.
+// algorithmic bytes).  Tile = 512 threads x 32 slots (64 KB), warp-striped
+// L1-bypassing 128-bit loads/stores, tile id = blockIdx.x.
+//
+// Measured on B200, C2 (50 M slots; profiles/r01_o_scan_sweep.txt, r01_p_scan_variants.txt):
+//   150.5 us  256 thr x 16 slots, atomic ticket for the tile id (first version)
+//   109.7 us  this shape
+//   118.8 us  + look-back by the whole CTA (512 predecessors per round instead of 32)
+//   153.8 us  persistent CTAs, tiles i+1.. staged with cp.async while tile i is scanned (best of 7 shapes)
+// ncu on this shape: 50 % of the stall samples sit at the barrier behind warp 0's look-back and
+// 20 % on the tile's own loads -- a tile lives ~10 us, most of it waiting for its predecessors'
+// aggregates, and neither a wider window nor prefetching shortens that wait.  The fused path
+// (k_fused.cuh) exists because its tiles need no predecessor at all.
 #pragma once
 #include "common.cuh"
 
 namespace mcov {
 
-constexpr int kScanThreads = 256;
-constexpr int kScanVec = 4;                                   // int4 per thread
-constexpr int kScanTile = kScanThreads * kScanVec * 4;        // 4096 slots
+#ifndef MCOV_SCAN_VEC
+#define MCOV_SCAN_VEC 8
+#endif
+#ifndef MCOV_SCAN_THREADS
+#define MCOV_SCAN_THREADS 512
+#endif
+constexpr int kScanThreads = MCOV_SCAN_THREADS;
+constexpr int kScanVec = MCOV_SCAN_VEC;                       // int4 per thread
+constexpr int kScanTile = kScanThreads * kScanVec * 4;        // 16384 slots (64 KB)
 
 // tile status word: [63:62] state, [31:0] value
 constexpr unsigned long long kTileAggregate = 1ull << 62;
@@ -53,12 +68,11 @@ template <bool kMetrics>
 __global__ void __launch_bounds__(kScanThreads)
 k_scan_inplace(int32_t* __restrict__ data, int64_t n_slots, unsigned long long* status,
                PassCounters* pc) {
-  __shared__ int64_t s_tile;
   __shared__ int s_warp[kScanThreads / 32];
   __shared__ int s_prefix;
-  if (threadIdx.x == 0) s_tile = atomicAdd(&pc->ticket, 1u);
-  __syncthreads();
-  const int64_t tile = s_tile;
+  // CTAs are dispatched in index order (CUB's decoupled look-back relies on the same), so a tile's
+  // predecessors are always running or done; an atomic ticket costs a dependent L2 round trip per CTA
+  const int64_t tile = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t base = tile * kScanTile;
   int4* vp = reinterpret_cast<int4*>(data + base);
@@ -69,7 +83,7 @@ k_scan_inplace(int32_t* __restrict__ data, int64_t n_slots, unsigned long long* 
 #pragma unroll
   for (int j = 0; j < kScanVec; ++j) {
     int idx = (warp * kScanVec + j) * 32 + lane;
-    v[j] = (idx < n_vec) ? vp[idx] : make_int4(0, 0, 0, 0);
+    v[j] = (idx < n_vec) ? ld_na_int4(vp + idx) : make_int4(0, 0, 0, 0);
     v[j].y += v[j].x; v[j].z += v[j].y; v[j].w += v[j].z;
     run[j] = v[j].w;
   }
@@ -121,7 +135,7 @@ k_scan_inplace(int32_t* __restrict__ data, int64_t n_slots, unsigned long long* 
     mx = max(mx, max(max(v[j].x, v[j].y), max(v[j].z, v[j].w)));
     // upper bound of the cap metric: depth[p-1] + depth[p] >= depth[p-1] + starts[p]
     pair = max(pair, max(max(prev + v[j].x, v[j].x + v[j].y), max(v[j].y + v[j].z, v[j].z + v[j].w)));
-    if (idx < n_vec) vp[idx] = v[j];
+    if (idx < n_vec) st_stream_int4(vp + idx, v[j]);
   }
   if (!kMetrics) return;
   mx = warp_max(mx);

@@ -441,6 +441,96 @@ k_region_stats_warp(StatArgs a, int64_t task0, int64_t n_tasks, uint32_t* __rest
   }
 }
 
+// ---- regions cut across devices: partial histograms, merged, then finished -------
+// When a contig is split between ranks, a region that straddles the cut cannot be finished from
+// 64-byte records: the median and the interquartile sum need the merged multiset.  Each rank adds
+// the exact counting histogram of ITS part to a [g][kHistBins] table (k_region_hist), the tables are
+// summed across ranks (one all-reduce over NVLink) and k_hist_finish walks the merged histogram --
+// the same hist_walk as the single-device kernels, so the records are identical.
+struct HistTask {
+  int64_t slot;     // first slot of the chunk
+  int32_t n;        // slots in the chunk
+  int32_t region;
+  int32_t pad;      // zeros to add to bin 0 (positions beyond the contig end; first chunk of the region only)
+  int32_t reserved;
+};
+
+__global__ void __launch_bounds__(kStatThreads, 4)
+k_region_hist(const int32_t* __restrict__ depth, const HistTask* __restrict__ tasks, uint32_t* __restrict__ hist_out) {
+  __shared__ __align__(16) uint32_t s_hist[kHistBins];
+  __shared__ int s_rng[2 * (kStatThreads / 32)];
+  const HistTask task = tasks[blockIdx.x];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  {
+    uint4* h4 = reinterpret_cast<uint4*>(s_hist);
+    for (int k = t; k < kHistBins / 4; k += kStatThreads) h4[k] = make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();
+  const int64_t s0 = task.slot, s1 = task.slot + task.n;
+  const int64_t a0 = s0 & ~(int64_t)3;
+  const int64_t nvec = ((s1 - a0) + 3) >> 2;
+  const int4* vp = reinterpret_cast<const int4*>(depth + a0);
+  const int head = (int)(s0 - a0), tail = (int)((a0 + (nvec << 2)) - s1);
+  const int64_t jf0 = head ? 1 : 0, jf1 = nvec - (tail ? 1 : 0);
+  int lo = kHistBins, hi = -1;
+  for (int64_t j = jf0 + t; j < jf1; j += kStatThreads) hist_vec(s_hist, __ldcs(vp + j), lo, hi);
+  if (nvec > 0) {
+    if (nvec == 1) { if (t == 0 && (head || tail)) hist_partial(s_hist, __ldcs(vp), head, 4 - tail, lo, hi); }
+    else {
+      if (t == 0 && head) hist_partial(s_hist, __ldcs(vp), head, 4, lo, hi);
+      if (t == 32 && tail) hist_partial(s_hist, __ldcs(vp + nvec - 1), 0, 4 - tail, lo, hi);
+    }
+  }
+  if (t == 0 && task.pad > 0) { atomicAdd(&s_hist[0], (uint32_t)task.pad); lo = 0; hi = max(hi, 0); }
+  lo = warp_min(lo); hi = warp_max(hi);
+  if (lane == 0) { s_rng[warp] = lo; s_rng[kStatThreads / 32 + warp] = hi; }
+  __syncthreads();
+  lo = kHistBins; hi = -1;
+#pragma unroll
+  for (int k = 0; k < kStatThreads / 32; ++k) { lo = min(lo, s_rng[k]); hi = max(hi, s_rng[kStatThreads / 32 + k]); }
+  uint32_t* gh = hist_out + (int64_t)task.region * kHistBins;
+  for (int b = lo + t; b <= hi; b += kStatThreads) {
+    const uint32_t c = s_hist[b];
+    if (c) atomicAdd(gh + b, c);
+  }
+}
+
+// One CTA per region: statistics record from a complete counting histogram in global memory.
+__global__ void __launch_bounds__(kStatThreads, 4)
+k_hist_finish(const uint32_t* __restrict__ hist, mcov_region_stats* __restrict__ out, int32_t breadth_n) {
+  __shared__ __align__(16) uint32_t s_hist[kHistBins];
+  __shared__ unsigned long long s_u64[6 * (kStatThreads / 32)];
+  __shared__ int s_i32[4 * (kStatThreads / 32)];
+  __shared__ int s_med[2];
+  __shared__ unsigned long long s_n;
+  const int g = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const uint4* src = reinterpret_cast<const uint4*>(hist + (int64_t)g * kHistBins);
+  unsigned long long n = 0;
+  for (int k = t; k < kHistBins / 4; k += kStatThreads) {
+    const uint4 v = src[k];
+    reinterpret_cast<uint4*>(s_hist)[k] = v;
+    n += (unsigned long long)v.x + v.y + v.z + v.w;
+  }
+  n = warp_sum(n);
+  if (lane == 0) s_u64[warp] = n;
+  if (t == 0) { s_med[0] = 0; s_med[1] = 0; }
+  __syncthreads();
+  if (t == 0) {
+    unsigned long long tot = 0;
+    for (int k = 0; k < kStatThreads / 32; ++k) tot += s_u64[k];
+    s_n = tot;
+  }
+  __syncthreads();
+  const long long total = (long long)s_n;
+  __syncthreads();                                    // s_u64 is reused by hist_walk
+  if (total == 0) {                                   // empty region: an all-zero record
+    if (t == 0) { mcov_region_stats r; memset(&r, 0, sizeof(r)); out[g] = r; }
+    return;
+  }
+  WalkOut w = hist_walk<kStatThreads>(s_hist, total, breadth_n, 0, kHistBins - 1, s_u64, s_i32, s_med);
+  if (t == 0) write_stats(out + g, w);
+}
+
 // Fixed-window mean depth: one warp per window.
 __global__ void k_window_sums(const int32_t* __restrict__ depth, const int64_t* __restrict__ win_slot,
                               const int32_t* __restrict__ win_n, int64_t n_win, long long* __restrict__ out) {

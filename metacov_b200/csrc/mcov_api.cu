@@ -243,6 +243,7 @@ int mcov_create(mcov_ctx** out, int device, void* stream) {
     ctx->own_stream = true;
   }
   bool ok = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreateWithFlags(&ctx->copied, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&ctx->stage[0].consumed, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&ctx->stage[1].consumed, cudaEventDisableTiming) == cudaSuccess;
@@ -257,6 +258,7 @@ void mcov_destroy(mcov_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+  if (ctx->d2h_stream) { cudaStreamSynchronize(ctx->d2h_stream); cudaStreamDestroy(ctx->d2h_stream); }
   if (ctx->copied) cudaEventDestroy(ctx->copied);
   for (auto& s : ctx->stage) {
     if (s.consumed) cudaEventDestroy(s.consumed);
@@ -265,10 +267,14 @@ void mcov_destroy(mcov_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->d_len, &ctx->d_off, &ctx->depth_own, &ctx->d_pc, &ctx->d_status, &ctx->d_end_slot,
                     &ctx->d_start_slot, &ctx->d_far_list, &ctx->d_tile_cnt, &ctx->d_tile_off, &ctx->d_far_sorted,
                     &ctx->d_tasks, &ctx->d_rlen, &ctx->d_rchunks, &ctx->d_rhist, &ctx->d_pool, &ctx->d_done,
-                    &ctx->d_out, &ctx->d_win_slot, &ctx->d_win_n, &ctx->d_win_out};
+                    &ctx->d_out, &ctx->d_win_slot, &ctx->d_win_n, &ctx->d_win_out, &ctx->d_htasks};
   for (DevBuf* b : bufs) b->release();
   ctx->h_pin.release();
-  for (auto& sl : ctx->slot) { sl.buf.release(); if (sl.done) cudaEventDestroy(sl.done); }
+  for (auto& sl : ctx->slot) {
+    sl.buf.release(); sl.d_rec.release();
+    if (sl.done) cudaEventDestroy(sl.done);
+    if (sl.ready) cudaEventDestroy(sl.ready);
+  }
   ctx->prof_collect();
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -352,7 +358,14 @@ int mcov_push_reads(mcov_ctx* ctx, int64_t n, const int32_t* tid, const int32_t*
   ReadStage* st = nullptr;
   int rc = stage_reads(ctx, n, tid, pos, flag, mapq, cig_off, cig, mem_kind, a, &st);
   if (rc) return rc;
-  MCOV_LAUNCH(ctx, kKExpand, (k_expand<<<grid_for(n, kExpandThreads, 8), kExpandThreads, 0, ctx->stream>>>(a)));
+  FusedArgs f;
+  std::memset(&f, 0, sizeof(f));
+  f.e = a;
+  {
+    auto al = [](const void* p, uintptr_t m) { return (reinterpret_cast<uintptr_t>(p) & (m - 1)) == 0; };
+    f.vec_ok = (al(a.tid, 16) && al(a.pos, 16) && al(a.cig_off, 16) && al(a.flag, 8) && al(a.mapq, 4)) ? 1 : 0;
+  }
+  MCOV_LAUNCH(ctx, kKExpand, (k_expand<<<grid_for((n + kPrepPer - 1) / kPrepPer, kPrepThreads, 8), kPrepThreads, 0, ctx->stream>>>(f)));
   CU(cudaGetLastError());
   ctx->n_reads_pushed += n;
   return finish_stage(ctx, st);
@@ -365,7 +378,6 @@ int mcov_finalize(mcov_ctx* ctx) {
   int64_t n_tiles = (ctx->n_slots + kScanTile - 1) / kScanTile;
   CU(ctx->d_status.ensure((size_t)n_tiles * 8));
   CU(cudaMemsetAsync(ctx->d_status.p, 0, (size_t)n_tiles * 8, ctx->stream));
-  CU(cudaMemsetAsync(&pc_of(ctx)->ticket, 0, sizeof(unsigned int), ctx->stream));
   MCOV_LAUNCH(ctx, kKScan, (k_scan_inplace<true><<<(unsigned)n_tiles, kScanThreads, 0, ctx->stream>>>(
       ctx->depth, ctx->n_slots, ctx->d_status.as<unsigned long long>(), pc_of(ctx))));
   CU(cudaGetLastError());
@@ -465,7 +477,6 @@ int mcov_depth_sorted_packed(mcov_ctx* ctx, int64_t n, const int64_t* contig_rea
     MCOV_LAUNCH(ctx, kKScanCounts, (k_scan_inplace<false><<<(unsigned)tiles, kScanThreads, 0, s>>>(
         st.cig_off.as<int32_t>(), off_len, ctx->d_tile_cnt.as<unsigned long long>(), pc_of(ctx))));
     CU(cudaGetLastError());
-    CU(cudaMemsetAsync(&pc_of(ctx)->ticket, 0, sizeof(unsigned int), s));      // the fused pass scans again
   }
   ExpandArgs a;
   std::memset(&a, 0, sizeof(a));
@@ -511,7 +522,14 @@ static const char* kKernelNames[kKernelCount] = {
     "k_expand", "k_scan_inplace", "k_fused_prep", "k_tile_first", "k_scan_counts", "k_far_scatter", "k_fused_tile",
     "k_init_region_stats", "k_region_stats", "k_window_sums", "k_isize_hist", "k_group_count", "k_sorted_stats",
     "memset_depth", "k_region_stats_small", "k_cap_replay", "k_unpack_reads", "k_kmer_hist", "k_region_stats_warp",
-    "k_exp_prep", "k_exp_entries", "k_exp_region", "k_exp_revsum"};
+    "k_exp_prep", "k_exp_entries", "k_exp_region", "k_exp_revsum", "k_region_hist", "k_hist_finish"};
+
+int mcov_sync(mcov_ctx* ctx) {
+  if (!ctx) return MCOV_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MCOV_OK;
+}
 
 int64_t mcov_launch_count(const mcov_ctx* ctx) { return ctx ? ctx->n_launches : 0; }
 
@@ -748,18 +766,24 @@ int mcov_region_stats_submit(mcov_ctx* ctx, int64_t g, const int32_t* tid, const
   const size_t out_bytes = (size_t)g * sizeof(mcov_region_stats);
   CU(sl.buf.ensure(out_bytes + sizeof(PassCounters)));
   if (!sl.done) CU(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+  if (!sl.ready) CU(cudaEventCreateWithFlags(&sl.ready, cudaEventDisableTiming));
   if (g > 0) {
-    CU(ctx->d_out.ensure(out_bytes));
-    int rc = stats_launch(ctx, g, tid, start, end, breadth_n, ctx->d_out.as<mcov_region_stats>());
+    CU(sl.d_rec.ensure(out_bytes));
+    int rc = stats_launch(ctx, g, tid, start, end, breadth_n, sl.d_rec.as<mcov_region_stats>());
     if (rc) return rc;
-    CU(cudaMemcpyAsync(sl.buf.p, ctx->d_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
   }
   sl.has_verdict = ctx->verdict_pending;
   if (sl.has_verdict) {
+    // (on the main stream: the next pass clears the counters there)
     CU(cudaMemcpyAsync(sl.buf.as<char>() + out_bytes, ctx->d_pc.p, sizeof(PassCounters), cudaMemcpyDeviceToHost, s));
     ctx->verdict_pending = false;                  // the verdict of this pass now travels with the slot
   }
-  CU(cudaEventRecord(sl.done, s));
+  // The records travel on their own stream, so the kernels of the next pass do not queue behind the
+  // copy (32 MB for the 500 k regions of config C3).
+  CU(cudaEventRecord(sl.ready, s));
+  CU(cudaStreamWaitEvent(ctx->d2h_stream, sl.ready, 0));
+  if (g > 0) CU(cudaMemcpyAsync(sl.buf.p, sl.d_rec.p, out_bytes, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+  CU(cudaEventRecord(sl.done, ctx->d2h_stream));
   sl.g = g;
   sl.n_reads = ctx->n_reads_pushed;
   sl.len0.clear();
@@ -767,12 +791,12 @@ int mcov_region_stats_submit(mcov_ctx* ctx, int64_t g, const int32_t* tid, const
   return MCOV_OK;
 }
 
-int mcov_region_stats_collect(mcov_ctx* ctx, int slot, mcov_region_stats* host_out) {
-  if (!ctx) return MCOV_ERR_ARG;
+// Wait for a submitted slot and vet it; on success *view points at its g records in the slot's
+// pinned buffer (valid until the next submit on that slot).
+static int stats_collect_common(mcov_ctx* ctx, int slot, mcov_region_stats** view, int64_t* g_out) {
   if (slot < 0 || slot > 1) return fail(ctx, MCOV_ERR_ARG, "mcov_region_stats_collect: bad slot");
   mcov_ctx::StatSlot& sl = ctx->slot[slot];
   if (sl.g < 0) return fail(ctx, MCOV_ERR_STATE, "mcov_region_stats_collect: nothing submitted in this slot");
-  if (sl.g > 0 && !host_out) return fail(ctx, MCOV_ERR_ARG, "mcov_region_stats_collect: null output");
   CU(cudaSetDevice(ctx->device));
   CU(cudaEventSynchronize(sl.done));
   const int64_t g = sl.g;
@@ -787,11 +811,34 @@ int mcov_region_stats_collect(mcov_ctx* ctx, int slot, mcov_region_stats* host_o
     if (ctx->filt.max_depth > 0 && h.cap_metric > ctx->filt.max_depth)
       return fail(ctx, MCOV_ERR_STATE, "mcov_region_stats_collect: that pass needs the max_depth replay; rerun it through mcov_depth_sorted + mcov_region_stats_run");
   }
-  if (g > 0) std::memcpy(host_out, sl.buf.p, out_bytes);
-  for (int32_t i : sl.len0) std::memset(&host_out[i], 0, sizeof(mcov_region_stats));
+  mcov_region_stats* rec = sl.buf.as<mcov_region_stats>();
+  for (int32_t i : sl.len0) std::memset(&rec[i], 0, sizeof(mcov_region_stats));
   for (int64_t i = 0; i < g; ++i)
-    if (host_out[i].flags & kStatOverflow)
+    if (rec[i].flags & kStatOverflow)
       return fail(ctx, MCOV_ERR_STATE, "mcov_region_stats_collect: a region's depth left the counting histogram; rerun it through mcov_region_stats_run");
+  *view = rec;
+  *g_out = g;
+  return MCOV_OK;
+}
+
+int mcov_region_stats_collect(mcov_ctx* ctx, int slot, mcov_region_stats* host_out) {
+  if (!ctx) return MCOV_ERR_ARG;
+  if (slot >= 0 && slot <= 1 && ctx->slot[slot].g > 0 && !host_out) return fail(ctx, MCOV_ERR_ARG, "mcov_region_stats_collect: null output");
+  mcov_region_stats* rec = nullptr;
+  int64_t g = 0;
+  int rc = stats_collect_common(ctx, slot, &rec, &g);
+  if (rc) return rc;
+  if (g > 0) std::memcpy(host_out, rec, (size_t)g * sizeof(mcov_region_stats));
+  return MCOV_OK;
+}
+
+int mcov_region_stats_collect_view(mcov_ctx* ctx, int slot, const mcov_region_stats** view, int64_t* g_out) {
+  if (!ctx) return MCOV_ERR_ARG;
+  if (!view || !g_out) return fail(ctx, MCOV_ERR_ARG, "mcov_region_stats_collect_view: null output");
+  mcov_region_stats* rec = nullptr;
+  int rc = stats_collect_common(ctx, slot, &rec, g_out);
+  if (rc) return rc;
+  *view = rec;
   return MCOV_OK;
 }
 
@@ -804,6 +851,54 @@ int mcov_region_stats_enqueue(mcov_ctx* ctx, int64_t g, const int32_t* tid, cons
   if (g == 0) return MCOV_OK;
   CU(cudaSetDevice(ctx->device));
   return stats_launch(ctx, g, tid, start, end, breadth_n, dev_out);
+}
+
+int mcov_region_hist_enqueue(mcov_ctx* ctx, int64_t g, const int32_t* tid, const int32_t* start, const int32_t* end,
+                             uint32_t* dev_hist) {
+  if (!ctx) return MCOV_ERR_ARG;
+  if (ctx->state != kDepthReady) return fail(ctx, MCOV_ERR_STATE, "mcov_region_hist_enqueue: depth not ready");
+  if (g < 0 || (g > 0 && (!tid || !start || !end || !dev_hist))) return fail(ctx, MCOV_ERR_ARG, "mcov_region_hist_enqueue: bad arguments");
+  if (g > INT32_MAX) return fail(ctx, MCOV_ERR_RANGE, "mcov_region_hist_enqueue: more than 2^31-1 regions");
+  if (g == 0) return MCOV_OK;
+  CU(cudaSetDevice(ctx->device));
+  constexpr int64_t kChunk = 65536;
+  std::vector<HistTask> tasks;
+  for (int64_t i = 0; i < g; ++i) {
+    if (tid[i] < 0 || tid[i] >= ctx->n_contigs || start[i] < 0 || end[i] < start[i])
+      return fail(ctx, MCOV_ERR_ARG, "mcov_region_hist_enqueue: need 0 <= start <= end and a valid tid");
+    const int64_t len = ctx->len[tid[i]];
+    const int64_t cs = std::min<int64_t>(start[i], len), ce = std::min<int64_t>(end[i], len);
+    const int64_t n = ce - cs;
+    int32_t pad = (int32_t)((int64_t)end[i] - start[i] - n);       // beyond the contig end: depth 0 (pileup.py:10-11)
+    const int64_t nch = std::max<int64_t>((n + kChunk - 1) / kChunk, pad > 0 ? 1 : 0);
+    for (int64_t k = 0; k < nch; ++k) {
+      HistTask t;
+      t.slot = ctx->off[tid[i]] + cs + k * kChunk;
+      t.n = (int32_t)std::max<int64_t>(0, std::min<int64_t>(kChunk, n - k * kChunk));
+      t.region = (int32_t)i; t.pad = k == 0 ? pad : 0; t.reserved = 0;
+      tasks.push_back(t);
+    }
+  }
+  if (tasks.empty()) return MCOV_OK;
+  cudaStream_t s = ctx->stream;
+  CU(ctx->d_htasks.ensure(tasks.size() * sizeof(HistTask)));
+  CU(cudaMemcpyAsync(ctx->d_htasks.p, tasks.data(), tasks.size() * sizeof(HistTask), cudaMemcpyHostToDevice, s));
+  MCOV_LAUNCH(ctx, kKRegionHist, (k_region_hist<<<(unsigned)tasks.size(), kStatThreads, 0, s>>>(
+      ctx->depth, ctx->d_htasks.as<HistTask>(), dev_hist)));
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(s));                    // `tasks` goes out of scope (pageable source)
+  return MCOV_OK;
+}
+
+int mcov_hist_stats_enqueue(mcov_ctx* ctx, int64_t g, const uint32_t* dev_hist, int32_t breadth_n, mcov_region_stats* dev_out) {
+  if (!ctx) return MCOV_ERR_ARG;
+  if (g < 0 || (g > 0 && (!dev_hist || !dev_out))) return fail(ctx, MCOV_ERR_ARG, "mcov_hist_stats_enqueue: bad arguments");
+  if (g > INT32_MAX) return fail(ctx, MCOV_ERR_RANGE, "mcov_hist_stats_enqueue: more than 2^31-1 regions");
+  if (g == 0) return MCOV_OK;
+  CU(cudaSetDevice(ctx->device));
+  MCOV_LAUNCH(ctx, kKHistFinish, (k_hist_finish<<<(unsigned)g, kStatThreads, 0, ctx->stream>>>(dev_hist, dev_out, breadth_n)));
+  CU(cudaGetLastError());
+  return MCOV_OK;
 }
 
 int mcov_window_means(mcov_ctx* ctx, int32_t window, double* host_out, int64_t n_out) {

@@ -175,6 +175,10 @@ class CoverageEngine:
     def depth_ptr(self):
         return lib.mcov_depth_ptr(self._ctx)
 
+    def sync(self):
+        """Wait for everything enqueued on the engine's stream."""
+        self._check(lib.mcov_sync(self._ctx))
+
     # -- accounting ---------------------------------------------------------
     def launch_count(self):
         return lib.mcov_launch_count(self._ctx)
@@ -226,11 +230,21 @@ class CoverageEngine:
                                                  int(breadth_n), int(slot)))
         return (int(slot), len(tid))
 
-    def region_stats_collect(self, ticket):
+    def region_stats_collect(self, ticket, copy=True):
+        """Records of a submitted slot.  copy=False returns a zero-copy view of the engine's pinned
+        staging slot (valid until the next submit on that slot): what a pipeline with hundreds of
+        thousands of regions wants."""
         slot, g = ticket
-        out = np.zeros(g, dtype=_capi.REGION_STATS_DTYPE)
-        self._check(lib.mcov_region_stats_collect(self._ctx, slot, _capi.ptr(out)))
-        return out
+        if copy:
+            out = np.zeros(g, dtype=_capi.REGION_STATS_DTYPE)
+            self._check(lib.mcov_region_stats_collect(self._ctx, slot, _capi.ptr(out)))
+            return out
+        view, n = C.c_void_p(), C.c_int64()
+        self._check(lib.mcov_region_stats_collect_view(self._ctx, slot, C.byref(view), C.byref(n)))
+        if n.value == 0:
+            return np.zeros(0, dtype=_capi.REGION_STATS_DTYPE)
+        raw = (C.c_uint8 * (n.value * 64)).from_address(view.value)
+        return np.frombuffer(raw, dtype=_capi.REGION_STATS_DTYPE)
 
     def region_stats_enqueue(self, tid, start, end, out, breadth_n=1):
         """Asynchronous: write len(tid) records into the CUDA uint8 tensor ``out`` (>= 64 bytes per
@@ -242,6 +256,25 @@ class CoverageEngine:
             raise ValueError("output tensor too small")
         self._check(lib.mcov_region_stats_enqueue(self._ctx, len(tid), _capi.ptr(tid), _capi.ptr(start),
                                                   _capi.ptr(end), int(breadth_n), out.data_ptr()))
+
+    def region_hist_enqueue(self, tid, start, end, hist):
+        """Regions cut across devices: ADD the exact counting histogram of this engine's part of each
+        region to ``hist`` (CUDA int32/uint32 tensor [g, 8192], zeroed by the caller); see
+        mcov_region_hist_enqueue and sharding.ShardedCoverage."""
+        tid = np.ascontiguousarray(tid, dtype=np.int32)
+        start = np.ascontiguousarray(start, dtype=np.int32)
+        end = np.ascontiguousarray(end, dtype=np.int32)
+        if hist.numel() < _capi.HIST_BINS * len(tid) or hist.element_size() != 4 or not hist.is_contiguous():
+            raise ValueError("hist must be a contiguous 4-byte tensor of g x %d bins" % _capi.HIST_BINS)
+        self._check(lib.mcov_region_hist_enqueue(self._ctx, len(tid), _capi.ptr(tid), _capi.ptr(start), _capi.ptr(end),
+                                                 hist.data_ptr()))
+
+    def hist_stats_enqueue(self, hist, g, out, breadth_n=1):
+        """Statistics records of g regions from complete (merged) counting histograms -> CUDA uint8
+        tensor ``out`` (>= 64 bytes per region); no synchronisation."""
+        if out.numel() * out.element_size() < 64 * g:
+            raise ValueError("output tensor too small")
+        self._check(lib.mcov_hist_stats_enqueue(self._ctx, int(g), hist.data_ptr(), int(breadth_n), out.data_ptr()))
 
     def experimental_stats(self, soa, name_hash, kmer_code, k_len, kc_val, kc_has, r_start, r_end, r_lb, r_ub):
         """One ``mcov_experimental_run`` call -> EXP_STATS_DTYPE records."""
