@@ -117,21 +117,29 @@ class DeviceGather:
         self.out = [torch.empty(self.world * self.cap * self.rec, dtype=torch.uint8, device=device) for _ in range(2)]
         self.host = [torch.empty(self.world * self.cap * self.rec, dtype=torch.uint8).pin_memory() for _ in range(2)]
         self.done = [torch.cuda.Event() for _ in range(2)]
+        self.ready = [torch.cuda.Event() for _ in range(2)]
+        # the collective and the copy-back run on a stream of their own: the next pass's kernels (enqueued on
+        # the caller's stream right after submit) overlap the all-gather instead of queueing behind it
+        self.side = torch.cuda.Stream(device=device)
         self.local_dev, self.out_dev, self.out_host = self.local[0], self.out[0], self.host[0]
         self.merged = np.zeros(self.n_regions, dtype=_capi.REGION_STATS_DTYPE)
 
     def submit(self, slot=0, want_host=True):
-        """Enqueue (current stream) the all-gather of ``local[slot]`` and, with want_host, the copy of
-        all records to pinned memory; returns without waiting."""
+        """Enqueue the all-gather of ``local[slot]`` (written on the current stream) and, with want_host,
+        the copy of all records to pinned memory -- both on the gather's side stream; returns without
+        waiting.  ``local[slot]`` may be rewritten once ``collect(slot)`` has returned."""
         import torch
         import torch.distributed as dist
-        if self.world > 1:
-            dist.all_gather_into_tensor(self.out[slot], self.local[slot], group=self.group)
-        else:
-            self.out[slot].copy_(self.local[slot])
-        if want_host:
-            self.host[slot].copy_(self.out[slot], non_blocking=True)
-        self.done[slot].record(torch.cuda.current_stream())
+        self.ready[slot].record(torch.cuda.current_stream())
+        self.side.wait_event(self.ready[slot])
+        with torch.cuda.stream(self.side):
+            if self.world > 1:
+                dist.all_gather_into_tensor(self.out[slot], self.local[slot], group=self.group)
+            else:
+                self.out[slot].copy_(self.local[slot])
+            if want_host:
+                self.host[slot].copy_(self.out[slot], non_blocking=True)
+            self.done[slot].record(self.side)
 
     def collect(self, slot=0, want_host=True):
         """Wait for ``submit(slot)``; with want_host return the records in region order."""
