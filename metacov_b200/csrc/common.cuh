@@ -94,6 +94,14 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization
+// attribute may start while its predecessor in the stream drains; pdl_wait() blocks until the predecessor
+// has completed and its writes are visible (a no-op for a normal launch), pdl_launch_dependents() lets the
+// successor's CTAs take free slots from now on.  Removes the drain/launch/ramp gap between the short
+// kernels of one step.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll

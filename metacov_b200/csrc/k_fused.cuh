@@ -541,6 +541,7 @@ __device__ __forceinline__ void prep_emit(const FusedArgs& f, const int64_t i0, 
 // First kernel of the fused path: 4 consecutive reads per thread, 128-bit SoA loads.
 __global__ void __launch_bounds__(kPrepThreads, 4)
 k_fused_prep(const __grid_constant__ FusedArgs f) {
+  pdl_launch_dependents();                                    // k_scan_counts may take free slots as this grid drains
   const ExpandArgs& a = f.e;
   const int lane = threadIdx.x & 31;
   const int64_t n = a.n;
@@ -570,6 +571,8 @@ k_fused_prep(const __grid_constant__ FusedArgs f) {
 // scan runs over [tile_agg | tile_cnt] as one array and tile_agg sums to zero, tile_cnt's running
 // sum starts from zero.
 __global__ void k_far_scatter(FusedArgs f) {
+  pdl_wait();
+  pdl_launch_dependents();
   uint32_t n_far = min(f.e.pc->n_far, f.far_cap);
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_far; k += gridDim.x * blockDim.x) {
     int64_t e = f.far_end[k];
@@ -780,6 +783,14 @@ k_fused_tile(const __grid_constant__ FusedArgs f) {
   PassCounters* pc = f.e.pc;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t stride = gridDim.x;
+  {                                                     // (before the dependency wait: touches nothing global)
+    int4* z0 = reinterpret_cast<int4*>(s_cnt);
+    int4* z1 = reinterpret_cast<int4*>(s_end);
+    for (int k = threadIdx.x; k < kTile / 4; k += kFusedThreads) { z0[k] = make_int4(0, 0, 0, 0); z1[k] = make_int4(0, 0, 0, 0); }
+    if (threadIdx.x < 2) s_open[threadIdx.x] = 0;
+  }
+  pdl_wait();                                           // records, tile_first and the far tables are complete
+  pdl_launch_dependents();
   TileCtx c;
   c.reach = pc->max_span;                               // written by k_fused_prep
   c.has_far = pc->n_far != 0;                           // else the far tables are all zero and are not read
@@ -789,12 +800,6 @@ k_fused_tile(const __grid_constant__ FusedArgs f) {
   TileMeta m_next = load_tile_meta(f, c.tile + stride);
   stage_recs(f, c.m, s_own[0], s_back[0]);
   int mx = 0, cap = 0;
-  {
-    int4* z0 = reinterpret_cast<int4*>(s_cnt);
-    int4* z1 = reinterpret_cast<int4*>(s_end);
-    for (int k = threadIdx.x; k < kTile / 4; k += kFusedThreads) { z0[k] = make_int4(0, 0, 0, 0); z1[k] = make_int4(0, 0, 0, 0); }
-    if (threadIdx.x < 2) s_open[threadIdx.x] = 0;
-  }
   __syncthreads();
 
 #pragma unroll 1

@@ -73,6 +73,8 @@ k_scan_inplace(int32_t* __restrict__ data, int64_t n_slots, unsigned long long* 
   // CTAs are dispatched in index order (CUB's decoupled look-back relies on the same), so a tile's
   // predecessors are always running or done; an atomic ticket costs a dependent L2 round trip per CTA
   const int64_t tile = blockIdx.x;
+  pdl_wait();
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t base = tile * kScanTile;
   int4* vp = reinterpret_cast<int4*>(data + base);

@@ -184,7 +184,7 @@ k_region_stats(StatArgs a) {
   __shared__ int s_med[2];
   __shared__ int s_last;
 
-  const StatTask task = a.tasks[blockIdx.x];
+  const StatTask task = a.tasks[blockIdx.x];            // (the plan is older than the previous kernel)
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int g = task.region;
   const int n_chunks = a.region_chunks[g];
@@ -194,6 +194,7 @@ k_region_stats(StatArgs a) {
     uint4* h4 = reinterpret_cast<uint4*>(s_hist);
     for (int k = t; k < kHistBins / 4; k += kStatThreads) h4[k] = make_uint4(0, 0, 0, 0);
   }
+  pdl_wait();                                           // the depth (k_fused_tile / k_scan_inplace) is complete
   __syncthreads();
 
   // ---- stream the chunk: aligned int4 window covering [slot, slot+n) ----
