@@ -27,10 +27,10 @@ struct PassCounters {
   int cap_metric;
   int unsorted;          // set to 1 if any adjacent pair of reads is out of (tid,pos) order
   unsigned int ticket;   // dynamic tile id for the scan kernel
-  unsigned int ticket2;  // dynamic tile id for the fused tile kernel
+  unsigned int ticket2;  // dynamic tile tickets of the fused tile kernel (beyond the 3 static rounds)
   unsigned int max_span; // max clipped span of a near read (fused path)
   unsigned int n_far;    // reads whose span exceeds the near window (fused path)
-  unsigned int pad;
+  unsigned int n_heavy;  // tiles holding >= heavy_min reads (fused path: scheduled first)
 };
 
 // pysam __advance_samtools predicate + bam_plp_push's own UNMAP drop

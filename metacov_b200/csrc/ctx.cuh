@@ -105,7 +105,7 @@ struct mcov_ctx {
   mcov::DevBuf d_end_slot, d_start_slot, d_far_list, d_tile_cnt, d_tile_off, d_far_sorted;
 
   // stats scratch
-  mcov::DevBuf d_tasks, d_rlen, d_rchunks, d_rhist, d_pool, d_done, d_out, d_win_slot, d_win_n, d_win_out, d_htasks;
+  mcov::DevBuf d_tasks, d_rlen, d_rchunks, d_rhist, d_pool, d_done, d_out, d_win_slot, d_win_n, d_win_out, d_htasks, d_tile_heavy;
   mcov::PinBuf h_pin;
   // pipelined statistics (mcov_region_stats_submit / collect): two pinned slots
   struct StatSlot {

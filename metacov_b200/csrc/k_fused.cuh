@@ -69,6 +69,8 @@ struct FusedArgs {
   uint32_t* tile_first;       // [n_tiles+1] (a fused batch holds < 2^32 reads)
   int32_t* depth;
   int32_t* tile_cap;          // [n_tiles] max of depth[p-1]+starts[p] in the tile, written only when > max_depth
+  uint32_t* tile_heavy;       // [n_tiles] ids of the tiles with >= heavy_min reads (k_far_scatter; pc->n_heavy of them)
+  uint32_t heavy_min;
   int32_t max_depth;          // htslib maxcnt (<= 0: cap disabled)
   int vec_ok;                 // SoA base pointers aligned for 128-bit loads
 };
@@ -573,6 +575,11 @@ k_fused_prep(const __grid_constant__ FusedArgs f) {
 __global__ void k_far_scatter(FusedArgs f) {
   pdl_wait();
   pdl_launch_dependents();
+  // tiles that hold very many reads (skewed abundance: a 4000x contig puts ~55 k reads into one tile,
+  // 100x the average of config C3) are listed here so that the tile kernel can start with them
+  for (int64_t T = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; T < f.n_tiles; T += (int64_t)gridDim.x * blockDim.x) {
+    if (f.tile_first[T + 1] - f.tile_first[T] >= f.heavy_min) f.tile_heavy[atomicAdd(&f.e.pc->n_heavy, 1u)] = (uint32_t)T;
+  }
   uint32_t n_far = min(f.e.pc->n_far, f.far_cap);
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_far; k += gridDim.x * blockDim.x) {
     int64_t e = f.far_end[k];
@@ -782,7 +789,6 @@ k_fused_tile(const __grid_constant__ FusedArgs f) {
   __shared__ int s_open[2];                             // near reads open at the tile border (double-buffered)
   PassCounters* pc = f.e.pc;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t stride = gridDim.x;
   {                                                     // (before the dependency wait: touches nothing global)
     int4* z0 = reinterpret_cast<int4*>(s_cnt);
     int4* z1 = reinterpret_cast<int4*>(s_end);
@@ -791,30 +797,67 @@ k_fused_tile(const __grid_constant__ FusedArgs f) {
   }
   pdl_wait();                                           // records, tile_first and the far tables are complete
   pdl_launch_dependents();
+  // Tile order.  Work per tile is proportional to the reads in it, and skewed abundance makes that
+  // vary 100-fold, so tiles are handed out through TICKETS instead of a fixed stride: tickets
+  // [0, n_heavy) are the heavy tiles listed by k_far_scatter (largest jobs first), tickets
+  // [n_heavy, n_heavy + n_tiles) all tiles in position order (heavy ones are skipped there).  A CTA's
+  // first four tickets are b, b+G, b+2G, b+3G; after that one atomicAdd per tile, issued four tiles ahead
+  // so that the software pipeline below (records of the next tile, metadata of the one after) never
+  // waits for it.  The depth does not depend on the order: every tile is self-contained.
+  __shared__ unsigned s_tk[2];
+  const uint32_t n_heavy = pc->n_heavy;
+  auto resolve = [&](unsigned tk, TileMeta& m) -> int64_t {   // ticket -> tile id; -1: nothing to do; n_tiles: past the end
+    m.r0 = m.r1 = m.jmin = 0;
+    int64_t T;
+    if (tk < n_heavy) {
+      T = f.tile_heavy[tk];
+    } else {
+      T = (int64_t)(tk - n_heavy);
+      if (T >= f.n_tiles) return f.n_tiles;
+    }
+    m = load_tile_meta(f, T);
+    if (tk >= n_heavy && n_heavy != 0 && m.r1 - m.r0 >= f.heavy_min) { m.r0 = m.r1 = m.jmin = 0; return -1; }
+    return T;
+  };
+  const unsigned G = gridDim.x;
   TileCtx c;
   c.reach = pc->max_span;                               // written by k_fused_prep
   c.has_far = pc->n_far != 0;                           // else the far tables are all zero and are not read
-  c.tile = blockIdx.x;
   c.par = 0;
-  c.m = load_tile_meta(f, c.tile);
-  TileMeta m_next = load_tile_meta(f, c.tile + stride);
+  c.tile = resolve(blockIdx.x, c.m);
+  TileMeta m_next;
+  int64_t t_next = resolve(blockIdx.x + G, m_next);
+  unsigned tk_nn = blockIdx.x + 2u * G;                 // ticket of the tile after next
+  unsigned tk_hold = blockIdx.x + 3u * G;               // thread 0: the ticket after that (drawn one iteration ago)
   stage_recs(f, c.m, s_own[0], s_back[0]);
   int mx = 0, cap = 0;
   __syncthreads();
 
 #pragma unroll 1
-  for (; c.tile < f.n_tiles; c.tile += stride, c.par ^= 1) {
+  for (unsigned it = 0; c.tile < f.n_tiles; ++it, c.par ^= 1) {
+    unsigned tk_new = 0;
+    if (threadIdx.x == 0) tk_new = 4u * G + atomicAdd(&pc->ticket2, 1u);   // not looked at before the end of this iteration
     // the following tiles first: these copies / loads stay in flight during the whole body
-    stage_recs(f, m_next, s_own[c.par ^ 1], s_back[c.par ^ 1]);   // empty ranges when tile+stride is past the end
-    const TileMeta m_nn = load_tile_meta(f, c.tile + 2 * stride);
+    stage_recs(f, m_next, s_own[c.par ^ 1], s_back[c.par ^ 1]);   // empty ranges for "nothing to do" / past the end
+    TileMeta m_nn;
+    const int64_t t_nn = resolve(tk_nn, m_nn);
     cp_async_wait<1>();                                           // this tile's records have landed
-    // every +1 of the tile comes from an own record, a walk-back candidate or a far end: fewer
-    // than 65 536 of them keep both halves of the packed counters from overflowing
-    uint32_t touching = c.m.r1 - c.m.jmin;
-    if (c.has_far) touching += f.tile_cnt[c.tile] - (c.tile > 0 ? f.tile_cnt[c.tile - 1] : 0u);
-    if (touching < 65536u) tile_body<true>(f, c, s_cnt, s_end, s_own[c.par], s_back[c.par], s_warp, s_open, mx, cap);
-    else tile_body<false>(f, c, s_cnt, s_end, s_own[c.par], s_back[c.par], s_warp, s_open, mx, cap);
-    c.m = m_next; m_next = m_nn;
+    if (c.tile >= 0) {
+      // every +1 of the tile comes from an own record, a walk-back candidate or a far end: fewer
+      // than 65 536 of them keep both halves of the packed counters from overflowing
+      uint32_t touching = c.m.r1 - c.m.jmin;
+      if (c.has_far) touching += f.tile_cnt[c.tile] - (c.tile > 0 ? f.tile_cnt[c.tile - 1] : 0u);
+      if (threadIdx.x == 0) s_tk[it & 1] = tk_hold;               // (published by the barriers of the body)
+      if (touching < 65536u) tile_body<true>(f, c, s_cnt, s_end, s_own[c.par], s_back[c.par], s_warp, s_open, mx, cap);
+      else tile_body<false>(f, c, s_cnt, s_end, s_own[c.par], s_back[c.par], s_warp, s_open, mx, cap);
+    } else {                                                      // a heavy tile met again in position order: done already
+      if (threadIdx.x == 0) { s_tk[it & 1] = tk_hold; s_open[c.par ^ 1] = 0; }
+      __syncthreads();
+    }
+    tk_nn = s_tk[it & 1];
+    tk_hold = tk_new;
+    c.tile = t_next; c.m = m_next;
+    t_next = t_nn; m_next = m_nn;
   }
   cp_async_wait<0>();
 

@@ -155,6 +155,10 @@ int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a) {
   f.tile_cursor = reinterpret_cast<uint32_t*>(z + o_cur);
   f.far_sorted = ctx->d_far_sorted.as<uint32_t>();
   f.tile_first = ctx->d_tile_off.as<uint32_t>();
+  CU(ctx->d_tile_heavy.ensure((size_t)n_tiles * 4));
+  f.tile_heavy = ctx->d_tile_heavy.as<uint32_t>();
+  // "heavy" = at least 8x the average tile (and at least 4096 reads): scheduled first by the tile kernel
+  f.heavy_min = (uint32_t)std::min<int64_t>(std::max<int64_t>(4096, 8 * n / std::max<int64_t>(n_tiles, 1)), 0x7fffffff);
   f.depth = ctx->depth;
   f.tile_cap = reinterpret_cast<int32_t*>(z + o_cap);
   f.max_depth = ctx->filt.max_depth;
@@ -281,7 +285,7 @@ void mcov_destroy(mcov_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->d_len, &ctx->d_off, &ctx->depth_own, &ctx->d_pc, &ctx->d_status, &ctx->d_end_slot,
                     &ctx->d_start_slot, &ctx->d_far_list, &ctx->d_tile_cnt, &ctx->d_tile_off, &ctx->d_far_sorted,
                     &ctx->d_tasks, &ctx->d_rlen, &ctx->d_rchunks, &ctx->d_rhist, &ctx->d_pool, &ctx->d_done,
-                    &ctx->d_out, &ctx->d_win_slot, &ctx->d_win_n, &ctx->d_win_out, &ctx->d_htasks};
+                    &ctx->d_out, &ctx->d_win_slot, &ctx->d_win_n, &ctx->d_win_out, &ctx->d_htasks, &ctx->d_tile_heavy};
   for (DevBuf* b : bufs) b->release();
   ctx->h_pin.release();
   for (auto& sl : ctx->slot) {
