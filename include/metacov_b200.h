@@ -210,6 +210,18 @@ int  mcov_region_hist_enqueue(mcov_ctx* ctx, int64_t g,
 int  mcov_hist_stats_enqueue(mcov_ctx* ctx, int64_t g, const uint32_t* dev_hist,
                              int32_t breadth_n, mcov_region_stats* dev_out);
 
+/* Run-length export of the per-base depth of the contigs [tid0, tid1) -- the rows
+ * of a bedGraph file (additive feature; the reference keeps
+ * its `columns` vector private, pileup.py:10-26).  A run is a maximal stretch of
+ * equal depth inside one contig, zero-depth runs included.  mcov_depth_runs
+ * computes the runs on the GPU, keeps them in the context and reports their
+ * number; mcov_depth_runs_read copies runs [first, first+n) to host arrays
+ * (tid, start, end, depth; 0-based half-open, position order).  The depth must
+ * not be recomputed between the two calls. */
+int  mcov_depth_runs(mcov_ctx* ctx, int32_t tid0, int32_t tid1, int64_t* n_runs_out);
+int  mcov_depth_runs_read(mcov_ctx* ctx, int64_t first, int64_t n,
+                          int32_t* tid, int32_t* start, int32_t* end, int32_t* depth);
+
 /* Fixed-window mean depth (additive feature named by north_star; no
  * reference counterpart): for every contig, ceil(len/window) float64 means,
  * concatenated in tid order into host_out (n_out = total windows). */

@@ -104,6 +104,8 @@ SIGNATURES = {
     "mcov_region_stats_submit": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i32, C.c_int]),
     "mcov_region_stats_collect": (C.c_int, [_vp, C.c_int, _vp]),
     "mcov_sync": (C.c_int, [_vp]),
+    "mcov_depth_runs": (C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]),
+    "mcov_depth_runs_read": (C.c_int, [_vp, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp]),
     "mcov_region_hist_enqueue": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp]),
     "mcov_hist_stats_enqueue": (C.c_int, [_vp, C.c_int64, _vp, C.c_int32, _vp]),
     "mcov_region_stats_collect_view": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),

@@ -14,6 +14,7 @@
 #include "k_fused.cuh"
 #include "k_hist.cuh"
 #include "k_scan.cuh"
+#include "k_export.cuh"
 #include "k_stats.cuh"
 
 using namespace mcov;
@@ -285,7 +286,7 @@ void mcov_destroy(mcov_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->d_len, &ctx->d_off, &ctx->depth_own, &ctx->d_pc, &ctx->d_status, &ctx->d_end_slot,
                     &ctx->d_start_slot, &ctx->d_far_list, &ctx->d_tile_cnt, &ctx->d_tile_off, &ctx->d_far_sorted,
                     &ctx->d_tasks, &ctx->d_rlen, &ctx->d_rchunks, &ctx->d_rhist, &ctx->d_pool, &ctx->d_done,
-                    &ctx->d_out, &ctx->d_win_slot, &ctx->d_win_n, &ctx->d_win_out, &ctx->d_htasks, &ctx->d_tile_heavy};
+                    &ctx->d_out, &ctx->d_win_slot, &ctx->d_win_n, &ctx->d_win_out, &ctx->d_htasks, &ctx->d_tile_heavy, &ctx->d_run_tasks, &ctx->d_run_counts, &ctx->d_run_out};
   for (DevBuf* b : bufs) b->release();
   ctx->h_pin.release();
   for (auto& sl : ctx->slot) {
@@ -540,7 +541,7 @@ static const char* kKernelNames[kKernelCount] = {
     "k_expand", "k_scan_inplace", "k_fused_prep", "k_tile_first", "k_scan_counts", "k_far_scatter", "k_fused_tile",
     "k_init_region_stats", "k_region_stats", "k_window_sums", "k_isize_hist", "k_group_count", "k_sorted_stats",
     "memset_depth", "k_region_stats_small", "k_cap_replay", "k_unpack_reads", "k_kmer_hist", "k_region_stats_warp",
-    "k_exp_prep", "k_exp_entries", "k_exp_region", "k_exp_revsum", "k_region_hist", "k_hist_finish"};
+    "k_exp_prep", "k_exp_entries", "k_exp_region", "k_exp_revsum", "k_region_hist", "k_hist_finish", "k_run_count", "k_run_offsets", "k_run_write", "k_run_ends"};
 
 int mcov_sync(mcov_ctx* ctx) {
   if (!ctx) return MCOV_ERR_ARG;
@@ -660,6 +661,12 @@ static int stats_launch(mcov_ctx* ctx, int64_t g, const int32_t* tid, const int3
         tasks.push_back(t);
       }
     }
+    // Largest jobs first, and -- for the warp-per-region kernel, where a CTA of 8 warps lives as long as its
+    // largest region -- neighbours of similar size: with the log-normal contig lengths of config C3 an
+    // unsorted CTA keeps its slots for about twice the mean of its regions.
+    auto by_size = [](const StatTask& x, const StatTask& y) { return x.n > y.n; };
+    if (!std::is_sorted(tasks.begin(), tasks.end(), by_size)) std::stable_sort(tasks.begin(), tasks.end(), by_size);
+    if (!std::is_sorted(small.begin(), small.end(), by_size)) std::stable_sort(small.begin(), small.end(), by_size);
     rp.n_tasks = (int64_t)tasks.size();
     rp.n_small = (int64_t)small.size();
     rp.n_multi = n_multi;
@@ -915,6 +922,68 @@ int mcov_hist_stats_enqueue(mcov_ctx* ctx, int64_t g, const uint32_t* dev_hist, 
   CU(cudaSetDevice(ctx->device));
   MCOV_LAUNCH(ctx, kKHistFinish, (k_hist_finish<<<(unsigned)g, kStatThreads, 0, ctx->stream>>>(dev_hist, dev_out, breadth_n)));
   CU(cudaGetLastError());
+  return MCOV_OK;
+}
+
+int mcov_depth_runs(mcov_ctx* ctx, int32_t tid0, int32_t tid1, int64_t* n_runs_out) {
+  if (!ctx) return MCOV_ERR_ARG;
+  if (ctx->state != kDepthReady) return fail(ctx, MCOV_ERR_STATE, "mcov_depth_runs: depth not ready (finalize first)");
+  if (tid0 < 0 || tid1 < tid0 || tid1 > ctx->n_contigs || !n_runs_out) return fail(ctx, MCOV_ERR_ARG, "mcov_depth_runs: bad contig range");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  ctx->n_runs = -1;
+  std::vector<RunTask> tasks;
+  for (int32_t c = tid0; c < tid1; ++c)
+    for (int64_t p = 0; p < ctx->len[c]; p += kRunChunk) {
+      RunTask t;
+      t.slot = ctx->off[c] + p; t.n = (int32_t)std::min<int64_t>(kRunChunk, ctx->len[c] - p); t.tid = c; t.pos0 = (int32_t)p; t.reserved = 0;
+      tasks.push_back(t);
+    }
+  const int64_t nt = (int64_t)tasks.size();
+  *n_runs_out = 0;
+  if (nt == 0) { ctx->n_runs = 0; return MCOV_OK; }
+  if (nt > INT32_MAX) return fail(ctx, MCOV_ERR_RANGE, "mcov_depth_runs: contig range too large for one call");
+  CU(ctx->d_run_tasks.ensure((size_t)nt * sizeof(RunTask)));
+  CU(ctx->d_run_counts.ensure(((size_t)nt + 1) * 8));
+  CU(cudaMemcpyAsync(ctx->d_run_tasks.p, tasks.data(), (size_t)nt * sizeof(RunTask), cudaMemcpyHostToDevice, s));
+  long long* counts = ctx->d_run_counts.as<long long>();
+  MCOV_LAUNCH(ctx, kKRunCount, (k_run_count<<<(unsigned)nt, kRunThreads, 0, s>>>(ctx->depth, ctx->d_run_tasks.as<RunTask>(), counts)));
+  CU(cudaGetLastError());
+  MCOV_LAUNCH(ctx, kKRunOffsets, (k_run_offsets<<<1, 1024, 0, s>>>(counts, nt)));
+  CU(cudaGetLastError());
+  long long total = 0;
+  PassCounters h;
+  CU(cudaMemcpyAsync(&total, counts + nt, 8, cudaMemcpyDeviceToHost, s));
+  if (ctx->verdict_pending) CU(cudaMemcpyAsync(&h, ctx->d_pc.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));                    // (also: `tasks` has been consumed)
+  if (ctx->verdict_pending) { int vr = fused_verdict(ctx, h); if (vr) return vr; }
+  if (total > 0) {
+    CU(ctx->d_run_out.ensure((size_t)total * 16));
+    int32_t* o = ctx->d_run_out.as<int32_t>();
+    MCOV_LAUNCH(ctx, kKRunWrite, (k_run_write<<<(unsigned)nt, kRunThreads, 0, s>>>(ctx->depth, ctx->d_run_tasks.as<RunTask>(), counts,
+                                                                                    o, o + total, o + 3 * total)));
+    CU(cudaGetLastError());
+    MCOV_LAUNCH(ctx, kKRunEnds, (k_run_ends<<<grid_for(total, 256, 8), 256, 0, s>>>(o, o + total, ctx->d_len.as<int32_t>(), total, o + 2 * total)));
+    CU(cudaGetLastError());
+  }
+  ctx->n_runs = total;
+  *n_runs_out = total;
+  return MCOV_OK;
+}
+
+int mcov_depth_runs_read(mcov_ctx* ctx, int64_t first, int64_t n, int32_t* tid, int32_t* start, int32_t* end, int32_t* depth) {
+  if (!ctx) return MCOV_ERR_ARG;
+  if (ctx->n_runs < 0) return fail(ctx, MCOV_ERR_STATE, "mcov_depth_runs_read: call mcov_depth_runs first");
+  if (first < 0 || n < 0 || first + n > ctx->n_runs || (n > 0 && (!tid || !start || !end || !depth)))
+    return fail(ctx, MCOV_ERR_ARG, "mcov_depth_runs_read: bad range");
+  if (n == 0) return MCOV_OK;
+  CU(cudaSetDevice(ctx->device));
+  const int32_t* o = ctx->d_run_out.as<int32_t>();
+  const int64_t total = ctx->n_runs;
+  int32_t* dst[4] = {tid, start, end, depth};
+  for (int k = 0; k < 4; ++k)
+    CU(cudaMemcpyAsync(dst[k], o + (int64_t)k * total + first, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
   return MCOV_OK;
 }
 

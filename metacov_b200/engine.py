@@ -19,6 +19,8 @@ tid:int32[n] pos:int32[n] flag:uint16[n] mapq:uint8[n] cig_off:uint32[n+1]
 cig:uint32[cig_off[n]] (BAM encoding len<<4|op).  numpy arrays (host) or torch
 tensors (host or CUDA)."""
 
+RUNS_DTYPE = np.dtype([("tid", "<i4"), ("start", "<i4"), ("end", "<i4"), ("depth", "<i4")])
+
 _DT = dict(tid=np.int32, pos=np.int32, flag=np.uint16, mapq=np.uint8, cig_off=np.uint32, cig=np.uint32)
 
 
@@ -318,6 +320,21 @@ class CoverageEngine:
                                        win_bases, K, NK, STEP, OFFSET, len(gf), _capi.ptr(gf) if len(gf) else None,
                                        _capi.ptr(hist)))
         return hist
+
+    def depth_runs(self, tid0=0, tid1=None, skip_zero=False):
+        """Run-length form of the per-base depth of contigs [tid0, tid1): structured array
+        (tid, start, end, depth), one record per maximal run of equal depth -- the rows of a
+        bedGraph file (mcov_depth_runs)."""
+        tid1 = len(self.lengths) if tid1 is None else int(tid1)
+        n = C.c_int64()
+        self._check(lib.mcov_depth_runs(self._ctx, int(tid0), tid1, C.byref(n)))
+        n = n.value
+        cols = [np.empty(n, dtype=np.int32) for _ in range(4)]
+        self._check(lib.mcov_depth_runs_read(self._ctx, 0, n, *[_capi.ptr(c) for c in cols]))
+        out = np.empty(n, dtype=RUNS_DTYPE)
+        for name, c in zip(RUNS_DTYPE.names, cols):
+            out[name] = c
+        return out[out["depth"] != 0] if skip_zero else out
 
     def window_means(self, window):
         n_out = int(sum((int(l) + window - 1) // window for l in self.lengths))
