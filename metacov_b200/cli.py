@@ -42,10 +42,19 @@ def main():
 @click.option("--kmer-histogram", "-k", type=click.File("r"), help="Kmer Histogram produced with metacov scan")
 @click.option("--kmer-length", "-K", type=int, default=7, help="Length of k-mer")
 @click.option("--outfile", "-o", type=click.File("w"), default="-", help="Output CSV (default STDOUT)")
-def pileup(bamfile, reference_fasta, regionfile_blast7, regionfile_csv, kmer_histogram, kmer_length, outfile):
+@click.option("--bedgraph", "-bg", type=click.File("w"), metavar="FILE",
+              help="Also write the per-base depth as bedGraph (runs of equal depth; zero-depth runs omitted). "
+                   "Not in the reference: additive.")
+@click.option("--window", "-w", type=click.IntRange(1), metavar="N",
+              help="Also write the mean depth of fixed windows of N bp to --window-out. Not in the reference: additive.")
+@click.option("--window-out", "-wo", type=click.File("w"), metavar="FILE", help="Output CSV of --window (sacc,start,end,avg)")
+def pileup(bamfile, reference_fasta, regionfile_blast7, regionfile_csv, kmer_histogram, kmer_length, outfile,
+           bedgraph=None, window=None, window_out=None):
     """
     Compute fold coverage values
     """
+    if (window is None) != (window_out is None):
+        raise click.UsageError("--window and --window-out go together")
     bam = AlignmentFile(bamfile.name)
     fasta = FastaFile(reference_fasta.name) if reference_fasta else None          # cli.py:59
     regions = util.make_region_iterator(regionfile_blast7, regionfile_csv, bam)
@@ -83,7 +92,32 @@ def pileup(bamfile, reference_fasta, regionfile_blast7, regionfile_csv, kmer_his
             writer.writeheader()
         result.update({"sacc": hit.sacc, "start": hit.sstart, "end": hit.send})
         writer.writerow(result)
+    if bedgraph is not None:
+        write_bedgraph(bam, bedgraph)
+    if window is not None:
+        write_windows(bam, window, window_out)
     bam.close()
+
+
+def write_bedgraph(bam, out):
+    """Per-base depth as bedGraph lines `name<TAB>start<TAB>end<TAB>depth` (0-based half-open), one per
+    run of equal non-zero depth; the runs come from the GPU (mcov_depth_runs)."""
+    names = [ref.split()[0] for ref in bam.references]
+    runs = bam.coverage_engine().depth_runs(skip_zero=True)
+    for t, s, e, d in zip(runs["tid"].tolist(), runs["start"].tolist(), runs["end"].tolist(), runs["depth"].tolist()):
+        out.write("%s\t%d\t%d\t%d\n" % (names[t], s, e, d))
+
+
+def write_windows(bam, window, out):
+    """Mean depth of fixed windows (the last window of a contig may be shorter): CSV sacc,start,end,avg."""
+    means = bam.coverage_engine().window_means(window)
+    w = csv.writer(out)
+    w.writerow(["sacc", "start", "end", "avg"])
+    k = 0
+    for ref, ln in zip(bam.references, bam.lengths):
+        for p in range(0, ln, window):
+            w.writerow([ref.split()[0], p, min(p + window, ln), round(float(means[k]), 2)])
+            k += 1
 
 
 @main.command()

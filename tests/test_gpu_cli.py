@@ -190,3 +190,69 @@ def test_cli_pileup_with_kmer_histogram(fixture_bam, tmp_path):
             _, want = oexp.experimental(obam.recs, obam.references, k_cor, 7, gold["fasta"][ref], ref, 0, ln)
         got = {k: float(row[k]) for k in keys}
         assert_experimental_equal(got, {k: float(v) for k, v in want.items()}, ref)
+
+
+def _numpy_runs(depth_by_contig):
+    """Run-length form of per-contig depth vectors, the plain way (test oracle of mcov_depth_runs)."""
+    rows = []
+    for t, d in enumerate(depth_by_contig):
+        if len(d) == 0:
+            continue
+        cut = np.flatnonzero(np.diff(d)) + 1
+        st = np.concatenate(([0], cut))
+        en = np.concatenate((cut, [len(d)]))
+        rows += [(t, int(s), int(e), int(d[s])) for s, e in zip(st, en)]
+    return rows
+
+
+def test_depth_runs_match_numpy_rle():
+    """mcov_depth_runs on the fixture, on a synthetic set with empty / tiny contigs, and on a scaled C2
+    shard (runs crossing the 8192-slot chunks of the export kernels), against numpy on the oracle depth."""
+    from metacov_b200 import CoverageEngine, synth
+    cases = []
+    z, fb = load_soa("fixture_soa.npz")
+    cases.append((fb, z["lengths"]))
+    z2, sb = load_soa("synth_small_soa.npz")
+    cases.append((sb, z2["lengths"]))
+    w = synth.c2(0.003)
+    hb, _ = synth.generate_host(w)
+    cases.append((hb, w.contig_len))
+    w5 = synth.c5(0.0005)                                   # long reads: long flat runs across many chunks
+    h5, _ = synth.generate_host(w5)
+    cases.append((h5, w5.contig_len))
+    for batch, lengths in cases:
+        d, off, _ = cport.depth(batch, lengths, mode="diff")
+        want = _numpy_runs([d[off[c]:off[c] + lengths[c]] for c in range(len(lengths))])
+        with CoverageEngine(lengths) as eng:
+            eng.compute_depth(batch)
+            runs = eng.depth_runs()
+            got = list(zip(runs["tid"].tolist(), runs["start"].tolist(), runs["end"].tolist(), runs["depth"].tolist()))
+            assert got == want
+            # a contig sub-range and the zero filter
+            if len(lengths) > 1:
+                sub = eng.depth_runs(1, 2)
+                assert [r for r in want if r[0] == 1] == list(zip(sub["tid"].tolist(), sub["start"].tolist(),
+                                                                  sub["end"].tolist(), sub["depth"].tolist()))
+            nz = eng.depth_runs(skip_zero=True)
+            assert len(nz) == sum(1 for r in want if r[3] != 0) and int(((nz["end"] - nz["start"]).astype(np.int64) * nz["depth"]).sum()) == int(d.astype(np.int64).sum())
+            assert len(eng.depth_runs(0, 0)) == 0
+
+
+def test_cli_bedgraph_and_windows(fixture_bam, tmp_path):
+    """Additive outputs of `metacov pileup`: --bedgraph (runs of equal non-zero depth) and --window."""
+    bg, wo, out = tmp_path / "cov.bedgraph", tmp_path / "win.csv", tmp_path / "cov.csv"
+    run_pileup(["-b", fixture_bam, "-o", str(out), "-bg", str(bg), "-w", "100", "-wo", str(wo)])
+    ref1 = np.load(os.path.join(os.path.dirname(__file__), "golden", "fixture_depth_ref1.npy"))
+    ref2 = np.load(os.path.join(os.path.dirname(__file__), "golden", "fixture_depth_ref2.npy"))
+    names = ["ref1", "ref2"]
+    want = ["%s\t%d\t%d\t%d" % (names[t], s, e, d) for t, s, e, d in _numpy_runs([ref1, ref2]) if d != 0]
+    assert bg.read_text().splitlines() == want
+    rows = list(csv.DictReader(io.StringIO(wo.read_text())))
+    exp = []
+    for name, d in zip(names, (ref1, ref2)):
+        for p in range(0, len(d), 100):
+            exp.append({"sacc": name, "start": str(p), "end": str(min(p + 100, len(d))),
+                        "avg": str(round(float(np.mean(d[p:p + 100])), 2))})
+    assert rows == exp
+    from metacov_b200.cli import pileup
+    assert CliRunner().invoke(pileup, ["-b", fixture_bam, "-w", "100"]).exit_code != 0      # --window without --window-out
