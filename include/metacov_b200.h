@@ -257,6 +257,8 @@ typedef struct mcov_kernel_time {
 /* Wait for everything enqueued on the context's stream (for callers that mix the *_enqueue entry
  * points with work on other streams). */
 int  mcov_sync(mcov_ctx* ctx);
+/* Copy n_bytes of device memory owned by the context (e.g. the columns of mcov_bam_dev) to the host. */
+int  mcov_copy_to_host(mcov_ctx* ctx, const void* dev, void* host, int64_t n_bytes);
 
 /* kernels (and clears) enqueued by this context since it was created */
 int64_t mcov_launch_count(const mcov_ctx* ctx);
@@ -379,6 +381,39 @@ int  mcov_bam_qas_kmer(const mcov_bam* b, int32_t k_len, int32_t* out);
 /* ---- synthetic workloads (bench / test support; include/mcov_synth.h) ---- */
 
 struct mcov_synth_params;
+
+/* ---- GPU-side BAM decode ----------------------------
+ * Replaces, for the coverage path, `pysam.AlignmentFile` + `IteratorRowAll`
+ * (reference metacov/scan.pyx:204, 216; cli.py:56) without the host decode of
+ * mcov_bam_open / mcov_bam_load: the COMPRESSED file image goes to the device,
+ * every BGZF block is inflated by one GPU thread, the record chain is walked in
+ * parallel (guessed segment starts, every link verified: exact) and the SoA
+ * columns are written to device memory owned by the context -- valid until the
+ * next mcov_bam_decode_gpu or mcov_destroy, and ready for
+ * mcov_depth_sorted(..., MCOV_MEM_DEVICE).  file_bytes: the whole .bam file in
+ * host memory (pinned memory makes the copy fast).  The inflated stream and
+ * the SoA must fit the device.  `inflated` points at the inflated stream
+ * (header_bytes = offset of the first alignment record: magic, header text and
+ * the reference table lie before it). */
+typedef struct mcov_bam_dev {
+  int64_t n_records, n_cigar, inflated_bytes, header_bytes, n_segments;
+  int32_t n_ref, reserved;
+  const int32_t*  tid;
+  const int32_t*  pos;
+  const uint16_t* flag;
+  const uint8_t*  mapq;
+  const int32_t*  l_seq;
+  const int32_t*  isize;
+  const uint32_t* cig_off;   /* n_records + 1 */
+  const uint32_t* cig;
+  const uint8_t*  inflated;
+} mcov_bam_dev;
+int  mcov_bam_decode_gpu(mcov_ctx* ctx, const void* file_bytes, int64_t n_bytes, int verify_crc, mcov_bam_dev* out);
+/* Test hooks: the device inflate / CRC-32 code (csrc/inflate.cuh) compiled for the host, so that the CPU
+ * suite can check it against zlib.  mcov_inflate_host returns 0 or a positive decoder status. */
+int  mcov_inflate_host(const uint8_t* src, uint32_t clen, uint8_t* dst, uint32_t ulen);
+uint32_t mcov_crc32_host(const uint8_t* p, uint32_t n);
+
 /* n_cigar of reads [i0, i0+n) -> out[n] (host or device memory per mem_kind;
  * device work is enqueued on `stream`, a cudaStream_t or NULL). */
 int  mcov_synth_gen_ncigar(const struct mcov_synth_params* P, int64_t i0, int64_t n,

@@ -56,6 +56,14 @@ REGION_STATS_DTYPE = np.dtype([
 assert REGION_STATS_DTYPE.itemsize == C.sizeof(RegionStats) == 64
 
 
+class BamDev(C.Structure):
+    """mcov_bam_dev: device-resident SoA of a BAM decoded on the GPU."""
+    _fields_ = [("n_records", C.c_int64), ("n_cigar", C.c_int64), ("inflated_bytes", C.c_int64), ("header_bytes", C.c_int64),
+                ("n_segments", C.c_int64), ("n_ref", C.c_int32), ("reserved", C.c_int32),
+                ("tid", C.c_void_p), ("pos", C.c_void_p), ("flag", C.c_void_p), ("mapq", C.c_void_p), ("l_seq", C.c_void_p),
+                ("isize", C.c_void_p), ("cig_off", C.c_void_p), ("cig", C.c_void_p), ("inflated", C.c_void_p)]
+
+
 class PassInfo(C.Structure):
     _fields_ = [("n_reads", C.c_int64), ("n_pass", C.c_int64), ("aligned_bases", C.c_int64),
                 ("max_depth_seen", C.c_int32), ("cap_metric", C.c_int32), ("sorted", C.c_int32),
@@ -104,6 +112,10 @@ SIGNATURES = {
     "mcov_region_stats_submit": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i32, C.c_int]),
     "mcov_region_stats_collect": (C.c_int, [_vp, C.c_int, _vp]),
     "mcov_sync": (C.c_int, [_vp]),
+    "mcov_copy_to_host": (C.c_int, [_vp, _vp, _vp, C.c_int64]),
+    "mcov_bam_decode_gpu": (C.c_int, [_vp, _vp, C.c_int64, C.c_int, _vp]),
+    "mcov_inflate_host": (C.c_int, [_vp, C.c_uint32, _vp, C.c_uint32]),
+    "mcov_crc32_host": (C.c_uint32, [_vp, C.c_uint32]),
     "mcov_depth_runs": (C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]),
     "mcov_depth_runs_read": (C.c_int, [_vp, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp]),
     "mcov_region_hist_enqueue": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp]),

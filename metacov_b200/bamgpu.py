@@ -1,0 +1,85 @@
+"""BAM decode on the GPU: the compressed file goes to the device, BGZF blocks are
+inflated and the records parsed there (csrc/bam_gpu.cu), and the SoA columns stay in HBM for the coverage
+kernels.  Replaces, for this path, ``pysam.AlignmentFile`` + ``IteratorRowAll`` (reference
+metacov/scan.pyx:204, 216; cli.py:56) without the host decode of ``alignmentfile.AlignmentFile``.
+
+    eng = CoverageEngine(lengths)
+    soa = bamgpu.decode(eng, "reads.bam")        # device-resident columns, owned by the engine's context
+    bamgpu.depth_sorted(eng, soa)                # per-base depth straight from them
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import lib
+
+
+class DeviceSoA:
+    """Device pointers of a decoded BAM (``mcov_bam_dev``); valid until the next decode on the same engine."""
+
+    COLS = (("tid", np.int32), ("pos", np.int32), ("flag", np.uint16), ("mapq", np.uint8), ("l_seq", np.int32),
+            ("isize", np.int32), ("cig_off", np.uint32), ("cig", np.uint32))
+
+    def __init__(self, engine, raw):
+        self._engine = engine
+        self.raw = raw
+        self.n_records, self.n_cigar, self.n_ref = raw.n_records, raw.n_cigar, raw.n_ref
+        self.inflated_bytes, self.header_bytes, self.n_segments = raw.inflated_bytes, raw.header_bytes, raw.n_segments
+
+    def _len(self, name):
+        return self.n_cigar if name == "cig" else (self.n_records + 1 if name == "cig_off" else self.n_records)
+
+    def to_host(self, name):
+        """One column copied to a numpy array (tests, accessors)."""
+        dt = dict(self.COLS)[name]
+        out = np.empty(self._len(name), dtype=dt)
+        self._engine._check(lib.mcov_copy_to_host(self._engine._ctx, getattr(self.raw, name), _capi.ptr(out), out.nbytes))
+        return out
+
+    def header(self):
+        """(text, [(name, length)]) parsed from the inflated stream's header (SAM spec 4.2)."""
+        buf = np.empty(self.header_bytes, dtype=np.uint8)
+        self._engine._check(lib.mcov_copy_to_host(self._engine._ctx, self.raw.inflated, _capi.ptr(buf), buf.nbytes))
+        b = buf.tobytes()
+        l_text = int.from_bytes(b[4:8], "little")
+        text = b[8:8 + l_text].split(b"\0")[0].decode()
+        p = 8 + l_text
+        n_ref = int.from_bytes(b[p:p + 4], "little")
+        p += 4
+        refs = []
+        for _ in range(n_ref):
+            ln = int.from_bytes(b[p:p + 4], "little")
+            name = b[p + 4:p + 4 + ln - 1].decode()
+            refs.append((name, int.from_bytes(b[p + 4 + ln:p + 8 + ln], "little")))
+            p += 8 + ln
+        return text, refs
+
+
+def decode(engine, source, verify_crc=True):
+    """Decode a BAM on the GPU.  ``source``: a path, ``bytes`` or a uint8 numpy array / pinned torch tensor
+    holding the file image.  Returns a ``DeviceSoA``."""
+    keep = None
+    if isinstance(source, (str, bytes)) and not isinstance(source, bytes):
+        with open(source, "rb") as fh:
+            source = fh.read()
+    if isinstance(source, bytes):
+        keep = np.frombuffer(source, dtype=np.uint8)
+        ptr, n = keep.ctypes.data, keep.nbytes
+    elif hasattr(source, "data_ptr"):
+        keep = source
+        ptr, n = source.data_ptr(), source.numel() * source.element_size()
+    else:
+        keep = np.ascontiguousarray(source, dtype=np.uint8)
+        ptr, n = keep.ctypes.data, keep.nbytes
+    raw = _capi.BamDev()
+    engine._check(lib.mcov_bam_decode_gpu(engine._ctx, ptr, n, 1 if verify_crc else 0, C.byref(raw)))
+    del keep
+    return DeviceSoA(engine, raw)
+
+
+def depth_sorted(engine, soa, wait=True):
+    """Per-base depth of every contig from device-resident columns (fused sorted path)."""
+    fn = lib.mcov_depth_sorted if wait else lib.mcov_depth_sorted_async
+    r = soa.raw
+    engine._check(fn(engine._ctx, soa.n_records, r.tid, r.pos, r.flag, r.mapq, r.cig_off, r.cig, _capi.MEM_DEVICE))

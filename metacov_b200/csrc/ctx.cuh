@@ -45,7 +45,7 @@ enum PassState { kIdle = 0, kAccumulating = 1, kDepthReady = 2 };
 enum KernelId {
   kKExpand = 0, kKScan, kKFusedPrep, kKTileFirst, kKScanCounts, kKFarScatter, kKFusedTile,
   kKInitStats, kKRegionStats, kKWindowSums, kKIsizeHist, kKGroupCount, kKSortedStats, kKClear, kKRegionStatsSmall, kKCapReplay, kKUnpack, kKKmerHist, kKRegionStatsWarp,
-  kKExpPrep, kKExpEntries, kKExpRegion, kKExpRevsum, kKRegionHist, kKHistFinish, kKRunCount, kKRunOffsets, kKRunWrite, kKRunEnds,
+  kKExpPrep, kKExpEntries, kKExpRegion, kKExpRevsum, kKRegionHist, kKHistFinish, kKRunCount, kKRunOffsets, kKRunWrite, kKRunEnds, kKBgzfInflate, kKBamGuess, kKBamWalkCount, kKBamWalkWrite,
   kKernelCount
 };
 
@@ -100,6 +100,15 @@ struct mcov_ctx {
   mcov::RegionPlan plan;
   int32_t cap_contigs = 0;        // contigs replayed under htslib's max_depth cap in the last fused pass
   std::vector<unsigned char> fused_blob;   // FusedArgs of the last fused pass (k_fused.cuh), for the cap replay
+
+  // GPU-side BAM decode (bam_gpu.cu): compressed image, inflated stream, record-chain scratch, SoA columns
+  struct BamDev {
+    mcov::DevBuf raw, blocks, data, status, starts, segs, wout, tid, pos, flag, mapq, lseq, isize, cig_off, cig;
+    void release() {
+      mcov::DevBuf* b[] = {&raw, &blocks, &data, &status, &starts, &segs, &wout, &tid, &pos, &flag, &mapq, &lseq, &isize, &cig_off, &cig};
+      for (mcov::DevBuf* x : b) x->release();
+    }
+  } bam;
 
   // fused (sorted) path scratch
   mcov::DevBuf d_end_slot, d_start_slot, d_far_list, d_tile_cnt, d_tile_off, d_far_sorted;

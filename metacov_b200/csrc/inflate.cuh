@@ -1,0 +1,234 @@
+// inflate.cuh -- raw DEFLATE (RFC 1951) decoder for one BGZF block, usable on the device and on the host.
+//
+// BGZF (SAM spec 4.1) cuts a BAM file into independent deflate streams of at most 64 KiB, so a file is
+// thousands of independent decode jobs: on the GPU one WARP inflates one block (k_bgzf_inflate,
+// bam_gpu.cu).  All lanes decode the symbol stream redundantly (identical state, broadcast loads), which
+// keeps the control flow uniform; the work that can be split is split: an LZ77 match of `len` bytes is
+// copied by the lanes in parallel -- byte k comes from dst[o - dist + k % dist], so even a run with
+// dist = 1 has no serial dependency (one thread per block spent ~2 us per byte there, an L2 round trip
+// each).  Huffman decoding is the canonical-code walk (one bit per step, count[] / symbol[] tables as in
+// zlib's contrib/puff) -- no lookup tables, ~1.4 KB of per-lane local memory, no shared state.  Every loop
+// consumes input or produces output and both are bounded, so malformed data ends in an error code,
+// never in a hang.  On the host the same code runs with one "lane".
+//
+// The same source compiles for the host: mcov_inflate_host() lets the CPU test suite check the decoder
+// against zlib without a GPU.
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define MCOV_HD __host__ __device__ __forceinline__
+#else
+#define MCOV_HD inline
+#endif
+
+namespace mcov {
+
+#if defined(__CUDA_ARCH__)
+#define MCOV_INF_SYNC() __syncwarp()
+#define MCOV_INF_LDOUT(p) __ldcg(p)          /* output written by other lanes: read through L2 */
+#else
+#define MCOV_INF_SYNC() ((void)0)
+#define MCOV_INF_LDOUT(p) (*(p))
+#endif
+
+enum InflateStatus {
+  kInfOk = 0, kInfInputOverrun = 1, kInfOutputOverrun = 2, kInfBadBlockType = 3, kInfBadStored = 4,
+  kInfBadCodeLengths = 5, kInfBadSymbol = 6, kInfBadDistance = 7, kInfShortOutput = 8
+};
+
+struct InfBits {
+  const uint8_t* in;
+  uint32_t n, p;
+  uint64_t buf;
+  int cnt;
+  bool over;
+};
+
+MCOV_HD uint32_t inf_bits(InfBits& r, int need) {
+  while (r.cnt < need) {
+    uint64_t b = 0;
+    if (r.p < r.n) b = r.in[r.p]; else r.over = true;
+    ++r.p;
+    r.buf |= b << r.cnt;
+    r.cnt += 8;
+  }
+  const uint32_t v = (uint32_t)(r.buf & ((1ull << need) - 1ull));
+  r.buf >>= need;
+  r.cnt -= need;
+  return v;
+}
+
+struct InfHuff {
+  int16_t count[16];
+  int16_t* symbol;
+};
+
+// canonical Huffman code from code lengths; returns <0 over-subscribed, 0 complete, >0 incomplete
+MCOV_HD int inf_construct(InfHuff& h, const int16_t* length, int n) {
+  int16_t offs[16];
+  for (int len = 0; len <= 15; ++len) h.count[len] = 0;
+  for (int s = 0; s < n; ++s) h.count[length[s]]++;
+  if (h.count[0] == n) return 0;
+  int left = 1;
+  for (int len = 1; len <= 15; ++len) {
+    left <<= 1;
+    left -= h.count[len];
+    if (left < 0) return left;
+  }
+  offs[1] = 0;
+  for (int len = 1; len < 15; ++len) offs[len + 1] = (int16_t)(offs[len] + h.count[len]);
+  for (int s = 0; s < n; ++s)
+    if (length[s] != 0) h.symbol[offs[length[s]]++] = (int16_t)s;
+  return left;
+}
+
+MCOV_HD int inf_decode(InfBits& r, const InfHuff& h) {
+  int code = 0, first = 0, index = 0;
+  for (int len = 1; len <= 15; ++len) {
+    code |= (int)inf_bits(r, 1);
+    const int count = h.count[len];
+    if (code - count < first) return h.symbol[index + (code - first)];
+    index += count;
+    first += count;
+    first <<= 1;
+    code <<= 1;
+  }
+  return -1;
+}
+
+// length / distance base values and extra bits of RFC 1951 3.2.5 in closed form (no tables in local memory)
+MCOV_HD int inf_len_extra(int s) { return (s < 8 || s == 28) ? 0 : ((s - 4) >> 2); }
+MCOV_HD int inf_len_base(int s) { return s < 8 ? 3 + s : (s == 28 ? 258 : 3 + ((4 + (s & 3)) << ((s - 4) >> 2))); }
+MCOV_HD int inf_dist_extra(int s) { return s < 4 ? 0 : ((s - 2) >> 1); }
+MCOV_HD int inf_dist_base(int s) { return s < 4 ? 1 + s : 1 + ((2 + (s & 1)) << ((s - 2) >> 1)); }
+
+// Inflate one raw deflate stream of clen bytes into exactly ulen bytes.  Returns an InflateStatus.
+// Called by `nlanes` cooperating lanes (a warp, or 1 on the host) with identical arguments except `lane`;
+// every lane returns the same status.
+MCOV_HD int inflate_raw(const uint8_t* src, uint32_t clen, uint8_t* dst, uint32_t ulen, int lane = 0, int nlanes = 1) {
+  InfBits r;
+  r.in = src; r.n = clen; r.p = 0; r.buf = 0; r.cnt = 0; r.over = false;
+  int16_t lengths[320];
+  int16_t lensym[288], distsym[30];
+  InfHuff lencode, distcode;
+  lencode.symbol = lensym;
+  distcode.symbol = distsym;
+  uint32_t o = 0;
+  int last;
+  do {
+    last = (int)inf_bits(r, 1);
+    const int type = (int)inf_bits(r, 2);
+    if (r.over) return kInfInputOverrun;
+    if (type == 0) {                                        // stored
+      const int drop = r.cnt & 7;
+      (void)inf_bits(r, drop);
+      const uint32_t len = inf_bits(r, 16), nlen = inf_bits(r, 16);
+      if (r.over || (len ^ 0xffffu) != nlen) return kInfBadStored;
+      if (o + len > ulen) return kInfOutputOverrun;
+      for (uint32_t k = 0; k < len; ++k) {
+        const uint8_t v = (uint8_t)inf_bits(r, 8);
+        if (lane == 0) dst[o] = v;
+        ++o;
+      }
+      if (r.over) return kInfInputOverrun;
+      continue;
+    }
+    if (type == 3) return kInfBadBlockType;
+    if (type == 1) {                                        // fixed codes
+      int s = 0;
+      for (; s < 144; ++s) lengths[s] = 8;
+      for (; s < 256; ++s) lengths[s] = 9;
+      for (; s < 280; ++s) lengths[s] = 7;
+      for (; s < 288; ++s) lengths[s] = 8;
+      inf_construct(lencode, lengths, 288);
+      for (s = 0; s < 30; ++s) lengths[s] = 5;
+      inf_construct(distcode, lengths, 30);
+    } else {                                                // dynamic codes
+      const int order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+      const int nlen = (int)inf_bits(r, 5) + 257, ndist = (int)inf_bits(r, 5) + 1, ncode = (int)inf_bits(r, 4) + 4;
+      if (r.over) return kInfInputOverrun;
+      if (nlen > 286 || ndist > 30) return kInfBadCodeLengths;
+      int idx = 0;
+      for (; idx < ncode; ++idx) lengths[order[idx]] = (int16_t)inf_bits(r, 3);
+      for (; idx < 19; ++idx) lengths[order[idx]] = 0;
+      if (inf_construct(lencode, lengths, 19) != 0) return kInfBadCodeLengths;
+      idx = 0;
+      while (idx < nlen + ndist) {
+        int sym = inf_decode(r, lencode);
+        if (sym < 0 || r.over) return kInfBadCodeLengths;
+        if (sym < 16) {
+          lengths[idx++] = (int16_t)sym;
+        } else {
+          int len = 0, rep;
+          if (sym == 16) {
+            if (idx == 0) return kInfBadCodeLengths;
+            len = lengths[idx - 1];
+            rep = 3 + (int)inf_bits(r, 2);
+          } else if (sym == 17) {
+            rep = 3 + (int)inf_bits(r, 3);
+          } else {
+            rep = 11 + (int)inf_bits(r, 7);
+          }
+          if (idx + rep > nlen + ndist) return kInfBadCodeLengths;
+          while (rep--) lengths[idx++] = (int16_t)len;
+        }
+      }
+      if (lengths[256] == 0) return kInfBadCodeLengths;
+      int err = inf_construct(lencode, lengths, nlen);
+      if (err < 0 || (err > 0 && nlen - lencode.count[0] != 1)) return kInfBadCodeLengths;
+      err = inf_construct(distcode, lengths + nlen, ndist);
+      if (err < 0 || (err > 0 && ndist - distcode.count[0] != 1)) return kInfBadCodeLengths;
+    }
+    // literal/length + distance symbols until end-of-block
+    for (;;) {
+      int sym = inf_decode(r, lencode);
+      if (sym < 0) return kInfBadSymbol;
+      if (r.over) return kInfInputOverrun;
+      if (sym < 256) {
+        if (o >= ulen) return kInfOutputOverrun;
+        if (lane == 0) dst[o] = (uint8_t)sym;
+        ++o;
+      } else if (sym == 256) {
+        break;
+      } else {
+        sym -= 257;
+        if (sym >= 29) return kInfBadSymbol;
+        const uint32_t len = (uint32_t)inf_len_base(sym) + inf_bits(r, inf_len_extra(sym));
+        const int ds = inf_decode(r, distcode);
+        if (ds < 0 || ds >= 30) return kInfBadSymbol;
+        const uint32_t dist = (uint32_t)inf_dist_base(ds) + inf_bits(r, inf_dist_extra(ds));
+        if (r.over) return kInfInputOverrun;
+        if (dist > o) return kInfBadDistance;
+        if (o + len > ulen) return kInfOutputOverrun;
+        // the match source [o - dist, o) is complete: byte k of the match repeats it with period dist
+        MCOV_INF_SYNC();
+        const uint8_t* from = dst + (o - dist);
+        if (dist >= len) {
+          for (uint32_t k = (uint32_t)lane; k < len; k += (uint32_t)nlanes) dst[o + k] = MCOV_INF_LDOUT(from + k);
+        } else {
+          for (uint32_t k = (uint32_t)lane; k < len; k += (uint32_t)nlanes) dst[o + k] = MCOV_INF_LDOUT(from + k % dist);
+        }
+        MCOV_INF_SYNC();
+        o += len;
+      }
+    }
+  } while (!last);
+  MCOV_INF_SYNC();
+  return o == ulen ? kInfOk : kInfShortOutput;
+}
+
+// CRC-32 (IEEE 802.3, as in gzip) of n bytes, 4 bits per step from a 16-entry table
+MCOV_HD uint32_t crc32_bytes(const uint8_t* p, uint32_t n) {
+  const uint32_t t[16] = {0x00000000u, 0x1db71064u, 0x3b6e20c8u, 0x26d930acu, 0x76dc4190u, 0x6b6b51f4u, 0x4db26158u, 0x5005713cu,
+                          0xedb88320u, 0xf00f9344u, 0xd6d6a3e8u, 0xcb61b38cu, 0x9b64c2b0u, 0x86d3d2d4u, 0xa00ae278u, 0xbdbdf21cu};
+  uint32_t c = 0xffffffffu;
+  for (uint32_t k = 0; k < n; ++k) {
+    c ^= p[k];
+    c = t[c & 15u] ^ (c >> 4);
+    c = t[c & 15u] ^ (c >> 4);
+  }
+  return c ^ 0xffffffffu;
+}
+
+}  // namespace mcov

@@ -288,6 +288,7 @@ void mcov_destroy(mcov_ctx* ctx) {
                     &ctx->d_tasks, &ctx->d_rlen, &ctx->d_rchunks, &ctx->d_rhist, &ctx->d_pool, &ctx->d_done,
                     &ctx->d_out, &ctx->d_win_slot, &ctx->d_win_n, &ctx->d_win_out, &ctx->d_htasks, &ctx->d_tile_heavy, &ctx->d_run_tasks, &ctx->d_run_counts, &ctx->d_run_out};
   for (DevBuf* b : bufs) b->release();
+  ctx->bam.release();
   ctx->h_pin.release();
   for (auto& sl : ctx->slot) {
     sl.buf.release(); sl.d_rec.release();
@@ -541,7 +542,18 @@ static const char* kKernelNames[kKernelCount] = {
     "k_expand", "k_scan_inplace", "k_fused_prep", "k_tile_first", "k_scan_counts", "k_far_scatter", "k_fused_tile",
     "k_init_region_stats", "k_region_stats", "k_window_sums", "k_isize_hist", "k_group_count", "k_sorted_stats",
     "memset_depth", "k_region_stats_small", "k_cap_replay", "k_unpack_reads", "k_kmer_hist", "k_region_stats_warp",
-    "k_exp_prep", "k_exp_entries", "k_exp_region", "k_exp_revsum", "k_region_hist", "k_hist_finish", "k_run_count", "k_run_offsets", "k_run_write", "k_run_ends"};
+    "k_exp_prep", "k_exp_entries", "k_exp_region", "k_exp_revsum", "k_region_hist", "k_hist_finish", "k_run_count", "k_run_offsets", "k_run_write", "k_run_ends",
+    "k_bgzf_inflate", "k_bam_guess", "k_bam_walk_count", "k_bam_walk_write"};
+
+int mcov_copy_to_host(mcov_ctx* ctx, const void* dev, void* host, int64_t n_bytes) {
+  if (!ctx) return MCOV_ERR_ARG;
+  if (n_bytes < 0 || (n_bytes > 0 && (!dev || !host))) return fail(ctx, MCOV_ERR_ARG, "mcov_copy_to_host: bad arguments");
+  if (n_bytes == 0) return MCOV_OK;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(host, dev, (size_t)n_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MCOV_OK;
+}
 
 int mcov_sync(mcov_ctx* ctx) {
   if (!ctx) return MCOV_ERR_ARG;

@@ -1,0 +1,104 @@
+"""BAM decode on the GPU (mcov_bam_decode_gpu: BGZF inflate + record chain + SoA columns) against the host
+decoder (mcov_bam_open / mcov_bam_load) on the same files: the fixture, short reads over many BGZF
+blocks, long reads whose records are larger than a 64 KiB chunk, stored (level 0) blocks, an empty file;
+corrupt files fail loudly; depth from the device-resident columns equals the oracle."""
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+from helpers import load_soa
+from oracle import bamio, cport
+
+pytestmark = pytest.mark.gpu
+
+COLS = ("tid", "pos", "flag", "mapq", "l_seq", "isize", "cig_off", "cig")
+
+
+def _write(tmp, name, refs, lengths, b, level=6, **kw):
+    path = str(tmp / name)
+    old = bamio._bgzf_block
+    if level != 6:
+        def blk(payload):
+            comp = zlib.compressobj(level, zlib.DEFLATED, -15)
+            cdata = comp.compress(payload) + comp.flush()
+            head = struct.pack("<BBBBIBBHBBHH", 0x1f, 0x8b, 8, 4, 0, 0, 0xff, 6, 66, 67, 2, len(cdata) + 25)
+            return head + cdata + struct.pack("<II", zlib.crc32(payload) & 0xFFFFFFFF, len(payload))
+        bamio._bgzf_block = blk
+    try:
+        bamio.write_bam(path, refs, [int(x) for x in lengths], b.tid, b.pos, b.flag, b.mapq, b.cig_off, b.cig, **kw)
+    finally:
+        bamio._bgzf_block = old
+    return path
+
+
+def _host_columns(path):
+    from metacov_b200 import AlignmentFile
+    with AlignmentFile(path) as bam:
+        s = bam.soa()                                       # views of the reader's arrays: copy before it closes
+        return {c: np.array(s[c]) for c in COLS}, list(bam.references), list(bam.lengths)
+
+
+def _check_file(path, lengths, batch=None):
+    from metacov_b200 import CoverageEngine, bamgpu
+    want, refs, lens = _host_columns(path)
+    with CoverageEngine(lengths) as eng:
+        soa = bamgpu.decode(eng, path)
+        assert soa.n_records == len(want["tid"]) and soa.n_cigar == len(want["cig"]) and soa.n_ref == len(refs)
+        for c in COLS:
+            assert np.array_equal(soa.to_host(c), np.asarray(want[c])), c
+        text, hrefs = soa.header()
+        assert [r for r, _ in hrefs] == [r.split()[0] for r in refs] and [l for _, l in hrefs] == lens
+        if batch is not None:
+            bamgpu.depth_sorted(eng, soa)
+            d, off, info = cport.depth(batch, lengths, mode="diff")
+            assert eng.pass_info()["n_pass"] == info["n_pass"]
+            for c in range(len(lengths)):
+                assert np.array_equal(eng.copy_depth(c), d[off[c]:off[c] + lengths[c]])
+        return soa.n_segments
+
+
+def test_fixture_and_multi_block_files(tmp_path):
+    from metacov_b200 import synth
+    z, b = load_soa("fixture_soa.npz")
+    so = z["seq_off"]
+    seqs = [z["seq"][so[i]:so[i + 1]] for i in range(len(b.tid))]
+    p = _write(tmp_path, "fixture.bam", [str(x) for x in z["references"]], z["lengths"], b, isize=z["isize"],
+               names=[str(x) for x in z["names"]], seqs=seqs)
+    _check_file(p, z["lengths"], b)
+    w = synth.c2(0.003)                                      # 30 000 reads: ~100 BGZF blocks / chunks
+    hb, isz = synth.generate_host(w)
+    refs = ["c%d" % c for c in range(w.n_contigs)]
+    for level in (6, 1, 0):                                  # dynamic Huffman, fast, stored blocks
+        p = _write(tmp_path, "c2_l%d.bam" % level, refs, w.contig_len, hb, level=level, isize=isz)
+        nseg = _check_file(p, w.contig_len, hb)
+        assert nseg > 20                                     # the record chain really was walked in parallel
+
+
+def test_long_records_span_chunks(tmp_path):
+    from metacov_b200 import synth
+    w = synth.c5(0.0005)                                     # 10-50 kb reads: records of 30-150 KB
+    hb, isz = synth.generate_host(w)
+    p = _write(tmp_path, "c5.bam", ["c%d" % c for c in range(w.n_contigs)], w.contig_len, hb, isize=isz)
+    _check_file(p, w.contig_len, hb)
+
+
+def test_empty_and_corrupt_files(tmp_path):
+    from metacov_b200 import CoverageEngine, McovError, ReadBatch, bamgpu
+    z, b = load_soa("fixture_soa.npz")
+    empty = ReadBatch(*(np.zeros(0, a.dtype) for a in (b.tid, b.pos, b.flag, b.mapq)), np.zeros(1, np.uint32), np.zeros(0, np.uint32))
+    p = _write(tmp_path, "empty.bam", ["ref1", "ref2"], [425, 575], empty)
+    with CoverageEngine([425, 575]) as eng:
+        soa = bamgpu.decode(eng, p)
+        assert soa.n_records == 0 and soa.n_ref == 2
+        good = _write(tmp_path, "good.bam", [str(x) for x in z["references"]], z["lengths"], b)
+        raw = bytearray(open(good, "rb").read())
+        bad = bytes(raw[:200]) + bytes([raw[200] ^ 0x5A]) + bytes(raw[201:])          # one payload byte flipped
+        with pytest.raises(McovError):
+            bamgpu.decode(eng, bad)
+        with pytest.raises(McovError):
+            bamgpu.decode(eng, bytes(raw[:len(raw) // 2]))                             # truncated file
+        with pytest.raises(McovError):
+            bamgpu.decode(eng, b"not a bam file at all" * 10)
+        assert bamgpu.decode(eng, bytes(raw)).n_records == len(b.tid)                  # the context survives errors

@@ -1,0 +1,95 @@
+#!/usr/bin/env python
+"""From the BAM FILE to per-base depth: host decode (mcov_bam_open/load: zlib on all host cores + serial
+record walk, then H2D of the SoA) against GPU decode (mcov_bam_decode_gpu: compressed image over PCIe,
+inflate + record chain + SoA on the device).  SURVEY.md 8(f) row 3.  Prints one JSON line.
+
+  python tools/bench_bam.py [--scale 0.2] [--reps 3]
+"""
+import argparse
+import json
+import os
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scale", type=float, default=0.2, help="fraction of config C2 (10 M reads) written to the BAM")
+    ap.add_argument("--reps", type=int, default=3)
+    args = ap.parse_args()
+    import torch
+    from metacov_b200 import AlignmentFile, CoverageEngine, bamgpu, synth
+    from oracle import bamio
+    w = synth.c2(args.scale)
+    hb, isz = synth.generate_host(w)
+    d = tempfile.mkdtemp()
+    path = os.path.join(d, "c2.bam")
+    t0 = time.perf_counter()
+    # random bases (nt16 codes of A C G T) so that the file compresses like sequence data, not like padding;
+    # l_seq follows the CIGAR-independent read length of the generator (150)
+    rng = np.random.Generator(np.random.PCG64(11))
+    big = np.array([1, 2, 4, 8], dtype=np.uint8)[rng.integers(0, 4, len(hb.tid) * 150, dtype=np.uint8)]
+    seqs = [big[i * 150:(i + 1) * 150] for i in range(len(hb.tid))]
+    bamio.write_bam(path, ["c%d" % c for c in range(w.n_contigs)], [int(x) for x in w.contig_len], hb.tid, hb.pos, hb.flag,
+                    hb.mapq, hb.cig_off, hb.cig, isize=isz, seqs=seqs)
+    del seqs, big
+    t_write = time.perf_counter() - t0
+    size = os.path.getsize(path)
+    n = len(hb.tid)
+    eng = CoverageEngine(w.contig_len)
+
+    def host_path():
+        t0 = time.perf_counter()
+        with AlignmentFile(path) as bam:
+            t1 = time.perf_counter()                 # file read + inflate (all host cores) + header
+            s = bam.soa()
+            t2 = time.perf_counter()                 # serial record walk -> SoA
+            from metacov_b200 import ReadBatch
+            eng.depth_sorted(ReadBatch(s["tid"], s["pos"], s["flag"], s["mapq"], s["cig_off"], s["cig"]))
+            t3 = time.perf_counter()                 # H2D of the SoA + kernels
+        return t1 - t0, t2 - t1, t3 - t2
+
+    def gpu_path(pinned):
+        t0 = time.perf_counter()
+        soa = bamgpu.decode(eng, pinned)
+        t1 = time.perf_counter()                     # H2D of the compressed image + inflate + record chain + SoA
+        bamgpu.depth_sorted(eng, soa)
+        t2 = time.perf_counter()
+        return t1 - t0, t2 - t1, soa
+
+    host = [host_path() for _ in range(args.reps)]
+    t0 = time.perf_counter()
+    raw = np.fromfile(path, dtype=np.uint8)
+    pinned = torch.from_numpy(raw).pin_memory()
+    t_read = time.perf_counter() - t0
+    gpu_path(pinned)
+    eng.profile(True)
+    gpu = [gpu_path(pinned)[:2] for _ in range(args.reps)]
+    kt = eng.profile_read()
+    eng.profile(False)
+    soa = gpu_path(pinned)[2]
+    best_h = min(host, key=sum)
+    best_g = min(gpu, key=sum)
+    kern = {k: v[1] / max(v[0], 1) for k, v in kt.items() if k.startswith("k_b")}
+    line = {
+        "what": "BAM file -> per-base depth", "reads": n, "bam_bytes": size, "inflated_bytes": int(soa.inflated_bytes),
+        "segments": int(soa.n_segments), "host_cores": os.cpu_count(),
+        "host_decode": {"open_inflate_s": best_h[0], "record_walk_s": best_h[1], "h2d_and_depth_s": best_h[2], "total_s": sum(best_h),
+                        "reads_per_s": n / sum(best_h)},
+        "gpu_decode": {"decode_s": best_g[0], "depth_s": best_g[1], "total_s": sum(best_g), "reads_per_s": n / sum(best_g),
+                       "file_read_and_pin_s": t_read, "kernel_ms": kern,
+                       "inflate_gbs_out": soa.inflated_bytes / (kern.get("k_bgzf_inflate", 0) or float("nan")) / 1e6},
+        "speedup_total": sum(best_h) / sum(best_g), "bam_write_s": t_write,
+    }
+    print(json.dumps(line))
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()
