@@ -354,6 +354,8 @@ const char* mcov_bam_header_text(const mcov_bam* b);
 /* BAI metadata pseudo-bin sums (pysam `.mapped` / `.unmapped`, cli.py:73-75);
  * returns MCOV_ERR_IO if there is no index next to the BAM. */
 int  mcov_bam_index_stats(const mcov_bam* b, int64_t* mapped, int64_t* unmapped);
+/* Same from the path of the .bam file (looks for <path>.bai, then <path minus .bam>.bai). */
+int  mcov_bai_stats(const char* bam_path, int64_t* mapped, int64_t* unmapped);
 /* Decode the whole file (every record, like IteratorRowAll scan.pyx:204) into
  * SoA arrays owned by the handle; pointers stay valid until close. */
 int  mcov_bam_load(mcov_bam* b, int n_threads);
@@ -413,6 +415,7 @@ int  mcov_bam_decode_gpu(mcov_ctx* ctx, const void* file_bytes, int64_t n_bytes,
  * suite can check it against zlib.  mcov_inflate_host returns 0 or a positive decoder status. */
 int  mcov_inflate_host(const uint8_t* src, uint32_t clen, uint8_t* dst, uint32_t ulen);
 uint32_t mcov_crc32_host(const uint8_t* p, uint32_t n);
+uint32_t mcov_crc32_sliced_host(const uint8_t* p, uint32_t n, int nlanes);   /* the warp's lane-sliced CRC, folded on the host */
 
 /* n_cigar of reads [i0, i0+n) -> out[n] (host or device memory per mem_kind;
  * device work is enqueued on `stream`, a cudaStream_t or NULL). */

@@ -116,6 +116,7 @@ SIGNATURES = {
     "mcov_bam_decode_gpu": (C.c_int, [_vp, _vp, C.c_int64, C.c_int, _vp]),
     "mcov_inflate_host": (C.c_int, [_vp, C.c_uint32, _vp, C.c_uint32]),
     "mcov_crc32_host": (C.c_uint32, [_vp, C.c_uint32]),
+    "mcov_crc32_sliced_host": (C.c_uint32, [_vp, C.c_uint32, C.c_int]),
     "mcov_depth_runs": (C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]),
     "mcov_depth_runs_read": (C.c_int, [_vp, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp]),
     "mcov_region_hist_enqueue": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp]),
@@ -145,6 +146,7 @@ SIGNATURES = {
     "mcov_bam_ref_len": (_i32, [_vp, _i32]),
     "mcov_bam_header_text": (C.c_char_p, [_vp]),
     "mcov_bam_index_stats": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
+    "mcov_bai_stats": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mcov_bam_load": (C.c_int, [_vp, C.c_int]),
     "mcov_bam_n_records": (_i64, [_vp]),
     "mcov_bam_n_cigar": (_i64, [_vp]),

@@ -39,10 +39,56 @@ class PileupColumn:
 
 
 class AlignmentFile:
-    def __init__(self, filename, mode="rb", device=0, **kw):
+    def __init__(self, filename, mode="rb", device=0, decode="host", **kw):
+        """decode="host": BGZF inflate and record parsing by the native host reader (csrc/bamio.cpp);
+        decode="gpu": the compressed file goes to the device and is inflated and parsed there
+        (csrc/bam_gpu.cu) -- the coverage path then never holds the records on the host."""
         if "w" in mode:
             raise ValueError("metacov_b200.AlignmentFile is read-only")
+        if decode not in ("host", "gpu"):
+            raise ValueError("decode must be 'host' or 'gpu'")
         self.filename = filename
+        self._gpu = None
+        self._device = device
+        self._soa = None
+        self._engine = None
+        self._filter_kw = None
+        self._index_stats = None
+        if decode == "gpu":
+            self._open_gpu(filename, device)
+            return
+        self._open_host(filename)
+
+    def _open_gpu(self, filename, device):
+        from . import bamgpu
+        self._h = None
+        eng = CoverageEngine([1], device=device)            # the contig table follows once the header is decoded
+        try:
+            with open(filename, "rb") as fh:
+                image = fh.read()
+            dsoa = bamgpu.decode(eng, image)
+            self.text, refs = dsoa.header()
+        except McovError as e:
+            eng.close()
+            raise OSError("%s: %s" % (filename, e))
+        except BaseException:
+            eng.close()
+            raise
+        self.references = tuple(r for r, _ in refs)
+        self.lengths = tuple(l for _, l in refs)
+        self.nreferences = len(refs)
+        self._tid = {name: i for i, name in enumerate(self.references)}
+        eng.set_contigs(self.lengths)
+        self._gpu = (eng, dsoa)
+
+    def _host_handle(self):
+        """The host reader's handle; a GPU-decoded file opens it on first use (read names and sequences --
+        the k-mer histogram and `experimental` -- still come from the host reader)."""
+        if self._h is None:
+            self._open_host(self.filename, header=False)
+        return self._h
+
+    def _open_host(self, filename, header=True):
         self._h = C.c_void_p()
         err = C.create_string_buffer(256)
         rc = lib.mcov_bam_open(C.byref(self._h), str(filename).encode(), err, len(err))
@@ -50,23 +96,23 @@ class AlignmentFile:
             self._h = None
             # pysam raises OSError/ValueError for unreadable files
             raise OSError("%s: %s" % (filename, err.value.decode()))
+        if not header:
+            return
         n = lib.mcov_bam_n_ref(self._h)
         self.references = tuple(lib.mcov_bam_ref_name(self._h, i).decode() for i in range(n))
         self.lengths = tuple(lib.mcov_bam_ref_len(self._h, i) for i in range(n))
         self.nreferences = n
         self.text = lib.mcov_bam_header_text(self._h).decode()
         self._tid = {name: i for i, name in enumerate(self.references)}
-        self._device = device
-        self._soa = None
-        self._engine = None
-        self._filter_kw = None
-        self._index_stats = None
 
     # -- lifetime ---------------------------------------------------------
     def close(self):
         if getattr(self, "_engine", None) is not None:
             self._engine.close()
             self._engine = None
+        if getattr(self, "_gpu", None) is not None:
+            self._gpu[0].close()                            # (the same engine, if the depth was computed)
+            self._gpu = None
         if getattr(self, "_h", None):
             lib.mcov_bam_close(self._h)
             self._h = None
@@ -91,7 +137,7 @@ class AlignmentFile:
     def _idx(self):
         if self._index_stats is None:
             m, u = C.c_int64(0), C.c_int64(0)
-            rc = lib.mcov_bam_index_stats(self._h, C.byref(m), C.byref(u))
+            rc = lib.mcov_bai_stats(str(self.filename).encode(), C.byref(m), C.byref(u))
             if rc != 0:
                 raise ValueError("mapping information not recorded in index or index not available")
             self._index_stats = (m.value, u.value)
@@ -116,6 +162,8 @@ class AlignmentFile:
     def soa(self):
         """Every record of the file as SoA numpy views (file order; the arrays
         the reference reads field by field at scan.pyx:243-294)."""
+        if self._soa is None and self._gpu is not None:
+            self._soa = {c: self._gpu[1].to_host(c) for c, _ in self._gpu[1].COLS}
         if self._soa is None:
             rc = lib.mcov_bam_load(self._h, 0)
             if rc != 0:
@@ -138,11 +186,11 @@ class AlignmentFile:
         """uint8[n, (win_bases+1)//2]: per read the first (forward) / last (reverse) win_bases bases,
         nt16 two per byte -- the part of SEQ the k-mer histogram looks at."""
         n = len(self.soa()["tid"])
-        rc = lib.mcov_bam_load_seq(self._h)
+        rc = lib.mcov_bam_load_seq(self._host_handle())
         if rc != 0:
             raise McovError(rc, "BAM SEQ decode failed")
         out = np.empty((n, (win_bases + 1) // 2), dtype=np.uint8)
-        rc = lib.mcov_bam_seq_windows(self._h, int(win_bases), _capi.ptr(out))
+        rc = lib.mcov_bam_seq_windows(self._host_handle(), int(win_bases), _capi.ptr(out))
         if rc != 0:
             raise McovError(rc, "mcov_bam_seq_windows failed")
         return out
@@ -154,19 +202,19 @@ class AlignmentFile:
     def name_hashes(self):
         """uint64[n]: FNV-1a of every read name (the key of the reference's mate dict, pileup.py:101)."""
         n = len(self.soa()["tid"])
-        rc = lib.mcov_bam_load_seq(self._h)
+        rc = lib.mcov_bam_load_seq(self._host_handle())
         if rc != 0:
             raise McovError(rc, "BAM SEQ decode failed")
-        return _view(lib.mcov_bam_name_hash(self._h), n, np.uint64)
+        return _view(lib.mcov_bam_name_hash(self._host_handle()), n, np.uint64)
 
     def qas_kmer_codes(self, k_len):
         """int32[n]: code of ``read.query_alignment_sequence[0:k_len]`` (pileup.py:109, 123), -1 = no key."""
         n = len(self.soa()["tid"])
-        rc = lib.mcov_bam_load_seq(self._h)
+        rc = lib.mcov_bam_load_seq(self._host_handle())
         if rc != 0:
             raise McovError(rc, "BAM SEQ decode failed")
         out = np.empty(n, dtype=np.int32)
-        rc = lib.mcov_bam_qas_kmer(self._h, int(k_len), _capi.ptr(out))
+        rc = lib.mcov_bam_qas_kmer(self._host_handle(), int(k_len), _capi.ptr(out))
         if rc != 0:
             raise McovError(rc, "mcov_bam_qas_kmer failed")
         return out
@@ -225,21 +273,26 @@ class AlignmentFile:
         min_mapq, ignore_orphans, max_depth); invalidates the cached depth."""
         self._filter_kw = kw
         if self._engine is not None:
-            self._engine.close()
+            if self._gpu is None:
+                self._engine.close()                        # (a GPU-decoded file keeps its engine: it owns the columns)
             self._engine = None
 
     def coverage_engine(self):
         """The per-base depth of the whole file, computed once on the GPU."""
-        if self._engine is None:
+        if self._engine is None and self._gpu is not None:
+            eng, path = self._gpu_depth()
+        elif self._engine is None:
             s = self.soa()
             eng = CoverageEngine(self.lengths, device=self._device, filt=self._filter_kw)
             path = eng.compute_depth(ReadBatch(s["tid"], s["pos"], s["flag"], s["mapq"], s["cig_off"], s["cig"]))
+        if self._engine is None:
             info = eng.pass_info()
             md = eng.filter.max_depth
             # the fused (sorted) path replays htslib's cap exactly on the GPU; the any-order path cannot
             # (the cap is only defined for sorted input), so it refuses rather than return uncapped numbers
             if path != "fused" and md > 0 and info["cap_metric"] > md:
-                eng.close()
+                if self._gpu is None:
+                    eng.close()
                 from .pileup import DepthCapError
                 raise DepthCapError(
                     "depth[p-1]+starts[p] reaches %d > max_depth=%d: htslib's pileup would drop reads here "
@@ -247,6 +300,24 @@ class AlignmentFile:
                     % (info["cap_metric"], md))
             self._engine = eng
         return self._engine
+
+    def _gpu_depth(self):
+        """Depth straight from the device-resident columns of a GPU-decoded file."""
+        from . import bamgpu
+        eng, dsoa = self._gpu
+        if self._filter_kw:
+            eng.set_filter(**self._filter_kw)
+        try:
+            bamgpu.depth_sorted(eng, dsoa)
+            return eng, "fused"
+        except McovError as e:
+            if e.code not in (_capi.MCOV_ERR_UNSORTED, _capi.MCOV_ERR_RANGE):
+                raise
+        r = dsoa.raw
+        eng.begin()
+        eng._check(lib.mcov_push_reads(eng._ctx, dsoa.n_records, r.tid, r.pos, r.flag, r.mapq, r.cig_off, r.cig, _capi.MEM_DEVICE))
+        eng.finalize()
+        return eng, "push"
 
     def pileup(self, contig=None, start=None, stop=None, **kw):
         """Columns with n > 0 inside [start, stop) (pysam also emits columns

@@ -48,14 +48,16 @@ def main():
 @click.option("--window", "-w", type=click.IntRange(1), metavar="N",
               help="Also write the mean depth of fixed windows of N bp to --window-out. Not in the reference: additive.")
 @click.option("--window-out", "-wo", type=click.File("w"), metavar="FILE", help="Output CSV of --window (sacc,start,end,avg)")
+@click.option("--bam-decode", type=click.Choice(["host", "gpu"]), default="host", show_default=True,
+              help="Where the BAM file is inflated and parsed: host threads (zlib) or the GPU. Not in the reference: additive.")
 def pileup(bamfile, reference_fasta, regionfile_blast7, regionfile_csv, kmer_histogram, kmer_length, outfile,
-           bedgraph=None, window=None, window_out=None):
+           bedgraph=None, window=None, window_out=None, bam_decode="host"):
     """
     Compute fold coverage values
     """
     if (window is None) != (window_out is None):
         raise click.UsageError("--window and --window-out go together")
-    bam = AlignmentFile(bamfile.name)
+    bam = AlignmentFile(bamfile.name, decode=bam_decode)
     fasta = FastaFile(reference_fasta.name) if reference_fasta else None          # cli.py:59
     regions = util.make_region_iterator(regionfile_blast7, regionfile_csv, bam)
     try:

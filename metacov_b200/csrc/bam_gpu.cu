@@ -47,10 +47,21 @@ k_bgzf_inflate(const uint8_t* __restrict__ raw, const BgzfBlock* __restrict__ bl
   if (k >= n_blocks) return;
   const BgzfBlock b = blocks[k];
   int rc = b.ulen ? inflate_raw(raw + b.coff, b.clen, out + b.uoff, b.ulen, lane, 32) : 0;
-  if (lane == 0) {
-    if (rc == 0 && verify_crc && b.ulen && crc32_bytes(out + b.uoff, b.ulen) != b.crc) rc = 100;
-    if (rc) { atomicCAS(status, 0, rc); atomicMax(status + 1, (int)min(k, (int64_t)0x7fffffff)); }   // first error code, a failing block
+  if (rc == 0 && verify_crc && b.ulen) {
+    // lane-sliced CRC-32, folded left to right (inflate.cuh)
+    uint32_t lo, hi;
+    crc_slice(b.ulen, lane, 32, lo, hi);
+    const uint32_t mine = crc32_bytes(out + b.uoff + lo, hi - lo);
+    const uint32_t op_full = crc_x8n(hi - lo);                  // (lanes with a full slice all compute the same factor)
+    uint32_t crc = __shfl_sync(0xffffffffu, mine, 0);
+    for (int j = 1; j < 32; ++j) {
+      const uint32_t cj = __shfl_sync(0xffffffffu, mine, j), opj = __shfl_sync(0xffffffffu, op_full, j);
+      const uint32_t nj = __shfl_sync(0xffffffffu, hi - lo, j);
+      if (nj) crc = crc_multmodp(opj, crc) ^ cj;
+    }
+    if (crc != b.crc) rc = 100;
   }
+  if (lane == 0 && rc) { atomicCAS(status, 0, rc); atomicMax(status + 1, (int)min(k, (int64_t)0x7fffffff)); }   // first error code, a failing block
 }
 
 __device__ __forceinline__ uint32_t ld32u(const uint8_t* p) {
@@ -354,3 +365,4 @@ extern "C" int mcov_inflate_host(const uint8_t* src, uint32_t clen, uint8_t* dst
   return inflate_raw(src, clen, dst, ulen);
 }
 extern "C" uint32_t mcov_crc32_host(const uint8_t* p, uint32_t n) { return crc32_bytes(p, n); }
+extern "C" uint32_t mcov_crc32_sliced_host(const uint8_t* p, uint32_t n, int nlanes) { return crc32_sliced_host(p, n, nlanes < 1 ? 1 : nlanes); }

@@ -197,8 +197,14 @@ int32_t mcov_bam_ref_len(const mcov_bam* b, int32_t tid) {
 const char* mcov_bam_header_text(const mcov_bam* b) { return b ? b->text.c_str() : nullptr; }
 
 int mcov_bam_index_stats(const mcov_bam* b, int64_t* mapped, int64_t* unmapped) {
-  if (!b || !mapped || !unmapped) return MCOV_ERR_ARG;
-  std::string cand[2] = {b->path + ".bai", b->path};
+  if (!b) return MCOV_ERR_ARG;
+  return mcov_bai_stats(b->path.c_str(), mapped, unmapped);
+}
+
+int mcov_bai_stats(const char* bam_path, int64_t* mapped, int64_t* unmapped) {
+  if (!bam_path || !mapped || !unmapped) return MCOV_ERR_ARG;
+  const std::string path(bam_path);
+  std::string cand[2] = {path + ".bai", path};
   if (cand[1].size() > 4 && cand[1].compare(cand[1].size() - 4, 4, ".bam") == 0) cand[1].replace(cand[1].size() - 4, 4, ".bai");
   FILE* fh = nullptr;
   for (auto& c : cand) { fh = std::fopen(c.c_str(), "rb"); if (fh) break; }

@@ -78,6 +78,12 @@ class CoverageEngine:
         self._keep = None
         self._pinned = None
 
+    def set_contigs(self, lengths):
+        """Replace the contig table (any depth computed so far is dropped)."""
+        self.lengths = np.ascontiguousarray(lengths, dtype=np.int32)
+        self._check(lib.mcov_set_contigs(self._ctx, len(self.lengths), _capi.ptr(self.lengths)))
+        self.n_slots = lib.mcov_n_slots(self._ctx)
+
     # -- plumbing ---------------------------------------------------------
     def _check(self, rc):
         if rc != 0:

@@ -102,3 +102,42 @@ def test_empty_and_corrupt_files(tmp_path):
         with pytest.raises(McovError):
             bamgpu.decode(eng, b"not a bam file at all" * 10)
         assert bamgpu.decode(eng, bytes(raw)).n_records == len(b.tid)                  # the context survives errors
+
+
+def test_alignmentfile_and_cli_with_gpu_decode(tmp_path):
+    """AlignmentFile(decode="gpu") answers exactly like the host-decoded file: header, index statistics,
+    classic() of the golden regions, the pileup() protocol, the records; `metacov pileup --bam-decode gpu`
+    writes the same CSV."""
+    from click.testing import CliRunner
+    from helpers import load_json
+    from metacov_b200 import AlignmentFile, pileup
+    from metacov_b200.cli import pileup as cli_pileup
+    z, b = load_soa("fixture_soa.npz")
+    so = z["seq_off"]
+    seqs = [z["seq"][so[i]:so[i + 1]] for i in range(len(b.tid))]
+    p = _write(tmp_path, "fixture.bam", [str(x) for x in z["references"]], z["lengths"], b, isize=z["isize"],
+               names=[str(x) for x in z["names"]], seqs=seqs)
+    gold = load_json("fixture_classic.json")
+    with AlignmentFile(p) as host, AlignmentFile(p, decode="gpu") as gpu:
+        assert gpu.references == host.references and gpu.lengths == host.lengths and gpu.text == host.text
+        assert (gpu.mapped, gpu.unmapped) == (host.mapped, host.unmapped) == (gold["mapped"], gold["unmapped"])
+        for row in gold["classic"]:
+            assert pileup.classic(gpu, row["ref"], row["start"], row["end"]) == row["result"], row
+        assert [(c.pos, c.n) for c in gpu.pileup("ref1", 0, 425)] == [(c.pos, c.n) for c in host.pileup("ref1", 0, 425)]
+        hs, gs = host.soa(), gpu.soa()
+        for c in COLS:
+            assert np.array_equal(hs[c], gs[c]), c
+        # read names / sequences come from the host reader on demand
+        assert np.array_equal(gpu.name_hashes(), host.name_hashes())
+        gpu.set_pileup_filter(min_mapq=20)
+        host.set_pileup_filter(min_mapq=20)
+        assert pileup.classic(gpu, "ref1", 0, 425) == pileup.classic(host, "ref1", 0, 425)
+    outs = []
+    for mode in ("host", "gpu"):
+        out = tmp_path / ("cov_%s.csv" % mode)
+        res = CliRunner().invoke(cli_pileup, ["-b", p, "-o", str(out), "--bam-decode", mode])
+        assert res.exit_code == 0, res.output
+        outs.append(out.read_text())
+    assert outs[0] == outs[1] and len(outs[0].splitlines()) == 3
+    with pytest.raises(OSError):
+        AlignmentFile(str(tmp_path / "fixture.bam.bai"), decode="gpu")          # not a BGZF file

@@ -38,6 +38,9 @@ def test_inflate_matches_zlib_on_every_block_type():
                 assert rc == 0 and out == data, (len(data), level, strat, rc)
         buf = np.frombuffer(data, dtype=np.uint8) if data else np.zeros(1, np.uint8)
         assert _capi.lib.mcov_crc32_host(buf.ctypes.data, len(data)) == (zlib.crc32(data) & 0xFFFFFFFF)
+        for lanes in (1, 2, 7, 32):                                     # the warp's lane-sliced CRC fold
+            for n in {len(data), min(len(data), 31), min(len(data), 33), min(len(data), 4097)}:
+                assert _capi.lib.mcov_crc32_sliced_host(buf.ctypes.data, n, lanes) == (zlib.crc32(data[:n]) & 0xFFFFFFFF), (lanes, n)
 
 
 def test_inflate_rejects_bad_streams():

@@ -55,9 +55,9 @@ def main():
             t3 = time.perf_counter()                 # H2D of the SoA + kernels
         return t1 - t0, t2 - t1, t3 - t2
 
-    def gpu_path(pinned):
+    def gpu_path(pinned, crc=True):
         t0 = time.perf_counter()
-        soa = bamgpu.decode(eng, pinned)
+        soa = bamgpu.decode(eng, pinned, verify_crc=crc)
         t1 = time.perf_counter()                     # H2D of the compressed image + inflate + record chain + SoA
         bamgpu.depth_sorted(eng, soa)
         t2 = time.perf_counter()
@@ -74,6 +74,7 @@ def main():
     kt = eng.profile_read()
     eng.profile(False)
     soa = gpu_path(pinned)[2]
+    nocrc = min((gpu_path(pinned, crc=False)[:2] for _ in range(args.reps)), key=sum)
     best_h = min(host, key=sum)
     best_g = min(gpu, key=sum)
     kern = {k: v[1] / max(v[0], 1) for k, v in kt.items() if k.startswith("k_b")}
@@ -83,7 +84,7 @@ def main():
         "host_decode": {"open_inflate_s": best_h[0], "record_walk_s": best_h[1], "h2d_and_depth_s": best_h[2], "total_s": sum(best_h),
                         "reads_per_s": n / sum(best_h)},
         "gpu_decode": {"decode_s": best_g[0], "depth_s": best_g[1], "total_s": sum(best_g), "reads_per_s": n / sum(best_g),
-                       "file_read_and_pin_s": t_read, "kernel_ms": kern,
+                       "decode_s_without_crc_check": nocrc[0], "file_read_and_pin_s": t_read, "kernel_ms": kern,
                        "inflate_gbs_out": soa.inflated_bytes / (kern.get("k_bgzf_inflate", 0) or float("nan")) / 1e6},
         "speedup_total": sum(best_h) / sum(best_g), "bam_write_s": t_write,
     }
