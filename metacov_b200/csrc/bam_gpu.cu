@@ -39,7 +39,10 @@ constexpr int kInflateThreads = 128;          // 4 warps = 4 BGZF blocks per CTA
 constexpr uint32_t kGuessChunk = 65536;
 constexpr int kGuessChain = 3;
 
-__global__ void __launch_bounds__(kInflateThreads)
+#ifndef MCOV_INFLATE_MIN_CTAS
+#define MCOV_INFLATE_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(kInflateThreads, MCOV_INFLATE_MIN_CTAS)
 k_bgzf_inflate(const uint8_t* __restrict__ raw, const BgzfBlock* __restrict__ blocks, int64_t n_blocks, uint8_t* out,
                int verify_crc, int* __restrict__ status) {
   const int64_t k = ((int64_t)blockIdx.x * kInflateThreads + threadIdx.x) >> 5;      // one warp per block

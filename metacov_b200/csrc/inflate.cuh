@@ -10,6 +10,8 @@
 // zlib's contrib/puff) -- no lookup tables, ~1.4 KB of per-lane local memory, no shared state.  Every loop
 // consumes input or produces output and both are bounded, so malformed data ends in an error code,
 // never in a hang.  On the host the same code runs with one "lane".
+// (Measured on B200, 4 173 blocks of a 1 M-read BAM: 19.5 ms as written; with count[] packed into
+// registers and the 15-step decode loop unrolled 46 ms at 111 registers, 30 ms capped at 64.)
 //
 // The same source compiles for the host: mcov_inflate_host() lets the CPU test suite check the decoder
 // against zlib without a GPU.
