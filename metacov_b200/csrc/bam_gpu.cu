@@ -45,11 +45,12 @@ constexpr int kGuessChain = 3;
 __global__ void __launch_bounds__(kInflateThreads, MCOV_INFLATE_MIN_CTAS)
 k_bgzf_inflate(const uint8_t* __restrict__ raw, const BgzfBlock* __restrict__ blocks, int64_t n_blocks, uint8_t* out,
                int verify_crc, int* __restrict__ status) {
+  __shared__ uint16_t s_tabs[kInflateThreads / 32][kInfTabWords];                      // first-level Huffman tables, one set per warp
   const int64_t k = ((int64_t)blockIdx.x * kInflateThreads + threadIdx.x) >> 5;      // one warp per block
   const int lane = threadIdx.x & 31;
   if (k >= n_blocks) return;
   const BgzfBlock b = blocks[k];
-  int rc = b.ulen ? inflate_raw(raw + b.coff, b.clen, out + b.uoff, b.ulen, lane, 32) : 0;
+  int rc = b.ulen ? inflate_raw(raw + b.coff, b.clen, out + b.uoff, b.ulen, s_tabs[threadIdx.x >> 5], lane, 32) : 0;
   if (rc == 0 && verify_crc && b.ulen) {
     // lane-sliced CRC-32, folded left to right (inflate.cuh)
     uint32_t lo, hi;
@@ -365,7 +366,8 @@ extern "C" int mcov_bam_decode_gpu(mcov_ctx* ctx, const void* file_bytes, int64_
 // without a GPU (test hooks, not a product path).
 extern "C" int mcov_inflate_host(const uint8_t* src, uint32_t clen, uint8_t* dst, uint32_t ulen) {
   if ((!src && clen) || (!dst && ulen)) return -1;
-  return inflate_raw(src, clen, dst, ulen);
+  uint16_t tabs[kInfTabWords];
+  return inflate_raw(src, clen, dst, ulen, tabs);
 }
 extern "C" uint32_t mcov_crc32_host(const uint8_t* p, uint32_t n) { return crc32_bytes(p, n); }
 extern "C" uint32_t mcov_crc32_sliced_host(const uint8_t* p, uint32_t n, int nlanes) { return crc32_sliced_host(p, n, nlanes < 1 ? 1 : nlanes); }

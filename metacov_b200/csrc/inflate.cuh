@@ -43,21 +43,32 @@ struct InfBits {
   const uint8_t* in;
   uint32_t n, p;
   uint64_t buf;
-  int cnt;
-  bool over;
+  int cnt;        // bits in buf
+  int pad;        // how many of them (the most significant ones) are padding past the end of the input
+  bool over;      // padding was CONSUMED: the stream is truncated
 };
 
-MCOV_HD uint32_t inf_bits(InfBits& r, int need) {
+MCOV_HD void inf_need(InfBits& r, int need) {                  // make at least `need` (<= 32) bits available
   while (r.cnt < need) {
     uint64_t b = 0;
-    if (r.p < r.n) b = r.in[r.p]; else r.over = true;
+    if (r.p < r.n) b = r.in[r.p]; else r.pad += 8;
     ++r.p;
     r.buf |= b << r.cnt;
     r.cnt += 8;
   }
-  const uint32_t v = (uint32_t)(r.buf & ((1ull << need) - 1ull));
-  r.buf >>= need;
-  r.cnt -= need;
+}
+MCOV_HD uint32_t inf_peek(InfBits& r, int k) {
+  inf_need(r, k);
+  return (uint32_t)(r.buf & ((1ull << k) - 1ull));
+}
+MCOV_HD void inf_drop(InfBits& r, int k) {
+  r.buf >>= k;
+  r.cnt -= k;
+  if (r.cnt < r.pad) r.over = true;
+}
+MCOV_HD uint32_t inf_bits(InfBits& r, int need) {
+  const uint32_t v = inf_peek(r, need);
+  inf_drop(r, need);
   return v;
 }
 
@@ -99,6 +110,39 @@ MCOV_HD int inf_decode(InfBits& r, const InfHuff& h) {
   return -1;
 }
 
+// First-level lookup tables: the next kLitBits (kDistBits) bits of the stream index an entry
+// (symbol << 4 | code length) for every code of at most that many bits -- one lookup per symbol instead of
+// one step per bit; longer (rare) codes have entry 0 and take the canonical walk above.  Built by the lanes
+// together: the codes of one length are consecutive in symbol[] (canonical order), entry index = the
+// bit-reversed code with every combination of the remaining high bits.
+constexpr int kLitBits = 9, kDistBits = 6;
+constexpr int kInfTabWords = (1 << kLitBits) + (1 << kDistBits);
+
+MCOV_HD void inf_build_fast(const InfHuff& h, uint16_t* tab, int P, int lane, int nlanes) {
+  for (int i = lane; i < (1 << P); i += nlanes) tab[i] = 0;
+  MCOV_INF_SYNC();
+  int code = 0, base = 0;
+  for (int len = 1; len <= P; ++len) {
+    code = (code + h.count[len - 1] * (len > 1 ? 1 : 0)) << 1;   // first code of this length (count[0] does not enter)
+    const int cnt = h.count[len];
+    for (int t = lane; t < cnt; t += nlanes) {
+      const int c = code + t;
+      int rc = 0;
+      for (int b = 0; b < len; ++b) rc |= ((c >> b) & 1) << (len - 1 - b);
+      const uint16_t e = (uint16_t)((h.symbol[base + t] << 4) | len);
+      for (int i = rc; i < (1 << P); i += (1 << len)) tab[i] = e;
+    }
+    base += cnt;
+  }
+  MCOV_INF_SYNC();
+}
+
+MCOV_HD int inf_decode_fast(InfBits& r, const InfHuff& h, const uint16_t* tab, int P) {
+  const uint32_t e = tab[inf_peek(r, P)];
+  if (e & 15u) { inf_drop(r, (int)(e & 15u)); return (int)(e >> 4); }
+  return inf_decode(r, h);
+}
+
 // length / distance base values and extra bits of RFC 1951 3.2.5 in closed form (no tables in local memory)
 MCOV_HD int inf_len_extra(int s) { return (s < 8 || s == 28) ? 0 : ((s - 4) >> 2); }
 MCOV_HD int inf_len_base(int s) { return s < 8 ? 3 + s : (s == 28 ? 258 : 3 + ((4 + (s & 3)) << ((s - 4) >> 2))); }
@@ -108,9 +152,12 @@ MCOV_HD int inf_dist_base(int s) { return s < 4 ? 1 + s : 1 + ((2 + (s & 1)) << 
 // Inflate one raw deflate stream of clen bytes into exactly ulen bytes.  Returns an InflateStatus.
 // Called by `nlanes` cooperating lanes (a warp, or 1 on the host) with identical arguments except `lane`;
 // every lane returns the same status.
-MCOV_HD int inflate_raw(const uint8_t* src, uint32_t clen, uint8_t* dst, uint32_t ulen, int lane = 0, int nlanes = 1) {
+MCOV_HD int inflate_raw(const uint8_t* src, uint32_t clen, uint8_t* dst, uint32_t ulen, uint16_t* tabs /* kInfTabWords, shared by the lanes */,
+                        int lane = 0, int nlanes = 1) {
   InfBits r;
-  r.in = src; r.n = clen; r.p = 0; r.buf = 0; r.cnt = 0; r.over = false;
+  r.in = src; r.n = clen; r.p = 0; r.buf = 0; r.cnt = 0; r.pad = 0; r.over = false;
+  uint16_t* ltab = tabs;
+  uint16_t* dtab = tabs + (1 << kLitBits);
   int16_t lengths[320];
   int16_t lensym[288], distsym[30];
   InfHuff lencode, distcode;
@@ -182,9 +229,11 @@ MCOV_HD int inflate_raw(const uint8_t* src, uint32_t clen, uint8_t* dst, uint32_
       err = inf_construct(distcode, lengths + nlen, ndist);
       if (err < 0 || (err > 0 && ndist - distcode.count[0] != 1)) return kInfBadCodeLengths;
     }
+    inf_build_fast(lencode, ltab, kLitBits, lane, nlanes);
+    inf_build_fast(distcode, dtab, kDistBits, lane, nlanes);
     // literal/length + distance symbols until end-of-block
     for (;;) {
-      int sym = inf_decode(r, lencode);
+      int sym = inf_decode_fast(r, lencode, ltab, kLitBits);
       if (sym < 0) return kInfBadSymbol;
       if (r.over) return kInfInputOverrun;
       if (sym < 256) {
@@ -197,7 +246,7 @@ MCOV_HD int inflate_raw(const uint8_t* src, uint32_t clen, uint8_t* dst, uint32_
         sym -= 257;
         if (sym >= 29) return kInfBadSymbol;
         const uint32_t len = (uint32_t)inf_len_base(sym) + inf_bits(r, inf_len_extra(sym));
-        const int ds = inf_decode(r, distcode);
+        const int ds = inf_decode_fast(r, distcode, dtab, kDistBits);
         if (ds < 0 || ds >= 30) return kInfBadSymbol;
         const uint32_t dist = (uint32_t)inf_dist_base(ds) + inf_bits(r, inf_dist_extra(ds));
         if (r.over) return kInfInputOverrun;
