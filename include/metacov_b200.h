@@ -414,6 +414,7 @@ int  mcov_bam_decode_gpu(mcov_ctx* ctx, const void* file_bytes, int64_t n_bytes,
 /* Test hooks: the device inflate / CRC-32 code (csrc/inflate.cuh) compiled for the host, so that the CPU
  * suite can check it against zlib.  mcov_inflate_host returns 0 or a positive decoder status. */
 int  mcov_inflate_host(const uint8_t* src, uint32_t clen, uint8_t* dst, uint32_t ulen);
+int  mcov_inflate_host_win(const uint8_t* src, uint32_t clen, uint8_t* dst, uint32_t ulen, uint32_t window);   /* with the circular output window the GPU keeps in shared memory */
 uint32_t mcov_crc32_host(const uint8_t* p, uint32_t n);
 uint32_t mcov_crc32_sliced_host(const uint8_t* p, uint32_t n, int nlanes);   /* the warp's lane-sliced CRC, folded on the host */
 

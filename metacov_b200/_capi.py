@@ -115,6 +115,7 @@ SIGNATURES = {
     "mcov_copy_to_host": (C.c_int, [_vp, _vp, _vp, C.c_int64]),
     "mcov_bam_decode_gpu": (C.c_int, [_vp, _vp, C.c_int64, C.c_int, _vp]),
     "mcov_inflate_host": (C.c_int, [_vp, C.c_uint32, _vp, C.c_uint32]),
+    "mcov_inflate_host_win": (C.c_int, [_vp, C.c_uint32, _vp, C.c_uint32, C.c_uint32]),
     "mcov_crc32_host": (C.c_uint32, [_vp, C.c_uint32]),
     "mcov_crc32_sliced_host": (C.c_uint32, [_vp, C.c_uint32, C.c_int]),
     "mcov_depth_runs": (C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]),

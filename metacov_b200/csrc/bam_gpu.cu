@@ -5,6 +5,11 @@
 // 10 M reads the kernels finish in 0.2 ms).  Here the COMPRESSED file goes over PCIe (3-4x fewer bytes
 // than the SoA) and everything else happens on the device:
 //
+//   (inflate, B200, 4 173 blocks of a 1 M-read BAM: thread per block 127 ms; warp per block with lane-parallel
+//   match copies 19.5 ms; + first-level Huffman tables 17.1 ms; + shared-memory output window of 16 / 8 / 4 / 2 KiB
+//   25.6 / 19.1 / 13.0 / 11.6 ms -- the kernel is bound by instruction issue of the redundant symbol decode, so
+//   resident warps matter more than the window size)
+//
 //   k_bgzf_inflate     one warp per BGZF block (independent raw-deflate streams of <= 64 KiB, SAM spec
 //                      4.1; inflate.cuh: redundant symbol decode, lane-parallel match copies), optional
 //                      CRC-32 check
@@ -35,22 +40,26 @@ namespace mcov {
 
 struct BgzfBlock { uint64_t coff; uint64_t uoff; uint32_t clen; uint32_t ulen; uint32_t crc; uint32_t pad; };
 
-constexpr int kInflateThreads = 128;          // 4 warps = 4 BGZF blocks per CTA
+#ifndef MCOV_INFLATE_WINDOW
+#define MCOV_INFLATE_WINDOW 2048              /* bytes of recent output mirrored in shared memory, per warp */
+#endif
+constexpr int kInflateThreads = 64;           // 2 warps = 2 BGZF blocks per CTA
+constexpr uint32_t kInflateWindow = MCOV_INFLATE_WINDOW;
+static_assert((kInflateWindow & (kInflateWindow - 1)) == 0 && kInflateWindow >= 1024, "window: a power of two >= 1 KiB");
 constexpr uint32_t kGuessChunk = 65536;
 constexpr int kGuessChain = 3;
 
-#ifndef MCOV_INFLATE_MIN_CTAS
-#define MCOV_INFLATE_MIN_CTAS 4
-#endif
-__global__ void __launch_bounds__(kInflateThreads, MCOV_INFLATE_MIN_CTAS)
+__global__ void __launch_bounds__(kInflateThreads)
 k_bgzf_inflate(const uint8_t* __restrict__ raw, const BgzfBlock* __restrict__ blocks, int64_t n_blocks, uint8_t* out,
                int verify_crc, int* __restrict__ status) {
   __shared__ uint16_t s_tabs[kInflateThreads / 32][kInfTabWords];                      // first-level Huffman tables, one set per warp
+  __shared__ uint8_t s_win[kInflateThreads / 32][kInflateWindow];                     // recent output, one window per warp
   const int64_t k = ((int64_t)blockIdx.x * kInflateThreads + threadIdx.x) >> 5;      // one warp per block
   const int lane = threadIdx.x & 31;
   if (k >= n_blocks) return;
   const BgzfBlock b = blocks[k];
-  int rc = b.ulen ? inflate_raw(raw + b.coff, b.clen, out + b.uoff, b.ulen, s_tabs[threadIdx.x >> 5], lane, 32) : 0;
+  int rc = b.ulen ? inflate_raw(raw + b.coff, b.clen, out + b.uoff, b.ulen, s_tabs[threadIdx.x >> 5], lane, 32, s_win[threadIdx.x >> 5],
+                               kInflateWindow - 1u) : 0;
   if (rc == 0 && verify_crc && b.ulen) {
     // lane-sliced CRC-32, folded left to right (inflate.cuh)
     uint32_t lo, hi;
@@ -368,6 +377,12 @@ extern "C" int mcov_inflate_host(const uint8_t* src, uint32_t clen, uint8_t* dst
   if ((!src && clen) || (!dst && ulen)) return -1;
   uint16_t tabs[kInfTabWords];
   return inflate_raw(src, clen, dst, ulen, tabs);
+}
+extern "C" int mcov_inflate_host_win(const uint8_t* src, uint32_t clen, uint8_t* dst, uint32_t ulen, uint32_t window) {
+  if ((!src && clen) || (!dst && ulen) || window < 1024 || (window & (window - 1))) return -1;
+  uint16_t tabs[kInfTabWords];
+  std::vector<uint8_t> win(window);
+  return inflate_raw(src, clen, dst, ulen, tabs, 0, 1, win.data(), window - 1);
 }
 extern "C" uint32_t mcov_crc32_host(const uint8_t* p, uint32_t n) { return crc32_bytes(p, n); }
 extern "C" uint32_t mcov_crc32_sliced_host(const uint8_t* p, uint32_t n, int nlanes) { return crc32_sliced_host(p, n, nlanes < 1 ? 1 : nlanes); }

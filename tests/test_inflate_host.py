@@ -11,12 +11,21 @@ from oracle import bamio
 
 
 def _inflate(comp, ulen):
+    """Decode with and without the circular output window (1 KiB: most matches take the far path, 8 KiB: the
+    GPU's size); both must agree."""
     from metacov_b200 import _capi
     src = np.frombuffer(comp, dtype=np.uint8) if len(comp) else np.zeros(1, np.uint8)
-    dst = np.full(ulen + 8, 0xEE, dtype=np.uint8)
-    rc = _capi.lib.mcov_inflate_host(src.ctypes.data, len(comp), dst.ctypes.data, ulen)
-    assert np.all(dst[ulen:] == 0xEE), "wrote past the end of the output"
-    return rc, dst[:ulen].tobytes()
+    res = []
+    for window in (0, 1024, 8192):
+        dst = np.full(ulen + 8, 0xEE, dtype=np.uint8)
+        if window:
+            rc = _capi.lib.mcov_inflate_host_win(src.ctypes.data, len(comp), dst.ctypes.data, ulen, window)
+        else:
+            rc = _capi.lib.mcov_inflate_host(src.ctypes.data, len(comp), dst.ctypes.data, ulen)
+        assert np.all(dst[ulen:] == 0xEE), "wrote past the end of the output"
+        res.append((rc, dst[:ulen].tobytes()))
+    assert all(r[0] == res[0][0] for r in res) and (res[0][0] != 0 or all(r[1] == res[0][1] for r in res))
+    return res[0]
 
 
 def _deflate(data, level, strategy=zlib.Z_DEFAULT_STRATEGY):
