@@ -431,7 +431,7 @@ def run_ours(args):
     # measured DRAM traffic of the dominant kernel (dram__bytes_read+write from the committed ncu capture);
     # only quoted for the workload it was captured on
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_m_traffic_c2.json")
+    tpath = os.path.join(ROOT, "profiles", "r01_z_traffic_c2.json")
     if args.workload == "c2" and args.scale == 1.0 and os.path.exists(tpath):
         with open(tpath) as fh:
             traffic = json.load(fh)["dram_bytes_per_launch"].get(dom)
