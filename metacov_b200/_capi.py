@@ -108,6 +108,7 @@ SIGNATURES = {
     "mcov_depth_sorted": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int]),
     "mcov_depth_sorted_async": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int]),
     "mcov_depth_sorted_packed": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.c_int]),
+    "mcov_depth_sorted_delta": (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int]),
     "mcov_region_stats_run": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i32, _vp]),
     "mcov_region_stats_submit": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i32, C.c_int]),
     "mcov_region_stats_collect": (C.c_int, [_vp, C.c_int, _vp]),

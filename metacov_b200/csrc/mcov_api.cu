@@ -353,6 +353,98 @@ int mcov_set_filter(mcov_ctx* ctx, const mcov_filter* f) {
   return MCOV_OK;
 }
 
+int mcov_depth_sorted_delta(mcov_ctx* ctx, int64_t n, const int64_t* contig_read_start, const uint16_t* dpos,
+                            int64_t n_exc, const uint32_t* exc_index, const int32_t* exc_delta, const uint16_t* flag,
+                            const uint8_t* mapq, const uint8_t* n_cigar, const uint16_t* cig, int64_t n_cig_total, int wait) {
+  if (!ctx) return MCOV_ERR_ARG;
+  if (n < 0 || n_exc < 0 || n_cig_total < 0 || n_cig_total > 0xFFFFFFFFll) return fail(ctx, MCOV_ERR_ARG, "mcov_depth_sorted_delta: bad sizes");
+  if (!contig_read_start || (n > 0 && (!dpos || !flag || !n_cigar)) || (n_cig_total > 0 && !cig) || (n_exc > 0 && (!exc_index || !exc_delta)))
+    return fail(ctx, MCOV_ERR_ARG, "mcov_depth_sorted_delta: null array");
+  if (!mapq && ctx->filt.min_mapq > 0) return fail(ctx, MCOV_ERR_ARG, "mcov_depth_sorted_delta: mapq is required when min_mapq > 0");
+  CU(cudaSetDevice(ctx->device));
+  int rc = ensure_depth(ctx);
+  if (rc) return rc;
+  if (contig_read_start[0] != 0 || contig_read_start[ctx->n_contigs] > n)
+    return fail(ctx, MCOV_ERR_ARG, "mcov_depth_sorted_delta: contig_read_start must start at 0 and end <= n");
+  CU(cudaMemsetAsync(ctx->d_pc.p, 0, sizeof(PassCounters), ctx->stream));
+  ReadStage& st = ctx->stage[ctx->stage_next];
+  ctx->stage_next ^= 1;
+  if (st.in_flight) { CU(cudaEventSynchronize(st.consumed)); st.in_flight = false; }
+  const int64_t n1 = std::max<int64_t>(n, 1);
+  const int64_t off_len = (n + 1 + 3) & ~(int64_t)3;                    // scanned in place: multiple of 4
+  const size_t crs_bytes = ((size_t)ctx->n_contigs + 1) * 8;
+  CU(st.tid.ensure((size_t)n1 * 4)); CU(st.pos.ensure((size_t)n1 * 4));
+  CU(st.flag.ensure((size_t)n1 * 2)); CU(st.mapq.ensure((size_t)n1));
+  CU(st.cig_off.ensure((size_t)off_len * 4)); CU(st.cig.ensure((size_t)n_cig_total * 4 + 16));
+  // staging of the narrow columns: [contig_read_start | dpos u16 | n_cigar u8 | exc_index | exc_delta | cig u16]
+  const size_t o_dpos = (crs_bytes + 15) & ~(size_t)15, o_nc = (o_dpos + (size_t)n1 * 2 + 15) & ~(size_t)15,
+               o_ei = (o_nc + (size_t)n1 + 15) & ~(size_t)15, o_ed = (o_ei + (size_t)std::max<int64_t>(n_exc, 1) * 4 + 15) & ~(size_t)15,
+               o_c16 = (o_ed + (size_t)std::max<int64_t>(n_exc, 1) * 4 + 15) & ~(size_t)15, x_bytes = o_c16 + (size_t)n_cig_total * 2 + 16;
+  CU(ctx->d_end_slot.ensure(x_bytes));
+  CU(ctx->d_start_slot.ensure((size_t)(off_len + 8) * 4));              // S (the record buffer of the fused pass: free until k_fused_prep)
+  cudaStream_t cs = ctx->copy_stream;
+  char* x = ctx->d_end_slot.as<char>();
+  CU(cudaMemcpyAsync(x, contig_read_start, crs_bytes, cudaMemcpyHostToDevice, cs));
+  if (n > 0) {
+    CU(cudaMemcpyAsync(x + o_dpos, dpos, (size_t)n * 2, cudaMemcpyHostToDevice, cs));
+    CU(cudaMemcpyAsync(x + o_nc, n_cigar, (size_t)n, cudaMemcpyHostToDevice, cs));
+    if (n_exc) {
+      CU(cudaMemcpyAsync(x + o_ei, exc_index, (size_t)n_exc * 4, cudaMemcpyHostToDevice, cs));
+      CU(cudaMemcpyAsync(x + o_ed, exc_delta, (size_t)n_exc * 4, cudaMemcpyHostToDevice, cs));
+    }
+    CU(cudaMemcpyAsync(st.flag.p, flag, (size_t)n * 2, cudaMemcpyHostToDevice, cs));
+    if (mapq) CU(cudaMemcpyAsync(st.mapq.p, mapq, (size_t)n, cudaMemcpyHostToDevice, cs));
+    else CU(cudaMemsetAsync(st.mapq.p, 0xff, (size_t)n, cs));
+    if (n_cig_total) CU(cudaMemcpyAsync(x + o_c16, cig, (size_t)n_cig_total * 2, cudaMemcpyHostToDevice, cs));
+  }
+  CU(cudaEventRecord(ctx->copied, cs));
+  CU(cudaStreamWaitEvent(ctx->stream, ctx->copied, 0));
+  cudaStream_t s = ctx->stream;
+  int32_t* S = ctx->d_start_slot.as<int32_t>();
+  const int64_t* d_crs = reinterpret_cast<const int64_t*>(x);
+  ctx->prof_begin(kKDeltaUnpack);
+  k_delta_seed<<<(unsigned)((off_len + 255) / 256), 256, 0, s>>>(n, d_crs, ctx->n_contigs, reinterpret_cast<const uint16_t*>(x + o_dpos),
+                                                               reinterpret_cast<const uint8_t*>(x + o_nc), S, st.tid.as<int32_t>(),
+                                                               st.cig_off.as<uint32_t>(), off_len);
+  if (n_exc) k_delta_patch<<<(unsigned)((n_exc + 255) / 256), 256, 0, s>>>(n_exc, reinterpret_cast<const uint32_t*>(x + o_ei),
+                                                                          reinterpret_cast<const int32_t*>(x + o_ed), n, S);
+  ctx->prof_end();
+  CU(cudaGetLastError());
+  {
+    const int64_t tiles = (off_len + kScanTile - 1) / kScanTile;
+    CU(ctx->d_tile_cnt.ensure((size_t)tiles * 16));
+    CU(cudaMemsetAsync(ctx->d_tile_cnt.p, 0, (size_t)tiles * 16, s));
+    unsigned long long* stw = ctx->d_tile_cnt.as<unsigned long long>();
+    MCOV_LAUNCH(ctx, kKScanCounts, (k_scan_inplace<false><<<(unsigned)tiles, kScanThreads, 0, s>>>(st.cig_off.as<int32_t>(), off_len, stw, pc_of(ctx))));
+    MCOV_LAUNCH(ctx, kKScanCounts, (k_scan_inplace<false><<<(unsigned)tiles, kScanThreads, 0, s>>>(S, off_len, stw + tiles, pc_of(ctx))));
+    CU(cudaGetLastError());
+  }
+  MCOV_LAUNCH(ctx, kKDeltaUnpack, (k_delta_finish<<<grid_for(std::max<int64_t>(n1, n_cig_total), 256, 8), 256, 0, s>>>(
+      n, d_crs, ctx->n_contigs, st.tid.as<int32_t>(), S, st.pos.as<int32_t>(), reinterpret_cast<const uint16_t*>(x + o_c16),
+      st.cig.as<uint32_t>(), n_cig_total)));
+  CU(cudaGetLastError());
+  ExpandArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.n = n;
+  a.tid = st.tid.as<int32_t>(); a.pos = st.pos.as<int32_t>(); a.flag = st.flag.as<uint16_t>();
+  a.mapq = st.mapq.as<uint8_t>(); a.cig_off = st.cig_off.as<uint32_t>(); a.cig = st.cig.as<uint32_t>();
+  a.contig_off = ctx->d_off.as<int64_t>(); a.contig_len = ctx->d_len.as<int32_t>(); a.n_contigs = ctx->n_contigs;
+  a.filt = ctx->filt; a.delta = ctx->depth; a.pc = pc_of(ctx);
+  a.cig_aligned16 = 1;
+  rc = fused_depth_sorted(ctx, a);
+  if (rc) return rc;
+  ctx->n_reads_pushed = n;
+  rc = finish_stage(ctx, &st);
+  if (rc) return rc;
+  ctx->state = kDepthReady;
+  ctx->verdict_pending = true;
+  if (!wait) return MCOV_OK;
+  PassCounters h;
+  CU(cudaMemcpyAsync(&h, ctx->d_pc.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return fused_verdict(ctx, h);
+}
+
 int mcov_begin(mcov_ctx* ctx) {
   if (!ctx) return MCOV_ERR_ARG;
   CU(cudaSetDevice(ctx->device));
@@ -543,7 +635,7 @@ static const char* kKernelNames[kKernelCount] = {
     "k_init_region_stats", "k_region_stats", "k_window_sums", "k_isize_hist", "k_group_count", "k_sorted_stats",
     "memset_depth", "k_region_stats_small", "k_cap_replay", "k_unpack_reads", "k_kmer_hist", "k_region_stats_warp",
     "k_exp_prep", "k_exp_entries", "k_exp_region", "k_exp_revsum", "k_region_hist", "k_hist_finish", "k_run_count", "k_run_offsets", "k_run_write", "k_run_ends",
-    "k_bgzf_inflate", "k_bam_guess", "k_bam_walk_count", "k_bam_walk_write"};
+    "k_bgzf_inflate", "k_bam_guess", "k_bam_walk_count", "k_bam_walk_write", "k_delta_unpack"};
 
 int mcov_copy_to_host(mcov_ctx* ctx, const void* dev, void* host, int64_t n_bytes) {
   if (!ctx) return MCOV_ERR_ARG;

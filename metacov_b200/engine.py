@@ -153,6 +153,15 @@ class CoverageEngine:
             _capi.ptr(packed["flag"]), _capi.ptr(packed["mapq"]) if packed.get("mapq") is not None else None,
             _capi.ptr(packed["n_cigar"]), _capi.ptr(packed["cig"]), packed["n_cig_total"], 1 if wait else 0))
 
+    def depth_sorted_delta(self, packed, wait=True):
+        """Fused path from the delta host transport (see ``pack_batch_delta``)."""
+        n_exc = len(packed["exc_index"]) if not _is_torch(packed["exc_index"]) else packed["exc_index"].numel()
+        self._check(lib.mcov_depth_sorted_delta(
+            self._ctx, packed["n"], _capi.ptr(packed["contig_read_start"]), _capi.ptr(packed["dpos"]), n_exc,
+            _capi.ptr(packed["exc_index"]) if n_exc else None, _capi.ptr(packed["exc_delta"]) if n_exc else None,
+            _capi.ptr(packed["flag"]), _capi.ptr(packed["mapq"]) if packed.get("mapq") is not None else None,
+            _capi.ptr(packed["n_cigar"]), _capi.ptr(packed["cig"]), packed["n_cig_total"], 1 if wait else 0))
+
     def compute_depth(self, batch):
         """Per-base depth of all contigs from one batch: the fused sorted path,
         or clear + expand + scan when the reads are not coordinate-sorted (or
@@ -405,10 +414,44 @@ def pack_batch(batch, n_contigs, with_mapq=False, pinned=False):
     return out
 
 
+def pack_batch_delta(batch, n_contigs, with_mapq=False, pinned=False):
+    """Delta transport of a coordinate-sorted ``ReadBatch`` (see mcov_depth_sorted_delta): u16 position
+    differences inside each contig (+ exceptions), u8 op counts, u16 ops.  Raises ValueError when the batch
+    does not qualify (a CIGAR of more than 255 ops, an op longer than 4095, reads not grouped by contig);
+    ``pack_batch`` is the fallback."""
+    base = pack_batch(batch, n_contigs, with_mapq=with_mapq, pinned=False)
+    n = base["n"]
+    ncig, cig, pos, crs = base["n_cigar"], base["cig"], base["pos"], base["contig_read_start"]
+    if len(ncig) and int(ncig.max()) > 255:
+        raise ValueError("pack_batch_delta: a CIGAR has more than 255 ops")
+    if len(cig) and int(cig.max()) > 0xFFFF:
+        raise ValueError("pack_batch_delta: an op is longer than 4095")
+    d = np.empty(n, dtype=np.int64)
+    if n:
+        d[0] = pos[0]
+        np.subtract(pos[1:], pos[:-1], out=d[1:], dtype=np.int64)
+        firsts = np.unique(np.concatenate((crs[:-1], crs[-1:])))        # first read of every contig and of the unplaced tail
+        firsts = firsts[firsts < n]
+        d[firsts] = pos[firsts]
+    exc = np.nonzero((d < 0) | (d > 0xFFFF))[0]
+    dpos = d.astype(np.uint16)
+    dpos[exc] = 0
+    out = {"n": n, "contig_read_start": crs, "dpos": dpos, "exc_index": exc.astype(np.uint32), "exc_delta": d[exc].astype(np.int32),
+           "flag": base["flag"], "mapq": base["mapq"], "n_cigar": ncig.astype(np.uint8), "cig": cig.astype(np.uint16),
+           "n_cig_total": base["n_cig_total"]}
+    if pinned:
+        import torch
+        for k in ("contig_read_start", "dpos", "exc_index", "exc_delta", "flag", "mapq", "n_cigar", "cig"):
+            if out[k] is not None:
+                t = torch.from_numpy(out[k].view({8: np.int64, 4: np.int32, 2: np.int16, 1: np.uint8}[out[k].dtype.itemsize]))
+                out[k] = t.pin_memory()
+    return out
+
+
 def packed_bytes(packed):
     tot = 0
-    for k in ("contig_read_start", "pos", "flag", "mapq", "n_cigar", "cig"):
-        a = packed[k]
+    for k in ("contig_read_start", "pos", "dpos", "exc_index", "exc_delta", "flag", "mapq", "n_cigar", "cig"):
+        a = packed.get(k)
         if a is not None:
             tot += a.numel() * a.element_size() if _is_torch(a) else a.nbytes
     return int(tot)

@@ -73,7 +73,7 @@ def _case(seed):
 @pytest.mark.parametrize("block", range(6))
 def test_random_cases_match_oracle(block):
     from metacov_b200 import CoverageEngine, McovError, _capi
-    from metacov_b200.engine import pack_batch
+    from metacov_b200.engine import pack_batch, pack_batch_delta
     for seed in range(block * 10, block * 10 + 10):
         b, isize, lengths, (rt, rs, re), filt = _case(1000 + seed)
         of = cport.default_filter(**filt) if filt else None
@@ -81,7 +81,7 @@ def test_random_cases_match_oracle(block):
         want = cport.region_stats(d, off, lengths, rt, rs, re)
         nonempty = re > rs
         with CoverageEngine(lengths, filt=filt or None) as eng:
-            for path in ("auto", "push", "packed"):
+            for path in ("auto", "push", "packed", "delta"):
                 if path == "auto":
                     eng.compute_depth(b)
                 elif path == "push":
@@ -94,9 +94,15 @@ def test_random_cases_match_oracle(block):
                     eng.finalize()
                 else:
                     try:
-                        eng.depth_sorted_packed(pack_batch(b, len(lengths), with_mapq=True))
-                    except (McovError, ValueError):
-                        continue                                          # transport limits (u16 op counts): not this test's subject
+                        if path == "packed":
+                            eng.depth_sorted_packed(pack_batch(b, len(lengths), with_mapq=True))
+                        else:
+                            eng.depth_sorted_delta(pack_batch_delta(b, len(lengths), with_mapq=True))
+                    except ValueError:
+                        continue                                          # the batch does not qualify for this transport
+                    except McovError as e:
+                        assert e.code in (_capi.MCOV_ERR_UNSORTED, _capi.MCOV_ERR_RANGE), (seed, path, e)
+                        continue                                          # (the auto path took the push formulation for it)
                 pi = eng.pass_info()
                 assert pi["n_pass"] == info["n_pass"] and pi["aligned_bases"] == info["aligned_bases"], (seed, path)
                 for c in range(len(lengths)):

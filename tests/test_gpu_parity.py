@@ -445,3 +445,63 @@ def test_pipelined_statistics_equal_synchronous():
         with pytest.raises(McovError) as ei:
             eng.region_stats_collect(t)
         assert ei.value.code == _capi.MCOV_ERR_UNSORTED
+
+
+def test_delta_host_transport_equals_soa_path():
+    """mcov_depth_sorted_delta (u16 position differences + exceptions, u8 op counts, u16 ops): the SoA rebuilt
+    on the device gives the same depth as the plain columns -- short reads, sparse contigs whose gaps exceed
+    16 bits (exceptions), unplaced reads at the end, unsorted input (negative differences travel faithfully
+    and the pass reports MCOV_ERR_UNSORTED), batches that do not qualify."""
+    from metacov_b200 import McovError, ReadBatch, _capi, synth
+    from metacov_b200.engine import pack_batch_delta, packed_bytes, pack_batch
+    w = synth.c2(0.01)
+    b, _ = synth.generate_host(w)
+    pd = pack_batch_delta(b, w.n_contigs)
+    assert packed_bytes(pd) < 0.65 * packed_bytes(pack_batch(b, w.n_contigs)) and len(pd["exc_index"]) == 0
+    with engine_for(w.contig_len) as eng:
+        eng.depth_sorted_delta(pd)
+        want, dflat, off, info = oracle_depth(b, w.contig_len)
+        for c, d in enumerate(full_depth(eng)):
+            assert np.array_equal(d, want[c]), c
+        pi = eng.pass_info()
+        assert pi["n_pass"] == info["n_pass"] and pi["aligned_bases"] == info["aligned_bases"] and pi["sorted"] == 1
+        eng.set_filter(min_mapq=30)
+        with pytest.raises(McovError):
+            eng.depth_sorted_delta(pd)                           # mapq required when min_mapq > 0
+        eng.depth_sorted_delta(pack_batch_delta(b, w.n_contigs, with_mapq=True, pinned=True))
+        want30, _, _, _ = oracle_depth(b, w.contig_len, min_mapq=30)
+        assert np.array_equal(eng.copy_depth(0), want30[0])
+    # sparse reads on long contigs: gaps above 65535 become exceptions; first reads of contigs far from 0
+    rng = np.random.default_rng(8)
+    lengths = np.array([3_000_000, 500_000, 2_000_000], np.int32)
+    tid = np.repeat(np.arange(3, dtype=np.int32), [40, 5, 30])
+    pos = np.concatenate([np.sort(rng.integers(100_000, l - 200, k)) for l, k in zip(lengths, (40, 5, 30))]).astype(np.int32)
+    n = len(tid)
+    sb = ReadBatch(tid, pos, np.zeros(n, np.uint16), np.full(n, 60, np.uint8), np.arange(n + 1, dtype=np.uint32),
+                   np.full(n, 150 << 4, np.uint32))
+    ps = pack_batch_delta(sb, 3)
+    assert len(ps["exc_index"]) > 10
+    with engine_for(lengths) as eng:
+        eng.depth_sorted_delta(ps)
+        wants, _, _, _ = oracle_depth(sb, lengths)
+        for c in range(3):
+            assert np.array_equal(eng.copy_depth(c), wants[c]), c
+        # unsorted inside a contig: the negative difference is an exception, the verdict is UNSORTED
+        ub = ReadBatch(tid, pos[::-1].copy(), sb.flag, sb.mapq, sb.cig_off, sb.cig)
+        with pytest.raises(McovError) as ei:
+            eng.depth_sorted_delta(pack_batch_delta(ub, 3))
+        assert ei.value.code == _capi.MCOV_ERR_UNSORTED
+    # unplaced reads at the end (fixture) and empty input
+    z, fb = load_soa("fixture_soa.npz")
+    with engine_for(z["lengths"]) as eng:
+        eng.depth_sorted_delta(pack_batch_delta(fb, 2, pinned=True))
+        wantf, _, _, _ = oracle_depth(fb, z["lengths"])
+        assert np.array_equal(eng.copy_depth(1), wantf[1]) and eng.pass_info()["n_pass"] == 3350
+        empty = ReadBatch(*(np.zeros(0, a.dtype) for a in (fb.tid, fb.pos, fb.flag, fb.mapq)), np.zeros(1, np.uint32), np.zeros(0, np.uint32))
+        eng.depth_sorted_delta(pack_batch_delta(empty, 2))
+        assert eng.pass_info()["n_pass"] == 0 and not eng.copy_depth(0).any()
+    # long reads do not qualify (thousands of ops per CIGAR): the caller falls back to pack_batch
+    w5 = synth.c5(0.0005)
+    b5, _ = synth.generate_host(w5)
+    with pytest.raises(ValueError):
+        pack_batch_delta(b5, w5.n_contigs)
