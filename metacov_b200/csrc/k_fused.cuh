@@ -17,8 +17,10 @@
 //   k_scan_inplace one small scan over [tile_agg | far counts]: the inclusive
 //                  sum of tile_agg up to T-1 is the number of FAR reads open at
 //                  the start of tile T.
-//   k_far_scatter  bucket the far ends by tile (counting sort).
-//   k_fused_tile   one CTA per tile of kTile slots: +1/-1 of the tile's reads
+//   k_far_scatter  bucket the far ends by tile (counting sort); list the tiles that hold
+//                  very many reads (scheduled first by the tile kernel).
+//   k_fused_tile   persistent CTAs drawing tiles of kTile slots by ticket (heavy tiles
+//                  first): +1/-1 of the tile's reads
 //                  go to SHARED-memory counters (starts and ends kept apart),
 //                  the ends of near reads that started before the tile are
 //                  found by walking back at most max_span slots in the sorted
@@ -33,7 +35,8 @@
 //                  starts[p] = depth[p] + ends[p].
 //
 // HBM bytes (algorithmic): prep 15R + 4*sum(n_cigar of passing reads) + 4R;
-// tile 4R + 4(L+C).
+// tile 4R + 4(L+C).  The kernels of one pass are chained with programmatic
+// dependent launches (pdl_wait / pdl_launch_dependents, common.cuh).
 #pragma once
 #include "ctx.cuh"
 #include "k_expand.cuh"
