@@ -43,33 +43,46 @@ struct BgzfBlock { uint64_t coff; uint64_t uoff; uint32_t clen; uint32_t ulen; u
 #ifndef MCOV_INFLATE_WINDOW
 #define MCOV_INFLATE_WINDOW 2048              /* bytes of recent output mirrored in shared memory, per warp */
 #endif
-constexpr int kInflateThreads = 64;           // 2 warps = 2 BGZF blocks per CTA
+constexpr int kInflateThreads = 64;           // 2 warps per CTA
 constexpr uint32_t kInflateWindow = MCOV_INFLATE_WINDOW;
 static_assert((kInflateWindow & (kInflateWindow - 1)) == 0 && kInflateWindow >= 1024, "window: a power of two >= 1 KiB");
 constexpr uint32_t kGuessChunk = 65536;
 constexpr int kGuessChain = 3;
 
+#ifndef MCOV_INFLATE_GROUP
+#define MCOV_INFLATE_GROUP 32                 /* lanes that decode one BGZF block together (a power of two <= 32) */
+#endif
+constexpr int kInflateGroup = MCOV_INFLATE_GROUP;
+constexpr int kInflateGroupsPerCta = kInflateThreads / kInflateGroup;
+static_assert(kInflateGroup >= 1 && kInflateGroup <= 32 && (kInflateGroup & (kInflateGroup - 1)) == 0, "group: 1, 2, 4, ... 32 lanes");
+
+// The symbol decode is redundant across the lanes of a group (that keeps its control flow uniform).  Smaller
+// groups do NOT recover the redundant issue slots: groups of one warp sit at different points of their streams,
+// the warp serialises them, and each group only gets slower -- measured 11.6 ms with whole warps, 20.3 ms with
+// groups of 16, 34.9 ms with groups of 8 (same 1 M-read BAM).
 __global__ void __launch_bounds__(kInflateThreads)
 k_bgzf_inflate(const uint8_t* __restrict__ raw, const BgzfBlock* __restrict__ blocks, int64_t n_blocks, uint8_t* out,
                int verify_crc, int* __restrict__ status) {
-  __shared__ uint16_t s_tabs[kInflateThreads / 32][kInfTabWords];                      // first-level Huffman tables, one set per warp
-  __shared__ uint8_t s_win[kInflateThreads / 32][kInflateWindow];                     // recent output, one window per warp
-  const int64_t k = ((int64_t)blockIdx.x * kInflateThreads + threadIdx.x) >> 5;      // one warp per block
-  const int lane = threadIdx.x & 31;
+  __shared__ uint16_t s_tabs[kInflateGroupsPerCta][kInfTabWords];                     // first-level Huffman tables, one set per group
+  __shared__ uint8_t s_win[kInflateGroupsPerCta][kInflateWindow];                     // recent output, one window per group
+  const int grp = threadIdx.x / kInflateGroup;
+  const int64_t k = (int64_t)blockIdx.x * kInflateGroupsPerCta + grp;                 // one group per block
+  const int lane = threadIdx.x & (kInflateGroup - 1);
+  const unsigned gmask = (kInflateGroup == 32 ? 0xffffffffu : ((1u << kInflateGroup) - 1u)) << ((threadIdx.x & 31) & ~(kInflateGroup - 1));
   if (k >= n_blocks) return;
   const BgzfBlock b = blocks[k];
-  int rc = b.ulen ? inflate_raw(raw + b.coff, b.clen, out + b.uoff, b.ulen, s_tabs[threadIdx.x >> 5], lane, 32, s_win[threadIdx.x >> 5],
-                               kInflateWindow - 1u) : 0;
+  int rc = b.ulen ? inflate_raw(raw + b.coff, b.clen, out + b.uoff, b.ulen, s_tabs[grp], lane, kInflateGroup, s_win[grp],
+                               kInflateWindow - 1u, gmask) : 0;
   if (rc == 0 && verify_crc && b.ulen) {
     // lane-sliced CRC-32, folded left to right (inflate.cuh)
     uint32_t lo, hi;
-    crc_slice(b.ulen, lane, 32, lo, hi);
+    crc_slice(b.ulen, lane, kInflateGroup, lo, hi);
     const uint32_t mine = crc32_bytes(out + b.uoff + lo, hi - lo);
     const uint32_t op_full = crc_x8n(hi - lo);                  // (lanes with a full slice all compute the same factor)
-    uint32_t crc = __shfl_sync(0xffffffffu, mine, 0);
-    for (int j = 1; j < 32; ++j) {
-      const uint32_t cj = __shfl_sync(0xffffffffu, mine, j), opj = __shfl_sync(0xffffffffu, op_full, j);
-      const uint32_t nj = __shfl_sync(0xffffffffu, hi - lo, j);
+    uint32_t crc = __shfl_sync(gmask, mine, 0, kInflateGroup);
+    for (int j = 1; j < kInflateGroup; ++j) {
+      const uint32_t cj = __shfl_sync(gmask, mine, j, kInflateGroup), opj = __shfl_sync(gmask, op_full, j, kInflateGroup);
+      const uint32_t nj = __shfl_sync(gmask, hi - lo, j, kInflateGroup);
       if (nj) crc = crc_multmodp(opj, crc) ^ cj;
     }
     if (crc != b.crc) rc = 100;
@@ -257,7 +270,7 @@ extern "C" int mcov_bam_decode_gpu(mcov_ctx* ctx, const void* file_bytes, int64_
   CUB(cudaMemcpyAsync(B.raw.p, raw, (size_t)n_bytes, cudaMemcpyHostToDevice, s));
   CUB(cudaMemcpyAsync(B.blocks.p, blocks.data(), (size_t)nb * sizeof(BgzfBlock), cudaMemcpyHostToDevice, s));
   CUB(cudaMemsetAsync(B.status.p, 0, 64, s));
-  MCOV_LAUNCH(ctx, kKBgzfInflate, (k_bgzf_inflate<<<(unsigned)((nb * 32 + kInflateThreads - 1) / kInflateThreads), kInflateThreads, 0, s>>>(
+  MCOV_LAUNCH(ctx, kKBgzfInflate, (k_bgzf_inflate<<<(unsigned)((nb + kInflateGroupsPerCta - 1) / kInflateGroupsPerCta), kInflateThreads, 0, s>>>(
       B.raw.as<uint8_t>(), B.blocks.as<BgzfBlock>(), nb, B.data.as<uint8_t>(), verify_crc, B.status.as<int>())));
   CUB(cudaGetLastError());
   // header (host): magic, text, reference table -> n_ref, first record

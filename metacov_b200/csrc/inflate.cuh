@@ -1,8 +1,8 @@
 // inflate.cuh -- raw DEFLATE (RFC 1951) decoder for one BGZF block, usable on the device and on the host.
 //
 // BGZF (SAM spec 4.1) cuts a BAM file into independent deflate streams of at most 64 KiB, so a file is
-// thousands of independent decode jobs: on the GPU one WARP inflates one block (k_bgzf_inflate,
-// bam_gpu.cu).  All lanes decode the symbol stream redundantly (identical state, broadcast loads), which
+// thousands of independent decode jobs: on the GPU a GROUP of lanes (an aligned part of a warp) inflates
+// one block (k_bgzf_inflate, bam_gpu.cu).  All lanes of the group decode the symbol stream redundantly (identical state, broadcast loads), which
 // keeps the control flow uniform; the work that can be split is split: an LZ77 match of `len` bytes is
 // copied by the lanes in parallel -- byte k comes from dst[o - dist + k % dist], so even a run with
 // dist = 1 has no serial dependency (one thread per block spent ~2 us per byte there, an L2 round trip
@@ -27,7 +27,7 @@
 namespace mcov {
 
 #if defined(__CUDA_ARCH__)
-#define MCOV_INF_SYNC() __syncwarp()
+#define MCOV_INF_SYNC() __syncwarp(gmask)   /* the cooperating lanes: a warp or an aligned part of one */
 #define MCOV_INF_LDOUT(p) __ldcg(p)          /* output written by other lanes: read through L2 */
 #else
 #define MCOV_INF_SYNC() ((void)0)
@@ -118,7 +118,8 @@ MCOV_HD int inf_decode(InfBits& r, const InfHuff& h) {
 constexpr int kLitBits = 9, kDistBits = 6;
 constexpr int kInfTabWords = (1 << kLitBits) + (1 << kDistBits);
 
-MCOV_HD void inf_build_fast(const InfHuff& h, uint16_t* tab, int P, int lane, int nlanes) {
+MCOV_HD void inf_build_fast(const InfHuff& h, uint16_t* tab, int P, int lane, int nlanes, unsigned gmask) {
+  (void)gmask;
   for (int i = lane; i < (1 << P); i += nlanes) tab[i] = 0;
   MCOV_INF_SYNC();
   int code = 0, base = 0;
@@ -157,7 +158,8 @@ MCOV_HD int inf_dist_base(int s) { return s < 4 ? 1 + s : 1 + ((2 + (s & 1)) << 
 // the warp has just stored (measured: ~1.2 us per symbol without it, almost all of it that round trip).
 // Matches that reach further back than the window read the output itself.
 MCOV_HD int inflate_raw(const uint8_t* src, uint32_t clen, uint8_t* dst, uint32_t ulen, uint16_t* tabs /* kInfTabWords, shared by the lanes */,
-                        int lane = 0, int nlanes = 1, uint8_t* win = nullptr, uint32_t wmask = 0) {
+                        int lane = 0, int nlanes = 1, uint8_t* win = nullptr, uint32_t wmask = 0, unsigned gmask = 0xffffffffu) {
+  (void)gmask;
   InfBits r;
   r.in = src; r.n = clen; r.p = 0; r.buf = 0; r.cnt = 0; r.pad = 0; r.over = false;
   uint16_t* ltab = tabs;
@@ -233,8 +235,8 @@ MCOV_HD int inflate_raw(const uint8_t* src, uint32_t clen, uint8_t* dst, uint32_
       err = inf_construct(distcode, lengths + nlen, ndist);
       if (err < 0 || (err > 0 && ndist - distcode.count[0] != 1)) return kInfBadCodeLengths;
     }
-    inf_build_fast(lencode, ltab, kLitBits, lane, nlanes);
-    inf_build_fast(distcode, dtab, kDistBits, lane, nlanes);
+    inf_build_fast(lencode, ltab, kLitBits, lane, nlanes, gmask);
+    inf_build_fast(distcode, dtab, kDistBits, lane, nlanes, gmask);
     // literal/length + distance symbols until end-of-block
     for (;;) {
       int sym = inf_decode_fast(r, lencode, ltab, kLitBits);
