@@ -49,15 +49,18 @@ int grid_for(int64_t n, int threads, int per_sm) {
 // Launch with the programmatic-stream-serialization attribute (see pdl_wait in common.cuh): the kernel
 // may start while its predecessor in the stream drains.  Only for kernels that call pdl_wait() before
 // they touch anything the predecessor writes.
+// `allow`: the overlap pays for short kernels (config C2: 0.209 -> 0.200 ms per step) and costs on long ones
+// (C4 at full size: 14.9 -> 16.0 ms), so the callers enable it by problem size.
+constexpr int64_t kPdlMaxSlots = (int64_t)1 << 27;     // 134 M slots
 template <typename... KArgs, typename... Args>
-cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+cudaError_t launch_pdl(bool allow, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
   static const bool enabled = std::getenv("MCOV_NO_PDL") == nullptr;        // tuning hook: plain stream order instead
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = enabled ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = (enabled && allow) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
@@ -175,13 +178,14 @@ int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a) {
   }
   // prep -> scan_counts -> far_scatter -> tile (-> statistics) are chained with programmatic dependent
   // launches: each kernel's CTAs are in place before its predecessor has drained
-  MCOV_LAUNCH(ctx, kKScanCounts, CU(launch_pdl(k_scan_inplace<false>, dim3((unsigned)scan_tiles), dim3(kScanThreads), 0, s,
+  const bool pdl = ctx->n_slots <= kPdlMaxSlots;
+  MCOV_LAUNCH(ctx, kKScanCounts, CU(launch_pdl(pdl, k_scan_inplace<false>, dim3((unsigned)scan_tiles), dim3(kScanThreads), 0, s,
       f.tile_agg, scan_len, reinterpret_cast<unsigned long long*>(z + o_st), pc_of(ctx))));
-  MCOV_LAUNCH(ctx, kKFarScatter, CU(launch_pdl(k_far_scatter, dim3(kNumSMsB200 * 2), dim3(256), 0, s, f)));
+  MCOV_LAUNCH(ctx, kKFarScatter, CU(launch_pdl(pdl, k_far_scatter, dim3(kNumSMsB200 * 2), dim3(256), 0, s, f)));
   ctx->fused_blob.assign(reinterpret_cast<const unsigned char*>(&f), reinterpret_cast<const unsigned char*>(&f) + sizeof(f));
   {
     const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)kNumSMsB200 * MCOV_TILE_MIN_CTAS);   // persistent
-    MCOV_LAUNCH(ctx, kKFusedTile, CU(launch_pdl(k_fused_tile, dim3(grid), dim3(kFusedThreads), 0, s, f)));
+    MCOV_LAUNCH(ctx, kKFusedTile, CU(launch_pdl(pdl, k_fused_tile, dim3(grid), dim3(kFusedThreads), 0, s, f)));
   }
   return MCOV_OK;
 }
@@ -802,7 +806,7 @@ static int stats_launch(mcov_ctx* ctx, int64_t g, const int32_t* tid, const int3
       a.region_done = ctx->d_pool.as<uint32_t>();
       a.hist_pool = reinterpret_cast<uint32_t*>(ctx->d_pool.as<char>() + done_bytes);
       a.out = d_out; a.breadth_n = breadth_n;
-      MCOV_LAUNCH(ctx, kKRegionStats, CU(launch_pdl(k_region_stats, dim3((unsigned)rp.n_tasks), dim3(kStatThreads), 0, s, a)));
+      MCOV_LAUNCH(ctx, kKRegionStats, CU(launch_pdl(ctx->n_slots <= kPdlMaxSlots, k_region_stats, dim3((unsigned)rp.n_tasks), dim3(kStatThreads), 0, s, a)));
     }
     if (rp.n_small) {
       StatArgs a;
