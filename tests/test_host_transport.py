@@ -1,0 +1,100 @@
+"""Host-side packers of the narrow transports (CPU): what the device rebuilds must be what was packed.
+The device side (mcov_depth_sorted_packed / _delta) is covered by tests/test_gpu_parity.py and
+tests/test_gpu_fuzz.py."""
+import numpy as np
+import pytest
+
+from helpers import load_soa
+
+
+def _rebuild_delta(p):
+    """The arithmetic of k_delta_seed / k_delta_patch / prefix sum / k_delta_finish, in numpy."""
+    n = p["n"]
+    d = p["dpos"].astype(np.int64)
+    d[p["exc_index"]] = p["exc_delta"]
+    S = np.cumsum(d).astype(np.int64) & 0xFFFFFFFF                 # the device sums in 32 bits, wrap-around included
+    crs = p["contig_read_start"]
+    pos = np.empty(n, np.int64)
+    for a, b in list(zip(crs[:-1], crs[1:])) + [(crs[-1], n)]:
+        if b > a:
+            pos[a:b] = (S[a:b] - (S[a - 1] if a > 0 else 0)) & 0xFFFFFFFF
+    return pos.astype(np.uint32).view(np.int32)
+
+
+def test_delta_packer_round_trip():
+    from metacov_b200 import ReadBatch, synth
+    from metacov_b200.engine import pack_batch, pack_batch_delta, packed_bytes
+    w = synth.c2(0.01)
+    b, _ = synth.generate_host(w)
+    p = pack_batch_delta(b, w.n_contigs)
+    assert np.array_equal(_rebuild_delta(p), b.pos) and len(p["exc_index"]) == 0
+    assert np.array_equal(np.cumsum(p["n_cigar"], dtype=np.int64), b.cig_off[1:].astype(np.int64))
+    assert np.array_equal(p["cig"].astype(np.uint32), b.cig)
+    assert packed_bytes(p) / len(b.tid) < 7.5 < 12.0 < packed_bytes(pack_batch(b, w.n_contigs)) / len(b.tid)
+    # fixture: unplaced reads at the end form one more segment
+    z, fb = load_soa("fixture_soa.npz")
+    pf = pack_batch_delta(fb, 2)
+    assert np.array_equal(_rebuild_delta(pf), fb.pos) and pf["contig_read_start"][-1] < len(fb.tid)
+    # gaps beyond 16 bits, first reads far from 0, negative differences (unsorted), negative positions
+    rng = np.random.default_rng(4)
+    for trial in range(20):
+        n_contigs = int(rng.integers(1, 6))
+        counts = rng.integers(0, 60, n_contigs)
+        tid = np.repeat(np.arange(n_contigs, dtype=np.int32), counts)
+        pos = rng.integers(-1000, 2_000_000_000, len(tid)).astype(np.int32)
+        if trial % 2 == 0:
+            pos = np.concatenate([np.sort(pos[tid == c]) for c in range(n_contigs)]).astype(np.int32) if len(tid) else pos
+        n = len(tid)
+        rb = ReadBatch(tid, pos, np.zeros(n, np.uint16), np.zeros(n, np.uint8), np.arange(n + 1, dtype=np.uint32),
+                       np.full(n, 100 << 4, np.uint32))
+        pk = pack_batch_delta(rb, n_contigs)
+        assert np.array_equal(_rebuild_delta(pk), pos), trial
+        if n:
+            assert pk["dpos"][pk["exc_index"]].max(initial=0) == 0          # placeholders of the exceptions
+    # what does not qualify
+    n = 4
+    long_op = ReadBatch(np.zeros(n, np.int32), np.arange(n, dtype=np.int32), np.zeros(n, np.uint16), np.zeros(n, np.uint8),
+                        np.arange(n + 1, dtype=np.uint32), np.full(n, 5000 << 4, np.uint32))
+    with pytest.raises(ValueError):
+        pack_batch_delta(long_op, 1)
+    many_ops = ReadBatch(np.zeros(1, np.int32), np.zeros(1, np.int32), np.zeros(1, np.uint16), np.zeros(1, np.uint8),
+                         np.array([0, 300], np.uint32), np.full(300, 1 << 4, np.uint32))
+    with pytest.raises(ValueError):
+        pack_batch_delta(many_ops, 1)
+    ungrouped = ReadBatch(np.array([1, 0], np.int32), np.zeros(2, np.int32), np.zeros(2, np.uint16), np.zeros(2, np.uint8),
+                          np.arange(3, dtype=np.uint32), np.full(2, 1 << 4, np.uint32))
+    with pytest.raises(ValueError):
+        pack_batch_delta(ungrouped, 2)
+
+
+def test_partition_positions_covers_every_base_once():
+    from metacov_b200 import sharding
+    rng = np.random.default_rng(12)
+    for trial in range(40):
+        c = int(rng.integers(1, 30))
+        ln = rng.integers(1, 400_000, c)
+        rd = (ln * rng.uniform(0.0, 0.5, c)).astype(np.int64)
+        for n in (1, 2, 3, 8):
+            shares = sharding.partition_positions(ln, rd, n)
+            assert len(shares) == n
+            seen = {}
+            last = (-1, 0)
+            for pieces in shares:
+                for pc in pieces:
+                    assert 0 <= pc.p0 < pc.p1 <= ln[pc.tid]
+                    assert (pc.tid, pc.p0) >= last                      # contiguous, in order
+                    last = (pc.tid, pc.p1)
+                    seen.setdefault(pc.tid, []).append((pc.p0, pc.p1))
+            for t in range(c):
+                iv = sorted(seen.get(t, []))
+                assert iv and iv[0][0] == 0 and iv[-1][1] == ln[t] and all(iv[k][1] == iv[k + 1][0] for k in range(len(iv) - 1)), (trial, n, t)
+            # every region lands somewhere, whole or cut
+            rt = rng.integers(0, c, 10)
+            rs = np.array([rng.integers(0, ln[t]) for t in rt])
+            re = np.array([s + rng.integers(0, ln[t] + 50) for s, t in zip(rs, rt)])
+            plan = sharding.split_regions(rt, rs, re, shares, ln)
+            n_whole = sum(len(plan.whole[r][0]) for r in range(n))
+            assert n_whole + len(plan.cut_regions) == 10
+            for r in range(n):
+                ci, ctid, cst, cen = plan.arrays("cut", r)
+                assert np.all(cen > cst)
