@@ -129,3 +129,19 @@ def test_native_seq_windows(tmp_path):
             else:
                 want = [s[j] if j < len(s) else 15 for j in range(P)]
             assert nib[:P].tolist() == [int(x) for x in want], i
+
+
+def test_load_kmerhist_both_csv_dialects():
+    """`load_kmerhist` (reference pileup.py:29-35): k-mer -> n0 / mean(n1..) per read number, unmapped and
+    all-N rows dropped; the read-number column is `R` in the layout the reference was written for and
+    `IsRead1` at the reference's HEAD."""
+    import io
+    from metacov_b200 import pileup
+    rows = [("AAC", [10, 2, 4, 6], "Mapped", "R1"), ("AAC", [9, 3, 3, 3], "Mapped", "R2"), ("ACG", [0, 1, 1, 1], "Mapped", "R1"),
+            ("NNN", [5, 5, 5, 5], "Mapped", "R1"), ("TTT", [7, 1, 1, 1], "Unmapped", "R1"), ("GGA", [8, 4, 4, 4], "Mapped", "R2")]
+    want = [{"AAC": 10 / 4.0, "ACG": 0.0}, {"AAC": 9 / 3.0, "GGA": 2.0}]
+    for rcol in ("R", "IsRead1"):
+        csv_text = "kmer,n0,n1,n2,n3,Mapped,%s\n" % rcol + "".join(
+            "%s,%s,%s,%s\n" % (k, ",".join(str(x) for x in n), m, r) for k, n, m, r in rows)
+        got = pileup.load_kmerhist(io.StringIO(csv_text), k_len=3)
+        assert [dict((k, float(v)) for k, v in d.items()) for d in got] == want, rcol
