@@ -400,6 +400,7 @@ def run_ours(args):
         e2e = {"value": aligned_total / dt, "unit": UNIT,
                "h2d_bytes_per_step": packed_bytes(packed) + g * 16, "d2h_bytes_per_step": g * 64 + 64,
                "ms_per_step": 1e3 * dt, "unpipelined_ms_per_step": 1e3 * dt_sync,
+               "bytes_scope": "per rank (every rank copies its own shard; multiply by n_gpus for the whole job)" if world > 1 else "whole job",
                "transport": transport,
                "plain_soa": {"value": aligned_total / dt_soa, "h2d_bytes_per_step": batch_bytes(pbatch) + g * 16,
                              "ms_per_step": 1e3 * dt_soa}}
