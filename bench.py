@@ -41,7 +41,7 @@ def peaks():
 class ClockSampler(threading.Thread):
     """SM clock and throttle reasons sampled during the timed region (NVML)."""
 
-    def __init__(self, index, period=0.01):
+    def __init__(self, index, period=0.002):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
