@@ -130,6 +130,20 @@ int  mcov_depth_sorted(mcov_ctx* ctx, int64_t n,
                        const uint32_t* cig_off, const uint32_t* cig,
                        int mem_kind);
 
+/* Batches of 2^32 or more CIGAR ops (long reads: BASELINE config 5 at full size
+ * is 5 M reads with 1.4e10 ops): the same two entry points with 64-bit offsets.
+ * wait = 0 defers the verdict like mcov_depth_sorted_async. */
+int  mcov_depth_sorted_wide(mcov_ctx* ctx, int64_t n,
+                            const int32_t* tid, const int32_t* pos,
+                            const uint16_t* flag, const uint8_t* mapq,
+                            const uint64_t* cig_off, const uint32_t* cig,
+                            int mem_kind, int wait);
+int  mcov_push_reads_wide(mcov_ctx* ctx, int64_t n,
+                          const int32_t* tid, const int32_t* pos,
+                          const uint16_t* flag, const uint8_t* mapq,
+                          const uint64_t* cig_off, const uint32_t* cig,
+                          int mem_kind);
+
 /* Same, but returns without waiting for the GPU: the sortedness verdict
  * (MCOV_ERR_UNSORTED / MCOV_ERR_RANGE) is delivered by the next call that
  * synchronises -- mcov_region_stats_run, mcov_copy_depth, mcov_pass_info_get. */
@@ -442,6 +456,13 @@ int  mcov_synth_gen_ncigar(const struct mcov_synth_params* P, int64_t i0, int64_
 int  mcov_synth_gen_reads(const struct mcov_synth_params* P, int64_t i0, int64_t n,
                      const int64_t* read_start, const int32_t* contig_len, int32_t n_contigs,
                      int32_t tid_base, const uint32_t* cig_off,
+                     int32_t* tid, int32_t* pos, uint16_t* flag, uint8_t* mapq, int32_t* isize,
+                     uint32_t* cig, int64_t* reflen_out, int mem_kind, void* stream);
+
+/* Same with 64-bit CIGAR offsets (a batch of 2^32 or more ops). */
+int  mcov_synth_gen_reads_wide(const struct mcov_synth_params* P, int64_t i0, int64_t n,
+                     const int64_t* read_start, const int32_t* contig_len, int32_t n_contigs,
+                     int32_t tid_base, const uint64_t* cig_off,
                      int32_t* tid, int32_t* pos, uint16_t* flag, uint8_t* mapq, int32_t* isize,
                      uint32_t* cig, int64_t* reflen_out, int mem_kind, void* stream);
 

@@ -106,6 +106,8 @@ SIGNATURES = {
     "mcov_push_reads": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int]),
     "mcov_finalize": (C.c_int, [_vp]),
     "mcov_depth_sorted": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int]),
+    "mcov_depth_sorted_wide": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int]),
+    "mcov_push_reads_wide": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int]),
     "mcov_depth_sorted_async": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int]),
     "mcov_depth_sorted_packed": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.c_int]),
     "mcov_depth_sorted_delta": (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int]),
@@ -163,6 +165,8 @@ SIGNATURES = {
     "mcov_synth_gen_ncigar": (C.c_int, [C.POINTER(SynthParams), _i64, _i64, _vp, C.c_int, _vp]),
     "mcov_synth_gen_reads": (C.c_int, [C.POINTER(SynthParams), _i64, _i64, _vp, _vp, _i32, _i32, _vp,
                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp]),
+    "mcov_synth_gen_reads_wide": (C.c_int, [C.POINTER(SynthParams), _i64, _i64, _vp, _vp, _i32, _i32, _vp,
+                                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp]),
 }
 
 

@@ -13,6 +13,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -75,6 +76,7 @@ bool index_blocks(const std::vector<uint8_t>& raw, std::vector<Block>& blocks, s
     b.clen = bend - 8 - b.coff;
     b.crc = rd32(raw.data() + bend - 8);
     b.ulen = rd32(raw.data() + bend - 4);
+    if (b.ulen > 65536) return false;          // BGZF: a block inflates to at most 64 KiB (SAM spec 4.1)
     b.uoff = uoff;
     uoff += b.ulen;
     blocks.push_back(b);
@@ -149,6 +151,20 @@ bool parse_header(mcov_bam* b) {
   return true;
 }
 
+// fixed part + name + CIGAR + SEQ + QUAL of a record must fit its block_size (SAM spec 4.2)
+inline bool record_fits(const uint8_t* r, uint32_t bs) {
+  const uint64_t l_read_name = r[8], n_op = rd16(r + 12), l_seq = rd32(r + 16);
+  return 32ull + l_read_name + 4ull * n_op + (l_seq + 1) / 2 + l_seq <= (uint64_t)bs;
+}
+
+// nothing may throw across the C ABI: allocation failures and anything else become status codes
+template <typename F>
+int guarded(F fn) {
+  try { return fn(); }
+  catch (const std::bad_alloc&) { return MCOV_ERR_NOMEM; }
+  catch (...) { return MCOV_ERR_IO; }
+}
+
 }  // namespace
 
 static int read_inflate(mcov_bam* b);
@@ -175,11 +191,15 @@ extern "C" {
 int mcov_bam_open(mcov_bam** out, const char* path, char* err, int errlen) {
   if (!out || !path) return set_err(err, errlen, "mcov_bam_open: null argument");
   *out = nullptr;
-  mcov_bam* b = new mcov_bam();
-  b->path = path;
+  mcov_bam* b = new (std::nothrow) mcov_bam();
+  if (!b) return set_err(err, errlen, "mcov_bam_open: out of memory");
   static const char* msg[] = {"", "mcov_bam_open: cannot open file", "mcov_bam_open: short read",
-                              "mcov_bam_open: not a valid BGZF file", "mcov_bam_open: not a valid BAM file"};
-  int rc = read_inflate(b);
+                              "mcov_bam_open: not a valid BGZF file", "mcov_bam_open: not a valid BAM file",
+                              "mcov_bam_open: out of memory (a corrupt file may ask for more than the host has)"};
+  int rc = 5;
+  try { b->path = path; rc = read_inflate(b); }
+  catch (const std::bad_alloc&) { rc = 5; }
+  catch (...) { rc = 3; }
   if (rc) { delete b; return set_err(err, errlen, msg[rc]); }
   *out = b;
   return MCOV_OK;
@@ -240,16 +260,20 @@ int mcov_bai_stats(const char* bam_path, int64_t* mapped, int64_t* unmapped) {
   return MCOV_OK;
 }
 
+static int bam_load_impl(mcov_bam* b);
 int mcov_bam_load(mcov_bam* b, int /*n_threads*/) {
   if (!b) return MCOV_ERR_ARG;
   if (b->loaded) return MCOV_OK;
+  return guarded([&]() { return bam_load_impl(b); });
+}
+static int bam_load_impl(mcov_bam* b) {
   const uint8_t* d = b->data.data();
   const size_t n = b->data.size();
   // pass 1: count records and ops
   size_t p = b->rec_begin, n_rec = 0, n_cig = 0;
   while (p + 4 <= n) {
     uint32_t bs = rd32(d + p);
-    if (bs < 32 || p + 4 + bs > n) return MCOV_ERR_IO;
+    if (bs < 32 || p + 4 + bs > n || !record_fits(d + p + 4, bs)) return MCOV_ERR_IO;
     n_cig += rd16(d + p + 4 + 12);
     ++n_rec;
     p += 4 + bs;
@@ -296,16 +320,20 @@ const uint32_t* mcov_bam_cig(const mcov_bam* b) { return (b && b->loaded) ? b->c
 
 // Packed SEQ of every record (needed by the k-mer histogram only).  Re-inflates the file when the
 // record pass has already released it.
+static int bam_load_seq_impl(mcov_bam* b);
 int mcov_bam_load_seq(mcov_bam* b) {
   if (!b) return MCOV_ERR_ARG;
   if (b->has_seq) return MCOV_OK;
+  return guarded([&]() { return bam_load_seq_impl(b); });
+}
+static int bam_load_seq_impl(mcov_bam* b) {
   if (b->data.empty()) { if (read_inflate(b)) return MCOV_ERR_IO; }
   const uint8_t* d = b->data.data();
   const size_t n = b->data.size();
   size_t p = b->rec_begin, n_rec = 0, bytes = 0;
   while (p + 4 <= n) {
     uint32_t bs = rd32(d + p);
-    if (bs < 32 || p + 4 + bs > n) return MCOV_ERR_IO;
+    if (bs < 32 || p + 4 + bs > n || !record_fits(d + p + 4, bs)) return MCOV_ERR_IO;
     bytes += ((size_t)rd32(d + p + 4 + 16) + 1) / 2;
     ++n_rec;
     p += 4 + bs;
@@ -344,9 +372,13 @@ int mcov_bam_load_seq(mcov_bam* b) {
 // missing bases are 'N' (15).  This is all the k-mer histogram needs (reference scan.pyx:240-259
 // decodes the whole SEQ and undoes the mapper's reverse complement; only the read's first
 // OFFSET+STEP*(NK-1)+K bases are ever looked at, scan.pyx:513-520).
+static int bam_seq_windows_impl(const mcov_bam* b, int32_t win_bases, uint8_t* out);
 int mcov_bam_seq_windows(const mcov_bam* b, int32_t win_bases, uint8_t* out) {
   if (!b || !out || win_bases <= 0) return MCOV_ERR_ARG;
   if (!b->has_seq || !b->loaded) return MCOV_ERR_ARG;
+  return guarded([&]() { return bam_seq_windows_impl(b, win_bases, out); });
+}
+static int bam_seq_windows_impl(const mcov_bam* b, int32_t win_bases, uint8_t* out) {
   const size_t n = b->tid.size(), W = ((size_t)win_bases + 1) / 2;
   unsigned hw = std::thread::hardware_concurrency();
   int nt = (int)std::max(1u, std::min(hw ? hw : 4u, 32u));

@@ -6,7 +6,6 @@
 
 namespace mcov {
 
-constexpr int kNumSMsB200 = 148;
 constexpr int kStatValidBit = 1;     // mcov_region_stats.flags bit0: record valid
 constexpr int kStatOverflowBit = 2;  // bit1: depth left the counting histogram, radix path used
 
@@ -31,6 +30,7 @@ struct PassCounters {
   unsigned int max_span; // max clipped span of a near read (fused path)
   unsigned int n_far;    // reads whose span exceeds the near window (fused path)
   unsigned int n_heavy;  // tiles holding >= heavy_min reads (fused path: scheduled first)
+  unsigned int cap_contigs;  // contigs replayed under htslib's max_depth cap (k_cap_replay)
 };
 
 // pysam __advance_samtools predicate + bam_plp_push's own UNMAP drop
@@ -123,16 +123,16 @@ __device__ __forceinline__ int warp_min(int v) {
 // warp with 128-bit loads where alignment allows (long-read path, config C5:
 // thousands of ops per read, the CIGAR stream is the dominant HBM traffic).
 __device__ __forceinline__ unsigned long long warp_cigar_reflen(const uint32_t* __restrict__ cig,
-                                                                uint32_t b0, uint32_t b1, int lane,
+                                                                uint64_t b0, uint64_t b1, int lane,
                                                                 bool base_aligned16) {
   unsigned long long acc = 0;
-  uint32_t k = b0;
+  uint64_t k = b0;
   if (base_aligned16) {
-    uint32_t a0 = (b0 + 3u) & ~3u;           // first 16-byte aligned op index
+    uint64_t a0 = (b0 + 3u) & ~(uint64_t)3;  // first 16-byte aligned op index
     if (a0 > b1) a0 = b1;
     // head (< 4 ops)
     if (b0 + (uint32_t)lane < a0) acc += cigar_ref_len(__ldg(cig + b0 + lane));
-    uint32_t nvec = (b1 - a0) >> 2;
+    uint32_t nvec = (uint32_t)((b1 - a0) >> 2);
     const uint4* v = reinterpret_cast<const uint4*>(cig + a0);
     uint32_t j = lane;
     // 4 independent 512-byte warp loads in flight
@@ -148,10 +148,10 @@ __device__ __forceinline__ unsigned long long warp_cigar_reflen(const uint32_t* 
       uint4 q = ld_stream_uint4(v + j);
       acc += cigar_ref_len(q.x) + cigar_ref_len(q.y) + cigar_ref_len(q.z) + cigar_ref_len(q.w);
     }
-    k = a0 + (nvec << 2);                     // tail (< 4 ops)
+    k = a0 + ((uint64_t)nvec << 2);           // tail (< 4 ops)
     if (k + (uint32_t)lane < b1) acc += cigar_ref_len(__ldg(cig + k + lane));
   } else {
-    for (uint32_t i = k + lane; i < b1; i += 32u) acc += cigar_ref_len(__ldg(cig + i));
+    for (uint64_t i = k + lane; i < b1; i += 32u) acc += cigar_ref_len(__ldg(cig + i));
   }
   return warp_sum(acc);
 }

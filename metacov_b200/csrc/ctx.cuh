@@ -70,6 +70,7 @@ struct ReadStage {            // one staging set for host-resident batches
 
 struct mcov_ctx {
   int device = 0;
+  int n_sm = 0;               // multiprocessors of the device (queried in mcov_create); grids are sized from it
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   cudaStream_t copy_stream = nullptr;
@@ -99,7 +100,8 @@ struct mcov_ctx {
   int64_t contig_epoch = 0;
   mcov::RegionPlan plan;
   int32_t cap_contigs = 0;        // contigs replayed under htslib's max_depth cap in the last fused pass
-  std::vector<unsigned char> fused_blob;   // FusedArgs of the last fused pass (k_fused.cuh), for the cap replay
+  uint8_t* cap_flags = nullptr;   // device, [n_contigs]: contigs replayed in the last fused pass (inside d_status)
+  std::vector<unsigned char> fused_blob;   // FusedArgs of the last fused pass (k_fused.cuh)
 
   // GPU-side BAM decode (bam_gpu.cu): compressed image, inflated stream, record-chain scratch, SoA columns
   struct BamDev {

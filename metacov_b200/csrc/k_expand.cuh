@@ -34,7 +34,8 @@ struct ExpandArgs {
   const int32_t* pos;
   const uint16_t* flag;
   const uint8_t* mapq;
-  const uint32_t* cig_off;
+  const uint32_t* cig_off;       // 32-bit op offsets (n+1 entries), or nullptr when cig_off64 is set
+  const uint64_t* cig_off64;     // 64-bit op offsets for batches of 2^32 or more ops (config C5 at full size)
   const uint32_t* cig;
   const int64_t* contig_off;
   const int32_t* contig_len;

@@ -38,6 +38,7 @@
 // tile 4R + 4(L+C).  The kernels of one pass are chained with programmatic
 // dependent launches (pdl_wait / pdl_launch_dependents, common.cuh).
 #pragma once
+#include <type_traits>
 #include "ctx.cuh"
 #include "k_expand.cuh"
 #include "k_scan.cuh"
@@ -89,7 +90,7 @@ __device__ __forceinline__ int64_t slot_key(const ExpandArgs& a, int32_t t, int3
   return base + q;
 }
 
-__device__ __noinline__ unsigned long long warp_cigar_reflen_call(const uint32_t* cig, uint32_t b0, uint32_t b1, int lane,
+__device__ __noinline__ unsigned long long warp_cigar_reflen_call(const uint32_t* cig, uint64_t b0, uint64_t b1, int lane,
                                                                   int aligned16) {
   return warp_cigar_reflen(cig, b0, b1, lane, aligned16 != 0);
 }
@@ -280,13 +281,16 @@ struct PrepReads {
   int nv;                 // valid reads of this thread
 };
 
+// OFF64: the CIGAR offsets are 64-bit (a batch of 2^32 or more ops: config C5 at full size).
+template <bool OFF64>
 __device__ __forceinline__ PrepReads prep_load_reduce(const FusedArgs& f, int64_t i0, int lane) {
+  using off_t = typename std::conditional<OFF64, uint64_t, uint32_t>::type;
   const ExpandArgs& a = f.e;
   const int32_t* __restrict__ g_tid = a.tid;
   const int32_t* __restrict__ g_pos = a.pos;
   const uint16_t* __restrict__ g_flag = a.flag;
   const uint8_t* __restrict__ g_mapq = a.mapq;
-  const uint32_t* __restrict__ g_off = a.cig_off;
+  const off_t* __restrict__ g_off = OFF64 ? reinterpret_cast<const off_t*>(a.cig_off64) : reinterpret_cast<const off_t*>(a.cig_off);
   const uint32_t* __restrict__ g_cig = a.cig;
   const uint32_t n_contigs = (uint32_t)a.n_contigs;
   // pysam __advance_samtools + bam_plp_push's UNMAP drop, branch-free:
@@ -295,20 +299,26 @@ __device__ __forceinline__ PrepReads prep_load_reduce(const FusedArgs& f, int64_
   const uint32_t req_none = req == 0 ? 1u : 0u, orph_mask = a.filt.ignore_orphans ? 3u : 0u;
   const int64_t n = a.n;
   PrepReads R;
-  uint32_t F[4], Q[4], O[5];
+  uint32_t F[4], Q[4];
+  off_t O[5];
   R.nv = (int)min((int64_t)kPrepPer, max((int64_t)0, n - i0));
   if (R.nv == kPrepPer && f.vec_ok) {
     int4 t4 = *reinterpret_cast<const int4*>(g_tid + i0);
     int4 p4 = *reinterpret_cast<const int4*>(g_pos + i0);
     ushort4 f4 = *reinterpret_cast<const ushort4*>(g_flag + i0);
     uchar4 q4 = *reinterpret_cast<const uchar4*>(g_mapq + i0);
-    uint4 o4 = *reinterpret_cast<const uint4*>(g_off + i0);
+    if (OFF64) {
+      const ulonglong2 oa = *reinterpret_cast<const ulonglong2*>(g_off + i0), ob = *reinterpret_cast<const ulonglong2*>(g_off + i0 + 2);
+      O[0] = (off_t)oa.x; O[1] = (off_t)oa.y; O[2] = (off_t)ob.x; O[3] = (off_t)ob.y;
+    } else {
+      const uint4 o4 = *reinterpret_cast<const uint4*>(g_off + i0);
+      O[0] = o4.x; O[1] = o4.y; O[2] = o4.z; O[3] = o4.w;
+    }
     O[4] = g_off[i0 + 4];
     R.T[0] = t4.x; R.T[1] = t4.y; R.T[2] = t4.z; R.T[3] = t4.w;
     R.P[0] = p4.x; R.P[1] = p4.y; R.P[2] = p4.z; R.P[3] = p4.w;
     F[0] = f4.x; F[1] = f4.y; F[2] = f4.z; F[3] = f4.w;
     Q[0] = q4.x; Q[1] = q4.y; Q[2] = q4.z; Q[3] = q4.w;
-    O[0] = o4.x; O[1] = o4.y; O[2] = o4.z; O[3] = o4.w;
   } else {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -320,7 +330,7 @@ __device__ __forceinline__ PrepReads prep_load_reduce(const FusedArgs& f, int64_
     }
     // padding reads get an empty CIGAR: their offsets all equal cig_off[n]
 #pragma unroll
-    for (int r = 0; r <= 4; ++r) O[r] = (i0 <= n) ? g_off[min(i0 + r, n)] : 0u;
+    for (int r = 0; r <= 4; ++r) O[r] = (i0 <= n) ? g_off[min(i0 + r, n)] : (off_t)0;
   }
   unsigned passm = 0, coop = 0;
   uint32_t op0[4], nc[4];
@@ -329,7 +339,7 @@ __device__ __forceinline__ PrepReads prep_load_reduce(const FusedArgs& f, int64_
   for (int r = 0; r < 4; ++r) {
     const bool p = (r < R.nv) & ((F[r] & drop) == 0u) & (((F[r] & req) | req_none) != 0u) & (Q[r] >= minq) &
                    ((F[r] & orph_mask) != 1u) & ((uint32_t)R.T[r] < n_contigs);
-    nc[r] = O[r + 1] - O[r];
+    nc[r] = (uint32_t)(O[r + 1] - O[r]);
     bool c = p && nc[r] > kThreadOps;
     passm |= p ? (1u << r) : 0u;
     coop |= c ? (1u << r) : 0u;
@@ -352,8 +362,8 @@ __device__ __forceinline__ PrepReads prep_load_reduce(const FusedArgs& f, int64_
     unsigned lanes = __ballot_sync(0xffffffffu, coop != 0);
     int src = __ffs(lanes) - 1;
     int r = __ffs(__shfl_sync(0xffffffffu, coop, src)) - 1;
-    uint32_t ob = r == 0 ? O[0] : r == 1 ? O[1] : r == 2 ? O[2] : O[3];
-    uint32_t oe = r == 0 ? O[1] : r == 1 ? O[2] : r == 2 ? O[3] : O[4];
+    off_t ob = r == 0 ? O[0] : r == 1 ? O[1] : r == 2 ? O[2] : O[3];
+    off_t oe = r == 0 ? O[1] : r == 1 ? O[2] : r == 2 ? O[3] : O[4];
     ob = __shfl_sync(0xffffffffu, ob, src);
     oe = __shfl_sync(0xffffffffu, oe, src);
     unsigned long long v = warp_cigar_reflen_call(g_cig, ob, oe, lane, a.cig_aligned16);
@@ -392,6 +402,7 @@ __device__ __forceinline__ void prep_flush_counters(PassCounters* pc, uint32_t n
 
 // K1 of the push path (any read order): filter + CIGAR reduce + difference-array deltas, see
 // k_expand.cuh.  Shares prep_load_reduce with the fused path (only f.e and f.vec_ok are read).
+template <bool OFF64>
 __global__ void __launch_bounds__(kPrepThreads, 4)
 k_expand(const __grid_constant__ FusedArgs f) {
   const ExpandArgs& a = f.e;
@@ -413,7 +424,7 @@ k_expand(const __grid_constant__ FusedArgs f) {
     int32_t pvT = 0, pvP = 0;
     const bool has_prev = lane == 0 && i0 > 0 && i0 - 1 < n;
     if (has_prev) { pvT = a.tid[i0 - 1]; pvP = a.pos[i0 - 1]; }
-    const PrepReads R = prep_load_reduce(f, i0, lane);
+    const PrepReads R = prep_load_reduce<OFF64>(f, i0, lane);
     // sortedness by (tid as unsigned: unplaced reads sort last, pos) -- informational (mcov_pass_info.sorted)
     {
       uint32_t pt = __shfl_up_sync(0xffffffffu, (uint32_t)R.T[3], 1);
@@ -544,6 +555,7 @@ __device__ __forceinline__ void prep_emit(const FusedArgs& f, const int64_t i0, 
 }
 
 // First kernel of the fused path: 4 consecutive reads per thread, 128-bit SoA loads.
+template <bool OFF64>
 __global__ void __launch_bounds__(kPrepThreads, 4)
 k_fused_prep(const __grid_constant__ FusedArgs f) {
   pdl_launch_dependents();                                    // k_scan_counts may take free slots as this grid drains
@@ -560,7 +572,7 @@ k_fused_prep(const __grid_constant__ FusedArgs f) {
     // the read before this warp's first one (lane 0 only): sortedness and tile border across warps
     int32_t pvT = -1, pvP = -1;
     if (lane == 0 && i0 > 0 && i0 - 1 < n) { pvT = a.tid[i0 - 1]; pvP = a.pos[i0 - 1]; }
-    const PrepReads R = prep_load_reduce(f, i0, lane);
+    const PrepReads R = prep_load_reduce<OFF64>(f, i0, lane);
     prep_emit(f, i0, R, pvT, pvP, lane, W);
   }
   prep_flush_counters(a.pc, W.n_pass, W.aligned, W.unsorted, W.max_span);
@@ -886,10 +898,25 @@ k_fused_tile(const __grid_constant__ FusedArgs f) {
 // on earlier decisions, so a contig is replayed by ONE thread, in place: the contig's slots are
 // first cleared, kept reads add +1 at their end slot, and the running depth overwrites each slot
 // as the walk passes it.  Only contigs flagged through tile_cap are replayed.
-__global__ void k_cap_replay(FusedArgs f, const int32_t* __restrict__ contigs, int n_flagged) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n_flagged) return;
-  const int c = contigs[k];
+__global__ void k_cap_replay(FusedArgs f, uint8_t* __restrict__ contig_capped) {
+  pdl_wait();                                       // the tile kernel is complete: cap_metric and tile_cap are final
+  pdl_launch_dependents();
+  // Launched after EVERY fused pass on the same stream, so whatever consumes the depth next
+  // (statistics, copies, exports, pipelined or not) sees the capped depth; one load and out when
+  // the cap cannot fire anywhere (always, in BASELINE's configs).
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= f.e.n_contigs || f.max_depth <= 0) return;
+  if (f.e.pc->cap_metric <= f.max_depth) return;
+  if (f.e.pc->unsorted || f.e.pc->n_far > f.far_cap) return;     // the pass is rejected by the verdict: nothing to replay
+  {
+    const int64_t b0 = f.e.contig_off[c];
+    const int64_t T0 = b0 >> kTileShift, T1 = min((b0 + f.e.contig_len[c]) >> kTileShift, f.n_tiles - 1);
+    bool hit = false;
+    for (int64_t T = T0; T <= T1 && !hit; ++T) hit = f.tile_cap[T] > f.max_depth;
+    if (!hit) return;
+  }
+  atomicAdd(&f.e.pc->cap_contigs, 1u);
+  contig_capped[c] = 1;
   const int64_t base = f.e.contig_off[c];
   const int32_t len = f.e.contig_len[c];
   int32_t* d = f.depth + base;
@@ -925,7 +952,9 @@ __global__ void k_cap_replay(FusedArgs f, const int32_t* __restrict__ contigs, i
         int64_t span = code;
         if (code == kRecFar) {                      // long span: not in the record, reduce the CIGAR again
           int64_t rl = 0;
-          for (uint32_t o = f.e.cig_off[j - 1]; o < f.e.cig_off[j]; ++o) rl += cigar_ref_len(f.e.cig[o]);
+          const uint64_t o0 = f.e.cig_off64 ? f.e.cig_off64[j - 1] : f.e.cig_off[j - 1];
+          const uint64_t o1 = f.e.cig_off64 ? f.e.cig_off64[j] : f.e.cig_off[j];
+          for (uint64_t o = o0; o < o1; ++o) rl += cigar_ref_len(f.e.cig[o]);
           int64_t e = (int64_t)p + rl;
           span = (e > len ? len : e) - p;
         }

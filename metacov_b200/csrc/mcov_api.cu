@@ -38,9 +38,9 @@ int fail(mcov_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
     if (e__ != cudaSuccess) return fail(ctx, MCOV_ERR_CUDA, #call, e__); \
   } while (0)
 
-int grid_for(int64_t n, int threads, int per_sm) {
+int grid_for(const mcov_ctx* ctx, int64_t n, int threads, int per_sm) {
   int64_t want = (n + threads - 1) / threads;
-  int64_t cap = (int64_t)kNumSMsB200 * per_sm;
+  int64_t cap = (int64_t)ctx->n_sm * per_sm;
   if (want < 1) want = 1;
   return (int)std::min<int64_t>(want, cap);
 }
@@ -80,30 +80,34 @@ int ensure_depth(mcov_ctx* ctx) {
 // pass device pointers through.  On return `a` holds device pointers and the
 // compute stream has been made to wait for the copies.
 int stage_reads(mcov_ctx* ctx, int64_t n, const int32_t* tid, const int32_t* pos, const uint16_t* flag,
-                const uint8_t* mapq, const uint32_t* cig_off, const uint32_t* cig, int mem_kind,
+                const uint8_t* mapq, const void* cig_off, bool off64, const uint32_t* cig, int mem_kind,
                 ExpandArgs& a, ReadStage** used) {
   *used = nullptr;
   a.n = n;
+  a.cig_off = nullptr; a.cig_off64 = nullptr;
+  const size_t ow = off64 ? 8 : 4;
   if (mem_kind == MCOV_MEM_DEVICE) {
-    a.tid = tid; a.pos = pos; a.flag = flag; a.mapq = mapq; a.cig_off = cig_off; a.cig = cig;
+    a.tid = tid; a.pos = pos; a.flag = flag; a.mapq = mapq; a.cig = cig;
+    if (off64) a.cig_off64 = static_cast<const uint64_t*>(cig_off); else a.cig_off = static_cast<const uint32_t*>(cig_off);
   } else if (mem_kind == MCOV_MEM_HOST) {
     ReadStage& s = ctx->stage[ctx->stage_next];
     ctx->stage_next ^= 1;
     if (s.in_flight) { CU(cudaEventSynchronize(s.consumed)); s.in_flight = false; }
-    uint32_t n_cig = cig_off[n];
+    const uint64_t n_cig = off64 ? static_cast<const uint64_t*>(cig_off)[n] : static_cast<const uint32_t*>(cig_off)[n];
     CU(s.tid.ensure(n * 4)); CU(s.pos.ensure(n * 4)); CU(s.flag.ensure(n * 2)); CU(s.mapq.ensure(n));
-    CU(s.cig_off.ensure((n + 1) * 4)); CU(s.cig.ensure((size_t)n_cig * 4 + 16));
+    CU(s.cig_off.ensure((n + 1) * ow)); CU(s.cig.ensure((size_t)n_cig * 4 + 16));
     cudaStream_t cs = ctx->copy_stream;
     CU(cudaMemcpyAsync(s.tid.p, tid, n * 4, cudaMemcpyHostToDevice, cs));
     CU(cudaMemcpyAsync(s.pos.p, pos, n * 4, cudaMemcpyHostToDevice, cs));
     CU(cudaMemcpyAsync(s.flag.p, flag, n * 2, cudaMemcpyHostToDevice, cs));
     CU(cudaMemcpyAsync(s.mapq.p, mapq, n, cudaMemcpyHostToDevice, cs));
-    CU(cudaMemcpyAsync(s.cig_off.p, cig_off, (n + 1) * 4, cudaMemcpyHostToDevice, cs));
+    CU(cudaMemcpyAsync(s.cig_off.p, cig_off, (n + 1) * ow, cudaMemcpyHostToDevice, cs));
     if (n_cig) CU(cudaMemcpyAsync(s.cig.p, cig, (size_t)n_cig * 4, cudaMemcpyHostToDevice, cs));
     CU(cudaEventRecord(ctx->copied, cs));
     CU(cudaStreamWaitEvent(ctx->stream, ctx->copied, 0));
     a.tid = s.tid.as<int32_t>(); a.pos = s.pos.as<int32_t>(); a.flag = s.flag.as<uint16_t>();
-    a.mapq = s.mapq.as<uint8_t>(); a.cig_off = s.cig_off.as<uint32_t>(); a.cig = s.cig.as<uint32_t>();
+    a.mapq = s.mapq.as<uint8_t>(); a.cig = s.cig.as<uint32_t>();
+    if (off64) a.cig_off64 = s.cig_off.as<uint64_t>(); else a.cig_off = s.cig_off.as<uint32_t>();
     *used = &s;
   } else {
     return fail(ctx, MCOV_ERR_ARG, "mem_kind must be MCOV_MEM_HOST or MCOV_MEM_DEVICE");
@@ -136,10 +140,10 @@ int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a) {
   const int64_t scan_len = 2 * cnt_pad;                                // [tile_agg | tile_cnt]
   const int64_t scan_tiles = (scan_len + kScanTile - 1) / kScanTile;
   const uint32_t far_cap = (uint32_t)std::min<int64_t>(std::max<int64_t>(n, 1), kFarCapDefault);
-  // one zeroed scratch block: [tile_agg | tile_cnt | tile_cursor | tile_cap | scan status]
+  // one zeroed scratch block: [tile_agg | tile_cnt | tile_cursor | tile_cap | scan status | per-contig "capped" flags]
   const size_t o_agg = 0, o_cnt = o_agg + (size_t)cnt_pad * 4, o_cur = o_cnt + (size_t)cnt_pad * 4,
                o_cap = o_cur + (size_t)n_tiles * 4, o_st = (o_cap + (size_t)n_tiles * 4 + 7) & ~(size_t)7,
-               z_bytes = o_st + (size_t)scan_tiles * 8;
+               o_flag = o_st + (size_t)scan_tiles * 8, z_bytes = o_flag + (size_t)ctx->n_contigs;
   CU(ctx->d_status.ensure(z_bytes));
   CU(ctx->d_start_slot.ensure((size_t)(std::max<int64_t>(n, 1) + 8) * sizeof(uint32_t)));   // rec (+ vector-load padding)
   CU(ctx->d_tile_off.ensure((size_t)(n_tiles + 1) * 4));                                 // tile_first
@@ -168,10 +172,13 @@ int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a) {
   f.tile_cap = reinterpret_cast<int32_t*>(z + o_cap);
   f.max_depth = ctx->filt.max_depth;
   auto al = [](const void* p, uintptr_t m) { return (reinterpret_cast<uintptr_t>(p) & (m - 1)) == 0; };
-  f.vec_ok = (n > 0 && al(a.tid, 16) && al(a.pos, 16) && al(a.cig_off, 16) && al(a.flag, 8) && al(a.mapq, 4)) ? 1 : 0;
+  const bool off64 = a.cig_off64 != nullptr;
+  f.vec_ok = (n > 0 && al(a.tid, 16) && al(a.pos, 16) && al(off64 ? (const void*)a.cig_off64 : (const void*)a.cig_off, 16) &&
+              al(a.flag, 8) && al(a.mapq, 4)) ? 1 : 0;
   if (n > 0) {
     const int64_t groups = (n + kPrepPer - 1) / kPrepPer;
-    MCOV_LAUNCH(ctx, kKFusedPrep, (k_fused_prep<<<grid_for(groups, kPrepThreads, 8), kPrepThreads, 0, s>>>(f)));
+    if (off64) MCOV_LAUNCH(ctx, kKFusedPrep, (k_fused_prep<true><<<grid_for(ctx, groups, kPrepThreads, 8), kPrepThreads, 0, s>>>(f)));
+    else MCOV_LAUNCH(ctx, kKFusedPrep, (k_fused_prep<false><<<grid_for(ctx, groups, kPrepThreads, 8), kPrepThreads, 0, s>>>(f)));
     CU(cudaGetLastError());
   } else {
     CU(cudaMemsetAsync(f.tile_first, 0, (size_t)(n_tiles + 1) * 4, s));
@@ -181,12 +188,19 @@ int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a) {
   const bool pdl = ctx->n_slots <= kPdlMaxSlots;
   MCOV_LAUNCH(ctx, kKScanCounts, CU(launch_pdl(pdl, k_scan_inplace<false>, dim3((unsigned)scan_tiles), dim3(kScanThreads), 0, s,
       f.tile_agg, scan_len, reinterpret_cast<unsigned long long*>(z + o_st), pc_of(ctx))));
-  MCOV_LAUNCH(ctx, kKFarScatter, CU(launch_pdl(pdl, k_far_scatter, dim3(kNumSMsB200 * 2), dim3(256), 0, s, f)));
+  MCOV_LAUNCH(ctx, kKFarScatter, CU(launch_pdl(pdl, k_far_scatter, dim3(ctx->n_sm * 2), dim3(256), 0, s, f)));
   ctx->fused_blob.assign(reinterpret_cast<const unsigned char*>(&f), reinterpret_cast<const unsigned char*>(&f) + sizeof(f));
   {
-    const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)kNumSMsB200 * MCOV_TILE_MIN_CTAS);   // persistent
+    const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)ctx->n_sm * MCOV_TILE_MIN_CTAS);   // persistent
     MCOV_LAUNCH(ctx, kKFusedTile, CU(launch_pdl(pdl, k_fused_tile, dim3(grid), dim3(kFusedThreads), 0, s, f)));
   }
+  // htslib's max_depth cap: replayed on the device, in stream order, where the tile kernel found that
+  // it can fire (k_cap_replay returns after one load otherwise) -- every consumer of the depth that
+  // follows on this stream sees the capped values, whether or not the host has looked at the verdict yet
+  ctx->cap_flags = reinterpret_cast<uint8_t*>(z + o_flag);
+  if (f.max_depth > 0)
+    MCOV_LAUNCH(ctx, kKCapReplay, CU(launch_pdl(pdl, k_cap_replay, dim3((unsigned)((ctx->n_contigs + 127) / 128)), dim3(128), 0, s,
+                                                f, ctx->cap_flags)));
   return MCOV_OK;
 }
 
@@ -203,35 +217,7 @@ int fused_verdict(mcov_ctx* ctx, const PassCounters& h) {
     ctx->state = kIdle;
     return fail(ctx, MCOV_ERR_RANGE, "mcov_depth_sorted: too many long-span reads for the bucket list; use mcov_begin/push/finalize");
   }
-  ctx->cap_contigs = 0;
-  if (ctx->filt.max_depth > 0 && h.cap_metric > ctx->filt.max_depth) {
-    // htslib's max_depth cap fires somewhere: replay the affected contigs exactly (k_cap_replay)
-    FusedArgs f;
-    std::memcpy(&f, ctx->fused_blob.data(), sizeof(f));
-    std::vector<int32_t> tc((size_t)f.n_tiles);
-    CU(cudaMemcpyAsync(tc.data(), f.tile_cap, (size_t)f.n_tiles * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    std::vector<int32_t> flagged;
-    for (int64_t T = 0; T < f.n_tiles; ++T) {
-      if (tc[T] <= ctx->filt.max_depth) continue;
-      // contigs with a slot in tile T
-      int64_t lo = T * kTile, hi = std::min<int64_t>(lo + kTile, ctx->n_slots);
-      int32_t c = (int32_t)(std::upper_bound(ctx->off.begin(), ctx->off.begin() + ctx->n_contigs, lo) - ctx->off.begin()) - 1;
-      for (; c < ctx->n_contigs && ctx->off[c] < hi; ++c)
-        if (c >= 0 && (flagged.empty() || flagged.back() != c)) flagged.push_back(c);
-    }
-    std::sort(flagged.begin(), flagged.end());
-    flagged.erase(std::unique(flagged.begin(), flagged.end()), flagged.end());
-    if (!flagged.empty()) {
-      CU(ctx->d_win_n.ensure(flagged.size() * 4));
-      CU(cudaMemcpyAsync(ctx->d_win_n.p, flagged.data(), flagged.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-      MCOV_LAUNCH(ctx, kKCapReplay, (k_cap_replay<<<(unsigned)((flagged.size() + 31) / 32), 32, 0, ctx->stream>>>(
-          f, ctx->d_win_n.as<int32_t>(), (int)flagged.size())));
-      CU(cudaGetLastError());
-      CU(cudaStreamSynchronize(ctx->stream));
-      ctx->cap_contigs = (int32_t)flagged.size();
-    }
-  }
+  ctx->cap_contigs = (int32_t)h.cap_contigs;        // replayed by k_cap_replay right after the tile kernel
   return MCOV_OK;
 }
 
@@ -261,6 +247,7 @@ int mcov_create(mcov_ctx** out, int device, void* stream) {
   if (!ctx) return MCOV_ERR_NOMEM;
   ctx->device = device;
   if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return MCOV_ERR_CUDA; }
+  if (cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || ctx->n_sm <= 0) { delete ctx; return MCOV_ERR_CUDA; }
   if (stream) { ctx->stream = reinterpret_cast<cudaStream_t>(stream); ctx->own_stream = false; }
   else {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MCOV_ERR_CUDA; }
@@ -424,7 +411,7 @@ int mcov_depth_sorted_delta(mcov_ctx* ctx, int64_t n, const int64_t* contig_read
     MCOV_LAUNCH(ctx, kKScanCounts, (k_scan_inplace<false><<<(unsigned)tiles, kScanThreads, 0, s>>>(S, off_len, stw + tiles, pc_of(ctx))));
     CU(cudaGetLastError());
   }
-  MCOV_LAUNCH(ctx, kKDeltaUnpack, (k_delta_finish<<<grid_for(std::max<int64_t>(n1, n_cig_total), 256, 8), 256, 0, s>>>(
+  MCOV_LAUNCH(ctx, kKDeltaUnpack, (k_delta_finish<<<grid_for(ctx, std::max<int64_t>(n1, n_cig_total), 256, 8), 256, 0, s>>>(
       n, d_crs, ctx->n_contigs, st.tid.as<int32_t>(), S, st.pos.as<int32_t>(), reinterpret_cast<const uint16_t*>(x + o_c16),
       st.cig.as<uint32_t>(), n_cig_total)));
   CU(cudaGetLastError());
@@ -463,8 +450,8 @@ int mcov_begin(mcov_ctx* ctx) {
   return MCOV_OK;
 }
 
-int mcov_push_reads(mcov_ctx* ctx, int64_t n, const int32_t* tid, const int32_t* pos, const uint16_t* flag,
-                    const uint8_t* mapq, const uint32_t* cig_off, const uint32_t* cig, int mem_kind) {
+static int push_reads_impl(mcov_ctx* ctx, int64_t n, const int32_t* tid, const int32_t* pos, const uint16_t* flag,
+                           const uint8_t* mapq, const void* cig_off, bool off64, const uint32_t* cig, int mem_kind) {
   if (!ctx) return MCOV_ERR_ARG;
   if (ctx->state != kAccumulating) return fail(ctx, MCOV_ERR_STATE, "mcov_push_reads: call mcov_begin first");
   if (n < 0) return fail(ctx, MCOV_ERR_ARG, "mcov_push_reads: n < 0");
@@ -473,19 +460,32 @@ int mcov_push_reads(mcov_ctx* ctx, int64_t n, const int32_t* tid, const int32_t*
   CU(cudaSetDevice(ctx->device));
   ExpandArgs a;
   ReadStage* st = nullptr;
-  int rc = stage_reads(ctx, n, tid, pos, flag, mapq, cig_off, cig, mem_kind, a, &st);
+  int rc = stage_reads(ctx, n, tid, pos, flag, mapq, cig_off, off64, cig, mem_kind, a, &st);
   if (rc) return rc;
   FusedArgs f;
   std::memset(&f, 0, sizeof(f));
   f.e = a;
   {
     auto al = [](const void* p, uintptr_t m) { return (reinterpret_cast<uintptr_t>(p) & (m - 1)) == 0; };
-    f.vec_ok = (al(a.tid, 16) && al(a.pos, 16) && al(a.cig_off, 16) && al(a.flag, 8) && al(a.mapq, 4)) ? 1 : 0;
+    f.vec_ok = (al(a.tid, 16) && al(a.pos, 16) && al(off64 ? (const void*)a.cig_off64 : (const void*)a.cig_off, 16) &&
+                al(a.flag, 8) && al(a.mapq, 4)) ? 1 : 0;
   }
-  MCOV_LAUNCH(ctx, kKExpand, (k_expand<<<grid_for((n + kPrepPer - 1) / kPrepPer, kPrepThreads, 8), kPrepThreads, 0, ctx->stream>>>(f)));
+  const int grid = grid_for(ctx, (n + kPrepPer - 1) / kPrepPer, kPrepThreads, 8);
+  if (off64) MCOV_LAUNCH(ctx, kKExpand, (k_expand<true><<<grid, kPrepThreads, 0, ctx->stream>>>(f)));
+  else MCOV_LAUNCH(ctx, kKExpand, (k_expand<false><<<grid, kPrepThreads, 0, ctx->stream>>>(f)));
   CU(cudaGetLastError());
   ctx->n_reads_pushed += n;
   return finish_stage(ctx, st);
+}
+
+int mcov_push_reads(mcov_ctx* ctx, int64_t n, const int32_t* tid, const int32_t* pos, const uint16_t* flag,
+                    const uint8_t* mapq, const uint32_t* cig_off, const uint32_t* cig, int mem_kind) {
+  return push_reads_impl(ctx, n, tid, pos, flag, mapq, cig_off, false, cig, mem_kind);
+}
+
+int mcov_push_reads_wide(mcov_ctx* ctx, int64_t n, const int32_t* tid, const int32_t* pos, const uint16_t* flag,
+                         const uint8_t* mapq, const uint64_t* cig_off, const uint32_t* cig, int mem_kind) {
+  return push_reads_impl(ctx, n, tid, pos, flag, mapq, cig_off, true, cig, mem_kind);
 }
 
 int mcov_finalize(mcov_ctx* ctx) {
@@ -503,7 +503,7 @@ int mcov_finalize(mcov_ctx* ctx) {
 }
 
 static int depth_sorted_impl(mcov_ctx* ctx, int64_t n, const int32_t* tid, const int32_t* pos, const uint16_t* flag,
-                             const uint8_t* mapq, const uint32_t* cig_off, const uint32_t* cig, int mem_kind, bool wait) {
+                             const uint8_t* mapq, const void* cig_off, bool off64, const uint32_t* cig, int mem_kind, bool wait) {
   if (!ctx) return MCOV_ERR_ARG;
   if (n < 0) return fail(ctx, MCOV_ERR_ARG, "mcov_depth_sorted: n < 0");
   if (n > 0 && (!tid || !pos || !flag || !mapq || !cig_off)) return fail(ctx, MCOV_ERR_ARG, "mcov_depth_sorted: null array");
@@ -514,7 +514,7 @@ static int depth_sorted_impl(mcov_ctx* ctx, int64_t n, const int32_t* tid, const
   ExpandArgs a;
   ReadStage* st = nullptr;
   if (n > 0) {
-    rc = stage_reads(ctx, n, tid, pos, flag, mapq, cig_off, cig, mem_kind, a, &st);
+    rc = stage_reads(ctx, n, tid, pos, flag, mapq, cig_off, off64, cig, mem_kind, a, &st);
     if (rc) return rc;
   } else {
     std::memset(&a, 0, sizeof(a));
@@ -537,12 +537,17 @@ static int depth_sorted_impl(mcov_ctx* ctx, int64_t n, const int32_t* tid, const
 
 int mcov_depth_sorted(mcov_ctx* ctx, int64_t n, const int32_t* tid, const int32_t* pos, const uint16_t* flag,
                       const uint8_t* mapq, const uint32_t* cig_off, const uint32_t* cig, int mem_kind) {
-  return depth_sorted_impl(ctx, n, tid, pos, flag, mapq, cig_off, cig, mem_kind, true);
+  return depth_sorted_impl(ctx, n, tid, pos, flag, mapq, cig_off, false, cig, mem_kind, true);
+}
+
+int mcov_depth_sorted_wide(mcov_ctx* ctx, int64_t n, const int32_t* tid, const int32_t* pos, const uint16_t* flag,
+                           const uint8_t* mapq, const uint64_t* cig_off, const uint32_t* cig, int mem_kind, int wait) {
+  return depth_sorted_impl(ctx, n, tid, pos, flag, mapq, cig_off, true, cig, mem_kind, wait != 0);
 }
 
 int mcov_depth_sorted_async(mcov_ctx* ctx, int64_t n, const int32_t* tid, const int32_t* pos, const uint16_t* flag,
                             const uint8_t* mapq, const uint32_t* cig_off, const uint32_t* cig, int mem_kind) {
-  return depth_sorted_impl(ctx, n, tid, pos, flag, mapq, cig_off, cig, mem_kind, false);
+  return depth_sorted_impl(ctx, n, tid, pos, flag, mapq, cig_off, false, cig, mem_kind, false);
 }
 
 int mcov_depth_sorted_packed(mcov_ctx* ctx, int64_t n, const int64_t* contig_read_start, const int32_t* pos,
@@ -733,7 +738,7 @@ static int stats_launch(mcov_ctx* ctx, int64_t g, const int32_t* tid, const int3
     // on C2 (1 000 regions of 50 kb): 52 us with one chunk per region, 62 / 73 / 87 us with chunks of
     // 32 k / 16 k / 8 k slots.  So chunks are as long as possible (64 k slots) and only shrink when
     // the work would otherwise leave the machine underfilled (~1.5 waves of 4 CTAs/SM).
-    int64_t chunk_max = (total / ((int64_t)kNumSMsB200 * 6) + 4095) / 4096 * 4096;
+    int64_t chunk_max = (total / ((int64_t)ctx->n_sm * 6) + 4095) / 4096 * 4096;
     chunk_max = std::max<int64_t>(8192, std::min<int64_t>(65536, chunk_max));
     if (const char* ov = std::getenv("MCOV_STAT_CHUNK")) {          // tuning hook
       int64_t v = std::atoll(ov);
@@ -823,7 +828,7 @@ static int stats_launch(mcov_ctx* ctx, int64_t g, const int32_t* tid, const int3
       const unsigned wgrid = (unsigned)((rp.n_small + kWarpsPerCta - 1) / kWarpsPerCta);
       MCOV_LAUNCH(ctx, kKRegionStatsWarp, (k_region_stats_warp<<<wgrid, kWarpsPerCta * 32, 0, s>>>(a, rp.n_tasks, rp.n_small, retry)));
       CU(cudaGetLastError());
-      const unsigned rgrid = (unsigned)std::min<int64_t>(rp.n_small, (int64_t)kNumSMsB200 * 6);
+      const unsigned rgrid = (unsigned)std::min<int64_t>(rp.n_small, (int64_t)ctx->n_sm * 6);
       MCOV_LAUNCH(ctx, kKRegionStatsSmall, (k_region_stats_small<<<rgrid, kSmallThreads, 0, s>>>(a, retry)));
       CU(cudaGetLastError());
     }
@@ -941,8 +946,7 @@ static int stats_collect_common(mcov_ctx* ctx, int slot, mcov_region_stats** vie
     if (h.unsorted) return fail(ctx, MCOV_ERR_UNSORTED, "mcov_region_stats_collect: the reads of that pass were not sorted by (tid,pos)");
     if ((int64_t)h.n_far > std::min<int64_t>(std::max<int64_t>(sl.n_reads, 1), kFarCapDefault))
       return fail(ctx, MCOV_ERR_RANGE, "mcov_region_stats_collect: too many long-span reads in that pass");
-    if (ctx->filt.max_depth > 0 && h.cap_metric > ctx->filt.max_depth)
-      return fail(ctx, MCOV_ERR_STATE, "mcov_region_stats_collect: that pass needs the max_depth replay; rerun it through mcov_depth_sorted + mcov_region_stats_run");
+    ctx->cap_contigs = (int32_t)h.cap_contigs;      // (the replay ran on the device before the statistics kernels)
   }
   mcov_region_stats* rec = sl.buf.as<mcov_region_stats>();
   for (int32_t i : sl.len0) std::memset(&rec[i], 0, sizeof(mcov_region_stats));
@@ -1072,7 +1076,7 @@ int mcov_depth_runs(mcov_ctx* ctx, int32_t tid0, int32_t tid1, int64_t* n_runs_o
     MCOV_LAUNCH(ctx, kKRunWrite, (k_run_write<<<(unsigned)nt, kRunThreads, 0, s>>>(ctx->depth, ctx->d_run_tasks.as<RunTask>(), counts,
                                                                                     o, o + total, o + 3 * total)));
     CU(cudaGetLastError());
-    MCOV_LAUNCH(ctx, kKRunEnds, (k_run_ends<<<grid_for(total, 256, 8), 256, 0, s>>>(o, o + total, ctx->d_len.as<int32_t>(), total, o + 2 * total)));
+    MCOV_LAUNCH(ctx, kKRunEnds, (k_run_ends<<<grid_for(ctx, total, 256, 8), 256, 0, s>>>(o, o + total, ctx->d_len.as<int32_t>(), total, o + 2 * total)));
     CU(cudaGetLastError());
   }
   ctx->n_runs = total;
@@ -1160,7 +1164,7 @@ int mcov_isize_hist(mcov_ctx* ctx, int64_t n, const uint16_t* flag, const int32_
       a.flag = flag; a.isize = isize;
     } else return fail(ctx, MCOV_ERR_ARG, "mcov_isize_hist: bad mem_kind");
     int use_smem = ((int64_t)groups * n_bins <= kIsizeSmemBins) ? 1 : 0;
-    int grid = grid_for(n, kHistThreads, 4);
+    int grid = grid_for(ctx, n, kHistThreads, 4);
     MCOV_LAUNCH(ctx, kKIsizeHist, (k_isize_hist<<<grid, kHistThreads, 0, s>>>(a, use_smem)));
     CU(cudaGetLastError());
     MCOV_LAUNCH(ctx, kKGroupCount, (k_group_count<<<grid, kHistThreads, 0, s>>>(a)));
@@ -1200,7 +1204,7 @@ int mcov_kmer_hist(mcov_ctx* ctx, int64_t n, const uint16_t* flag, const int32_t
     a.n_group_flags = n_group_flags;
     for (int k = 0; k < kMaxGroupFlags; ++k) a.group_flags[k] = k < n_group_flags ? group_flags[k] : 0;
     a.hist = ctx->d_win_out.as<uint32_t>();
-    MCOV_LAUNCH(ctx, kKKmerHist, (k_kmer_hist<<<grid_for(n, kHistThreads, 8), kHistThreads, 0, s>>>(a)));
+    MCOV_LAUNCH(ctx, kKKmerHist, (k_kmer_hist<<<grid_for(ctx, n, kHistThreads, 8), kHistThreads, 0, s>>>(a)));
     CU(cudaGetLastError());
   }
   CU(cudaMemcpyAsync(hist_out, ctx->d_win_out.p, hist_bytes, cudaMemcpyDeviceToHost, s));

@@ -58,7 +58,7 @@ int mcov_order_stats_by_sort(mcov_ctx* ctx, const int32_t* d_region, int64_t n, 
     return MCOV_ERR_CUDA;
   if (cudaMemsetAsync(d_stat, 0, sizeof(mcov_region_stats), s) != cudaSuccess) return MCOV_ERR_CUDA;
   ctx->prof_begin(kKSortedStats);
-  k_sorted_stats<<<kNumSMsB200, 256, 0, s>>>(keys_out.as<int32_t>(), n, pad, breadth_n, d_stat);
+  k_sorted_stats<<<ctx->n_sm, 256, 0, s>>>(keys_out.as<int32_t>(), n, pad, breadth_n, d_stat);
   ctx->prof_end();
   return cudaGetLastError() == cudaSuccess ? MCOV_OK : MCOV_ERR_CUDA;
 }

@@ -16,8 +16,9 @@ __global__ void k_synth_ncigar(mcov_synth_params P, int64_t i0, int64_t n, uint3
   if (k < n) out[k] = mcov_synth_ncigar(&P, i0 + k);
 }
 
+template <typename OffT>
 __global__ void k_synth_fill(mcov_synth_params P, int64_t i0, int64_t n, const int64_t* read_start,
-                             const int32_t* contig_len, int32_t n_contigs, int32_t tid_base, const uint32_t* cig_off,
+                             const int32_t* contig_len, int32_t n_contigs, int32_t tid_base, const OffT* cig_off,
                              int32_t* tid, int32_t* pos, uint16_t* flag, uint8_t* mapq, int32_t* isize, uint32_t* cig,
                              int64_t* reflen_out) {
   int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -25,8 +26,8 @@ __global__ void k_synth_fill(mcov_synth_params P, int64_t i0, int64_t n, const i
   int32_t t, p, is;
   uint16_t f;
   uint8_t q;
-  uint32_t o0 = cig_off[k], o1 = cig_off[k + 1];
-  int64_t rl = mcov_synth_read(&P, i0 + k, read_start, contig_len, n_contigs, &t, &p, &f, &q, &is, cig + o0, o1 - o0);
+  OffT o0 = cig_off[k], o1 = cig_off[k + 1];
+  int64_t rl = mcov_synth_read(&P, i0 + k, read_start, contig_len, n_contigs, &t, &p, &f, &q, &is, cig + o0, (uint32_t)(o1 - o0));
   tid[k] = t - tid_base; pos[k] = p; flag[k] = f; mapq[k] = q; isize[k] = is;
   if (reflen_out) reflen_out[k] = rl;
 }
@@ -48,6 +49,32 @@ void parallel_for(int64_t n, F fn) {
 
 }  // namespace
 
+template <typename OffT>
+static int synth_gen_reads_impl(const mcov_synth_params* P, int64_t i0, int64_t n, const int64_t* read_start,
+                    const int32_t* contig_len, int32_t n_contigs, int32_t tid_base, const OffT* cig_off, int32_t* tid,
+                    int32_t* pos, uint16_t* flag, uint8_t* mapq, int32_t* isize, uint32_t* cig, int64_t* reflen_out,
+                    int mem_kind, void* stream) {
+  if (!P || n < 0 || n_contigs <= 0 || !read_start || !contig_len) return MCOV_ERR_ARG;
+  if (n == 0) return MCOV_OK;
+  if (!cig_off || !tid || !pos || !flag || !mapq || !isize || !cig) return MCOV_ERR_ARG;
+  if (mem_kind == MCOV_MEM_DEVICE) {
+    k_synth_fill<OffT><<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        *P, i0, n, read_start, contig_len, n_contigs, tid_base, cig_off, tid, pos, flag, mapq, isize, cig, reflen_out);
+    return cudaGetLastError() == cudaSuccess ? MCOV_OK : MCOV_ERR_CUDA;
+  }
+  mcov_synth_params Q = *P;
+  parallel_for(n, [=](int64_t k) {
+    int32_t t, p, is;
+    uint16_t f;
+    uint8_t q;
+    OffT o0 = cig_off[k], o1 = cig_off[k + 1];
+    int64_t rl = mcov_synth_read(&Q, i0 + k, read_start, contig_len, n_contigs, &t, &p, &f, &q, &is, cig + o0, (uint32_t)(o1 - o0));
+    tid[k] = t - tid_base; pos[k] = p; flag[k] = f; mapq[k] = q; isize[k] = is;
+    if (reflen_out) reflen_out[k] = rl;
+  });
+  return MCOV_OK;
+}
+
 extern "C" {
 
 int mcov_synth_gen_ncigar(const mcov_synth_params* P, int64_t i0, int64_t n, uint32_t* out, int mem_kind, void* stream) {
@@ -66,25 +93,16 @@ int mcov_synth_gen_reads(const mcov_synth_params* P, int64_t i0, int64_t n, cons
                     const int32_t* contig_len, int32_t n_contigs, int32_t tid_base, const uint32_t* cig_off, int32_t* tid,
                     int32_t* pos, uint16_t* flag, uint8_t* mapq, int32_t* isize, uint32_t* cig, int64_t* reflen_out,
                     int mem_kind, void* stream) {
-  if (!P || n < 0 || n_contigs <= 0 || !read_start || !contig_len) return MCOV_ERR_ARG;
-  if (n == 0) return MCOV_OK;
-  if (!cig_off || !tid || !pos || !flag || !mapq || !isize || !cig) return MCOV_ERR_ARG;
-  if (mem_kind == MCOV_MEM_DEVICE) {
-    k_synth_fill<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-        *P, i0, n, read_start, contig_len, n_contigs, tid_base, cig_off, tid, pos, flag, mapq, isize, cig, reflen_out);
-    return cudaGetLastError() == cudaSuccess ? MCOV_OK : MCOV_ERR_CUDA;
-  }
-  mcov_synth_params Q = *P;
-  parallel_for(n, [=](int64_t k) {
-    int32_t t, p, is;
-    uint16_t f;
-    uint8_t q;
-    uint32_t o0 = cig_off[k], o1 = cig_off[k + 1];
-    int64_t rl = mcov_synth_read(&Q, i0 + k, read_start, contig_len, n_contigs, &t, &p, &f, &q, &is, cig + o0, o1 - o0);
-    tid[k] = t - tid_base; pos[k] = p; flag[k] = f; mapq[k] = q; isize[k] = is;
-    if (reflen_out) reflen_out[k] = rl;
-  });
-  return MCOV_OK;
+  return synth_gen_reads_impl<uint32_t>(P, i0, n, read_start, contig_len, n_contigs, tid_base, cig_off, tid, pos, flag, mapq,
+                                        isize, cig, reflen_out, mem_kind, stream);
+}
+
+int mcov_synth_gen_reads_wide(const mcov_synth_params* P, int64_t i0, int64_t n, const int64_t* read_start,
+                    const int32_t* contig_len, int32_t n_contigs, int32_t tid_base, const uint64_t* cig_off, int32_t* tid,
+                    int32_t* pos, uint16_t* flag, uint8_t* mapq, int32_t* isize, uint32_t* cig, int64_t* reflen_out,
+                    int mem_kind, void* stream) {
+  return synth_gen_reads_impl<uint64_t>(P, i0, n, read_start, contig_len, n_contigs, tid_base, cig_off, tid, pos, flag, mapq,
+                                        isize, cig, reflen_out, mem_kind, stream);
 }
 
 }  // extern "C"

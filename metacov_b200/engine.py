@@ -17,7 +17,8 @@ ReadBatch.__doc__ = """SoA of mapped reads: the bam1_t fields the coverage path 
 
 tid:int32[n] pos:int32[n] flag:uint16[n] mapq:uint8[n] cig_off:uint32[n+1]
 cig:uint32[cig_off[n]] (BAM encoding len<<4|op).  numpy arrays (host) or torch
-tensors (host or CUDA)."""
+tensors (host or CUDA).  A batch of 2^32 or more ops carries 64-bit offsets
+(numpy uint64/int64, torch int64) and takes the *_wide entry points."""
 
 RUNS_DTYPE = np.dtype([("tid", "<i4"), ("start", "<i4"), ("end", "<i4"), ("depth", "<i4")])
 
@@ -42,21 +43,32 @@ def _mem_kind(batch):
     return kinds.pop()
 
 
+def _is_wide(batch):
+    """True when the batch carries 64-bit CIGAR offsets."""
+    o = batch.cig_off
+    if _is_torch(o):
+        return o.element_size() == 8
+    return np.asarray(o).dtype.itemsize == 8
+
+
 def _canon(batch):
     """numpy members -> contiguous arrays of the ABI dtypes; torch members are
     checked, not converted."""
     out = []
+    wide = _is_wide(batch)
     for name, a in zip(ReadBatch._fields, batch):
         if _is_torch(a):
             import torch
             want = {np.int32: torch.int32, np.uint16: (torch.uint16, torch.int16),
                     np.uint8: torch.uint8, np.uint32: (torch.uint32, torch.int32)}[_DT[name]]
+            if name == "cig_off" and wide:
+                want = (torch.int64, torch.uint64)
             want = want if isinstance(want, tuple) else (want,)
             if a.dtype not in want:
                 raise TypeError("ReadBatch.%s: dtype %s, expected %s" % (name, a.dtype, want[0]))
             out.append(a)
         else:
-            out.append(np.ascontiguousarray(a, dtype=_DT[name]))
+            out.append(np.ascontiguousarray(a, dtype=np.uint64 if (name == "cig_off" and wide) else _DT[name]))
     return ReadBatch(*out)
 
 
@@ -132,7 +144,8 @@ class CoverageEngine:
     def push(self, batch):
         b = _canon(batch)
         n = len(b.tid)
-        self._check(lib.mcov_push_reads(self._ctx, n, *[_capi.ptr(x) for x in b], _mem_kind(b)))
+        fn = lib.mcov_push_reads_wide if _is_wide(b) else lib.mcov_push_reads
+        self._check(fn(self._ctx, n, *[_capi.ptr(x) for x in b], _mem_kind(b)))
 
     def finalize(self):
         self._check(lib.mcov_finalize(self._ctx))
@@ -143,6 +156,9 @@ class CoverageEngine:
         synchronising call (region_stats / copy_depth / pass_info)."""
         b = _canon(batch)
         n = len(b.tid)
+        if _is_wide(b):
+            self._check(lib.mcov_depth_sorted_wide(self._ctx, n, *[_capi.ptr(x) for x in b], _mem_kind(b), 1 if wait else 0))
+            return
         fn = lib.mcov_depth_sorted if wait else lib.mcov_depth_sorted_async
         self._check(fn(self._ctx, n, *[_capi.ptr(x) for x in b], _mem_kind(b)))
 

@@ -309,6 +309,80 @@ def test_max_depth_cap_replayed_exactly():
         assert np.array_equal(eng.copy_depth(0), free[off[0]:off[0] + lengths[0]])
 
 
+def _capped_pile_batch():
+    from metacov_b200 import ReadBatch
+    rng = np.random.default_rng(19)
+    lengths = np.array([2000, 1200], np.int32)
+    ps0 = np.sort(np.r_[np.full(11000, 500), np.full(2500, 505), rng.integers(0, 1800, 3000)])
+    ps1 = np.sort(rng.integers(0, 1100, 1500))
+    tid = np.r_[np.zeros(len(ps0), np.int32), np.ones(len(ps1), np.int32)]
+    pos = np.r_[ps0, ps1].astype(np.int32)
+    n = len(tid)
+    rl = rng.integers(60, 140, n).astype(np.uint32)
+    b = ReadBatch(tid, pos, np.zeros(n, np.uint16), np.full(n, 30, np.uint8), np.arange(n + 1, dtype=np.uint32), rl << 4)
+    return b, lengths
+
+
+def test_cap_replay_precedes_every_consumer_of_an_async_pass():
+    """depth_sorted(wait=False) defers the verdict, but the max_depth replay runs on the device in
+    stream order: statistics, copies, run export and window means issued before the verdict has been
+    looked at must already see the capped depth (oracle: the sequential htslib machine)."""
+    b, lengths = _capped_pile_batch()
+    want, off, info = cport.depth(b, lengths, mode="plp")
+    assert info["dropped_by_cap"] > 0
+    t, a, e = [0, 1, 0], [0, 0, 450], [2000, 1200, 700]
+    ref = cport.region_stats(want, off, lengths, t, a, e)
+    keys = ("sum", "sumsq", "iq_sum", "min", "max", "med_lo", "med_hi")
+    with engine_for(lengths) as eng:
+        eng.depth_sorted(b, wait=False)
+        got = eng.region_stats(t, a, e)                       # first synchronising call after the async pass
+        for k in keys:
+            assert np.array_equal(got[k], ref[k]), k
+        assert eng.pass_info()["cap_contigs"] == 1
+        eng.depth_sorted(b, wait=False)
+        assert np.array_equal(eng.copy_depth(0), want[off[0]:off[0] + lengths[0]])
+        eng.depth_sorted(b, wait=False)
+        runs = eng.depth_runs()
+        d0 = np.repeat(runs["depth"][runs["tid"] == 0], (runs["end"] - runs["start"])[runs["tid"] == 0])
+        assert np.array_equal(d0, want[off[0]:off[0] + lengths[0]])
+        eng.depth_sorted(b, wait=False)
+        wm = eng.window_means(500)
+        assert np.allclose(wm[:4], want[off[0]:off[0] + 2000].reshape(4, 500).mean(axis=1))
+        # pipelined statistics: the replay is part of the pass, so submit/collect deliver capped records too
+        eng.depth_sorted(b, wait=False)
+        tk = eng.region_stats_submit(t, a, e, slot=0)
+        eng.depth_sorted(b, wait=False)                        # the next pass overwrites the depth
+        tk2 = eng.region_stats_submit(t, a, e, slot=1)
+        for tkt in (tk, tk2):
+            got = eng.region_stats_collect(tkt)
+            for k in keys:
+                assert np.array_equal(got[k], ref[k]), k
+
+
+@pytest.mark.parametrize("wl,scale", [("c2", 0.01), ("c5", 0.004)])
+def test_wide_cigar_offsets_equal_narrow(wl, scale):
+    """64-bit CIGAR offsets (mcov_depth_sorted_wide / mcov_push_reads_wide: batches of 2^32 or more ops,
+    config C5 at full size) give the depth of the 32-bit entry points -- host and device-resident."""
+    import torch
+    from metacov_b200 import ReadBatch, synth
+    w = synth.WORKLOADS[wl](scale)
+    b, _ = synth.generate_host(w)
+    bw, _ = synth.generate_host(w, wide=True)
+    assert bw.cig_off.dtype == np.uint64
+    want, off, _ = cport.depth(b, w.contig_len, mode="diff")
+    with engine_for(w.contig_len) as eng:
+        eng.depth_sorted(bw)
+        assert np.array_equal(full_depth(eng), want)
+        eng.begin(); eng.push(bw); eng.finalize()
+        assert np.array_equal(full_depth(eng), want)
+        db, _ = synth.generate_device(w, 0, wide=True)
+        assert db.cig_off.dtype == torch.int64
+        eng.depth_sorted(db, wait=False)
+        assert np.array_equal(full_depth(eng), want)
+        eng.begin(); eng.push(db); eng.finalize()
+        assert np.array_equal(full_depth(eng), want)
+
+
 @pytest.mark.parametrize("wl,scale", [("c2", 0.01), ("c5", 0.002)])
 def test_packed_host_transport_equals_soa_path(wl, scale):
     """mcov_depth_sorted_packed (contig prefix + u16 op counts, no mapq) rebuilds the SoA on the device."""

@@ -145,3 +145,40 @@ def test_load_kmerhist_both_csv_dialects():
             "%s,%s,%s,%s\n" % (k, ",".join(str(x) for x in n), m, r) for k, n, m, r in rows)
         got = pileup.load_kmerhist(io.StringIO(csv_text), k_len=3)
         assert [dict((k, float(v)) for k, v in d.items()) for d in got] == want, rcol
+
+
+def test_native_bam_reader_rejects_malformed_sizes(tmp_path):
+    """Sizes read from the file are validated before anything is allocated from them (a corrupt
+    ISIZE or l_seq must end in an error code / OSError, never in an exception crossing the C ABI)."""
+    import ctypes as C
+    import struct
+    import zlib
+    from metacov_b200 import AlignmentFile, _capi
+    z, b = load_soa("synth_small_soa.npz")
+    refs = [str(x) for x in z["references"]]
+    good = str(tmp_path / "good.bam")
+    bamio.write_bam(good, refs, z["lengths"].tolist(), b.tid, b.pos, b.flag, b.mapq, b.cig_off, b.cig)
+    raw = bytearray(open(good, "rb").read())
+    # (1) ISIZE of the first BGZF block claims 1 GiB
+    bsize = struct.unpack_from("<H", raw, 16)[0] + 1
+    bad1 = bytearray(raw)
+    struct.pack_into("<I", bad1, bsize - 4, 1 << 30)
+    p1 = str(tmp_path / "isize.bam")
+    open(p1, "wb").write(bad1)
+    with pytest.raises(OSError):
+        AlignmentFile(p1)
+    # (2) a record whose l_seq does not fit its block_size
+    data = bytearray(bamio.bgzf_inflate(bytes(raw)))
+    hdr, recs = bamio.read_bam(good)
+    p = 12 + struct.unpack_from("<i", data, 4)[0]
+    for _ in refs:
+        p += 8 + struct.unpack_from("<i", data, p)[0]
+    struct.pack_into("<i", data, p + 4 + 16, 0x7fffff00)          # l_seq of the first record
+    p2 = str(tmp_path / "lseq.bam")
+    open(p2, "wb").write(bamio.bgzf_compress(bytes(data)))
+    h = C.c_void_p()
+    err = C.create_string_buffer(256)
+    assert _capi.lib.mcov_bam_open(C.byref(h), p2.encode(), err, 256) == 0
+    assert _capi.lib.mcov_bam_load(h, 0) == _capi.MCOV_ERR_IO
+    assert _capi.lib.mcov_bam_load_seq(h) == _capi.MCOV_ERR_IO
+    _capi.lib.mcov_bam_close(h)
