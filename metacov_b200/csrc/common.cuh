@@ -102,6 +102,51 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// ---- TMA bulk copies behind mbarriers (sm_90+; SASS: UBLKCP / SYNCS) ----------------------------
+// The streaming kernels stage their inputs with cp.async.bulk: ONE elected thread issues a
+// multi-kilobyte global -> shared copy that completes on an mbarrier (complete_tx::bytes); the
+// consumer threads wait on the barrier's phase parity and read shared memory.  No register is held
+// while the copy is in flight and no per-thread load instruction is issued for the data.
+// Addresses and sizes must be multiples of 16 bytes.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(arrivals) : "memory");
+}
+// makes the initialised barriers visible to the async proxy (the TMA unit); follow with a CTA barrier
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// same with an L2 eviction-priority hint (streams that are read once: evict_first)
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_1d_hint(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+// named barrier over a subset of the CTA's warps (the consumer warps of a warp-specialised kernel)
+template <int ID, int THREADS>
+__device__ __forceinline__ void named_bar_sync() { asm volatile("bar.sync %0, %1;" :: "n"(ID), "n"(THREADS) : "memory"); }
+
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll
@@ -119,40 +164,33 @@ __device__ __forceinline__ int warp_min(int v) {
   return v;
 }
 
-// Reference length of one read whose ops are cig[b0, b1), computed by a whole
+// Reference length of one read whose ops are p[0, cnt), computed by a whole
 // warp with 128-bit loads where alignment allows (long-read path, config C5:
 // thousands of ops per read, the CIGAR stream is the dominant HBM traffic).
-__device__ __forceinline__ unsigned long long warp_cigar_reflen(const uint32_t* __restrict__ cig,
-                                                                uint64_t b0, uint64_t b1, int lane,
-                                                                bool base_aligned16) {
+__device__ __forceinline__ unsigned long long warp_cigar_reflen(const uint32_t* __restrict__ p, uint32_t cnt, int lane) {
   unsigned long long acc = 0;
-  uint64_t k = b0;
-  if (base_aligned16) {
-    uint64_t a0 = (b0 + 3u) & ~(uint64_t)3;  // first 16-byte aligned op index
-    if (a0 > b1) a0 = b1;
-    // head (< 4 ops)
-    if (b0 + (uint32_t)lane < a0) acc += cigar_ref_len(__ldg(cig + b0 + lane));
-    uint32_t nvec = (uint32_t)((b1 - a0) >> 2);
-    const uint4* v = reinterpret_cast<const uint4*>(cig + a0);
-    uint32_t j = lane;
-    // 4 independent 512-byte warp loads in flight
-    for (; j + 96u < nvec; j += 128u) {
-      uint4 q0 = ld_stream_uint4(v + j), q1 = ld_stream_uint4(v + j + 32u);
-      uint4 q2 = ld_stream_uint4(v + j + 64u), q3 = ld_stream_uint4(v + j + 96u);
-      acc += cigar_ref_len(q0.x) + cigar_ref_len(q0.y) + cigar_ref_len(q0.z) + cigar_ref_len(q0.w);
-      acc += cigar_ref_len(q1.x) + cigar_ref_len(q1.y) + cigar_ref_len(q1.z) + cigar_ref_len(q1.w);
-      acc += cigar_ref_len(q2.x) + cigar_ref_len(q2.y) + cigar_ref_len(q2.z) + cigar_ref_len(q2.w);
-      acc += cigar_ref_len(q3.x) + cigar_ref_len(q3.y) + cigar_ref_len(q3.z) + cigar_ref_len(q3.w);
-    }
-    for (; j < nvec; j += 32u) {
-      uint4 q = ld_stream_uint4(v + j);
-      acc += cigar_ref_len(q.x) + cigar_ref_len(q.y) + cigar_ref_len(q.z) + cigar_ref_len(q.w);
-    }
-    k = a0 + ((uint64_t)nvec << 2);           // tail (< 4 ops)
-    if (k + (uint32_t)lane < b1) acc += cigar_ref_len(__ldg(cig + k + lane));
-  } else {
-    for (uint64_t i = k + lane; i < b1; i += 32u) acc += cigar_ref_len(__ldg(cig + i));
+  // head: ops before the first 16-byte aligned one (< 4)
+  uint32_t head = (uint32_t)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15u)) & 15u) >> 2;
+  if (head > cnt) head = cnt;
+  if ((uint32_t)lane < head) acc += cigar_ref_len(__ldg(p + lane));
+  const uint32_t nvec = (cnt - head) >> 2;
+  const uint4* v = reinterpret_cast<const uint4*>(p + head);
+  uint32_t j = lane;
+  // 4 independent 512-byte warp loads in flight
+  for (; j + 96u < nvec; j += 128u) {
+    uint4 q0 = ld_stream_uint4(v + j), q1 = ld_stream_uint4(v + j + 32u);
+    uint4 q2 = ld_stream_uint4(v + j + 64u), q3 = ld_stream_uint4(v + j + 96u);
+    acc += cigar_ref_len(q0.x) + cigar_ref_len(q0.y) + cigar_ref_len(q0.z) + cigar_ref_len(q0.w);
+    acc += cigar_ref_len(q1.x) + cigar_ref_len(q1.y) + cigar_ref_len(q1.z) + cigar_ref_len(q1.w);
+    acc += cigar_ref_len(q2.x) + cigar_ref_len(q2.y) + cigar_ref_len(q2.z) + cigar_ref_len(q2.w);
+    acc += cigar_ref_len(q3.x) + cigar_ref_len(q3.y) + cigar_ref_len(q3.z) + cigar_ref_len(q3.w);
   }
+  for (; j < nvec; j += 32u) {
+    uint4 q = ld_stream_uint4(v + j);
+    acc += cigar_ref_len(q.x) + cigar_ref_len(q.y) + cigar_ref_len(q.z) + cigar_ref_len(q.w);
+  }
+  const uint32_t k = head + (nvec << 2);      // tail (< 4 ops)
+  if (k + (uint32_t)lane < cnt) acc += cigar_ref_len(__ldg(p + k + lane));
   return warp_sum(acc);
 }
 

@@ -56,6 +56,7 @@ struct RegionPlan {
   bool valid = false;
   int64_t g = 0, n_tasks = 0, n_small = 0;
   int32_t n_multi = 0;
+  int32_t ss_grid = 0, n_split = 0;      // balanced stream over the large regions (k_stats_stream.cuh): CTAs, split regions
   int64_t n_contigs_epoch = -1;
   std::vector<int32_t> tid, start, end, rlen, rpad;
 };
@@ -116,6 +117,7 @@ struct mcov_ctx {
   mcov::DevBuf d_end_slot, d_start_slot, d_far_list, d_tile_cnt, d_tile_off, d_far_sorted;
 
   // stats scratch
+  mcov::DevBuf d_ss_pieces, d_ss_cta, d_ss_split, d_ss_pool;
   mcov::DevBuf d_tasks, d_rlen, d_rchunks, d_rhist, d_pool, d_done, d_out, d_win_slot, d_win_n, d_win_out, d_htasks, d_tile_heavy, d_run_tasks, d_run_counts, d_run_out;
   int64_t n_runs = -1;               // records held in d_run_out ([tid | start | end | depth] x n_runs), -1 = none
   mcov::PinBuf h_pin;

@@ -64,6 +64,7 @@ struct FusedArgs {
   uint32_t* rec;              // [n] 4-byte records, see make_rec
   int64_t n_slots;
   int64_t n_tiles;
+  int64_t tile_lo, tile_hi;   // tiles this pass writes (the whole slot space, or the batch's share when a file is streamed)
   int64_t* far_end;           // [far_cap] end slots of far reads
   uint32_t far_cap;
   int32_t* tile_agg;          // [cnt_pad] (#far starts - #far ends) per tile -> inclusive scan in place
@@ -90,9 +91,8 @@ __device__ __forceinline__ int64_t slot_key(const ExpandArgs& a, int32_t t, int3
   return base + q;
 }
 
-__device__ __noinline__ unsigned long long warp_cigar_reflen_call(const uint32_t* cig, uint64_t b0, uint64_t b1, int lane,
-                                                                  int aligned16) {
-  return warp_cigar_reflen(cig, b0, b1, lane, aligned16 != 0);
+__device__ __noinline__ unsigned long long warp_cigar_reflen_call(const uint32_t* p, uint32_t cnt, int lane) {
+  return warp_cigar_reflen(p, cnt, lane);
 }
 
 // Rare path of k_fused_prep: some read of this warp is the first of a new tile.  Entered by the
@@ -364,9 +364,10 @@ __device__ __forceinline__ PrepReads prep_load_reduce(const FusedArgs& f, int64_
     int r = __ffs(__shfl_sync(0xffffffffu, coop, src)) - 1;
     off_t ob = r == 0 ? O[0] : r == 1 ? O[1] : r == 2 ? O[2] : O[3];
     off_t oe = r == 0 ? O[1] : r == 1 ? O[2] : r == 2 ? O[3] : O[4];
+    uint32_t cnt = (uint32_t)(oe - ob);
     ob = __shfl_sync(0xffffffffu, ob, src);
-    oe = __shfl_sync(0xffffffffu, oe, src);
-    unsigned long long v = warp_cigar_reflen_call(g_cig, ob, oe, lane, a.cig_aligned16);
+    cnt = __shfl_sync(0xffffffffu, cnt, src);
+    unsigned long long v = warp_cigar_reflen_call(g_cig + ob, cnt, lane);
     if (lane == src) {
       uint32_t v32 = v > 0x7fffffffull ? 0x7fffffffu : (uint32_t)v;
       if (r == 0) R.reflen[0] = v32; else if (r == 1) R.reflen[1] = v32; else if (r == 2) R.reflen[2] = v32; else R.reflen[3] = v32;
@@ -377,7 +378,9 @@ __device__ __forceinline__ PrepReads prep_load_reduce(const FusedArgs& f, int64_
   return R;
 }
 
-// block-level reduction of the pass counters of a prep kernel
+// block-level reduction of the pass counters of a prep kernel (CONSUMERS_ONLY: the CTA has further warps
+// that do not take part -- the kPrepThreads consumer warps meet at a named barrier)
+template <bool CONSUMERS_ONLY = false>
 __device__ __forceinline__ void prep_flush_counters(PassCounters* pc, uint32_t n_pass, unsigned long long aligned,
                                                     uint32_t unsorted, uint32_t max_span) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -389,7 +392,7 @@ __device__ __forceinline__ void prep_flush_counters(PassCounters* pc, uint32_t n
   __shared__ int s_un[kPrepThreads / 32];
   __shared__ uint32_t s_ms[kPrepThreads / 32];
   if (lane == 0) { s_np[warp] = np64; s_al[warp] = aligned; s_un[warp] = (int)unsorted; s_ms[warp] = max_span; }
-  __syncthreads();
+  if (CONSUMERS_ONLY) named_bar_sync<1, kPrepThreads>(); else __syncthreads();
   if (threadIdx.x == 0) {
     unsigned long long np = 0, al = 0; int un = 0; uint32_t ms = 0;
     for (int k = 0; k < kPrepThreads / 32; ++k) { np += s_np[k]; al += s_al[k]; un |= s_un[k]; ms = max(ms, s_ms[k]); }
@@ -592,7 +595,7 @@ __global__ void k_far_scatter(FusedArgs f) {
   pdl_launch_dependents();
   // tiles that hold very many reads (skewed abundance: a 4000x contig puts ~55 k reads into one tile,
   // 100x the average of config C3) are listed here so that the tile kernel can start with them
-  for (int64_t T = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; T < f.n_tiles; T += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t T = f.tile_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; T < f.tile_hi; T += (int64_t)gridDim.x * blockDim.x) {
     if (f.tile_first[T + 1] - f.tile_first[T] >= f.heavy_min) f.tile_heavy[atomicAdd(&f.e.pc->n_heavy, 1u)] = (uint32_t)T;
   }
   uint32_t n_far = min(f.e.pc->n_far, f.far_cap);

@@ -1,0 +1,216 @@
+// k_prep_tma.cuh -- first kernel of the fused path, TMA-staged (the short-read hot path).
+//
+// Same work and same outputs as k_fused_prep (k_fused.cuh): filter + CIGAR reduce of every read,
+// 4-byte records, tile borders, far-read tables.  What differs is how the reads reach the SM.
+// k_fused_prep issues five 128-bit loads per thread and then a dependent load per CIGAR op; ncu
+// showed it waiting on exactly those (long_scoreboard 46 % of the stall samples: 20 % on the first
+// use of the SoA columns, 17 % on the first use of the CIGAR op) at 64 registers / 50 % occupancy.
+// Here a PRODUCER warp stages whole chunks of the SoA -- 1024 consecutive reads: tid, pos, flag,
+// mapq, offsets and the chunk's contiguous CIGAR range -- into a ring of shared-memory stages
+// with cp.async.bulk (TMA) completing on mbarriers; the 8 CONSUMER warps wait on the stage's
+// "full" barrier, take everything from shared memory and release the stage through its "empty"
+// barrier.  The dependent load (offset -> op) disappears: the producer knows a chunk's op range
+// from the two offsets at its ends (fetched one chunk ahead), so ops and columns travel together.
+//
+// Requirements (else the caller launches k_fused_prep): 32-bit offsets, every column 16-byte
+// aligned.  A chunk whose ops do not fit the stage (long reads) leaves them in global memory.
+#pragma once
+#include "k_fused.cuh"
+
+namespace mcov {
+
+#ifndef MCOV_PREP_STAGES
+#define MCOV_PREP_STAGES 3
+#endif
+#ifndef MCOV_PREP_CTAS
+#define MCOV_PREP_CTAS 3
+#endif
+constexpr int kPtStages = MCOV_PREP_STAGES;
+constexpr int kPtChunk = kPrepThreads * kPrepPer;          // 1024 reads per stage
+constexpr int kPtCigCap = 2048;                            // ops staged per chunk (average 2 per read)
+constexpr int kPtThreads = kPrepThreads + 32;              // 8 consumer warps + the producer warp
+// stage layout (byte offsets; every part a multiple of 16)
+constexpr int kPtOffTid = 0;                               // 4 reads before the chunk + the chunk
+constexpr int kPtOffPos = kPtOffTid + 16 + 4 * kPtChunk;
+constexpr int kPtOffOff = kPtOffPos + 16 + 4 * kPtChunk;   // kPtChunk + 1 offsets (+ padding)
+constexpr int kPtOffFlag = kPtOffOff + 4 * kPtChunk + 16;
+constexpr int kPtOffMapq = kPtOffFlag + 2 * kPtChunk;
+constexpr int kPtOffCig = kPtOffMapq + kPtChunk;
+constexpr int kPtStageBytes = kPtOffCig + 4 * kPtCigCap;
+constexpr int kPtSmemBytes = kPtStages * kPtStageBytes;
+static_assert(kPtStageBytes % 16 == 0, "stage size must keep every stage 16-byte aligned");
+
+struct PtMeta { uint32_t a0; uint32_t in_smem; };           // first staged op index; ops are in the stage
+
+// Loads + filter + CIGAR reduction of the 4 reads of one consumer thread, from a landed stage.
+__device__ __forceinline__ PrepReads prep_reduce_staged(const FusedArgs& f, const char* st, const PtMeta m, int64_t i0, int lane) {
+  const ExpandArgs& a = f.e;
+  const uint32_t n_contigs = (uint32_t)a.n_contigs;
+  const uint32_t drop = (uint32_t)a.filt.flag_filter | 0x4u, req = a.filt.flag_require, minq = a.filt.min_mapq;
+  const uint32_t req_none = req == 0 ? 1u : 0u, orph_mask = a.filt.ignore_orphans ? 3u : 0u;
+  const int t = threadIdx.x;
+  PrepReads R;
+  R.nv = (int)min((int64_t)kPrepPer, max((int64_t)0, a.n - i0));
+  const int4 t4 = *reinterpret_cast<const int4*>(st + kPtOffTid + 16 + 16 * t);
+  const int4 p4 = *reinterpret_cast<const int4*>(st + kPtOffPos + 16 + 16 * t);
+  const uint4 o4 = *reinterpret_cast<const uint4*>(st + kPtOffOff + 16 * t);
+  const uint32_t o_end = *reinterpret_cast<const uint32_t*>(st + kPtOffOff + 16 * t + 16);
+  const ushort4 f4 = *reinterpret_cast<const ushort4*>(st + kPtOffFlag + 8 * t);
+  const uchar4 q4 = *reinterpret_cast<const uchar4*>(st + kPtOffMapq + 4 * t);
+  R.T[0] = t4.x; R.T[1] = t4.y; R.T[2] = t4.z; R.T[3] = t4.w;
+  R.P[0] = p4.x; R.P[1] = p4.y; R.P[2] = p4.z; R.P[3] = p4.w;
+  const uint32_t F[4] = {f4.x, f4.y, f4.z, f4.w}, Q[4] = {q4.x, q4.y, q4.z, q4.w};
+  const uint32_t O[5] = {o4.x, o4.y, o4.z, o4.w, o_end};
+  if (R.nv < kPrepPer) {                         // ragged end of the batch: what lies behind it in the stage is not data
+#pragma unroll
+    for (int r = 0; r < 4; ++r) if (r >= R.nv) { R.T[r] = -1; R.P[r] = 0; }
+  }
+  // ops of this chunk: in the stage (generic pointer biased by the first staged op) or left in global memory
+  const uint32_t* __restrict__ cp = m.in_smem ? reinterpret_cast<const uint32_t*>(st + kPtOffCig) - m.a0 : a.cig;
+  unsigned passm = 0, coop = 0;
+  uint32_t op0[4], nc[4];
+  uint32_t nc_max = 0;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const bool p = (r < R.nv) & ((F[r] & drop) == 0u) & (((F[r] & req) | req_none) != 0u) & (Q[r] >= minq) &
+                   ((F[r] & orph_mask) != 1u) & ((uint32_t)R.T[r] < n_contigs);
+    nc[r] = O[r + 1] - O[r];
+    const bool c = p && nc[r] > kThreadOps;
+    passm |= p ? (1u << r) : 0u;
+    coop |= c ? (1u << r) : 0u;
+    if (!p || c) nc[r] = 0;
+    nc_max = max(nc_max, nc[r]);
+    op0[r] = nc[r] > 0 ? cp[O[r]] : 0u;
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) R.reflen[r] = cigar_ref_len(op0[r]);
+#pragma unroll 1
+  for (uint32_t k = 1; k < nc_max; ++k) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const uint32_t op = k < nc[r] ? cp[O[r] + k] : 0u;
+      R.reflen[r] += cigar_ref_len(op);
+    }
+  }
+  // long CIGARs: the whole warp reduces one read at a time with 128-bit loads from global memory
+  while (__any_sync(0xffffffffu, coop != 0)) {
+    const unsigned lanes = __ballot_sync(0xffffffffu, coop != 0);
+    const int src = __ffs(lanes) - 1;
+    const int r = __ffs(__shfl_sync(0xffffffffu, coop, src)) - 1;
+    uint32_t ob = r == 0 ? O[0] : r == 1 ? O[1] : r == 2 ? O[2] : O[3];
+    const uint32_t oe = r == 0 ? O[1] : r == 1 ? O[2] : r == 2 ? O[3] : O[4];
+    uint32_t cnt = oe - ob;
+    ob = __shfl_sync(0xffffffffu, ob, src);
+    cnt = __shfl_sync(0xffffffffu, cnt, src);
+    const unsigned long long v = warp_cigar_reflen_call(a.cig + ob, cnt, lane);
+    if (lane == src) {
+      const uint32_t v32 = v > 0x7fffffffull ? 0x7fffffffu : (uint32_t)v;
+      if (r == 0) R.reflen[0] = v32; else if (r == 1) R.reflen[1] = v32; else if (r == 2) R.reflen[2] = v32; else R.reflen[3] = v32;
+      coop &= ~(1u << r);
+    }
+  }
+  R.passm = passm;
+  return R;
+}
+
+// The producer: lane 0 of the last warp.  Chunk c = reads [c*1024, min(n, (c+1)*1024)); the CTA's
+// chunks are blockIdx.x, blockIdx.x + gridDim.x, ...
+__device__ __forceinline__ void prep_producer(const FusedArgs& f, char* smem, uint64_t* full, uint64_t* empty, PtMeta* meta,
+                                              int64_t n_chunks) {
+  const ExpandArgs& a = f.e;
+  const int64_t n = a.n;
+  const uint32_t* __restrict__ g_off = a.cig_off;
+  const uint32_t cig_total = __ldg(g_off + n);
+  const uint64_t pol = l2_policy_evict_first();
+  const unsigned G = gridDim.x;
+  int64_t c = blockIdx.x;
+  uint32_t ob = 0, oe = 0;
+  if (c < n_chunks) { ob = __ldg(g_off + c * kPtChunk); oe = __ldg(g_off + min((c + 1) * (int64_t)kPtChunk, n)); }
+#pragma unroll 1
+  for (unsigned it = 0; c < n_chunks; ++it, c += G) {
+    // the op range of the CTA's next chunk: fetched now, needed one iteration from now
+    const int64_t cn = c + G;
+    uint32_t nob = 0, noe = 0;
+    if (cn < n_chunks) { nob = __ldg(g_off + cn * kPtChunk); noe = __ldg(g_off + min((cn + 1) * (int64_t)kPtChunk, n)); }
+    const unsigned s = it % kPtStages, k = it / kPtStages;
+    if (k > 0) mbar_wait(&empty[s], (k - 1) & 1);                  // the consumers have released this stage
+    char* st = smem + (size_t)s * kPtStageBytes;
+    const int64_t r0 = c * kPtChunk;
+    const uint32_t nread = (uint32_t)min((int64_t)kPtChunk, n - r0);
+    const uint32_t n4 = nread & ~3u, n8 = nread & ~7u, n16 = nread & ~15u;   // reads covered by whole 16-byte units
+    const uint32_t prev = c > 0 ? 16u : 0u;                        // the four reads before the chunk (sortedness, tile border)
+    // CIGAR ops [ob, oe) -> aligned window [a0, a1); never past the last whole vector of the array
+    const uint32_t a0 = ob & ~3u;
+    uint32_t a1 = (oe + 3u) & ~3u;
+    const bool fits = a1 - a0 <= (uint32_t)kPtCigCap;
+    a1 = min(a1, cig_total & ~3u);
+    const uint32_t cig_bytes = (fits && a1 > a0) ? 4u * (a1 - a0) : 0u;
+    // what whole 16-byte units do not cover (only at the ragged end of the batch) is copied by hand, BEFORE
+    // the arrival below publishes the stage
+    for (uint32_t r = n4; r < nread; ++r) {
+      reinterpret_cast<int32_t*>(st + kPtOffTid + 16)[r] = a.tid[r0 + r];
+      reinterpret_cast<int32_t*>(st + kPtOffPos + 16)[r] = a.pos[r0 + r];
+      reinterpret_cast<uint32_t*>(st + kPtOffOff)[r] = g_off[r0 + r];
+    }
+    for (uint32_t r = n8; r < nread; ++r) reinterpret_cast<uint16_t*>(st + kPtOffFlag)[r] = a.flag[r0 + r];
+    for (uint32_t r = n16; r < nread; ++r) reinterpret_cast<uint8_t*>(st + kPtOffMapq)[r] = a.mapq[r0 + r];
+    reinterpret_cast<uint32_t*>(st + kPtOffOff)[nread] = oe;        // offsets: one entry more than reads
+    if (fits) for (uint32_t o = max(a1, a0); o < oe; ++o) reinterpret_cast<uint32_t*>(st + kPtOffCig)[o - a0] = a.cig[o];
+    meta[s].a0 = a0; meta[s].in_smem = fits ? 1u : 0u;
+    const uint32_t tx = 2u * (prev + 4u * n4) + 4u * n4 + 2u * n8 + n16 + cig_bytes;
+    mbar_arrive_expect_tx(&full[s], tx);
+    if (prev + n4) {
+      tma_load_1d_hint(st + kPtOffTid + 16 - prev, a.tid + r0 - (prev >> 2), prev + 4u * n4, &full[s], pol);
+      tma_load_1d_hint(st + kPtOffPos + 16 - prev, a.pos + r0 - (prev >> 2), prev + 4u * n4, &full[s], pol);
+    }
+    if (n4) tma_load_1d_hint(st + kPtOffOff, g_off + r0, 4u * n4, &full[s], pol);
+    if (n8) tma_load_1d_hint(st + kPtOffFlag, a.flag + r0, 2u * n8, &full[s], pol);
+    if (n16) tma_load_1d_hint(st + kPtOffMapq, a.mapq + r0, n16, &full[s], pol);
+    if (cig_bytes) tma_load_1d_hint(st + kPtOffCig, a.cig + a0, cig_bytes, &full[s], pol);
+    ob = nob; oe = noe;
+  }
+}
+
+__global__ void __launch_bounds__(kPtThreads, MCOV_PREP_CTAS)
+k_fused_prep_tma(const __grid_constant__ FusedArgs f) {
+  extern __shared__ __align__(128) char pt_smem[];
+  __shared__ __align__(8) uint64_t s_full[kPtStages], s_empty[kPtStages];
+  __shared__ PtMeta s_meta[kPtStages];
+  pdl_launch_dependents();                                    // k_scan_counts may take free slots as this grid drains
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kPtStages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kPrepThreads / 32); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const int64_t n = f.e.n;
+  const int64_t n_chunks = (n + kPtChunk - 1) / kPtChunk;
+  if (warp == kPrepThreads / 32) {                             // producer warp
+    if (lane == 0) prep_producer(f, pt_smem, s_full, s_empty, s_meta, n_chunks);
+    return;
+  }
+  PrepWarp W = {0ull, 0u, 0u, 0u, -1, 0u, 0u, 0u};
+  const unsigned G = gridDim.x;
+  unsigned it = 0;
+#pragma unroll 1
+  for (int64_t c = blockIdx.x; c < n_chunks; c += G, ++it) {
+    const unsigned s = it % kPtStages, k = it / kPtStages;
+    mbar_wait(&s_full[s], k & 1);                               // the chunk has landed
+    const char* st = pt_smem + (size_t)s * kPtStageBytes;
+    const PtMeta m = s_meta[s];
+    const int64_t i0 = c * kPtChunk + (int64_t)threadIdx.x * kPrepPer;
+    // the read before this warp's first one (lane 0 only): sortedness and tile border across warps
+    int32_t pvT = -1, pvP = -1;
+    if (lane == 0 && i0 > 0 && i0 - 1 < n) {
+      pvT = reinterpret_cast<const int32_t*>(st + kPtOffTid + 16)[(int)threadIdx.x * kPrepPer - 1];
+      pvP = reinterpret_cast<const int32_t*>(st + kPtOffPos + 16)[(int)threadIdx.x * kPrepPer - 1];
+    }
+    const PrepReads R = prep_reduce_staged(f, st, m, i0, lane);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_empty[s]);                    // this warp is done with the stage
+    prep_emit(f, i0, R, pvT, pvP, lane, W);
+  }
+  prep_flush_counters<true>(f.e.pc, W.n_pass, W.aligned, W.unsorted, W.max_span);
+}
+
+}  // namespace mcov

@@ -61,7 +61,8 @@ struct WalkOut {
 // Walk the bins [lo, hi] of a counting histogram held in shared memory (bins outside the range are
 // not touched and may hold garbage); all THREADS threads participate, the result is valid on thread
 // 0.  n = number of values the histogram describes.
-template <int THREADS>
+// CONSUMERS_ONLY: the THREADS threads are the consumer warps of a warp-specialised CTA and meet at named barrier 1
+template <int THREADS, bool CONSUMERS_ONLY = false>
 __device__ __forceinline__ WalkOut hist_walk(const uint32_t* hist, long long n, int breadth_n, int lo, int hi,
                                              unsigned long long* s_u64 /* [6][THREADS/32] */,
                                              int* s_i32 /* [4][THREADS/32] */, int* s_med /* 2 */) {
@@ -81,7 +82,7 @@ __device__ __forceinline__ WalkOut hist_walk(const uint32_t* hist, long long n, 
     if (lane >= o) x += y;
   }
   if (lane == 31) s_u64[warp] = x;
-  __syncthreads();
+  if (CONSUMERS_ONLY) named_bar_sync<1, THREADS>(); else __syncthreads();
   unsigned long long before = 0;
 #pragma unroll
   for (int k = 0; k < kW; ++k) before += (k < warp) ? s_u64[k] : 0ull;
@@ -107,7 +108,7 @@ __device__ __forceinline__ WalkOut hist_walk(const uint32_t* hist, long long n, 
       }
     }
   }
-  __syncthreads();                                            // s_u64[0..kW) consumed, s_med written
+  if (CONSUMERS_ONLY) named_bar_sync<1, THREADS>(); else __syncthreads();                                            // s_u64[0..kW) consumed, s_med written
   sum = warp_sum(sum); iq = warp_sum(iq); ge1 = warp_sum(ge1); geN = warp_sum(geN); sumsq = warp_sum(sumsq);
   mn = warp_min(mn); mx = warp_max(mx);
   if (lane == 0) {
@@ -116,7 +117,7 @@ __device__ __forceinline__ WalkOut hist_walk(const uint32_t* hist, long long n, 
     s_u64[4 * kW + warp] = sumsq;
     s_i32[0 * kW + warp] = mn; s_i32[1 * kW + warp] = mx;
   }
-  __syncthreads();
+  if (CONSUMERS_ONLY) named_bar_sync<1, THREADS>(); else __syncthreads();
   WalkOut w;
   w.sum = 0; w.iq_sum = 0; w.ge1 = 0; w.geN = 0; w.sumsq = 0; w.mn = INT_MAX; w.mx = INT_MIN;
   if (t == 0) {

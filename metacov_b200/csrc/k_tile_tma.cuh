@@ -1,0 +1,276 @@
+// k_tile_tma.cuh -- second kernel of the fused path, warp-specialised: a producer warp feeds the
+// tiles' records through a ring of shared-memory stages with TMA bulk copies behind mbarriers,
+// four consumer warps turn them into depth.
+//
+// Same arithmetic as k_fused_tile (k_fused.cuh): a tile's +1 / +1 go to packed start|end counters in
+// shared memory, the ends of near reads that started before the tile are found by walking back in
+// the sorted order (their number IS the depth entering the tile), far ends come from the buckets,
+// block scan, 128-bit streaming stores.  What moved:
+//   * everything that is latency and bookkeeping -- drawing tickets, resolving them to tiles,
+//     loading tile_first, staging records -- is done by ONE thread of a separate warp, several
+//     tiles ahead of the consumers, instead of by every thread of the CTA in front of every tile
+//     (k_fused_tile spent ~70 % of its 54 M warp instructions outside the scan itself);
+//   * records arrive by cp.async.bulk (one copy per tile: walk-back candidates and own records are
+//     contiguous in the sorted order), consumers read them from shared memory;
+//   * two barriers per tile instead of three (a thread clears exactly the counter vectors it has
+//     just read), over the four consumer warps only;
+//   * tiles touched by >= 65 536 reads take two 32-bit passes (starts, then ends) over the same
+//     8 KB of counters instead of a second counter array, so a CTA needs 8 KB + the ring.
+// Tile order: tickets, heavy tiles first, exactly as in k_fused_tile.  A pass may be restricted to
+// the tile range [tile_lo, tile_hi) (streaming: successive batches of a sorted file).
+#pragma once
+#include "k_fused.cuh"
+
+namespace mcov {
+
+#ifndef MCOV_TT_STAGES
+#define MCOV_TT_STAGES 3
+#endif
+#ifndef MCOV_TT_STAGE_RECS
+#define MCOV_TT_STAGE_RECS 1536
+#endif
+#ifndef MCOV_TT_CTAS
+#define MCOV_TT_CTAS 8
+#endif
+constexpr int kTtStages = MCOV_TT_STAGES;
+constexpr int kTtStageRecs = MCOV_TT_STAGE_RECS;             // records staged per tile (walk-back candidates + own)
+constexpr int kTtThreads = kFusedThreads + 32;               // 4 consumer warps + the producer warp
+static_assert(kTtStageRecs % 4 == 0, "stage = whole 16-byte vectors");
+
+struct TtMeta {
+  int64_t tile;           // < 0: no more tiles
+  uint32_t r0, r1, jmin;  // own records [r0, r1); walk-back candidates [jmin, r0)
+  uint32_t jb, nst;       // records [jb, jb + nst) are in the stage
+};
+
+__device__ __forceinline__ uint32_t tt_rec(const FusedArgs& f, const TtMeta& m, const uint32_t* s_rec, uint32_t j) {
+  const uint32_t k = j - m.jb;
+  return k < m.nst ? s_rec[k] : __ldg(f.rec + j);               // dense tiles: what does not fit the stage, from global
+}
+
+// scatter of one tile's records into the counters.  WHAT: 0 = packed starts|ends, 1 = starts only, 2 = ends only
+template <int WHAT>
+__device__ __forceinline__ int tt_scatter(const FusedArgs& f, const TtMeta& m, const uint32_t* s_rec, int* s_cnt, uint32_t reach,
+                                          bool has_far) {
+  const int t = threadIdx.x;
+  for (uint32_t j = m.r0 + t; j < m.r1; j += kFusedThreads) {
+    const uint32_t r = tt_rec(f, m, s_rec, j);
+    const uint32_t code = r >> kTileShift;
+    if (code) {
+      const uint32_t local = r & (kTile - 1);
+      if (WHAT != 2) atomicAdd(&s_cnt[local], 1);
+      const uint32_t el = local + code;
+      if (WHAT != 1 && el < (uint32_t)kTile) atomicAdd(&s_cnt[el], WHAT == 0 ? 0x10000 : 1);
+    }
+  }
+  // near reads that started before the tile and end inside it (see k_fused_tile): walk back while the
+  // start is within `reach` slots of the tile; every hit covers the last slot before the tile
+  int open = 0;
+  if (WHAT != 1) {
+    for (int64_t j = (int64_t)m.r0 - 1 - t; j >= (int64_t)m.jmin; j -= kFusedThreads) {
+      const uint32_t r = tt_rec(f, m, s_rec, (uint32_t)j);
+      const uint32_t d = (uint32_t)kTile - (r & (kTile - 1));
+      if (d > reach) break;
+      const uint32_t code = r >> kTileShift;
+      if (code >= d && code <= kNearSpan) { atomicAdd(&s_cnt[code - d], WHAT == 0 ? 0x10000 : 1); ++open; }
+    }
+    if (has_far) {
+      const uint32_t k0 = m.tile > 0 ? f.tile_cnt[m.tile - 1] : 0u, k1 = f.tile_cnt[m.tile];
+      for (uint32_t k = k0 + t; k < k1; k += kFusedThreads) atomicAdd(&s_cnt[f.far_sorted[k] & (kTile - 1)], WHAT == 0 ? 0x10000 : 1);
+    }
+  }
+  return open;
+}
+
+__global__ void __launch_bounds__(kTtThreads, MCOV_TT_CTAS)
+k_fused_tile_tma(const __grid_constant__ FusedArgs f) {
+  __shared__ __align__(16) int s_cnt[kTile];
+  __shared__ __align__(16) uint32_t s_rec[kTtStages][kTtStageRecs];
+  __shared__ __align__(8) uint64_t s_full[kTtStages], s_empty[kTtStages];
+  __shared__ TtMeta s_meta[kTtStages];
+  __shared__ int s_warp[kFusedThreads / 32], s_warp2[kFusedThreads / 32];
+  __shared__ int s_open[2];
+  PassCounters* pc = f.e.pc;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  {                                                     // (before the dependency wait: touches nothing global)
+    int4* z0 = reinterpret_cast<int4*>(s_cnt);
+    for (int k = threadIdx.x; k < kTile / 4; k += kTtThreads) z0[k] = make_int4(0, 0, 0, 0);
+    if (threadIdx.x < 2) s_open[threadIdx.x] = 0;
+    if (threadIdx.x == 0) {
+      for (int s = 0; s < kTtStages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kFusedThreads / 32); }
+      mbar_fence_init();
+    }
+  }
+  __syncthreads();
+  pdl_wait();                                           // records, tile_first and the far tables are complete
+  pdl_launch_dependents();
+
+  if (warp == kFusedThreads / 32) {
+    // ---------------- producer: one thread ----------------
+    if (lane != 0) return;
+    const uint32_t n_heavy = pc->n_heavy;
+    const unsigned G = gridDim.x;
+    auto resolve = [&](unsigned tk, TtMeta& m) {        // ticket -> tile + its record ranges; tile = -1: skip, -2: past the end
+      m.r0 = m.r1 = m.jmin = m.jb = m.nst = 0;
+      int64_t T;
+      if (tk < n_heavy) T = f.tile_heavy[tk];
+      else {
+        T = f.tile_lo + (int64_t)(tk - n_heavy);
+        if (T >= f.tile_hi) { m.tile = -2; return; }
+      }
+      m.r0 = f.tile_first[T]; m.r1 = f.tile_first[T + 1];
+      m.jmin = T > 0 ? f.tile_first[T - 1] : 0u;
+      m.tile = (tk >= n_heavy && n_heavy != 0 && m.r1 - m.r0 >= f.heavy_min) ? -1 : T;   // a heavy tile met again in position order
+    };
+    TtMeta m_cur, m_nxt;
+    resolve(blockIdx.x, m_cur);
+    unsigned tk_nxt = blockIdx.x + G;
+    unsigned it = 0;
+    while (true) {
+      // the ticket after next (one atomic per tile) and the metadata of the next tile: in flight while this tile is published
+      const unsigned tk_new = 2u * G + atomicAdd(&pc->ticket2, 1u);
+      resolve(tk_nxt, m_nxt);
+      if (m_cur.tile != -1) {
+        const unsigned s = it % kTtStages, k = it / kTtStages;
+        if (k > 0) mbar_wait(&s_empty[s], (k - 1) & 1);
+        if (m_cur.tile >= 0) {
+          m_cur.jb = m_cur.jmin & ~3u;
+          const uint32_t want = ((m_cur.r1 + 3u) & ~3u) - m_cur.jb;        // (the record buffer is padded past n)
+          m_cur.nst = min(want, (uint32_t)kTtStageRecs);
+        }
+        s_meta[s] = m_cur;
+        if (m_cur.tile >= 0 && m_cur.nst) {
+          mbar_arrive_expect_tx(&s_full[s], 4u * m_cur.nst);
+          tma_load_1d(&s_rec[s][0], f.rec + m_cur.jb, 4u * m_cur.nst, &s_full[s]);
+        } else {
+          mbar_arrive(&s_full[s]);
+        }
+        ++it;
+        if (m_cur.tile < 0) break;                      // -2: the consumers have been told to stop
+      }
+      m_cur = m_nxt; tk_nxt = tk_new;
+    }
+    return;
+  }
+
+  // ---------------- consumers: 4 warps ----------------
+  const uint32_t reach = pc->max_span;                  // written by the prep kernel
+  const bool has_far = pc->n_far != 0;                  // else the far tables are all zero and are not read
+  int mx = 0, cap = 0;
+  int par = 0;
+#pragma unroll 1
+  for (unsigned it = 0;; ++it, par ^= 1) {
+    const unsigned s = it % kTtStages, k = it / kTtStages;
+    mbar_wait(&s_full[s], k & 1);
+    const TtMeta m = s_meta[s];
+    if (m.tile < 0) break;
+    const uint32_t* rec = s_rec[s];
+    // every +1 of the tile comes from an own record, a walk-back candidate or a far end: fewer than 65 536 of
+    // them keep both halves of the packed counters from overflowing
+    uint32_t touching = m.r1 - m.jmin;
+    if (has_far) touching += f.tile_cnt[m.tile] - (m.tile > 0 ? f.tile_cnt[m.tile - 1] : 0u);
+    const bool packed = touching < 65536u;
+    int4 st[kTileVec], en[kTileVec];
+    if (packed) {
+      int open = tt_scatter<0>(f, m, rec, s_cnt, reach, has_far);
+      open = __reduce_add_sync(0xffffffffu, open);
+      if (lane == 0) { if (open) atomicAdd(&s_open[par], open); mbar_arrive(&s_empty[s]); }   // stage free: the records have been read
+      named_bar_sync<1, kFusedThreads>();
+      const int4* vs = reinterpret_cast<const int4*>(s_cnt);
+#pragma unroll
+      for (int j = 0; j < kTileVec; ++j) {
+        const int idx = (warp * kTileVec + j) * 32 + lane;
+        const int4 c = vs[idx];
+        reinterpret_cast<int4*>(s_cnt)[idx] = make_int4(0, 0, 0, 0);      // cleared by the thread that read it
+        en[j] = make_int4((int)((unsigned)c.x >> 16), (int)((unsigned)c.y >> 16), (int)((unsigned)c.z >> 16), (int)((unsigned)c.w >> 16));
+        st[j] = make_int4(c.x & 0xffff, c.y & 0xffff, c.z & 0xffff, c.w & 0xffff);
+      }
+    } else {
+      // dense tile: starts and ends counted in two 32-bit passes over the same counters
+      tt_scatter<1>(f, m, rec, s_cnt, reach, has_far);
+      named_bar_sync<1, kFusedThreads>();
+#pragma unroll
+      for (int j = 0; j < kTileVec; ++j) {
+        const int idx = (warp * kTileVec + j) * 32 + lane;
+        st[j] = reinterpret_cast<const int4*>(s_cnt)[idx];
+        reinterpret_cast<int4*>(s_cnt)[idx] = make_int4(0, 0, 0, 0);
+      }
+      named_bar_sync<1, kFusedThreads>();
+      int open = tt_scatter<2>(f, m, rec, s_cnt, reach, has_far);
+      open = __reduce_add_sync(0xffffffffu, open);
+      if (lane == 0) { if (open) atomicAdd(&s_open[par], open); mbar_arrive(&s_empty[s]); }
+      named_bar_sync<1, kFusedThreads>();
+#pragma unroll
+      for (int j = 0; j < kTileVec; ++j) {
+        const int idx = (warp * kTileVec + j) * 32 + lane;
+        en[j] = reinterpret_cast<const int4*>(s_cnt)[idx];
+        reinterpret_cast<int4*>(s_cnt)[idx] = make_int4(0, 0, 0, 0);
+      }
+    }
+    // block scan of (starts - ends), warp-striped.  cap[p] = depth[p-1] + starts[p] is folded into one value per
+    // vector, relative to the vector's incoming depth.
+    int4 v[kTileVec];
+    int run[kTileVec], capv[kTileVec];
+#pragma unroll
+    for (int j = 0; j < kTileVec; ++j) {
+      v[j].x = st[j].x - en[j].x;
+      v[j].y = v[j].x + st[j].y - en[j].y;
+      v[j].z = v[j].y + st[j].z - en[j].z;
+      v[j].w = v[j].z + st[j].w - en[j].w;
+      capv[j] = max(max(st[j].x, v[j].x + st[j].y), max(v[j].y + st[j].z, v[j].z + st[j].w));
+      run[j] = v[j].w;
+    }
+    int acc = 0;
+#pragma unroll
+    for (int j = 0; j < kTileVec; ++j) {
+      int x = run[j];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      const int total = __shfl_sync(0xffffffffu, x, 31);
+      run[j] = x - run[j] + acc;
+      acc += total;
+    }
+    if (lane == 31) s_warp[warp] = acc;
+    // the other s_open buffer: last read after the previous tile's second barrier (every thread has passed this
+    // tile's first barrier since), next added to after this tile's second barrier
+    if (threadIdx.x == 0) s_open[par ^ 1] = 0;
+    const int carry = (has_far && m.tile > 0) ? f.tile_agg[m.tile - 1] : 0;     // far reads open at the tile border
+    named_bar_sync<1, kFusedThreads>();
+    int off = carry + s_open[par];                       // + near reads open at the border
+#pragma unroll
+    for (int w = 0; w < kFusedThreads / 32; ++w) off += (w < warp) ? s_warp[w] : 0;
+    const int64_t base = m.tile << kTileShift;
+    int4* out = reinterpret_cast<int4*>(f.depth + base);
+    const int64_t n_vec = (f.n_slots - base) >> 2;
+    int cap_t = 0;
+#pragma unroll
+    for (int j = 0; j < kTileVec; ++j) {
+      const int idx = (warp * kTileVec + j) * 32 + lane;
+      const int o = off + run[j];
+      cap_t = max(cap_t, o + capv[j]);
+      v[j].x += o; v[j].y += o; v[j].z += o; v[j].w += o;
+      mx = max(mx, max(max(v[j].x, v[j].y), max(v[j].z, v[j].w)));
+      if (idx < n_vec) st_stream_int4(out + idx, v[j]);
+    }
+    cap = max(cap, cap_t);
+    // htslib's cap could fire somewhere in this tile (rare): remember the tile for the exact replay
+    if (f.max_depth > 0 && cap_t > f.max_depth) atomicMax(f.tile_cap + m.tile, cap_t);
+  }
+  mx = warp_max(mx);
+  cap = warp_max(cap);
+  if (lane == 0) { s_warp2[warp] = cap; }
+  named_bar_sync<1, kFusedThreads>();                    // (s_warp of the last tile has been read by everyone)
+  if (lane == 0) s_warp[warp] = mx;
+  named_bar_sync<1, kFusedThreads>();
+  if (threadIdx.x == 0) {
+    int m2 = 0, c2 = 0;
+    for (int w = 0; w < kFusedThreads / 32; ++w) { m2 = max(m2, s_warp[w]); c2 = max(c2, s_warp2[w]); }
+    if (m2 > 0) atomicMax(&pc->max_depth_seen, m2);
+    if (c2 > 0) atomicMax(&pc->cap_metric, c2);
+  }
+}
+
+}  // namespace mcov

@@ -12,10 +12,13 @@
 #include "ctx.cuh"
 #include "k_expand.cuh"
 #include "k_fused.cuh"
+#include "k_prep_tma.cuh"
+#include "k_tile_tma.cuh"
 #include "k_hist.cuh"
 #include "k_scan.cuh"
 #include "k_export.cuh"
 #include "k_stats.cuh"
+#include "k_stats_stream.cuh"
 
 using namespace mcov;
 
@@ -157,6 +160,7 @@ int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a) {
   f.rec = ctx->d_start_slot.as<uint32_t>();
   f.n_slots = ctx->n_slots;
   f.n_tiles = n_tiles;
+  f.tile_lo = 0; f.tile_hi = n_tiles;
   f.far_end = ctx->d_far_list.as<int64_t>();
   f.far_cap = far_cap;
   f.tile_agg = reinterpret_cast<int32_t*>(z + o_agg);
@@ -177,7 +181,18 @@ int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a) {
               al(a.flag, 8) && al(a.mapq, 4)) ? 1 : 0;
   if (n > 0) {
     const int64_t groups = (n + kPrepPer - 1) / kPrepPer;
-    if (off64) MCOV_LAUNCH(ctx, kKFusedPrep, (k_fused_prep<true><<<grid_for(ctx, groups, kPrepThreads, 8), kPrepThreads, 0, s>>>(f)));
+    // short-read hot path: SoA chunks staged by TMA bulk copies behind mbarriers (k_prep_tma.cuh); needs 32-bit
+    // offsets and 16-byte aligned columns.  Anything else takes the per-thread loads of k_fused_prep.
+    static const bool no_tma = std::getenv("MCOV_PREP_LEGACY") != nullptr;     // tuning hook
+    const bool tma = !off64 && !no_tma && al(a.tid, 16) && al(a.pos, 16) && al(a.cig_off, 16) && al(a.flag, 16) &&
+                     al(a.mapq, 16) && al(a.cig, 16);
+    if (tma) {
+      static bool attr_set = false;
+      if (!attr_set) { CU(cudaFuncSetAttribute(k_fused_prep_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kPtSmemBytes)); attr_set = true; }
+      const int64_t n_chunks = (n + kPtChunk - 1) / kPtChunk;
+      const unsigned grid = (unsigned)std::min<int64_t>(n_chunks, (int64_t)ctx->n_sm * MCOV_PREP_CTAS);
+      MCOV_LAUNCH(ctx, kKFusedPrep, (k_fused_prep_tma<<<grid, kPtThreads, kPtSmemBytes, s>>>(f)));
+    } else if (off64) MCOV_LAUNCH(ctx, kKFusedPrep, (k_fused_prep<true><<<grid_for(ctx, groups, kPrepThreads, 8), kPrepThreads, 0, s>>>(f)));
     else MCOV_LAUNCH(ctx, kKFusedPrep, (k_fused_prep<false><<<grid_for(ctx, groups, kPrepThreads, 8), kPrepThreads, 0, s>>>(f)));
     CU(cudaGetLastError());
   } else {
@@ -191,8 +206,15 @@ int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a) {
   MCOV_LAUNCH(ctx, kKFarScatter, CU(launch_pdl(pdl, k_far_scatter, dim3(ctx->n_sm * 2), dim3(256), 0, s, f)));
   ctx->fused_blob.assign(reinterpret_cast<const unsigned char*>(&f), reinterpret_cast<const unsigned char*>(&f) + sizeof(f));
   {
-    const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)ctx->n_sm * MCOV_TILE_MIN_CTAS);   // persistent
-    MCOV_LAUNCH(ctx, kKFusedTile, CU(launch_pdl(pdl, k_fused_tile, dim3(grid), dim3(kFusedThreads), 0, s, f)));
+    static const bool tile_legacy = std::getenv("MCOV_TILE_LEGACY") != nullptr;     // tuning hook
+    if (tile_legacy) {
+      const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)ctx->n_sm * MCOV_TILE_MIN_CTAS);   // persistent
+      MCOV_LAUNCH(ctx, kKFusedTile, CU(launch_pdl(pdl, k_fused_tile, dim3(grid), dim3(kFusedThreads), 0, s, f)));
+    } else {
+      // warp-specialised: producer warp + TMA record ring + 4 consumer warps (k_tile_tma.cuh); persistent
+      const unsigned grid = (unsigned)std::min<int64_t>(f.tile_hi - f.tile_lo, (int64_t)ctx->n_sm * MCOV_TT_CTAS);
+      MCOV_LAUNCH(ctx, kKFusedTile, CU(launch_pdl(pdl, k_fused_tile_tma, dim3(std::max(grid, 1u)), dim3(kTtThreads), 0, s, f)));
+    }
   }
   // htslib's max_depth cap: replayed on the device, in stream order, where the tile kernel found that
   // it can fire (k_cap_replay returns after one load otherwise) -- every consumer of the depth that
@@ -278,6 +300,7 @@ void mcov_destroy(mcov_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->d_len, &ctx->d_off, &ctx->depth_own, &ctx->d_pc, &ctx->d_status, &ctx->d_end_slot,
                     &ctx->d_start_slot, &ctx->d_far_list, &ctx->d_tile_cnt, &ctx->d_tile_off, &ctx->d_far_sorted,
                     &ctx->d_tasks, &ctx->d_rlen, &ctx->d_rchunks, &ctx->d_rhist, &ctx->d_pool, &ctx->d_done,
+                    &ctx->d_ss_pieces, &ctx->d_ss_cta, &ctx->d_ss_split, &ctx->d_ss_pool,
                     &ctx->d_out, &ctx->d_win_slot, &ctx->d_win_n, &ctx->d_win_out, &ctx->d_htasks, &ctx->d_tile_heavy, &ctx->d_run_tasks, &ctx->d_run_counts, &ctx->d_run_out};
   for (DevBuf* b : bufs) b->release();
   ctx->bam.release();
@@ -775,6 +798,53 @@ static int stats_launch(mcov_ctx* ctx, int64_t g, const int32_t* tid, const int3
         tasks.push_back(t);
       }
     }
+    // The balanced stream over the large regions (k_stats_stream.cuh): their concatenation cut into equal slices,
+    // one per persistent CTA; a region cut by a slice border becomes a "split" region with a global histogram.
+    {
+      int64_t total_big = 0;
+      for (int64_t i = 0; i < g; ++i) if (rchunks[i] >= 1 && !(rchunks[i] == 1 && rp.rlen[i] <= kSmallRegion)) total_big += rp.rlen[i];
+      std::vector<SsPiece> pieces;
+      std::vector<int32_t> cta_start, split_region;
+      int32_t grid = (int32_t)std::min<int64_t>((int64_t)ctx->n_sm * MCOV_SS_CTAS, std::max<int64_t>(1, total_big / 16384));
+      const int64_t W = std::max<int64_t>(4, ((total_big + grid - 1) / grid + 3) & ~(int64_t)3);
+      int64_t room = W;
+      cta_start.push_back(0);
+      for (int64_t i = 0; i < g && total_big > 0; ++i) {
+        if (rchunks[i] < 1 || (rchunks[i] == 1 && rp.rlen[i] <= kSmallRegion)) continue;
+        int64_t rem = rp.rlen[i];
+        int64_t slot = ctx->off[tid[i]] + std::min<int64_t>(start[i], ctx->len[tid[i]]);
+        const size_t first_piece = pieces.size();
+        while (rem > 0) {
+          const int64_t take = std::min(rem, room);
+          SsPiece pc;
+          pc.slot = slot; pc.n = (int32_t)take; pc.region = (int32_t)i; pc.pad = pieces.size() == first_piece ? rp.rpad[i] : 0; pc.split = -1;
+          pieces.push_back(pc);
+          rem -= take; slot += take; room -= take;
+          if (room == 0) { cta_start.push_back((int32_t)pieces.size()); room = W; }
+        }
+        if (pieces.size() - first_piece > 1) {
+          const int32_t id = (int32_t)split_region.size();
+          split_region.push_back((int32_t)i);
+          for (size_t k = first_piece; k < pieces.size(); ++k) pieces[k].split = id;
+        }
+      }
+      if (cta_start.back() != (int32_t)pieces.size()) cta_start.push_back((int32_t)pieces.size());
+      rp.ss_grid = total_big > 0 ? (int32_t)cta_start.size() - 1 : 0;
+      rp.n_split = (int32_t)split_region.size();
+      if (rp.ss_grid > 0) {
+        CU(ctx->d_ss_pieces.ensure(pieces.size() * sizeof(SsPiece)));
+        CU(ctx->d_ss_cta.ensure(cta_start.size() * 4));
+        CU(ctx->d_ss_split.ensure(std::max<size_t>(split_region.size(), 1) * 4));
+        CU(ctx->d_ss_pool.ensure((size_t)std::max(rp.n_split, 1) * (sizeof(RegionScratch) + (size_t)kHistBins * 4)));
+        CU(cudaMemcpyAsync(ctx->d_ss_pieces.p, pieces.data(), pieces.size() * sizeof(SsPiece), cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(ctx->d_ss_cta.p, cta_start.data(), cta_start.size() * 4, cudaMemcpyHostToDevice, s));
+        if (rp.n_split) {
+          CU(cudaMemcpyAsync(ctx->d_ss_split.p, split_region.data(), split_region.size() * 4, cudaMemcpyHostToDevice, s));
+          CU(cudaMemsetAsync(ctx->d_ss_pool.p, 0, (size_t)rp.n_split * (sizeof(RegionScratch) + (size_t)kHistBins * 4), s));
+        }
+        CU(cudaStreamSynchronize(s));                 // the host vectors above go out of scope
+      }
+    }
     // Largest jobs first, and -- for the warp-per-region kernel, where a CTA of 8 warps lives as long as its
     // largest region -- neighbours of similar size: with the log-normal contig lengths of config C3 an
     // unsorted CTA keeps its slots for about twice the mean of its regions.
@@ -803,7 +873,23 @@ static int stats_launch(mcov_ctx* ctx, int64_t g, const int32_t* tid, const int3
   }
   if (g > 0) {
     const size_t done_bytes = (size_t)rp.n_multi * sizeof(RegionScratch);
-    if (rp.n_tasks) {
+    static const bool stats_legacy = std::getenv("MCOV_STATS_LEGACY") != nullptr;     // tuning hook
+    if (rp.ss_grid > 0 && !stats_legacy) {
+      static bool attr_set = false;
+      if (!attr_set) { CU(cudaFuncSetAttribute(k_stats_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, kSsSmemBytes)); attr_set = true; }
+      SsArgs a;
+      int32_t* d_rlen = ctx->d_rlen.as<int32_t>();
+      a.depth = ctx->depth; a.pieces = ctx->d_ss_pieces.as<SsPiece>(); a.cta_piece_start = ctx->d_ss_cta.as<int32_t>();
+      a.region_len = d_rlen; a.region_pad = d_rlen + g;
+      a.split_scratch = ctx->d_ss_pool.as<RegionScratch>();
+      a.split_hist = reinterpret_cast<uint32_t*>(ctx->d_ss_pool.as<char>() + (size_t)rp.n_split * sizeof(RegionScratch));
+      a.out = d_out; a.breadth_n = breadth_n;
+      const bool pdl = ctx->n_slots <= kPdlMaxSlots;
+      MCOV_LAUNCH(ctx, kKRegionStats, CU(launch_pdl(pdl, k_stats_stream, dim3((unsigned)rp.ss_grid), dim3(kSsThreads), (size_t)kSsSmemBytes, s, a)));
+      if (rp.n_split)
+        MCOV_LAUNCH(ctx, kKHistFinish, CU(launch_pdl(pdl, k_stats_split_finish, dim3((unsigned)rp.n_split), dim3(kSsConsumers), 0, s, a,
+                                                     (const int32_t*)ctx->d_ss_split.as<int32_t>())));
+    } else if (rp.n_tasks) {
       StatArgs a;
       int32_t* d_rlen = ctx->d_rlen.as<int32_t>();
       a.depth = ctx->depth; a.tasks = ctx->d_tasks.as<StatTask>(); a.region_len = d_rlen; a.region_pad = d_rlen + g;
