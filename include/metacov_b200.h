@@ -153,6 +153,33 @@ int  mcov_depth_sorted_async(mcov_ctx* ctx, int64_t n,
                              const uint32_t* cig_off, const uint32_t* cig,
                              int mem_kind);
 
+/* Streaming a coordinate-sorted file in batches (the reference never holds the file:
+ * metacov/scan.pyx:653-667 loops over `cnext()`, pileup.py:13 iterates htslib's
+ * streaming pileup).  mcov_stream_begin starts a pass; every mcov_stream_push adds the
+ * next batch in file order through the fused sorted path and makes the depth FINAL up
+ * to the 2048-slot tile that holds the batch's last read; the last push (last = 1)
+ * finishes the slot space.  What crosses a batch border travels as DATA, like the
+ * boundary reads of a contig cut between GPUs: each push returns a resend point
+ * (resend_tid, resend_pos), and the next batch must BEGIN with a copy of every read of
+ * the earlier batches that starts at or after that point or whose interval
+ * [pos, pos + reflen) reaches past it, in file order (n_carry = how many such reads
+ * lead the batch; they are not counted twice in mcov_pass_info).  Sending more than
+ * required is harmless as long as the order is kept.  The final push carries the last
+ * resend set too (n may equal n_carry).  The sortedness verdict is delivered by the
+ * first synchronising call after the last push.  A file in which htslib's max_depth
+ * cap fires is reported (MCOV_ERR_STATE) rather than replayed: the replay needs a
+ * contig's reads in one batch.  mcov_stream_resend_point computes the resend point a
+ * batch ending with the read (last_tid, last_pos) will return (host arithmetic only). */
+int  mcov_stream_begin(mcov_ctx* ctx);
+int  mcov_stream_push(mcov_ctx* ctx, int64_t n, int64_t n_carry,
+                      const int32_t* tid, const int32_t* pos,
+                      const uint16_t* flag, const uint8_t* mapq,
+                      const uint32_t* cig_off, const uint32_t* cig,
+                      int mem_kind, int last,
+                      int32_t* resend_tid, int32_t* resend_pos);
+int  mcov_stream_resend_point(const mcov_ctx* ctx, int32_t last_tid, int32_t last_pos,
+                              int32_t* resend_tid, int32_t* resend_pos);
+
 /* Compact HOST transport of a coordinate-sorted batch (the PCIe link bounds the
  * end-to-end rate): instead of tid[n] the per-contig read prefix
  * contig_read_start[n_contigs+1] (reads [crs[c], crs[c+1]) belong to contig c,

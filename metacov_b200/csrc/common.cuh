@@ -16,6 +16,14 @@ constexpr uint32_t kRefConsumeMask = 0x18Du;
 __host__ __device__ __forceinline__ uint32_t cigar_ref_len(uint32_t op) {
   return ((kRefConsumeMask >> (op & 15u)) & 1u) ? (op >> 4) : 0u;
 }
+// acc + cigar_ref_len(op), arranged for the pipes of the SM: the integer ALU pipe (logic, shifts,
+// compares, selects: 16 lanes per clock) is what bounds the prep kernels (ncu: 72 % busy, FMA pipe
+// 12 %), so the length extraction and the conditional add are done as IMAD.HI + IMAD on the FMA
+// pipe; the mask lookup is one wrap-around shift of the table replicated into both half words.
+__device__ __forceinline__ uint32_t cigar_ref_len_add(uint32_t acc, uint32_t op) {
+  const uint32_t bit = ((kRefConsumeMask * 0x10001u) >> (op & 31u)) & 1u;
+  return __umulhi(op, 0x10000000u) * bit + acc;
+}
 
 // Counters of one pass, device resident (mirrored to mcov_pass_info).
 struct PassCounters {
@@ -31,6 +39,8 @@ struct PassCounters {
   unsigned int n_far;    // reads whose span exceeds the near window (fused path)
   unsigned int n_heavy;  // tiles holding >= heavy_min reads (fused path: scheduled first)
   unsigned int cap_contigs;  // contigs replayed under htslib's max_depth cap (k_cap_replay)
+  unsigned int cap_unreplayed;  // streamed pass: the cap can fire in a batch (a contig's reads are not all on the device)
+  unsigned int far_overflow;    // streamed pass: a batch had more long-span reads than the bucket list holds
 };
 
 // pysam __advance_samtools predicate + bam_plp_push's own UNMAP drop
@@ -128,6 +138,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {}
+}
+// Producer-side wait: a producer is usually several stages ahead and would otherwise spin on the
+// "empty" barrier -- a single thread, but every retry costs its scheduler a full issue slot (ncu: 6-12 %
+// of the executed instructions of the first TMA kernels).  try_wait with a suspend-time hint parks the
+// thread in hardware; the sleep between retries bounds what is left.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  for (;;) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+    if (ok) return;
+    __nanosleep(256);
+  }
 }
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

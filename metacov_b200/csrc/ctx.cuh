@@ -39,13 +39,13 @@ struct PinBuf {
   template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-enum PassState { kIdle = 0, kAccumulating = 1, kDepthReady = 2 };
+enum PassState { kIdle = 0, kAccumulating = 1, kDepthReady = 2, kStreaming = 3 };
 
 // kernel ids for the optional per-kernel CUDA-event timing (mcov_profile_*)
 enum KernelId {
   kKExpand = 0, kKScan, kKFusedPrep, kKTileFirst, kKScanCounts, kKFarScatter, kKFusedTile,
   kKInitStats, kKRegionStats, kKWindowSums, kKIsizeHist, kKGroupCount, kKSortedStats, kKClear, kKRegionStatsSmall, kKCapReplay, kKUnpack, kKKmerHist, kKRegionStatsWarp,
-  kKExpPrep, kKExpEntries, kKExpRegion, kKExpRevsum, kKRegionHist, kKHistFinish, kKRunCount, kKRunOffsets, kKRunWrite, kKRunEnds, kKBgzfInflate, kKBamGuess, kKBamWalkCount, kKBamWalkWrite, kKDeltaUnpack,
+  kKExpPrep, kKExpEntries, kKExpRegion, kKExpRevsum, kKRegionHist, kKHistFinish, kKRunCount, kKRunOffsets, kKRunWrite, kKRunEnds, kKBgzfInflate, kKBamGuess, kKBamWalkCount, kKBamWalkWrite, kKDeltaUnpack, kKStreamAcc,
   kKernelCount
 };
 
@@ -90,6 +90,7 @@ struct mcov_ctx {
   bool depth_bound = false;
 
   mcov_filter filt;
+  uint32_t flag_lut[128] = {0};   // the flag part of the filter as a 4096-bit table (rebuilt by mcov_set_filter)
   int state = mcov::kIdle;
 
   mcov::DevBuf d_pc;          // PassCounters
@@ -118,6 +119,10 @@ struct mcov_ctx {
 
   // stats scratch
   mcov::DevBuf d_ss_pieces, d_ss_cta, d_ss_split, d_ss_pool;
+  // streamed passes (mcov_stream_begin / mcov_stream_push)
+  mcov::DevBuf d_stream_acc;          // StreamAcc + the carried reads' counts of the current batch
+  int64_t stream_tile_lo = 0;         // tiles below this one hold final depth
+  int64_t stream_reads = 0;           // distinct reads pushed so far
   mcov::DevBuf d_tasks, d_rlen, d_rchunks, d_rhist, d_pool, d_done, d_out, d_win_slot, d_win_n, d_win_out, d_htasks, d_tile_heavy, d_run_tasks, d_run_counts, d_run_out;
   int64_t n_runs = -1;               // records held in d_run_out ([tid | start | end | depth] x n_runs), -1 = none
   mcov::PinBuf h_pin;

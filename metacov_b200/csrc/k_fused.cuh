@@ -65,6 +65,7 @@ struct FusedArgs {
   int64_t n_slots;
   int64_t n_tiles;
   int64_t tile_lo, tile_hi;   // tiles this pass writes (the whole slot space, or the batch's share when a file is streamed)
+  int streaming;              // the pass is one batch of a streamed file (mcov_stream_push)
   int64_t* far_end;           // [far_cap] end slots of far reads
   uint32_t far_cap;
   int32_t* tile_agg;          // [cnt_pad] (#far starts - #far ends) per tile -> inclusive scan in place
@@ -78,6 +79,7 @@ struct FusedArgs {
   uint32_t heavy_min;
   int32_t max_depth;          // htslib maxcnt (<= 0: cap disabled)
   int vec_ok;                 // SoA base pointers aligned for 128-bit loads
+  uint32_t flag_lut[128];     // bit F of the table: a read with flag F (< 4096: the 12 bits BAM defines) passes the flag filter
 };
 
 // slot key of a read: contig offset + clamped position; reads without a valid
@@ -911,6 +913,7 @@ __global__ void k_cap_replay(FusedArgs f, uint8_t* __restrict__ contig_capped) {
   if (c >= f.e.n_contigs || f.max_depth <= 0) return;
   if (f.e.pc->cap_metric <= f.max_depth) return;
   if (f.e.pc->unsorted || f.e.pc->n_far > f.far_cap) return;     // the pass is rejected by the verdict: nothing to replay
+  if (f.streaming) { if (c == 0) f.e.pc->cap_unreplayed = 1u; return; }   // a contig's reads may lie in other batches: reported, not replayed
   {
     const int64_t b0 = f.e.contig_off[c];
     const int64_t T0 = b0 >> kTileShift, T1 = min((b0 + f.e.contig_len[c]) >> kTileShift, f.n_tiles - 1);
@@ -1042,6 +1045,48 @@ __global__ void k_delta_finish(int64_t n, const int64_t* __restrict__ contig_rea
     const int64_t first = contig_read_start[t >= 0 ? t : n_contigs];      // unplaced reads: one more segment
     pos[i] = (int32_t)((uint32_t)S[i] - (first > 0 ? (uint32_t)S[first - 1] : 0u));
   }
+}
+
+// ---- streamed passes (mcov_stream_begin / mcov_stream_push) ---------------------------------------------
+// A batch of a streamed file starts with n_carry reads that earlier batches have already counted (they are
+// sent again because their intervals reach into this batch's tiles): their contribution to the pass counters
+// is computed here and taken out again by k_stream_accumulate.
+struct StreamAcc { unsigned long long n_pass, aligned_bases; int max_depth_seen, cap_metric; unsigned unsorted, cap_unreplayed, far_overflow, pad; };
+
+__global__ void k_carry_counts(FusedArgs f, int64_t n_carry, unsigned long long* out /* [2]: n_pass, aligned */) {
+  const ExpandArgs& a = f.e;
+  unsigned long long np = 0, al = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_carry; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t t = a.tid[i];
+    if (!read_passes(a.flag[i], a.mapq[i], a.filt) || (uint32_t)t >= (uint32_t)a.n_contigs) continue;
+    const uint64_t o0 = a.cig_off64 ? a.cig_off64[i] : a.cig_off[i], o1 = a.cig_off64 ? a.cig_off64[i + 1] : a.cig_off[i + 1];
+    int64_t rl = 0;
+    for (uint64_t o = o0; o < o1; ++o) rl += cigar_ref_len(a.cig[o]);
+    if (rl > 0x7fffffffll) rl = 0x7fffffffll;
+    const int64_t len = a.contig_len[t];
+    int64_t s = a.pos[i], e = (int64_t)a.pos[i] + rl;
+    s = s < 0 ? 0 : (s > len ? len : s);
+    e = e < 0 ? 0 : (e > len ? len : e);
+    if (e > s) { np += 1; al += (unsigned long long)rl; }
+  }
+  np = warp_sum(np); al = warp_sum(al);
+  if ((threadIdx.x & 31) == 0) { if (np) atomicAdd(out, np); if (al) atomicAdd(out + 1, al); }
+}
+
+// one thread: totals of the stream so far += this batch's counters - its carried reads; the totals are then written
+// back into the pass counters, so that every reader of PassCounters (verdict, mcov_pass_info_get) sees the stream.
+__global__ void k_stream_accumulate(PassCounters* pc, StreamAcc* acc, const unsigned long long* carry, uint32_t far_cap) {
+  acc->n_pass += pc->n_pass - carry[0];
+  acc->aligned_bases += pc->aligned_bases - carry[1];
+  acc->max_depth_seen = max(acc->max_depth_seen, pc->max_depth_seen);
+  acc->cap_metric = max(acc->cap_metric, pc->cap_metric);
+  acc->unsorted |= (unsigned)pc->unsorted;
+  acc->cap_unreplayed |= pc->cap_unreplayed;
+  acc->far_overflow |= pc->n_far > far_cap ? 1u : 0u;
+  pc->n_pass = acc->n_pass; pc->aligned_bases = acc->aligned_bases;
+  pc->max_depth_seen = acc->max_depth_seen; pc->cap_metric = acc->cap_metric;
+  pc->unsorted = (int)acc->unsorted; pc->cap_unreplayed = acc->cap_unreplayed; pc->far_overflow = acc->far_overflow;
+  pc->n_far = 0;
 }
 
 }  // namespace mcov

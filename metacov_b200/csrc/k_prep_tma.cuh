@@ -36,18 +36,20 @@ constexpr int kPtOffOff = kPtOffPos + 16 + 4 * kPtChunk;   // kPtChunk + 1 offse
 constexpr int kPtOffFlag = kPtOffOff + 4 * kPtChunk + 16;
 constexpr int kPtOffMapq = kPtOffFlag + 2 * kPtChunk;
 constexpr int kPtOffCig = kPtOffMapq + kPtChunk;
-constexpr int kPtStageBytes = kPtOffCig + 4 * kPtCigCap;
+constexpr int kPtStageBytes = kPtOffCig + 4 * kPtCigCap + 16;   // (+16: unpredicated op loads may look 3 ops past a read's last one)
 constexpr int kPtSmemBytes = kPtStages * kPtStageBytes;
 static_assert(kPtStageBytes % 16 == 0, "stage size must keep every stage 16-byte aligned");
 
-struct PtMeta { uint32_t a0; uint32_t in_smem; };           // first staged op index; ops are in the stage
+struct PtMeta { int64_t chunk; uint32_t a0; uint32_t in_smem; };   // chunk in the stage (-1: no more); first staged op index; ops are in the stage
 
 // Loads + filter + CIGAR reduction of the 4 reads of one consumer thread, from a landed stage.
-__device__ __forceinline__ PrepReads prep_reduce_staged(const FusedArgs& f, const char* st, const PtMeta m, int64_t i0, int lane) {
+// OPS_STAGED: the chunk's ops are in the stage (LDS), else they stayed in global memory.
+template <bool OPS_STAGED>
+__device__ __forceinline__ PrepReads prep_reduce_staged(const FusedArgs& f, const char* st, const PtMeta m, int64_t i0, int lane,
+                                                        const uint32_t* s_lut) {
   const ExpandArgs& a = f.e;
   const uint32_t n_contigs = (uint32_t)a.n_contigs;
-  const uint32_t drop = (uint32_t)a.filt.flag_filter | 0x4u, req = a.filt.flag_require, minq = a.filt.min_mapq;
-  const uint32_t req_none = req == 0 ? 1u : 0u, orph_mask = a.filt.ignore_orphans ? 3u : 0u;
+  const uint32_t minq = a.filt.min_mapq;
   const int t = threadIdx.x;
   PrepReads R;
   R.nv = (int)min((int64_t)kPrepPer, max((int64_t)0, a.n - i0));
@@ -56,40 +58,79 @@ __device__ __forceinline__ PrepReads prep_reduce_staged(const FusedArgs& f, cons
   const uint4 o4 = *reinterpret_cast<const uint4*>(st + kPtOffOff + 16 * t);
   const uint32_t o_end = *reinterpret_cast<const uint32_t*>(st + kPtOffOff + 16 * t + 16);
   const ushort4 f4 = *reinterpret_cast<const ushort4*>(st + kPtOffFlag + 8 * t);
-  const uchar4 q4 = *reinterpret_cast<const uchar4*>(st + kPtOffMapq + 4 * t);
   R.T[0] = t4.x; R.T[1] = t4.y; R.T[2] = t4.z; R.T[3] = t4.w;
   R.P[0] = p4.x; R.P[1] = p4.y; R.P[2] = p4.z; R.P[3] = p4.w;
-  const uint32_t F[4] = {f4.x, f4.y, f4.z, f4.w}, Q[4] = {q4.x, q4.y, q4.z, q4.w};
-  const uint32_t O[5] = {o4.x, o4.y, o4.z, o4.w, o_end};
-  if (R.nv < kPrepPer) {                         // ragged end of the batch: what lies behind it in the stage is not data
+  const uint32_t F[4] = {f4.x, f4.y, f4.z, f4.w};
+  // The flag filter (pysam __advance_samtools + bam_plp_push's UNMAP drop) is a function of
+  // the flag alone: one bit per flag value in a 4096-bit table (the 12 bits BAM defines), instead of four mask tests
+  // on the ALU pipe that bounds this kernel.  A flag with higher bits set is evaluated in full; mapq only when asked.
+  uint32_t fpass[4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) if (r >= R.nv) { R.T[r] = -1; R.P[r] = 0; }
+  for (int r = 0; r < 4; ++r) fpass[r] = (s_lut[(F[r] >> 5) & 127u] >> (F[r] & 31u)) & 1u;
+  if (((F[0] | F[1]) | (F[2] | F[3])) > 0xFFFu) {
+    const uint32_t drop = (uint32_t)a.filt.flag_filter | 0x4u, req = a.filt.flag_require;
+    const uint32_t req_none = req == 0 ? 1u : 0u, orph_mask = a.filt.ignore_orphans ? 3u : 0u;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      fpass[r] = (((F[r] & drop) == 0u) & (((F[r] & req) | req_none) != 0u) & ((F[r] & orph_mask) != 1u)) ? 1u : 0u;
   }
-  // ops of this chunk: in the stage (generic pointer biased by the first staged op) or left in global memory
-  const uint32_t* __restrict__ cp = m.in_smem ? reinterpret_cast<const uint32_t*>(st + kPtOffCig) - m.a0 : a.cig;
+  if (minq) {
+    const uchar4 q4 = *reinterpret_cast<const uchar4*>(st + kPtOffMapq + 4 * t);
+    const uint32_t Q[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+    for (int r = 0; r < 4; ++r) fpass[r] &= Q[r] >= minq ? 1u : 0u;
+  }
+  uint32_t O[5] = {o4.x, o4.y, o4.z, o4.w, o_end};
+  if (R.nv < kPrepPer) {                         // ragged end of the batch: what lies behind it in the stage is not data
+    const uint32_t o_last = R.nv == 0 ? m.a0 : R.nv == 1 ? O[1] : R.nv == 2 ? O[2] : O[3];     // = cig_off[n] for nv > 0
+#pragma unroll
+    for (int r = 0; r < 4; ++r) if (r >= R.nv) { R.T[r] = -1; R.P[r] = 0; O[r + 1] = o_last; if (R.nv == 0) O[r] = o_last; }
+  }
+  // ops of this chunk: in the stage or left in global memory
   unsigned passm = 0, coop = 0;
-  uint32_t op0[4], nc[4];
+  uint32_t nc[4];
   uint32_t nc_max = 0;
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
-    const bool p = (r < R.nv) & ((F[r] & drop) == 0u) & (((F[r] & req) | req_none) != 0u) & (Q[r] >= minq) &
-                   ((F[r] & orph_mask) != 1u) & ((uint32_t)R.T[r] < n_contigs);
+    const bool p = (r < R.nv) & (fpass[r] != 0u) & ((uint32_t)R.T[r] < n_contigs);
     nc[r] = O[r + 1] - O[r];
     const bool c = p && nc[r] > kThreadOps;
     passm |= p ? (1u << r) : 0u;
     coop |= c ? (1u << r) : 0u;
-    if (!p || c) nc[r] = 0;
+    if (!p || c) nc[r] = 0;                                           // ops this thread reduces itself
     nc_max = max(nc_max, nc[r]);
-    op0[r] = nc[r] > 0 ? cp[O[r]] : 0u;
   }
+  if (OPS_STAGED) {
+    // Shared-window byte address of each read's first op.  The loads are NOT predicated -- op k of a read with
+    // fewer ops is the next read's op or padding inside the stage, harmless to load -- only the accumulation is,
+    // which keeps a (read, op) evaluation at six instructions; rounds 2..4 run only if some lane of the warp needs them.
+    const uint32_t cig_s = smem_u32(st + kPtOffCig);
+    uint32_t A[4];
 #pragma unroll
-  for (int r = 0; r < 4; ++r) R.reflen[r] = cigar_ref_len(op0[r]);
+    for (int r = 0; r < 4; ++r) A[r] = cig_s + ((O[r] - m.a0) << 2);
+    auto lds = [](uint32_t addr) -> uint32_t { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; };
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { const uint32_t v = cigar_ref_len_add(0u, lds(A[r])); R.reflen[r] = nc[r] > 0 ? v : 0u; }
+    if (nc_max > 1) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) { const uint32_t v = cigar_ref_len_add(R.reflen[r], lds(A[r] + 4)); if (nc[r] > 1) R.reflen[r] = v; }
+      if (nc_max > 2) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { const uint32_t v = cigar_ref_len_add(R.reflen[r], lds(A[r] + 8)); if (nc[r] > 2) R.reflen[r] = v; }
+        if (nc_max > 3) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) { const uint32_t v = cigar_ref_len_add(R.reflen[r], lds(A[r] + 12)); if (nc[r] > 3) R.reflen[r] = v; }
+        }
+      }
+    }
+  } else {
+    const uint32_t* __restrict__ g_cig = a.cig;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) R.reflen[r] = cigar_ref_len_add(0u, nc[r] > 0 ? __ldg(g_cig + O[r]) : 0u);
 #pragma unroll 1
-  for (uint32_t k = 1; k < nc_max; ++k) {
+    for (uint32_t k = 1; k < nc_max; ++k) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const uint32_t op = k < nc[r] ? cp[O[r] + k] : 0u;
-      R.reflen[r] += cigar_ref_len(op);
+      for (int r = 0; r < 4; ++r) R.reflen[r] = cigar_ref_len_add(R.reflen[r], k < nc[r] ? __ldg(g_cig + O[r] + k) : 0u);
     }
   }
   // long CIGARs: the whole warp reduces one read at a time with 128-bit loads from global memory
@@ -113,8 +154,10 @@ __device__ __forceinline__ PrepReads prep_reduce_staged(const FusedArgs& f, cons
   return R;
 }
 
-// The producer: lane 0 of the last warp.  Chunk c = reads [c*1024, min(n, (c+1)*1024)); the CTA's
-// chunks are blockIdx.x, blockIdx.x + gridDim.x, ...
+// The producer: lane 0 of the last warp.  Chunk c = reads [c*1024, min(n, (c+1)*1024)).  A CTA's first two chunks
+// are blockIdx.x and blockIdx.x + gridDim.x; after that chunks are drawn from a ticket counter (one atomic per
+// chunk, issued two chunks ahead of its use): SMs do not run at the same speed, and with a fixed stride the
+// slowest ones kept the kernel alive for ~2 us (ncu: max - mean of sm__cycles_active) after the others had finished.
 __device__ __forceinline__ void prep_producer(const FusedArgs& f, char* smem, uint64_t* full, uint64_t* empty, PtMeta* meta,
                                               int64_t n_chunks) {
   const ExpandArgs& a = f.e;
@@ -123,17 +166,23 @@ __device__ __forceinline__ void prep_producer(const FusedArgs& f, char* smem, ui
   const uint32_t cig_total = __ldg(g_off + n);
   const uint64_t pol = l2_policy_evict_first();
   const unsigned G = gridDim.x;
-  int64_t c = blockIdx.x;
+  int64_t c = blockIdx.x, cn = (int64_t)blockIdx.x + G;
   uint32_t ob = 0, oe = 0;
   if (c < n_chunks) { ob = __ldg(g_off + c * kPtChunk); oe = __ldg(g_off + min((c + 1) * (int64_t)kPtChunk, n)); }
+  unsigned it = 0;
 #pragma unroll 1
-  for (unsigned it = 0; c < n_chunks; ++it, c += G) {
-    // the op range of the CTA's next chunk: fetched now, needed one iteration from now
-    const int64_t cn = c + G;
+  for (;; ++it) {
+    // the chunk after next (ticket) and the op range of the next chunk: fetched now, needed one iteration from now
+    const int64_t cnn = 2 * (int64_t)G + atomicAdd(&a.pc->ticket, 1u);
     uint32_t nob = 0, noe = 0;
     if (cn < n_chunks) { nob = __ldg(g_off + cn * kPtChunk); noe = __ldg(g_off + min((cn + 1) * (int64_t)kPtChunk, n)); }
     const unsigned s = it % kPtStages, k = it / kPtStages;
-    if (k > 0) mbar_wait(&empty[s], (k - 1) & 1);                  // the consumers have released this stage
+    if (k > 0) mbar_wait_relaxed(&empty[s], (k - 1) & 1);          // the consumers have released this stage
+    if (c >= n_chunks) {                                            // no more chunks: tell the consumers
+      meta[s].chunk = -1; meta[s].a0 = 0; meta[s].in_smem = 0;
+      mbar_arrive(&full[s]);
+      break;
+    }
     char* st = smem + (size_t)s * kPtStageBytes;
     const int64_t r0 = c * kPtChunk;
     const uint32_t nread = (uint32_t)min((int64_t)kPtChunk, n - r0);
@@ -156,7 +205,7 @@ __device__ __forceinline__ void prep_producer(const FusedArgs& f, char* smem, ui
     for (uint32_t r = n16; r < nread; ++r) reinterpret_cast<uint8_t*>(st + kPtOffMapq)[r] = a.mapq[r0 + r];
     reinterpret_cast<uint32_t*>(st + kPtOffOff)[nread] = oe;        // offsets: one entry more than reads
     if (fits) for (uint32_t o = max(a1, a0); o < oe; ++o) reinterpret_cast<uint32_t*>(st + kPtOffCig)[o - a0] = a.cig[o];
-    meta[s].a0 = a0; meta[s].in_smem = fits ? 1u : 0u;
+    meta[s].chunk = c; meta[s].a0 = a0; meta[s].in_smem = fits ? 1u : 0u;
     const uint32_t tx = 2u * (prev + 4u * n4) + 4u * n4 + 2u * n8 + n16 + cig_bytes;
     mbar_arrive_expect_tx(&full[s], tx);
     if (prev + n4) {
@@ -167,7 +216,7 @@ __device__ __forceinline__ void prep_producer(const FusedArgs& f, char* smem, ui
     if (n8) tma_load_1d_hint(st + kPtOffFlag, a.flag + r0, 2u * n8, &full[s], pol);
     if (n16) tma_load_1d_hint(st + kPtOffMapq, a.mapq + r0, n16, &full[s], pol);
     if (cig_bytes) tma_load_1d_hint(st + kPtOffCig, a.cig + a0, cig_bytes, &full[s], pol);
-    ob = nob; oe = noe;
+    c = cn; cn = cnn; ob = nob; oe = noe;
   }
 }
 
@@ -176,6 +225,8 @@ k_fused_prep_tma(const __grid_constant__ FusedArgs f) {
   extern __shared__ __align__(128) char pt_smem[];
   __shared__ __align__(8) uint64_t s_full[kPtStages], s_empty[kPtStages];
   __shared__ PtMeta s_meta[kPtStages];
+  __shared__ uint32_t s_lut[128];
+  if (threadIdx.x < 128) s_lut[threadIdx.x] = f.flag_lut[threadIdx.x];
   pdl_launch_dependents();                                    // k_scan_counts may take free slots as this grid drains
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
@@ -190,14 +241,14 @@ k_fused_prep_tma(const __grid_constant__ FusedArgs f) {
     return;
   }
   PrepWarp W = {0ull, 0u, 0u, 0u, -1, 0u, 0u, 0u};
-  const unsigned G = gridDim.x;
-  unsigned it = 0;
 #pragma unroll 1
-  for (int64_t c = blockIdx.x; c < n_chunks; c += G, ++it) {
+  for (unsigned it = 0;; ++it) {
     const unsigned s = it % kPtStages, k = it / kPtStages;
     mbar_wait(&s_full[s], k & 1);                               // the chunk has landed
     const char* st = pt_smem + (size_t)s * kPtStageBytes;
     const PtMeta m = s_meta[s];
+    if (m.chunk < 0) break;
+    const int64_t c = m.chunk;
     const int64_t i0 = c * kPtChunk + (int64_t)threadIdx.x * kPrepPer;
     // the read before this warp's first one (lane 0 only): sortedness and tile border across warps
     int32_t pvT = -1, pvP = -1;
@@ -205,7 +256,7 @@ k_fused_prep_tma(const __grid_constant__ FusedArgs f) {
       pvT = reinterpret_cast<const int32_t*>(st + kPtOffTid + 16)[(int)threadIdx.x * kPrepPer - 1];
       pvP = reinterpret_cast<const int32_t*>(st + kPtOffPos + 16)[(int)threadIdx.x * kPrepPer - 1];
     }
-    const PrepReads R = prep_reduce_staged(f, st, m, i0, lane);
+    const PrepReads R = m.in_smem ? prep_reduce_staged<true>(f, st, m, i0, lane, s_lut) : prep_reduce_staged<false>(f, st, m, i0, lane, s_lut);
     __syncwarp();
     if (lane == 0) mbar_arrive(&s_empty[s]);                    // this warp is done with the stage
     prep_emit(f, i0, R, pvT, pvP, lane, W);

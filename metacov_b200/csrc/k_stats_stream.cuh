@@ -89,7 +89,7 @@ k_stats_stream(const __grid_constant__ SsArgs a) {
     unsigned it = 0;
     auto publish = [&](const SsDesc& d, const int32_t* src, uint32_t bytes) {
       const unsigned s = it % kSsStages, k = it / kSsStages;
-      if (k > 0) mbar_wait(&s_empty[s], (k - 1) & 1);
+      if (k > 0) mbar_wait_relaxed(&s_empty[s], (k - 1) & 1);
       s_desc[s] = d;
       if (bytes) {
         mbar_arrive_expect_tx(&s_full[s], bytes);

@@ -32,10 +32,29 @@ namespace mcov {
 #ifndef MCOV_TT_CTAS
 #define MCOV_TT_CTAS 8
 #endif
+#ifndef MCOV_TT_BLOCKED
+#define MCOV_TT_BLOCKED 0
+#endif
 constexpr int kTtStages = MCOV_TT_STAGES;
+// Counter layout.  BLOCKED: a thread owns 16 CONSECUTIVE slots (four vectors), so the block scan needs one warp
+// scan per thread instead of one per vector (4 x 10 shuffle/add instructions -> 10).  Consecutive lanes then read
+// vectors 64 bytes apart, which would be a 4-way bank conflict; the counters are therefore stored with the
+// vector index XOR-swizzled by bits 3..5 (slot ^ ((slot >> 3) & 0x1C)), which makes those reads conflict-free and
+// costs the scatter two instructions per atomic.  MEASURED on B200 (C2): 88 us against 64 us for the warp-striped
+// layout -- the four 128-bit stores of a thread then lie 64 bytes apart across lanes, every store instruction
+// fills only half of each 32-byte sector it touches, and that costs far more than the 30 instructions saved.
+// Kept as a compile-time variant (it would need a swizzled TMA tensor store to pay off); default off.
+constexpr bool kTtBlocked = MCOV_TT_BLOCKED != 0;
+__device__ __forceinline__ uint32_t tt_phys(uint32_t slot) { return kTtBlocked ? (slot ^ ((slot >> 3) & 0x1Cu)) : slot; }
 constexpr int kTtStageRecs = MCOV_TT_STAGE_RECS;             // records staged per tile (walk-back candidates + own)
 constexpr int kTtThreads = kFusedThreads + 32;               // 4 consumer warps + the producer warp
 static_assert(kTtStageRecs % 4 == 0, "stage = whole 16-byte vectors");
+
+// logical vector (four slots) number j of a thread, and where the counters of that vector live
+__device__ __forceinline__ int tt_vec(int warp, int lane, int j) {
+  return kTtBlocked ? (warp * 128 + lane * kTileVec + j) : ((warp * kTileVec + j) * 32 + lane);
+}
+__device__ __forceinline__ int tt_vec_phys(int v) { return kTtBlocked ? (v ^ ((v >> 3) & 7)) : v; }
 
 struct TtMeta {
   int64_t tile;           // < 0: no more tiles
@@ -43,24 +62,28 @@ struct TtMeta {
   uint32_t jb, nst;       // records [jb, jb + nst) are in the stage
 };
 
+// ALL_STAGED: every record the tile looks at is in the stage (the normal case, decided once per tile)
+template <bool ALL_STAGED>
 __device__ __forceinline__ uint32_t tt_rec(const FusedArgs& f, const TtMeta& m, const uint32_t* s_rec, uint32_t j) {
   const uint32_t k = j - m.jb;
+  if (ALL_STAGED) return s_rec[k];
   return k < m.nst ? s_rec[k] : __ldg(f.rec + j);               // dense tiles: what does not fit the stage, from global
 }
 
 // scatter of one tile's records into the counters.  WHAT: 0 = packed starts|ends, 1 = starts only, 2 = ends only
-template <int WHAT>
+template <int WHAT, bool ALL_STAGED>
 __device__ __forceinline__ int tt_scatter(const FusedArgs& f, const TtMeta& m, const uint32_t* s_rec, int* s_cnt, uint32_t reach,
                                           bool has_far) {
   const int t = threadIdx.x;
+#pragma unroll 2
   for (uint32_t j = m.r0 + t; j < m.r1; j += kFusedThreads) {
-    const uint32_t r = tt_rec(f, m, s_rec, j);
+    const uint32_t r = tt_rec<ALL_STAGED>(f, m, s_rec, j);
     const uint32_t code = r >> kTileShift;
     if (code) {
       const uint32_t local = r & (kTile - 1);
-      if (WHAT != 2) atomicAdd(&s_cnt[local], 1);
+      if (WHAT != 2) atomicAdd(&s_cnt[tt_phys(local)], 1);
       const uint32_t el = local + code;
-      if (WHAT != 1 && el < (uint32_t)kTile) atomicAdd(&s_cnt[el], WHAT == 0 ? 0x10000 : 1);
+      if (WHAT != 1 && el < (uint32_t)kTile) atomicAdd(&s_cnt[tt_phys(el)], WHAT == 0 ? 0x10000 : 1);
     }
   }
   // near reads that started before the tile and end inside it (see k_fused_tile): walk back while the
@@ -68,15 +91,15 @@ __device__ __forceinline__ int tt_scatter(const FusedArgs& f, const TtMeta& m, c
   int open = 0;
   if (WHAT != 1) {
     for (int64_t j = (int64_t)m.r0 - 1 - t; j >= (int64_t)m.jmin; j -= kFusedThreads) {
-      const uint32_t r = tt_rec(f, m, s_rec, (uint32_t)j);
+      const uint32_t r = tt_rec<ALL_STAGED>(f, m, s_rec, (uint32_t)j);
       const uint32_t d = (uint32_t)kTile - (r & (kTile - 1));
       if (d > reach) break;
       const uint32_t code = r >> kTileShift;
-      if (code >= d && code <= kNearSpan) { atomicAdd(&s_cnt[code - d], WHAT == 0 ? 0x10000 : 1); ++open; }
+      if (code >= d && code <= kNearSpan) { atomicAdd(&s_cnt[tt_phys(code - d)], WHAT == 0 ? 0x10000 : 1); ++open; }
     }
     if (has_far) {
       const uint32_t k0 = m.tile > 0 ? f.tile_cnt[m.tile - 1] : 0u, k1 = f.tile_cnt[m.tile];
-      for (uint32_t k = k0 + t; k < k1; k += kFusedThreads) atomicAdd(&s_cnt[f.far_sorted[k] & (kTile - 1)], WHAT == 0 ? 0x10000 : 1);
+      for (uint32_t k = k0 + t; k < k1; k += kFusedThreads) atomicAdd(&s_cnt[tt_phys(f.far_sorted[k] & (kTile - 1))], WHAT == 0 ? 0x10000 : 1);
     }
   }
   return open;
@@ -132,7 +155,7 @@ k_fused_tile_tma(const __grid_constant__ FusedArgs f) {
       resolve(tk_nxt, m_nxt);
       if (m_cur.tile != -1) {
         const unsigned s = it % kTtStages, k = it / kTtStages;
-        if (k > 0) mbar_wait(&s_empty[s], (k - 1) & 1);
+        if (k > 0) mbar_wait_relaxed(&s_empty[s], (k - 1) & 1);
         if (m_cur.tile >= 0) {
           m_cur.jb = m_cur.jmin & ~3u;
           const uint32_t want = ((m_cur.r1 + 3u) & ~3u) - m_cur.jb;        // (the record buffer is padded past n)
@@ -172,14 +195,15 @@ k_fused_tile_tma(const __grid_constant__ FusedArgs f) {
     const bool packed = touching < 65536u;
     int4 st[kTileVec], en[kTileVec];
     if (packed) {
-      int open = tt_scatter<0>(f, m, rec, s_cnt, reach, has_far);
+      int open = (m.r1 - m.jb <= m.nst) ? tt_scatter<0, true>(f, m, rec, s_cnt, reach, has_far)
+                                        : tt_scatter<0, false>(f, m, rec, s_cnt, reach, has_far);
       open = __reduce_add_sync(0xffffffffu, open);
       if (lane == 0) { if (open) atomicAdd(&s_open[par], open); mbar_arrive(&s_empty[s]); }   // stage free: the records have been read
       named_bar_sync<1, kFusedThreads>();
       const int4* vs = reinterpret_cast<const int4*>(s_cnt);
 #pragma unroll
       for (int j = 0; j < kTileVec; ++j) {
-        const int idx = (warp * kTileVec + j) * 32 + lane;
+        const int idx = tt_vec_phys(tt_vec(warp, lane, j));
         const int4 c = vs[idx];
         reinterpret_cast<int4*>(s_cnt)[idx] = make_int4(0, 0, 0, 0);      // cleared by the thread that read it
         en[j] = make_int4((int)((unsigned)c.x >> 16), (int)((unsigned)c.y >> 16), (int)((unsigned)c.z >> 16), (int)((unsigned)c.w >> 16));
@@ -187,28 +211,28 @@ k_fused_tile_tma(const __grid_constant__ FusedArgs f) {
       }
     } else {
       // dense tile: starts and ends counted in two 32-bit passes over the same counters
-      tt_scatter<1>(f, m, rec, s_cnt, reach, has_far);
+      tt_scatter<1, false>(f, m, rec, s_cnt, reach, has_far);
       named_bar_sync<1, kFusedThreads>();
 #pragma unroll
       for (int j = 0; j < kTileVec; ++j) {
-        const int idx = (warp * kTileVec + j) * 32 + lane;
+        const int idx = tt_vec_phys(tt_vec(warp, lane, j));
         st[j] = reinterpret_cast<const int4*>(s_cnt)[idx];
         reinterpret_cast<int4*>(s_cnt)[idx] = make_int4(0, 0, 0, 0);
       }
       named_bar_sync<1, kFusedThreads>();
-      int open = tt_scatter<2>(f, m, rec, s_cnt, reach, has_far);
+      int open = tt_scatter<2, false>(f, m, rec, s_cnt, reach, has_far);
       open = __reduce_add_sync(0xffffffffu, open);
       if (lane == 0) { if (open) atomicAdd(&s_open[par], open); mbar_arrive(&s_empty[s]); }
       named_bar_sync<1, kFusedThreads>();
 #pragma unroll
       for (int j = 0; j < kTileVec; ++j) {
-        const int idx = (warp * kTileVec + j) * 32 + lane;
+        const int idx = tt_vec_phys(tt_vec(warp, lane, j));
         en[j] = reinterpret_cast<const int4*>(s_cnt)[idx];
         reinterpret_cast<int4*>(s_cnt)[idx] = make_int4(0, 0, 0, 0);
       }
     }
-    // block scan of (starts - ends), warp-striped.  cap[p] = depth[p-1] + starts[p] is folded into one value per
-    // vector, relative to the vector's incoming depth.
+    // block scan of (starts - ends).  cap[p] = depth[p-1] + starts[p] is folded into one value per vector, relative
+    // to the vector's incoming depth.  run[j] = exclusive offset of vector j inside the warp's 512 slots.
     int4 v[kTileVec];
     int run[kTileVec], capv[kTileVec];
 #pragma unroll
@@ -221,17 +245,31 @@ k_fused_tile_tma(const __grid_constant__ FusedArgs f) {
       run[j] = v[j].w;
     }
     int acc = 0;
-#pragma unroll
-    for (int j = 0; j < kTileVec; ++j) {
-      int x = run[j];
+    if (kTtBlocked) {
+      // the thread's four vectors are consecutive: one warp scan over the threads' totals
+      const int t0 = run[0], t1 = t0 + run[1], t2 = t1 + run[2], t3 = t2 + run[3];
+      int x = t3;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int y = __shfl_up_sync(0xffffffffu, x, o);
         if (lane >= o) x += y;
       }
-      const int total = __shfl_sync(0xffffffffu, x, 31);
-      run[j] = x - run[j] + acc;
-      acc += total;
+      acc = __shfl_sync(0xffffffffu, x, 31);
+      const int ex = x - t3;
+      run[0] = ex; run[1] = ex + t0; run[2] = ex + t1; run[3] = ex + t2;
+    } else {
+#pragma unroll
+      for (int j = 0; j < kTileVec; ++j) {
+        int x = run[j];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int y = __shfl_up_sync(0xffffffffu, x, o);
+          if (lane >= o) x += y;
+        }
+        const int total = __shfl_sync(0xffffffffu, x, 31);
+        run[j] = x - run[j] + acc;
+        acc += total;
+      }
     }
     if (lane == 31) s_warp[warp] = acc;
     // the other s_open buffer: last read after the previous tile's second barrier (every thread has passed this
@@ -248,7 +286,7 @@ k_fused_tile_tma(const __grid_constant__ FusedArgs f) {
     int cap_t = 0;
 #pragma unroll
     for (int j = 0; j < kTileVec; ++j) {
-      const int idx = (warp * kTileVec + j) * 32 + lane;
+      const int idx = tt_vec(warp, lane, j);
       const int o = off + run[j];
       cap_t = max(cap_t, o + capv[j]);
       v[j].x += o; v[j].y += o; v[j].z += o; v[j].w += o;

@@ -69,6 +69,19 @@ cudaError_t launch_pdl(bool allow, void (*kern)(KArgs...), dim3 grid, dim3 block
 
 PassCounters* pc_of(mcov_ctx* ctx) { return ctx->d_pc.as<PassCounters>(); }
 
+// The flag tests of the read filter (pysam __advance_samtools + htslib's UNMAP drop) as one
+// bit per flag value below 4096; the prep kernel looks reads up instead of evaluating the masks.
+void build_flag_lut(mcov_ctx* ctx) {
+  const mcov_filter& f = ctx->filt;
+  for (int w = 0; w < 128; ++w) ctx->flag_lut[w] = 0;
+  for (uint32_t F = 0; F < 4096; ++F) {
+    bool p = !(F & ((uint32_t)f.flag_filter | 0x4u));
+    if (f.flag_require && !(F & f.flag_require)) p = false;
+    if (f.ignore_orphans && (F & 0x1u) && !(F & 0x2u)) p = false;
+    if (p) ctx->flag_lut[F >> 5] |= 1u << (F & 31u);
+  }
+}
+
 int ensure_depth(mcov_ctx* ctx) {
   if (ctx->n_contigs <= 0) return fail(ctx, MCOV_ERR_STATE, "mcov_set_contigs has not been called");
   if (!ctx->depth_bound) {
@@ -135,7 +148,8 @@ int finish_stage(mcov_ctx* ctx, ReadStage* s) {
 }
 
 // Fused depth path for coordinate-sorted reads (k_fused.cuh).  `a` holds device pointers.
-int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a) {
+// tile_lo < 0: the pass writes the whole slot space; else only the tiles [tile_lo, tile_hi) (one batch of a streamed file).
+int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a, int64_t tile_lo = -1, int64_t tile_hi = -1) {
   const int64_t n = a.n;
   if (n >= (int64_t)0xFFFFFFF0ll) return fail(ctx, MCOV_ERR_RANGE, "mcov_depth_sorted: a batch holds at most 2^32-16 reads (read indices are 32-bit); split it or use mcov_begin/push/finalize");
   const int64_t n_tiles = (ctx->n_slots + kTile - 1) / kTile;
@@ -160,7 +174,8 @@ int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a) {
   f.rec = ctx->d_start_slot.as<uint32_t>();
   f.n_slots = ctx->n_slots;
   f.n_tiles = n_tiles;
-  f.tile_lo = 0; f.tile_hi = n_tiles;
+  f.tile_lo = 0; f.tile_hi = n_tiles; f.streaming = 0;
+  if (tile_lo >= 0) { f.tile_lo = tile_lo; f.tile_hi = std::min(tile_hi, n_tiles); f.streaming = 1; }
   f.far_end = ctx->d_far_list.as<int64_t>();
   f.far_cap = far_cap;
   f.tile_agg = reinterpret_cast<int32_t*>(z + o_agg);
@@ -175,6 +190,7 @@ int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a) {
   f.depth = ctx->depth;
   f.tile_cap = reinterpret_cast<int32_t*>(z + o_cap);
   f.max_depth = ctx->filt.max_depth;
+  std::memcpy(f.flag_lut, ctx->flag_lut, sizeof(f.flag_lut));
   auto al = [](const void* p, uintptr_t m) { return (reinterpret_cast<uintptr_t>(p) & (m - 1)) == 0; };
   const bool off64 = a.cig_off64 != nullptr;
   f.vec_ok = (n > 0 && al(a.tid, 16) && al(a.pos, 16) && al(off64 ? (const void*)a.cig_off64 : (const void*)a.cig_off, 16) &&
@@ -187,8 +203,6 @@ int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a) {
     const bool tma = !off64 && !no_tma && al(a.tid, 16) && al(a.pos, 16) && al(a.cig_off, 16) && al(a.flag, 16) &&
                      al(a.mapq, 16) && al(a.cig, 16);
     if (tma) {
-      static bool attr_set = false;
-      if (!attr_set) { CU(cudaFuncSetAttribute(k_fused_prep_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kPtSmemBytes)); attr_set = true; }
       const int64_t n_chunks = (n + kPtChunk - 1) / kPtChunk;
       const unsigned grid = (unsigned)std::min<int64_t>(n_chunks, (int64_t)ctx->n_sm * MCOV_PREP_CTAS);
       MCOV_LAUNCH(ctx, kKFusedPrep, (k_fused_prep_tma<<<grid, kPtThreads, kPtSmemBytes, s>>>(f)));
@@ -207,7 +221,9 @@ int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a) {
   ctx->fused_blob.assign(reinterpret_cast<const unsigned char*>(&f), reinterpret_cast<const unsigned char*>(&f) + sizeof(f));
   {
     static const bool tile_legacy = std::getenv("MCOV_TILE_LEGACY") != nullptr;     // tuning hook
-    if (tile_legacy) {
+    if (f.tile_hi <= f.tile_lo) {
+      // (a streamed batch that does not reach a new tile: everything it holds is carried into the next one)
+    } else if (tile_legacy && !f.streaming) {
       const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)ctx->n_sm * MCOV_TILE_MIN_CTAS);   // persistent
       MCOV_LAUNCH(ctx, kKFusedTile, CU(launch_pdl(pdl, k_fused_tile, dim3(grid), dim3(kFusedThreads), 0, s, f)));
     } else {
@@ -239,7 +255,38 @@ int fused_verdict(mcov_ctx* ctx, const PassCounters& h) {
     ctx->state = kIdle;
     return fail(ctx, MCOV_ERR_RANGE, "mcov_depth_sorted: too many long-span reads for the bucket list; use mcov_begin/push/finalize");
   }
+  if (h.far_overflow) {
+    ctx->state = kIdle;
+    return fail(ctx, MCOV_ERR_RANGE, "mcov_stream_push: a batch held too many long-span reads for the bucket list; use mcov_begin/push/finalize");
+  }
+  if (h.cap_unreplayed) {
+    ctx->state = kIdle;
+    return fail(ctx, MCOV_ERR_STATE, "mcov_stream_push: htslib's max_depth cap fires in this file (a pile deeper than max_depth); the exact replay needs "
+                                     "the contig's reads in one batch -- run the file through mcov_depth_sorted, or raise max_depth");
+  }
   ctx->cap_contigs = (int32_t)h.cap_contigs;        // replayed by k_cap_replay right after the tile kernel
+  return MCOV_OK;
+}
+
+// Every kernel of a pass asks for the same shared-memory carve-out (the maximum): consecutive kernels with
+// different L1 / shared-memory splits make the SMs reconfigure between launches, which costs a few
+// microseconds per kernel on a step of ~180 us.  Also opts the TMA kernels into their dynamic shared memory.
+int configure_kernels(mcov_ctx* ctx) {
+  const int mx = (int)cudaSharedmemCarveoutMaxShared;           // (function attributes are per device: set for every context)
+  CU(cudaFuncSetAttribute(k_fused_prep_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kPtSmemBytes));
+  CU(cudaFuncSetAttribute(k_stats_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, kSsSmemBytes));
+  CU(cudaFuncSetAttribute(k_fused_prep_tma, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  CU(cudaFuncSetAttribute(k_fused_prep<false>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  CU(cudaFuncSetAttribute(k_scan_inplace<false>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  CU(cudaFuncSetAttribute(k_far_scatter, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  CU(cudaFuncSetAttribute(k_fused_tile_tma, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  CU(cudaFuncSetAttribute(k_fused_tile, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  CU(cudaFuncSetAttribute(k_cap_replay, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  CU(cudaFuncSetAttribute(k_stats_stream, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  CU(cudaFuncSetAttribute(k_stats_split_finish, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  CU(cudaFuncSetAttribute(k_region_stats, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  CU(cudaFuncSetAttribute(k_region_stats_warp, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  CU(cudaFuncSetAttribute(k_region_stats_small, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
   return MCOV_OK;
 }
 
@@ -282,6 +329,8 @@ int mcov_create(mcov_ctx** out, int device, void* stream) {
             cudaEventCreateWithFlags(&ctx->stage[1].consumed, cudaEventDisableTiming) == cudaSuccess;
   if (!ok) { mcov_destroy(ctx); return MCOV_ERR_CUDA; }
   mcov_default_filter(&ctx->filt);
+  build_flag_lut(ctx);
+  if (configure_kernels(ctx) != MCOV_OK) { mcov_destroy(ctx); return MCOV_ERR_CUDA; }
   *out = ctx;
   return MCOV_OK;
 }
@@ -300,7 +349,7 @@ void mcov_destroy(mcov_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->d_len, &ctx->d_off, &ctx->depth_own, &ctx->d_pc, &ctx->d_status, &ctx->d_end_slot,
                     &ctx->d_start_slot, &ctx->d_far_list, &ctx->d_tile_cnt, &ctx->d_tile_off, &ctx->d_far_sorted,
                     &ctx->d_tasks, &ctx->d_rlen, &ctx->d_rchunks, &ctx->d_rhist, &ctx->d_pool, &ctx->d_done,
-                    &ctx->d_ss_pieces, &ctx->d_ss_cta, &ctx->d_ss_split, &ctx->d_ss_pool,
+                    &ctx->d_stream_acc, &ctx->d_ss_pieces, &ctx->d_ss_cta, &ctx->d_ss_split, &ctx->d_ss_pool,
                     &ctx->d_out, &ctx->d_win_slot, &ctx->d_win_n, &ctx->d_win_out, &ctx->d_htasks, &ctx->d_tile_heavy, &ctx->d_run_tasks, &ctx->d_run_counts, &ctx->d_run_out};
   for (DevBuf* b : bufs) b->release();
   ctx->bam.release();
@@ -365,6 +414,7 @@ int mcov_bind_depth(mcov_ctx* ctx, int32_t* dev, int64_t n_slots) {
 int mcov_set_filter(mcov_ctx* ctx, const mcov_filter* f) {
   if (!ctx || !f) return fail(ctx, MCOV_ERR_ARG, "mcov_set_filter: null argument");
   ctx->filt = *f;
+  build_flag_lut(ctx);
   return MCOV_OK;
 }
 
@@ -573,6 +623,109 @@ int mcov_depth_sorted_async(mcov_ctx* ctx, int64_t n, const int32_t* tid, const 
   return depth_sorted_impl(ctx, n, tid, pos, flag, mapq, cig_off, false, cig, mem_kind, false);
 }
 
+// ---- streaming a coordinate-sorted file in batches ------------------------------------------------------------
+int mcov_stream_begin(mcov_ctx* ctx) {
+  if (!ctx) return MCOV_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  int rc = ensure_depth(ctx);
+  if (rc) return rc;
+  CU(ctx->d_stream_acc.ensure(sizeof(StreamAcc) + 16));
+  CU(cudaMemsetAsync(ctx->d_stream_acc.p, 0, sizeof(StreamAcc) + 16, ctx->stream));
+  ctx->stream_tile_lo = 0;
+  ctx->stream_reads = 0;
+  ctx->verdict_pending = false;
+  ctx->state = kStreaming;
+  return MCOV_OK;
+}
+
+int mcov_stream_resend_point(const mcov_ctx* ctx, int32_t last_tid, int32_t last_pos, int32_t* resend_tid, int32_t* resend_pos) {
+  if (!ctx || !resend_tid || !resend_pos || ctx->n_contigs <= 0) return MCOV_ERR_ARG;
+  // tile of the last read's start slot (reads without a valid contig sort after every slot)
+  int64_t slot = ctx->n_slots;
+  if (last_tid >= 0 && last_tid < ctx->n_contigs)
+    slot = ctx->off[last_tid] + std::min<int64_t>(std::max<int64_t>(last_pos, 0), ctx->len[last_tid]);
+  const int64_t tb = std::min<int64_t>(slot >> kTileShift, (ctx->n_slots + kTile - 1) / kTile);
+  // everything that starts at or after the first slot of tile tb-1, or reaches past it, is needed again
+  const int64_t rs = std::max<int64_t>(tb - 1, 0) << kTileShift;
+  if (rs >= ctx->n_slots) { *resend_tid = ctx->n_contigs; *resend_pos = 0; return MCOV_OK; }
+  const int32_t c = (int32_t)(std::upper_bound(ctx->off.begin(), ctx->off.begin() + ctx->n_contigs, rs) - ctx->off.begin()) - 1;
+  *resend_tid = c;
+  *resend_pos = (int32_t)std::min<int64_t>(rs - ctx->off[c], ctx->len[c]);
+  return MCOV_OK;
+}
+
+int mcov_stream_push(mcov_ctx* ctx, int64_t n, int64_t n_carry, const int32_t* tid, const int32_t* pos, const uint16_t* flag,
+                     const uint8_t* mapq, const uint32_t* cig_off, const uint32_t* cig, int mem_kind, int last,
+                     int32_t* resend_tid, int32_t* resend_pos) {
+  if (!ctx) return MCOV_ERR_ARG;
+  if (ctx->state != kStreaming) return fail(ctx, MCOV_ERR_STATE, "mcov_stream_push: call mcov_stream_begin first");
+  if (n < 0 || n_carry < 0 || n_carry > n) return fail(ctx, MCOV_ERR_ARG, "mcov_stream_push: need 0 <= n_carry <= n");
+  if (n > 0 && (!tid || !pos || !flag || !mapq || !cig_off)) return fail(ctx, MCOV_ERR_ARG, "mcov_stream_push: null array");
+  CU(cudaSetDevice(ctx->device));
+  const int64_t n_tiles = (ctx->n_slots + kTile - 1) / kTile;
+  // the batch's last read decides how far the depth becomes final
+  int32_t lt = -1, lp = 0;
+  if (n > 0) {
+    if (mem_kind == MCOV_MEM_HOST) { lt = tid[n - 1]; lp = pos[n - 1]; }
+    else {
+      CU(cudaMemcpyAsync(&lt, tid + n - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaMemcpyAsync(&lp, pos + n - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+    }
+  }
+  int64_t tile_hi = n_tiles;
+  if (!last) {
+    if (n == 0) tile_hi = ctx->stream_tile_lo;
+    else {
+      int64_t slot = ctx->n_slots;
+      if (lt >= 0 && lt < ctx->n_contigs) slot = ctx->off[lt] + std::min<int64_t>(std::max<int64_t>(lp, 0), ctx->len[lt]);
+      tile_hi = std::min<int64_t>(slot >> kTileShift, n_tiles);
+    }
+    if (tile_hi < ctx->stream_tile_lo) {
+      ctx->state = kIdle;
+      return fail(ctx, MCOV_ERR_UNSORTED, "mcov_stream_push: the batch ends before the previous one (batches must follow the sorted order)");
+    }
+  }
+  if (resend_tid && resend_pos) {
+    if (n > 0) mcov_stream_resend_point(ctx, lt, lp, resend_tid, resend_pos);
+    else { *resend_tid = -1; *resend_pos = 0; }                  // (an empty batch changes nothing: keep sending what was being sent)
+  }
+  CU(cudaMemsetAsync(ctx->d_pc.p, 0, sizeof(PassCounters), ctx->stream));
+  ExpandArgs a;
+  ReadStage* st = nullptr;
+  int rc;
+  if (n > 0) {
+    rc = stage_reads(ctx, n, tid, pos, flag, mapq, cig_off, false, cig, mem_kind, a, &st);
+    if (rc) return rc;
+  } else {
+    std::memset(&a, 0, sizeof(a));
+    a.pc = pc_of(ctx);
+  }
+  rc = fused_depth_sorted(ctx, a, ctx->stream_tile_lo, tile_hi);
+  if (rc) return rc;
+  // pass counters of the stream: this batch minus its carried reads, added to the running totals
+  unsigned long long* carry = reinterpret_cast<unsigned long long*>(ctx->d_stream_acc.as<char>() + sizeof(StreamAcc));
+  CU(cudaMemsetAsync(carry, 0, 16, ctx->stream));
+  FusedArgs f;
+  std::memcpy(&f, ctx->fused_blob.data(), sizeof(f));
+  if (n_carry > 0) {
+    MCOV_LAUNCH(ctx, kKStreamAcc, (k_carry_counts<<<grid_for(ctx, n_carry, 256, 4), 256, 0, ctx->stream>>>(f, n_carry, carry)));
+    CU(cudaGetLastError());
+  }
+  MCOV_LAUNCH(ctx, kKStreamAcc, (k_stream_accumulate<<<1, 1, 0, ctx->stream>>>(pc_of(ctx), ctx->d_stream_acc.as<StreamAcc>(), carry, f.far_cap)));
+  CU(cudaGetLastError());
+  ctx->stream_reads += n - n_carry;
+  ctx->n_reads_pushed = ctx->stream_reads;
+  ctx->stream_tile_lo = tile_hi;
+  rc = finish_stage(ctx, st);
+  if (rc) return rc;
+  if (last) {
+    ctx->state = kDepthReady;
+    ctx->verdict_pending = true;                                 // delivered by the next synchronising call, like mcov_depth_sorted_async
+  }
+  return MCOV_OK;
+}
+
 int mcov_depth_sorted_packed(mcov_ctx* ctx, int64_t n, const int64_t* contig_read_start, const int32_t* pos,
                              const uint16_t* flag, const uint8_t* mapq, const uint16_t* n_cigar, const uint32_t* cig,
                              int64_t n_cig_total, int wait) {
@@ -668,7 +821,7 @@ static const char* kKernelNames[kKernelCount] = {
     "k_init_region_stats", "k_region_stats", "k_window_sums", "k_isize_hist", "k_group_count", "k_sorted_stats",
     "memset_depth", "k_region_stats_small", "k_cap_replay", "k_unpack_reads", "k_kmer_hist", "k_region_stats_warp",
     "k_exp_prep", "k_exp_entries", "k_exp_region", "k_exp_revsum", "k_region_hist", "k_hist_finish", "k_run_count", "k_run_offsets", "k_run_write", "k_run_ends",
-    "k_bgzf_inflate", "k_bam_guess", "k_bam_walk_count", "k_bam_walk_write", "k_delta_unpack"};
+    "k_bgzf_inflate", "k_bam_guess", "k_bam_walk_count", "k_bam_walk_write", "k_delta_unpack", "k_stream_accumulate"};
 
 int mcov_copy_to_host(mcov_ctx* ctx, const void* dev, void* host, int64_t n_bytes) {
   if (!ctx) return MCOV_ERR_ARG;
@@ -875,8 +1028,6 @@ static int stats_launch(mcov_ctx* ctx, int64_t g, const int32_t* tid, const int3
     const size_t done_bytes = (size_t)rp.n_multi * sizeof(RegionScratch);
     static const bool stats_legacy = std::getenv("MCOV_STATS_LEGACY") != nullptr;     // tuning hook
     if (rp.ss_grid > 0 && !stats_legacy) {
-      static bool attr_set = false;
-      if (!attr_set) { CU(cudaFuncSetAttribute(k_stats_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, kSsSmemBytes)); attr_set = true; }
       SsArgs a;
       int32_t* d_rlen = ctx->d_rlen.as<int32_t>();
       a.depth = ctx->depth; a.pieces = ctx->d_ss_pieces.as<SsPiece>(); a.cta_piece_start = ctx->d_ss_cta.as<int32_t>();

@@ -162,6 +162,28 @@ class CoverageEngine:
         fn = lib.mcov_depth_sorted if wait else lib.mcov_depth_sorted_async
         self._check(fn(self._ctx, n, *[_capi.ptr(x) for x in b], _mem_kind(b)))
 
+    # -- streaming: successive batches of a coordinate-sorted file -------------
+    def stream_begin(self):
+        """Start a streamed pass (mcov_stream_begin)."""
+        self._check(lib.mcov_stream_begin(self._ctx))
+
+    def stream_push(self, batch, n_carry=0, last=False):
+        """Add the next batch (file order) of a streamed pass; the batch begins with ``n_carry`` reads
+        re-sent from earlier batches (see mcov_stream_push).  Returns the resend point (tid, pos): the
+        next batch must begin with every earlier read that starts at or after it or reaches past it."""
+        b = _canon(batch)
+        if _is_wide(b):
+            raise ValueError("stream_push takes 32-bit CIGAR offsets (a batch is far below 2^32 ops)")
+        rt, rp = C.c_int32(-1), C.c_int32(0)
+        self._check(lib.mcov_stream_push(self._ctx, len(b.tid), int(n_carry), *[_capi.ptr(x) for x in b], _mem_kind(b),
+                                         1 if last else 0, C.byref(rt), C.byref(rp)))
+        return rt.value, rp.value
+
+    def stream_resend_point(self, last_tid, last_pos):
+        rt, rp = C.c_int32(-1), C.c_int32(0)
+        self._check(lib.mcov_stream_resend_point(self._ctx, int(last_tid), int(last_pos), C.byref(rt), C.byref(rp)))
+        return rt.value, rp.value
+
     def depth_sorted_packed(self, packed, wait=True):
         """Fused path from the compact host transport (see ``pack_batch``)."""
         self._check(lib.mcov_depth_sorted_packed(
