@@ -143,6 +143,9 @@ k_fused_tile_tma(const __grid_constant__ FusedArgs f) {
       }
       m.r0 = f.tile_first[T]; m.r1 = f.tile_first[T + 1];
       m.jmin = T > 0 ? f.tile_first[T - 1] : 0u;
+      // unsorted input (the pass is rejected by the verdict) leaves tile_first non-monotone: such a tile is treated
+      // as empty, so that no copy or index is formed from an inverted range
+      if (!(m.jmin <= m.r0 && m.r0 <= m.r1)) m.r0 = m.r1 = m.jmin = 0u;
       m.tile = (tk >= n_heavy && n_heavy != 0 && m.r1 - m.r0 >= f.heavy_min) ? -1 : T;   // a heavy tile met again in position order
     };
     TtMeta m_cur, m_nxt;
