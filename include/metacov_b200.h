@@ -435,6 +435,44 @@ const uint64_t* mcov_bam_name_hash(const mcov_bam* b);
  * 123; first base most significant, A0 C1 G2 T3), -1 when shorter or not ACGT.  k_len <= 15. */
 int  mcov_bam_qas_kmer(const mcov_bam* b, int32_t k_len, int32_t* out);
 
+/* ---- streaming host reader: a BAM read, inflated and parsed in batches ------
+ * Replaces the record loop of reference metacov/scan.pyx:653-667 (`cnext()` over
+ * pysam's IteratorRowAll) for the coverage path without ever holding the file:
+ * mcov_bam_stream_next decodes the next `batch_reads` records (BGZF blocks inflated on
+ * n_threads host threads, 0 = all) into PINNED SoA buffers owned by the stream (two
+ * sets, so batch k can still be copied to the GPU while batch k+1 is decoded; a
+ * batch's arrays stay valid until the second call after the one that returned them)
+ * and puts in front of them the reads of the earlier batches that mcov_stream_push
+ * asked to see again: pass the resend point it returned (resend_tid < 0 on the first
+ * call).  Returns 1 with *out filled, 0 after the batch flagged `last`, or a negative
+ * mcov_status (mcov_bam_stream_error has the text). */
+typedef struct mcov_bam_stream mcov_bam_stream;
+typedef struct mcov_bam_batch {
+  int64_t n;              /* reads in the batch, carried ones included        */
+  int64_t n_carry;        /* leading reads repeated from earlier batches       */
+  int64_t n_cigar;        /* CIGAR ops of the batch                            */
+  int32_t last;           /* 1: the file ends with this batch                  */
+  int32_t reserved;
+  const int32_t*  tid;
+  const int32_t*  pos;
+  const uint16_t* flag;
+  const uint8_t*  mapq;
+  const int32_t*  l_seq;
+  const int32_t*  isize;
+  const int32_t*  reflen; /* reference length of each read (sum of M D N = X)  */
+  const uint32_t* cig_off;   /* n + 1 */
+  const uint32_t* cig;
+} mcov_bam_batch;
+int  mcov_bam_stream_open(mcov_bam_stream** out, const char* path, int64_t batch_reads, int n_threads, char* err, int errlen);
+void mcov_bam_stream_close(mcov_bam_stream* s);
+int32_t mcov_bam_stream_n_ref(const mcov_bam_stream* s);
+const char* mcov_bam_stream_ref_name(const mcov_bam_stream* s, int32_t tid);
+int32_t mcov_bam_stream_ref_len(const mcov_bam_stream* s, int32_t tid);
+const char* mcov_bam_stream_header_text(const mcov_bam_stream* s);
+const char* mcov_bam_stream_error(const mcov_bam_stream* s);
+int  mcov_bam_stream_next(mcov_bam_stream* s, int32_t resend_tid, int32_t resend_pos, mcov_bam_batch* out);
+int64_t mcov_bam_stream_records(const mcov_bam_stream* s);   /* distinct records handed out so far */
+
 /* ---- synthetic workloads (bench / test support; include/mcov_synth.h) ---- */
 
 struct mcov_synth_params;

@@ -64,6 +64,13 @@ class BamDev(C.Structure):
                 ("isize", C.c_void_p), ("cig_off", C.c_void_p), ("cig", C.c_void_p), ("inflated", C.c_void_p)]
 
 
+class BamBatch(C.Structure):
+    """mcov_bam_batch: one batch of the streaming host reader (pinned SoA views)."""
+    _fields_ = [("n", C.c_int64), ("n_carry", C.c_int64), ("n_cigar", C.c_int64), ("last", C.c_int32), ("reserved", C.c_int32),
+                ("tid", C.c_void_p), ("pos", C.c_void_p), ("flag", C.c_void_p), ("mapq", C.c_void_p), ("l_seq", C.c_void_p),
+                ("isize", C.c_void_p), ("reflen", C.c_void_p), ("cig_off", C.c_void_p), ("cig", C.c_void_p)]
+
+
 class PassInfo(C.Structure):
     _fields_ = [("n_reads", C.c_int64), ("n_pass", C.c_int64), ("aligned_bases", C.c_int64),
                 ("max_depth_seen", C.c_int32), ("cap_metric", C.c_int32), ("sorted", C.c_int32),
@@ -166,6 +173,15 @@ SIGNATURES = {
     "mcov_bam_isize": (_vp, [_vp]),
     "mcov_bam_cig_off": (_vp, [_vp]),
     "mcov_bam_cig": (_vp, [_vp]),
+    "mcov_bam_stream_open": (C.c_int, [C.POINTER(_vp), C.c_char_p, _i64, C.c_int, C.c_char_p, C.c_int]),
+    "mcov_bam_stream_close": (None, [_vp]),
+    "mcov_bam_stream_n_ref": (_i32, [_vp]),
+    "mcov_bam_stream_ref_name": (C.c_char_p, [_vp, _i32]),
+    "mcov_bam_stream_ref_len": (_i32, [_vp, _i32]),
+    "mcov_bam_stream_header_text": (C.c_char_p, [_vp]),
+    "mcov_bam_stream_error": (C.c_char_p, [_vp]),
+    "mcov_bam_stream_next": (C.c_int, [_vp, _i32, _i32, C.POINTER(BamBatch)]),
+    "mcov_bam_stream_records": (_i64, [_vp]),
     "mcov_synth_gen_ncigar": (C.c_int, [C.POINTER(SynthParams), _i64, _i64, _vp, C.c_int, _vp]),
     "mcov_synth_gen_reads": (C.c_int, [C.POINTER(SynthParams), _i64, _i64, _vp, _vp, _i32, _i32, _vp,
                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp]),

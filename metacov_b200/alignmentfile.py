@@ -38,6 +38,79 @@ class PileupColumn:
     nsegments = property(lambda self: self.n)
 
 
+class BamStream:
+    """The streaming host reader (csrc/bamio.cpp, mcov_bam_stream_*): batches of a BAM decoded into pinned SoA
+    buffers, each led by the reads the depth engine asked to see again.  Iterate with ``next_batch(resend)``."""
+
+    def __init__(self, filename, batch_reads=1 << 21, threads=0):
+        self._h = C.c_void_p()
+        err = C.create_string_buffer(256)
+        rc = lib.mcov_bam_stream_open(C.byref(self._h), str(filename).encode(), int(batch_reads), int(threads), err, len(err))
+        if rc != 0:
+            self._h = None
+            raise OSError("%s: %s" % (filename, err.value.decode()))
+        n = lib.mcov_bam_stream_n_ref(self._h)
+        self.references = tuple(lib.mcov_bam_stream_ref_name(self._h, i).decode() for i in range(n))
+        self.lengths = tuple(lib.mcov_bam_stream_ref_len(self._h, i) for i in range(n))
+        self.text = lib.mcov_bam_stream_header_text(self._h).decode()
+
+    def next_batch(self, resend=(-1, 0)):
+        """(ReadBatch of pinned numpy views, n_carry, last, extra columns) or None after the last batch."""
+        b = _capi.BamBatch()
+        rc = lib.mcov_bam_stream_next(self._h, int(resend[0]), int(resend[1]), C.byref(b))
+        if rc < 0:
+            raise McovError(rc, lib.mcov_bam_stream_error(self._h).decode())
+        if rc == 0:
+            return None
+        n = b.n
+        batch = ReadBatch(_view(b.tid, n, np.int32), _view(b.pos, n, np.int32), _view(b.flag, n, np.uint16),
+                          _view(b.mapq, n, np.uint8), _view(b.cig_off, n + 1, np.uint32), _view(b.cig, b.n_cigar, np.uint32))
+        extra = dict(l_seq=_view(b.l_seq, n, np.int32), isize=_view(b.isize, n, np.int32), reflen=_view(b.reflen, n, np.int32))
+        return batch, int(b.n_carry), bool(b.last), extra
+
+    @property
+    def n_records(self):
+        return lib.mcov_bam_stream_records(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.mcov_bam_stream_close(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+        return False
+
+
+def stream_depth(engine, stream):
+    """Per-base depth of a whole sorted BAM through the streamed fused path: batch k+1 is decoded on the host while
+    the GPU works on batch k.  Returns the number of batches.  Raises McovError(MCOV_ERR_UNSORTED) -- at the first
+    synchronising call on the engine -- when the file is not coordinate-sorted."""
+    engine.stream_begin()
+    resend = (-1, 0)
+    k = 0
+    while True:
+        item = stream.next_batch(resend)
+        if item is None:
+            if k == 0:
+                engine.stream_push(ReadBatch(*[np.zeros(0, d) for d in (np.int32, np.int32, np.uint16, np.uint8)],
+                                             np.zeros(1, np.uint32), np.zeros(0, np.uint32)), 0, last=True)
+            break
+        batch, n_carry, last, _ = item
+        rt = engine.stream_push(batch, n_carry=n_carry, last=last)
+        if len(batch.tid):
+            resend = rt
+        k += 1
+        if last:
+            break
+    return k
+
+
 class AlignmentFile:
     def __init__(self, filename, mode="rb", device=0, decode="host", **kw):
         """decode="host": BGZF inflate and record parsing by the native host reader (csrc/bamio.cpp);
@@ -54,6 +127,8 @@ class AlignmentFile:
         self._engine = None
         self._filter_kw = None
         self._index_stats = None
+        self._batch_reads = int(kw.get("batch_reads", 1 << 21))     # records per batch of the streamed depth pass
+        self.stream_batches = 0
         if decode == "gpu":
             self._open_gpu(filename, device)
             return
@@ -281,6 +356,23 @@ class AlignmentFile:
         """The per-base depth of the whole file, computed once on the GPU."""
         if self._engine is None and self._gpu is not None:
             eng, path = self._gpu_depth()
+        elif self._engine is None and self._soa is None:
+            # host decode, records not loaded: stream the file in batches (never held in memory); a file that is not
+            # coordinate-sorted, or one where htslib's max_depth cap fires, takes the whole-file path below
+            eng = CoverageEngine(self.lengths, device=self._device, filt=self._filter_kw)
+            path = None
+            try:
+                with BamStream(self.filename, batch_reads=self._batch_reads) as st:
+                    self.stream_batches = stream_depth(eng, st)
+                eng.pass_info()                                  # delivers the verdict of the stream
+                path = "fused"
+            except McovError as e:
+                if e.code not in (_capi.MCOV_ERR_UNSORTED, _capi.MCOV_ERR_RANGE, _capi.MCOV_ERR_STATE):
+                    eng.close()
+                    raise
+            if path is None:
+                s = self.soa()
+                path = eng.compute_depth(ReadBatch(s["tid"], s["pos"], s["flag"], s["mapq"], s["cig_off"], s["cig"]))
         elif self._engine is None:
             s = self.soa()
             eng = CoverageEngine(self.lengths, device=self._device, filt=self._filter_kw)

@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -445,5 +446,373 @@ int mcov_bam_qas_kmer(const mcov_bam* b, int32_t k_len, int32_t* out) {
   }
   return MCOV_OK;
 }
+
+}  // extern "C"
+
+// ===========================================================================================================
+// Streaming reader: the file is read, inflated and parsed in BATCHES straight into pinned SoA buffers (two sets:
+// the GPU copies batch k from one set while batch k+1 is decoded into the other).  Replaces the record loop of
+// reference metacov/scan.pyx:653-667 (`cnext()` over IteratorRowAll) for the coverage path: the file is never held,
+// neither compressed nor inflated.  Each batch begins with the reads of earlier batches that the depth engine asked
+// to see again (mcov_stream_push: everything that starts at or after the resend point or reaches past it).
+// ===========================================================================================================
+#include <cuda_runtime.h>
+
+struct mcov_bam_stream {
+  FILE* fh = nullptr;
+  std::string text;
+  std::vector<std::string> ref_name;
+  std::vector<int32_t> ref_len;
+  std::vector<uint8_t> raw;        // compressed bytes read but not yet inflated (an incomplete trailing block)
+  std::vector<uint8_t> data;       // inflated bytes not yet parsed
+  size_t data_pos = 0;
+  bool eof = false, header_done = false, finished = false;
+  int n_threads = 4;
+  int64_t batch_reads = 1 << 21;
+  int64_t cap_reads = 0, cap_ops = 0;
+  struct Set {
+    int32_t *tid = nullptr, *pos = nullptr, *lseq = nullptr, *isize = nullptr, *reflen = nullptr;
+    uint16_t* flag = nullptr;
+    uint8_t* mapq = nullptr;
+    uint32_t *cig_off = nullptr, *cig = nullptr;
+    int64_t n = 0, n_carry = 0, n_ops = 0;
+    bool pinned = true;
+  } set[2];
+  int cur = 0;                     // set the NEXT batch is decoded into
+  int32_t max_reflen = 1;
+  int64_t n_records = 0;           // distinct records handed out so far
+  std::vector<size_t> rec_off;     // scratch: record offsets of the batch being built
+  std::string err;
+};
+
+namespace {
+
+constexpr size_t kStreamChunk = 32u << 20;     // compressed bytes per read() call
+
+// Pinned memory when a CUDA device is there (true asynchronous H2D); without one (the CPU test suite checks the
+// reader against the oracle's) plain aligned memory -- these are buffers, no compute path depends on which.
+template <typename T>
+bool pin_alloc(T*& p, size_t n, bool& pinned) {
+  const size_t bytes = std::max<size_t>(n * sizeof(T), 64);
+  if (pinned) {
+    if (cudaHostAlloc(reinterpret_cast<void**>(&p), bytes, cudaHostAllocDefault) == cudaSuccess) return true;
+    (void)cudaGetLastError();
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) == cudaSuccess && n_dev > 0) { p = nullptr; return false; }   // a device, but no pinned memory left
+    (void)cudaGetLastError();
+    pinned = false;
+  }
+  p = static_cast<T*>(std::aligned_alloc(64, (bytes + 63) & ~(size_t)63));
+  return p != nullptr;
+}
+
+void stream_free_set(mcov_bam_stream::Set& s) {
+  void* ps[] = {s.tid, s.pos, s.lseq, s.isize, s.reflen, s.flag, s.mapq, s.cig_off, s.cig};
+  for (void* p : ps) if (p) { if (s.pinned) cudaFreeHost(p); else std::free(p); }
+  s = mcov_bam_stream::Set();
+}
+
+bool stream_alloc_set(mcov_bam_stream::Set& s, int64_t reads, int64_t ops) {
+  bool& pn = s.pinned;
+  return pin_alloc(s.tid, reads, pn) && pin_alloc(s.pos, reads, pn) && pin_alloc(s.lseq, reads, pn) && pin_alloc(s.isize, reads, pn) &&
+         pin_alloc(s.reflen, reads, pn) && pin_alloc(s.flag, reads, pn) && pin_alloc(s.mapq, reads, pn) && pin_alloc(s.cig_off, reads + 1, pn) &&
+         pin_alloc(s.cig, ops + 4, pn);
+}
+
+// Read the next chunk of the file and inflate every complete BGZF block of it (in parallel) onto the end of `data`.
+// Returns false on a malformed file.
+bool stream_refill(mcov_bam_stream* s) {
+  if (s->eof) return true;
+  // drop what has been parsed
+  if (s->data_pos > 0) { s->data.erase(s->data.begin(), s->data.begin() + (ptrdiff_t)s->data_pos); s->data_pos = 0; }
+  const size_t old = s->raw.size();
+  s->raw.resize(old + kStreamChunk);
+  const size_t got = std::fread(s->raw.data() + old, 1, kStreamChunk, s->fh);
+  s->raw.resize(old + got);
+  if (got < kStreamChunk) s->eof = true;
+  // index the complete blocks
+  std::vector<Block> blocks;
+  size_t off = 0, uoff = 0;
+  const size_t n = s->raw.size();
+  while (off + 18 <= n) {
+    const uint8_t* h = s->raw.data() + off;
+    if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return false;
+    const uint16_t xlen = rd16(h + 10);
+    if (off + 12 + xlen > n) break;
+    int bsize = -1;
+    size_t p = off + 12;
+    const size_t xend = off + 12 + xlen;
+    while (p + 4 <= xend) {
+      const uint16_t slen = rd16(s->raw.data() + p + 2);
+      if (s->raw[p] == 'B' && s->raw[p + 1] == 'C' && slen == 2 && p + 6 <= xend) bsize = rd16(s->raw.data() + p + 4);
+      p += 4 + slen;
+    }
+    if (bsize < 0) return false;
+    const size_t bend = off + (size_t)bsize + 1;
+    if (bend > n) break;                                   // incomplete block: wait for the next chunk
+    if ((size_t)bsize + 1 < (size_t)(12 + xlen + 8)) return false;
+    Block b;
+    b.coff = off + 12 + xlen; b.clen = bend - 8 - b.coff;
+    b.crc = rd32(s->raw.data() + bend - 8); b.ulen = rd32(s->raw.data() + bend - 4);
+    if (b.ulen > 65536) return false;
+    b.uoff = uoff; uoff += b.ulen;
+    blocks.push_back(b);
+    off = bend;
+  }
+  if (s->eof && off != n) return false;                    // trailing garbage / truncated block
+  const size_t base = s->data.size();
+  s->data.resize(base + uoff);
+  std::atomic<size_t> next(0);
+  std::atomic<bool> good(true);
+  auto work = [&]() {
+    for (;;) {
+      const size_t k = next.fetch_add(1);
+      if (k >= blocks.size() || !good.load()) break;
+      const Block& bl = blocks[k];
+      if (!inflate_block(s->raw.data() + bl.coff, bl.clen, s->data.data() + base + bl.uoff, bl.ulen, bl.crc)) good.store(false);
+    }
+  };
+  const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)s->n_threads, blocks.size()));
+  std::vector<std::thread> th;
+  for (int t = 1; t < nt; ++t) th.emplace_back(work);
+  work();
+  for (auto& t : th) t.join();
+  if (!good.load()) return false;
+  s->raw.erase(s->raw.begin(), s->raw.begin() + (ptrdiff_t)off);
+  return true;
+}
+
+// header: magic, text, reference table; may span several chunks
+int stream_parse_header(mcov_bam_stream* s) {
+  for (;;) {
+    const std::vector<uint8_t>& d = s->data;
+    bool need = false;
+    size_t p = 0;
+    if (d.size() < 12) need = true;
+    else {
+      if (std::memcmp(d.data(), "BAM\1", 4) != 0) return 4;
+      const uint32_t l_text = rd32(d.data() + 4);
+      p = 8;
+      if (p + (size_t)l_text + 4 > d.size()) need = true;
+      else {
+        const uint32_t n_ref = rd32(d.data() + p + l_text);
+        size_t q = p + l_text + 4;
+        std::vector<std::string> names;
+        std::vector<int32_t> lens;
+        for (uint32_t i = 0; i < n_ref && !need; ++i) {
+          if (q + 4 > d.size()) { need = true; break; }
+          const uint32_t l_name = rd32(d.data() + q);
+          if (l_name == 0) return 4;
+          if (q + 4 + (size_t)l_name + 4 > d.size()) { need = true; break; }
+          names.emplace_back(reinterpret_cast<const char*>(d.data() + q + 4), l_name - 1);
+          lens.push_back((int32_t)rd32(d.data() + q + 4 + l_name));
+          q += 8 + l_name;
+        }
+        if (!need) {
+          s->text.assign(reinterpret_cast<const char*>(d.data() + p), strnlen(reinterpret_cast<const char*>(d.data() + p), l_text));
+          s->ref_name.swap(names); s->ref_len.swap(lens);
+          s->data_pos = q;
+          s->header_done = true;
+          return 0;
+        }
+      }
+    }
+    if (s->eof) return 4;
+    if (!stream_refill(s)) return 3;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int mcov_bam_stream_open(mcov_bam_stream** out, const char* path, int64_t batch_reads, int n_threads, char* err, int errlen) {
+  if (!out || !path) return set_err(err, errlen, "mcov_bam_stream_open: null argument");
+  *out = nullptr;
+  mcov_bam_stream* s = new (std::nothrow) mcov_bam_stream();
+  if (!s) return set_err(err, errlen, "mcov_bam_stream_open: out of memory");
+  int rc = 0;
+  try {
+    s->fh = std::fopen(path, "rb");
+    if (!s->fh) rc = 1;
+    if (batch_reads > 0) s->batch_reads = batch_reads;
+    unsigned hw = std::thread::hardware_concurrency();
+    s->n_threads = n_threads > 0 ? n_threads : (hw ? (int)hw : 4);
+    if (!rc && !stream_refill(s)) rc = 3;
+    if (!rc) rc = stream_parse_header(s);
+  } catch (const std::bad_alloc&) { rc = 5; }
+  catch (...) { rc = 3; }
+  static const char* msg[] = {"", "mcov_bam_stream_open: cannot open file", "", "mcov_bam_stream_open: not a valid BGZF file",
+                              "mcov_bam_stream_open: not a valid BAM file", "mcov_bam_stream_open: out of memory"};
+  if (rc) { if (s->fh) std::fclose(s->fh); delete s; return set_err(err, errlen, msg[rc]); }
+  *out = s;
+  return MCOV_OK;
+}
+
+void mcov_bam_stream_close(mcov_bam_stream* s) {
+  if (!s) return;
+  if (s->fh) std::fclose(s->fh);
+  stream_free_set(s->set[0]); stream_free_set(s->set[1]);
+  delete s;
+}
+
+int32_t mcov_bam_stream_n_ref(const mcov_bam_stream* s) { return s ? (int32_t)s->ref_name.size() : 0; }
+const char* mcov_bam_stream_ref_name(const mcov_bam_stream* s, int32_t tid) {
+  return (s && tid >= 0 && (size_t)tid < s->ref_name.size()) ? s->ref_name[tid].c_str() : nullptr;
+}
+int32_t mcov_bam_stream_ref_len(const mcov_bam_stream* s, int32_t tid) {
+  return (s && tid >= 0 && (size_t)tid < s->ref_len.size()) ? s->ref_len[tid] : -1;
+}
+const char* mcov_bam_stream_header_text(const mcov_bam_stream* s) { return s ? s->text.c_str() : nullptr; }
+const char* mcov_bam_stream_error(const mcov_bam_stream* s) { return s ? s->err.c_str() : "null stream"; }
+
+static int stream_next_impl(mcov_bam_stream* s, int32_t resend_tid, int32_t resend_pos, mcov_bam_batch* out) {
+  std::memset(out, 0, sizeof(*out));
+  if (s->finished) return 0;
+  mcov_bam_stream::Set& prev = s->set[s->cur ^ 1];
+  // ---- walk the record chain of the new batch (serial: a length-prefixed list), refilling as needed ----
+  s->rec_off.clear();
+  int64_t new_ops = 0;
+  bool at_end = false;
+  while ((int64_t)s->rec_off.size() < s->batch_reads) {
+    const size_t avail = s->data.size() - s->data_pos;
+    bool have = false;
+    if (avail >= 4) {
+      const uint32_t bs = rd32(s->data.data() + s->data_pos);
+      if (bs < 32) { s->err = "record shorter than its fixed part"; return MCOV_ERR_IO; }
+      if (avail >= 4 + (size_t)bs) {
+        if (!record_fits(s->data.data() + s->data_pos + 4, bs)) { s->err = "record fields exceed block_size"; return MCOV_ERR_IO; }
+        s->rec_off.push_back(s->data_pos);
+        new_ops += rd16(s->data.data() + s->data_pos + 4 + 12);
+        s->data_pos += 4 + (size_t)bs;
+        have = true;
+      }
+    }
+    if (have) continue;
+    if (s->eof) {
+      if (avail != 0) { s->err = "truncated record at the end of the file"; return MCOV_ERR_IO; }
+      at_end = true;
+      break;
+    }
+    // more data needed: the offsets collected so far move with the buffer
+    const size_t shift = s->rec_off.empty() ? s->data_pos : s->rec_off.front();
+    const size_t keep_pos = s->data_pos;
+    s->data_pos = shift;                                     // keep the batch's records in the buffer
+    if (!stream_refill(s)) { s->err = "BGZF block does not inflate"; return MCOV_ERR_IO; }
+    for (size_t& o : s->rec_off) o -= shift;
+    s->data_pos = keep_pos - shift;
+  }
+  if (!at_end && s->eof && s->data_pos == s->data.size()) at_end = true;
+  const int64_t n_new = (int64_t)s->rec_off.size();
+  // ---- carry: reads of the previous batch that start at or after the resend point or reach past it ----
+  int64_t c_lo = prev.n;                                      // carry candidates are prev[c_lo, prev.n): a suffix in sorted order
+  if (resend_tid >= 0 && prev.n > 0) {
+    const int64_t reach = (int64_t)resend_pos - s->max_reflen;
+    while (c_lo > 0) {
+      const int32_t t = prev.tid[c_lo - 1];
+      if (t >= 0 && (t < resend_tid || (t == resend_tid && prev.pos[c_lo - 1] < reach))) break;
+      --c_lo;
+    }
+  }
+  std::vector<int64_t> carry;
+  int64_t carry_ops = 0;
+  for (int64_t i = c_lo; i < prev.n && resend_tid >= 0; ++i) {
+    const int32_t t = prev.tid[i];
+    if (t < 0) continue;                                      // unplaced reads cover nothing: never needed again
+    const bool need = t > resend_tid || (t == resend_tid && (prev.pos[i] >= resend_pos || (int64_t)prev.pos[i] + prev.reflen[i] > resend_pos));
+    if (need) { carry.push_back(i); carry_ops += prev.cig_off[i + 1] - prev.cig_off[i]; }
+  }
+  const int64_t n = (int64_t)carry.size() + n_new, n_ops = carry_ops + new_ops;
+  if (n_ops > 0xFFFFFFF0ll) { s->err = "more than 2^32 CIGAR ops in one batch: lower batch_reads"; return MCOV_ERR_RANGE; }
+  // ---- (re)allocate both pinned sets when this batch does not fit ----
+  if (n > s->cap_reads || n_ops > s->cap_ops) {
+    const int64_t cr = std::max<int64_t>(n + n / 4, s->batch_reads + (s->batch_reads >> 2)), co = std::max<int64_t>(n_ops + n_ops / 4, 1024);
+    mcov_bam_stream::Set fresh[2];
+    if (!stream_alloc_set(fresh[0], cr, co) || !stream_alloc_set(fresh[1], cr, co)) {
+      stream_free_set(fresh[0]); stream_free_set(fresh[1]);
+      s->err = "pinned host memory exhausted";
+      return MCOV_ERR_NOMEM;
+    }
+    // the previous batch is still needed for the carry: move it over
+    mcov_bam_stream::Set& np = fresh[s->cur ^ 1];
+    if (prev.n > 0) {
+      std::memcpy(np.tid, prev.tid, prev.n * 4); std::memcpy(np.pos, prev.pos, prev.n * 4); std::memcpy(np.lseq, prev.lseq, prev.n * 4);
+      std::memcpy(np.isize, prev.isize, prev.n * 4); std::memcpy(np.reflen, prev.reflen, prev.n * 4); std::memcpy(np.flag, prev.flag, prev.n * 2);
+      std::memcpy(np.mapq, prev.mapq, prev.n); std::memcpy(np.cig_off, prev.cig_off, (prev.n + 1) * 4); std::memcpy(np.cig, prev.cig, prev.n_ops * 4);
+    }
+    np.n = prev.n; np.n_carry = prev.n_carry; np.n_ops = prev.n_ops;
+    // (the caller must have finished with the old buffers: mcov_stream_push returns after its copies are done)
+    stream_free_set(s->set[0]); stream_free_set(s->set[1]);
+    s->set[0] = fresh[0]; s->set[1] = fresh[1];
+    s->cap_reads = cr; s->cap_ops = co;
+  }
+  mcov_bam_stream::Set& cur = s->set[s->cur];
+  mcov_bam_stream::Set& pv = s->set[s->cur ^ 1];
+  // ---- carried reads first ----
+  uint32_t co = 0;
+  for (size_t k = 0; k < carry.size(); ++k) {
+    const int64_t i = carry[k];
+    cur.tid[k] = pv.tid[i]; cur.pos[k] = pv.pos[i]; cur.lseq[k] = pv.lseq[i]; cur.isize[k] = pv.isize[i]; cur.reflen[k] = pv.reflen[i];
+    cur.flag[k] = pv.flag[i]; cur.mapq[k] = pv.mapq[i];
+    const uint32_t nops = pv.cig_off[i + 1] - pv.cig_off[i];
+    cur.cig_off[k] = co;
+    std::memcpy(cur.cig + co, pv.cig + pv.cig_off[i], (size_t)nops * 4);
+    co += nops;
+  }
+  const int64_t nc = (int64_t)carry.size();
+  // ---- new reads: offsets serially (a prefix sum over the op counts), fields and ops in parallel ----
+  const uint8_t* d = s->data.data();
+  for (int64_t i = 0; i < n_new; ++i) { cur.cig_off[nc + i] = co; co += rd16(d + s->rec_off[(size_t)i] + 4 + 12); }
+  cur.cig_off[n] = co;
+  std::atomic<int32_t> mx(s->max_reflen);
+  auto fill = [&](int64_t lo, int64_t hi) {
+    int32_t local_max = 1;
+    for (int64_t i = lo; i < hi; ++i) {
+      const uint8_t* r = d + s->rec_off[(size_t)i] + 4;
+      const int64_t k = nc + i;
+      cur.tid[k] = (int32_t)rd32(r); cur.pos[k] = (int32_t)rd32(r + 4);
+      const uint8_t l_read_name = r[8];
+      cur.mapq[k] = r[9];
+      const uint16_t n_op = rd16(r + 12);
+      cur.flag[k] = rd16(r + 14);
+      cur.lseq[k] = (int32_t)rd32(r + 16); cur.isize[k] = (int32_t)rd32(r + 28);
+      uint32_t* dst = cur.cig + cur.cig_off[k];
+      std::memcpy(dst, r + 32 + l_read_name, 4u * n_op);
+      int64_t rl = 0;
+      for (uint16_t o = 0; o < n_op; ++o) { const uint32_t op = dst[o]; if ((0x18Du >> (op & 15u)) & 1u) rl += op >> 4; }
+      const int32_t rl32 = rl > 0x7fffffff ? 0x7fffffff : (int32_t)rl;
+      cur.reflen[k] = rl32;
+      local_max = std::max(local_max, rl32);
+    }
+    int32_t seen = mx.load();
+    while (local_max > seen && !mx.compare_exchange_weak(seen, local_max)) {}
+  };
+  {
+    const int nt = n_new >= 65536 ? std::max(1, std::min(s->n_threads, 32)) : 1;
+    const int64_t per = (n_new + nt - 1) / nt;
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) { const int64_t lo = t * per, hi = std::min(n_new, lo + per); if (lo < hi) th.emplace_back(fill, lo, hi); }
+    fill(0, std::min(n_new, per));
+    for (auto& t : th) t.join();
+  }
+  s->max_reflen = mx.load();
+  cur.n = n; cur.n_carry = nc; cur.n_ops = co;
+  s->n_records += n_new;
+  out->n = n; out->n_carry = nc; out->n_cigar = co; out->last = at_end ? 1 : 0;
+  out->tid = cur.tid; out->pos = cur.pos; out->flag = cur.flag; out->mapq = cur.mapq; out->l_seq = cur.lseq; out->isize = cur.isize;
+  out->reflen = cur.reflen; out->cig_off = cur.cig_off; out->cig = cur.cig;
+  s->cur ^= 1;
+  if (at_end) s->finished = true;
+  return 1;
+}
+
+int mcov_bam_stream_next(mcov_bam_stream* s, int32_t resend_tid, int32_t resend_pos, mcov_bam_batch* out) {
+  if (!s || !out) return MCOV_ERR_ARG;
+  try { return stream_next_impl(s, resend_tid, resend_pos, out); }
+  catch (const std::bad_alloc&) { s->err = "out of memory"; return MCOV_ERR_NOMEM; }
+  catch (...) { s->err = "unexpected failure"; return MCOV_ERR_IO; }
+}
+
+int64_t mcov_bam_stream_records(const mcov_bam_stream* s) { return s ? s->n_records : 0; }
 
 }  // extern "C"
