@@ -207,6 +207,52 @@ int  mcov_depth_sorted_delta(mcov_ctx* ctx, int64_t n,
                              const uint16_t* flag, const uint8_t* mapq /* may be NULL */,
                              const uint8_t* n_cigar, const uint16_t* cig, int64_t n_cig_total, int wait);
 
+/* ---- the transport block: what the host decoder hands to the GPU ----------------
+ * ONE contiguous host buffer per batch of coordinate-sorted reads -> ONE host-to-device
+ * copy; the SoA columns are rebuilt on the device.  The end-to-end rate is bound by the
+ * PCIe link, so the block is as narrow as the data allows (config C2: 3.6 bytes per
+ * read instead of 19.6 for the plain columns):
+ *   crs      int64[n_contigs+1]  reads [crs[c], crs[c+1]) belong to contig c, reads from
+ *                                crs[n_contigs] on are unplaced (instead of tid[n])
+ *   dpos     u8[n]               position - position of the previous read of the same
+ *                                contig (first read of a contig: - 0); differences outside
+ *                                0..255 are listed as exceptions (exc_idx u32, exc_val i32)
+ *   fidx     u8[n] + flagdict u16[<=256]   flag dictionary (u16 flags directly when a
+ *                                batch holds more than 256 distinct flags: flag_wide = 1)
+ *   cclass   u8[n]               < 128: the read's whole CIGAR is dictionary entry cclass
+ *                                (dict_off u32[n_dict+1], dict_ops u32[]: the batch's most
+ *                                frequent CIGARs); >= 128: cclass - 128 explicit ops follow
+ *                                in xops u32[] in read order
+ *   mapq     u8[n]               only when the filter asks for it (min_mapq > 0)
+ * A batch with a CIGAR of more than 127 ops (long reads) does not qualify
+ * (mcov_pack_block returns MCOV_ERR_RANGE): it travels as plain columns or through
+ * mcov_depth_sorted_packed.  All sections start on 16-byte boundaries. */
+#define MCOV_BLOCK_MAGIC 0x4256434Du   /* "MCVB" */
+typedef struct mcov_block_hdr {
+  uint32_t magic, version;
+  int64_t  n, n_carry, n_cigar, n_exc, n_xops, total_bytes;
+  int32_t  n_contigs, n_flagdict, n_dict, n_dictops, flag_wide, has_mapq;
+  int32_t  last_tid, last_pos;                 /* the batch's last read (streams: how far the depth becomes final) */
+  uint32_t off_crs, off_dpos, off_exc_idx, off_exc_val, off_fidx, off_flagdict, off_cclass, off_dict_off,
+           off_dict_ops, off_xops, off_mapq, reserved;
+} mcov_block_hdr;
+/* Upper bound of the block size for a batch of n reads with n_cigar ops over n_contigs contigs. */
+int64_t mcov_block_bound(int64_t n, int64_t n_cigar, int32_t n_contigs);
+/* Pack a coordinate-sorted SoA batch (host arrays, grouped by contig with unplaced reads last; the first
+ * n_carry reads are repeats of earlier batches, see mcov_stream_push) into `out` (capacity cap bytes, 16-byte
+ * aligned; pinned memory makes the copy asynchronous).  mapq may be NULL.  n_threads <= 0: all cores.
+ * Returns MCOV_OK and the size in *bytes_out, MCOV_ERR_ARG (not grouped by contig, cap too small) or
+ * MCOV_ERR_RANGE (a CIGAR of more than 127 ops). */
+int  mcov_pack_block(int64_t n, int64_t n_carry, const int32_t* tid, const int32_t* pos, const uint16_t* flag,
+                     const uint8_t* mapq, const uint32_t* cig_off, const uint32_t* cig, int32_t n_contigs,
+                     void* out, int64_t cap, int64_t* bytes_out, int n_threads);
+/* The fused sorted pass from a transport block in host memory (wait = 0 defers the verdict like
+ * mcov_depth_sorted_async), and one batch of a streamed pass (see mcov_stream_push; the block's n_carry
+ * leading reads are the repeats). */
+int  mcov_depth_sorted_block(mcov_ctx* ctx, const void* block, int64_t bytes, int wait);
+int  mcov_stream_push_block(mcov_ctx* ctx, const void* block, int64_t bytes, int last,
+                            int32_t* resend_tid, int32_t* resend_pos);
+
 /* Replaces the seven reductions of `classic` (reference
  * metacov/pileup.py:18-26) for g regions at once (the loop at cli.py:85-95).
  * tid/start/end are host arrays; 0 <= start <= end.  Positions >= len[tid]
@@ -472,6 +518,11 @@ const char* mcov_bam_stream_header_text(const mcov_bam_stream* s);
 const char* mcov_bam_stream_error(const mcov_bam_stream* s);
 int  mcov_bam_stream_next(mcov_bam_stream* s, int32_t resend_tid, int32_t resend_pos, mcov_bam_batch* out);
 int64_t mcov_bam_stream_records(const mcov_bam_stream* s);   /* distinct records handed out so far */
+/* Same, and the batch packed as a transport block in pinned memory owned by the stream (valid like the
+ * batch's arrays).  *block is NULL when the batch does not qualify (long-read CIGARs, unsorted file):
+ * push the columns of *out instead. */
+int  mcov_bam_stream_next_block(mcov_bam_stream* s, int32_t resend_tid, int32_t resend_pos, int with_mapq,
+                                const void** block, int64_t* bytes, mcov_bam_batch* out);
 
 /* ---- synthetic workloads (bench / test support; include/mcov_synth.h) ---- */
 

@@ -19,7 +19,7 @@ LIB = os.path.join(HERE, "libmetacov_b200.so")
 BUILD_DIR = os.path.join(ROOT, "build")
 
 CUDA_SOURCES = ["mcov_api.cu", "stats_sort.cu", "experimental.cu", "synth.cu", "bam_gpu.cu"]
-CXX_SOURCES = ["bamio.cpp"]
+CXX_SOURCES = ["bamio.cpp", "transport.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-I" + INCLUDE,

@@ -119,6 +119,10 @@ SIGNATURES = {
     "mcov_stream_push": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int,
                                    C.POINTER(_i32), C.POINTER(_i32)]),
     "mcov_stream_resend_point": (C.c_int, [_vp, _i32, _i32, C.POINTER(_i32), C.POINTER(_i32)]),
+    "mcov_block_bound": (_i64, [_i64, _i64, _i32]),
+    "mcov_pack_block": (C.c_int, [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, C.POINTER(_i64), C.c_int]),
+    "mcov_depth_sorted_block": (C.c_int, [_vp, _vp, _i64, C.c_int]),
+    "mcov_stream_push_block": (C.c_int, [_vp, _vp, _i64, C.c_int, C.POINTER(_i32), C.POINTER(_i32)]),
     "mcov_depth_sorted_async": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int]),
     "mcov_depth_sorted_packed": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.c_int]),
     "mcov_depth_sorted_delta": (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int]),
@@ -182,6 +186,7 @@ SIGNATURES = {
     "mcov_bam_stream_error": (C.c_char_p, [_vp]),
     "mcov_bam_stream_next": (C.c_int, [_vp, _i32, _i32, C.POINTER(BamBatch)]),
     "mcov_bam_stream_records": (_i64, [_vp]),
+    "mcov_bam_stream_next_block": (C.c_int, [_vp, _i32, _i32, C.c_int, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(BamBatch)]),
     "mcov_synth_gen_ncigar": (C.c_int, [C.POINTER(SynthParams), _i64, _i64, _vp, C.c_int, _vp]),
     "mcov_synth_gen_reads": (C.c_int, [C.POINTER(SynthParams), _i64, _i64, _vp, _vp, _i32, _i32, _vp,
                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp]),

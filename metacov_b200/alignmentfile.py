@@ -68,6 +68,23 @@ class BamStream:
         extra = dict(l_seq=_view(b.l_seq, n, np.int32), isize=_view(b.isize, n, np.int32), reflen=_view(b.reflen, n, np.int32))
         return batch, int(b.n_carry), bool(b.last), extra
 
+    def next_block(self, resend=(-1, 0), with_mapq=False):
+        """Like ``next_batch`` plus the batch as a transport block: (block or None, ReadBatch, n_carry, last, extra)."""
+        b = _capi.BamBatch()
+        blk, nb = C.c_void_p(), C.c_int64(0)
+        rc = lib.mcov_bam_stream_next_block(self._h, int(resend[0]), int(resend[1]), 1 if with_mapq else 0,
+                                            C.byref(blk), C.byref(nb), C.byref(b))
+        if rc < 0:
+            raise McovError(rc, lib.mcov_bam_stream_error(self._h).decode())
+        if rc == 0:
+            return None
+        n = b.n
+        batch = ReadBatch(_view(b.tid, n, np.int32), _view(b.pos, n, np.int32), _view(b.flag, n, np.uint16),
+                          _view(b.mapq, n, np.uint8), _view(b.cig_off, n + 1, np.uint32), _view(b.cig, b.n_cigar, np.uint32))
+        extra = dict(l_seq=_view(b.l_seq, n, np.int32), isize=_view(b.isize, n, np.int32), reflen=_view(b.reflen, n, np.int32))
+        block = (blk.value, nb.value) if blk.value else None
+        return block, batch, int(b.n_carry), bool(b.last), extra
+
     @property
     def n_records(self):
         return lib.mcov_bam_stream_records(self._h)
@@ -95,14 +112,18 @@ def stream_depth(engine, stream):
     resend = (-1, 0)
     k = 0
     while True:
-        item = stream.next_batch(resend)
+        item = stream.next_block(resend, with_mapq=engine.filter.min_mapq > 0)
         if item is None:
             if k == 0:
                 engine.stream_push(ReadBatch(*[np.zeros(0, d) for d in (np.int32, np.int32, np.uint16, np.uint8)],
                                              np.zeros(1, np.uint32), np.zeros(0, np.uint32)), 0, last=True)
             break
-        batch, n_carry, last, _ = item
-        rt = engine.stream_push(batch, n_carry=n_carry, last=last)
+        block, batch, n_carry, last, _ = item
+        # the transport block (one narrow host-to-device copy) when the batch qualifies, else its columns
+        if block is not None and len(batch.tid):
+            rt = engine.stream_push_block(block, last=last)
+        else:
+            rt = engine.stream_push(batch, n_carry=n_carry, last=last)
         if len(batch.tid):
             resend = rt
         k += 1

@@ -483,6 +483,11 @@ struct mcov_bam_stream {
   int64_t n_records = 0;           // distinct records handed out so far
   std::vector<size_t> rec_off;     // scratch: record offsets of the batch being built
   std::string err;
+  // transport blocks of the batches (mcov_bam_stream_next_block): two pinned buffers, like the SoA sets
+  void* blk[2] = {nullptr, nullptr};
+  int64_t blk_cap[2] = {0, 0};
+  bool blk_pinned = true;
+  int blk_cur = 0;
 };
 
 namespace {
@@ -653,6 +658,7 @@ void mcov_bam_stream_close(mcov_bam_stream* s) {
   if (!s) return;
   if (s->fh) std::fclose(s->fh);
   stream_free_set(s->set[0]); stream_free_set(s->set[1]);
+  for (void* p : s->blk) if (p) { if (s->blk_pinned) cudaFreeHost(p); else std::free(p); }
   delete s;
 }
 
@@ -814,5 +820,38 @@ int mcov_bam_stream_next(mcov_bam_stream* s, int32_t resend_tid, int32_t resend_
 }
 
 int64_t mcov_bam_stream_records(const mcov_bam_stream* s) { return s ? s->n_records : 0; }
+
+// The next batch as a transport block (mcov_pack_block) in pinned memory owned by the stream: what
+// mcov_stream_push_block / mcov_depth_sorted_block take with ONE host-to-device copy.  *block is NULL when the batch does
+// not qualify for the block (a CIGAR of more than 127 ops: long reads) -- push its columns (*out) instead.
+int mcov_bam_stream_next_block(mcov_bam_stream* s, int32_t resend_tid, int32_t resend_pos, int with_mapq,
+                               const void** block, int64_t* bytes, mcov_bam_batch* out) {
+  if (!s || !out || !block || !bytes) return MCOV_ERR_ARG;
+  *block = nullptr; *bytes = 0;
+  int rc = mcov_bam_stream_next(s, resend_tid, resend_pos, out);
+  if (rc <= 0) return rc;
+  try {
+    const int32_t n_contigs = (int32_t)s->ref_len.size();
+    if (n_contigs <= 0) return rc;
+    const int64_t need = mcov_block_bound(out->n, out->n_cigar, n_contigs);
+    const int k = s->blk_cur;
+    s->blk_cur ^= 1;
+    if (need > s->blk_cap[k]) {
+      if (s->blk[k]) { if (s->blk_pinned) cudaFreeHost(s->blk[k]); else std::free(s->blk[k]); s->blk[k] = nullptr; s->blk_cap[k] = 0; }
+      const int64_t want = need + need / 4;
+      uint8_t* p = nullptr;
+      if (!pin_alloc(p, (size_t)want, s->blk_pinned)) { s->err = "pinned host memory exhausted"; return MCOV_ERR_NOMEM; }
+      s->blk[k] = p; s->blk_cap[k] = want;
+    }
+    int64_t nb = 0;
+    const int prc = mcov_pack_block(out->n, out->n_carry, out->tid, out->pos, out->flag, with_mapq ? out->mapq : nullptr, out->cig_off,
+                                    out->cig, n_contigs, s->blk[k], s->blk_cap[k], &nb, s->n_threads);
+    if (prc == MCOV_OK) { *block = s->blk[k]; *bytes = nb; }
+    else if (prc != MCOV_ERR_RANGE && prc != MCOV_ERR_ARG) { s->err = "transport block packing failed"; return prc; }
+    // (MCOV_ERR_ARG: the file is not grouped by contig, i.e. not sorted -- the caller pushes the columns and gets the verdict)
+    return rc;
+  } catch (const std::bad_alloc&) { s->err = "out of memory"; return MCOV_ERR_NOMEM; }
+  catch (...) { s->err = "unexpected failure"; return MCOV_ERR_IO; }
+}
 
 }  // extern "C"

@@ -63,6 +63,7 @@ struct RegionPlan {
 
 struct ReadStage {            // one staging set for host-resident batches
   DevBuf tid, pos, flag, mapq, cig_off, cig;
+  DevBuf raw;                       // the narrow host transports land here before they are widened into the columns
   cudaEvent_t consumed = nullptr;   // recorded after the kernel that read this set
   bool in_flight = false;
 };

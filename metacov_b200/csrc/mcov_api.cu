@@ -14,6 +14,7 @@
 #include "k_fused.cuh"
 #include "k_prep_tma.cuh"
 #include "k_tile_tma.cuh"
+#include "k_block.cuh"
 #include "k_hist.cuh"
 #include "k_scan.cuh"
 #include "k_export.cuh"
@@ -268,6 +269,75 @@ int fused_verdict(mcov_ctx* ctx, const PassCounters& h) {
   return MCOV_OK;
 }
 
+// Bring a transport block (host memory) to the device with ONE copy and widen it into the columns of a staging
+// set (k_block.cuh).  On return `a` describes the batch and the compute stream has the unpack kernels enqueued.
+int block_stage(mcov_ctx* ctx, const void* block, int64_t bytes, ExpandArgs& a, ReadStage** used, mcov_block_hdr& h) {
+  *used = nullptr;
+  if (!block || bytes < (int64_t)sizeof(mcov_block_hdr)) return fail(ctx, MCOV_ERR_ARG, "transport block: null or too short");
+  std::memcpy(&h, block, sizeof(h));
+  if (h.magic != MCOV_BLOCK_MAGIC || h.version != 1) return fail(ctx, MCOV_ERR_ARG, "transport block: bad magic / version");
+  const int64_t n = h.n;
+  if (n < 0 || n >= 0xFFFFFFF0ll || h.n_carry < 0 || h.n_carry > n || h.n_exc < 0 || h.n_xops < 0 || h.n_cigar < 0 || h.n_cigar > 0xFFFFFFF0ll ||
+      h.total_bytes > bytes || h.n_contigs != ctx->n_contigs || h.n_dict < 0 || h.n_dict > 128 || h.n_flagdict < 0 || h.n_flagdict > 256 ||
+      h.n_dictops < 0 || h.n_dictops > 512)
+    return fail(ctx, MCOV_ERR_ARG, "transport block: inconsistent header (or packed for another contig table)");
+  {
+    const uint64_t tb = (uint64_t)h.total_bytes, n1 = (uint64_t)std::max<int64_t>(n, 1);
+    auto in = [&](uint32_t off, uint64_t len) { return (off & 15u) == 0 && (uint64_t)off + len <= tb; };
+    if (!in(h.off_crs, ((uint64_t)h.n_contigs + 1) * 8) || !in(h.off_dpos, n1) || !in(h.off_exc_idx, (uint64_t)h.n_exc * 4) ||
+        !in(h.off_exc_val, (uint64_t)h.n_exc * 4) || !in(h.off_fidx, h.flag_wide ? n1 * 2 : n1) || !in(h.off_flagdict, 512) ||
+        !in(h.off_cclass, n1) || !in(h.off_dict_off, 129 * 4) || !in(h.off_dict_ops, 2048) || !in(h.off_xops, (uint64_t)h.n_xops * 4) ||
+        (h.has_mapq && !in(h.off_mapq, n1)))
+      return fail(ctx, MCOV_ERR_ARG, "transport block: a section lies outside the block");
+  }
+  if (!h.has_mapq && ctx->filt.min_mapq > 0) return fail(ctx, MCOV_ERR_ARG, "transport block: packed without mapq, but the filter has min_mapq > 0");
+  ReadStage& st = ctx->stage[ctx->stage_next];
+  ctx->stage_next ^= 1;
+  if (st.in_flight) { CU(cudaEventSynchronize(st.consumed)); st.in_flight = false; }
+  const int64_t n1 = std::max<int64_t>(n, 1);
+  const int64_t off_len = (n + 1 + 3) & ~(int64_t)3;                    // scanned in place: multiple of 4
+  CU(st.raw.ensure((size_t)h.total_bytes + 16));
+  CU(st.tid.ensure((size_t)n1 * 4)); CU(st.pos.ensure((size_t)n1 * 4)); CU(st.flag.ensure((size_t)n1 * 2)); CU(st.mapq.ensure((size_t)n1));
+  CU(st.cig_off.ensure((size_t)off_len * 4)); CU(st.cig.ensure((size_t)h.n_cigar * 4 + 16));
+  CU(ctx->d_start_slot.ensure((size_t)(off_len + 8) * 4));              // S (the record buffer of the fused pass: free until the prep kernel)
+  CU(ctx->d_end_slot.ensure((size_t)off_len * 4));                      // explicit-op offsets
+  CU(cudaMemcpyAsync(st.raw.p, block, (size_t)h.total_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+  CU(cudaEventRecord(ctx->copied, ctx->copy_stream));
+  CU(cudaStreamWaitEvent(ctx->stream, ctx->copied, 0));
+  cudaStream_t s = ctx->stream;
+  BlockArgs b;
+  b.blk = st.raw.as<char>(); b.h = h; b.off_len = off_len;
+  b.S = ctx->d_start_slot.as<int32_t>(); b.xoff = ctx->d_end_slot.as<uint32_t>();
+  b.tid = st.tid.as<int32_t>(); b.pos = st.pos.as<int32_t>(); b.flag = st.flag.as<uint16_t>(); b.mapq = st.mapq.as<uint8_t>();
+  b.cig_off = st.cig_off.as<uint32_t>(); b.cig = st.cig.as<uint32_t>();
+  ctx->prof_begin(kKDeltaUnpack);
+  k_block_seed<<<(unsigned)((off_len + 255) / 256), 256, 0, s>>>(b);
+  if (h.n_exc) k_delta_patch<<<(unsigned)((h.n_exc + 255) / 256), 256, 0, s>>>(h.n_exc, reinterpret_cast<const uint32_t*>(b.blk + h.off_exc_idx),
+                                                                               reinterpret_cast<const int32_t*>(b.blk + h.off_exc_val), n, b.S);
+  ctx->prof_end();
+  CU(cudaGetLastError());
+  {
+    const int64_t tiles = (off_len + kScanTile - 1) / kScanTile;
+    CU(ctx->d_tile_cnt.ensure((size_t)tiles * 24));
+    CU(cudaMemsetAsync(ctx->d_tile_cnt.p, 0, (size_t)tiles * 24, s));
+    unsigned long long* stw = ctx->d_tile_cnt.as<unsigned long long>();
+    MCOV_LAUNCH(ctx, kKScanCounts, (k_scan_inplace<false><<<(unsigned)tiles, kScanThreads, 0, s>>>(reinterpret_cast<int32_t*>(b.cig_off), off_len, stw, pc_of(ctx))));
+    MCOV_LAUNCH(ctx, kKScanCounts, (k_scan_inplace<false><<<(unsigned)tiles, kScanThreads, 0, s>>>(b.S, off_len, stw + tiles, pc_of(ctx))));
+    if (h.n_xops) MCOV_LAUNCH(ctx, kKScanCounts, (k_scan_inplace<false><<<(unsigned)tiles, kScanThreads, 0, s>>>(reinterpret_cast<int32_t*>(b.xoff), off_len, stw + 2 * tiles, pc_of(ctx))));
+    CU(cudaGetLastError());
+  }
+  MCOV_LAUNCH(ctx, kKDeltaUnpack, (k_block_finish<<<grid_for(ctx, n1, 256, 8), 256, 0, s>>>(b)));
+  CU(cudaGetLastError());
+  std::memset(&a, 0, sizeof(a));
+  a.n = n;
+  a.tid = b.tid; a.pos = b.pos; a.flag = b.flag; a.mapq = b.mapq; a.cig_off = b.cig_off; a.cig = b.cig;
+  a.contig_off = ctx->d_off.as<int64_t>(); a.contig_len = ctx->d_len.as<int32_t>(); a.n_contigs = ctx->n_contigs;
+  a.filt = ctx->filt; a.delta = ctx->depth; a.pc = pc_of(ctx);
+  a.cig_aligned16 = 1;
+  *used = &st;
+  return MCOV_OK;
+}
+
 // Every kernel of a pass asks for the same shared-memory carve-out (the maximum): consecutive kernels with
 // different L1 / shared-memory splits make the SMs reconfigure between launches, which costs a few
 // microseconds per kernel on a step of ~180 us.  Also opts the TMA kernels into their dynamic shared memory.
@@ -344,7 +414,7 @@ void mcov_destroy(mcov_ctx* ctx) {
   if (ctx->copied) cudaEventDestroy(ctx->copied);
   for (auto& s : ctx->stage) {
     if (s.consumed) cudaEventDestroy(s.consumed);
-    s.tid.release(); s.pos.release(); s.flag.release(); s.mapq.release(); s.cig_off.release(); s.cig.release();
+    s.tid.release(); s.pos.release(); s.flag.release(); s.mapq.release(); s.cig_off.release(); s.cig.release(); s.raw.release();
   }
   DevBuf* bufs[] = {&ctx->d_len, &ctx->d_off, &ctx->depth_own, &ctx->d_pc, &ctx->d_status, &ctx->d_end_slot,
                     &ctx->d_start_slot, &ctx->d_far_list, &ctx->d_tile_cnt, &ctx->d_tile_off, &ctx->d_far_sorted,
@@ -445,10 +515,11 @@ int mcov_depth_sorted_delta(mcov_ctx* ctx, int64_t n, const int64_t* contig_read
   const size_t o_dpos = (crs_bytes + 15) & ~(size_t)15, o_nc = (o_dpos + (size_t)n1 * 2 + 15) & ~(size_t)15,
                o_ei = (o_nc + (size_t)n1 + 15) & ~(size_t)15, o_ed = (o_ei + (size_t)std::max<int64_t>(n_exc, 1) * 4 + 15) & ~(size_t)15,
                o_c16 = (o_ed + (size_t)std::max<int64_t>(n_exc, 1) * 4 + 15) & ~(size_t)15, x_bytes = o_c16 + (size_t)n_cig_total * 2 + 16;
-  CU(ctx->d_end_slot.ensure(x_bytes));
+  CU(st.raw.ensure(x_bytes));                                           // (part of the double-buffered stage: the copy of the next
+                                                                        //  call must not land on columns this call's kernels still read)
   CU(ctx->d_start_slot.ensure((size_t)(off_len + 8) * 4));              // S (the record buffer of the fused pass: free until k_fused_prep)
   cudaStream_t cs = ctx->copy_stream;
-  char* x = ctx->d_end_slot.as<char>();
+  char* x = st.raw.as<char>();
   CU(cudaMemcpyAsync(x, contig_read_start, crs_bytes, cudaMemcpyHostToDevice, cs));
   if (n > 0) {
     CU(cudaMemcpyAsync(x + o_dpos, dpos, (size_t)n * 2, cudaMemcpyHostToDevice, cs));
@@ -654,33 +725,21 @@ int mcov_stream_resend_point(const mcov_ctx* ctx, int32_t last_tid, int32_t last
   return MCOV_OK;
 }
 
-int mcov_stream_push(mcov_ctx* ctx, int64_t n, int64_t n_carry, const int32_t* tid, const int32_t* pos, const uint16_t* flag,
-                     const uint8_t* mapq, const uint32_t* cig_off, const uint32_t* cig, int mem_kind, int last,
-                     int32_t* resend_tid, int32_t* resend_pos) {
-  if (!ctx) return MCOV_ERR_ARG;
-  if (ctx->state != kStreaming) return fail(ctx, MCOV_ERR_STATE, "mcov_stream_push: call mcov_stream_begin first");
-  if (n < 0 || n_carry < 0 || n_carry > n) return fail(ctx, MCOV_ERR_ARG, "mcov_stream_push: need 0 <= n_carry <= n");
-  if (n > 0 && (!tid || !pos || !flag || !mapq || !cig_off)) return fail(ctx, MCOV_ERR_ARG, "mcov_stream_push: null array");
-  CU(cudaSetDevice(ctx->device));
+// tile up to which a batch ending with the read (lt, lp) makes the depth final
+static int64_t stream_tile_of(const mcov_ctx* ctx, int32_t lt, int32_t lp) {
   const int64_t n_tiles = (ctx->n_slots + kTile - 1) / kTile;
-  // the batch's last read decides how far the depth becomes final
-  int32_t lt = -1, lp = 0;
-  if (n > 0) {
-    if (mem_kind == MCOV_MEM_HOST) { lt = tid[n - 1]; lp = pos[n - 1]; }
-    else {
-      CU(cudaMemcpyAsync(&lt, tid + n - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
-      CU(cudaMemcpyAsync(&lp, pos + n - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
-      CU(cudaStreamSynchronize(ctx->stream));
-    }
-  }
+  int64_t slot = ctx->n_slots;
+  if (lt >= 0 && lt < ctx->n_contigs) slot = ctx->off[lt] + std::min<int64_t>(std::max<int64_t>(lp, 0), ctx->len[lt]);
+  return std::min<int64_t>(slot >> kTileShift, n_tiles);
+}
+
+// the part of a stream push that follows the staging of the batch (`a` = device columns)
+static int stream_push_staged(mcov_ctx* ctx, const ExpandArgs& a, ReadStage* st, int64_t n, int64_t n_carry, int32_t lt, int32_t lp,
+                              int last, int32_t* resend_tid, int32_t* resend_pos) {
+  const int64_t n_tiles = (ctx->n_slots + kTile - 1) / kTile;
   int64_t tile_hi = n_tiles;
   if (!last) {
-    if (n == 0) tile_hi = ctx->stream_tile_lo;
-    else {
-      int64_t slot = ctx->n_slots;
-      if (lt >= 0 && lt < ctx->n_contigs) slot = ctx->off[lt] + std::min<int64_t>(std::max<int64_t>(lp, 0), ctx->len[lt]);
-      tile_hi = std::min<int64_t>(slot >> kTileShift, n_tiles);
-    }
+    tile_hi = n == 0 ? ctx->stream_tile_lo : stream_tile_of(ctx, lt, lp);
     if (tile_hi < ctx->stream_tile_lo) {
       ctx->state = kIdle;
       return fail(ctx, MCOV_ERR_UNSORTED, "mcov_stream_push: the batch ends before the previous one (batches must follow the sorted order)");
@@ -691,17 +750,7 @@ int mcov_stream_push(mcov_ctx* ctx, int64_t n, int64_t n_carry, const int32_t* t
     else { *resend_tid = -1; *resend_pos = 0; }                  // (an empty batch changes nothing: keep sending what was being sent)
   }
   CU(cudaMemsetAsync(ctx->d_pc.p, 0, sizeof(PassCounters), ctx->stream));
-  ExpandArgs a;
-  ReadStage* st = nullptr;
-  int rc;
-  if (n > 0) {
-    rc = stage_reads(ctx, n, tid, pos, flag, mapq, cig_off, false, cig, mem_kind, a, &st);
-    if (rc) return rc;
-  } else {
-    std::memset(&a, 0, sizeof(a));
-    a.pc = pc_of(ctx);
-  }
-  rc = fused_depth_sorted(ctx, a, ctx->stream_tile_lo, tile_hi);
+  int rc = fused_depth_sorted(ctx, a, ctx->stream_tile_lo, tile_hi);
   if (rc) return rc;
   // pass counters of the stream: this batch minus its carried reads, added to the running totals
   unsigned long long* carry = reinterpret_cast<unsigned long long*>(ctx->d_stream_acc.as<char>() + sizeof(StreamAcc));
@@ -726,6 +775,73 @@ int mcov_stream_push(mcov_ctx* ctx, int64_t n, int64_t n_carry, const int32_t* t
   return MCOV_OK;
 }
 
+int mcov_stream_push(mcov_ctx* ctx, int64_t n, int64_t n_carry, const int32_t* tid, const int32_t* pos, const uint16_t* flag,
+                     const uint8_t* mapq, const uint32_t* cig_off, const uint32_t* cig, int mem_kind, int last,
+                     int32_t* resend_tid, int32_t* resend_pos) {
+  if (!ctx) return MCOV_ERR_ARG;
+  if (ctx->state != kStreaming) return fail(ctx, MCOV_ERR_STATE, "mcov_stream_push: call mcov_stream_begin first");
+  if (n < 0 || n_carry < 0 || n_carry > n) return fail(ctx, MCOV_ERR_ARG, "mcov_stream_push: need 0 <= n_carry <= n");
+  if (n > 0 && (!tid || !pos || !flag || !mapq || !cig_off)) return fail(ctx, MCOV_ERR_ARG, "mcov_stream_push: null array");
+  CU(cudaSetDevice(ctx->device));
+  // the batch's last read decides how far the depth becomes final
+  int32_t lt = -1, lp = 0;
+  if (n > 0) {
+    if (mem_kind == MCOV_MEM_HOST) { lt = tid[n - 1]; lp = pos[n - 1]; }
+    else {
+      CU(cudaMemcpyAsync(&lt, tid + n - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaMemcpyAsync(&lp, pos + n - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+    }
+  }
+  ExpandArgs a;
+  ReadStage* st = nullptr;
+  if (n > 0) {
+    int rc = stage_reads(ctx, n, tid, pos, flag, mapq, cig_off, false, cig, mem_kind, a, &st);
+    if (rc) return rc;
+  } else {
+    std::memset(&a, 0, sizeof(a));
+    a.pc = pc_of(ctx);
+  }
+  return stream_push_staged(ctx, a, st, n, n_carry, lt, lp, last, resend_tid, resend_pos);
+}
+
+int mcov_stream_push_block(mcov_ctx* ctx, const void* block, int64_t bytes, int last, int32_t* resend_tid, int32_t* resend_pos) {
+  if (!ctx) return MCOV_ERR_ARG;
+  if (ctx->state != kStreaming) return fail(ctx, MCOV_ERR_STATE, "mcov_stream_push_block: call mcov_stream_begin first");
+  CU(cudaSetDevice(ctx->device));
+  ExpandArgs a;
+  ReadStage* st = nullptr;
+  mcov_block_hdr h;
+  int rc = block_stage(ctx, block, bytes, a, &st, h);
+  if (rc) return rc;
+  return stream_push_staged(ctx, a, st, h.n, h.n_carry, h.last_tid, h.last_pos, last, resend_tid, resend_pos);
+}
+
+int mcov_depth_sorted_block(mcov_ctx* ctx, const void* block, int64_t bytes, int wait) {
+  if (!ctx) return MCOV_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  int rc = ensure_depth(ctx);
+  if (rc) return rc;
+  ExpandArgs a;
+  ReadStage* st = nullptr;
+  mcov_block_hdr h;
+  rc = block_stage(ctx, block, bytes, a, &st, h);
+  if (rc) return rc;
+  CU(cudaMemsetAsync(ctx->d_pc.p, 0, sizeof(PassCounters), ctx->stream));
+  rc = fused_depth_sorted(ctx, a);
+  if (rc) return rc;
+  ctx->n_reads_pushed = h.n;
+  rc = finish_stage(ctx, st);
+  if (rc) return rc;
+  ctx->state = kDepthReady;
+  ctx->verdict_pending = true;
+  if (!wait) return MCOV_OK;
+  PassCounters hc;
+  CU(cudaMemcpyAsync(&hc, ctx->d_pc.p, sizeof(hc), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return fused_verdict(ctx, hc);
+}
+
 int mcov_depth_sorted_packed(mcov_ctx* ctx, int64_t n, const int64_t* contig_read_start, const int32_t* pos,
                              const uint16_t* flag, const uint8_t* mapq, const uint16_t* n_cigar, const uint32_t* cig,
                              int64_t n_cig_total, int wait) {
@@ -748,9 +864,9 @@ int mcov_depth_sorted_packed(mcov_ctx* ctx, int64_t n, const int64_t* contig_rea
   CU(st.tid.ensure((size_t)std::max<int64_t>(n, 1) * 4)); CU(st.pos.ensure((size_t)std::max<int64_t>(n, 1) * 4));
   CU(st.flag.ensure((size_t)std::max<int64_t>(n, 1) * 2)); CU(st.mapq.ensure((size_t)std::max<int64_t>(n, 1)));
   CU(st.cig_off.ensure((size_t)off_len * 4)); CU(st.cig.ensure((size_t)n_cig_total * 4 + 16));
-  CU(ctx->d_end_slot.ensure((size_t)std::max<int64_t>(n, 1) * 2 + crs_bytes + 16));     // [contig_read_start | n_cigar]
+  CU(st.raw.ensure((size_t)std::max<int64_t>(n, 1) * 2 + crs_bytes + 16));     // [contig_read_start | n_cigar]
   cudaStream_t cs = ctx->copy_stream;
-  char* extra = ctx->d_end_slot.as<char>();
+  char* extra = st.raw.as<char>();
   CU(cudaMemcpyAsync(extra, contig_read_start, crs_bytes, cudaMemcpyHostToDevice, cs));
   if (n > 0) {
     CU(cudaMemcpyAsync(extra + crs_bytes, n_cigar, (size_t)n * 2, cudaMemcpyHostToDevice, cs));

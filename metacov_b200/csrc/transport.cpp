@@ -1,0 +1,215 @@
+// transport.cpp -- host side of the transport block (include/metacov_b200.h: mcov_block_hdr, mcov_pack_block).
+//
+// What the native decoder hands to the GPU for a batch of coordinate-sorted reads: one contiguous buffer, as
+// narrow as the data allows (the end-to-end rate is bound by the PCIe link).  The reference has no counterpart:
+// it walks `bam1_t` records one by one on the host (metacov/scan.pyx:243-294).
+#include <algorithm>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "metacov_b200.h"
+
+namespace {
+
+inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+struct CigKey { uint32_t n; uint32_t op[4]; };        // CIGARs of up to four ops are dictionary candidates
+inline uint64_t cig_hash(const uint32_t* ops, uint32_t n) {
+  uint64_t h = 1469598103934665603ull ^ n;
+  for (uint32_t k = 0; k < n; ++k) { h ^= ops[k]; h *= 1099511628211ull; }
+  return h;
+}
+
+constexpr int kTable = 1 << 14;                       // open-addressing table of candidate CIGARs
+
+struct Cand { CigKey key; uint64_t count; bool used; };
+
+template <typename F>
+void par_for(int64_t n, int nt, F fn) {
+  if (nt < 1) nt = 1;
+  if (n < (1 << 16)) nt = 1;
+  const int64_t per = (n + nt - 1) / nt;
+  std::vector<std::thread> th;
+  for (int t = 1; t < nt; ++t) { const int64_t a = t * per, b = std::min(n, a + per); if (a < b) th.emplace_back(fn, t, a, b); }
+  fn(0, 0, std::min(n, per));
+  for (auto& t : th) t.join();
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t mcov_block_bound(int64_t n, int64_t n_cigar, int32_t n_contigs) {
+  if (n < 0 || n_cigar < 0 || n_contigs < 0) return -1;
+  const size_t n1 = (size_t)std::max<int64_t>(n, 1);
+  return (int64_t)(al16(sizeof(mcov_block_hdr)) + al16(((size_t)n_contigs + 1) * 8) + al16(n1) /*dpos*/ + 2 * al16(n1 * 4) /*exceptions*/ +
+                   al16(n1 * 2) /*fidx or wide flags*/ + al16(512) + al16(n1) /*cclass*/ + al16(129 * 4) + al16(128 * 4 * 4) +
+                   al16((size_t)n_cigar * 4 + 16) + al16(n1) /*mapq*/ + 256);
+}
+
+int mcov_pack_block(int64_t n, int64_t n_carry, const int32_t* tid, const int32_t* pos, const uint16_t* flag,
+                    const uint8_t* mapq, const uint32_t* cig_off, const uint32_t* cig, int32_t n_contigs,
+                    void* out, int64_t cap, int64_t* bytes_out, int n_threads) {
+  if (n < 0 || n_carry < 0 || n_carry > n || n_contigs <= 0 || !out || !bytes_out || (reinterpret_cast<uintptr_t>(out) & 15u)) return MCOV_ERR_ARG;
+  if (n > 0 && (!tid || !pos || !flag || !cig_off)) return MCOV_ERR_ARG;
+  if (n >= 0xFFFFFFF0ll) return MCOV_ERR_RANGE;
+  const int64_t n_cig = n > 0 ? (int64_t)cig_off[n] : 0;
+  if (cap < mcov_block_bound(n, n_cig, n_contigs)) return MCOV_ERR_ARG;
+  if (n_threads <= 0) { unsigned hw = std::thread::hardware_concurrency(); n_threads = hw ? (int)std::min(hw, 32u) : 4; }
+  try {
+    char* base = static_cast<char*>(out);
+    mcov_block_hdr h;
+    std::memset(&h, 0, sizeof(h));
+    h.magic = MCOV_BLOCK_MAGIC; h.version = 1; h.n = n; h.n_carry = n_carry; h.n_cigar = n_cig; h.n_contigs = n_contigs;
+    h.last_tid = n > 0 ? tid[n - 1] : -1; h.last_pos = n > 0 ? pos[n - 1] : 0;
+    h.has_mapq = mapq ? 1 : 0;
+    size_t o = al16(sizeof(mcov_block_hdr));
+    // ---- contig prefix (and the check that the batch is grouped by contig, unplaced reads last) ----
+    h.off_crs = (uint32_t)o;
+    int64_t* crs = reinterpret_cast<int64_t*>(base + o);
+    o += al16(((size_t)n_contigs + 1) * 8);
+    {
+      int64_t i = 0;
+      for (int32_t c = 0; c < n_contigs; ++c) {
+        crs[c] = i;
+        while (i < n && tid[i] == c) ++i;
+      }
+      crs[n_contigs] = i;
+      for (int64_t k = i; k < n; ++k) if (tid[k] >= 0 && tid[k] < n_contigs) return MCOV_ERR_ARG;   // not grouped by contig
+    }
+    const size_t n1 = (size_t)std::max<int64_t>(n, 1);
+    // ---- positions: u8 differences + exceptions ----
+    h.off_dpos = (uint32_t)o;
+    uint8_t* dpos = reinterpret_cast<uint8_t*>(base + o);
+    o += al16(n1);
+    std::vector<std::vector<std::pair<uint32_t, int32_t>>> exc((size_t)n_threads);
+    // ---- flags: dictionary ----
+    std::vector<int32_t> fslot(65536, -1);
+    std::vector<uint16_t> fdict;
+    for (int64_t i = 0; i < n && fdict.size() <= 256; ++i) if (fslot[flag[i]] < 0) { fslot[flag[i]] = (int32_t)fdict.size(); fdict.push_back(flag[i]); }
+    h.flag_wide = fdict.size() > 256 ? 1 : 0;
+    h.off_fidx = (uint32_t)o;
+    uint8_t* fidx8 = reinterpret_cast<uint8_t*>(base + o);
+    uint16_t* fidx16 = reinterpret_cast<uint16_t*>(base + o);
+    o += al16(h.flag_wide ? n1 * 2 : n1);
+    h.off_flagdict = (uint32_t)o;
+    h.n_flagdict = h.flag_wide ? 0 : (int32_t)fdict.size();
+    if (!h.flag_wide) std::memcpy(base + o, fdict.data(), fdict.size() * 2);
+    o += al16(512);
+    // ---- CIGAR dictionary: the 128 most frequent CIGARs of up to four ops (counted on a sample of the batch) ----
+    std::vector<Cand> table(kTable);
+    for (auto& c : table) { c.used = false; c.count = 0; }
+    const int64_t step = std::max<int64_t>(1, n / 200000);
+    for (int64_t i = 0; i < n; i += step) {
+      const uint32_t nc = cig_off[i + 1] - cig_off[i];
+      if (nc == 0 || nc > 4) continue;
+      const uint32_t* ops = cig + cig_off[i];
+      uint64_t hsh = cig_hash(ops, nc);
+      for (int probe = 0; probe < 64; ++probe) {
+        Cand& c = table[(hsh + probe) & (kTable - 1)];
+        if (!c.used) { c.used = true; c.key.n = nc; std::memcpy(c.key.op, ops, nc * 4); c.count = 1; break; }
+        if (c.key.n == nc && std::memcmp(c.key.op, ops, nc * 4) == 0) { ++c.count; break; }
+      }
+    }
+    std::vector<const Cand*> top;
+    for (const auto& c : table) if (c.used) top.push_back(&c);
+    std::sort(top.begin(), top.end(), [](const Cand* a, const Cand* b) { return a->count > b->count; });
+    if (top.size() > 128) top.resize(128);
+    // lookup table of the chosen entries (same hashing)
+    std::vector<int16_t> chosen(kTable, -1);
+    std::vector<CigKey> dict;
+    for (const Cand* c : top) {
+      const uint64_t hsh = cig_hash(c->key.op, c->key.n);
+      for (int probe = 0; probe < kTable; ++probe) {
+        int16_t& slot = chosen[(hsh + probe) & (kTable - 1)];
+        if (slot < 0) { slot = (int16_t)dict.size(); break; }
+      }
+      dict.push_back(c->key);
+    }
+    auto dict_find = [&](const uint32_t* ops, uint32_t nc) -> int {
+      if (nc == 0 || nc > 4 || dict.empty()) return -1;
+      const uint64_t hsh = cig_hash(ops, nc);
+      for (int probe = 0; probe < kTable; ++probe) {
+        const int16_t slot = chosen[(hsh + probe) & (kTable - 1)];
+        if (slot < 0) return -1;
+        const CigKey& k = dict[(size_t)slot];
+        if (k.n == nc && std::memcmp(k.op, ops, nc * 4) == 0) return slot;
+      }
+      return -1;
+    };
+    h.off_cclass = (uint32_t)o;
+    uint8_t* cclass = reinterpret_cast<uint8_t*>(base + o);
+    o += al16(n1);
+    h.off_dict_off = (uint32_t)o;
+    uint32_t* dict_off = reinterpret_cast<uint32_t*>(base + o);
+    o += al16(129 * 4);
+    h.off_dict_ops = (uint32_t)o;
+    uint32_t* dict_ops = reinterpret_cast<uint32_t*>(base + o);
+    o += al16(128 * 4 * 4);
+    h.n_dict = (int32_t)dict.size();
+    {
+      uint32_t k = 0;
+      for (size_t d = 0; d < dict.size(); ++d) { dict_off[d] = k; std::memcpy(dict_ops + k, dict[d].op, dict[d].n * 4); k += dict[d].n; }
+      dict_off[dict.size()] = k;
+      h.n_dictops = (int32_t)k;
+    }
+    h.off_xops = (uint32_t)o;
+    uint32_t* xops = reinterpret_cast<uint32_t*>(base + o);
+    // ---- per-read pass (parallel): position differences, flag indices, CIGAR classes; explicit op counts per range ----
+    std::vector<int64_t> xcount((size_t)n_threads + 1, 0);
+    std::vector<int> too_long((size_t)n_threads, 0);
+    par_for(n, n_threads, [&](int t, int64_t a, int64_t b) {
+      int64_t xc = 0;
+      for (int64_t i = a; i < b; ++i) {
+        // first read of a contig (or of the unplaced tail): difference to 0
+        const bool first = i == 0 || tid[i] != tid[i - 1];
+        const int64_t d = first ? (int64_t)pos[i] : (int64_t)pos[i] - (int64_t)pos[i - 1];
+        if (d < 0 || d > 255) { dpos[i] = 0; exc[(size_t)t].emplace_back((uint32_t)i, (int32_t)d); }
+        else dpos[i] = (uint8_t)d;
+        if (h.flag_wide) fidx16[i] = flag[i]; else fidx8[i] = (uint8_t)fslot[flag[i]];
+        const uint32_t nc = cig_off[i + 1] - cig_off[i];
+        const int k = dict_find(cig + cig_off[i], nc);
+        if (k >= 0) cclass[i] = (uint8_t)k;
+        else if (nc <= 127) { cclass[i] = (uint8_t)(128 + nc); xc += nc; }
+        else { too_long[(size_t)t] = 1; cclass[i] = 128; }
+      }
+      xcount[(size_t)t + 1] = xc;
+    });
+    for (int t = 0; t < n_threads; ++t) if (too_long[(size_t)t]) return MCOV_ERR_RANGE;
+    for (int t = 0; t < n_threads; ++t) xcount[(size_t)t + 1] += xcount[(size_t)t];
+    h.n_xops = xcount[(size_t)n_threads];
+    par_for(n, n_threads, [&](int t, int64_t a, int64_t b) {
+      int64_t w = xcount[(size_t)t];
+      for (int64_t i = a; i < b; ++i) {
+        if (cclass[i] < 128) continue;
+        const uint32_t nc = cclass[i] - 128u;
+        std::memcpy(xops + w, cig + cig_off[i], (size_t)nc * 4);
+        w += nc;
+      }
+    });
+    o += al16((size_t)h.n_xops * 4 + 16);
+    // ---- exceptions ----
+    size_t n_exc = 0;
+    for (auto& v : exc) n_exc += v.size();
+    h.n_exc = (int64_t)n_exc;
+    h.off_exc_idx = (uint32_t)o;
+    uint32_t* ei = reinterpret_cast<uint32_t*>(base + o);
+    o += al16(std::max<size_t>(n_exc, 1) * 4);
+    h.off_exc_val = (uint32_t)o;
+    int32_t* ev = reinterpret_cast<int32_t*>(base + o);
+    o += al16(std::max<size_t>(n_exc, 1) * 4);
+    { size_t k = 0; for (auto& v : exc) for (auto& e : v) { ei[k] = e.first; ev[k] = e.second; ++k; } }
+    // ---- mapq ----
+    h.off_mapq = 0;
+    if (mapq) { h.off_mapq = (uint32_t)o; if (n > 0) std::memcpy(base + o, mapq, (size_t)n); o += al16(n1); }
+    if (o > (size_t)cap || o > 0xFFFFFFFFull) return MCOV_ERR_RANGE;     // (section offsets are 32-bit: a block holds < 4 GiB)
+    h.total_bytes = (int64_t)o;
+    std::memcpy(base, &h, sizeof(h));
+    *bytes_out = (int64_t)o;
+    return MCOV_OK;
+  } catch (const std::bad_alloc&) { return MCOV_ERR_NOMEM; }
+  catch (...) { return MCOV_ERR_ARG; }
+}
+
+}  // extern "C"

@@ -184,6 +184,19 @@ class CoverageEngine:
         self._check(lib.mcov_stream_resend_point(self._ctx, int(last_tid), int(last_pos), C.byref(rt), C.byref(rp)))
         return rt.value, rp.value
 
+    def depth_sorted_block(self, block, wait=True):
+        """Fused path from a transport block (``pack_block`` / the streaming reader): one host-to-device copy."""
+        buf, nbytes = block
+        self._check(lib.mcov_depth_sorted_block(self._ctx, _capi.ptr(buf), int(nbytes), 1 if wait else 0))
+
+    def stream_push_block(self, block, last=False):
+        """One batch of a streamed pass as a transport block; returns the resend point like ``stream_push``."""
+        buf, nbytes = block
+        rt, rp = C.c_int32(-1), C.c_int32(0)
+        self._check(lib.mcov_stream_push_block(self._ctx, buf if isinstance(buf, int) else _capi.ptr(buf), int(nbytes),
+                                               1 if last else 0, C.byref(rt), C.byref(rp)))
+        return rt.value, rp.value
+
     def depth_sorted_packed(self, packed, wait=True):
         """Fused path from the compact host transport (see ``pack_batch``)."""
         self._check(lib.mcov_depth_sorted_packed(
@@ -484,6 +497,35 @@ def pack_batch_delta(batch, n_contigs, with_mapq=False, pinned=False):
                 t = torch.from_numpy(out[k].view({8: np.int64, 4: np.int32, 2: np.int16, 1: np.uint8}[out[k].dtype.itemsize]))
                 out[k] = t.pin_memory()
     return out
+
+
+def pack_block(batch, n_contigs, with_mapq=False, n_carry=0, pinned=False, threads=0):
+    """Transport block of a coordinate-sorted ``ReadBatch`` (numpy or CPU torch members) -- the format the native
+    decoder hands to the GPU (mcov_pack_block: u8 position differences + exceptions, flag dictionary, CIGAR
+    dictionary + explicit ops; ONE buffer, one host-to-device copy).  Returns (buffer, n_bytes); the buffer is a
+    pinned torch uint8 tensor with ``pinned`` else a numpy array.  Raises ValueError when the batch does not qualify
+    (a CIGAR of more than 127 ops, reads not grouped by contig): ``pack_batch`` / the plain columns are the fallback."""
+    def as_np(a, dt):
+        if _is_torch(a):
+            a = a.cpu().numpy()
+        a = np.ascontiguousarray(a)
+        return a.view(dt) if a.dtype.itemsize == np.dtype(dt).itemsize else a.astype(dt)
+    tid, pos = as_np(batch.tid, np.int32), as_np(batch.pos, np.int32)
+    flag, mapq = as_np(batch.flag, np.uint16), as_np(batch.mapq, np.uint8)
+    off, cig = as_np(batch.cig_off, np.uint32), as_np(batch.cig, np.uint32)
+    n = len(tid)
+    cap = lib.mcov_block_bound(n, int(off[-1]) if n else 0, int(n_contigs))
+    if pinned:
+        import torch
+        buf = torch.empty(cap + 16, dtype=torch.uint8).pin_memory()
+    else:
+        buf = np.empty(cap + 16, dtype=np.uint8)
+    nb = C.c_int64(0)
+    rc = lib.mcov_pack_block(n, int(n_carry), _capi.ptr(tid), _capi.ptr(pos), _capi.ptr(flag), _capi.ptr(mapq) if with_mapq else None,
+                             _capi.ptr(off), _capi.ptr(cig), int(n_contigs), _capi.ptr(buf), cap, C.byref(nb), int(threads))
+    if rc != 0:
+        raise ValueError("pack_block: the batch does not qualify for the transport block (status %d)" % rc)
+    return buf, nb.value
 
 
 def packed_bytes(packed):

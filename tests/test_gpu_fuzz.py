@@ -73,7 +73,7 @@ def _case(seed):
 @pytest.mark.parametrize("block", range(6))
 def test_random_cases_match_oracle(block):
     from metacov_b200 import CoverageEngine, McovError, _capi
-    from metacov_b200.engine import pack_batch, pack_batch_delta
+    from metacov_b200.engine import pack_batch, pack_batch_delta, pack_block
     for seed in range(block * 10, block * 10 + 10):
         b, isize, lengths, (rt, rs, re), filt = _case(1000 + seed)
         of = cport.default_filter(**filt) if filt else None
@@ -81,7 +81,7 @@ def test_random_cases_match_oracle(block):
         want = cport.region_stats(d, off, lengths, rt, rs, re)
         nonempty = re > rs
         with CoverageEngine(lengths, filt=filt or None) as eng:
-            for path in ("auto", "push", "packed", "delta"):
+            for path in ("auto", "push", "packed", "delta", "block"):
                 if path == "auto":
                     eng.compute_depth(b)
                 elif path == "push":
@@ -96,6 +96,8 @@ def test_random_cases_match_oracle(block):
                     try:
                         if path == "packed":
                             eng.depth_sorted_packed(pack_batch(b, len(lengths), with_mapq=True))
+                        elif path == "block":
+                            eng.depth_sorted_block(pack_block(b, len(lengths), with_mapq=True))
                         else:
                             eng.depth_sorted_delta(pack_batch_delta(b, len(lengths), with_mapq=True))
                     except ValueError:

@@ -583,3 +583,69 @@ def test_delta_host_transport_equals_soa_path():
     b5, _ = synth.generate_host(w5)
     with pytest.raises(ValueError):
         pack_batch_delta(b5, w5.n_contigs)
+
+
+def test_block_transport_equals_soa_path():
+    """mcov_depth_sorted_block: the transport block of the native packer (one host-to-device copy: u8 position
+    differences + exceptions, flag dictionary, CIGAR dictionary + explicit ops) rebuilt on the device gives the
+    depth of the plain columns -- short reads, sparse contigs (exceptions), the fixture's unplaced tail, unsorted
+    input, a filter that needs mapq, pinned and pageable buffers, a corrupted header."""
+    from metacov_b200 import McovError, ReadBatch, _capi, synth
+    from metacov_b200.engine import pack_block
+    w = synth.c2(0.01)
+    b, _ = synth.generate_host(w)
+    with engine_for(w.contig_len) as eng:
+        blk = pack_block(b, w.n_contigs, pinned=True)
+        assert blk[1] < 4.0 * len(b.tid)
+        eng.depth_sorted_block(blk)
+        want, dflat, off, info = oracle_depth(b, w.contig_len)
+        for c, d in enumerate(full_depth(eng)):
+            assert np.array_equal(d, want[c]), c
+        pi = eng.pass_info()
+        assert pi["n_pass"] == info["n_pass"] and pi["aligned_bases"] == info["aligned_bases"] and pi["sorted"] == 1
+        eng.depth_sorted_block(blk, wait=False)                  # deferred verdict, statistics straight after
+        tid = np.arange(w.n_contigs, dtype=np.int32)
+        st = eng.region_stats(tid, np.zeros_like(tid), w.contig_len)
+        ref = cport.region_stats(dflat, off, w.contig_len, tid, np.zeros_like(tid), w.contig_len)
+        for k in ("sum", "sumsq", "iq_sum", "min", "max", "med_lo", "med_hi"):
+            assert np.array_equal(st[k], ref[k]), k
+        eng.set_filter(min_mapq=30)
+        with pytest.raises(McovError):
+            eng.depth_sorted_block(blk)                          # packed without mapq
+        eng.depth_sorted_block(pack_block(b, w.n_contigs, with_mapq=True))
+        want30, _, _, _ = oracle_depth(b, w.contig_len, min_mapq=30)
+        assert np.array_equal(eng.copy_depth(0), want30[0])
+        bad = np.array(blk[0].numpy()[:blk[1]], copy=True)
+        bad[0] ^= 0xFF                                           # magic
+        with pytest.raises(McovError):
+            eng.depth_sorted_block((bad, len(bad)))
+        with pytest.raises(McovError):
+            eng.depth_sorted_block((blk[0], blk[1] - 64))        # shorter than the header says
+    # another contig table: refused
+    with engine_for(w.contig_len[:-1]) as eng:
+        with pytest.raises(McovError):
+            eng.depth_sorted_block(blk)
+    rng = np.random.default_rng(8)
+    lengths = np.array([3_000_000, 500_000, 2_000_000], np.int32)
+    tid = np.repeat(np.arange(3, dtype=np.int32), [40, 5, 30])
+    pos = np.concatenate([np.sort(rng.integers(100_000, l - 200, k)) for l, k in zip(lengths, (40, 5, 30))]).astype(np.int32)
+    n = len(tid)
+    sb = ReadBatch(tid, pos, np.zeros(n, np.uint16), np.full(n, 60, np.uint8), np.arange(n + 1, dtype=np.uint32),
+                   np.full(n, 150 << 4, np.uint32))
+    with engine_for(lengths) as eng:
+        eng.depth_sorted_block(pack_block(sb, 3))
+        wants, _, _, _ = oracle_depth(sb, lengths)
+        for c in range(3):
+            assert np.array_equal(eng.copy_depth(c), wants[c]), c
+        ub = ReadBatch(tid, pos[::-1].copy(), sb.flag, sb.mapq, sb.cig_off, sb.cig)
+        with pytest.raises(McovError) as ei:
+            eng.depth_sorted_block(pack_block(ub, 3))
+        assert ei.value.code == _capi.MCOV_ERR_UNSORTED
+    z, fb = load_soa("fixture_soa.npz")
+    with engine_for(z["lengths"]) as eng:
+        eng.depth_sorted_block(pack_block(fb, 2, pinned=True))
+        wantf, _, _, _ = oracle_depth(fb, z["lengths"])
+        assert np.array_equal(eng.copy_depth(1), wantf[1]) and eng.pass_info()["n_pass"] == 3350
+        empty = ReadBatch(*(np.zeros(0, a.dtype) for a in (fb.tid, fb.pos, fb.flag, fb.mapq)), np.zeros(1, np.uint32), np.zeros(0, np.uint32))
+        eng.depth_sorted_block(pack_block(empty, 2))
+        assert eng.pass_info()["n_pass"] == 0 and not eng.copy_depth(0).any()

@@ -98,3 +98,95 @@ def test_partition_positions_covers_every_base_once():
             for r in range(n):
                 ci, ctid, cst, cen = plan.arrays("cut", r)
                 assert np.all(cen > cst)
+
+
+def _unpack_block(buf):
+    """The transport block (include/metacov_b200.h: mcov_block_hdr) decoded in numpy: what k_block_seed /
+    k_delta_patch / the prefix sums / k_block_finish rebuild on the device."""
+    import struct
+    raw = np.asarray(buf, dtype=np.uint8)
+    (magic, version, n, n_carry, n_cigar, n_exc, n_xops, total, n_contigs, n_fd, n_dict, n_dictops, flag_wide, has_mapq,
+     last_tid, last_pos, o_crs, o_dpos, o_ei, o_ev, o_fidx, o_fd, o_cc, o_doff, o_dops, o_xops, o_mapq, _r) = struct.unpack_from(
+        "<IIqqqqqqiiiiiiiiIIIIIIIIIIII", raw.tobytes()[:160])
+    assert magic == 0x4256434D and version == 1 and total <= len(raw)
+    view = lambda off, cnt, dt: raw[off:off + cnt * np.dtype(dt).itemsize].view(dt)
+    crs = view(o_crs, n_contigs + 1, np.int64)
+    d = view(o_dpos, n, np.uint8).astype(np.int64)
+    d[view(o_ei, n_exc, np.uint32)] = view(o_ev, n_exc, np.int32)
+    S = np.cumsum(d)
+    pos = np.empty(n, np.int64)
+    tid = np.full(n, -1, np.int32)
+    for c, (a, b) in enumerate(list(zip(crs[:-1], crs[1:])) + [(crs[-1], n)]):
+        if b > a:
+            pos[a:b] = S[a:b] - (S[a - 1] if a > 0 else 0)
+            tid[a:b] = c if c < n_contigs else -1
+    flag = view(o_fidx, n, np.uint16) if flag_wide else view(o_fd, 256, np.uint16)[view(o_fidx, n, np.uint8)]
+    cc = view(o_cc, n, np.uint8).astype(np.int64)
+    doff = view(o_doff, n_dict + 1, np.uint32).astype(np.int64)
+    dops, xops = view(o_dops, n_dictops, np.uint32), view(o_xops, n_xops, np.uint32)
+    cig, ncig, x = [], np.zeros(n, np.int64), 0
+    for i in range(n):
+        if cc[i] < 128:
+            cig.append(dops[doff[cc[i]]:doff[cc[i] + 1]])
+        else:
+            cig.append(xops[x:x + cc[i] - 128]); x += cc[i] - 128
+        ncig[i] = len(cig[-1])
+    assert x == n_xops and int(ncig.sum()) == n_cigar
+    mapq = view(o_mapq, n, np.uint8) if has_mapq else None
+    return dict(n=n, n_carry=n_carry, tid=tid, pos=pos.astype(np.int64), flag=flag, ncig=ncig, mapq=mapq,
+                cig=np.concatenate(cig) if cig else np.zeros(0, np.uint32), last=(last_tid, last_pos), n_exc=n_exc, flag_wide=flag_wide)
+
+
+def test_block_packer_round_trip():
+    """mcov_pack_block (native): the block decodes to the columns it was packed from -- short reads, the fixture with
+    its unplaced tail, gaps beyond 8 bits (exceptions), negative differences, more than 256 distinct flags."""
+    from metacov_b200 import ReadBatch, synth
+    from metacov_b200.engine import pack_block
+
+    def check(b, n_contigs, **kw):
+        buf, nb = pack_block(b, n_contigs, **kw)
+        u = _unpack_block(buf[:nb])
+        valid = (b.tid >= 0) & (b.tid < n_contigs)
+        assert np.array_equal(u["tid"][valid], b.tid[valid]) and np.all(u["tid"][~valid] == -1)
+        assert np.array_equal(u["pos"], b.pos.astype(np.int64)) and np.array_equal(u["flag"], b.flag)
+        assert np.array_equal(u["ncig"], np.diff(b.cig_off.astype(np.int64))) and np.array_equal(u["cig"], b.cig)
+        if kw.get("with_mapq"):
+            assert np.array_equal(u["mapq"], b.mapq)
+        if len(b.tid):
+            assert u["last"] == (int(b.tid[-1]), int(b.pos[-1]))
+        return u, nb
+
+    w = synth.c2(0.01)
+    b, _ = synth.generate_host(w)
+    u, nb = check(b, w.n_contigs, with_mapq=False, n_carry=17)
+    assert nb / len(b.tid) < 4.0 and u["n_carry"] == 17 and u["n_exc"] == 0
+    check(b, w.n_contigs, with_mapq=True, threads=3)
+    z, fb = load_soa("fixture_soa.npz")
+    check(fb, 2, with_mapq=True)
+    rng = np.random.default_rng(4)
+    for trial in range(12):
+        nc = int(rng.integers(1, 6))
+        n = int(rng.integers(0, 3000))
+        tid = np.sort(rng.integers(0, nc, n)).astype(np.int32)
+        if n > 10 and trial % 3 == 0:
+            tid[-5:] = -1
+        pos = rng.integers(-100, 5_000_000 if trial % 2 else 3000, n).astype(np.int32)
+        if trial % 4:
+            for c in range(-1, nc):
+                m = tid == c
+                pos[m] = np.sort(pos[m])
+        flag = rng.integers(0, 4096 if trial % 5 else 65536, n).astype(np.uint16) if trial % 2 else rng.choice(np.array([99, 147, 83, 163, 4], np.uint16), n)
+        n_op = rng.integers(0, 7, n)
+        off = np.concatenate(([0], np.cumsum(n_op))).astype(np.uint32)
+        cig = ((rng.integers(1, 200, int(off[-1])).astype(np.uint32) << 4) | rng.integers(0, 9, int(off[-1])).astype(np.uint32))
+        rb = ReadBatch(tid, pos, flag, rng.integers(0, 61, n).astype(np.uint8), off, cig)
+        u, _ = check(rb, nc, with_mapq=True)
+        if n > 600 and trial % 2 and trial % 5:
+            assert u["flag_wide"] == 1
+    # what does not qualify
+    w5 = synth.c5(0.0005)
+    b5, _ = synth.generate_host(w5)
+    with pytest.raises(ValueError):
+        pack_block(b5, w5.n_contigs)
+    with pytest.raises(ValueError):
+        pack_block(ReadBatch(b.tid[::-1].copy(), b.pos, b.flag, b.mapq, b.cig_off, b.cig), w.n_contigs)   # not grouped by contig
