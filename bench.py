@@ -90,6 +90,36 @@ def make_workload(name, scale, n_ranks):
     return w
 
 
+def workload_label(name, n_ranks, w):
+    """config.workload: the same string in both arms (the driver compares it)."""
+    return "%s x%d ranks: %s" % (name, n_ranks, w.describe())
+
+
+def pin_rank_to_cores(local, world):
+    """One rank per GPU: give every rank its own slice of the host cores (and thereby of the memory controllers its
+    pinned buffers are first touched from) instead of letting all ranks share the default affinity mask -- the GPU's own
+    NUMA-local cores when NVML knows them."""
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+        near = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(cpus) // 64) + 1)
+            near = [c for c in cpus if (words[c // 64] >> (c % 64)) & 1]
+        except Exception:
+            near = None
+        pool = near if near and len(near) >= world else cpus
+        per = max(1, len(pool) // world)
+        mine = pool[(local * per) % len(pool):(local * per) % len(pool) + per]
+        if mine:
+            os.sched_setaffinity(0, mine)
+        return {"cores": len(mine), "first": mine[0] if mine else None, "numa_local": bool(near and pool is near)}
+    except Exception as e:                       # affinity is an optimisation, never a requirement
+        return {"error": str(e)}
+
+
 def cpu_port_time(batch, lengths, regions, threads, reps=2):
     """The C restatement (oracle/coverage.c), contig-parallel: depth + per-contig statistics."""
     from oracle import cport
@@ -130,21 +160,25 @@ def python_port_rate(batch, lengths, max_contigs=1):
 
 
 def run_reference(args):
-    """--impl reference: the CPU implementation of the path on the host cores (the reference itself
-    needs pysam/htslib, absent from this image, so this is the C port of oracle/, kind 'port')."""
+    """--impl reference: the CPU implementation of the path on the host cores (the reference itself needs
+    pysam/htslib, absent from this image, so this is the C port of oracle/, kind 'port').  Same workload as the GPU
+    arm at the same N (N x the named shape); built with the oracle-side generator, so this process never loads the
+    product library.  A step = the whole workload; the number of timed steps is bounded so that the run ends within
+    a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from metacov_b200 import synth
-    w = make_workload(args.workload, args.scale, 1)
+    from oracle import cport, synthgen
+    cport.build()
+    w = synthgen.WORKLOADS[args.workload](args.scale * args.gpus)
     cores = os.cpu_count() or 1
-    batch, _ = synth.generate_host(w)
+    batch, _ = synthgen.generate(w, threads=cores)
     tid = np.arange(w.n_contigs, dtype=np.int32)
     regions = (tid, np.zeros_like(tid), w.contig_len)
-    from oracle import cport
-    cport.build()
     times = []
     aligned = 0
+    budget_s, t_begin = 150.0, time.perf_counter()
+    steps_done = 0
     for k in range(args.warmup + args.steps):
         t0 = time.perf_counter()
         d, off, info = cport.depth(batch, w.contig_len, mode="par", threads=cores)
@@ -153,16 +187,20 @@ def run_reference(args):
         aligned = info["aligned_bases"]
         if k >= args.warmup:
             times.append(dt)
+            steps_done += 1
+            if time.perf_counter() - t_begin > budget_s and steps_done >= 2:
+                break
     ms = 1e3 * float(np.mean(times))
     value = aligned / (ms / 1e3)
     py_rate, py_n = python_port_rate(batch, w.contig_len, 1)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "steps": steps_done, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": "%s: %s" % (args.workload, w.describe()), "scale": args.scale},
+        "config": {"workload": workload_label(args.workload, args.gpus, w), "scale": args.scale},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "full %s workload per step (C port oracle/coverage.c, contig-parallel pthreads)" % args.workload,
+                         "sample": "the whole %s workload per step (C port oracle/coverage.c, contig-parallel pthreads); %d of the %d "
+                                   "requested steps timed (time budget %d s)" % (args.workload, steps_done, args.steps, int(budget_s)),
                          "python_port_value": py_rate,
                          "python_port_sample": "first contig (%d reads) through the reference-structured Python loop, 1 core" % py_n},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -178,6 +216,86 @@ def batch_bytes(b):
     return int(tot)
 
 
+def strong_scaling_c4(args, sharding, synth, dist, torch, world, rank, local, dev, barrier):
+    """BASELINE config 4 (1 B x 150 bp reads, 100 k contigs), the SAME total work at every N: contiguous contig ranges
+    balanced on cost, each rank generates and processes its range, one all-gather of the 64-byte records per pass.
+    Reported beside the weak-scaling `value` so that N = 1 keeps agreeing with the single-GPU bench line."""
+    from metacov_b200 import CoverageEngine
+    torch.cuda.empty_cache()
+    w = synth.WORKLOADS["c4"](args.strong_scale)
+    rpc = np.diff(w.read_start)
+    bounds = sharding.partition_contigs(w.contig_len, rpc, world)
+    c0, c1 = int(bounds[rank]), int(bounds[rank + 1])
+    r0, r1 = sharding.shard_read_range(w.read_start, bounds, rank)
+    lengths = w.contig_len[c0:c1]
+    dbatch, _ = synth.generate_device(w, local, i0=r0, n=r1 - r0, tid_base=c0)
+    g = c1 - c0
+    reg_tid = np.arange(g, dtype=np.int32)
+    reg_start, reg_end = np.zeros(g, dtype=np.int32), lengths.astype(np.int32)
+    stream = torch.cuda.current_stream(dev)
+    eng = CoverageEngine(lengths, device=local, stream=stream.cuda_stream)
+    owner = sharding.assign_regions(np.arange(w.n_contigs), bounds)
+    dg = sharding.DeviceGather(owner, world, dev) if world > 1 else None
+
+    def run(k):
+        prev = None
+        for i in range(k):
+            eng.depth_sorted(dbatch, wait=False)
+            if world > 1:
+                eng.region_stats_enqueue(reg_tid, reg_start, reg_end, dg.local[i & 1])
+                dg.submit(i & 1, want_host=(rank == 0))
+                if prev is not None:
+                    dg.collect(prev, want_host=(rank == 0))
+                prev = i & 1
+            else:
+                t = eng.region_stats_submit(reg_tid, reg_start, reg_end, slot=i & 1)
+                if prev is not None:
+                    eng.region_stats_collect(prev, copy=False)
+                prev = t
+        return dg.collect(prev, want_host=(rank == 0)) if world > 1 else eng.region_stats_collect(prev, copy=False)
+
+    run(3)
+    info = eng.pass_info()
+    al = torch.tensor([info["aligned_bases"]], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(al)
+    steps = max(5, min(args.steps, 20))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = run(steps)
+    e1.record()
+    barrier()
+    mine = e0.elapsed_time(e1) / steps
+    t_all = torch.zeros(world, dtype=torch.float64, device=dev)
+    t_all[rank] = mine
+    if world > 1:
+        dist.all_reduce(t_all)
+    per_rank = [float(x) for x in t_all.tolist()]
+    ms = max(per_rank)
+    # gather cost alone (the one collective of the path)
+    gather_ms = None
+    if world > 1:
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(10):
+            dg.submit(i & 1, want_host=(rank == 0))
+            dg.collect(i & 1, want_host=(rank == 0))
+        torch.cuda.synchronize()
+        gather_ms = 1e3 * (time.perf_counter() - t0) / 10
+    if rank == 0 and out is not None and world == 1:
+        assert int(np.asarray(out["sum"], dtype=np.int64).sum()) == int(al.item()), "strong-scaling block: mass conservation violated"
+    res = {"workload": "c4 (strong): %s, contig-range sharded over %d rank(s)" % (w.describe(), world),
+           "ms_per_pass": ms, "value": int(al.item()) / (ms / 1e3), "unit": UNIT, "steps": steps,
+           "per_rank_ms": per_rank, "imbalance": (max(per_rank) / (sum(per_rank) / len(per_rank))) if per_rank else None,
+           "gather_ms": gather_ms, "reads_total": int(w.n_reads), "reads_per_rank": int(r1 - r0),
+           "timing": "CUDA events around the pipelined passes on each rank, max over ranks"}
+    eng.close()
+    del dbatch
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -190,6 +308,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = pin_rank_to_cores(local, world) if world > 1 else None      # before any pinned allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -242,6 +361,13 @@ def run_ours(args):
         eng.region_stats_enqueue(reg_tid, reg_start, reg_end, local_dev)
         return dg.gather(want_host=(rank == 0))
 
+    # the first statistics call builds the region plan (chunk / slice tables, sorted tasks: host work + small copies),
+    # cached for every later call with the same regions; its cost is reported, not hidden in the warm-up
+    torch.cuda.synchronize()
+    t_first = time.perf_counter()
+    stats = step(dbatch)
+    torch.cuda.synchronize()
+    first_call_ms = 1e3 * (time.perf_counter() - t_first)
     for _ in range(max(args.warmup, 3)):
         stats = step(dbatch)
     if args.breakdown:
@@ -342,26 +468,34 @@ def run_ours(args):
     eng.profile(False)
 
     # ---- e2e: host (pinned) buffers through the public API, H2D + D2H inside the timed region ------
-    # The host side hands over what a BAM decoder produces for a sorted file: the compact transport
-    # (per-contig read prefix, u16 op counts, no mapq under the default filter) -- see pack_batch.
+    # The host side hands over what the product's decoder produces for a sorted file: the TRANSPORT BLOCK
+    # (mcov_bam_stream_next_block -> mcov_pack_block: one contiguous pinned buffer per batch, one host-to-device
+    # copy).  The block is packed here once, outside the timed region, by that same native packer (its time is
+    # reported as pack_ms); `plain_soa` is the same step from the plain pinned SoA columns, `from_bam` the whole
+    # way from the compressed file.
     e2e = None
     hbatch = None
     if not args.no_e2e:
-        from metacov_b200.engine import pack_batch, pack_batch_delta, packed_bytes
+        from metacov_b200.engine import pack_batch, pack_block, packed_bytes
         hbatch = ReadBatch(*[t.cpu() for t in dbatch])
-        # the narrowest transport the batch qualifies for: u16 position differences, u8 op counts, u16 ops
-        # (short reads); long reads (config C5: thousands of ops per CIGAR) take the u32 / u16-count form
+        t_pack = time.perf_counter()
         try:
-            packed = pack_batch_delta(hbatch, g, with_mapq=False, pinned=True)
-            transport = "delta (contig prefix, u16 position differences + exceptions, u8 op counts, u16 ops, no mapq)"
-            depth_packed = eng.depth_sorted_delta
+            blk = pack_block(hbatch, g, with_mapq=False, pinned=True)
+            pack_ms = 1e3 * (time.perf_counter() - t_pack)
+            transport = ("transport block of the product decoder (mcov_pack_block: contig prefix, u8 position differences + "
+                         "exceptions, flag dictionary, CIGAR dictionary + explicit ops, no mapq): ONE pinned buffer, ONE H2D copy")
+            depth_packed = lambda wait=False: eng.depth_sorted_block(blk, wait=wait)
+            h2d_bytes = int(blk[1])
         except ValueError:
+            # long reads (config C5: thousands of ops per CIGAR) do not qualify: compact columns instead
             packed = pack_batch(hbatch, g, with_mapq=False, pinned=True)
-            transport = "compact (contig prefix, u16 op counts, no mapq)"
-            depth_packed = eng.depth_sorted_packed
+            pack_ms = 1e3 * (time.perf_counter() - t_pack)
+            transport = "compact columns (contig prefix, u16 op counts, no mapq)"
+            depth_packed = lambda wait=False: eng.depth_sorted_packed(packed, wait=wait)
+            h2d_bytes = packed_bytes(packed)
 
         def e2e_step():
-            depth_packed(packed, wait=False)
+            depth_packed(False)
             if world == 1:
                 return eng.region_stats(reg_tid, reg_start, reg_end)
             eng.region_stats_enqueue(reg_tid, reg_start, reg_end, local_dev)
@@ -380,10 +514,12 @@ def run_ours(args):
             return float(d_t.item())
 
         for _ in range(2):
-            e2e_step()
+            st_e2e = e2e_step()
+        if world == 1:
+            assert int(np.asarray(st_e2e["sum"], dtype=np.int64).sum()) == aligned_total, "e2e path: mass conservation violated"
         # pipelined like the device-resident run: the copy of batch k+1 overlaps the kernels of batch k
-        run_steps(2, lambda: depth_packed(packed, wait=False))
-        dt = timed(lambda: run_steps(args.e2e_steps, lambda: depth_packed(packed, wait=False)), 1) / args.e2e_steps
+        run_steps(2, lambda: depth_packed(False))
+        dt = timed(lambda: run_steps(args.e2e_steps, lambda: depth_packed(False)), 1) / args.e2e_steps
         dt_sync = timed(e2e_step, args.e2e_steps)
         # for comparison: the plain SoA columns (tid[], u32 offsets, mapq) from pinned memory
         pbatch = ReadBatch(*[t.pin_memory() for t in hbatch])
@@ -398,12 +534,70 @@ def run_ours(args):
         soa_step()
         dt_soa = timed(soa_step, args.e2e_steps)
         e2e = {"value": aligned_total / dt, "unit": UNIT,
-               "h2d_bytes_per_step": packed_bytes(packed) + g * 16, "d2h_bytes_per_step": g * 64 + 64,
+               "h2d_bytes_per_step": h2d_bytes + g * 16, "d2h_bytes_per_step": g * 64 + 64,
                "ms_per_step": 1e3 * dt, "unpipelined_ms_per_step": 1e3 * dt_sync,
                "bytes_scope": "per rank (every rank copies its own shard; multiply by n_gpus for the whole job)" if world > 1 else "whole job",
-               "transport": transport,
+               "transport": transport, "pack_ms": pack_ms,
                "plain_soa": {"value": aligned_total / dt_soa, "h2d_bytes_per_step": batch_bytes(pbatch) + g * 16,
                              "ms_per_step": 1e3 * dt_soa}}
+        # ---- the whole way from the compressed FILE (rank 0 at N = 1): BGZF inflate + record parsing on the host cores in
+        # batches (mcov_bam_stream_*), transport blocks, streamed fused pass (mcov_stream_push_block), statistics.
+        if world == 1 and not args.no_bam:
+            import tempfile
+            n_bam = int(min(n_reads, args.bam_reads))
+            wb = synth.WORKLOADS[args.workload](args.scale * n_bam / max(n_reads, 1))
+            hb, isz = synth.generate_host(wb)
+            if len(hb.tid) and int(np.diff(hb.cig_off.astype(np.int64)).max()) < 65536:
+                tmp = tempfile.mkdtemp(prefix="mcov_bench_")
+                path = os.path.join(tmp, "bench.bam")
+                synth.write_bam(path, wb, hb, isz)
+                from metacov_b200 import AlignmentFile
+                rt_ = np.arange(wb.n_contigs, dtype=np.int32)
+                best, batches, al_b = None, 0, 0
+                for _ in range(3):
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    with AlignmentFile(path, device=local, batch_reads=args.bam_batch) as af:
+                        e2 = af.coverage_engine()
+                        sb = e2.region_stats(rt_, np.zeros_like(rt_), wb.contig_len)
+                        al_b = e2.pass_info()["aligned_bases"]
+                        batches = af.stream_batches
+                    dtb = time.perf_counter() - t0
+                    best = dtb if best is None else min(best, dtb)
+                assert int(np.asarray(sb["sum"], dtype=np.int64).sum()) == al_b
+                e2e["from_bam"] = {"value": al_b / best, "unit": UNIT, "reads": int(len(hb.tid)), "bam_bytes": os.path.getsize(path),
+                                   "ms_total": 1e3 * best, "batches": int(batches), "batch_reads": int(args.bam_batch),
+                                   "host_cores": os.cpu_count(),
+                                   "what": "open + BGZF inflate + record parsing on the host cores, batch by batch into pinned buffers, "
+                                           "transport blocks, streamed fused pass, per-contig statistics; best of 3 (page cache warm)"}
+                # the same file decoded ON THE GPU (mcov_bam_decode_gpu: the compressed image over PCIe, inflate + record
+                # parsing on the device); file read and the copy of the image included, like for like with the host leg
+                try:
+                    bestg = None
+                    for _ in range(3):
+                        torch.cuda.synchronize()
+                        t0 = time.perf_counter()
+                        with AlignmentFile(path, device=local, decode="gpu") as af:
+                            e2 = af.coverage_engine()
+                            sg = e2.region_stats(rt_, np.zeros_like(rt_), wb.contig_len)
+                            al_g = e2.pass_info()["aligned_bases"]
+                        dtg = time.perf_counter() - t0
+                        bestg = dtg if bestg is None else min(bestg, dtg)
+                    assert sg.tobytes() == sb.tobytes() and al_g == al_b, "GPU-decoded file gives other records than the host-decoded one"
+                    e2e["from_bam"]["gpu_decode"] = {"value": al_b / bestg, "ms_total": 1e3 * bestg,
+                                                     "what": "file read + image H2D (pageable) + BGZF inflate and record parsing on the "
+                                                             "GPU + fused pass + statistics; records identical to the host-decoded leg"}
+                except Exception as e:                       # (reported, not fatal: the headline legs stand without it)
+                    e2e["from_bam"]["gpu_decode"] = {"error": str(e)[:200]}
+                try:
+                    os.remove(path); os.remove(path + ".bai"); os.rmdir(tmp)
+                except OSError:
+                    pass
+
+    # ---- strong scaling on the 1 B-read config C4, contig-range sharded over the N ranks (north_star) -----------------
+    strong = None
+    if not args.no_strong:
+        strong = strong_scaling_c4(args, sharding, synth, dist, torch, world, rank, local, dev, barrier)
 
     if rank != 0:
         if world > 1:
@@ -441,7 +635,7 @@ def run_ours(args):
     # measured DRAM traffic of the dominant kernel (dram__bytes_read+write from the committed ncu capture);
     # only quoted for the workload it was captured on
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_z_traffic_c2.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic_c2.json")
     if args.workload == "c2" and args.scale == 1.0 and os.path.exists(tpath):
         with open(tpath) as fh:
             traffic = json.load(fh)["dram_bytes_per_launch"].get(dom)
@@ -480,7 +674,7 @@ def run_ours(args):
         "metric": METRIC, "value": aligned_total / (ms_step / 1e3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": "%s x%d ranks: %s" % (args.workload, world, w.describe()), "scale": args.scale,
+        "config": {"workload": workload_label(args.workload, world, w), "scale": args.scale,
                    "path": ("fused sorted path (k_fused_prep, k_fused_tile)" if args.path == "fused" else
                             "push path (memset, k_expand, k_scan_inplace): the any-order formulation"),
                    "per_gpu": {"reads": n_reads, "contigs": g, "slots": int(slots)},
@@ -494,7 +688,8 @@ def run_ours(args):
                                   "as N=1, with the NCCL all-gather of the records inside the pipeline (two DeviceGather slots)"},
         "unpipelined_ms_per_step": ms_sync,
         "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "aligned_bases_per_step": aligned_total,
+        "aligned_bases_per_step": aligned_total, "strong_scaling": strong,
+        "region_plan_first_call_ms": first_call_ms, "rank_affinity": affinity,
     }
     emit(args.real_stdout, line)
     if world > 1:
@@ -531,6 +726,11 @@ def _main(real_stdout):
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the named workload per GPU")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-bam", action="store_true", help="skip the from-the-BAM-file leg of e2e")
+    ap.add_argument("--bam-reads", type=int, default=2_000_000, help="reads written to the synthetic BAM of the from-file leg")
+    ap.add_argument("--bam-batch", type=int, default=1 << 19, help="records per batch of the streamed from-file pass")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling block (config C4 sharded over the ranks)")
+    ap.add_argument("--strong-scale", type=float, default=1.0, help="fraction of config C4 (1 B reads) used by the strong-scaling block")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="print a host-side time breakdown of one step to stderr")
     args = ap.parse_args()

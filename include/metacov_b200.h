@@ -524,6 +524,12 @@ int64_t mcov_bam_stream_records(const mcov_bam_stream* s);   /* distinct records
 int  mcov_bam_stream_next_block(mcov_bam_stream* s, int32_t resend_tid, int32_t resend_pos, int with_mapq,
                                 const void** block, int64_t* bytes, mcov_bam_batch* out);
 
+/* BAM writer (bench / test support): SoA columns -> BGZF-compressed BAM (+ the metadata-only .bai the
+ * coverage path reads); names "r<i>", pseudo-random ACGT bases, no qualities.  level: zlib level. */
+int  mcov_bam_write(const char* path, int32_t n_ref, const char* const* ref_name, const int32_t* ref_len, int64_t n,
+                    const int32_t* tid, const int32_t* pos, const uint16_t* flag, const uint8_t* mapq,
+                    const uint32_t* cig_off, const uint32_t* cig, const int32_t* isize, int level, int n_threads);
+
 /* ---- synthetic workloads (bench / test support; include/mcov_synth.h) ---- */
 
 struct mcov_synth_params;

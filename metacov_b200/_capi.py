@@ -187,6 +187,7 @@ SIGNATURES = {
     "mcov_bam_stream_next": (C.c_int, [_vp, _i32, _i32, C.POINTER(BamBatch)]),
     "mcov_bam_stream_records": (_i64, [_vp]),
     "mcov_bam_stream_next_block": (C.c_int, [_vp, _i32, _i32, C.c_int, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(BamBatch)]),
+    "mcov_bam_write": (C.c_int, [C.c_char_p, _i32, C.POINTER(C.c_char_p), _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int]),
     "mcov_synth_gen_ncigar": (C.c_int, [C.POINTER(SynthParams), _i64, _i64, _vp, C.c_int, _vp]),
     "mcov_synth_gen_reads": (C.c_int, [C.POINTER(SynthParams), _i64, _i64, _vp, _vp, _i32, _i32, _vp,
                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp]),

@@ -150,10 +150,17 @@ class AlignmentFile:
         self._index_stats = None
         self._batch_reads = int(kw.get("batch_reads", 1 << 21))     # records per batch of the streamed depth pass
         self.stream_batches = 0
+        self._h = None
+        self._stream = None
         if decode == "gpu":
             self._open_gpu(filename, device)
             return
-        self._open_host(filename)
+        # host decode: only the header is read here (streaming reader: the first blocks of the file); the records are
+        # streamed batch by batch by coverage_engine(), or loaded whole by soa() for the callers that need every column
+        self._stream = BamStream(filename, batch_reads=self._batch_reads)
+        self.references, self.lengths, self.text = self._stream.references, self._stream.lengths, self._stream.text
+        self.nreferences = len(self.references)
+        self._tid = {name: i for i, name in enumerate(self.references)}
 
     def _open_gpu(self, filename, device):
         from . import bamgpu
@@ -212,6 +219,9 @@ class AlignmentFile:
         if getattr(self, "_h", None):
             lib.mcov_bam_close(self._h)
             self._h = None
+        if getattr(self, "_stream", None) is not None:
+            self._stream.close()
+            self._stream = None
         self._soa = None
 
     __del__ = close
@@ -261,6 +271,7 @@ class AlignmentFile:
         if self._soa is None and self._gpu is not None:
             self._soa = {c: self._gpu[1].to_host(c) for c, _ in self._gpu[1].COLS}
         if self._soa is None:
+            self._host_handle()
             rc = lib.mcov_bam_load(self._h, 0)
             if rc != 0:
                 raise McovError(rc, "BAM record decode failed")
@@ -383,7 +394,10 @@ class AlignmentFile:
             eng = CoverageEngine(self.lengths, device=self._device, filt=self._filter_kw)
             path = None
             try:
-                with BamStream(self.filename, batch_reads=self._batch_reads) as st:
+                st, self._stream = self._stream, None           # the reader opened for the header, not yet advanced
+                if st is None:
+                    st = BamStream(self.filename, batch_reads=self._batch_reads)
+                with st:
                     self.stream_batches = stream_depth(eng, st)
                 eng.pass_info()                                  # delivers the verdict of the stream
                 path = "fused"

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -526,15 +527,27 @@ bool stream_alloc_set(mcov_bam_stream::Set& s, int64_t reads, int64_t ops) {
 
 // Read the next chunk of the file and inflate every complete BGZF block of it (in parallel) onto the end of `data`.
 // Returns false on a malformed file.
+struct StreamTimer {
+  const char* what; std::chrono::steady_clock::time_point t0;
+  explicit StreamTimer(const char* w) : what(w), t0(std::chrono::steady_clock::now()) {}
+  ~StreamTimer() {
+    static const bool on = std::getenv("MCOV_STREAM_DEBUG") != nullptr;
+    if (on) std::fprintf(stderr, "[stream] %-10s %.1f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  }
+};
+
 bool stream_refill(mcov_bam_stream* s) {
   if (s->eof) return true;
+  StreamTimer tm("refill");
   // drop what has been parsed
   if (s->data_pos > 0) { s->data.erase(s->data.begin(), s->data.begin() + (ptrdiff_t)s->data_pos); s->data_pos = 0; }
+  // (the first read is small: opening a file should cost no more than its header)
+  const size_t want = s->header_done ? kStreamChunk : (size_t)256 << 10;
   const size_t old = s->raw.size();
-  s->raw.resize(old + kStreamChunk);
-  const size_t got = std::fread(s->raw.data() + old, 1, kStreamChunk, s->fh);
+  s->raw.resize(old + want);
+  const size_t got = std::fread(s->raw.data() + old, 1, want, s->fh);
   s->raw.resize(old + got);
-  if (got < kStreamChunk) s->eof = true;
+  if (got < want) s->eof = true;
   // index the complete blocks
   std::vector<Block> blocks;
   size_t off = 0, uoff = 0;
@@ -680,6 +693,7 @@ static int stream_next_impl(mcov_bam_stream* s, int32_t resend_tid, int32_t rese
   s->rec_off.clear();
   int64_t new_ops = 0;
   bool at_end = false;
+  StreamTimer tm_all("next");
   while ((int64_t)s->rec_off.size() < s->batch_reads) {
     const size_t avail = s->data.size() - s->data_pos;
     bool have = false;
@@ -710,6 +724,7 @@ static int stream_next_impl(mcov_bam_stream* s, int32_t resend_tid, int32_t rese
   }
   if (!at_end && s->eof && s->data_pos == s->data.size()) at_end = true;
   const int64_t n_new = (int64_t)s->rec_off.size();
+  StreamTimer tm_rest("carry+fill");
   // ---- carry: reads of the previous batch that start at or after the resend point or reach past it ----
   int64_t c_lo = prev.n;                                      // carry candidates are prev[c_lo, prev.n): a suffix in sorted order
   if (resend_tid >= 0 && prev.n > 0) {
@@ -855,3 +870,172 @@ int mcov_bam_stream_next_block(mcov_bam_stream* s, int32_t resend_tid, int32_t r
 }
 
 }  // extern "C"
+
+// ===========================================================================================================
+// BAM writer (bench / test support): SoA columns -> a BGZF-compressed BAM + the metadata-only BAI the coverage
+// path reads (`mapped` / `unmapped`).  Read names are "r<index>", SEQ is pseudo-random ACGT (so that the file
+// compresses like sequence data, not like padding), QUAL is 0xff (absent).  Blocks are deflated in parallel.
+// The reference has no writer on this path; its fixtures were made by samtools.
+// ===========================================================================================================
+namespace {
+
+inline void put32(std::vector<uint8_t>& v, uint32_t x) { v.push_back((uint8_t)x); v.push_back((uint8_t)(x >> 8)); v.push_back((uint8_t)(x >> 16)); v.push_back((uint8_t)(x >> 24)); }
+inline void put16(std::vector<uint8_t>& v, uint16_t x) { v.push_back((uint8_t)x); v.push_back((uint8_t)(x >> 8)); }
+
+int reg2bin(int64_t beg, int64_t end) {               // SAM spec 5.3
+  --end;
+  if (beg >> 14 == end >> 14) return (int)(((1 << 15) - 1) / 7 + (beg >> 14));
+  if (beg >> 17 == end >> 17) return (int)(((1 << 12) - 1) / 7 + (beg >> 17));
+  if (beg >> 20 == end >> 20) return (int)(((1 << 9) - 1) / 7 + (beg >> 20));
+  if (beg >> 23 == end >> 23) return (int)(((1 << 6) - 1) / 7 + (beg >> 23));
+  if (beg >> 26 == end >> 26) return (int)(((1 << 3) - 1) / 7 + (beg >> 26));
+  return 0;
+}
+
+bool bgzf_block(const uint8_t* src, size_t n, int level, std::vector<uint8_t>& out) {
+  z_stream zs;
+  std::memset(&zs, 0, sizeof(zs));
+  if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
+  std::vector<uint8_t> c(deflateBound(&zs, (uLong)n) + 64);
+  zs.next_in = const_cast<Bytef*>(src); zs.avail_in = (uInt)n;
+  zs.next_out = c.data(); zs.avail_out = (uInt)c.size();
+  const int rc = deflate(&zs, Z_FINISH);
+  const size_t clen = zs.total_out;
+  deflateEnd(&zs);
+  if (rc != Z_STREAM_END || clen + 26 > 65536) return false;
+  const uint8_t head[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
+  out.assign(head, head + 16);
+  put16(out, (uint16_t)(clen + 25));
+  out.insert(out.end(), c.begin(), c.begin() + (ptrdiff_t)clen);
+  put32(out, (uint32_t)crc32(crc32(0L, Z_NULL, 0), src, (uInt)n));
+  put32(out, (uint32_t)n);
+  return true;
+}
+
+}  // namespace
+
+extern "C" int mcov_bam_write(const char* path, int32_t n_ref, const char* const* ref_name, const int32_t* ref_len, int64_t n,
+                              const int32_t* tid, const int32_t* pos, const uint16_t* flag, const uint8_t* mapq,
+                              const uint32_t* cig_off, const uint32_t* cig, const int32_t* isize, int level, int n_threads) {
+  if (!path || n_ref <= 0 || !ref_name || !ref_len || n < 0 || (n > 0 && (!tid || !pos || !flag || !mapq || !cig_off))) return MCOV_ERR_ARG;
+  try {
+    if (n_threads <= 0) { unsigned hw = std::thread::hardware_concurrency(); n_threads = hw ? (int)std::min(hw, 32u) : 4; }
+    std::vector<uint8_t> head;
+    std::string text = "@HD\tVN:1.4\tSO:coordinate\n";
+    for (int32_t r = 0; r < n_ref; ++r) text += std::string("@SQ\tSN:") + ref_name[r] + "\tLN:" + std::to_string(ref_len[r]) + "\n";
+    head.insert(head.end(), {'B', 'A', 'M', 1});
+    put32(head, (uint32_t)text.size());
+    head.insert(head.end(), text.begin(), text.end());
+    put32(head, (uint32_t)n_ref);
+    for (int32_t r = 0; r < n_ref; ++r) {
+      const size_t l = std::strlen(ref_name[r]) + 1;
+      put32(head, (uint32_t)l);
+      head.insert(head.end(), ref_name[r], ref_name[r] + l);
+      put32(head, (uint32_t)ref_len[r]);
+    }
+    // records are serialised by ranges of reads in parallel, then cut into BGZF payloads of <= 0xff00 bytes
+    std::vector<std::vector<uint8_t>> part((size_t)n_threads);
+    const int64_t per = (n + n_threads - 1) / std::max(n_threads, 1);
+    auto ser = [&](int t) {
+      std::vector<uint8_t>& v = part[(size_t)t];
+      const int64_t a = t * per, b = std::min(n, a + per);
+      if (a >= b) return;
+      v.reserve((size_t)(b - a) * 260);
+      for (int64_t i = a; i < b; ++i) {
+        char name[24];
+        const int ln = std::snprintf(name, sizeof(name), "r%lld", (long long)i) + 1;
+        const uint32_t nc = cig_off[i + 1] - cig_off[i];
+        int64_t ls = 0, rl = 0;
+        for (uint32_t k = 0; k < nc; ++k) {
+          const uint32_t op = cig[cig_off[i] + k], o = op & 15u, l = op >> 4;
+          if (o == 0 || o == 1 || o == 4 || o == 7 || o == 8) ls += l;       // M I S = X consume the query
+          if ((0x18Du >> o) & 1u) rl += l;
+        }
+        const size_t body = 32 + (size_t)ln + 4 * (size_t)nc + (size_t)(ls + 1) / 2 + (size_t)ls;
+        put32(v, (uint32_t)body);
+        put32(v, (uint32_t)tid[i]); put32(v, (uint32_t)pos[i]);
+        v.push_back((uint8_t)ln); v.push_back(mapq[i]);
+        const int64_t p0 = std::max<int64_t>(pos[i], 0);
+        put16(v, tid[i] >= 0 ? (uint16_t)reg2bin(p0, p0 + std::max<int64_t>(rl, 1)) : (uint16_t)4680);
+        put16(v, (uint16_t)nc); put16(v, flag[i]);
+        put32(v, (uint32_t)ls); put32(v, 0xFFFFFFFFu); put32(v, 0xFFFFFFFFu); put32(v, isize ? (uint32_t)isize[i] : 0u);
+        v.insert(v.end(), name, name + ln);
+        const uint8_t* cp = reinterpret_cast<const uint8_t*>(cig + cig_off[i]);
+        v.insert(v.end(), cp, cp + 4 * (size_t)nc);
+        uint64_t x = 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1);
+        static const uint8_t nt[4] = {1, 2, 4, 8};
+        for (int64_t k = 0; k < (ls + 1) / 2; ++k) {
+          x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+          const uint8_t hi = nt[x & 3], lo = (2 * k + 1 < ls) ? nt[(x >> 2) & 3] : 0;
+          v.push_back((uint8_t)((hi << 4) | lo));
+        }
+        v.insert(v.end(), (size_t)ls, (uint8_t)0xff);
+      }
+    };
+    {
+      std::vector<std::thread> th;
+      for (int t = 1; t < n_threads; ++t) th.emplace_back(ser, t);
+      ser(0);
+      for (auto& t : th) t.join();
+    }
+    // one logical stream: header + parts; payload boundaries every 0xff00 bytes
+    std::vector<const std::vector<uint8_t>*> segs;
+    segs.push_back(&head);
+    for (auto& p : part) if (!p.empty()) segs.push_back(&p);
+    size_t total = 0;
+    for (auto* sgm : segs) total += sgm->size();
+    std::vector<uint8_t> stream;
+    stream.reserve(total);
+    for (auto* sgm : segs) stream.insert(stream.end(), sgm->begin(), sgm->end());
+    for (auto& p : part) std::vector<uint8_t>().swap(p);
+    const size_t kPay = 0xff00, n_blk = (total + kPay - 1) / kPay;
+    std::vector<std::vector<uint8_t>> blk(n_blk);
+    std::atomic<size_t> next(0);
+    std::atomic<bool> good(true);
+    auto comp = [&]() {
+      for (;;) {
+        const size_t k = next.fetch_add(1);
+        if (k >= n_blk || !good.load()) break;
+        const size_t a = k * kPay, len = std::min(kPay, total - a);
+        if (!bgzf_block(stream.data() + a, len, level, blk[k])) good.store(false);
+      }
+    };
+    {
+      std::vector<std::thread> th;
+      for (int t = 1; t < n_threads; ++t) th.emplace_back(comp);
+      comp();
+      for (auto& t : th) t.join();
+    }
+    if (!good.load()) return MCOV_ERR_IO;
+    FILE* fh = std::fopen(path, "wb");
+    if (!fh) return MCOV_ERR_IO;
+    bool ok = true;
+    for (auto& b : blk) ok = ok && std::fwrite(b.data(), 1, b.size(), fh) == b.size();
+    static const uint8_t eof_blk[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    ok = ok && std::fwrite(eof_blk, 1, 28, fh) == 28;
+    ok = (std::fclose(fh) == 0) && ok;
+    if (!ok) return MCOV_ERR_IO;
+    // metadata-only index: per reference one pseudo-bin 37450 with the mapped / unmapped counts
+    std::vector<uint64_t> n_map((size_t)n_ref, 0), n_un((size_t)n_ref, 0);
+    uint64_t no_coor = 0;
+    for (int64_t i = 0; i < n; ++i) {
+      if (tid[i] < 0 || tid[i] >= n_ref) { ++no_coor; continue; }
+      if (flag[i] & 4) ++n_un[(size_t)tid[i]]; else ++n_map[(size_t)tid[i]];
+    }
+    std::vector<uint8_t> bai = {'B', 'A', 'I', 1};
+    put32(bai, (uint32_t)n_ref);
+    for (int32_t r = 0; r < n_ref; ++r) {
+      put32(bai, 1); put32(bai, 37450); put32(bai, 2);
+      for (uint64_t v : {(uint64_t)0, (uint64_t)0, n_map[(size_t)r], n_un[(size_t)r]}) { put32(bai, (uint32_t)v); put32(bai, (uint32_t)(v >> 32)); }
+      put32(bai, 0);
+    }
+    put32(bai, (uint32_t)no_coor); put32(bai, (uint32_t)(no_coor >> 32));
+    const std::string ipath = std::string(path) + ".bai";
+    fh = std::fopen(ipath.c_str(), "wb");
+    if (!fh) return MCOV_ERR_IO;
+    ok = std::fwrite(bai.data(), 1, bai.size(), fh) == bai.size();
+    ok = (std::fclose(fh) == 0) && ok;
+    return ok ? MCOV_OK : MCOV_ERR_IO;
+  } catch (const std::bad_alloc&) { return MCOV_ERR_NOMEM; }
+  catch (...) { return MCOV_ERR_IO; }
+}

@@ -26,8 +26,9 @@ def default_filter(**kw):
 
 
 def build(force=False):
-    src = os.path.join(HERE, "coverage.c")
-    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
+    srcs = [os.path.join(HERE, "coverage.c"), os.path.join(HERE, "synthgen.c"),
+            os.path.join(os.path.dirname(HERE), "include", "mcov_synth.h")]
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(s) for s in srcs):
         subprocess.run(["make", "-C", HERE, "-B", "liboracle.so"], check=True, stdout=subprocess.DEVNULL)
     return LIB
 
