@@ -248,7 +248,10 @@ int  mcov_pack_block(int64_t n, int64_t n_carry, const int32_t* tid, const int32
                      void* out, int64_t cap, int64_t* bytes_out, int n_threads);
 /* The fused sorted pass from a transport block in host memory (wait = 0 defers the verdict like
  * mcov_depth_sorted_async), and one batch of a streamed pass (see mcov_stream_push; the block's n_carry
- * leading reads are the repeats). */
+ * leading reads are the repeats).  These two calls do NOT wait for the host-to-device copy of the
+ * block (the host goes on preparing the next batch while the link is busy): the block must stay
+ * unchanged until the next call on the context that takes reads has returned, or until mcov_sync /
+ * a call that delivers results (the streaming reader's two block buffers satisfy this). */
 int  mcov_depth_sorted_block(mcov_ctx* ctx, const void* block, int64_t bytes, int wait);
 int  mcov_stream_push_block(mcov_ctx* ctx, const void* block, int64_t bytes, int last,
                             int32_t* resend_tid, int32_t* resend_pos);

@@ -78,6 +78,7 @@ struct mcov_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaStream_t d2h_stream = nullptr;   // copy-back of pipelined statistics records (overlaps the next pass)
   cudaEvent_t copied = nullptr;
+  bool copy_pending = false;       // a transport block's copy has been enqueued and not yet waited for
   std::string err;
 
   int32_t n_contigs = 0;

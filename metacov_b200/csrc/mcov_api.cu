@@ -93,6 +93,8 @@ int ensure_depth(mcov_ctx* ctx) {
   return MCOV_OK;
 }
 
+int wait_pending_copy(mcov_ctx* ctx);
+
 // Stage host SoA into device memory on the copy stream (double-buffered), or
 // pass device pointers through.  On return `a` holds device pointers and the
 // compute stream has been made to wait for the copies.
@@ -100,6 +102,7 @@ int stage_reads(mcov_ctx* ctx, int64_t n, const int32_t* tid, const int32_t* pos
                 const uint8_t* mapq, const void* cig_off, bool off64, const uint32_t* cig, int mem_kind,
                 ExpandArgs& a, ReadStage** used) {
   *used = nullptr;
+  { int wrc = wait_pending_copy(ctx); if (wrc) return wrc; }
   a.n = n;
   a.cig_off = nullptr; a.cig_off64 = nullptr;
   const size_t ow = off64 ? 8 : 4;
@@ -139,12 +142,23 @@ int stage_reads(mcov_ctx* ctx, int64_t n, const int32_t* tid, const int32_t* pos
   return MCOV_OK;
 }
 
-int finish_stage(mcov_ctx* ctx, ReadStage* s) {
+// A transport block is copied without the call waiting for the copy (the host goes on to enqueue the statistics and
+// to prepare the next batch while the link is busy); the copy is waited for at the start of the NEXT staging call,
+// in mcov_sync and in mcov_destroy -- the block must stay unchanged until then.
+int wait_pending_copy(mcov_ctx* ctx) {
+  if (!ctx->copy_pending) return MCOV_OK;
+  ctx->copy_pending = false;
+  CU(cudaEventSynchronize(ctx->copied));
+  return MCOV_OK;
+}
+
+int finish_stage(mcov_ctx* ctx, ReadStage* s, bool wait_copy = true) {
   if (!s) return MCOV_OK;
   CU(cudaEventRecord(s->consumed, ctx->stream));
   s->in_flight = true;
   // the caller may reuse its host arrays once the copies are done
-  CU(cudaEventSynchronize(ctx->copied));
+  if (wait_copy) CU(cudaEventSynchronize(ctx->copied));
+  else ctx->copy_pending = true;
   return MCOV_OK;
 }
 
@@ -291,6 +305,7 @@ int block_stage(mcov_ctx* ctx, const void* block, int64_t bytes, ExpandArgs& a, 
       return fail(ctx, MCOV_ERR_ARG, "transport block: a section lies outside the block");
   }
   if (!h.has_mapq && ctx->filt.min_mapq > 0) return fail(ctx, MCOV_ERR_ARG, "transport block: packed without mapq, but the filter has min_mapq > 0");
+  { int wrc = wait_pending_copy(ctx); if (wrc) return wrc; }
   ReadStage& st = ctx->stage[ctx->stage_next];
   ctx->stage_next ^= 1;
   if (st.in_flight) { CU(cudaEventSynchronize(st.consumed)); st.in_flight = false; }
@@ -501,6 +516,7 @@ int mcov_depth_sorted_delta(mcov_ctx* ctx, int64_t n, const int64_t* contig_read
   if (rc) return rc;
   if (contig_read_start[0] != 0 || contig_read_start[ctx->n_contigs] > n)
     return fail(ctx, MCOV_ERR_ARG, "mcov_depth_sorted_delta: contig_read_start must start at 0 and end <= n");
+  { int wrc = wait_pending_copy(ctx); if (wrc) return wrc; }
   CU(cudaMemsetAsync(ctx->d_pc.p, 0, sizeof(PassCounters), ctx->stream));
   ReadStage& st = ctx->stage[ctx->stage_next];
   ctx->stage_next ^= 1;
@@ -735,7 +751,7 @@ static int64_t stream_tile_of(const mcov_ctx* ctx, int32_t lt, int32_t lp) {
 
 // the part of a stream push that follows the staging of the batch (`a` = device columns)
 static int stream_push_staged(mcov_ctx* ctx, const ExpandArgs& a, ReadStage* st, int64_t n, int64_t n_carry, int32_t lt, int32_t lp,
-                              int last, int32_t* resend_tid, int32_t* resend_pos) {
+                              int last, int32_t* resend_tid, int32_t* resend_pos, bool wait_copy = true) {
   const int64_t n_tiles = (ctx->n_slots + kTile - 1) / kTile;
   int64_t tile_hi = n_tiles;
   if (!last) {
@@ -766,7 +782,7 @@ static int stream_push_staged(mcov_ctx* ctx, const ExpandArgs& a, ReadStage* st,
   ctx->stream_reads += n - n_carry;
   ctx->n_reads_pushed = ctx->stream_reads;
   ctx->stream_tile_lo = tile_hi;
-  rc = finish_stage(ctx, st);
+  rc = finish_stage(ctx, st, wait_copy);
   if (rc) return rc;
   if (last) {
     ctx->state = kDepthReady;
@@ -814,7 +830,7 @@ int mcov_stream_push_block(mcov_ctx* ctx, const void* block, int64_t bytes, int 
   mcov_block_hdr h;
   int rc = block_stage(ctx, block, bytes, a, &st, h);
   if (rc) return rc;
-  return stream_push_staged(ctx, a, st, h.n, h.n_carry, h.last_tid, h.last_pos, last, resend_tid, resend_pos);
+  return stream_push_staged(ctx, a, st, h.n, h.n_carry, h.last_tid, h.last_pos, last, resend_tid, resend_pos, /*wait_copy=*/false);
 }
 
 int mcov_depth_sorted_block(mcov_ctx* ctx, const void* block, int64_t bytes, int wait) {
@@ -831,7 +847,7 @@ int mcov_depth_sorted_block(mcov_ctx* ctx, const void* block, int64_t bytes, int
   rc = fused_depth_sorted(ctx, a);
   if (rc) return rc;
   ctx->n_reads_pushed = h.n;
-  rc = finish_stage(ctx, st);
+  rc = finish_stage(ctx, st, /*wait_copy=*/false);
   if (rc) return rc;
   ctx->state = kDepthReady;
   ctx->verdict_pending = true;
@@ -855,6 +871,7 @@ int mcov_depth_sorted_packed(mcov_ctx* ctx, int64_t n, const int64_t* contig_rea
   if (rc) return rc;
   if (contig_read_start[0] != 0 || contig_read_start[ctx->n_contigs] > n)
     return fail(ctx, MCOV_ERR_ARG, "mcov_depth_sorted_packed: contig_read_start must start at 0 and end <= n");
+  { int wrc = wait_pending_copy(ctx); if (wrc) return wrc; }
   CU(cudaMemsetAsync(ctx->d_pc.p, 0, sizeof(PassCounters), ctx->stream));
   ReadStage& st = ctx->stage[ctx->stage_next];
   ctx->stage_next ^= 1;
@@ -952,6 +969,7 @@ int mcov_copy_to_host(mcov_ctx* ctx, const void* dev, void* host, int64_t n_byte
 int mcov_sync(mcov_ctx* ctx) {
   if (!ctx) return MCOV_ERR_ARG;
   CU(cudaSetDevice(ctx->device));
+  { int wrc = wait_pending_copy(ctx); if (wrc) return wrc; }
   CU(cudaStreamSynchronize(ctx->stream));
   return MCOV_OK;
 }
