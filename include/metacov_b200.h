@@ -54,7 +54,12 @@ typedef struct mcov_filter {
   uint16_t flag_require;   /* if !=0 drop unless (flag & flag_require) default 0    */
   uint8_t  min_mapq;       /* drop if mapq < min_mapq                 default 0     */
   uint8_t  ignore_orphans; /* drop paired && !proper_pair             default 1     */
-  uint8_t  reserved[2];
+  uint8_t  count_del;      /* 1: positions under D / N ops count (`column.n`, what the reference reads,
+                              pileup.py:16); 0: only M = X positions count (like get_num_aligned()) --
+                              additive; computed by the any-order formulation        default 1 */
+  uint8_t  reflen0_as_one; /* a passing read whose CIGAR consumes no reference: 0 = contributes nothing
+                              (current htslib), 1 = occupies the one position `pos` (older htslib);
+                              SURVEY.md Appendix A-4                                 default 0 */
   int32_t  max_depth;      /* htslib maxcnt; <=0 disables the cap     default 8000  */
 } mcov_filter;
 

@@ -39,7 +39,7 @@ class McovError(RuntimeError):
 class Filter(C.Structure):
     """mcov_filter: pysam's implicit pileup arguments."""
     _fields_ = [("flag_filter", C.c_uint16), ("flag_require", C.c_uint16), ("min_mapq", C.c_uint8),
-                ("ignore_orphans", C.c_uint8), ("reserved", C.c_uint8 * 2), ("max_depth", C.c_int32)]
+                ("ignore_orphans", C.c_uint8), ("count_del", C.c_uint8), ("reflen0_as_one", C.c_uint8), ("max_depth", C.c_int32)]
 
 
 class RegionStats(C.Structure):

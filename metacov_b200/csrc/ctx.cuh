@@ -125,6 +125,7 @@ struct mcov_ctx {
   mcov::DevBuf d_stream_acc;          // StreamAcc + the carried reads' counts of the current batch
   int64_t stream_tile_lo = 0;         // tiles below this one hold final depth
   int64_t stream_reads = 0;           // distinct reads pushed so far
+  bool stream_started = false;        // (count_del = 0 streams: the difference array has been cleared)
   mcov::DevBuf d_tasks, d_rlen, d_rchunks, d_rhist, d_pool, d_done, d_out, d_win_slot, d_win_n, d_win_out, d_htasks, d_tile_heavy, d_run_tasks, d_run_counts, d_run_out;
   int64_t n_runs = -1;               // records held in d_run_out ([tid | start | end | depth] x n_runs), -1 = none
   mcov::PinBuf h_pin;

@@ -376,6 +376,10 @@ __device__ __forceinline__ PrepReads prep_load_reduce(const FusedArgs& f, int64_
       coop &= ~(1u << r);
     }
   }
+  if (a.filt.reflen0_as_one) {                     // older htslib: a read that consumes no reference still occupies `pos`
+#pragma unroll
+    for (int r = 0; r < 4; ++r) if (((passm >> r) & 1u) && R.reflen[r] == 0u) R.reflen[r] = 1u;
+  }
   R.passm = passm;
   return R;
 }
@@ -1047,6 +1051,41 @@ __global__ void k_delta_finish(int64_t n, const int64_t* __restrict__ contig_rea
   }
 }
 
+// ---- count_del = 0: only M = X positions count ------------------------------------------------------------
+// The additive switch of mcov_filter (the reference reads `column.n`, which counts D / N positions too): a read is
+// then one interval per run of M = X ops, so it goes through the any-order formulation -- +1 / -1 per run into the
+// difference array, look-back scan afterwards.  One thread per read, ops walked serially: the generic path, not
+// the tuned one.  Reads [i_begin, n) of the batch are expanded (a streamed batch skips its carried prefix).
+__global__ void k_expand_runs(FusedArgs f, int64_t i_begin) {
+  const ExpandArgs& a = f.e;
+  unsigned long long np = 0, al = 0;
+  for (int64_t i = i_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t t = a.tid[i];
+    if (!read_passes(a.flag[i], a.mapq[i], a.filt) || (uint32_t)t >= (uint32_t)a.n_contigs) continue;
+    const uint64_t o0 = a.cig_off64 ? a.cig_off64[i] : a.cig_off[i], o1 = a.cig_off64 ? a.cig_off64[i + 1] : a.cig_off[i + 1];
+    const int64_t L = a.contig_len[t];
+    int32_t* d = a.delta + a.contig_off[t];
+    int64_t p = a.pos[i], counted = 0, consumed = 0;
+    bool hit = false;
+    for (uint64_t o = o0; o < o1; ++o) {
+      const uint32_t op = a.cig[o], c = op & 15u;
+      const int64_t ln = op >> 4;
+      if (c == 0u || c == 7u || c == 8u) {
+        const int64_t s = min(max(p, (int64_t)0), L), e = min(max(p + ln, (int64_t)0), L);
+        if (e > s) { atomicAdd(d + s, 1); atomicAdd(d + e, -1); hit = true; }
+        counted += ln; p += ln; consumed += ln;
+      } else if (c == 2u || c == 3u) { p += ln; consumed += ln; }
+    }
+    if (consumed == 0 && a.filt.reflen0_as_one) {
+      const int64_t s = a.pos[i];
+      if (s >= 0 && s < L) { atomicAdd(d + s, 1); atomicAdd(d + s + 1, -1); hit = true; counted = 1; }
+    }
+    if (hit) { np += 1; al += (unsigned long long)counted; }
+  }
+  np = warp_sum(np); al = warp_sum(al);
+  if ((threadIdx.x & 31) == 0) { if (np) atomicAdd(&a.pc->n_pass, np); if (al) atomicAdd(&a.pc->aligned_bases, al); }
+}
+
 // ---- streamed passes (mcov_stream_begin / mcov_stream_push) ---------------------------------------------
 // A batch of a streamed file starts with n_carry reads that earlier batches have already counted (they are
 // sent again because their intervals reach into this batch's tiles): their contribution to the pass counters
@@ -1063,6 +1102,7 @@ __global__ void k_carry_counts(FusedArgs f, int64_t n_carry, unsigned long long*
     int64_t rl = 0;
     for (uint64_t o = o0; o < o1; ++o) rl += cigar_ref_len(a.cig[o]);
     if (rl > 0x7fffffffll) rl = 0x7fffffffll;
+    if (rl == 0 && a.filt.reflen0_as_one) rl = 1;
     const int64_t len = a.contig_len[t];
     int64_t s = a.pos[i], e = (int64_t)a.pos[i] + rl;
     s = s < 0 ? 0 : (s > len ? len : s);

@@ -150,6 +150,10 @@ __device__ __forceinline__ PrepReads prep_reduce_staged(const FusedArgs& f, cons
       coop &= ~(1u << r);
     }
   }
+  if (a.filt.reflen0_as_one) {                     // older htslib: a read that consumes no reference still occupies `pos`
+#pragma unroll
+    for (int r = 0; r < 4; ++r) if (((passm >> r) & 1u) && R.reflen[r] == 0u) R.reflen[r] = 1u;
+  }
   R.passm = passm;
   return R;
 }

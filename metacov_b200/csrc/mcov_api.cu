@@ -257,6 +257,37 @@ int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a, int64_t tile_lo = -1,
   return MCOV_OK;
 }
 
+// count_del = 0 (only M = X positions count): the any-order formulation -- clear, one +1 / -1 pair per run of M = X ops
+// (k_expand_runs), look-back scan.  Reads [i_begin, n) of the batch; `clear` / `finalize` let a stream spread the
+// pass over its batches.
+int runs_depth(mcov_ctx* ctx, const ExpandArgs& a, int64_t i_begin, bool clear, bool finalize) {
+  cudaStream_t s = ctx->stream;
+  if (clear) MCOV_LAUNCH(ctx, kKClear, CU(cudaMemsetAsync(ctx->depth, 0, (size_t)ctx->n_slots * 4, s)));
+  if (a.n > i_begin) {
+    FusedArgs f;
+    std::memset(&f, 0, sizeof(f));
+    f.e = a;
+    MCOV_LAUNCH(ctx, kKExpand, (k_expand_runs<<<grid_for(ctx, a.n - i_begin, 256, 8), 256, 0, s>>>(f, i_begin)));
+    CU(cudaGetLastError());
+  }
+  if (finalize) {
+    const int64_t n_tiles = (ctx->n_slots + kScanTile - 1) / kScanTile;
+    CU(ctx->d_status.ensure((size_t)n_tiles * 8));
+    CU(cudaMemsetAsync(ctx->d_status.p, 0, (size_t)n_tiles * 8, s));
+    MCOV_LAUNCH(ctx, kKScan, (k_scan_inplace<true><<<(unsigned)n_tiles, kScanThreads, 0, s>>>(ctx->depth, ctx->n_slots,
+                                                                                            ctx->d_status.as<unsigned long long>(), pc_of(ctx))));
+    CU(cudaGetLastError());
+  }
+  return MCOV_OK;
+}
+
+// per-base depth of a whole sorted batch from device columns: the fused path, or the M-run formulation when the
+// filter says count_del = 0
+int depth_from_columns(mcov_ctx* ctx, const ExpandArgs& a) {
+  if (ctx->filt.count_del) return fused_depth_sorted(ctx, a);
+  return runs_depth(ctx, a, 0, true, true);
+}
+
 // Deliver the deferred verdict of an asynchronous fused pass (stream already synchronised,
 // `h` = the pass counters just read back).
 int fused_verdict(mcov_ctx* ctx, const PassCounters& h) {
@@ -388,6 +419,8 @@ void mcov_default_filter(mcov_filter* f) {
   f->flag_require = 0;
   f->min_mapq = 0;
   f->ignore_orphans = 1;
+  f->count_del = 1;          // `column.n` counts the reads whose op at the position is D or N
+  f->reflen0_as_one = 0;     // a read that consumes no reference contributes nothing (current htslib)
   f->max_depth = 8000;
 }
 
@@ -583,7 +616,7 @@ int mcov_depth_sorted_delta(mcov_ctx* ctx, int64_t n, const int64_t* contig_read
   a.contig_off = ctx->d_off.as<int64_t>(); a.contig_len = ctx->d_len.as<int32_t>(); a.n_contigs = ctx->n_contigs;
   a.filt = ctx->filt; a.delta = ctx->depth; a.pc = pc_of(ctx);
   a.cig_aligned16 = 1;
-  rc = fused_depth_sorted(ctx, a);
+  rc = depth_from_columns(ctx, a);
   if (rc) return rc;
   ctx->n_reads_pushed = n;
   rc = finish_stage(ctx, &st);
@@ -631,7 +664,8 @@ static int push_reads_impl(mcov_ctx* ctx, int64_t n, const int32_t* tid, const i
                 al(a.flag, 8) && al(a.mapq, 4)) ? 1 : 0;
   }
   const int grid = grid_for(ctx, (n + kPrepPer - 1) / kPrepPer, kPrepThreads, 8);
-  if (off64) MCOV_LAUNCH(ctx, kKExpand, (k_expand<true><<<grid, kPrepThreads, 0, ctx->stream>>>(f)));
+  if (!ctx->filt.count_del) MCOV_LAUNCH(ctx, kKExpand, (k_expand_runs<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(f, 0)));
+  else if (off64) MCOV_LAUNCH(ctx, kKExpand, (k_expand<true><<<grid, kPrepThreads, 0, ctx->stream>>>(f)));
   else MCOV_LAUNCH(ctx, kKExpand, (k_expand<false><<<grid, kPrepThreads, 0, ctx->stream>>>(f)));
   CU(cudaGetLastError());
   ctx->n_reads_pushed += n;
@@ -680,7 +714,7 @@ static int depth_sorted_impl(mcov_ctx* ctx, int64_t n, const int32_t* tid, const
     std::memset(&a, 0, sizeof(a));
     a.pc = pc_of(ctx);
   }
-  rc = fused_depth_sorted(ctx, a);
+  rc = depth_from_columns(ctx, a);
   if (rc) return rc;
   ctx->n_reads_pushed = n;
   rc = finish_stage(ctx, st);
@@ -720,6 +754,8 @@ int mcov_stream_begin(mcov_ctx* ctx) {
   CU(cudaMemsetAsync(ctx->d_stream_acc.p, 0, sizeof(StreamAcc) + 16, ctx->stream));
   ctx->stream_tile_lo = 0;
   ctx->stream_reads = 0;
+  ctx->stream_started = false;
+  CU(cudaMemsetAsync(ctx->d_pc.p, 0, sizeof(PassCounters), ctx->stream));
   ctx->verdict_pending = false;
   ctx->state = kStreaming;
   return MCOV_OK;
@@ -764,6 +800,19 @@ static int stream_push_staged(mcov_ctx* ctx, const ExpandArgs& a, ReadStage* st,
   if (resend_tid && resend_pos) {
     if (n > 0) mcov_stream_resend_point(ctx, lt, lp, resend_tid, resend_pos);
     else { *resend_tid = -1; *resend_pos = 0; }                  // (an empty batch changes nothing: keep sending what was being sent)
+  }
+  if (!ctx->filt.count_del) {
+    // M = X positions only: the batches accumulate in the difference array (carried reads skipped), the last one scans
+    int rc = runs_depth(ctx, a, n_carry, ctx->stream_reads == 0 && ctx->stream_tile_lo == 0 && !ctx->stream_started, last != 0);
+    if (rc) return rc;
+    ctx->stream_started = true;
+    ctx->stream_reads += n - n_carry;
+    ctx->n_reads_pushed = ctx->stream_reads;
+    ctx->stream_tile_lo = tile_hi;
+    rc = finish_stage(ctx, st, wait_copy);
+    if (rc) return rc;
+    if (last) { ctx->state = kDepthReady; ctx->verdict_pending = true; }
+    return MCOV_OK;
   }
   CU(cudaMemsetAsync(ctx->d_pc.p, 0, sizeof(PassCounters), ctx->stream));
   int rc = fused_depth_sorted(ctx, a, ctx->stream_tile_lo, tile_hi);
@@ -844,7 +893,7 @@ int mcov_depth_sorted_block(mcov_ctx* ctx, const void* block, int64_t bytes, int
   rc = block_stage(ctx, block, bytes, a, &st, h);
   if (rc) return rc;
   CU(cudaMemsetAsync(ctx->d_pc.p, 0, sizeof(PassCounters), ctx->stream));
-  rc = fused_depth_sorted(ctx, a);
+  rc = depth_from_columns(ctx, a);
   if (rc) return rc;
   ctx->n_reads_pushed = h.n;
   rc = finish_stage(ctx, st, /*wait_copy=*/false);
@@ -917,7 +966,7 @@ int mcov_depth_sorted_packed(mcov_ctx* ctx, int64_t n, const int64_t* contig_rea
   a.contig_off = ctx->d_off.as<int64_t>(); a.contig_len = ctx->d_len.as<int32_t>(); a.n_contigs = ctx->n_contigs;
   a.filt = ctx->filt; a.delta = ctx->depth; a.pc = pc_of(ctx);
   a.cig_aligned16 = 1;
-  rc = fused_depth_sorted(ctx, a);
+  rc = depth_from_columns(ctx, a);
   if (rc) return rc;
   ctx->n_reads_pushed = n;
   rc = finish_stage(ctx, &st);

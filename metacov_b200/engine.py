@@ -115,7 +115,8 @@ class CoverageEngine:
         self.close()
         return False
 
-    def set_filter(self, flag_filter=None, flag_require=None, min_mapq=None, ignore_orphans=None, max_depth=None):
+    def set_filter(self, flag_filter=None, flag_require=None, min_mapq=None, ignore_orphans=None, max_depth=None,
+                   count_del=None, reflen0_as_one=None):
         f = self.filter
         if flag_filter is not None:
             f.flag_filter = flag_filter
@@ -127,6 +128,10 @@ class CoverageEngine:
             f.ignore_orphans = 1 if ignore_orphans else 0
         if max_depth is not None:
             f.max_depth = max_depth
+        if count_del is not None:
+            f.count_del = 1 if count_del else 0
+        if reflen0_as_one is not None:
+            f.reflen0_as_one = 1 if reflen0_as_one else 0
         self._check(lib.mcov_set_filter(self._ctx, C.byref(f)))
 
     def contig_offset(self, tid):

@@ -23,7 +23,7 @@
 
 typedef struct orc_filter {
   uint16_t flag_filter, flag_require;
-  uint8_t min_mapq, ignore_orphans, reserved[2];
+  uint8_t min_mapq, ignore_orphans, count_del, reflen0_as_one;   /* the two switches of SURVEY.md Appendix A-4 / 8(b) */
   int32_t max_depth;
 } orc_filter;
 
@@ -72,8 +72,30 @@ static void diff_add(diff_job* j) {
   for (int64_t i = j->i0; i < j->i1; ++i) {
     int32_t t = j->tid[i];
     if (t < 0 || t >= j->n_contigs || !orc_pass(j->flag[i], j->mapq[i], j->f)) continue;
+    int64_t L = j->len[t];
+    if (!j->f->count_del) {
+      /* only M = X positions count: one interval per run of such ops; D / N advance the position uncounted */
+      int64_t p = j->pos[i], counted = 0, hit = 0;
+      for (uint32_t k = j->cig_off[i]; k < j->cig_off[i + 1]; ++k) {
+        uint32_t op = j->cig[k] & 15u; int64_t ln = j->cig[k] >> 4;
+        if (op == 0 || op == 7 || op == 8) {
+          int64_t s = p, e = p + ln;
+          if (s < 0) s = 0; if (s > L) s = L;
+          if (e < 0) e = 0; if (e > L) e = L;
+          if (e > s) { j->depth[j->off[t] + s] += 1; j->depth[j->off[t] + e] -= 1; hit = 1; }
+          counted += ln; p += ln;
+        } else if (op == 2 || op == 3) p += ln;
+      }
+      if (counted == 0 && j->f->reflen0_as_one && orc_reflen(j->cig + j->cig_off[i], j->cig_off[i + 1] - j->cig_off[i]) == 0) {
+        int64_t s = j->pos[i];
+        if (s >= 0 && s < L) { j->depth[j->off[t] + s] += 1; j->depth[j->off[t] + s + 1] -= 1; hit = 1; counted = 1; }
+      }
+      if (hit) { j->n_pass++; j->aligned += counted; }
+      continue;
+    }
     int64_t rl = orc_reflen(j->cig + j->cig_off[i], j->cig_off[i + 1] - j->cig_off[i]);
-    int64_t L = j->len[t], s = j->pos[i], e = s + rl;
+    if (rl == 0 && j->f->reflen0_as_one) rl = 1;
+    int64_t s = j->pos[i], e = s + rl;
     if (s < 0) s = 0; if (s > L) s = L;
     if (e < 0) e = 0; if (e > L) e = L;
     if (e <= s) continue;

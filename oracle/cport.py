@@ -15,11 +15,11 @@ ORC_STATS_DTYPE = np.dtype([
 
 class OrcFilter(C.Structure):
     _fields_ = [("flag_filter", C.c_uint16), ("flag_require", C.c_uint16), ("min_mapq", C.c_uint8),
-                ("ignore_orphans", C.c_uint8), ("reserved", C.c_uint8 * 2), ("max_depth", C.c_int32)]
+                ("ignore_orphans", C.c_uint8), ("count_del", C.c_uint8), ("reflen0_as_one", C.c_uint8), ("max_depth", C.c_int32)]
 
 
 def default_filter(**kw):
-    f = OrcFilter(0x704, 0, 0, 1, (C.c_uint8 * 2)(0, 0), 8000)
+    f = OrcFilter(0x704, 0, 0, 1, 1, 0, 8000)
     for k, v in kw.items():
         setattr(f, k, v)
     return f

@@ -649,3 +649,42 @@ def test_block_transport_equals_soa_path():
         empty = ReadBatch(*(np.zeros(0, a.dtype) for a in (fb.tid, fb.pos, fb.flag, fb.mapq)), np.zeros(1, np.uint32), np.zeros(0, np.uint32))
         eng.depth_sorted_block(pack_block(empty, 2))
         assert eng.pass_info()["n_pass"] == 0 and not eng.copy_depth(0).any()
+
+
+@pytest.mark.parametrize("wl,scale", [("c2", 0.01), ("c5", 0.002)])
+def test_filter_switches_count_del_and_reflen0(wl, scale):
+    """The two switches SURVEY.md Appendix A-4 / 8(b) ask to keep: count_del = 0 (only M = X positions count, one
+    interval per run of such ops) and reflen0_as_one (a read that consumes no reference occupies `pos`, as in older
+    htslib) -- every entry point against the C oracle with the same switches; the defaults are the reference's."""
+    from metacov_b200 import ReadBatch, synth
+    from metacov_b200.engine import pack_block
+    w = synth.WORKLOADS[wl](scale)
+    b, _, reflen = synth.generate_host(w, want_reflen=True)
+    # a few reads whose CIGAR consumes no reference (soft clip / insertion only), kept in sorted order
+    cig = b.cig.copy()
+    o = b.cig_off.astype(np.int64)
+    single = np.nonzero(np.diff(o) == 1)[0][::97]
+    cig[o[single]] = (cig[o[single]] & ~np.uint32(15)) | np.uint32(4)
+    b = ReadBatch(b.tid, b.pos, b.flag, b.mapq, b.cig_off, cig)
+    n = len(b.tid)
+    for sw in (dict(count_del=0), dict(reflen0_as_one=1), dict(count_del=0, reflen0_as_one=1)):
+        want, dflat, off, info = oracle_depth(b, w.contig_len, **sw)
+        base, _, _, _ = oracle_depth(b, w.contig_len)
+        if "count_del" in sw or len(single):
+            assert any(not np.array_equal(x, y) for x, y in zip(want, base)), sw   # the switch changes something here
+        with engine_for(w.contig_len, **sw) as eng:
+            def same(tag):
+                for c, d in enumerate(full_depth(eng)):
+                    assert np.array_equal(d, want[c]), (sw, tag, c)
+                pi = eng.pass_info()
+                assert pi["n_pass"] == info["n_pass"] and pi["aligned_bases"] == info["aligned_bases"], (sw, tag)
+            eng.depth_sorted(b); same("sorted")
+            eng.begin(); eng.push(b); eng.finalize(); same("push")
+            if wl == "c2":
+                eng.depth_sorted_block(pack_block(b, w.n_contigs)); same("block")
+            # streamed in three batches (the carry rule is the same; carried reads must not count twice)
+            from test_gpu_stream import push_in_batches
+            rl = np.asarray(reflen).copy()
+            push_in_batches(eng, b, rl, np.r_[0, n // 3, 2 * n // 3, n])
+            eng.region_stats([0], [0], [10])
+            same("stream")
