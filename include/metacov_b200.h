@@ -215,31 +215,33 @@ int  mcov_depth_sorted_delta(mcov_ctx* ctx, int64_t n,
 /* ---- the transport block: what the host decoder hands to the GPU ----------------
  * ONE contiguous host buffer per batch of coordinate-sorted reads -> ONE host-to-device
  * copy; the SoA columns are rebuilt on the device.  The end-to-end rate is bound by the
- * PCIe link, so the block is as narrow as the data allows (config C2: 3.6 bytes per
+ * PCIe link, so the block is as narrow as the data allows (config C2: 2.6 bytes per
  * read instead of 19.6 for the plain columns):
  *   crs      int64[n_contigs+1]  reads [crs[c], crs[c+1]) belong to contig c, reads from
  *                                crs[n_contigs] on are unplaced (instead of tid[n])
  *   dpos     u8[n]               position - position of the previous read of the same
  *                                contig (first read of a contig: - 0); differences outside
  *                                0..255 are listed as exceptions (exc_idx u32, exc_val i32)
- *   fidx     u8[n] + flagdict u16[<=256]   flag dictionary (u16 flags directly when a
- *                                batch holds more than 256 distinct flags: flag_wide = 1)
- *   cclass   u8[n]               < 128: the read's whole CIGAR is dictionary entry cclass
+ *   fc       u8[n]               index into the joint table jt[<=255] of the batch's most
+ *                                frequent (flag, CIGAR class) pairs (u16 flag, u8 class);
+ *                                255 = the pair is listed as an escape (esc_idx u32,
+ *                                esc_flag u16, esc_cls u8)
+ *   CIGAR class                  < 128: the read's whole CIGAR is dictionary entry `class`
  *                                (dict_off u32[n_dict+1], dict_ops u32[]: the batch's most
- *                                frequent CIGARs); >= 128: cclass - 128 explicit ops follow
- *                                in xops u32[] in read order
+ *                                frequent CIGARs of up to four ops); >= 128: class - 128
+ *                                explicit ops follow in xops u32[] in read order
  *   mapq     u8[n]               only when the filter asks for it (min_mapq > 0)
  * A batch with a CIGAR of more than 127 ops (long reads) does not qualify
  * (mcov_pack_block returns MCOV_ERR_RANGE): it travels as plain columns or through
  * mcov_depth_sorted_packed.  All sections start on 16-byte boundaries. */
 #define MCOV_BLOCK_MAGIC 0x4256434Du   /* "MCVB" */
 typedef struct mcov_block_hdr {
-  uint32_t magic, version;
-  int64_t  n, n_carry, n_cigar, n_exc, n_xops, total_bytes;
-  int32_t  n_contigs, n_flagdict, n_dict, n_dictops, flag_wide, has_mapq;
+  uint32_t magic, version;                     /* version 2 */
+  int64_t  n, n_carry, n_cigar, n_exc, n_esc, n_xops, total_bytes;
+  int32_t  n_contigs, n_jt, n_dict, n_dictops, has_mapq, reserved0;
   int32_t  last_tid, last_pos;                 /* the batch's last read (streams: how far the depth becomes final) */
-  uint32_t off_crs, off_dpos, off_exc_idx, off_exc_val, off_fidx, off_flagdict, off_cclass, off_dict_off,
-           off_dict_ops, off_xops, off_mapq, reserved;
+  uint32_t off_crs, off_dpos, off_exc_idx, off_exc_val, off_fc, off_jt, off_esc_idx, off_esc_flag, off_esc_cls,
+           off_dict_off, off_dict_ops, off_xops, off_mapq, reserved1;
 } mcov_block_hdr;
 /* Upper bound of the block size for a batch of n reads with n_cigar ops over n_contigs contigs. */
 int64_t mcov_block_bound(int64_t n, int64_t n_cigar, int32_t n_contigs);

@@ -320,19 +320,19 @@ int block_stage(mcov_ctx* ctx, const void* block, int64_t bytes, ExpandArgs& a, 
   *used = nullptr;
   if (!block || bytes < (int64_t)sizeof(mcov_block_hdr)) return fail(ctx, MCOV_ERR_ARG, "transport block: null or too short");
   std::memcpy(&h, block, sizeof(h));
-  if (h.magic != MCOV_BLOCK_MAGIC || h.version != 1) return fail(ctx, MCOV_ERR_ARG, "transport block: bad magic / version");
+  if (h.magic != MCOV_BLOCK_MAGIC || h.version != 2) return fail(ctx, MCOV_ERR_ARG, "transport block: bad magic / version");
   const int64_t n = h.n;
-  if (n < 0 || n >= 0xFFFFFFF0ll || h.n_carry < 0 || h.n_carry > n || h.n_exc < 0 || h.n_xops < 0 || h.n_cigar < 0 || h.n_cigar > 0xFFFFFFF0ll ||
-      h.total_bytes > bytes || h.n_contigs != ctx->n_contigs || h.n_dict < 0 || h.n_dict > 128 || h.n_flagdict < 0 || h.n_flagdict > 256 ||
-      h.n_dictops < 0 || h.n_dictops > 512)
+  if (n < 0 || n >= 0xFFFFFFF0ll || h.n_carry < 0 || h.n_carry > n || h.n_exc < 0 || h.n_esc < 0 || h.n_esc > n || h.n_xops < 0 || h.n_cigar < 0 ||
+      h.n_cigar > 0xFFFFFFF0ll || h.n_xops > h.n_cigar || h.total_bytes > bytes || h.n_contigs != ctx->n_contigs || h.n_dict < 0 || h.n_dict > 128 ||
+      h.n_jt < 0 || h.n_jt > 255 || h.n_dictops < 0 || h.n_dictops > 512)
     return fail(ctx, MCOV_ERR_ARG, "transport block: inconsistent header (or packed for another contig table)");
   {
     const uint64_t tb = (uint64_t)h.total_bytes, n1 = (uint64_t)std::max<int64_t>(n, 1);
     auto in = [&](uint32_t off, uint64_t len) { return (off & 15u) == 0 && (uint64_t)off + len <= tb; };
     if (!in(h.off_crs, ((uint64_t)h.n_contigs + 1) * 8) || !in(h.off_dpos, n1) || !in(h.off_exc_idx, (uint64_t)h.n_exc * 4) ||
-        !in(h.off_exc_val, (uint64_t)h.n_exc * 4) || !in(h.off_fidx, h.flag_wide ? n1 * 2 : n1) || !in(h.off_flagdict, 512) ||
-        !in(h.off_cclass, n1) || !in(h.off_dict_off, 129 * 4) || !in(h.off_dict_ops, 2048) || !in(h.off_xops, (uint64_t)h.n_xops * 4) ||
-        (h.has_mapq && !in(h.off_mapq, n1)))
+        !in(h.off_exc_val, (uint64_t)h.n_exc * 4) || !in(h.off_fc, n1) || !in(h.off_jt, 1024) || !in(h.off_esc_idx, (uint64_t)h.n_esc * 4) ||
+        !in(h.off_esc_flag, (uint64_t)h.n_esc * 2) || !in(h.off_esc_cls, (uint64_t)h.n_esc) || !in(h.off_dict_off, 129 * 4) ||
+        !in(h.off_dict_ops, 2048) || !in(h.off_xops, (uint64_t)h.n_xops * 4) || (h.has_mapq && !in(h.off_mapq, n1)))
       return fail(ctx, MCOV_ERR_ARG, "transport block: a section lies outside the block");
   }
   if (!h.has_mapq && ctx->filt.min_mapq > 0) return fail(ctx, MCOV_ERR_ARG, "transport block: packed without mapq, but the filter has min_mapq > 0");
@@ -346,7 +346,7 @@ int block_stage(mcov_ctx* ctx, const void* block, int64_t bytes, ExpandArgs& a, 
   CU(st.tid.ensure((size_t)n1 * 4)); CU(st.pos.ensure((size_t)n1 * 4)); CU(st.flag.ensure((size_t)n1 * 2)); CU(st.mapq.ensure((size_t)n1));
   CU(st.cig_off.ensure((size_t)off_len * 4)); CU(st.cig.ensure((size_t)h.n_cigar * 4 + 16));
   CU(ctx->d_start_slot.ensure((size_t)(off_len + 8) * 4));              // S (the record buffer of the fused pass: free until the prep kernel)
-  CU(ctx->d_end_slot.ensure((size_t)off_len * 4));                      // explicit-op offsets
+  CU(ctx->d_end_slot.ensure((size_t)off_len * 4 + (size_t)n1 + 16));    // explicit-op offsets | CIGAR classes
   CU(cudaMemcpyAsync(st.raw.p, block, (size_t)h.total_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
   CU(cudaEventRecord(ctx->copied, ctx->copy_stream));
   CU(cudaStreamWaitEvent(ctx->stream, ctx->copied, 0));
@@ -354,10 +354,13 @@ int block_stage(mcov_ctx* ctx, const void* block, int64_t bytes, ExpandArgs& a, 
   BlockArgs b;
   b.blk = st.raw.as<char>(); b.h = h; b.off_len = off_len;
   b.S = ctx->d_start_slot.as<int32_t>(); b.xoff = ctx->d_end_slot.as<uint32_t>();
+  b.cls = ctx->d_end_slot.as<uint8_t>() + (size_t)off_len * 4;
   b.tid = st.tid.as<int32_t>(); b.pos = st.pos.as<int32_t>(); b.flag = st.flag.as<uint16_t>(); b.mapq = st.mapq.as<uint8_t>();
   b.cig_off = st.cig_off.as<uint32_t>(); b.cig = st.cig.as<uint32_t>();
   ctx->prof_begin(kKDeltaUnpack);
   k_block_seed<<<(unsigned)((off_len + 255) / 256), 256, 0, s>>>(b);
+  if (h.n_esc) k_block_patch<<<(unsigned)((h.n_esc + 255) / 256), 256, 0, s>>>(b);
+  k_block_counts<<<(unsigned)((off_len + 255) / 256), 256, 0, s>>>(b);
   if (h.n_exc) k_delta_patch<<<(unsigned)((h.n_exc + 255) / 256), 256, 0, s>>>(h.n_exc, reinterpret_cast<const uint32_t*>(b.blk + h.off_exc_idx),
                                                                                reinterpret_cast<const int32_t*>(b.blk + h.off_exc_val), n, b.S);
   ctx->prof_end();

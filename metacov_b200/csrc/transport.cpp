@@ -44,8 +44,8 @@ int64_t mcov_block_bound(int64_t n, int64_t n_cigar, int32_t n_contigs) {
   if (n < 0 || n_cigar < 0 || n_contigs < 0) return -1;
   const size_t n1 = (size_t)std::max<int64_t>(n, 1);
   return (int64_t)(al16(sizeof(mcov_block_hdr)) + al16(((size_t)n_contigs + 1) * 8) + al16(n1) /*dpos*/ + 2 * al16(n1 * 4) /*exceptions*/ +
-                   al16(n1 * 2) /*fidx or wide flags*/ + al16(512) + al16(n1) /*cclass*/ + al16(129 * 4) + al16(128 * 4 * 4) +
-                   al16((size_t)n_cigar * 4 + 16) + al16(n1) /*mapq*/ + 256);
+                   al16(n1) /*fc*/ + al16(1024) /*jt*/ + al16(n1 * 4) + al16(n1 * 2) + al16(n1) /*escapes*/ + al16(129 * 4) +
+                   al16(128 * 4 * 4) + al16((size_t)n_cigar * 4 + 16) + al16(n1) /*mapq*/ + 256);
 }
 
 int mcov_pack_block(int64_t n, int64_t n_carry, const int32_t* tid, const int32_t* pos, const uint16_t* flag,
@@ -61,7 +61,7 @@ int mcov_pack_block(int64_t n, int64_t n_carry, const int32_t* tid, const int32_
     char* base = static_cast<char*>(out);
     mcov_block_hdr h;
     std::memset(&h, 0, sizeof(h));
-    h.magic = MCOV_BLOCK_MAGIC; h.version = 1; h.n = n; h.n_carry = n_carry; h.n_cigar = n_cig; h.n_contigs = n_contigs;
+    h.magic = MCOV_BLOCK_MAGIC; h.version = 2; h.n = n; h.n_carry = n_carry; h.n_cigar = n_cig; h.n_contigs = n_contigs;
     h.last_tid = n > 0 ? tid[n - 1] : -1; h.last_pos = n > 0 ? pos[n - 1] : 0;
     h.has_mapq = mapq ? 1 : 0;
     size_t o = al16(sizeof(mcov_block_hdr));
@@ -84,19 +84,6 @@ int mcov_pack_block(int64_t n, int64_t n_carry, const int32_t* tid, const int32_
     uint8_t* dpos = reinterpret_cast<uint8_t*>(base + o);
     o += al16(n1);
     std::vector<std::vector<std::pair<uint32_t, int32_t>>> exc((size_t)n_threads);
-    // ---- flags: dictionary ----
-    std::vector<int32_t> fslot(65536, -1);
-    std::vector<uint16_t> fdict;
-    for (int64_t i = 0; i < n && fdict.size() <= 256; ++i) if (fslot[flag[i]] < 0) { fslot[flag[i]] = (int32_t)fdict.size(); fdict.push_back(flag[i]); }
-    h.flag_wide = fdict.size() > 256 ? 1 : 0;
-    h.off_fidx = (uint32_t)o;
-    uint8_t* fidx8 = reinterpret_cast<uint8_t*>(base + o);
-    uint16_t* fidx16 = reinterpret_cast<uint16_t*>(base + o);
-    o += al16(h.flag_wide ? n1 * 2 : n1);
-    h.off_flagdict = (uint32_t)o;
-    h.n_flagdict = h.flag_wide ? 0 : (int32_t)fdict.size();
-    if (!h.flag_wide) std::memcpy(base + o, fdict.data(), fdict.size() * 2);
-    o += al16(512);
     // ---- CIGAR dictionary: the 128 most frequent CIGARs of up to four ops (counted on a sample of the batch) ----
     std::vector<Cand> table(kTable);
     for (auto& c : table) { c.used = false; c.count = 0; }
@@ -138,9 +125,6 @@ int mcov_pack_block(int64_t n, int64_t n_carry, const int32_t* tid, const int32_
       }
       return -1;
     };
-    h.off_cclass = (uint32_t)o;
-    uint8_t* cclass = reinterpret_cast<uint8_t*>(base + o);
-    o += al16(n1);
     h.off_dict_off = (uint32_t)o;
     uint32_t* dict_off = reinterpret_cast<uint32_t*>(base + o);
     o += al16(129 * 4);
@@ -154,9 +138,8 @@ int mcov_pack_block(int64_t n, int64_t n_carry, const int32_t* tid, const int32_
       dict_off[dict.size()] = k;
       h.n_dictops = (int32_t)k;
     }
-    h.off_xops = (uint32_t)o;
-    uint32_t* xops = reinterpret_cast<uint32_t*>(base + o);
-    // ---- per-read pass (parallel): position differences, flag indices, CIGAR classes; explicit op counts per range ----
+    // ---- per-read pass 1 (parallel): position differences, CIGAR classes; explicit op counts per range ----
+    std::vector<uint8_t> cls((size_t)n1);
     std::vector<int64_t> xcount((size_t)n_threads + 1, 0);
     std::vector<int> too_long((size_t)n_threads, 0);
     par_for(n, n_threads, [&](int t, int64_t a, int64_t b) {
@@ -167,28 +150,94 @@ int mcov_pack_block(int64_t n, int64_t n_carry, const int32_t* tid, const int32_
         const int64_t d = first ? (int64_t)pos[i] : (int64_t)pos[i] - (int64_t)pos[i - 1];
         if (d < 0 || d > 255) { dpos[i] = 0; exc[(size_t)t].emplace_back((uint32_t)i, (int32_t)d); }
         else dpos[i] = (uint8_t)d;
-        if (h.flag_wide) fidx16[i] = flag[i]; else fidx8[i] = (uint8_t)fslot[flag[i]];
         const uint32_t nc = cig_off[i + 1] - cig_off[i];
         const int k = dict_find(cig + cig_off[i], nc);
-        if (k >= 0) cclass[i] = (uint8_t)k;
-        else if (nc <= 127) { cclass[i] = (uint8_t)(128 + nc); xc += nc; }
-        else { too_long[(size_t)t] = 1; cclass[i] = 128; }
+        if (k >= 0) cls[(size_t)i] = (uint8_t)k;
+        else if (nc <= 127) { cls[(size_t)i] = (uint8_t)(128 + nc); xc += nc; }
+        else { too_long[(size_t)t] = 1; cls[(size_t)i] = 128; }
       }
       xcount[(size_t)t + 1] = xc;
     });
     for (int t = 0; t < n_threads; ++t) if (too_long[(size_t)t]) return MCOV_ERR_RANGE;
+    // ---- joint table: the 255 most frequent (flag, class) pairs of a sample of the batch ----
+    std::vector<uint32_t> jt;
+    std::vector<int16_t> jslot(1u << 16, -1);                 // hash table over (flag << 8 | class), open addressing
+    std::vector<uint32_t> jkey(1u << 16, 0xFFFFFFFFu);
+    {
+      std::vector<uint32_t> cnt(1u << 16, 0);
+      auto slot_of = [&](uint32_t key) -> uint32_t {
+        uint32_t hsh = (key * 2654435761u) >> 16;
+        for (int probe = 0; probe < 65536; ++probe) {
+          const uint32_t sl = (hsh + (uint32_t)probe) & 0xFFFFu;
+          if (jkey[sl] == key || jkey[sl] == 0xFFFFFFFFu) return sl;
+        }
+        return 0xFFFFFFFFu;
+      };
+      size_t distinct = 0;
+      for (int64_t i = 0; i < n; i += step) {
+        const uint32_t key = ((uint32_t)flag[i] << 8) | cls[(size_t)i];
+        if (distinct >= 60000) break;                          // (a pathological batch: enough candidates seen)
+        const uint32_t sl = slot_of(key);
+        if (sl == 0xFFFFFFFFu) break;
+        if (jkey[sl] == 0xFFFFFFFFu) { jkey[sl] = key; ++distinct; }
+        ++cnt[sl];
+      }
+      std::vector<uint32_t> order;
+      for (uint32_t sl = 0; sl < (1u << 16); ++sl) if (jkey[sl] != 0xFFFFFFFFu) order.push_back(sl);
+      std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return cnt[x] > cnt[y]; });
+      if (order.size() > 255) order.resize(255);
+      for (uint32_t sl : order) { jslot[sl] = (int16_t)jt.size(); jt.push_back(jkey[sl]); }
+    }
+    auto jt_find = [&](uint32_t key) -> int {
+      uint32_t hsh = (key * 2654435761u) >> 16;
+      for (int probe = 0; probe < 65536; ++probe) {
+        const uint32_t sl = (hsh + (uint32_t)probe) & 0xFFFFu;
+        if (jkey[sl] == key) return jslot[sl];
+        if (jkey[sl] == 0xFFFFFFFFu) return -1;
+      }
+      return -1;
+    };
+    h.off_fc = (uint32_t)o;
+    uint8_t* fc = reinterpret_cast<uint8_t*>(base + o);
+    o += al16(n1);
+    h.off_jt = (uint32_t)o;
+    h.n_jt = (int32_t)jt.size();
+    std::memset(base + o, 0, 1024);
+    std::memcpy(base + o, jt.data(), jt.size() * 4);           // entry: flag << 8 | class
+    o += al16(1024);
+    h.off_xops = (uint32_t)o;
+    uint32_t* xops = reinterpret_cast<uint32_t*>(base + o);
     for (int t = 0; t < n_threads; ++t) xcount[(size_t)t + 1] += xcount[(size_t)t];
     h.n_xops = xcount[(size_t)n_threads];
+    // ---- per-read pass 2 (parallel): joint-table indices (escapes listed), explicit ops ----
+    std::vector<std::vector<uint32_t>> esc((size_t)n_threads);
     par_for(n, n_threads, [&](int t, int64_t a, int64_t b) {
       int64_t w = xcount[(size_t)t];
       for (int64_t i = a; i < b; ++i) {
-        if (cclass[i] < 128) continue;
-        const uint32_t nc = cclass[i] - 128u;
-        std::memcpy(xops + w, cig + cig_off[i], (size_t)nc * 4);
-        w += nc;
+        const int k = jt_find(((uint32_t)flag[i] << 8) | cls[(size_t)i]);
+        if (k >= 0) fc[i] = (uint8_t)k; else { fc[i] = 255; esc[(size_t)t].push_back((uint32_t)i); }
+        if (cls[(size_t)i] >= 128) {
+          const uint32_t nc = cls[(size_t)i] - 128u;
+          std::memcpy(xops + w, cig + cig_off[i], (size_t)nc * 4);
+          w += nc;
+        }
       }
     });
     o += al16((size_t)h.n_xops * 4 + 16);
+    // ---- escapes ----
+    size_t n_esc = 0;
+    for (auto& v : esc) n_esc += v.size();
+    h.n_esc = (int64_t)n_esc;
+    h.off_esc_idx = (uint32_t)o;
+    uint32_t* qi = reinterpret_cast<uint32_t*>(base + o);
+    o += al16(std::max<size_t>(n_esc, 1) * 4);
+    h.off_esc_flag = (uint32_t)o;
+    uint16_t* qf = reinterpret_cast<uint16_t*>(base + o);
+    o += al16(std::max<size_t>(n_esc, 1) * 2);
+    h.off_esc_cls = (uint32_t)o;
+    uint8_t* qc = reinterpret_cast<uint8_t*>(base + o);
+    o += al16(std::max<size_t>(n_esc, 1));
+    { size_t k = 0; for (auto& v : esc) for (uint32_t i : v) { qi[k] = i; qf[k] = flag[i]; qc[k] = cls[i]; ++k; } }
     // ---- exceptions ----
     size_t n_exc = 0;
     for (auto& v : exc) n_exc += v.size();

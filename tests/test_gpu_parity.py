@@ -596,7 +596,7 @@ def test_block_transport_equals_soa_path():
     b, _ = synth.generate_host(w)
     with engine_for(w.contig_len) as eng:
         blk = pack_block(b, w.n_contigs, pinned=True)
-        assert blk[1] < 4.0 * len(b.tid)
+        assert blk[1] < 3.0 * len(b.tid)
         eng.depth_sorted_block(blk)
         want, dflat, off, info = oracle_depth(b, w.contig_len)
         for c, d in enumerate(full_depth(eng)):
