@@ -608,7 +608,10 @@ def run_ours(args):
     peak, peak_src = peaks()
     flag = dbatch.flag.to(torch.int32) & 0xFFFF
     passing = ((flag & 0x704) == 0) & ~(((flag & 1) != 0) & ((flag & 2) == 0)) & ((flag & 4) == 0)
-    ncig = (dbatch.cig_off[1:].to(torch.int64) & 0xFFFFFFFF) - (dbatch.cig_off[:-1].to(torch.int64) & 0xFFFFFFFF)
+    if dbatch.cig_off.dtype == torch.int64:                       # 64-bit offsets (a batch of 2^32 or more ops)
+        ncig = dbatch.cig_off[1:] - dbatch.cig_off[:-1]
+    else:
+        ncig = (dbatch.cig_off[1:].to(torch.int64) & 0xFFFFFFFF) - (dbatch.cig_off[:-1].to(torch.int64) & 0xFFFFFFFF)
     cig_pass = int((ncig * passing).sum().item())
     n_pass = int(passing.sum().item())
     slots = eng.n_slots
@@ -616,7 +619,10 @@ def run_ours(args):
     alg_bytes = {
         "k_fused_prep": 15 * n_reads + 4 * cig_pass + 4 * n_reads,      # SoA + CIGAR ops in, 4-byte records out
         "k_fused_tile": 4 * n_reads + 4 * slots,                        # records in, depth out
+        "k_fused_prep_tma": 15 * n_reads + 4 * cig_pass + 4 * n_reads,  # (the TMA-staged kernels move the same bytes)
+        "k_fused_tile_tma": 4 * n_reads + 4 * slots,
         "k_region_stats": 4 * int(lengths[lengths > 8192].astype(np.int64).sum()) + 64 * int((lengths > 8192).sum()),
+        "k_stats_stream": 4 * int(lengths[lengths > 8192].astype(np.int64).sum()) + 64 * int((lengths > 8192).sum()),
         "k_region_stats_warp": 4 * int(lengths[lengths <= 8192].astype(np.int64).sum()) + 64 * int((lengths <= 8192).sum()),
         "k_expand": 15 * n_reads + 4 * cig_pass + 8 * n_pass,
         "k_scan_inplace": 8 * slots,
@@ -675,7 +681,7 @@ def run_ours(args):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": {"workload": workload_label(args.workload, world, w), "scale": args.scale,
-                   "path": ("fused sorted path (k_fused_prep, k_fused_tile)" if args.path == "fused" else
+                   "path": ("fused sorted path (k_fused_prep_tma, k_fused_tile_tma, k_stats_stream)" if args.path == "fused" else
                             "push path (memset, k_expand, k_scan_inplace): the any-order formulation"),
                    "per_gpu": {"reads": n_reads, "contigs": g, "slots": int(slots)},
                    "regions": "one whole-contig region per contig (reference util.py:64-69)",

@@ -220,7 +220,7 @@ int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a, int64_t tile_lo = -1,
     if (tma) {
       const int64_t n_chunks = (n + kPtChunk - 1) / kPtChunk;
       const unsigned grid = (unsigned)std::min<int64_t>(n_chunks, (int64_t)ctx->n_sm * MCOV_PREP_CTAS);
-      MCOV_LAUNCH(ctx, kKFusedPrep, (k_fused_prep_tma<<<grid, kPtThreads, kPtSmemBytes, s>>>(f)));
+      MCOV_LAUNCH(ctx, kKFusedPrepTma, (k_fused_prep_tma<<<grid, kPtThreads, kPtSmemBytes, s>>>(f)));
     } else if (off64) MCOV_LAUNCH(ctx, kKFusedPrep, (k_fused_prep<true><<<grid_for(ctx, groups, kPrepThreads, 8), kPrepThreads, 0, s>>>(f)));
     else MCOV_LAUNCH(ctx, kKFusedPrep, (k_fused_prep<false><<<grid_for(ctx, groups, kPrepThreads, 8), kPrepThreads, 0, s>>>(f)));
     CU(cudaGetLastError());
@@ -244,7 +244,7 @@ int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a, int64_t tile_lo = -1,
     } else {
       // warp-specialised: producer warp + TMA record ring + 4 consumer warps (k_tile_tma.cuh); persistent
       const unsigned grid = (unsigned)std::min<int64_t>(f.tile_hi - f.tile_lo, (int64_t)ctx->n_sm * MCOV_TT_CTAS);
-      MCOV_LAUNCH(ctx, kKFusedTile, CU(launch_pdl(pdl, k_fused_tile_tma, dim3(std::max(grid, 1u)), dim3(kTtThreads), 0, s, f)));
+      MCOV_LAUNCH(ctx, kKFusedTileTma, CU(launch_pdl(pdl, k_fused_tile_tma, dim3(std::max(grid, 1u)), dim3(kTtThreads), 0, s, f)));
     }
   }
   // htslib's max_depth cap: replayed on the device, in stream order, where the tile kernel found that
@@ -357,7 +357,7 @@ int block_stage(mcov_ctx* ctx, const void* block, int64_t bytes, ExpandArgs& a, 
   b.cls = ctx->d_end_slot.as<uint8_t>() + (size_t)off_len * 4;
   b.tid = st.tid.as<int32_t>(); b.pos = st.pos.as<int32_t>(); b.flag = st.flag.as<uint16_t>(); b.mapq = st.mapq.as<uint8_t>();
   b.cig_off = st.cig_off.as<uint32_t>(); b.cig = st.cig.as<uint32_t>();
-  ctx->prof_begin(kKDeltaUnpack);
+  ctx->prof_begin(kKBlockUnpack);
   k_block_seed<<<(unsigned)((off_len + 255) / 256), 256, 0, s>>>(b);
   if (h.n_esc) k_block_patch<<<(unsigned)((h.n_esc + 255) / 256), 256, 0, s>>>(b);
   k_block_counts<<<(unsigned)((off_len + 255) / 256), 256, 0, s>>>(b);
@@ -375,7 +375,7 @@ int block_stage(mcov_ctx* ctx, const void* block, int64_t bytes, ExpandArgs& a, 
     if (h.n_xops) MCOV_LAUNCH(ctx, kKScanCounts, (k_scan_inplace<false><<<(unsigned)tiles, kScanThreads, 0, s>>>(reinterpret_cast<int32_t*>(b.xoff), off_len, stw + 2 * tiles, pc_of(ctx))));
     CU(cudaGetLastError());
   }
-  MCOV_LAUNCH(ctx, kKDeltaUnpack, (k_block_finish<<<grid_for(ctx, n1, 256, 8), 256, 0, s>>>(b)));
+  MCOV_LAUNCH(ctx, kKBlockUnpack, (k_block_finish<<<grid_for(ctx, n1, 256, 8), 256, 0, s>>>(b)));
   CU(cudaGetLastError());
   std::memset(&a, 0, sizeof(a));
   a.n = n;
@@ -1006,7 +1006,8 @@ static const char* kKernelNames[kKernelCount] = {
     "k_init_region_stats", "k_region_stats", "k_window_sums", "k_isize_hist", "k_group_count", "k_sorted_stats",
     "memset_depth", "k_region_stats_small", "k_cap_replay", "k_unpack_reads", "k_kmer_hist", "k_region_stats_warp",
     "k_exp_prep", "k_exp_entries", "k_exp_region", "k_exp_revsum", "k_region_hist", "k_hist_finish", "k_run_count", "k_run_offsets", "k_run_write", "k_run_ends",
-    "k_bgzf_inflate", "k_bam_guess", "k_bam_walk_count", "k_bam_walk_write", "k_delta_unpack", "k_stream_accumulate"};
+    "k_bgzf_inflate", "k_bam_guess", "k_bam_walk_count", "k_bam_walk_write", "k_delta_unpack", "k_stream_accumulate",
+    "k_fused_prep_tma", "k_fused_tile_tma", "k_stats_stream", "k_stats_split_finish", "k_block_unpack"};
 
 int mcov_copy_to_host(mcov_ctx* ctx, const void* dev, void* host, int64_t n_bytes) {
   if (!ctx) return MCOV_ERR_ARG;
@@ -1222,9 +1223,9 @@ static int stats_launch(mcov_ctx* ctx, int64_t g, const int32_t* tid, const int3
       a.split_hist = reinterpret_cast<uint32_t*>(ctx->d_ss_pool.as<char>() + (size_t)rp.n_split * sizeof(RegionScratch));
       a.out = d_out; a.breadth_n = breadth_n;
       const bool pdl = ctx->n_slots <= kPdlMaxSlots;
-      MCOV_LAUNCH(ctx, kKRegionStats, CU(launch_pdl(pdl, k_stats_stream, dim3((unsigned)rp.ss_grid), dim3(kSsThreads), (size_t)kSsSmemBytes, s, a)));
+      MCOV_LAUNCH(ctx, kKStatsStream, CU(launch_pdl(pdl, k_stats_stream, dim3((unsigned)rp.ss_grid), dim3(kSsThreads), (size_t)kSsSmemBytes, s, a)));
       if (rp.n_split)
-        MCOV_LAUNCH(ctx, kKHistFinish, CU(launch_pdl(pdl, k_stats_split_finish, dim3((unsigned)rp.n_split), dim3(kSsConsumers), 0, s, a,
+        MCOV_LAUNCH(ctx, kKStatsSplitFinish, CU(launch_pdl(pdl, k_stats_split_finish, dim3((unsigned)rp.n_split), dim3(kSsConsumers), 0, s, a,
                                                      (const int32_t*)ctx->d_ss_split.as<int32_t>())));
     } else if (rp.n_tasks) {
       StatArgs a;

@@ -261,8 +261,8 @@ class CoverageEngine:
 
     def profile_read(self):
         """{kernel name: (launches, total_ms)} of the CUDA-event timing since profile(True)."""
-        arr = (_capi.KernelTime * 32)()
-        n = lib.mcov_profile_read(self._ctx, arr, 32)
+        arr = (_capi.KernelTime * 48)()
+        n = lib.mcov_profile_read(self._ctx, arr, 48)
         if n < 0:
             self._check(n)
         return {arr[i].name.decode(): (arr[i].launches, arr[i].total_ms) for i in range(n)}
