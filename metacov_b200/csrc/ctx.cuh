@@ -93,6 +93,8 @@ struct mcov_ctx {
 
   mcov_filter filt;
   uint32_t flag_lut[128] = {0};   // the flag part of the filter as a 4096-bit table (rebuilt by mcov_set_filter)
+  bool flag_lut_dirty = true;
+  mcov::DevBuf d_flag_lut;        // its device copy
   int state = mcov::kIdle;
 
   mcov::DevBuf d_pc;          // PassCounters

@@ -79,7 +79,8 @@ struct FusedArgs {
   uint32_t heavy_min;
   int32_t max_depth;          // htslib maxcnt (<= 0: cap disabled)
   int vec_ok;                 // SoA base pointers aligned for 128-bit loads
-  uint32_t flag_lut[128];     // bit F of the table: a read with flag F (< 4096: the 12 bits BAM defines) passes the flag filter
+  const uint32_t* flag_lut;   // device, [128]: bit F of the table: a read with flag F (< 4096: the 12 bits BAM defines) passes the
+                              // flag filter (kept out of the argument block: kernel parameters are copied at every launch)
 };
 
 // slot key of a read: contig offset + clamped position; reads without a valid

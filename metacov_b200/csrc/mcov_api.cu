@@ -81,6 +81,7 @@ void build_flag_lut(mcov_ctx* ctx) {
     if (f.ignore_orphans && (F & 0x1u) && !(F & 0x2u)) p = false;
     if (p) ctx->flag_lut[F >> 5] |= 1u << (F & 31u);
   }
+  ctx->flag_lut_dirty = true;
 }
 
 int ensure_depth(mcov_ctx* ctx) {
@@ -189,6 +190,11 @@ int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a, int64_t tile_lo = -1,
   f.rec = ctx->d_start_slot.as<uint32_t>();
   f.n_slots = ctx->n_slots;
   f.n_tiles = n_tiles;
+  if (ctx->flag_lut_dirty) {                                  // the filter changed: refresh the device copy of its flag table
+    CU(ctx->d_flag_lut.ensure(sizeof(ctx->flag_lut)));
+    CU(cudaMemcpyAsync(ctx->d_flag_lut.p, ctx->flag_lut, sizeof(ctx->flag_lut), cudaMemcpyHostToDevice, s));
+    ctx->flag_lut_dirty = false;
+  }
   f.tile_lo = 0; f.tile_hi = n_tiles; f.streaming = 0;
   if (tile_lo >= 0) { f.tile_lo = tile_lo; f.tile_hi = std::min(tile_hi, n_tiles); f.streaming = 1; }
   f.far_end = ctx->d_far_list.as<int64_t>();
@@ -205,7 +211,7 @@ int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a, int64_t tile_lo = -1,
   f.depth = ctx->depth;
   f.tile_cap = reinterpret_cast<int32_t*>(z + o_cap);
   f.max_depth = ctx->filt.max_depth;
-  std::memcpy(f.flag_lut, ctx->flag_lut, sizeof(f.flag_lut));
+  f.flag_lut = ctx->d_flag_lut.as<uint32_t>();
   auto al = [](const void* p, uintptr_t m) { return (reinterpret_cast<uintptr_t>(p) & (m - 1)) == 0; };
   const bool off64 = a.cig_off64 != nullptr;
   f.vec_ok = (n > 0 && al(a.tid, 16) && al(a.pos, 16) && al(off64 ? (const void*)a.cig_off64 : (const void*)a.cig_off, 16) &&
@@ -470,7 +476,7 @@ void mcov_destroy(mcov_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->d_len, &ctx->d_off, &ctx->depth_own, &ctx->d_pc, &ctx->d_status, &ctx->d_end_slot,
                     &ctx->d_start_slot, &ctx->d_far_list, &ctx->d_tile_cnt, &ctx->d_tile_off, &ctx->d_far_sorted,
                     &ctx->d_tasks, &ctx->d_rlen, &ctx->d_rchunks, &ctx->d_rhist, &ctx->d_pool, &ctx->d_done,
-                    &ctx->d_stream_acc, &ctx->d_ss_pieces, &ctx->d_ss_cta, &ctx->d_ss_split, &ctx->d_ss_pool,
+                    &ctx->d_flag_lut, &ctx->d_stream_acc, &ctx->d_ss_pieces, &ctx->d_ss_cta, &ctx->d_ss_split, &ctx->d_ss_pool,
                     &ctx->d_out, &ctx->d_win_slot, &ctx->d_win_n, &ctx->d_win_out, &ctx->d_htasks, &ctx->d_tile_heavy, &ctx->d_run_tasks, &ctx->d_run_counts, &ctx->d_run_out};
   for (DevBuf* b : bufs) b->release();
   ctx->bam.release();
