@@ -40,7 +40,11 @@ constexpr int kPtStageBytes = kPtOffCig + 4 * kPtCigCap + 16;   // (+16: unpredi
 constexpr int kPtSmemBytes = kPtStages * kPtStageBytes;
 static_assert(kPtStageBytes % 16 == 0, "stage size must keep every stage 16-byte aligned");
 
-struct PtMeta { int64_t chunk; uint32_t a0; uint32_t in_smem; };   // chunk in the stage (-1: no more); first staged op index; ops are in the stage
+struct PtMeta {            // what the producer tells the consumers about a stage
+  int64_t chunk;           // chunk in the stage (-1: no more)
+  uint32_t a0, in_smem;    // first staged op index; the ops are in the stage
+  uint32_t nread, last;    // reads of the chunk; the chunk ends the batch
+};
 
 // Loads + filter + CIGAR reduction of the 4 reads of one consumer thread, from a landed stage.
 // OPS_STAGED: the chunk's ops are in the stage (LDS), else they stayed in global memory.
@@ -52,7 +56,7 @@ __device__ __forceinline__ PrepReads prep_reduce_staged(const FusedArgs& f, cons
   const uint32_t minq = a.filt.min_mapq;
   const int t = threadIdx.x;
   PrepReads R;
-  R.nv = (int)min((int64_t)kPrepPer, max((int64_t)0, a.n - i0));
+  R.nv = min(kPrepPer, max(0, (int)m.nread - kPrepPer * t));
   const int4 t4 = *reinterpret_cast<const int4*>(st + kPtOffTid + 16 + 16 * t);
   const int4 p4 = *reinterpret_cast<const int4*>(st + kPtOffPos + 16 + 16 * t);
   const uint4 o4 = *reinterpret_cast<const uint4*>(st + kPtOffOff + 16 * t);
@@ -158,6 +162,97 @@ __device__ __forceinline__ PrepReads prep_reduce_staged(const FusedArgs& f, cons
   return R;
 }
 
+// prep_emit (k_fused.cuh) for the staged kernel.  Same outputs; the fixed per-thread part of the warp's bookkeeping is
+// trimmed, because this kernel is bound by its instruction count (integer pipe): every thread takes its predecessor read
+// (pvT, pvP) from the stage instead of by shuffle + lane-0 fix-up, the end-of-batch test is a per-chunk flag, and the rare
+// events (tile border, end of batch, far read) share ONE warp vote.
+__device__ __forceinline__ void prep_emit_staged(const FusedArgs& f, const int64_t i0, const PrepReads& R, const int32_t pvT,
+                                                 const int32_t pvP, const bool is_last, const int lane, PrepWarp& W) {
+  const ExpandArgs& a = f.e;
+  const uint32_t n_contigs = (uint32_t)a.n_contigs;
+  const int32_t* T = R.T;
+  const int32_t* P = R.P;
+  const uint32_t* reflen = R.reflen;
+  const unsigned passm = R.passm;
+  const int32_t Tw = __shfl_sync(0xffffffffu, T[0], 0);
+  const bool simple = R.nv == kPrepPer && pvT == Tw && T[0] == Tw && T[1] == Tw && T[2] == Tw && T[3] == Tw &&
+                      (pvP | P[0] | P[1] | P[2] | P[3]) >= 0;
+  if (!(__all_sync(0xffffffffu, simple) && (uint32_t)Tw < n_contigs)) {
+    const PrepAcc pa = prep_general(f, i0, R.nv, T[0], T[1], T[2], T[3], P[0], P[1], P[2], P[3], reflen[0], reflen[1],
+                                    reflen[2], reflen[3], passm, lane);
+    W.n_pass += pa.n_pass; W.aligned += pa.al32; W.max_span = max(W.max_span, pa.max_span); W.unsorted |= pa.unsorted;
+    return;
+  }
+  if (Tw != W.w_tid) {                               // warp-uniform
+    W.w_tid = Tw;
+    const int64_t base = a.contig_off[Tw];
+    W.w_len = (uint32_t)a.contig_len[Tw];
+    W.w_tb = (uint32_t)(base >> kTileShift); W.w_bo = (uint32_t)base & (kTile - 1);
+  }
+  const uint32_t w_len = W.w_len, w_tb = W.w_tb, w_bo = W.w_bo;
+  uint32_t q[4], sq[4], rc[4], sp[4];
+  uint32_t al32 = 0, n_pass = 0;
+  unsigned farmask = 0;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    q[r] = min((uint32_t)P[r], w_len);
+    const uint32_t e = min((uint32_t)P[r] + reflen[r], w_len);     // P >= 0 and reflen < 2^31: no wrap
+    sp[r] = ((passm >> r) & 1u) ? e - q[r] : 0u;
+    sq[r] = w_bo + q[r];
+    rc[r] = sp[r] * (uint32_t)kTile + (sq[r] & (kTile - 1));         // {start offset in its tile, span}: one IMAD
+    n_pass += sp[r] ? 1u : 0u;
+    al32 += sp[r] ? reflen[r] : 0u;
+  }
+  // far reads (span beyond one tile) are the exception: one test on the largest span, the per-read work only when it fires
+  const uint32_t sp_max = max(max(sp[0], sp[1]), max(sp[2], sp[3]));
+  if (sp_max > kNearSpan) {
+    uint32_t near_max = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const bool far = sp[r] > kNearSpan;
+      if (far) { farmask |= 1u << r; rc[r] = (sq[r] & (kTile - 1)) | (kRecFar << kTileShift); }
+      near_max = max(near_max, far ? 0u : sp[r]);
+    }
+    W.max_span = max(W.max_span, near_max);
+  } else {
+    W.max_span = max(W.max_span, sp_max);
+  }
+  W.aligned += al32; W.n_pass += n_pass;
+  *reinterpret_cast<uint4*>(f.rec + i0) = make_uint4(rc[0], rc[1], rc[2], rc[3]);
+  // sorted inside the contig <=> clamped positions never decrease (the predecessor is in the same contig: pvT == Tw)
+  const uint32_t pq = min((uint32_t)pvP, w_len);
+  W.unsorted |= (q[0] < pq || q[1] < q[0] || q[2] < q[1] || q[3] < q[2]) ? 1u : 0u;
+  // tiles relative to the contig's first tile
+  const uint32_t t3 = sq[3] >> kTileShift, ptile = (w_bo + pq) >> kTileShift;
+  if (__any_sync(0xffffffffu, t3 > ptile || is_last || farmask != 0)) {
+    if (__any_sync(0xffffffffu, t3 > ptile || is_last)) {
+      // a tile border inside the warp's reads: the first read of every tile entered writes its index
+      if (__any_sync(0xffffffffu, t3 - ptile > 4u || is_last)) {       // long gaps / end of batch: warp-cooperative
+        prep_tile_boundaries(f.tile_first, i0, kPrepPer, (int64_t)(w_tb + ptile), w_tb + (sq[0] >> kTileShift),
+                             w_tb + (sq[1] >> kTileShift), w_tb + (sq[2] >> kTileShift), w_tb + t3, is_last, a.n,
+                             (uint32_t)f.n_tiles, lane);
+      } else if (t3 > ptile) {
+        uint32_t* __restrict__ tf = f.tile_first + w_tb;
+        uint32_t prev = ptile;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const uint32_t tr = sq[r] >> kTileShift;
+          for (uint32_t T2 = prev + 1; T2 <= tr; ++T2) tf[T2] = (uint32_t)(i0 + r);
+          prev = max(prev, tr);
+        }
+      }
+    }
+    if (__any_sync(0xffffffffu, farmask != 0)) {
+      const int64_t base = a.contig_off[Tw];
+      int64_t e64[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) e64[r] = base + min((uint32_t)P[r] + reflen[r], w_len);
+      prep_far(f, w_tb + (sq[0] >> kTileShift), w_tb + (sq[1] >> kTileShift), w_tb + (sq[2] >> kTileShift), w_tb + t3, e64[0],
+               e64[1], e64[2], e64[3], farmask, lane);
+    }
+  }
+}
+
 // The producer: lane 0 of the last warp.  Chunk c = reads [c*1024, min(n, (c+1)*1024)).  A CTA's first two chunks
 // are blockIdx.x and blockIdx.x + gridDim.x; after that chunks are drawn from a ticket counter (one atomic per
 // chunk, issued two chunks ahead of its use): SMs do not run at the same speed, and with a fixed stride the
@@ -183,7 +278,7 @@ __device__ __forceinline__ void prep_producer(const FusedArgs& f, char* smem, ui
     const unsigned s = it % kPtStages, k = it / kPtStages;
     if (k > 0) mbar_wait_relaxed(&empty[s], (k - 1) & 1);          // the consumers have released this stage
     if (c >= n_chunks) {                                            // no more chunks: tell the consumers
-      meta[s].chunk = -1; meta[s].a0 = 0; meta[s].in_smem = 0;
+      meta[s].chunk = -1; meta[s].a0 = 0; meta[s].in_smem = 0; meta[s].nread = 0; meta[s].last = 0;
       mbar_arrive(&full[s]);
       break;
     }
@@ -209,7 +304,7 @@ __device__ __forceinline__ void prep_producer(const FusedArgs& f, char* smem, ui
     for (uint32_t r = n16; r < nread; ++r) reinterpret_cast<uint8_t*>(st + kPtOffMapq)[r] = a.mapq[r0 + r];
     reinterpret_cast<uint32_t*>(st + kPtOffOff)[nread] = oe;        // offsets: one entry more than reads
     if (fits) for (uint32_t o = max(a1, a0); o < oe; ++o) reinterpret_cast<uint32_t*>(st + kPtOffCig)[o - a0] = a.cig[o];
-    meta[s].chunk = c; meta[s].a0 = a0; meta[s].in_smem = fits ? 1u : 0u;
+    meta[s].chunk = c; meta[s].a0 = a0; meta[s].in_smem = fits ? 1u : 0u; meta[s].nread = nread; meta[s].last = (r0 + nread == n) ? 1u : 0u;
     const uint32_t tx = 2u * (prev + 4u * n4) + 4u * n4 + 2u * n8 + n16 + cig_bytes;
     mbar_arrive_expect_tx(&full[s], tx);
     if (prev + n4) {
@@ -245,25 +340,25 @@ k_fused_prep_tma(const __grid_constant__ FusedArgs f) {
     return;
   }
   PrepWarp W = {0ull, 0u, 0u, 0u, -1, 0u, 0u, 0u};
+  unsigned s = 0, ph = 0;                                       // stage of this iteration and the parity of its "full" phase
 #pragma unroll 1
-  for (unsigned it = 0;; ++it) {
-    const unsigned s = it % kPtStages, k = it / kPtStages;
-    mbar_wait(&s_full[s], k & 1);                               // the chunk has landed
+  for (;; s = (s + 1 == kPtStages) ? 0u : s + 1, ph ^= (s == 0) ? 1u : 0u) {
+    mbar_wait(&s_full[s], ph);                                  // the chunk has landed
     const char* st = pt_smem + (size_t)s * kPtStageBytes;
     const PtMeta m = s_meta[s];
     if (m.chunk < 0) break;
     const int64_t c = m.chunk;
     const int64_t i0 = c * kPtChunk + (int64_t)threadIdx.x * kPrepPer;
-    // the read before this warp's first one (lane 0 only): sortedness and tile border across warps
-    int32_t pvT = -1, pvP = -1;
-    if (lane == 0 && i0 > 0 && i0 - 1 < n) {
-      pvT = reinterpret_cast<const int32_t*>(st + kPtOffTid + 16)[(int)threadIdx.x * kPrepPer - 1];
-      pvP = reinterpret_cast<const int32_t*>(st + kPtOffPos + 16)[(int)threadIdx.x * kPrepPer - 1];
-    }
+    // every thread's predecessor read, straight from the stage (the four reads before the chunk lead it); the very first
+    // read of the batch has none
+    int32_t pvT = reinterpret_cast<const int32_t*>(st + kPtOffTid + 16)[(int)threadIdx.x * kPrepPer - 1];
+    const int32_t pvP = reinterpret_cast<const int32_t*>(st + kPtOffPos + 16)[(int)threadIdx.x * kPrepPer - 1];
+    if (i0 == 0) pvT = -1;
+    const bool is_last = m.last != 0u && (uint32_t)(threadIdx.x * kPrepPer + kPrepPer) == m.nread;
     const PrepReads R = m.in_smem ? prep_reduce_staged<true>(f, st, m, i0, lane, s_lut) : prep_reduce_staged<false>(f, st, m, i0, lane, s_lut);
     __syncwarp();
     if (lane == 0) mbar_arrive(&s_empty[s]);                    // this warp is done with the stage
-    prep_emit(f, i0, R, pvT, pvP, lane, W);
+    prep_emit_staged(f, i0, R, pvT, pvP, is_last, lane, W);
   }
   prep_flush_counters<true>(f.e.pc, W.n_pass, W.aligned, W.unsorted, W.max_span);
 }
