@@ -14,7 +14,7 @@
 //     contiguous in the sorted order), consumers read them from shared memory;
 //   * two barriers per tile instead of three (a thread clears exactly the counter vectors it has
 //     just read), over the four consumer warps only;
-//   * tiles touched by >= 65 536 reads take two 32-bit passes (starts, then ends) over the same
+//   * tiles touched by >= 32 768 reads take two 32-bit passes (starts, then ends) over the same
 //     8 KB of counters instead of a second counter array, so a CTA needs 8 KB + the ring.
 // Tile order: tickets, heavy tiles first, exactly as in k_fused_tile.  A pass may be restricted to
 // the tile range [tile_lo, tile_hi) (streaming: successive batches of a sorted file).
@@ -90,8 +90,8 @@ __device__ __forceinline__ int tt_scatter(const FusedArgs& f, const TtMeta& m, c
   // start is within `reach` slots of the tile; every hit covers the last slot before the tile
   int open = 0;
   if (WHAT != 1) {
-    for (int64_t j = (int64_t)m.r0 - 1 - t; j >= (int64_t)m.jmin; j -= kFusedThreads) {
-      const uint32_t r = tt_rec<ALL_STAGED>(f, m, s_rec, (uint32_t)j);
+    for (uint32_t k = (uint32_t)t; k < m.r0 - m.jmin; k += kFusedThreads) {       // candidate m.r0 - 1 - k (sanitised ranges: jmin <= r0)
+      const uint32_t r = tt_rec<ALL_STAGED>(f, m, s_rec, m.r0 - 1u - k);
       const uint32_t d = (uint32_t)kTile - (r & (kTile - 1));
       if (d > reach) break;
       const uint32_t code = r >> kTileShift;
@@ -184,19 +184,23 @@ k_fused_tile_tma(const __grid_constant__ FusedArgs f) {
   const bool has_far = pc->n_far != 0;                  // else the far tables are all zero and are not read
   int mx = 0, cap = 0;
   int par = 0;
+  unsigned s = 0, ph = 0;                                 // stage of this iteration and the parity of its "full" phase
 #pragma unroll 1
-  for (unsigned it = 0;; ++it, par ^= 1) {
-    const unsigned s = it % kTtStages, k = it / kTtStages;
-    mbar_wait(&s_full[s], k & 1);
+  for (;; par ^= 1, s = (s + 1 == kTtStages) ? 0u : s + 1, ph ^= (s == 0) ? 1u : 0u) {
+    mbar_wait(&s_full[s], ph);
     const TtMeta m = s_meta[s];
     if (m.tile < 0) break;
     const uint32_t* rec = s_rec[s];
-    // every +1 of the tile comes from an own record, a walk-back candidate or a far end: fewer than 65 536 of
-    // them keep both halves of the packed counters from overflowing
+    // every +1 of the tile comes from an own record, a walk-back candidate or a far end: fewer than 32 768 of
+    // them keep both halves of the packed counters within a signed 16-bit value (the scan below subtracts the halves
+    // with one two-way dot product per slot)
     uint32_t touching = m.r1 - m.jmin;
     if (has_far) touching += f.tile_cnt[m.tile] - (m.tile > 0 ? f.tile_cnt[m.tile - 1] : 0u);
-    const bool packed = touching < 65536u;
-    int4 st[kTileVec], en[kTileVec];
+    const bool packed = touching < 32768u;
+    // v[j] = prefix sums of (starts - ends) inside vector j; capv[j] = max over its slots of (prefix before the slot +
+    // starts of the slot): cap[p] = depth[p-1] + starts[p] relative to the vector's incoming depth
+    int4 v[kTileVec];
+    int capv[kTileVec];
     if (packed) {
       int open = (m.r1 - m.jb <= m.nst) ? tt_scatter<0, true>(f, m, rec, s_cnt, reach, has_far)
                                         : tt_scatter<0, false>(f, m, rec, s_cnt, reach, has_far);
@@ -209,10 +213,16 @@ k_fused_tile_tma(const __grid_constant__ FusedArgs f) {
         const int idx = tt_vec_phys(tt_vec(warp, lane, j));
         const int4 c = vs[idx];
         reinterpret_cast<int4*>(s_cnt)[idx] = make_int4(0, 0, 0, 0);      // cleared by the thread that read it
-        en[j] = make_int4((int)((unsigned)c.x >> 16), (int)((unsigned)c.y >> 16), (int)((unsigned)c.z >> 16), (int)((unsigned)c.w >> 16));
-        st[j] = make_int4(c.x & 0xffff, c.y & 0xffff, c.z & 0xffff, c.w & 0xffff);
+        // starts - ends of a packed counter, accumulated: ONE instruction (IDP.2A: lo * 1 + hi * -1 + acc)
+        constexpr int kPlusMinus = 0x0000FF01;
+        v[j].x = __dp2a_lo(c.x, kPlusMinus, 0);
+        v[j].y = __dp2a_lo(c.y, kPlusMinus, v[j].x);
+        v[j].z = __dp2a_lo(c.z, kPlusMinus, v[j].y);
+        v[j].w = __dp2a_lo(c.w, kPlusMinus, v[j].z);
+        capv[j] = max(max(c.x & 0xffff, v[j].x + (c.y & 0xffff)), max(v[j].y + (c.z & 0xffff), v[j].z + (c.w & 0xffff)));
       }
     } else {
+      int4 st[kTileVec], en[kTileVec];
       // dense tile: starts and ends counted in two 32-bit passes over the same counters
       tt_scatter<1, false>(f, m, rec, s_cnt, reach, has_far);
       named_bar_sync<1, kFusedThreads>();
@@ -232,21 +242,18 @@ k_fused_tile_tma(const __grid_constant__ FusedArgs f) {
         const int idx = tt_vec_phys(tt_vec(warp, lane, j));
         en[j] = reinterpret_cast<const int4*>(s_cnt)[idx];
         reinterpret_cast<int4*>(s_cnt)[idx] = make_int4(0, 0, 0, 0);
+        v[j].x = st[j].x - en[j].x;
+        v[j].y = v[j].x + st[j].y - en[j].y;
+        v[j].z = v[j].y + st[j].z - en[j].z;
+        v[j].w = v[j].z + st[j].w - en[j].w;
+        capv[j] = max(max(st[j].x, v[j].x + st[j].y), max(v[j].y + st[j].z, v[j].z + st[j].w));
       }
     }
     // block scan of (starts - ends).  cap[p] = depth[p-1] + starts[p] is folded into one value per vector, relative
     // to the vector's incoming depth.  run[j] = exclusive offset of vector j inside the warp's 512 slots.
-    int4 v[kTileVec];
-    int run[kTileVec], capv[kTileVec];
+    int run[kTileVec];
 #pragma unroll
-    for (int j = 0; j < kTileVec; ++j) {
-      v[j].x = st[j].x - en[j].x;
-      v[j].y = v[j].x + st[j].y - en[j].y;
-      v[j].z = v[j].y + st[j].z - en[j].z;
-      v[j].w = v[j].z + st[j].w - en[j].w;
-      capv[j] = max(max(st[j].x, v[j].x + st[j].y), max(v[j].y + st[j].z, v[j].z + st[j].w));
-      run[j] = v[j].w;
-    }
+    for (int j = 0; j < kTileVec; ++j) run[j] = v[j].w;
     int acc = 0;
     if (kTtBlocked) {
       // the thread's four vectors are consecutive: one warp scan over the threads' totals
@@ -285,7 +292,7 @@ k_fused_tile_tma(const __grid_constant__ FusedArgs f) {
     for (int w = 0; w < kFusedThreads / 32; ++w) off += (w < warp) ? s_warp[w] : 0;
     const int64_t base = m.tile << kTileShift;
     int4* out = reinterpret_cast<int4*>(f.depth + base);
-    const int64_t n_vec = (f.n_slots - base) >> 2;
+    const int n_vec = (int)min((int64_t)(kTile / 4), (f.n_slots - base) >> 2);   // (only the last tile is short)
     int cap_t = 0;
 #pragma unroll
     for (int j = 0; j < kTileVec; ++j) {
