@@ -267,7 +267,11 @@ int  mcov_stream_push_block(mcov_ctx* ctx, const void* block, int64_t bytes, int
  * metacov/pileup.py:18-26) for g regions at once (the loop at cli.py:85-95).
  * tid/start/end are host arrays; 0 <= start <= end.  Positions >= len[tid]
  * count as depth 0 (the reference's vector is end-start long, pileup.py:10-11).
- * breadth_n: threshold of n_geN.  host_out: g structs.  Synchronises. */
+ * breadth_n: threshold of n_geN.  host_out: g structs.  Synchronises.
+ * When the max_depth cap fired in the pass (mcov_pass_info.cap_contigs > 0), a
+ * region that starts inside a replayed contig is replayed again with its own
+ * iterator -- only the reads overlapping it, as bam.pileup(ref, start, end)
+ * feeds htslib (pileup.py:13) -- and its record computed from that. */
 int  mcov_region_stats_run(mcov_ctx* ctx, int64_t g,
                            const int32_t* tid, const int32_t* start, const int32_t* end,
                            int32_t breadth_n, mcov_region_stats* host_out);
@@ -280,9 +284,10 @@ int  mcov_region_stats_run(mcov_ctx* ctx, int64_t g,
  * waits for that slot, delivers the verdict of the pass the statistics belong
  * to and copies the records to host_out.  What cannot be done once a later
  * pass may have overwritten the depth is reported instead of approximated:
- * MCOV_ERR_STATE if that pass needs the max_depth replay or a region's depth
- * left the counting histogram (run the batch again through mcov_depth_sorted +
- * mcov_region_stats_run). */
+ * MCOV_ERR_STATE if the max_depth cap fired in that pass and a region of the
+ * slot starts inside its contig (it needs its own iterator over reads that may
+ * be gone), or a region's depth left the counting histogram (run the batch
+ * again through mcov_depth_sorted + mcov_region_stats_run). */
 int  mcov_region_stats_submit(mcov_ctx* ctx, int64_t g,
                               const int32_t* tid, const int32_t* start, const int32_t* end,
                               int32_t breadth_n, int slot);

@@ -125,6 +125,7 @@ struct mcov_ctx {
   mcov::DevBuf d_ss_pieces, d_ss_cta, d_ss_split, d_ss_pool;
   // streamed passes (mcov_stream_begin / mcov_stream_push)
   mcov::DevBuf d_stream_acc;          // StreamAcc + the carried reads' counts of the current batch
+  mcov::DevBuf d_cap_scratch;         // per-region replays of the max_depth cap (mcov_region_stats_run)
   int64_t stream_tile_lo = 0;         // tiles below this one hold final depth
   int64_t stream_reads = 0;           // distinct reads pushed so far
   bool stream_started = false;        // (count_del = 0 streams: the difference array has been cleared)
@@ -139,6 +140,8 @@ struct mcov_ctx {
     cudaEvent_t done = nullptr;    // records in `buf` (d2h_stream)
     int64_t g = -1;                // -1 = nothing submitted
     bool has_verdict = false;
+    bool has_subregion = false;    // some region starts inside its contig (matters only when the max_depth cap fired)
+    int32_t cap_contigs = 0;       // of the pass the slot's records describe (-1: arrives with the verdict)
     int64_t n_reads = 0;
     std::vector<int32_t> len0;     // regions of length 0 (their records are zeroed, like mcov_region_stats_run)
   } slot[2];

@@ -908,29 +908,14 @@ k_fused_tile(const __grid_constant__ FusedArgs f) {
 // on earlier decisions, so a contig is replayed by ONE thread, in place: the contig's slots are
 // first cleared, kept reads add +1 at their end slot, and the running depth overwrites each slot
 // as the walk passes it.  Only contigs flagged through tile_cap are replayed.
-__global__ void k_cap_replay(FusedArgs f, uint8_t* __restrict__ contig_capped) {
-  pdl_wait();                                       // the tile kernel is complete: cap_metric and tile_cap are final
-  pdl_launch_dependents();
-  // Launched after EVERY fused pass on the same stream, so whatever consumes the depth next
-  // (statistics, copies, exports, pipelined or not) sees the capped depth; one load and out when
-  // the cap cannot fire anywhere (always, in BASELINE's configs).
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= f.e.n_contigs || f.max_depth <= 0) return;
-  if (f.e.pc->cap_metric <= f.max_depth) return;
-  if (f.e.pc->unsorted || f.e.pc->n_far > f.far_cap) return;     // the pass is rejected by the verdict: nothing to replay
-  if (f.streaming) { if (c == 0) f.e.pc->cap_unreplayed = 1u; return; }   // a contig's reads may lie in other batches: reported, not replayed
-  {
-    const int64_t b0 = f.e.contig_off[c];
-    const int64_t T0 = b0 >> kTileShift, T1 = min((b0 + f.e.contig_len[c]) >> kTileShift, f.n_tiles - 1);
-    bool hit = false;
-    for (int64_t T = T0; T <= T1 && !hit; ++T) hit = f.tile_cap[T] > f.max_depth;
-    if (!hit) return;
-  }
-  atomicAdd(&f.e.pc->cap_contigs, 1u);
-  contig_capped[c] = 1;
+//
+// The recurrence for one contig.  d[0 .. len] receives the capped depth (contig-relative positions; d[len] = sentinel 0).
+// Only reads overlapping [rs, re) take part (rs = 0, re > len: every read of the contig -- the whole-contig iterator;
+// else the reads `bam.fetch(ref, rs, re)` hands the per-region iterator pysam builds for pileup(ref, rs, re), reference
+// metacov/cli.py:85-95 -> pileup.py:13).
+__device__ void cap_replay_contig(const FusedArgs& f, const int c, int32_t* d, const int64_t rs, const int64_t re) {
   const int64_t base = f.e.contig_off[c];
   const int32_t len = f.e.contig_len[c];
-  int32_t* d = f.depth + base;
   for (int32_t p = 0; p <= len; ++p) d[p] = 0;
   // Reads in file order from the first read of the tile holding the contig's first slot.  A
   // record stores its start relative to its tile; the tile follows from tile_first.
@@ -956,21 +941,19 @@ __global__ void k_cap_replay(FusedArgs f, uint8_t* __restrict__ contig_capped) {
       uint32_t code = f.rec[j] >> kTileShift;
       ++j;
       if (code == 0) continue;                      // filtered / empty read
+      int64_t span = code;
+      if (code == kRecFar) {                        // long span: not in the record, reduce the CIGAR again
+        int64_t rl = 0;
+        const uint64_t o0 = f.e.cig_off64 ? f.e.cig_off64[j - 1] : f.e.cig_off[j - 1];
+        const uint64_t o1 = f.e.cig_off64 ? f.e.cig_off64[j] : f.e.cig_off[j];
+        for (uint64_t o = o0; o < o1; ++o) rl += cigar_ref_len(f.e.cig[o]);
+        int64_t e = (int64_t)p + rl;
+        span = (e > len ? len : e) - p;
+      }
+      if (!((int64_t)p + span > rs && (int64_t)p < re)) continue;     // not among the reads this iterator is given
       bool keep = first || (depth + kept) < maxcnt; // depth = D[p-1] = reads buffered from earlier positions
       first = false;
-      if (keep) {
-        ++kept;
-        int64_t span = code;
-        if (code == kRecFar) {                      // long span: not in the record, reduce the CIGAR again
-          int64_t rl = 0;
-          const uint64_t o0 = f.e.cig_off64 ? f.e.cig_off64[j - 1] : f.e.cig_off[j - 1];
-          const uint64_t o1 = f.e.cig_off64 ? f.e.cig_off64[j] : f.e.cig_off[j];
-          for (uint64_t o = o0; o < o1; ++o) rl += cigar_ref_len(f.e.cig[o]);
-          int64_t e = (int64_t)p + rl;
-          span = (e > len ? len : e) - p;
-        }
-        d[p + span] += 1;
-      }
+      if (keep) { ++kept; d[p + span] += 1; }
     }
     int32_t ends = d[p];
     depth += kept - ends;
@@ -983,6 +966,40 @@ __global__ void k_cap_replay(FusedArgs f, uint8_t* __restrict__ contig_capped) {
     }
   }
   d[len] = 0;                                       // sentinel slot
+}
+
+__global__ void k_cap_replay(FusedArgs f, uint8_t* __restrict__ contig_capped) {
+  pdl_wait();                                       // the tile kernel is complete: cap_metric and tile_cap are final
+  pdl_launch_dependents();
+  // Launched after EVERY fused pass on the same stream, so whatever consumes the depth next
+  // (statistics, copies, exports, pipelined or not) sees the capped depth; one load and out when
+  // the cap cannot fire anywhere (always, in BASELINE's configs).
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= f.e.n_contigs || f.max_depth <= 0) return;
+  if (f.e.pc->cap_metric <= f.max_depth) return;
+  if (f.e.pc->unsorted || f.e.pc->n_far > f.far_cap) return;     // the pass is rejected by the verdict: nothing to replay
+  if (f.streaming) { if (c == 0) f.e.pc->cap_unreplayed = 1u; return; }   // a contig's reads may lie in other batches: reported, not replayed
+  {
+    const int64_t b0 = f.e.contig_off[c];
+    const int64_t T0 = b0 >> kTileShift, T1 = min((b0 + f.e.contig_len[c]) >> kTileShift, f.n_tiles - 1);
+    bool hit = false;
+    for (int64_t T = T0; T <= T1 && !hit; ++T) hit = f.tile_cap[T] > f.max_depth;
+    if (!hit) return;
+  }
+  atomicAdd(&f.e.pc->cap_contigs, 1u);
+  contig_capped[c] = 1;
+  cap_replay_contig(f, c, f.depth + f.e.contig_off[c], 0, (int64_t)f.e.contig_len[c] + 1);
+}
+
+// Per-REGION replay (mcov_region_stats_run, regions that do not start at 0 inside a capped contig): pysam builds a fresh
+// iterator per pileup(ref, start, end) call and gives it only the reads overlapping the region, so fewer reads are
+// buffered when the pile is reached and a few more of it are kept than the whole-contig iterator keeps.  One thread per
+// region; the capped depth of the region's contig under THAT iterator goes to scratch[off[k] .. off[k] + len].
+__global__ void k_cap_replay_region(FusedArgs f, int n_reg, const int32_t* __restrict__ r_tid, const int32_t* __restrict__ r_start,
+                                    const int32_t* __restrict__ r_end, const int64_t* __restrict__ scratch_off, int32_t* scratch) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_reg) return;
+  cap_replay_contig(f, r_tid[k], scratch + scratch_off[k], r_start[k], r_end[k]);
 }
 
 // ---- compact host transport (mcov_depth_sorted_packed) ---------------------------------------------

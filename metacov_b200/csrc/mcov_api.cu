@@ -476,7 +476,7 @@ void mcov_destroy(mcov_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->d_len, &ctx->d_off, &ctx->depth_own, &ctx->d_pc, &ctx->d_status, &ctx->d_end_slot,
                     &ctx->d_start_slot, &ctx->d_far_list, &ctx->d_tile_cnt, &ctx->d_tile_off, &ctx->d_far_sorted,
                     &ctx->d_tasks, &ctx->d_rlen, &ctx->d_rchunks, &ctx->d_rhist, &ctx->d_pool, &ctx->d_done,
-                    &ctx->d_flag_lut, &ctx->d_stream_acc, &ctx->d_ss_pieces, &ctx->d_ss_cta, &ctx->d_ss_split, &ctx->d_ss_pool,
+                    &ctx->d_cap_scratch, &ctx->d_flag_lut, &ctx->d_stream_acc, &ctx->d_ss_pieces, &ctx->d_ss_cta, &ctx->d_ss_split, &ctx->d_ss_pool,
                     &ctx->d_out, &ctx->d_win_slot, &ctx->d_win_n, &ctx->d_win_out, &ctx->d_htasks, &ctx->d_tile_heavy, &ctx->d_run_tasks, &ctx->d_run_counts, &ctx->d_run_out};
   for (DevBuf* b : bufs) b->release();
   ctx->bam.release();
@@ -1298,6 +1298,53 @@ int mcov_region_stats_run(mcov_ctx* ctx, int64_t g, const int32_t* tid, const in
   CU(cudaStreamSynchronize(s));
   if (ctx->verdict_pending) { PassCounters h = *hp; int vr = fused_verdict(ctx, h); if (vr) return vr; }
   if (g > 0 && !direct) std::memcpy(host_out, stage, out_bytes);
+  // htslib's cap fired in this pass (rare: a pile deeper than max_depth).  The depth store holds the replay of the
+  // WHOLE-CONTIG iterator; the reference builds one iterator per region (metacov/cli.py:85-95 -> pileup.py:13), which is
+  // given only the reads overlapping the region.  For a region that starts at 0 the two agree; every other region of
+  // a capped contig is replayed with its own iterator into scratch memory and its record recomputed from that.
+  if (ctx->cap_contigs > 0 && g > 0 && ctx->state == kDepthReady && !ctx->fused_blob.empty()) {
+    std::vector<uint8_t> capped((size_t)ctx->n_contigs);
+    CU(cudaMemcpyAsync(capped.data(), ctx->cap_flags, (size_t)ctx->n_contigs, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    std::vector<int32_t> idx, rt, rs_, re_;
+    std::vector<int64_t> soff;
+    int64_t tot = 0;
+    for (int64_t i = 0; i < g; ++i) {
+      if (!capped[(size_t)tid[i]] || start[i] <= 0 || end[i] <= start[i] || start[i] >= ctx->len[tid[i]]) continue;
+      idx.push_back((int32_t)i); rt.push_back(tid[i]); rs_.push_back(start[i]); re_.push_back(end[i]);
+      soff.push_back(tot);
+      tot += ((int64_t)ctx->len[tid[i]] + 1 + 3) & ~(int64_t)3;
+    }
+    if (!idx.empty()) {
+      const size_t k = idx.size();
+      FusedArgs f;
+      std::memcpy(&f, ctx->fused_blob.data(), sizeof(f));
+      CU(ctx->d_cap_scratch.ensure((size_t)tot * 4 + k * 20 + 64));
+      char* sb = ctx->d_cap_scratch.as<char>();
+      int32_t* d_scr = reinterpret_cast<int32_t*>(sb);
+      int64_t* d_soff = reinterpret_cast<int64_t*>(sb + (((size_t)tot * 4 + 7) & ~(size_t)7));
+      int32_t* d_rt = reinterpret_cast<int32_t*>(d_soff + k);
+      int32_t* d_rs = d_rt + k;
+      int32_t* d_re = d_rs + k;
+      CU(cudaMemcpyAsync(d_soff, soff.data(), k * 8, cudaMemcpyHostToDevice, s));
+      CU(cudaMemcpyAsync(d_rt, rt.data(), k * 4, cudaMemcpyHostToDevice, s));
+      CU(cudaMemcpyAsync(d_rs, rs_.data(), k * 4, cudaMemcpyHostToDevice, s));
+      CU(cudaMemcpyAsync(d_re, re_.data(), k * 4, cudaMemcpyHostToDevice, s));
+      MCOV_LAUNCH(ctx, kKCapReplay, (k_cap_replay_region<<<(unsigned)((k + 31) / 32), 32, 0, s>>>(f, (int)k, d_rt, d_rs, d_re, d_soff, d_scr)));
+      CU(cudaGetLastError());
+      for (size_t q = 0; q < k; ++q) {
+        const int64_t i = idx[q];
+        const int64_t len = ctx->len[tid[i]];
+        const int64_t cs = std::min<int64_t>(start[i], len), ce = std::min<int64_t>(end[i], len);
+        int rc = mcov_order_stats_by_sort(ctx, d_scr + soff[q] + cs, ce - cs, (int64_t)end[i] - start[i] - (ce - cs), breadth_n,
+                                          ctx->d_out.as<mcov_region_stats>() + i, ctx->d_win_slot, ctx->d_win_out);
+        if (rc) return fail(ctx, rc, "mcov_region_stats_run: per-region cap replay failed");
+        CU(cudaMemcpyAsync(&host_out[i], ctx->d_out.as<mcov_region_stats>() + i, sizeof(mcov_region_stats), cudaMemcpyDeviceToHost, s));
+      }
+      CU(cudaStreamSynchronize(s));
+      for (size_t q = 0; q < k; ++q) host_out[idx[q]].flags &= ~kStatOverflow;     // (the sort path marks its records)
+    }
+  }
   // regions whose depth left the counting histogram's range: exact statistics by a GPU radix sort
   // of the region (rare: needs max_depth raised above 8190)
   bool redo = false;
@@ -1355,7 +1402,12 @@ int mcov_region_stats_submit(mcov_ctx* ctx, int64_t g, const int32_t* tid, const
   sl.g = g;
   sl.n_reads = ctx->n_reads_pushed;
   sl.len0.clear();
-  for (int64_t i = 0; i < g; ++i) if (end[i] == start[i]) sl.len0.push_back((int32_t)i);
+  sl.has_subregion = false;
+  for (int64_t i = 0; i < g; ++i) {
+    if (end[i] == start[i]) sl.len0.push_back((int32_t)i);
+    else if (start[i] > 0) sl.has_subregion = true;
+  }
+  sl.cap_contigs = sl.has_verdict ? -1 : ctx->cap_contigs;
   return MCOV_OK;
 }
 
@@ -1377,7 +1429,14 @@ static int stats_collect_common(mcov_ctx* ctx, int slot, mcov_region_stats** vie
     if ((int64_t)h.n_far > std::min<int64_t>(std::max<int64_t>(sl.n_reads, 1), kFarCapDefault))
       return fail(ctx, MCOV_ERR_RANGE, "mcov_region_stats_collect: too many long-span reads in that pass");
     ctx->cap_contigs = (int32_t)h.cap_contigs;      // (the replay ran on the device before the statistics kernels)
+    sl.cap_contigs = (int32_t)h.cap_contigs;
   }
+  // The device replay is the whole-contig iterator's.  The reference builds one iterator per region, fed the reads that
+  // overlap it (pileup.py:13); a region that does not start at 0 can differ once the cap has fired, and the reads of the
+  // pass may be gone by now: refuse rather than return the other iterator's numbers.
+  if (sl.cap_contigs > 0 && sl.has_subregion)
+    return fail(ctx, MCOV_ERR_STATE, "mcov_region_stats_collect: max_depth fired in that pass and a region starts inside its contig; "
+                                     "rerun it through mcov_region_stats_run (per-region iterator)");
   mcov_region_stats* rec = sl.buf.as<mcov_region_stats>();
   for (int32_t i : sl.len0) std::memset(&rec[i], 0, sizeof(mcov_region_stats));
   for (int64_t i = 0; i < g; ++i)
