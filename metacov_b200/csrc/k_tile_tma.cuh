@@ -60,7 +60,25 @@ struct TtMeta {
   int64_t tile;           // < 0: no more tiles
   uint32_t r0, r1, jmin;  // own records [r0, r1); walk-back candidates [jmin, r0)
   uint32_t jb, nst;       // records [jb, jb + nst) are in the stage
+  uint32_t touching;      // own records + walk-back candidates + far ends: every +1 the tile can receive
+  int32_t carry;          // far reads open at the tile border
+  int32_t n_vec;          // 16-byte vectors of the tile inside the depth array (only the last tile is short)
+  int32_t pad;
 };
+
+// inclusive warp scan step: x += (value of lane - o), lanes below o unchanged -- the shuffle's own predicate guards the
+// add (two instructions per step; the C++ form `if (lane >= o) x += y` compiles to SHFL + SEL + IADD)
+__device__ __forceinline__ int scan_step_up(int x, int o) {
+  int r;
+  asm volatile("{ .reg .s32 t; .reg .pred p; shfl.sync.up.b32 t|p, %1, %2, 0, 0xffffffff; @p add.s32 t, t, %1; mov.s32 %0, t; }"
+               : "=r"(r) : "r"(x), "r"(o));
+  return r;
+}
+__device__ __forceinline__ int warp_scan_incl(int x) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) x = scan_step_up(x, o);
+  return x;
+}
 
 // ALL_STAGED: every record the tile looks at is in the stage (the normal case, decided once per tile)
 template <bool ALL_STAGED>
@@ -132,9 +150,11 @@ k_fused_tile_tma(const __grid_constant__ FusedArgs f) {
     // ---------------- producer: one thread ----------------
     if (lane != 0) return;
     const uint32_t n_heavy = pc->n_heavy;
+    const bool has_far = pc->n_far != 0;                // else the far tables are all zero and are not read
     const unsigned G = gridDim.x;
     auto resolve = [&](unsigned tk, TtMeta& m) {        // ticket -> tile + its record ranges; tile = -1: skip, -2: past the end
       m.r0 = m.r1 = m.jmin = m.jb = m.nst = 0;
+      m.touching = 0; m.carry = 0; m.n_vec = 0; m.pad = 0;
       int64_t T;
       if (tk < n_heavy) T = f.tile_heavy[tk];
       else {
@@ -146,6 +166,14 @@ k_fused_tile_tma(const __grid_constant__ FusedArgs f) {
       // unsorted input (the pass is rejected by the verdict) leaves tile_first non-monotone: such a tile is treated
       // as empty, so that no copy or index is formed from an inverted range
       if (!(m.jmin <= m.r0 && m.r0 <= m.r1)) m.r0 = m.r1 = m.jmin = 0u;
+      m.touching = m.r1 - m.jmin;
+      m.carry = 0;
+      if (has_far) {
+        const uint32_t k0 = T > 0 ? f.tile_cnt[T - 1] : 0u;
+        m.touching += f.tile_cnt[T] - k0;
+        if (T > 0) m.carry = f.tile_agg[T - 1];
+      }
+      m.n_vec = (int32_t)min((int64_t)(kTile / 4), (f.n_slots - (T << kTileShift)) >> 2);
       m.tile = (tk >= n_heavy && n_heavy != 0 && m.r1 - m.r0 >= f.heavy_min) ? -1 : T;   // a heavy tile met again in position order
     };
     TtMeta m_cur, m_nxt;
@@ -194,9 +222,7 @@ k_fused_tile_tma(const __grid_constant__ FusedArgs f) {
     // every +1 of the tile comes from an own record, a walk-back candidate or a far end: fewer than 32 768 of
     // them keep both halves of the packed counters within a signed 16-bit value (the scan below subtracts the halves
     // with one two-way dot product per slot)
-    uint32_t touching = m.r1 - m.jmin;
-    if (has_far) touching += f.tile_cnt[m.tile] - (m.tile > 0 ? f.tile_cnt[m.tile - 1] : 0u);
-    const bool packed = touching < 32768u;
+    const bool packed = m.touching < 32768u;
     // v[j] = prefix sums of (starts - ends) inside vector j; capv[j] = max over its slots of (prefix before the slot +
     // starts of the slot): cap[p] = depth[p-1] + starts[p] relative to the vector's incoming depth
     int4 v[kTileVec];
@@ -255,7 +281,21 @@ k_fused_tile_tma(const __grid_constant__ FusedArgs f) {
 #pragma unroll
     for (int j = 0; j < kTileVec; ++j) run[j] = v[j].w;
     int acc = 0;
-    if (kTtBlocked) {
+    if (!kTtBlocked && packed) {
+      // the totals of two rows share one scan: |partial sums| < 32 768 in a packed tile, so two signed 16-bit
+      // halves add independently modulo a borrow that the unpacking undoes (lo = sign-extended low half,
+      // hi = (x - lo) >> 16)
+      const int p01 = run[1] * 65536 + run[0], p23 = run[3] * 65536 + run[2];
+      const int x01 = warp_scan_incl(p01), x23 = warp_scan_incl(p23);
+      const int t01 = __shfl_sync(0xffffffffu, x01, 31), t23 = __shfl_sync(0xffffffffu, x23, 31);
+      const int e01 = x01 - p01, e23 = x23 - p23;                          // exclusive, still packed
+      const int e0 = __dp2a_lo(e01, 0x0001, 0), e2 = __dp2a_lo(e23, 0x0001, 0);
+      const int e1 = (e01 - e0) >> 16, e3 = (e23 - e2) >> 16;
+      const int T0 = __dp2a_lo(t01, 0x0001, 0), T2 = __dp2a_lo(t23, 0x0001, 0);
+      const int T1 = (t01 - T0) >> 16, T3 = (t23 - T2) >> 16;
+      run[0] = e0; run[1] = e1 + T0; run[2] = e2 + T0 + T1; run[3] = e3 + T0 + T1 + T2;
+      acc = T0 + T1 + T2 + T3;
+    } else if (kTtBlocked) {
       // the thread's four vectors are consecutive: one warp scan over the threads' totals
       const int t0 = run[0], t1 = t0 + run[1], t2 = t1 + run[2], t3 = t2 + run[3];
       int x = t3;
@@ -285,14 +325,13 @@ k_fused_tile_tma(const __grid_constant__ FusedArgs f) {
     // the other s_open buffer: last read after the previous tile's second barrier (every thread has passed this
     // tile's first barrier since), next added to after this tile's second barrier
     if (threadIdx.x == 0) s_open[par ^ 1] = 0;
-    const int carry = (has_far && m.tile > 0) ? f.tile_agg[m.tile - 1] : 0;     // far reads open at the tile border
     named_bar_sync<1, kFusedThreads>();
-    int off = carry + s_open[par];                       // + near reads open at the border
+    int off = m.carry + s_open[par];                     // far reads + near reads open at the border
 #pragma unroll
     for (int w = 0; w < kFusedThreads / 32; ++w) off += (w < warp) ? s_warp[w] : 0;
     const int64_t base = m.tile << kTileShift;
     int4* out = reinterpret_cast<int4*>(f.depth + base);
-    const int n_vec = (int)min((int64_t)(kTile / 4), (f.n_slots - base) >> 2);   // (only the last tile is short)
+    const int n_vec = m.n_vec;
     int cap_t = 0;
 #pragma unroll
     for (int j = 0; j < kTileVec; ++j) {
