@@ -93,6 +93,24 @@ template <int WHAT, bool ALL_STAGED>
 __device__ __forceinline__ int tt_scatter(const FusedArgs& f, const TtMeta& m, const uint32_t* s_rec, int* s_cnt, uint32_t reach,
                                           bool has_far) {
   const int t = threadIdx.x;
+  if (WHAT == 0 && ALL_STAGED && !kTtBlocked) {
+    // the common case, branch-free: both atomics of every record are issued; an end beyond the tile goes to the spare
+    // counter behind the tile, a record that does not count here (code 0: filtered, or far) to the lane's own spare
+    // counter (spares are never read and never cleared)
+    const uint32_t spare = (uint32_t)kTile + 1u + (threadIdx.x & 31u);
+    const uint32_t* p = s_rec + (m.r0 - m.jb) + t;
+    const uint32_t* const pe = s_rec + (m.r1 - m.jb);
+#pragma unroll 2
+    for (; p < pe; p += kFusedThreads) {
+      const uint32_t r = *p;
+      const uint32_t code = r >> kTileShift, local = r & (kTile - 1);
+      const bool counts = code != 0;
+      const uint32_t a = counts ? local : spare;
+      const uint32_t e = counts ? min(local + code, (uint32_t)kTile) : spare;
+      atomicAdd(&s_cnt[a], 1);
+      atomicAdd(&s_cnt[e], 0x10000);
+    }
+  } else
 #pragma unroll 2
   for (uint32_t j = m.r0 + t; j < m.r1; j += kFusedThreads) {
     const uint32_t r = tt_rec<ALL_STAGED>(f, m, s_rec, j);
@@ -125,7 +143,7 @@ __device__ __forceinline__ int tt_scatter(const FusedArgs& f, const TtMeta& m, c
 
 __global__ void __launch_bounds__(kTtThreads, MCOV_TT_CTAS)
 k_fused_tile_tma(const __grid_constant__ FusedArgs f) {
-  __shared__ __align__(16) int s_cnt[kTile];
+  __shared__ __align__(16) int s_cnt[kTile + 36];       // [kTile ..]: spare counters (tt_scatter)
   __shared__ __align__(16) uint32_t s_rec[kTtStages][kTtStageRecs];
   __shared__ __align__(8) uint64_t s_full[kTtStages], s_empty[kTtStages];
   __shared__ TtMeta s_meta[kTtStages];
