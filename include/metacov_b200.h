@@ -576,6 +576,22 @@ typedef struct mcov_bam_dev {
   const uint8_t*  inflated;
 } mcov_bam_dev;
 int  mcov_bam_decode_gpu(mcov_ctx* ctx, const void* file_bytes, int64_t n_bytes, int verify_crc, mcov_bam_dev* out);
+/* Read names and SEQ of the file last decoded on this context, computed on the
+ * device from the inflated stream (no host reader is opened).  Each output is
+ * optional (NULL = not wanted) and lies in host or device memory per mem_kind:
+ *   name_hash_out  u64[n]  FNV-1a 64 of `read.query_name`, the key of the
+ *                  reference's mate dict (metacov/pileup.py:101-118)
+ *                  == mcov_bam_name_hash;
+ *   kmer_code_out  i32[n]  code of `query_alignment_sequence[0:k_len]`
+ *                  (pileup.py:109-110, 123), -1 = no key  == mcov_bam_qas_kmer;
+ *   seq_win_out    u8[n][(win_bases+1)/2]  the read's first (forward) / last
+ *                  (reverse) win_bases bases as nt16 nibbles, what the k-mer
+ *                  histogram reads (scan.pyx:240-259, 513-520)
+ *                  == mcov_bam_seq_windows.
+ * MCOV_ERR_STATE without a decoded file, MCOV_ERR_IO if a record's SEQ leaves
+ * the record.  Synchronises. */
+int  mcov_bam_gpu_names_seq(mcov_ctx* ctx, int32_t k_len, int32_t win_bases,
+                            uint64_t* name_hash_out, int32_t* kmer_code_out, uint8_t* seq_win_out, int mem_kind);
 /* Test hooks: the device inflate / CRC-32 code (csrc/inflate.cuh) compiled for the host, so that the CPU
  * suite can check it against zlib.  mcov_inflate_host returns 0 or a positive decoder status. */
 int  mcov_inflate_host(const uint8_t* src, uint32_t clen, uint8_t* dst, uint32_t ulen);

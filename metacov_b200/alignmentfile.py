@@ -185,8 +185,8 @@ class AlignmentFile:
         self._gpu = (eng, dsoa)
 
     def _host_handle(self):
-        """The host reader's handle; a GPU-decoded file opens it on first use (read names and sequences --
-        the k-mer histogram and `experimental` -- still come from the host reader)."""
+        """The host reader's handle (a GPU-decoded file never needs it: columns, read names and SEQ all come from
+        the device, bamgpu.DeviceSoA)."""
         if self._h is None:
             self._open_host(self.filename, header=False)
         return self._h
@@ -292,6 +292,8 @@ class AlignmentFile:
     def seq_windows(self, win_bases):
         """uint8[n, (win_bases+1)//2]: per read the first (forward) / last (reverse) win_bases bases,
         nt16 two per byte -- the part of SEQ the k-mer histogram looks at."""
+        if self._gpu is not None:                       # decoded on the GPU: SEQ is read there too
+            return self._gpu[1].names_seq(win_bases=win_bases)["seq_win"]
         n = len(self.soa()["tid"])
         rc = lib.mcov_bam_load_seq(self._host_handle())
         if rc != 0:
@@ -308,6 +310,8 @@ class AlignmentFile:
     # -- pileup.experimental ------------------------------------------------
     def name_hashes(self):
         """uint64[n]: FNV-1a of every read name (the key of the reference's mate dict, pileup.py:101)."""
+        if self._gpu is not None:
+            return self._gpu[1].names_seq(name_hash=True)["name_hash"]
         n = len(self.soa()["tid"])
         rc = lib.mcov_bam_load_seq(self._host_handle())
         if rc != 0:
@@ -316,6 +320,8 @@ class AlignmentFile:
 
     def qas_kmer_codes(self, k_len):
         """int32[n]: code of ``read.query_alignment_sequence[0:k_len]`` (pileup.py:109, 123), -1 = no key."""
+        if self._gpu is not None:
+            return self._gpu[1].names_seq(k_len=k_len)["kmer_code"]
         n = len(self.soa()["tid"])
         rc = lib.mcov_bam_load_seq(self._host_handle())
         if rc != 0:

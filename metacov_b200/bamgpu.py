@@ -37,6 +37,23 @@ class DeviceSoA:
         self._engine._check(lib.mcov_copy_to_host(self._engine._ctx, getattr(self.raw, name), _capi.ptr(out), out.nbytes))
         return out
 
+    def names_seq(self, name_hash=False, k_len=0, win_bases=0):
+        """Read names and SEQ computed on the device from the inflated stream (``mcov_bam_gpu_names_seq``): a dict with
+        ``name_hash`` uint64[n] (FNV-1a of query_name), ``kmer_code`` int32[n] (query_alignment_sequence[0:k_len], -1 = no
+        key) and ``seq_win`` uint8[n, (win_bases+1)//2] (the k-mer histogram's view of SEQ), whichever were asked for."""
+        n = self.n_records
+        out = {}
+        if name_hash:
+            out["name_hash"] = np.empty(n, dtype=np.uint64)
+        if k_len:
+            out["kmer_code"] = np.empty(n, dtype=np.int32)
+        if win_bases:
+            out["seq_win"] = np.empty((n, (win_bases + 1) // 2), dtype=np.uint8)
+        p = lambda k: _capi.ptr(out[k]) if k in out and n else None
+        self._engine._check(lib.mcov_bam_gpu_names_seq(self._engine._ctx, int(k_len), int(win_bases), p("name_hash"),
+                                                       p("kmer_code"), p("seq_win"), _capi.MEM_HOST))
+        return out
+
     def header(self):
         """(text, [(name, length)]) parsed from the inflated stream's header (SAM spec 4.2)."""
         buf = np.empty(self.header_bytes, dtype=np.uint8)

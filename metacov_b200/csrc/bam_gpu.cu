@@ -169,6 +169,7 @@ __global__ void k_bam_walk_count(const uint8_t* __restrict__ d, uint64_t total, 
 
 struct SoaOut {
   int32_t* tid; int32_t* pos; uint16_t* flag; uint8_t* mapq; int32_t* l_seq; int32_t* isize; uint32_t* cig_off; uint32_t* cig;
+  uint64_t* rec_off;      // where the record (its block_size field) starts in the inflated stream
 };
 
 __global__ void k_bam_walk_write(const uint8_t* __restrict__ d, const WalkSeg* __restrict__ segs, int64_t n_seg, SoaOut o) {
@@ -187,11 +188,79 @@ __global__ void k_bam_walk_write(const uint8_t* __restrict__ d, const WalkSeg* _
     o.l_seq[i] = (int32_t)ld32u(r + 16);
     o.isize[i] = (int32_t)ld32u(r + 28);
     o.cig_off[i] = (uint32_t)co;
+    o.rec_off[i] = p;
     const uint8_t* c = r + 32 + l_name;
     for (uint32_t k = 0; k < n_op; ++k) o.cig[co + k] = ld32u(c + 4 * k);
     co += n_op;
     ++i;
     p += 4ull + bs;
+  }
+}
+
+// Read names and SEQ, the parts of a record the coverage path never looks at but `pileup.experimental` and the k-mer
+// histogram do.  One thread per record, straight from the inflated stream:
+//   name_hash[i]  FNV-1a 64 of the read name (the key of the reference's mate dict, metacov/pileup.py:101-118);
+//   kmer_code[i]  2-bit code of query_alignment_sequence[0:k_len] (pileup.py:109-110, 123): SEQ without the soft-clipped
+//                 ends, first base most significant, A0 C1 G2 T3; -1 = shorter than k_len or another letter;
+//   win[i][W]     the first (forward) / last (reverse strand, flag 0x10) win_bases bases, nt16 two per byte, high nibble
+//                 first, missing bases 'N' (15): all of SEQ the k-mer histogram reads (scan.pyx:240-259, 513-520).
+// Same definitions, bit for bit, as the host reader's mcov_bam_name_hash / mcov_bam_qas_kmer / mcov_bam_seq_windows.
+__global__ void k_bam_names_seq(const uint8_t* __restrict__ d, const uint64_t* __restrict__ rec_off, int64_t n, int32_t k_len,
+                                int32_t win_bases, uint64_t* __restrict__ name_hash, int32_t* __restrict__ kmer_code,
+                                uint8_t* __restrict__ win, int* __restrict__ status) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t p = rec_off[i];
+  const uint8_t* r = d + p + 4;
+  const uint32_t bs = ld32u(d + p);
+  const uint32_t l_name = r[8], n_op = ld16u(r + 12), flag = ld16u(r + 14);
+  const int64_t l_seq = (int64_t)ld32u(r + 16);
+  const uint8_t* cig = r + 32 + l_name;
+  const uint8_t* sq = cig + 4ull * n_op;
+  if (32ull + l_name + 4ull * n_op + (uint64_t)((l_seq + 1) / 2) > bs) { atomicExch(status + 2, 1); return; }   // SEQ leaves the record
+  if (name_hash) {
+    uint64_t h = 1469598103934665603ull;
+    for (uint32_t k = 0; k + 1 < l_name; ++k) { h ^= r[32 + k]; h *= 1099511628211ull; }
+    name_hash[i] = h == ~0ull ? h - 1 : h;                     // ~0 is the "no entry" key of the pair sort
+  }
+  auto base = [&](int64_t a) -> uint32_t { const uint32_t b = sq[a >> 1]; return (a & 1) ? (b & 15u) : (b >> 4); };
+  if (kmer_code) {
+    int64_t lo = 0, hi = l_seq;
+    for (uint32_t k = 0; k < n_op; ++k) {                      // leading soft clips (hard clips hold no bases)
+      const uint32_t c = ld32u(cig + 4 * k), op = c & 15u;
+      if (op == 5) continue;
+      if (op == 4) lo += c >> 4; else break;
+    }
+    for (uint32_t k = n_op; k > 0; --k) {
+      const uint32_t c = ld32u(cig + 4 * (k - 1)), op = c & 15u;
+      if (op == 5) continue;
+      if (op == 4) hi -= c >> 4; else break;
+    }
+    int32_t code = hi - lo < k_len ? -1 : 0;
+    for (int32_t j = 0; j < k_len && code >= 0; ++j) {
+      const uint32_t b = base(lo + j);                         // "=ACMGRSVTWYHKDBN": A 1, C 2, G 4, T 8
+      const int c = b == 1 ? 0 : b == 2 ? 1 : b == 4 ? 2 : b == 8 ? 3 : -1;
+      code = c < 0 ? -1 : (code << 2) | c;
+    }
+    kmer_code[i] = code;
+  }
+  if (win) {
+    const int W = (win_bases + 1) / 2;
+    const bool rev = (flag & 0x10u) != 0;
+    uint8_t* o = win + (size_t)i * W;
+    for (int b2 = 0; b2 < W; ++b2) {
+      uint32_t v = 0;
+      for (int h = 0; h < 2; ++h) {
+        const int j = 2 * b2 + h;
+        uint32_t c = 15;
+        if (j < win_bases) {
+          const int64_t a = rev ? l_seq - win_bases + j : j;
+          if (a >= 0 && a < l_seq) c = base(a);
+        }
+        v = (v << 4) | c;
+      }
+      o[b2] = (uint8_t)v;
+    }
   }
 }
 
@@ -368,6 +437,9 @@ extern "C" int mcov_bam_decode_gpu(mcov_ctx* ctx, const void* file_bytes, int64_
   SoaOut o;
   o.tid = B.tid.as<int32_t>(); o.pos = B.pos.as<int32_t>(); o.flag = B.flag.as<uint16_t>(); o.mapq = B.mapq.as<uint8_t>();
   o.l_seq = B.lseq.as<int32_t>(); o.isize = B.isize.as<int32_t>(); o.cig_off = B.cig_off.as<uint32_t>(); o.cig = B.cig.as<uint32_t>();
+  CUB(B.rec_off.ensure((n_rec + 4) * 8));
+  o.rec_off = B.rec_off.as<uint64_t>();
+  B.n_rec = 0;
   if (!segs.empty()) {
     CUB(cudaMemcpyAsync(B.segs.p, segs.data(), segs.size() * sizeof(WalkSeg), cudaMemcpyHostToDevice, s));
     MCOV_LAUNCH(ctx, kKBamWalkWrite, (k_bam_walk_write<<<(unsigned)((segs.size() + 127) / 128), 128, 0, s>>>(
@@ -381,6 +453,43 @@ extern "C" int mcov_bam_decode_gpu(mcov_ctx* ctx, const void* file_bytes, int64_
   out->inflated_bytes = (int64_t)total; out->header_bytes = (int64_t)rec_begin; out->n_segments = (int64_t)segs.size();
   out->tid = o.tid; out->pos = o.pos; out->flag = o.flag; out->mapq = o.mapq; out->l_seq = o.l_seq; out->isize = o.isize;
   out->cig_off = o.cig_off; out->cig = o.cig; out->inflated = B.data.as<uint8_t>();
+  B.n_rec = (int64_t)n_rec;
+  return MCOV_OK;
+}
+
+extern "C" int mcov_bam_gpu_names_seq(mcov_ctx* ctx, int32_t k_len, int32_t win_bases, uint64_t* name_hash_out,
+                                      int32_t* kmer_code_out, uint8_t* seq_win_out, int mem_kind) {
+  if (!ctx) return MCOV_ERR_ARG;
+  mcov_ctx::BamDev& B = ctx->bam;
+  if (B.n_rec < 0 || !B.data.p) return bfail(ctx, MCOV_ERR_STATE, "mcov_bam_gpu_names_seq: no file decoded on this context");
+  if ((kmer_code_out && (k_len <= 0 || k_len > 15)) || (seq_win_out && win_bases <= 0) ||
+      (mem_kind != MCOV_MEM_HOST && mem_kind != MCOV_MEM_DEVICE))
+    return bfail(ctx, MCOV_ERR_ARG, "mcov_bam_gpu_names_seq: bad arguments");
+  const int64_t n = B.n_rec;
+  if (n == 0 || (!name_hash_out && !kmer_code_out && !seq_win_out)) return MCOV_OK;
+  CUB(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const size_t W = seq_win_out ? ((size_t)win_bases + 1) / 2 : 0;
+  const bool dev = mem_kind == MCOV_MEM_DEVICE;
+  uint64_t* d_hash = name_hash_out; int32_t* d_kmer = kmer_code_out; uint8_t* d_win = seq_win_out;
+  if (!dev) {                                                  // results are produced on the device, then copied out
+    if (name_hash_out) { CUB(B.name_hash.ensure((size_t)n * 8)); d_hash = B.name_hash.as<uint64_t>(); }
+    if (kmer_code_out) { CUB(B.kmer.ensure((size_t)n * 4)); d_kmer = B.kmer.as<int32_t>(); }
+    if (seq_win_out) { CUB(B.win.ensure((size_t)n * W)); d_win = B.win.as<uint8_t>(); }
+  }
+  CUB(cudaMemsetAsync(B.status.as<int>() + 2, 0, 4, s));
+  MCOV_LAUNCH(ctx, kKBamNamesSeq, (k_bam_names_seq<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(
+      B.data.as<uint8_t>(), B.rec_off.as<uint64_t>(), n, k_len, win_bases, d_hash, d_kmer, d_win, B.status.as<int>())));
+  CUB(cudaGetLastError());
+  int bad = 0;
+  CUB(cudaMemcpyAsync(&bad, B.status.as<int>() + 2, 4, cudaMemcpyDeviceToHost, s));
+  if (!dev) {
+    if (name_hash_out) CUB(cudaMemcpyAsync(name_hash_out, d_hash, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+    if (kmer_code_out) CUB(cudaMemcpyAsync(kmer_code_out, d_kmer, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    if (seq_win_out) CUB(cudaMemcpyAsync(seq_win_out, d_win, (size_t)n * W, cudaMemcpyDeviceToHost, s));
+  }
+  CUB(cudaStreamSynchronize(s));
+  if (bad) return bfail(ctx, MCOV_ERR_IO, "mcov_bam_gpu_names_seq: a record's SEQ leaves the record");
   return MCOV_OK;
 }
 

@@ -104,6 +104,67 @@ def test_empty_and_corrupt_files(tmp_path):
         assert bamgpu.decode(eng, bytes(raw)).n_records == len(b.tid)                  # the context survives errors
 
 
+def test_names_and_seq_on_the_device(tmp_path):
+    """mcov_bam_gpu_names_seq against the host reader on reads with soft / hard clips, both strands, odd lengths,
+    ambiguity codes, empty SEQ and names of every length; then `experimental` and the k-mer histogram of a
+    GPU-decoded file equal the host-decoded file's without a host reader being opened."""
+    from metacov_b200 import AlignmentFile, ReadBatch, pileup
+    from metacov_b200 import scan as mscan
+    rng = np.random.default_rng(77)
+    n = 6000
+    lengths = np.array([40000, 30000], np.int32)
+    tid = np.sort(rng.integers(0, 2, n)).astype(np.int32)
+    pos = np.zeros(n, np.int32)
+    for c in range(2):
+        m = tid == c
+        pos[m] = np.sort(rng.integers(0, lengths[c] - 400, m.sum()))
+    flag = (rng.integers(0, 2, n) * 0x10 + rng.integers(0, 2, n) * 0x1 + rng.integers(0, 2, n) * 0x2 +
+            rng.choice([0x40, 0x80], n)).astype(np.uint16)
+    cig, off, seqs, names = [], [0], [], []
+    for i in range(n):
+        ops = []
+        if rng.random() < 0.2: ops.append((5, int(rng.integers(1, 9))))
+        if rng.random() < 0.4: ops.append((4, int(rng.integers(1, 30))))
+        ops.append((0, int(rng.integers(1, 120))))
+        if rng.random() < 0.3: ops += [(1, int(rng.integers(1, 5))), (0, int(rng.integers(1, 60)))]
+        if rng.random() < 0.3: ops += [(2, int(rng.integers(1, 5))), (0, int(rng.integers(1, 60)))]
+        if rng.random() < 0.4: ops.append((4, int(rng.integers(1, 30))))
+        if rng.random() < 0.2: ops.append((5, int(rng.integers(1, 9))))
+        qlen = sum(l for o, l in ops if o in (0, 1, 4))
+        if i % 97 == 0:
+            qlen = 0                                         # SEQ "*"
+        cig += [(l << 4) | o for o, l in ops]
+        off.append(len(cig))
+        seqs.append(rng.choice(np.array([1, 2, 4, 8, 15, 1, 2, 4, 8, 1, 2, 4, 8, 3], np.uint8), qlen))
+        names.append("r%d/%s" % (i // 2, "x" * int(rng.integers(0, 40))))
+    b = ReadBatch(tid, pos, flag, np.full(n, 30, np.uint8), np.array(off, np.uint32), np.array(cig, np.uint32))
+    p = _write(tmp_path, "seq.bam", ["c0", "c1"], lengths, b, isize=rng.integers(-600, 600, n).astype(np.int32),
+               names=names, seqs=seqs)
+    with AlignmentFile(p) as host, AlignmentFile(p, decode="gpu") as gpu:
+        assert np.array_equal(gpu.name_hashes(), host.name_hashes())
+        for k in (1, 3, 7, 15):
+            assert np.array_equal(gpu.qas_kmer_codes(k), host.qas_kmer_codes(k)), k
+        for w in (1, 2, 56, 57, 300):
+            assert np.array_equal(gpu.seq_windows(w), host.seq_windows(w)), w
+        kc = [{}, {}]
+        rr = np.random.default_rng(5)
+        for r in range(2):
+            for code in range(4 ** 3):
+                if rr.random() < 0.8:
+                    kc[r]["".join("ACGT"[(code >> (2 * (2 - j))) & 3] for j in range(3))] = float(rr.uniform(0.5, 2.0))
+        for ref, s0, e0 in (("c0", 0, 4000), ("c1", 1000, 9000)):
+            a = pileup.experimental(host, kc, 3, None, ref, s0, e0)
+            g = pileup.experimental(gpu, kc, 3, None, ref, s0, e0)
+            assert a == g, (ref, s0, e0)
+        rows = []
+        for f in (host, gpu):
+            kh = mscan.KmerHist(3, 4, 3, 1)
+            mscan.scan_reads(f, None, [kh])
+            rows.append(kh.counts.copy())
+        assert np.array_equal(rows[0], rows[1]) and rows[0].sum() > 0
+        assert gpu._h is None
+
+
 def test_alignmentfile_and_cli_with_gpu_decode(tmp_path):
     """AlignmentFile(decode="gpu") answers exactly like the host-decoded file: header, index statistics,
     classic() of the golden regions, the pileup() protocol, the records; `metacov pileup --bam-decode gpu`
@@ -127,8 +188,14 @@ def test_alignmentfile_and_cli_with_gpu_decode(tmp_path):
         hs, gs = host.soa(), gpu.soa()
         for c in COLS:
             assert np.array_equal(hs[c], gs[c]), c
-        # read names / sequences come from the host reader on demand
+        # read names and SEQ are read on the device too: same hashes, k-mer keys and SEQ windows as the host reader's,
+        # and the GPU-decoded file never opens a host reader
         assert np.array_equal(gpu.name_hashes(), host.name_hashes())
+        for k in (1, 4, 7, 15):
+            assert np.array_equal(gpu.qas_kmer_codes(k), host.qas_kmer_codes(k)), k
+        for w in (1, 7, 56, 101, 400):
+            assert np.array_equal(gpu.seq_windows(w), host.seq_windows(w)), w
+        assert gpu._h is None
         gpu.set_pileup_filter(min_mapq=20)
         host.set_pileup_filter(min_mapq=20)
         assert pileup.classic(gpu, "ref1", 0, 425) == pileup.classic(host, "ref1", 0, 425)

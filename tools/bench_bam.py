@@ -1,7 +1,11 @@
 #!/usr/bin/env python
-"""From the BAM FILE to per-base depth: host decode (mcov_bam_open/load: zlib on all host cores + serial
-record walk, then H2D of the SoA) against GPU decode (mcov_bam_decode_gpu: compressed image over PCIe,
-inflate + record chain + SoA on the device).  SURVEY.md 8(f) row 3.  Prints one JSON line.
+"""From the BAM FILE to per-base depth, three ways, each timed from the closed file on disk to the finished depth:
+  host_decode   whole-file host reader (mcov_bam_open/load: zlib on all host cores + serial record walk), H2D of the SoA;
+  host_stream   the streaming reader (mcov_bam_stream_*: batches decoded into pinned sets and pushed while the next one
+                is decoded) -- what AlignmentFile does by default;
+  gpu_decode    the file is read into a pinned staging buffer (allocated once, like the engine's own staging; the READ is
+                inside the timed region), the compressed image goes over PCIe, inflate + record chain + SoA on the device.
+SURVEY.md 8(f) row 3.  Prints one JSON line.
 
   python tools/bench_bam.py [--scale 0.2] [--reps 3]
 """
@@ -63,38 +67,55 @@ def _measure(args, path, w, hb, t_write):
             t3 = time.perf_counter()                 # H2D of the SoA + kernels
         return t1 - t0, t2 - t1, t3 - t2
 
-    def gpu_path(pinned, crc=True):
+    def stream_path():
+        from metacov_b200.alignmentfile import BamStream, stream_depth
         t0 = time.perf_counter()
-        soa = bamgpu.decode(eng, pinned, verify_crc=crc)
-        t1 = time.perf_counter()                     # H2D of the compressed image + inflate + record chain + SoA
+        with BamStream(path) as st:
+            stream_depth(eng, st)
+        return time.perf_counter() - t0
+
+    t0 = time.perf_counter()
+    staging = torch.empty(size, dtype=torch.uint8).pin_memory()      # persistent staging buffer: allocated once, reported
+    t_pin = time.perf_counter() - t0
+    staging_np = staging.numpy()
+
+    def gpu_path(crc=True):
+        t0 = time.perf_counter()
+        with open(path, "rb", buffering=0) as fh:
+            got = fh.readinto(memoryview(staging_np))
+        assert got == size
+        t1 = time.perf_counter()                     # file -> pinned staging
+        soa = bamgpu.decode(eng, staging, verify_crc=crc)
+        t2 = time.perf_counter()                     # H2D of the compressed image + inflate + record chain + SoA
         bamgpu.depth_sorted(eng, soa)
-        t2 = time.perf_counter()
-        return t1 - t0, t2 - t1, soa
+        t3 = time.perf_counter()
+        return t1 - t0, t2 - t1, t3 - t2, soa
 
     host = [host_path() for _ in range(args.reps)]
-    t0 = time.perf_counter()
-    raw = np.fromfile(path, dtype=np.uint8)
-    pinned = torch.from_numpy(raw).pin_memory()
-    t_read = time.perf_counter() - t0
-    gpu_path(pinned)
+    stream = [stream_path() for _ in range(args.reps)]
+    gpu_path()
     eng.profile(True)
-    gpu = [gpu_path(pinned)[:2] for _ in range(args.reps)]
+    gpu = [gpu_path()[:3] for _ in range(args.reps)]
     kt = eng.profile_read()
     eng.profile(False)
-    soa = gpu_path(pinned)[2]
-    nocrc = min((gpu_path(pinned, crc=False)[:2] for _ in range(args.reps)), key=sum)
+    soa = gpu_path()[3]
+    nocrc = min((gpu_path(crc=False)[:3] for _ in range(args.reps)), key=sum)
     best_h = min(host, key=sum)
     best_g = min(gpu, key=sum)
+    best_s = min(stream)
     kern = {k: v[1] / max(v[0], 1) for k, v in kt.items() if k.startswith("k_b")}
     line = {
         "what": "BAM file -> per-base depth", "reads": n, "bam_bytes": size, "inflated_bytes": int(soa.inflated_bytes),
         "segments": int(soa.n_segments), "host_cores": os.cpu_count(),
         "host_decode": {"open_inflate_s": best_h[0], "record_walk_s": best_h[1], "h2d_and_depth_s": best_h[2], "total_s": sum(best_h),
                         "reads_per_s": n / sum(best_h)},
-        "gpu_decode": {"decode_s": best_g[0], "depth_s": best_g[1], "total_s": sum(best_g), "reads_per_s": n / sum(best_g),
-                       "decode_s_without_crc_check": nocrc[0], "file_read_and_pin_s": t_read, "kernel_ms": kern,
+        "host_stream": {"total_s": best_s, "reads_per_s": n / best_s},
+        "gpu_decode": {"file_read_s": best_g[0], "decode_s": best_g[1], "depth_s": best_g[2], "total_s": sum(best_g),
+                       "reads_per_s": n / sum(best_g), "decode_s_without_crc_check": nocrc[1],
+                       "staging_alloc_once_s": t_pin, "kernel_ms": kern,
                        "inflate_gbs_out": soa.inflated_bytes / (kern.get("k_bgzf_inflate", 0) or float("nan")) / 1e6},
-        "speedup_total": sum(best_h) / sum(best_g), "bam_write_s": t_write,
+        "timed": "every arm: closed file on disk (page cache warm) -> depth ready",
+        "speedup_total": sum(best_h) / sum(best_g), "speedup_vs_stream": best_s / sum(best_g), "bam_write_s": t_write,
     }
     print(json.dumps(line))
     eng.close()
