@@ -334,15 +334,30 @@ k_region_stats_small(StatArgs a, const uint32_t* __restrict__ retry) {
 }
 
 // ---- small regions, first attempt: ONE WARP per region ------------------------------------------------
-// 8 regions per CTA, each warp with a private window of kWarpBins one-value bins anchored at the
-// region's minimum depth.  Everything is warp-synchronous (no block barrier).  A region whose depth
-// range does not fit the window is appended to the retry list for k_region_stats_small.
+// 8 regions per CTA, each warp with a private window of kWarpBins one-value bins.  Everything is warp-synchronous
+// (no block barrier).  The region is read from HBM ONCE: the window is anchored from the first 512 slots (their
+// minimum less a margin; a region that begins where its contig begins starts at depth ~0, so the anchor is 0 for the
+// whole-contig regions `metacov pileup` makes by default), every value is counted with its index clamped into the
+// window, and the true minimum / maximum are tracked beside.  If they turn out to lie inside the window the counts are
+// exact and the window is walked; if not (rare: the depth wanders by more than the window) the region is counted again
+// from L2 with the window anchored at the now known minimum, and a region whose range does not fit any window is
+// appended to the retry list for k_region_stats_small.
 constexpr int kWarpBins = 1024;
 constexpr int kWarpsPerCta = 8;
+constexpr int kWarpAnchorMargin = 256;
+
+__device__ __forceinline__ void warp_win_add1(uint32_t* win, const int v, const int wlo) {
+  atomicAdd(&win[min((unsigned)(v - wlo), (unsigned)(kWarpBins - 1))], 1u);      // (a value below the window wraps and clamps too)
+}
+__device__ __forceinline__ void warp_win_add(uint32_t* win, const int4 q, const int wlo) {
+  warp_win_add1(win, q.x, wlo); warp_win_add1(win, q.y, wlo); warp_win_add1(win, q.z, wlo); warp_win_add1(win, q.w, wlo);
+}
+__device__ __forceinline__ int min4(const int4 q) { return min(min(q.x, q.y), min(q.z, q.w)); }
+__device__ __forceinline__ int max4(const int4 q) { return max(max(q.x, q.y), max(q.z, q.w)); }
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 k_region_stats_warp(StatArgs a, int64_t task0, int64_t n_tasks, uint32_t* __restrict__ retry) {
-  __shared__ uint32_t s_win[kWarpsPerCta][kWarpBins];
+  __shared__ __align__(16) uint32_t s_win[kWarpsPerCta][kWarpBins];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t wi = (int64_t)blockIdx.x * kWarpsPerCta + warp;
   if (wi >= n_tasks) return;
@@ -355,53 +370,93 @@ k_region_stats_warp(StatArgs a, int64_t task0, int64_t n_tasks, uint32_t* __rest
   const int64_t nvec = ((s1 - a0) + 3) >> 2;
   const int4* vp = reinterpret_cast<const int4*>(a.depth + a0);
   uint32_t* win = s_win[warp];
-  // pass 1: min / max bin.  Four independent 128-bit loads per lane in flight (this pass is the one
-  // that comes from HBM); the first and last vector may hold slots of the neighbouring contigs.
-  int lo = pad > 0 ? 0 : kHistBins - 1, hi = 0;
-  const int64_t jf0 = (s0 != a0) ? 1 : 0, jf1 = ((a0 + (nvec << 2)) != s1) ? nvec - 1 : nvec;   // full vectors [jf0, jf1)
-  for (int64_t j = jf0 + lane; j < jf1; j += 128) {
-    const bool v1 = j + 32 < jf1, v2 = j + 64 < jf1, v3 = j + 96 < jf1;
-    int4 q0 = __ldg(vp + j), q1 = q0, q2 = q0, q3 = q0;
+  // full vectors [jf0, jf1); the first and last vector may hold slots of the neighbouring contigs
+  const int64_t jf0 = (s0 != a0) ? 1 : 0, jf1 = ((a0 + (nvec << 2)) != s1) ? nvec - 1 : nvec;
+  int vlo = INT_MAX, vhi = INT_MIN;                      // true range of the region's depth
+  // the (at most two) partial vectors: lane 0 the head, lane 1 the tail
+  int pv[4] = {0, 0, 0, 0};
+  uint32_t inside = 0;                                    // which elements of pv belong to the region
+  if (lane < 2 && nvec > 0 && ((lane == 0 && jf0 == 1) || (lane == 1 && jf1 == nvec - 1 && (nvec > 1 || jf0 == 0)))) {
+    const int64_t j = lane == 0 ? 0 : nvec - 1;
+    const int4 q = __ldg(vp + j);
+    const int64_t e0 = a0 + (j << 2);
+    pv[0] = q.x; pv[1] = q.y; pv[2] = q.z; pv[3] = q.w;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (e0 + k >= s0 && e0 + k < s1) { inside |= 1u << k; vlo = min(vlo, pv[k]); vhi = max(vhi, pv[k]); }
+  }
+  // first chunk: four independent 128-bit loads per lane in flight; the window is cleared under them
+  int wlo = 0;
+  {
+    const int64_t j = jf0 + lane;
+    const bool v0 = j < jf1, v1 = j + 32 < jf1, v2 = j + 64 < jf1, v3 = j + 96 < jf1;
+    int4 q0 = make_int4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = q0;
+    if (v0) q0 = __ldg(vp + j);
     if (v1) q1 = __ldg(vp + j + 32);
     if (v2) q2 = __ldg(vp + j + 64);
     if (v3) q3 = __ldg(vp + j + 96);
-    int mn = min(min(min(q0.x, q0.y), min(q0.z, q0.w)), min(min(q1.x, q1.y), min(q1.z, q1.w)));
-    mn = min(mn, min(min(min(q2.x, q2.y), min(q2.z, q2.w)), min(min(q3.x, q3.y), min(q3.z, q3.w))));
-    int mxv = max(max(max(q0.x, q0.y), max(q0.z, q0.w)), max(max(q1.x, q1.y), max(q1.z, q1.w)));
-    mxv = max(mxv, max(max(max(q2.x, q2.y), max(q2.z, q2.w)), max(max(q3.x, q3.y), max(q3.z, q3.w))));
-    lo = min(lo, hist_bin(mn)); hi = max(hi, hist_bin(mxv));     // hist_bin is monotone
+    uint4* w4 = reinterpret_cast<uint4*>(win);
+#pragma unroll
+    for (int k = 0; k < kWarpBins / 4 / 32; ++k) w4[k * 32 + lane] = make_uint4(0, 0, 0, 0);
+    if (v0) { vlo = min(vlo, min4(q0)); vhi = max(vhi, max4(q0)); }
+    if (v1) { vlo = min(vlo, min4(q1)); vhi = max(vhi, max4(q1)); }
+    if (v2) { vlo = min(vlo, min4(q2)); vhi = max(vhi, max4(q2)); }
+    if (v3) { vlo = min(vlo, min4(q3)); vhi = max(vhi, max4(q3)); }
+    const int est = warp_min(vlo);
+    wlo = (pad > 0 || est == INT_MAX) ? 0 : max(0, est - kWarpAnchorMargin);       // pad > 0: zeros are counted in bin 0
+    __syncwarp();
+    if (v0) warp_win_add(win, q0, wlo);
+    if (v1) warp_win_add(win, q1, wlo);
+    if (v2) warp_win_add(win, q2, wlo);
+    if (v3) warp_win_add(win, q3, wlo);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (inside & (1u << k)) warp_win_add1(win, pv[k], wlo);
   }
-  if (lane < 2 && nvec > 0) {                                     // the (at most two) partial vectors
-    const int64_t j = lane == 0 ? 0 : nvec - 1;
-    if ((lane == 0 && jf0 == 1) || (lane == 1 && jf1 == nvec - 1 && (nvec > 1 || jf0 == 0))) {
+  for (int64_t jb = jf0 + 128; jb < jf1; jb += 128) {
+    const int64_t j = jb + lane;
+    const bool v0 = j < jf1, v1 = j + 32 < jf1, v2 = j + 64 < jf1, v3 = j + 96 < jf1;
+    int4 q0 = make_int4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = q0;
+    if (v0) q0 = __ldg(vp + j);
+    if (v1) q1 = __ldg(vp + j + 32);
+    if (v2) q2 = __ldg(vp + j + 64);
+    if (v3) q3 = __ldg(vp + j + 96);
+    if (v0) { vlo = min(vlo, min4(q0)); vhi = max(vhi, max4(q0)); warp_win_add(win, q0, wlo); }
+    if (v1) { vlo = min(vlo, min4(q1)); vhi = max(vhi, max4(q1)); warp_win_add(win, q1, wlo); }
+    if (v2) { vlo = min(vlo, min4(q2)); vhi = max(vhi, max4(q2)); warp_win_add(win, q2, wlo); }
+    if (v3) { vlo = min(vlo, min4(q3)); vhi = max(vhi, max4(q3)); warp_win_add(win, q3, wlo); }
+  }
+  vlo = warp_min(vlo); vhi = warp_max(vhi);
+  int lo, hi;
+  if (vlo == INT_MAX) { lo = kHistBins - 1; hi = 0; }    // no slot inside the contig
+  else { lo = hist_bin(vlo); hi = hist_bin(vhi); }       // hist_bin is monotone
+  if (pad > 0) lo = 0;
+  if (hi < lo) hi = lo;
+  const int nb = hi - lo + 1;
+  if (nb > kWarpBins || hi >= kHistBins - 1 || vlo < 0) {       // does not fit (or leaves the bin range): retry path
+    if (lane == 0) { uint32_t k = atomicAdd(retry, 1u); retry[1 + k] = (uint32_t)(task0 + wi); }
+    return;
+  }
+  if (pad > 0 && lane == 0) atomicAdd(&win[0], (uint32_t)pad);      // pad > 0 => wlo == 0
+  if (lo < wlo || hi > wlo + kWarpBins - 1) {
+    // the guess missed: count again (served by L1/L2) with the window anchored at the minimum
+    __syncwarp();
+    uint4* w4 = reinterpret_cast<uint4*>(win);
+#pragma unroll
+    for (int k = 0; k < kWarpBins / 4 / 32; ++k) w4[k * 32 + lane] = make_uint4(0, 0, 0, 0);
+    wlo = lo;
+    __syncwarp();
+    for (int64_t j = lane; j < nvec; j += 32) {
       int4 q = __ldg(vp + j);
       int v[4] = {q.x, q.y, q.z, q.w};
       int64_t e0 = a0 + (j << 2);
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (e0 + k >= s0 && e0 + k < s1) { int b = hist_bin(v[k]); lo = min(lo, b); hi = max(hi, b); }
+        if (e0 + k >= s0 && e0 + k < s1) atomicAdd(&win[v[k] - lo], 1u);
     }
+    if (pad > 0 && lane == 0) atomicAdd(&win[0], (uint32_t)pad);
   }
-  lo = warp_min(lo); hi = warp_max(hi);
-  if (hi < lo) hi = lo;
-  const int nb = hi - lo + 1;
-  if (nb > kWarpBins || hi >= kHistBins - 1) {          // does not fit (or overflows the bin range): retry path
-    if (lane == 0) { uint32_t k = atomicAdd(retry, 1u); retry[1 + k] = (uint32_t)(task0 + wi); }
-    return;
-  }
-  for (int b = lane; b < nb; b += 32) win[b] = 0;
   __syncwarp();
-  // pass 2: increments (served by L1/L2)
-  for (int64_t j = lane; j < nvec; j += 32) {
-    int4 q = __ldg(vp + j);
-    int v[4] = {q.x, q.y, q.z, q.w};
-    int64_t e0 = a0 + (j << 2);
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (e0 + k >= s0 && e0 + k < s1) atomicAdd(&win[hist_bin(v[k]) - lo], 1u);
-  }
-  if (pad > 0 && lane == 0) atomicAdd(&win[0], (uint32_t)pad);      // pad > 0 => lo == 0
-  __syncwarp();
+  win += lo - wlo;                                        // bin b of the walk below holds depth lo + b
   // walk the window: each lane a contiguous run of bins
   const long long k1 = n / 4, k2 = n - n / 4, m1 = (n - 1) / 2, m2 = n / 2;
   const int per = (nb + 31) / 32;

@@ -35,6 +35,9 @@ namespace mcov {
 #ifndef MCOV_TT_BLOCKED
 #define MCOV_TT_BLOCKED 0
 #endif
+#ifndef MCOV_TT_BATCH
+#define MCOV_TT_BATCH 4               // records a thread of a dense tile fetches from global memory before it scatters them
+#endif
 constexpr int kTtStages = MCOV_TT_STAGES;
 // Counter layout.  BLOCKED: a thread owns 16 CONSECUTIVE slots (four vectors), so the block scan needs one warp
 // scan per thread instead of one per vector (4 x 10 shuffle/add instructions -> 10).  Consecutive lanes then read
@@ -110,16 +113,28 @@ __device__ __forceinline__ int tt_scatter(const FusedArgs& f, const TtMeta& m, c
       atomicAdd(&s_cnt[a], 1);
       atomicAdd(&s_cnt[e], 0x10000);
     }
-  } else
-#pragma unroll 2
-  for (uint32_t j = m.r0 + t; j < m.r1; j += kFusedThreads) {
-    const uint32_t r = tt_rec<ALL_STAGED>(f, m, s_rec, j);
-    const uint32_t code = r >> kTileShift;
-    if (code) {
-      const uint32_t local = r & (kTile - 1);
-      if (WHAT != 2) atomicAdd(&s_cnt[tt_phys(local)], 1);
-      const uint32_t el = local + code;
-      if (WHAT != 1 && el < (uint32_t)kTile) atomicAdd(&s_cnt[tt_phys(el)], WHAT == 0 ? 0x10000 : 1);
+  } else {
+    // dense tiles (more records than a stage holds) read theirs from global memory: eight independent loads per thread
+    // in flight, THEN the atomics -- one load per iteration behind its atomics is a DRAM round trip per record (a
+    // 38 000-read tile of config C3 took 400 us that way and the whole pass waited for it)
+    constexpr int kBatch = MCOV_TT_BATCH;
+    for (uint32_t j0 = m.r0 + t; j0 < m.r1; j0 += kBatch * kFusedThreads) {
+      uint32_t r[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const uint32_t j = j0 + (uint32_t)u * kFusedThreads;
+        r[u] = j < m.r1 ? tt_rec<ALL_STAGED>(f, m, s_rec, j) : 0u;           // (code 0: does not count)
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const uint32_t code = r[u] >> kTileShift;
+        if (code) {
+          const uint32_t local = r[u] & (kTile - 1);
+          if (WHAT != 2) atomicAdd(&s_cnt[tt_phys(local)], 1);
+          const uint32_t el = local + code;
+          if (WHAT != 1 && el < (uint32_t)kTile) atomicAdd(&s_cnt[tt_phys(el)], WHAT == 0 ? 0x10000 : 1);
+        }
+      }
     }
   }
   // near reads that started before the tile and end inside it (see k_fused_tile): walk back while the

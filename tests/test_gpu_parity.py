@@ -723,3 +723,35 @@ def test_filter_switches_count_del_and_reflen0(wl, scale):
             push_in_batches(eng, b, rl, np.r_[0, n // 3, 2 * n // 3, n])
             eng.region_stats([0], [0], [10])
             same("stream")
+
+
+def test_warp_statistics_window_guess_refit_and_retry():
+    """k_region_stats_warp reads a small region once, with its histogram window anchored from the first 512 slots.  Regions
+    whose depth later leaves that window are counted again with the right anchor (range <= 1024 values) or go to the
+    CTA-per-region kernel (wider range): all three outcomes, falling and rising depth, against the oracle."""
+    from metacov_b200 import ReadBatch
+    lengths = np.array([6400, 6400, 6400, 300], np.int32)
+    tid, pos = [], []
+    for c, (d0, d1) in enumerate(((6, 1), (8, 1), (1, 7))):          # reads per position in the first / second half
+        p = np.r_[np.repeat(np.arange(0, 3000), d0), np.repeat(np.arange(3000, 6200), d1)]
+        tid += [c] * len(p); pos += p.tolist()
+    tid += [3] * 40; pos += sorted(np.random.default_rng(3).integers(0, 200, 40).tolist())
+    n = len(tid)
+    b = ReadBatch(np.array(tid, np.int32), np.array(pos, np.int32), np.zeros(n, np.uint16), np.full(n, 30, np.uint8),
+                  np.arange(n + 1, dtype=np.uint32), np.full(n, 150 << 4, np.uint32))
+    want, off, _ = cport.depth(b, lengths, mode="diff")
+    t = [0, 1, 2, 0, 1, 2, 3, 0, 2]
+    a = [1000, 1000, 1000, 0, 0, 0, 0, 2990, 3500]
+    e = [5000, 5000, 5000, 6400, 6400, 6400, 300, 3003, 6700]
+    with engine_for(lengths) as eng:
+        eng.depth_sorted(b)
+        assert np.array_equal(eng.copy_depth(0), want[off[0]:off[0] + 6400])
+        got = eng.region_stats(t, a, e)
+        ref = cport.region_stats(want, off, lengths, t, a, e)
+        for k in ("sum", "sumsq", "iq_sum", "min", "max", "med_lo", "med_hi", "n_ge1"):
+            assert np.array_equal(got[k], ref[k]), (k, got[k], ref[k])
+        # the depth really does what the cases need: a fall of ~750 (refit), of ~1050 (retry), a rise of ~900 (refit)
+        d0 = want[off[0] + 1000:off[0] + 5000]; d1 = want[off[1] + 1000:off[1] + 5000]; d2 = want[off[2] + 1000:off[2] + 5000]
+        assert d0[:512].min() - d0.min() > 256 and d0.max() - d0.min() < 1024
+        assert d1.max() - d1.min() >= 1024
+        assert d2.max() - d2[:512].min() > 768 and d2.max() - d2.min() < 1024
