@@ -130,6 +130,8 @@ struct mcov_ctx {
   // streamed passes (mcov_stream_begin / mcov_stream_push)
   mcov::DevBuf d_stream_acc;          // StreamAcc + the carried reads' counts of the current batch
   mcov::DevBuf d_cap_scratch;         // per-region replays of the max_depth cap (mcov_region_stats_run)
+  const void* ncig_key_ptr = nullptr; // device-resident offset array whose total op count is cached (stage_reads)
+  int64_t ncig_key_n = -1, ncig_val = -1;
   int64_t stream_tile_lo = 0;         // tiles below this one hold final depth
   int64_t stream_reads = 0;           // distinct reads pushed so far
   bool stream_started = false;        // (count_del = 0 streams: the difference array has been cleared)

@@ -44,6 +44,7 @@ struct ExpandArgs {
   int32_t* delta;
   PassCounters* pc;
   int cig_aligned16;
+  int64_t n_cig;                 // host side only: CIGAR ops in the batch, -1 = not known (picks the prep kernel)
 };
 
 // (the kernel itself, k_expand, lives in k_fused.cuh: it shares the vectorised load + filter + CIGAR

@@ -105,16 +105,29 @@ int stage_reads(mcov_ctx* ctx, int64_t n, const int32_t* tid, const int32_t* pos
   *used = nullptr;
   { int wrc = wait_pending_copy(ctx); if (wrc) return wrc; }
   a.n = n;
+  a.n_cig = -1;
   a.cig_off = nullptr; a.cig_off64 = nullptr;
   const size_t ow = off64 ? 8 : 4;
   if (mem_kind == MCOV_MEM_DEVICE) {
     a.tid = tid; a.pos = pos; a.flag = flag; a.mapq = mapq; a.cig = cig;
     if (off64) a.cig_off64 = static_cast<const uint64_t*>(cig_off); else a.cig_off = static_cast<const uint32_t*>(cig_off);
+    // ops per read decide between the two prep kernels; for device-resident columns the total is read back ONCE per
+    // (offset array, n) -- a caller that runs pass after pass over the same arrays pays the round trip the first time only
+    if (!off64 && n > 0) {
+      if (ctx->ncig_key_ptr != cig_off || ctx->ncig_key_n != n) {
+        uint32_t last = 0;
+        CU(cudaMemcpyAsync(&last, static_cast<const uint32_t*>(cig_off) + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->ncig_key_ptr = cig_off; ctx->ncig_key_n = n; ctx->ncig_val = (int64_t)last;
+      }
+      a.n_cig = ctx->ncig_val;
+    }
   } else if (mem_kind == MCOV_MEM_HOST) {
     ReadStage& s = ctx->stage[ctx->stage_next];
     ctx->stage_next ^= 1;
     if (s.in_flight) { CU(cudaEventSynchronize(s.consumed)); s.in_flight = false; }
     const uint64_t n_cig = off64 ? static_cast<const uint64_t*>(cig_off)[n] : static_cast<const uint32_t*>(cig_off)[n];
+    a.n_cig = (int64_t)n_cig;
     CU(s.tid.ensure(n * 4)); CU(s.pos.ensure(n * 4)); CU(s.flag.ensure(n * 2)); CU(s.mapq.ensure(n));
     CU(s.cig_off.ensure((n + 1) * ow)); CU(s.cig.ensure((size_t)n_cig * 4 + 16));
     cudaStream_t cs = ctx->copy_stream;
@@ -221,7 +234,13 @@ int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a, int64_t tile_lo = -1,
     // short-read hot path: SoA chunks staged by TMA bulk copies behind mbarriers (k_prep_tma.cuh); needs 32-bit
     // offsets and 16-byte aligned columns.  Anything else takes the per-thread loads of k_fused_prep.
     static const bool no_tma = std::getenv("MCOV_PREP_LEGACY") != nullptr;     // tuning hook
-    const bool tma = !off64 && !no_tma && al(a.tid, 16) && al(a.pos, 16) && al(a.cig_off, 16) && al(a.flag, 16) &&
+    // Long CIGARs (config C5: ~2 700 ops per read) are reduced by whole warps straight from global memory in either
+    // kernel, and there the 8 x 4 warps per SM of k_fused_prep keep more loads in flight than the staged kernel's 3 x 8
+    // consumer warps (B200, C5 at 1 M reads: 2.4 ms against 4.6 ms): more than kPrepLongOps ops per read on average
+    // take k_fused_prep.
+    constexpr int64_t kPrepLongOps = 16;
+    const bool long_cigars = a.n_cig >= 0 && a.n_cig > kPrepLongOps * n;
+    const bool tma = !off64 && !no_tma && !long_cigars && al(a.tid, 16) && al(a.pos, 16) && al(a.cig_off, 16) && al(a.flag, 16) &&
                      al(a.mapq, 16) && al(a.cig, 16);
     if (tma) {
       const int64_t n_chunks = (n + kPtChunk - 1) / kPtChunk;
@@ -384,7 +403,7 @@ int block_stage(mcov_ctx* ctx, const void* block, int64_t bytes, ExpandArgs& a, 
   MCOV_LAUNCH(ctx, kKBlockUnpack, (k_block_finish<<<grid_for(ctx, n1, 256, 8), 256, 0, s>>>(b)));
   CU(cudaGetLastError());
   std::memset(&a, 0, sizeof(a));
-  a.n = n;
+  a.n = n; a.n_cig = h.n_cigar;
   a.tid = b.tid; a.pos = b.pos; a.flag = b.flag; a.mapq = b.mapq; a.cig_off = b.cig_off; a.cig = b.cig;
   a.contig_off = ctx->d_off.as<int64_t>(); a.contig_len = ctx->d_len.as<int32_t>(); a.n_contigs = ctx->n_contigs;
   a.filt = ctx->filt; a.delta = ctx->depth; a.pc = pc_of(ctx);
@@ -619,7 +638,7 @@ int mcov_depth_sorted_delta(mcov_ctx* ctx, int64_t n, const int64_t* contig_read
   CU(cudaGetLastError());
   ExpandArgs a;
   std::memset(&a, 0, sizeof(a));
-  a.n = n;
+  a.n = n; a.n_cig = n_cig_total;
   a.tid = st.tid.as<int32_t>(); a.pos = st.pos.as<int32_t>(); a.flag = st.flag.as<uint16_t>();
   a.mapq = st.mapq.as<uint8_t>(); a.cig_off = st.cig_off.as<uint32_t>(); a.cig = st.cig.as<uint32_t>();
   a.contig_off = ctx->d_off.as<int64_t>(); a.contig_len = ctx->d_len.as<int32_t>(); a.n_contigs = ctx->n_contigs;
@@ -969,7 +988,7 @@ int mcov_depth_sorted_packed(mcov_ctx* ctx, int64_t n, const int64_t* contig_rea
   }
   ExpandArgs a;
   std::memset(&a, 0, sizeof(a));
-  a.n = n;
+  a.n = n; a.n_cig = n_cig_total;
   a.tid = st.tid.as<int32_t>(); a.pos = st.pos.as<int32_t>(); a.flag = st.flag.as<uint16_t>();
   a.mapq = st.mapq.as<uint8_t>(); a.cig_off = st.cig_off.as<uint32_t>(); a.cig = st.cig.as<uint32_t>();
   a.contig_off = ctx->d_off.as<int64_t>(); a.contig_len = ctx->d_len.as<int32_t>(); a.n_contigs = ctx->n_contigs;
