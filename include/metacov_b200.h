@@ -592,6 +592,23 @@ int  mcov_bam_decode_gpu(mcov_ctx* ctx, const void* file_bytes, int64_t n_bytes,
  * the record.  Synchronises. */
 int  mcov_bam_gpu_names_seq(mcov_ctx* ctx, int32_t k_len, int32_t win_bases,
                             uint64_t* name_hash_out, int32_t* kmer_code_out, uint8_t* seq_win_out, int mem_kind);
+
+/* A BAM of ANY size through the GPU decoder into the streamed depth pass: the file
+ * is read chunk_bytes at a time (<= 0: 256 MiB) into pinned memory by a host thread
+ * while the GPU inflates the previous chunk, establishes its record chain (a record
+ * cut by the chunk border is completed with the next chunk), writes the columns and
+ * pushes them, led by the reads the pass wants again, through mcov_stream_push from
+ * device memory.  The host does nothing but read().  Replaces the `cnext()` loop of
+ * reference metacov/scan.pyx:653-667 over a file that is never held.  Needs the
+ * file's contig table (mcov_set_contigs; header e.g. from mcov_bam_stream_open);
+ * on MCOV_OK the depth is ready (statistics, copies, exports).  A file that is not
+ * coordinate sorted is reported by the first synchronising call after it
+ * (MCOV_ERR_UNSORTED), like mcov_stream_push. */
+typedef struct mcov_bam_gpu_stream_info {
+  int64_t n_records, n_chunks, n_segments, inflated_bytes, file_bytes, max_carry;
+} mcov_bam_gpu_stream_info;
+int  mcov_bam_gpu_stream_depth(mcov_ctx* ctx, const char* path, int64_t chunk_bytes, int verify_crc,
+                               mcov_bam_gpu_stream_info* info);
 /* Test hooks: the device inflate / CRC-32 code (csrc/inflate.cuh) compiled for the host, so that the CPU
  * suite can check it against zlib.  mcov_inflate_host returns 0 or a positive decoder status. */
 int  mcov_inflate_host(const uint8_t* src, uint32_t clen, uint8_t* dst, uint32_t ulen);

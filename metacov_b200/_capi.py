@@ -56,6 +56,11 @@ REGION_STATS_DTYPE = np.dtype([
 assert REGION_STATS_DTYPE.itemsize == C.sizeof(RegionStats) == 64
 
 
+class BamGpuStreamInfo(C.Structure):
+    _fields_ = [("n_records", C.c_int64), ("n_chunks", C.c_int64), ("n_segments", C.c_int64), ("inflated_bytes", C.c_int64),
+                ("file_bytes", C.c_int64), ("max_carry", C.c_int64)]
+
+
 class BamDev(C.Structure):
     """mcov_bam_dev: device-resident SoA of a BAM decoded on the GPU."""
     _fields_ = [("n_records", C.c_int64), ("n_cigar", C.c_int64), ("inflated_bytes", C.c_int64), ("header_bytes", C.c_int64),
@@ -133,6 +138,7 @@ SIGNATURES = {
     "mcov_copy_to_host": (C.c_int, [_vp, _vp, _vp, C.c_int64]),
     "mcov_bam_decode_gpu": (C.c_int, [_vp, _vp, C.c_int64, C.c_int, _vp]),
     "mcov_bam_gpu_names_seq": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, C.c_int]),
+    "mcov_bam_gpu_stream_depth": (C.c_int, [_vp, C.c_char_p, _i64, C.c_int, _vp]),
     "mcov_inflate_host": (C.c_int, [_vp, C.c_uint32, _vp, C.c_uint32]),
     "mcov_inflate_host_win": (C.c_int, [_vp, C.c_uint32, _vp, C.c_uint32, C.c_uint32]),
     "mcov_crc32_host": (C.c_uint32, [_vp, C.c_uint32]),

@@ -9,6 +9,7 @@ Protocol provided (reference call sites): constructor from a path
 ``.pos`` / ``.n`` (pileup.py:13-16).
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -134,13 +135,24 @@ def stream_depth(engine, stream):
 
 class AlignmentFile:
     def __init__(self, filename, mode="rb", device=0, decode="host", **kw):
-        """decode="host": BGZF inflate and record parsing by the native host reader (csrc/bamio.cpp);
-        decode="gpu": the compressed file goes to the device and is inflated and parsed there
-        (csrc/bam_gpu.cu) -- the coverage path then never holds the records on the host."""
+        """decode="host": BGZF inflate and record parsing by the native host reader (csrc/bamio.cpp), streamed batch by
+        batch; decode="gpu": the compressed file goes to the device and is inflated and parsed there (csrc/bam_gpu.cu) --
+        the coverage path then never holds the records on the host, and the file is decoded ~10x faster than 16 host
+        cores manage (tools/bench_bam.py), but the compressed image, the inflated stream and the columns must fit the
+        device; decode="gpu-stream": the file is read in chunks (``gpu_chunk_bytes``, default 256 MiB) and every chunk is
+        inflated, parsed and pushed into the streamed depth pass on the device (mcov_bam_gpu_stream_depth) -- any file size,
+        the host only reads; accessors that need every record on the host (soa(), read names) open the host reader on
+        demand; decode="auto": "gpu" when the whole file fits the device (file size x GPU_DECODE_FOOTPRINT below the free
+        device memory), else "gpu-stream"."""
         if "w" in mode:
             raise ValueError("metacov_b200.AlignmentFile is read-only")
-        if decode not in ("host", "gpu"):
-            raise ValueError("decode must be 'host' or 'gpu'")
+        if decode not in ("host", "gpu", "gpu-stream", "auto"):
+            raise ValueError("decode must be 'host', 'gpu', 'gpu-stream' or 'auto'")
+        if decode == "auto":
+            decode = "gpu" if self._fits_device(filename, device) else "gpu-stream"
+        self._gpu_chunk_bytes = int(kw.get("gpu_chunk_bytes", 256 << 20))
+        self.gpu_stream_info = None
+        self.decode = decode
         self.filename = filename
         self._gpu = None
         self._device = device
@@ -161,6 +173,20 @@ class AlignmentFile:
         self.references, self.lengths, self.text = self._stream.references, self._stream.lengths, self._stream.text
         self.nreferences = len(self.references)
         self._tid = {name: i for i, name in enumerate(self.references)}
+
+    # device bytes per byte of BAM that a GPU decode needs: the image itself, the inflated stream (BAM records deflate
+    # ~4-5x), the SoA columns, and as much again for the depth arrays and scratch of the pass that follows
+    GPU_DECODE_FOOTPRINT = 12
+
+    @classmethod
+    def _fits_device(cls, filename, device):
+        import torch
+        try:
+            size = os.path.getsize(filename)
+            free, _total = torch.cuda.mem_get_info(device)
+        except (OSError, RuntimeError):
+            return False
+        return size * cls.GPU_DECODE_FOOTPRINT < free
 
     def _open_gpu(self, filename, device):
         from . import bamgpu
@@ -399,18 +425,32 @@ class AlignmentFile:
             # coordinate-sorted, or one where htslib's max_depth cap fires, takes the whole-file path below
             eng = CoverageEngine(self.lengths, device=self._device, filt=self._filter_kw)
             path = None
-            try:
-                st, self._stream = self._stream, None           # the reader opened for the header, not yet advanced
-                if st is None:
-                    st = BamStream(self.filename, batch_reads=self._batch_reads)
-                with st:
-                    self.stream_batches = stream_depth(eng, st)
-                eng.pass_info()                                  # delivers the verdict of the stream
-                path = "fused"
-            except McovError as e:
-                if e.code not in (_capi.MCOV_ERR_UNSORTED, _capi.MCOV_ERR_RANGE, _capi.MCOV_ERR_STATE):
-                    eng.close()
-                    raise
+            if self.decode == "gpu-stream":
+                # chunks of the file through the GPU decoder into the streamed pass; a file it cannot take (not sorted, the
+                # max_depth cap fires) falls through to the host paths below, which know what to do with it
+                from . import bamgpu
+                try:
+                    self.gpu_stream_info = bamgpu.stream_depth(eng, self.filename, chunk_bytes=self._gpu_chunk_bytes)
+                    eng.pass_info()
+                    path = "fused"
+                    self.stream_batches = self.gpu_stream_info["n_chunks"]
+                except McovError as e:
+                    if e.code not in (_capi.MCOV_ERR_UNSORTED, _capi.MCOV_ERR_RANGE, _capi.MCOV_ERR_STATE):
+                        eng.close()
+                        raise
+            if path is None and self.decode != "gpu-stream":    # (what the GPU stream refused, the host stream would refuse too)
+                try:
+                    st, self._stream = self._stream, None       # the reader opened for the header, not yet advanced
+                    if st is None:
+                        st = BamStream(self.filename, batch_reads=self._batch_reads)
+                    with st:
+                        self.stream_batches = stream_depth(eng, st)
+                    eng.pass_info()                              # delivers the verdict of the stream
+                    path = "fused"
+                except McovError as e:
+                    if e.code not in (_capi.MCOV_ERR_UNSORTED, _capi.MCOV_ERR_RANGE, _capi.MCOV_ERR_STATE):
+                        eng.close()
+                        raise
             if path is None:
                 s = self.soa()
                 path = eng.compute_depth(ReadBatch(s["tid"], s["pos"], s["flag"], s["mapq"], s["cig_off"], s["cig"]))

@@ -100,3 +100,13 @@ def depth_sorted(engine, soa, wait=True):
     fn = lib.mcov_depth_sorted if wait else lib.mcov_depth_sorted_async
     r = soa.raw
     engine._check(fn(engine._ctx, soa.n_records, r.tid, r.pos, r.flag, r.mapq, r.cig_off, r.cig, _capi.MEM_DEVICE))
+
+
+def stream_depth(engine, path, chunk_bytes=256 << 20, verify_crc=True):
+    """Per-base depth of a coordinate-sorted BAM of any size: the file goes through the GPU decoder chunk by chunk into the
+    streamed depth pass (``mcov_bam_gpu_stream_depth``); the engine's contig table must be the file's.  Returns the
+    decoder's counters (records, chunks, bytes)."""
+    info = _capi.BamGpuStreamInfo()
+    engine._check(lib.mcov_bam_gpu_stream_depth(engine._ctx, str(path).encode(), int(chunk_bytes), 1 if verify_crc else 0,
+                                                C.byref(info)))
+    return {k: getattr(info, k) for k, _ in info._fields_}

@@ -48,7 +48,7 @@ def main():
 @click.option("--window", "-w", type=click.IntRange(1), metavar="N",
               help="Also write the mean depth of fixed windows of N bp to --window-out. Not in the reference: additive.")
 @click.option("--window-out", "-wo", type=click.File("w"), metavar="FILE", help="Output CSV of --window (sacc,start,end,avg)")
-@click.option("--bam-decode", type=click.Choice(["host", "gpu"]), default="host", show_default=True,
+@click.option("--bam-decode", type=click.Choice(["host", "gpu", "gpu-stream", "auto"]), default="host", show_default=True,
               help="Where the BAM file is inflated and parsed: host threads (zlib) or the GPU. Not in the reference: additive.")
 def pileup(bamfile, reference_fasta, regionfile_blast7, regionfile_csv, kmer_histogram, kmer_length, outfile,
            bedgraph=None, window=None, window_out=None, bam_decode="host"):

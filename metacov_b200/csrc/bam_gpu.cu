@@ -146,7 +146,7 @@ struct WalkOut { uint64_t end; uint32_t n_rec; uint32_t n_cig; int32_t err; int3
 
 // One thread per segment: follow the record chain from seg.start until it reaches seg.limit.
 __global__ void k_bam_walk_count(const uint8_t* __restrict__ d, uint64_t total, const WalkSeg* __restrict__ segs, int64_t n_seg,
-                                 WalkOut* __restrict__ out) {
+                                 WalkOut* __restrict__ out, int allow_tail) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_seg) return;
   const WalkSeg g = segs[s];
@@ -154,9 +154,10 @@ __global__ void k_bam_walk_count(const uint8_t* __restrict__ d, uint64_t total, 
   uint32_t n_rec = 0, n_cig = 0;
   int err = 0;
   while (p < g.limit) {
-    if (p + 36 > total) { err = 1; break; }
+    if (p + 36 > total) { if (!allow_tail) err = 1; break; }      // (allow_tail: the record continues in the next chunk)
     const uint32_t bs = ld32u(d + p);
     const uint32_t l_name = d[p + 12], n_op = ld16u(d + p + 16);
+    if (bs >= 32u && p + 4 + bs > total && allow_tail) break;
     if (bs < 32u || p + 4 + bs > total || 32ull + l_name + 4ull * n_op > bs) { err = 2; break; }
     ++n_rec;
     n_cig += n_op;
@@ -264,16 +265,54 @@ __global__ void k_bam_names_seq(const uint8_t* __restrict__ d, const uint64_t* _
   }
 }
 
+// Streamed decode (mcov_bam_gpu_stream_depth): which reads of this batch must lead the next one.  The streamed depth
+// pass wants every read that starts at or after the resend point (rt, rp) or reaches past it; in a sorted batch those
+// form a SUFFIX plus a few earlier reads, and since resending more is harmless the whole suffix from the first such read
+// is carried.  One thread per read; *first receives the smallest qualifying index (initialised to n).
+__global__ void k_bam_carry_first(int64_t n, const int32_t* __restrict__ tid, const int32_t* __restrict__ pos,
+                                  const uint32_t* __restrict__ cig_off, const uint32_t* __restrict__ cig, int32_t rt, int32_t rp,
+                                  int32_t n_contigs, unsigned long long* __restrict__ first) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t t = (uint32_t)tid[i], r = (uint32_t)rt;
+  if (t >= (uint32_t)n_contigs) return;                           // unplaced reads (tid -1, sorted last) never count: not carried
+  bool take = t > r || (t == r && pos[i] >= rp);
+  if (!take && t == r) {                                          // same contig, starts before the point: does it reach past it?
+    long long e = pos[i];
+    for (uint32_t k = cig_off[i]; k < cig_off[i + 1] && e <= rp; ++k) e += cigar_ref_len(cig[k]);
+    take = e > rp;
+  }
+  if (take) atomicMin(first, (unsigned long long)i);
+}
+__global__ void k_bam_rebase_offsets(int64_t m, const uint32_t* __restrict__ src, uint32_t base, uint32_t* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) dst[i] = src[i] - base;
+}
+
 // ---- host side ------------------------------------------------------------------------------------
 
 static inline uint16_t h16(const uint8_t* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
 static inline uint32_t h32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
 
 // BGZF block table of a file image (SAM spec 4.1: gzip members with a 'BC' extra field holding BSIZE)
-static bool index_bgzf(const uint8_t* raw, size_t n, std::vector<BgzfBlock>& blocks, uint64_t& total) {
+// consumed (optional): a trailing INCOMPLETE block is not an error -- indexing stops in front of it and *consumed tells
+// how many bytes the complete blocks take (chunks of a larger file)
+static bool index_bgzf(const uint8_t* raw, size_t n, std::vector<BgzfBlock>& blocks, uint64_t& total, size_t* consumed = nullptr,
+                       uint64_t uoff0 = 0) {
   size_t off = 0;
-  uint64_t uoff = 0;
+  uint64_t uoff = uoff0;
+  if (consumed) *consumed = 0;
   while (off < n) {
+    if (consumed) {
+      // is the whole block here?  (BSIZE sits at a fixed place in every BGZF writer's header, but walk the extra field anyway)
+      if (off + 18 > n) break;
+      const uint16_t xl = h16(raw + off + 10);
+      if (off + 12 + xl > n) break;
+      int bs = -1;
+      for (size_t q = off + 12; q + 4 <= off + 12 + xl; q += 4 + h16(raw + q + 2))
+        if (raw[q] == 'B' && raw[q + 1] == 'C' && h16(raw + q + 2) == 2 && q + 6 <= off + 12 + xl) bs = h16(raw + q + 4);
+      if (bs >= 0 && off + (size_t)bs + 1 > n) break;
+    }
     if (off + 18 > n) return false;
     const uint8_t* h = raw + off;
     if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return false;
@@ -301,6 +340,7 @@ static bool index_bgzf(const uint8_t* raw, size_t n, std::vector<BgzfBlock>& blo
     uoff += b.ulen;
     blocks.push_back(b);
     off = bend;
+    if (consumed) *consumed = off;
   }
   total = uoff;
   return true;
@@ -318,31 +358,11 @@ using namespace mcov;
 
 static int bfail(mcov_ctx* ctx, int code, const char* msg) { ctx->err = msg; return code; }
 
-extern "C" int mcov_bam_decode_gpu(mcov_ctx* ctx, const void* file_bytes, int64_t n_bytes, int verify_crc, mcov_bam_dev* out) {
-  if (!ctx) return MCOV_ERR_ARG;
-  if (!file_bytes || n_bytes <= 0 || !out) return bfail(ctx, MCOV_ERR_ARG, "mcov_bam_decode_gpu: bad arguments");
-  std::memset(out, 0, sizeof(*out));
-  CUB(cudaSetDevice(ctx->device));
-  cudaStream_t s = ctx->stream;
-  const uint8_t* raw = static_cast<const uint8_t*>(file_bytes);
-  std::vector<BgzfBlock> blocks;
-  uint64_t total = 0;
-  if (!index_bgzf(raw, (size_t)n_bytes, blocks, total)) return bfail(ctx, MCOV_ERR_IO, "mcov_bam_decode_gpu: not a valid BGZF file");
-  if (total < 12) return bfail(ctx, MCOV_ERR_IO, "mcov_bam_decode_gpu: not a valid BAM file");
-  const int64_t nb = (int64_t)blocks.size();
+// Header of the inflated stream at B.data (host side: magic, text, reference table) -> n_ref and the offset of the
+// first alignment record.  Also the place where the inflate status is looked at.
+static int bam_dev_header(mcov_ctx* ctx, uint64_t total, uint64_t* rec_begin_out, int32_t* n_ref_out) {
   mcov_ctx::BamDev& B = ctx->bam;
-  // compressed image + block table to the device, inflate
-  CUB(B.raw.ensure((size_t)n_bytes));
-  CUB(B.blocks.ensure((size_t)nb * sizeof(BgzfBlock)));
-  CUB(B.data.ensure((size_t)total + 64));
-  CUB(B.status.ensure(64));
-  CUB(cudaMemcpyAsync(B.raw.p, raw, (size_t)n_bytes, cudaMemcpyHostToDevice, s));
-  CUB(cudaMemcpyAsync(B.blocks.p, blocks.data(), (size_t)nb * sizeof(BgzfBlock), cudaMemcpyHostToDevice, s));
-  CUB(cudaMemsetAsync(B.status.p, 0, 64, s));
-  MCOV_LAUNCH(ctx, kKBgzfInflate, (k_bgzf_inflate<<<(unsigned)((nb + kInflateGroupsPerCta - 1) / kInflateGroupsPerCta), kInflateThreads, 0, s>>>(
-      B.raw.as<uint8_t>(), B.blocks.as<BgzfBlock>(), nb, B.data.as<uint8_t>(), verify_crc, B.status.as<int>())));
-  CUB(cudaGetLastError());
-  // header (host): magic, text, reference table -> n_ref, first record
+  cudaStream_t s = ctx->stream;
   int st[2] = {0, 0};
   std::vector<uint8_t> head;
   size_t want = (size_t)std::min<uint64_t>(total, 1u << 20);
@@ -381,7 +401,17 @@ extern "C" int mcov_bam_decode_gpu(mcov_ctx* ctx, const void* file_bytes, int64_
     if (want >= total) return bfail(ctx, MCOV_ERR_IO, "mcov_bam_decode_gpu: truncated BAM header");
     want = (size_t)std::min<uint64_t>(total, (uint64_t)want * 4);
   }
-  // record starts: guess per chunk, walk, verify the links
+  *rec_begin_out = rec_begin; *n_ref_out = n_ref;
+  return MCOV_OK;
+}
+
+// Record starts of the inflated stream B.data[0, total): guess per 64 KiB chunk, walk, verify the links (see the
+// head of this file).  allow_tail: the stream may end inside a record (a chunk of a larger file): the chain then stops
+// in front of it and *end_out is where that record begins; otherwise the chain must end exactly at `total`.
+static int bam_dev_chain(mcov_ctx* ctx, uint64_t total, uint64_t rec_begin, int32_t n_ref, bool allow_tail,
+                         std::vector<WalkSeg>& segs, std::vector<WalkOut>& wo, uint64_t* end_out) {
+  mcov_ctx::BamDev& B = ctx->bam;
+  cudaStream_t s = ctx->stream;
   const int64_t n_chunks = (int64_t)((total + kGuessChunk - 1) / kGuessChunk);
   CUB(B.starts.ensure((size_t)n_chunks * 8));
   MCOV_LAUNCH(ctx, kKBamGuess, (k_bam_guess<<<(unsigned)((n_chunks * 32 + 127) / 128), 128, 0, s>>>(
@@ -394,8 +424,6 @@ extern "C" int mcov_bam_decode_gpu(mcov_ctx* ctx, const void* file_bytes, int64_
   if (rec_begin < total) cand.push_back(rec_begin);
   for (int64_t c = 0; c < n_chunks; ++c)
     if (starts[c] > (long long)rec_begin) cand.push_back((uint64_t)starts[c]);
-  std::vector<WalkSeg> segs;
-  std::vector<WalkOut> wo;
   for (int round = 0;; ++round) {
     if (round > 64) return bfail(ctx, MCOV_ERR_IO, "mcov_bam_decode_gpu: record chain could not be established");
     const int64_t ns = (int64_t)cand.size();
@@ -407,7 +435,7 @@ extern "C" int mcov_bam_decode_gpu(mcov_ctx* ctx, const void* file_bytes, int64_
     CUB(B.wout.ensure((size_t)ns * sizeof(WalkOut)));
     CUB(cudaMemcpyAsync(B.segs.p, segs.data(), (size_t)ns * sizeof(WalkSeg), cudaMemcpyHostToDevice, s));
     MCOV_LAUNCH(ctx, kKBamWalkCount, (k_bam_walk_count<<<(unsigned)((ns + 127) / 128), 128, 0, s>>>(
-        B.data.as<uint8_t>(), total, B.segs.as<WalkSeg>(), ns, B.wout.as<WalkOut>())));
+        B.data.as<uint8_t>(), total, B.segs.as<WalkSeg>(), ns, B.wout.as<WalkOut>(), allow_tail ? 1 : 0)));
     CUB(cudaGetLastError());
     CUB(cudaMemcpyAsync(wo.data(), B.wout.p, (size_t)ns * sizeof(WalkOut), cudaMemcpyDeviceToHost, s));
     CUB(cudaStreamSynchronize(s));
@@ -420,7 +448,7 @@ extern "C" int mcov_bam_decode_gpu(mcov_ctx* ctx, const void* file_bytes, int64_
       if (wo[i].err) return bfail(ctx, MCOV_ERR_IO, "mcov_bam_decode_gpu: malformed BAM record");
       if (i + 1 < ns) {
         if (wo[i].end == cand[i + 1]) keep.push_back(cand[i + 1]); else changed = true;
-      } else if (wo[i].end != total) {
+      } else if (wo[i].end != total && !allow_tail) {
         return bfail(ctx, MCOV_ERR_IO, "mcov_bam_decode_gpu: the last BAM record is truncated");
       }
     }
@@ -428,6 +456,40 @@ extern "C" int mcov_bam_decode_gpu(mcov_ctx* ctx, const void* file_bytes, int64_
     // (dropping start i+1 changes where the merged walk ends, so later links are re-examined next round)
     cand.swap(keep);
   }
+  *end_out = wo.empty() ? rec_begin : wo.back().end;
+  return MCOV_OK;
+}
+
+extern "C" int mcov_bam_decode_gpu(mcov_ctx* ctx, const void* file_bytes, int64_t n_bytes, int verify_crc, mcov_bam_dev* out) {
+  if (!ctx) return MCOV_ERR_ARG;
+  if (!file_bytes || n_bytes <= 0 || !out) return bfail(ctx, MCOV_ERR_ARG, "mcov_bam_decode_gpu: bad arguments");
+  std::memset(out, 0, sizeof(*out));
+  CUB(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const uint8_t* raw = static_cast<const uint8_t*>(file_bytes);
+  std::vector<BgzfBlock> blocks;
+  uint64_t total = 0;
+  if (!index_bgzf(raw, (size_t)n_bytes, blocks, total)) return bfail(ctx, MCOV_ERR_IO, "mcov_bam_decode_gpu: not a valid BGZF file");
+  if (total < 12) return bfail(ctx, MCOV_ERR_IO, "mcov_bam_decode_gpu: not a valid BAM file");
+  const int64_t nb = (int64_t)blocks.size();
+  mcov_ctx::BamDev& B = ctx->bam;
+  // compressed image + block table to the device, inflate
+  CUB(B.raw.ensure((size_t)n_bytes));
+  CUB(B.blocks.ensure((size_t)nb * sizeof(BgzfBlock)));
+  CUB(B.data.ensure((size_t)total + 64));
+  CUB(B.status.ensure(64));
+  CUB(cudaMemcpyAsync(B.raw.p, raw, (size_t)n_bytes, cudaMemcpyHostToDevice, s));
+  CUB(cudaMemcpyAsync(B.blocks.p, blocks.data(), (size_t)nb * sizeof(BgzfBlock), cudaMemcpyHostToDevice, s));
+  CUB(cudaMemsetAsync(B.status.p, 0, 64, s));
+  MCOV_LAUNCH(ctx, kKBgzfInflate, (k_bgzf_inflate<<<(unsigned)((nb + kInflateGroupsPerCta - 1) / kInflateGroupsPerCta), kInflateThreads, 0, s>>>(
+      B.raw.as<uint8_t>(), B.blocks.as<BgzfBlock>(), nb, B.data.as<uint8_t>(), verify_crc, B.status.as<int>())));
+  CUB(cudaGetLastError());
+  uint64_t rec_begin = 0;
+  int32_t n_ref = 0;
+  { int hrc = bam_dev_header(ctx, total, &rec_begin, &n_ref); if (hrc) return hrc; }
+  std::vector<WalkSeg> segs;
+  std::vector<WalkOut> wo;
+  { uint64_t chain_end = 0; int crc2 = bam_dev_chain(ctx, total, rec_begin, n_ref, false, segs, wo, &chain_end); if (crc2) return crc2; }
   // prefix sums -> where every segment writes
   uint64_t n_rec = 0, n_cig = 0;
   for (size_t i = 0; i < segs.size(); ++i) { segs[i].rec_base = n_rec; segs[i].cig_base = n_cig; n_rec += wo[i].n_rec; n_cig += wo[i].n_cig; }
@@ -490,6 +552,189 @@ extern "C" int mcov_bam_gpu_names_seq(mcov_ctx* ctx, int32_t k_len, int32_t win_
   }
   CUB(cudaStreamSynchronize(s));
   if (bad) return bfail(ctx, MCOV_ERR_IO, "mcov_bam_gpu_names_seq: a record's SEQ leaves the record");
+  return MCOV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Streamed decode: a BAM of ANY size, chunk by chunk through the GPU decoder into the streamed depth pass.  Per chunk:
+// the complete BGZF blocks of `chunk_bytes` of file go to the device and are inflated BEHIND the bytes of the record the
+// previous chunk ended in (so every chunk's stream begins on a record border and its chain has a known head), the
+// record chain is established as above but may stop in front of a record that continues in the next chunk, the columns
+// are written behind the reads carried over from the previous batch, and the batch goes to mcov_stream_push from device
+// memory.  The next chunk of the file is read (a host thread, into the other pinned buffer) while the GPU works.
+// Replaces the `cnext()` loop of reference metacov/scan.pyx:653-667 over a file that is never held, for the coverage
+// path, with the host doing nothing but read().
+// ---------------------------------------------------------------------------------------------------------------------
+#include <cstdio>
+#include <future>
+
+extern "C" int mcov_bam_gpu_stream_depth(mcov_ctx* ctx, const char* path, int64_t chunk_bytes, int verify_crc,
+                                         mcov_bam_gpu_stream_info* info) {
+  if (!ctx) return MCOV_ERR_ARG;
+  if (!path || !info) return bfail(ctx, MCOV_ERR_ARG, "mcov_bam_gpu_stream_depth: bad arguments");
+  std::memset(info, 0, sizeof(*info));
+  if (chunk_bytes <= 0) chunk_bytes = 256ll << 20;
+  chunk_bytes = std::max<int64_t>(chunk_bytes, 1 << 17);          // at least one BGZF block (<= 64 KiB) beside a leftover
+  CUB(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  mcov_ctx::BamDev& B = ctx->bam;
+  B.n_rec = -1;                                                   // (the whole-file decode's columns are gone after this)
+  FILE* fh = std::fopen(path, "rb");
+  if (!fh) return bfail(ctx, MCOV_ERR_IO, "mcov_bam_gpu_stream_depth: cannot open the file");
+  struct Closer { FILE* f; ~Closer() { if (f) std::fclose(f); } } closer{fh};
+  // two pinned buffers: [leftover of an incomplete block | chunk_bytes of file]
+  const size_t cap = (size_t)chunk_bytes + (1u << 17);
+  CUB(B.pin[0].ensure(cap)); CUB(B.pin[1].ensure(cap));
+  CUB(B.status.ensure(64));
+  auto read_into = [fh](uint8_t* dst, size_t want) -> size_t { return std::fread(dst, 1, want, fh); };
+  int rc = mcov_stream_begin(ctx);
+  if (rc) return rc;
+  int cur = 0;
+  size_t left = 0;                                                // bytes of an incomplete block at the front of pin[cur]
+  size_t got = read_into(B.pin[0].as<uint8_t>(), (size_t)chunk_bytes);
+  bool eof = got < (size_t)chunk_bytes;
+  uint64_t tail_len = 0;                                          // bytes of the record the previous chunk ended in (in B.tail)
+  int64_t n_carry = 0, carry_ops = 0;
+  int32_t n_ref = -1;
+  bool first = true, pushed_last = false;
+  int32_t rt = -1, rp = 0;
+  std::vector<BgzfBlock> blocks;
+  std::vector<WalkSeg> segs;
+  std::vector<WalkOut> wo;
+  while (!pushed_last) {
+    uint8_t* raw = B.pin[cur].as<uint8_t>();
+    const size_t have = left + got;
+    // the next chunk of the file, behind the bytes this one will leave over (their number is known once the blocks are indexed)
+    blocks.clear();
+    uint64_t total = 0;
+    size_t consumed = 0;
+    if (!index_bgzf(raw, have, blocks, total, &consumed, tail_len)) return bfail(ctx, MCOV_ERR_IO, "mcov_bam_gpu_stream_depth: not a valid BGZF file");
+    if (eof && consumed != have) return bfail(ctx, MCOV_ERR_IO, "mcov_bam_gpu_stream_depth: the file ends inside a BGZF block");
+    if (!eof && consumed == 0) return bfail(ctx, MCOV_ERR_IO, "mcov_bam_gpu_stream_depth: a BGZF block larger than the chunk");
+    const size_t next_left = have - consumed;
+    std::future<size_t> next_read;
+    const bool was_eof = eof;
+    if (!eof) {
+      uint8_t* nxt = B.pin[cur ^ 1].as<uint8_t>();
+      std::memcpy(nxt, raw + consumed, next_left);
+      next_read = std::async(std::launch::async, read_into, nxt + next_left, (size_t)chunk_bytes);
+    }
+    const int64_t nb = (int64_t)blocks.size();
+    int err_rc = MCOV_OK;
+    do {                                                          // (one pass; `break` = leave with err_rc set, after joining the reader)
+      // inflate behind the carried record bytes
+      if (B.raw.ensure(consumed + 16) != cudaSuccess || B.blocks.ensure((size_t)std::max<int64_t>(nb, 1) * sizeof(BgzfBlock)) != cudaSuccess ||
+          B.data.ensure((size_t)total + 64) != cudaSuccess) { err_rc = bfail(ctx, MCOV_ERR_NOMEM, "mcov_bam_gpu_stream_depth: out of device memory"); break; }
+      if (tail_len) cudaMemcpyAsync(B.data.p, B.tail.p, (size_t)tail_len, cudaMemcpyDeviceToDevice, s);
+      if (consumed) cudaMemcpyAsync(B.raw.p, raw, consumed, cudaMemcpyHostToDevice, s);
+      cudaMemsetAsync(B.status.p, 0, 64, s);
+      if (nb) {
+        cudaMemcpyAsync(B.blocks.p, blocks.data(), (size_t)nb * sizeof(BgzfBlock), cudaMemcpyHostToDevice, s);
+        MCOV_LAUNCH(ctx, kKBgzfInflate, (k_bgzf_inflate<<<(unsigned)((nb + kInflateGroupsPerCta - 1) / kInflateGroupsPerCta), kInflateThreads, 0, s>>>(
+            B.raw.as<uint8_t>(), B.blocks.as<BgzfBlock>(), nb, B.data.as<uint8_t>(), verify_crc, B.status.as<int>())));
+      }
+      if (cudaGetLastError() != cudaSuccess) { err_rc = bfail(ctx, MCOV_ERR_CUDA, "mcov_bam_gpu_stream_depth: inflate launch failed"); break; }
+      uint64_t rec_begin = 0;
+      if (first) {
+        if (total < 12) { err_rc = bfail(ctx, MCOV_ERR_IO, "mcov_bam_gpu_stream_depth: not a valid BAM file"); break; }
+        err_rc = bam_dev_header(ctx, total, &rec_begin, &n_ref);             // (a header that does not fit the first chunk reads as truncated)
+        if (err_rc) break;
+        if (n_ref != ctx->n_contigs) { err_rc = bfail(ctx, MCOV_ERR_ARG, "mcov_bam_gpu_stream_depth: the context's contig table is not this file's"); break; }
+        first = false;
+      } else {
+        int st2[2] = {0, 0};
+        cudaMemcpyAsync(st2, B.status.p, sizeof(st2), cudaMemcpyDeviceToHost, s);
+        if (cudaStreamSynchronize(s) != cudaSuccess) { err_rc = bfail(ctx, MCOV_ERR_CUDA, "mcov_bam_gpu_stream_depth: inflate failed"); break; }
+        if (st2[0]) { err_rc = bfail(ctx, MCOV_ERR_IO, st2[0] == 100 ? "mcov_bam_gpu_stream_depth: CRC mismatch in a BGZF block" : "mcov_bam_gpu_stream_depth: corrupt deflate stream in a BGZF block"); break; }
+      }
+      // the record chain of this chunk
+      uint64_t chain_end = rec_begin;
+      segs.clear(); wo.clear();
+      if (total > rec_begin) { err_rc = bam_dev_chain(ctx, total, rec_begin, n_ref, !was_eof, segs, wo, &chain_end); if (err_rc) break; }
+      uint64_t n_rec = 0, n_cig = 0;
+      for (size_t i = 0; i < segs.size(); ++i) { segs[i].rec_base = (uint64_t)n_carry + n_rec; segs[i].cig_base = (uint64_t)carry_ops + n_cig; n_rec += wo[i].n_rec; n_cig += wo[i].n_cig; }
+      const uint64_t n_tot = (uint64_t)n_carry + n_rec, ops_tot = (uint64_t)carry_ops + n_cig;
+      if (ops_tot > 0xFFFFFFF0ull || n_tot > 0x7FFFFFF0ull) { err_rc = bfail(ctx, MCOV_ERR_RANGE, "mcov_bam_gpu_stream_depth: a chunk holds too many records; use a smaller chunk"); break; }
+      // the bytes of the record this chunk ends in: kept for the front of the next chunk's stream
+      const uint64_t new_tail = total - chain_end;
+      if (new_tail) {
+        if (B.tail2.ensure((size_t)new_tail) != cudaSuccess) { err_rc = bfail(ctx, MCOV_ERR_NOMEM, "mcov_bam_gpu_stream_depth: out of device memory"); break; }
+        cudaMemcpyAsync(B.tail2.p, B.data.as<uint8_t>() + chain_end, (size_t)new_tail, cudaMemcpyDeviceToDevice, s);
+      }
+      // columns: [carried reads | this chunk's]
+      bool okm = B.tid.ensure((n_tot + 4) * 4) == cudaSuccess && B.pos.ensure((n_tot + 4) * 4) == cudaSuccess && B.flag.ensure((n_tot + 4) * 2) == cudaSuccess &&
+                 B.mapq.ensure(n_tot + 4) == cudaSuccess && B.lseq.ensure((n_tot + 4) * 4) == cudaSuccess && B.isize.ensure((n_tot + 4) * 4) == cudaSuccess &&
+                 B.cig_off.ensure((n_tot + 5) * 4) == cudaSuccess && B.cig.ensure((ops_tot + 4) * 4) == cudaSuccess && B.rec_off.ensure((n_tot + 4) * 8) == cudaSuccess;
+      if (!okm) { err_rc = bfail(ctx, MCOV_ERR_NOMEM, "mcov_bam_gpu_stream_depth: out of device memory"); break; }
+      if (n_carry) {
+        cudaMemcpyAsync(B.tid.p, B.c_tid.p, (size_t)n_carry * 4, cudaMemcpyDeviceToDevice, s);
+        cudaMemcpyAsync(B.pos.p, B.c_pos.p, (size_t)n_carry * 4, cudaMemcpyDeviceToDevice, s);
+        cudaMemcpyAsync(B.flag.p, B.c_flag.p, (size_t)n_carry * 2, cudaMemcpyDeviceToDevice, s);
+        cudaMemcpyAsync(B.mapq.p, B.c_mapq.p, (size_t)n_carry, cudaMemcpyDeviceToDevice, s);
+        cudaMemcpyAsync(B.cig_off.p, B.c_off.p, (size_t)n_carry * 4, cudaMemcpyDeviceToDevice, s);
+        if (carry_ops) cudaMemcpyAsync(B.cig.p, B.c_cig.p, (size_t)carry_ops * 4, cudaMemcpyDeviceToDevice, s);
+      }
+      SoaOut o;
+      o.tid = B.tid.as<int32_t>(); o.pos = B.pos.as<int32_t>(); o.flag = B.flag.as<uint16_t>(); o.mapq = B.mapq.as<uint8_t>();
+      o.l_seq = B.lseq.as<int32_t>(); o.isize = B.isize.as<int32_t>(); o.cig_off = B.cig_off.as<uint32_t>(); o.cig = B.cig.as<uint32_t>();
+      o.rec_off = B.rec_off.as<uint64_t>();
+      if (!segs.empty()) {
+        cudaMemcpyAsync(B.segs.p, segs.data(), segs.size() * sizeof(WalkSeg), cudaMemcpyHostToDevice, s);
+        MCOV_LAUNCH(ctx, kKBamWalkWrite, (k_bam_walk_write<<<(unsigned)((segs.size() + 127) / 128), 128, 0, s>>>(
+            B.data.as<uint8_t>(), B.segs.as<WalkSeg>(), (int64_t)segs.size(), o)));
+      }
+      const uint32_t last_off = (uint32_t)ops_tot;
+      cudaMemcpyAsync(o.cig_off + n_tot, &last_off, 4, cudaMemcpyHostToDevice, s);
+      if (cudaStreamSynchronize(s) != cudaSuccess) { err_rc = bfail(ctx, MCOV_ERR_CUDA, "mcov_bam_gpu_stream_depth: record walk failed"); break; }
+      std::swap(B.tail, B.tail2);
+      info->inflated_bytes += (int64_t)(total - tail_len);
+      tail_len = new_tail;
+      if (was_eof && tail_len) { err_rc = bfail(ctx, MCOV_ERR_IO, "mcov_bam_gpu_stream_depth: the last BAM record is truncated"); break; }
+      // the batch -> streamed depth pass
+      const int last = was_eof ? 1 : 0;
+      err_rc = mcov_stream_push(ctx, (int64_t)n_tot, n_carry, o.tid, o.pos, o.flag, o.mapq, o.cig_off, o.cig, MCOV_MEM_DEVICE, last, &rt, &rp);
+      if (err_rc) break;
+      info->n_records += (int64_t)n_rec; info->n_chunks += 1; info->n_segments += (int64_t)segs.size();
+      info->file_bytes += (int64_t)consumed;
+      if (last) { pushed_last = true; break; }
+      // what the next batch must begin with: the suffix from the first read that starts at / reaches past the resend point
+      n_carry = 0; carry_ops = 0;
+      if (n_tot) {
+        unsigned long long* d_first = reinterpret_cast<unsigned long long*>(B.status.as<int>() + 4);
+        const unsigned long long init = n_tot;
+        cudaMemcpyAsync(d_first, &init, 8, cudaMemcpyHostToDevice, s);
+        k_bam_carry_first<<<(unsigned)((n_tot + 255) / 256), 256, 0, s>>>((int64_t)n_tot, o.tid, o.pos, o.cig_off, o.cig, rt, rp, ctx->n_contigs, d_first);
+        unsigned long long j0 = n_tot;
+        cudaMemcpyAsync(&j0, d_first, 8, cudaMemcpyDeviceToHost, s);
+        if (cudaStreamSynchronize(s) != cudaSuccess) { err_rc = bfail(ctx, MCOV_ERR_CUDA, "mcov_bam_gpu_stream_depth: carry selection failed"); break; }
+        if (j0 < n_tot) {
+          uint32_t o0 = 0;
+          cudaMemcpyAsync(&o0, o.cig_off + j0, 4, cudaMemcpyDeviceToHost, s);
+          cudaStreamSynchronize(s);
+          n_carry = (int64_t)(n_tot - j0); carry_ops = (int64_t)ops_tot - (int64_t)o0;
+          okm = B.c_tid.ensure((size_t)n_carry * 4) == cudaSuccess && B.c_pos.ensure((size_t)n_carry * 4) == cudaSuccess &&
+                B.c_flag.ensure((size_t)n_carry * 2) == cudaSuccess && B.c_mapq.ensure((size_t)n_carry) == cudaSuccess &&
+                B.c_off.ensure((size_t)n_carry * 4) == cudaSuccess && B.c_cig.ensure((size_t)std::max<int64_t>(carry_ops, 1) * 4) == cudaSuccess;
+          if (!okm) { err_rc = bfail(ctx, MCOV_ERR_NOMEM, "mcov_bam_gpu_stream_depth: out of device memory"); break; }
+          cudaMemcpyAsync(B.c_tid.p, o.tid + j0, (size_t)n_carry * 4, cudaMemcpyDeviceToDevice, s);
+          cudaMemcpyAsync(B.c_pos.p, o.pos + j0, (size_t)n_carry * 4, cudaMemcpyDeviceToDevice, s);
+          cudaMemcpyAsync(B.c_flag.p, o.flag + j0, (size_t)n_carry * 2, cudaMemcpyDeviceToDevice, s);
+          cudaMemcpyAsync(B.c_mapq.p, o.mapq + j0, (size_t)n_carry, cudaMemcpyDeviceToDevice, s);
+          k_bam_rebase_offsets<<<(unsigned)((n_carry + 255) / 256), 256, 0, s>>>(n_carry, o.cig_off + j0, o0, B.c_off.as<uint32_t>());
+          if (carry_ops) cudaMemcpyAsync(B.c_cig.p, o.cig + o0, (size_t)carry_ops * 4, cudaMemcpyDeviceToDevice, s);
+          info->max_carry = std::max<int64_t>(info->max_carry, n_carry);
+        }
+      }
+      if (cudaGetLastError() != cudaSuccess) { err_rc = bfail(ctx, MCOV_ERR_CUDA, "mcov_bam_gpu_stream_depth: carry copy failed"); break; }
+    } while (false);
+    if (next_read.valid()) {                                      // always join the reader before leaving or going on
+      got = next_read.get();
+      eof = got < (size_t)chunk_bytes;
+      left = next_left;
+      cur ^= 1;
+    }
+    if (err_rc) return err_rc;
+  }
   return MCOV_OK;
 }
 

@@ -113,12 +113,17 @@ struct mcov_ctx {
   struct BamDev {
     mcov::DevBuf raw, blocks, data, status, starts, segs, wout, tid, pos, flag, mapq, lseq, isize, cig_off, cig;
     mcov::DevBuf rec_off, name_hash, kmer, win;      // record offsets in `data`; read names / SEQ derived from them on request
+    // streamed decode (mcov_bam_gpu_stream_depth): pinned file chunks, the bytes of the record a chunk ended in, the reads
+    // carried into the next batch
+    mcov::PinBuf pin[2];
+    mcov::DevBuf tail, tail2, c_tid, c_pos, c_flag, c_mapq, c_off, c_cig;
     int64_t n_rec = -1;                              // records of the last decode (-1: none)
     void release() {
       n_rec = -1;
       mcov::DevBuf* b[] = {&raw, &blocks, &data, &status, &starts, &segs, &wout, &tid, &pos, &flag, &mapq, &lseq, &isize, &cig_off, &cig,
-                           &rec_off, &name_hash, &kmer, &win};
+                           &rec_off, &name_hash, &kmer, &win, &tail, &tail2, &c_tid, &c_pos, &c_flag, &c_mapq, &c_off, &c_cig};
       for (mcov::DevBuf* x : b) x->release();
+      pin[0].release(); pin[1].release();
     }
   } bam;
 

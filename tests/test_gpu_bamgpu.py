@@ -208,3 +208,74 @@ def test_alignmentfile_and_cli_with_gpu_decode(tmp_path):
     assert outs[0] == outs[1] and len(outs[0].splitlines()) == 3
     with pytest.raises(OSError):
         AlignmentFile(str(tmp_path / "fixture.bam.bai"), decode="gpu")          # not a BGZF file
+    # decode="auto": a file this small fits the device -> GPU decode; with an impossible footprint -> streamed GPU decode
+    with AlignmentFile(p, decode="auto") as auto:
+        assert auto.decode == "gpu"
+    old = AlignmentFile.GPU_DECODE_FOOTPRINT
+    AlignmentFile.GPU_DECODE_FOOTPRINT = 1 << 50
+    try:
+        with AlignmentFile(p, decode="auto") as auto:
+            assert auto.decode == "gpu-stream"
+            assert pileup.classic(auto, "ref1", 0, 425) == gold["classic"][0]["result"] or gold["classic"][0]["ref"] != "ref1"
+    finally:
+        AlignmentFile.GPU_DECODE_FOOTPRINT = old
+
+
+def test_streamed_gpu_decode_matches_whole_file(tmp_path):
+    """mcov_bam_gpu_stream_depth: the file in chunks through the GPU decoder into the streamed pass.  Chunks far smaller
+    than the file (records and BGZF blocks cut by every chunk border, reads carried from batch to batch, long reads that
+    reach across several tiles) must give the depth of the one-shot pass bit for bit; unplaced reads at the end are not
+    carried; a truncated file and an unsorted file fail loudly; AlignmentFile(decode="gpu-stream") answers like the host."""
+    from metacov_b200 import AlignmentFile, CoverageEngine, McovError, ReadBatch, bamgpu, pileup, synth
+    w = synth.c2(0.004)                                     # 40 000 reads, 4 contigs
+    hb, isz = synth.generate_host(w)
+    rng = np.random.default_rng(4)
+    n = len(hb.tid)
+    # a few long reads (span >> a tile) and a block of unplaced reads at the end
+    cig = np.array(hb.cig); off = np.array(hb.cig_off)
+    longs = rng.choice(n, 200, replace=False)
+    single = np.flatnonzero(np.diff(off) == 1)
+    longs = np.intersect1d(longs, single)
+    cig[off[longs]] = (rng.integers(3000, 9000, len(longs)).astype(np.uint32) << 4)
+    nu = 500
+    tid = np.r_[hb.tid, np.full(nu, -1, np.int32)]; pos = np.r_[hb.pos, np.full(nu, -1, np.int32)]
+    flag = np.r_[hb.flag, np.full(nu, 4, np.uint16)]; mapq = np.r_[hb.mapq, np.zeros(nu, np.uint8)]
+    off2 = np.r_[off, np.full(nu, off[-1], np.uint32)]
+    b = ReadBatch(tid, pos, flag, mapq, off2, cig)
+    lengths = [int(x) for x in w.contig_len]
+    p = _write(tmp_path, "big.bam", ["c%d" % c for c in range(w.n_contigs)], lengths, b)
+    size = (tmp_path / "big.bam").stat().st_size
+    want, woff, winfo = cport.depth(b, lengths, mode="diff")
+    for chunk in (1 << 17, 300_000, 1 << 30):
+        with CoverageEngine(lengths) as eng:
+            info = bamgpu.stream_depth(eng, p, chunk_bytes=chunk)
+            assert info["n_records"] == len(tid) and info["file_bytes"] == size
+            assert info["n_chunks"] == 1 if chunk > size else info["n_chunks"] >= (4 if chunk == 1 << 17 else 2)
+            pi = eng.pass_info()
+            assert pi["n_pass"] == winfo["n_pass"] and pi["aligned_bases"] == winfo["aligned_bases"] and pi["sorted"] == 1
+            for c in range(len(lengths)):
+                assert np.array_equal(eng.copy_depth(c), want[woff[c]:woff[c] + lengths[c]]), (chunk, c)
+            assert info["max_carry"] < 5000                    # the unplaced tail is not dragged along
+    # truncated file
+    raw = open(p, "rb").read()
+    (tmp_path / "cut.bam").write_bytes(raw[:len(raw) * 2 // 3])
+    with CoverageEngine(lengths) as eng:
+        with pytest.raises(McovError):
+            bamgpu.stream_depth(eng, str(tmp_path / "cut.bam"), chunk_bytes=1 << 17)
+    # unsorted file: reported by the verdict
+    perm = np.arange(len(hb.tid)); perm[100], perm[30000] = perm[30000], perm[100]
+    ub = ReadBatch(hb.tid[perm], hb.pos[perm], hb.flag[perm], hb.mapq[perm], np.arange(len(perm) + 1, dtype=np.uint32),
+                   np.full(len(perm), 100 << 4, np.uint32))
+    pu = _write(tmp_path, "unsorted.bam", ["c%d" % c for c in range(w.n_contigs)], lengths, ub)
+    with CoverageEngine(lengths) as eng:
+        with pytest.raises(McovError):
+            bamgpu.stream_depth(eng, pu, chunk_bytes=1 << 17)
+            eng.pass_info()
+    # the drop-in: same classic() as the host-decoded file, and the unsorted file still gets its depth (whole-file path)
+    with AlignmentFile(p) as host, AlignmentFile(p, decode="gpu-stream", gpu_chunk_bytes=1 << 17) as gs:
+        assert gs.references == host.references and gs.lengths == host.lengths
+        for ref, a0, e0 in (("c0", 0, lengths[0]), ("c2", 1000, 30000), ("c3", 5, 50)):
+            assert pileup.classic(gs, ref, a0, e0) == pileup.classic(host, ref, a0, e0)
+        assert gs.stream_batches >= 4 and gs.gpu_stream_info["n_records"] == len(tid)
+    with AlignmentFile(pu) as host, AlignmentFile(pu, decode="gpu-stream", gpu_chunk_bytes=1 << 17) as gs:
+        assert pileup.classic(gs, "c1", 0, lengths[1]) == pileup.classic(host, "c1", 0, lengths[1])
