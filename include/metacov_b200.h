@@ -215,30 +215,33 @@ int  mcov_depth_sorted_delta(mcov_ctx* ctx, int64_t n,
 /* ---- the transport block: what the host decoder hands to the GPU ----------------
  * ONE contiguous host buffer per batch of coordinate-sorted reads -> ONE host-to-device
  * copy; the SoA columns are rebuilt on the device.  The end-to-end rate is bound by the
- * PCIe link, so the block is as narrow as the data allows (config C2: 2.6 bytes per
+ * PCIe link, so the block is as narrow as the data allows (config C2: 2.3 bytes per
  * read instead of 19.6 for the plain columns):
  *   crs      int64[n_contigs+1]  reads [crs[c], crs[c+1]) belong to contig c, reads from
  *                                crs[n_contigs] on are unplaced (instead of tid[n])
  *   dpos     u8[n]               position - position of the previous read of the same
  *                                contig (first read of a contig: - 0); differences outside
- *                                0..255 are listed as exceptions (exc_idx u32, exc_val i32)
+ *                                0..255 are listed as exceptions (exc_idx u32 ASCENDING,
+ *                                exc_val i32)
  *   fc       u8[n]               index into the joint table jt[<=255] of the batch's most
  *                                frequent (flag, CIGAR class) pairs (u16 flag, u8 class);
- *                                255 = the pair is listed as an escape (esc_idx u32,
- *                                esc_flag u16, esc_cls u8)
+ *                                255 = the pair is listed as an escape (esc_idx u32
+ *                                ASCENDING, esc_flag u16, esc_cls u8)
  *   CIGAR class                  < 128: the read's whole CIGAR is dictionary entry `class`
  *                                (dict_off u32[n_dict+1], dict_ops u32[]: the batch's most
  *                                frequent CIGARs of up to four ops); >= 128: class - 128
- *                                explicit ops follow in xops u32[] in read order
+ *                                explicit ops follow in xops[] in read order: u16
+ *                                (len << 4 | op) when every explicit op of the batch is
+ *                                shorter than 4096 (xop_bytes = 2), else u32
  *   mapq     u8[n]               only when the filter asks for it (min_mapq > 0)
  * A batch with a CIGAR of more than 127 ops (long reads) does not qualify
  * (mcov_pack_block returns MCOV_ERR_RANGE): it travels as plain columns or through
  * mcov_depth_sorted_packed.  All sections start on 16-byte boundaries. */
 #define MCOV_BLOCK_MAGIC 0x4256434Du   /* "MCVB" */
 typedef struct mcov_block_hdr {
-  uint32_t magic, version;                     /* version 2 */
+  uint32_t magic, version;                     /* version 3 */
   int64_t  n, n_carry, n_cigar, n_exc, n_esc, n_xops, total_bytes;
-  int32_t  n_contigs, n_jt, n_dict, n_dictops, has_mapq, reserved0;
+  int32_t  n_contigs, n_jt, n_dict, n_dictops, has_mapq, xop_bytes;   /* xop_bytes: 2 or 4 (width of an explicit op) */
   int32_t  last_tid, last_pos;                 /* the batch's last read (streams: how far the depth becomes final) */
   uint32_t off_crs, off_dpos, off_exc_idx, off_exc_val, off_fc, off_jt, off_esc_idx, off_esc_flag, off_esc_cls,
            off_dict_off, off_dict_ops, off_xops, off_mapq, reserved1;
@@ -262,6 +265,12 @@ int  mcov_pack_block(int64_t n, int64_t n_carry, const int32_t* tid, const int32
 int  mcov_depth_sorted_block(mcov_ctx* ctx, const void* block, int64_t bytes, int wait);
 int  mcov_stream_push_block(mcov_ctx* ctx, const void* block, int64_t bytes, int last,
                             int32_t* resend_tid, int32_t* resend_pos);
+/* The columns a transport block widens into on the device (k_block.cuh), copied back to host arrays of n
+ * (cig_off: n + 1, cig: n_cigar) entries; any output may be NULL.  mapq reads 0xff when the block carries none.
+ * What a caller uses to check a block it built itself, and the test suite to pin the unpack kernels column by
+ * column.  Synchronises; leaves the depth untouched. */
+int  mcov_block_unpack(mcov_ctx* ctx, const void* block, int64_t bytes, int32_t* tid, int32_t* pos, uint16_t* flag,
+                       uint8_t* mapq, uint32_t* cig_off, uint32_t* cig);
 
 /* Replaces the seven reductions of `classic` (reference
  * metacov/pileup.py:18-26) for g regions at once (the loop at cli.py:85-95).

@@ -128,6 +128,7 @@ SIGNATURES = {
     "mcov_pack_block": (C.c_int, [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, C.POINTER(_i64), C.c_int]),
     "mcov_depth_sorted_block": (C.c_int, [_vp, _vp, _i64, C.c_int]),
     "mcov_stream_push_block": (C.c_int, [_vp, _vp, _i64, C.c_int, C.POINTER(_i32), C.POINTER(_i32)]),
+    "mcov_block_unpack": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mcov_depth_sorted_async": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int]),
     "mcov_depth_sorted_packed": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.c_int]),
     "mcov_depth_sorted_delta": (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int]),

@@ -345,11 +345,11 @@ int block_stage(mcov_ctx* ctx, const void* block, int64_t bytes, ExpandArgs& a, 
   *used = nullptr;
   if (!block || bytes < (int64_t)sizeof(mcov_block_hdr)) return fail(ctx, MCOV_ERR_ARG, "transport block: null or too short");
   std::memcpy(&h, block, sizeof(h));
-  if (h.magic != MCOV_BLOCK_MAGIC || h.version != 2) return fail(ctx, MCOV_ERR_ARG, "transport block: bad magic / version");
+  if (h.magic != MCOV_BLOCK_MAGIC || h.version != 3) return fail(ctx, MCOV_ERR_ARG, "transport block: bad magic / version");
   const int64_t n = h.n;
   if (n < 0 || n >= 0xFFFFFFF0ll || h.n_carry < 0 || h.n_carry > n || h.n_exc < 0 || h.n_esc < 0 || h.n_esc > n || h.n_xops < 0 || h.n_cigar < 0 ||
       h.n_cigar > 0xFFFFFFF0ll || h.n_xops > h.n_cigar || h.total_bytes > bytes || h.n_contigs != ctx->n_contigs || h.n_dict < 0 || h.n_dict > 128 ||
-      h.n_jt < 0 || h.n_jt > 255 || h.n_dictops < 0 || h.n_dictops > 512)
+      h.n_jt < 0 || h.n_jt > 255 || h.n_dictops < 0 || h.n_dictops > 512 || (h.xop_bytes != 2 && h.xop_bytes != 4))
     return fail(ctx, MCOV_ERR_ARG, "transport block: inconsistent header (or packed for another contig table)");
   {
     const uint64_t tb = (uint64_t)h.total_bytes, n1 = (uint64_t)std::max<int64_t>(n, 1);
@@ -357,7 +357,7 @@ int block_stage(mcov_ctx* ctx, const void* block, int64_t bytes, ExpandArgs& a, 
     if (!in(h.off_crs, ((uint64_t)h.n_contigs + 1) * 8) || !in(h.off_dpos, n1) || !in(h.off_exc_idx, (uint64_t)h.n_exc * 4) ||
         !in(h.off_exc_val, (uint64_t)h.n_exc * 4) || !in(h.off_fc, n1) || !in(h.off_jt, 1024) || !in(h.off_esc_idx, (uint64_t)h.n_esc * 4) ||
         !in(h.off_esc_flag, (uint64_t)h.n_esc * 2) || !in(h.off_esc_cls, (uint64_t)h.n_esc) || !in(h.off_dict_off, 129 * 4) ||
-        !in(h.off_dict_ops, 2048) || !in(h.off_xops, (uint64_t)h.n_xops * 4) || (h.has_mapq && !in(h.off_mapq, n1)))
+        !in(h.off_dict_ops, 2048) || !in(h.off_xops, (uint64_t)h.n_xops * (uint64_t)h.xop_bytes) || (h.has_mapq && !in(h.off_mapq, n1)))
       return fail(ctx, MCOV_ERR_ARG, "transport block: a section lies outside the block");
   }
   if (!h.has_mapq && ctx->filt.min_mapq > 0) return fail(ctx, MCOV_ERR_ARG, "transport block: packed without mapq, but the filter has min_mapq > 0");
@@ -370,37 +370,26 @@ int block_stage(mcov_ctx* ctx, const void* block, int64_t bytes, ExpandArgs& a, 
   CU(st.raw.ensure((size_t)h.total_bytes + 16));
   CU(st.tid.ensure((size_t)n1 * 4)); CU(st.pos.ensure((size_t)n1 * 4)); CU(st.flag.ensure((size_t)n1 * 2)); CU(st.mapq.ensure((size_t)n1));
   CU(st.cig_off.ensure((size_t)off_len * 4)); CU(st.cig.ensure((size_t)h.n_cigar * 4 + 16));
-  CU(ctx->d_start_slot.ensure((size_t)(off_len + 8) * 4));              // S (the record buffer of the fused pass: free until the prep kernel)
-  CU(ctx->d_end_slot.ensure((size_t)off_len * 4 + (size_t)n1 + 16));    // explicit-op offsets | CIGAR classes
+  const int64_t n_chunks = (off_len + kBlkChunk - 1) / kBlkChunk;
+  CU(ctx->d_end_slot.ensure((size_t)n_chunks * 40 + 64));               // chunk tables of the unpack kernels (free until the prep kernel)
   CU(cudaMemcpyAsync(st.raw.p, block, (size_t)h.total_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
   CU(cudaEventRecord(ctx->copied, ctx->copy_stream));
   CU(cudaStreamWaitEvent(ctx->stream, ctx->copied, 0));
   cudaStream_t s = ctx->stream;
   BlockArgs b;
-  b.blk = st.raw.as<char>(); b.h = h; b.off_len = off_len;
-  b.S = ctx->d_start_slot.as<int32_t>(); b.xoff = ctx->d_end_slot.as<uint32_t>();
-  b.cls = ctx->d_end_slot.as<uint8_t>() + (size_t)off_len * 4;
+  b.blk = st.raw.as<char>(); b.h = h; b.off_len = off_len; b.n_chunks = n_chunks;
+  b.agg = ctx->d_end_slot.as<uint4>(); b.pre = b.agg + n_chunks;
+  b.esc_first = reinterpret_cast<uint32_t*>(b.pre + n_chunks); b.exc_first = b.esc_first + n_chunks;
   b.tid = st.tid.as<int32_t>(); b.pos = st.pos.as<int32_t>(); b.flag = st.flag.as<uint16_t>(); b.mapq = st.mapq.as<uint8_t>();
   b.cig_off = st.cig_off.as<uint32_t>(); b.cig = st.cig.as<uint32_t>();
   ctx->prof_begin(kKBlockUnpack);
-  k_block_seed<<<(unsigned)((off_len + 255) / 256), 256, 0, s>>>(b);
-  if (h.n_esc) k_block_patch<<<(unsigned)((h.n_esc + 255) / 256), 256, 0, s>>>(b);
-  k_block_counts<<<(unsigned)((off_len + 255) / 256), 256, 0, s>>>(b);
-  if (h.n_exc) k_delta_patch<<<(unsigned)((h.n_exc + 255) / 256), 256, 0, s>>>(h.n_exc, reinterpret_cast<const uint32_t*>(b.blk + h.off_exc_idx),
-                                                                               reinterpret_cast<const int32_t*>(b.blk + h.off_exc_val), n, b.S);
+  cudaMemsetAsync(b.esc_first, 0xff, (size_t)n_chunks * 8, s);
+  if (h.n_esc + h.n_exc) k_block_index<<<(unsigned)((h.n_esc + h.n_exc + 255) / 256), 256, 0, s>>>(b);
+  k_block_reduce<<<(unsigned)n_chunks, kBlkThreads, 0, s>>>(b);
+  k_block_prefix<<<1, kBlkPrefixThreads, 0, s>>>(b);
+  k_block_expand<<<(unsigned)n_chunks, kBlkThreads, 0, s>>>(b);
   ctx->prof_end();
-  CU(cudaGetLastError());
-  {
-    const int64_t tiles = (off_len + kScanTile - 1) / kScanTile;
-    CU(ctx->d_tile_cnt.ensure((size_t)tiles * 24));
-    CU(cudaMemsetAsync(ctx->d_tile_cnt.p, 0, (size_t)tiles * 24, s));
-    unsigned long long* stw = ctx->d_tile_cnt.as<unsigned long long>();
-    MCOV_LAUNCH(ctx, kKScanCounts, (k_scan_inplace<false><<<(unsigned)tiles, kScanThreads, 0, s>>>(reinterpret_cast<int32_t*>(b.cig_off), off_len, stw, pc_of(ctx))));
-    MCOV_LAUNCH(ctx, kKScanCounts, (k_scan_inplace<false><<<(unsigned)tiles, kScanThreads, 0, s>>>(b.S, off_len, stw + tiles, pc_of(ctx))));
-    if (h.n_xops) MCOV_LAUNCH(ctx, kKScanCounts, (k_scan_inplace<false><<<(unsigned)tiles, kScanThreads, 0, s>>>(reinterpret_cast<int32_t*>(b.xoff), off_len, stw + 2 * tiles, pc_of(ctx))));
-    CU(cudaGetLastError());
-  }
-  MCOV_LAUNCH(ctx, kKBlockUnpack, (k_block_finish<<<grid_for(ctx, n1, 256, 8), 256, 0, s>>>(b)));
+  ctx->n_launches += 3;                                                 // (prof_begin counted one)
   CU(cudaGetLastError());
   std::memset(&a, 0, sizeof(a));
   a.n = n; a.n_cig = h.n_cigar;
@@ -908,6 +897,31 @@ int mcov_stream_push_block(mcov_ctx* ctx, const void* block, int64_t bytes, int 
   int rc = block_stage(ctx, block, bytes, a, &st, h);
   if (rc) return rc;
   return stream_push_staged(ctx, a, st, h.n, h.n_carry, h.last_tid, h.last_pos, last, resend_tid, resend_pos, /*wait_copy=*/false);
+}
+
+int mcov_block_unpack(mcov_ctx* ctx, const void* block, int64_t bytes, int32_t* tid, int32_t* pos, uint16_t* flag,
+                      uint8_t* mapq, uint32_t* cig_off, uint32_t* cig) {
+  if (!ctx) return MCOV_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  ExpandArgs a;
+  ReadStage* st = nullptr;
+  mcov_block_hdr h;
+  int rc = block_stage(ctx, block, bytes, a, &st, h);
+  if (rc) return rc;
+  cudaStream_t s = ctx->stream;
+  const size_t n = (size_t)h.n;
+  if (n) {
+    if (tid) CU(cudaMemcpyAsync(tid, a.tid, n * 4, cudaMemcpyDeviceToHost, s));
+    if (pos) CU(cudaMemcpyAsync(pos, a.pos, n * 4, cudaMemcpyDeviceToHost, s));
+    if (flag) CU(cudaMemcpyAsync(flag, a.flag, n * 2, cudaMemcpyDeviceToHost, s));
+    if (mapq) CU(cudaMemcpyAsync(mapq, a.mapq, n, cudaMemcpyDeviceToHost, s));
+  }
+  if (cig_off) CU(cudaMemcpyAsync(cig_off, a.cig_off, (n + 1) * 4, cudaMemcpyDeviceToHost, s));
+  if (cig && h.n_cigar) CU(cudaMemcpyAsync(cig, a.cig, (size_t)h.n_cigar * 4, cudaMemcpyDeviceToHost, s));
+  rc = finish_stage(ctx, st, /*wait_copy=*/true);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(s));
+  return MCOV_OK;
 }
 
 int mcov_depth_sorted_block(mcov_ctx* ctx, const void* block, int64_t bytes, int wait) {

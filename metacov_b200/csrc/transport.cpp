@@ -61,7 +61,7 @@ int mcov_pack_block(int64_t n, int64_t n_carry, const int32_t* tid, const int32_
     char* base = static_cast<char*>(out);
     mcov_block_hdr h;
     std::memset(&h, 0, sizeof(h));
-    h.magic = MCOV_BLOCK_MAGIC; h.version = 2; h.n = n; h.n_carry = n_carry; h.n_cigar = n_cig; h.n_contigs = n_contigs;
+    h.magic = MCOV_BLOCK_MAGIC; h.version = 3; h.n = n; h.n_carry = n_carry; h.n_cigar = n_cig; h.n_contigs = n_contigs;
     h.last_tid = n > 0 ? tid[n - 1] : -1; h.last_pos = n > 0 ? pos[n - 1] : 0;
     h.has_mapq = mapq ? 1 : 0;
     size_t o = al16(sizeof(mcov_block_hdr));
@@ -141,7 +141,7 @@ int mcov_pack_block(int64_t n, int64_t n_carry, const int32_t* tid, const int32_
     // ---- per-read pass 1 (parallel): position differences, CIGAR classes; explicit op counts per range ----
     std::vector<uint8_t> cls((size_t)n1);
     std::vector<int64_t> xcount((size_t)n_threads + 1, 0);
-    std::vector<int> too_long((size_t)n_threads, 0);
+    std::vector<int> too_long((size_t)n_threads, 0), wide_op((size_t)n_threads, 0);
     par_for(n, n_threads, [&](int t, int64_t a, int64_t b) {
       int64_t xc = 0;
       for (int64_t i = a; i < b; ++i) {
@@ -153,12 +153,17 @@ int mcov_pack_block(int64_t n, int64_t n_carry, const int32_t* tid, const int32_
         const uint32_t nc = cig_off[i + 1] - cig_off[i];
         const int k = dict_find(cig + cig_off[i], nc);
         if (k >= 0) cls[(size_t)i] = (uint8_t)k;
-        else if (nc <= 127) { cls[(size_t)i] = (uint8_t)(128 + nc); xc += nc; }
+        else if (nc <= 127) {
+          cls[(size_t)i] = (uint8_t)(128 + nc); xc += nc;
+          for (uint32_t q = 0; q < nc; ++q) if (cig[cig_off[i] + q] > 0xFFFFu) wide_op[(size_t)t] = 1;   // len >= 4096: no u16 form
+        }
         else { too_long[(size_t)t] = 1; cls[(size_t)i] = 128; }
       }
       xcount[(size_t)t + 1] = xc;
     });
     for (int t = 0; t < n_threads; ++t) if (too_long[(size_t)t]) return MCOV_ERR_RANGE;
+    h.xop_bytes = 2;
+    for (int t = 0; t < n_threads; ++t) if (wide_op[(size_t)t]) h.xop_bytes = 4;
     // ---- joint table: the 255 most frequent (flag, class) pairs of a sample of the batch ----
     std::vector<uint32_t> jt;
     std::vector<int16_t> jslot(1u << 16, -1);                 // hash table over (flag << 8 | class), open addressing
@@ -207,6 +212,8 @@ int mcov_pack_block(int64_t n, int64_t n_carry, const int32_t* tid, const int32_
     o += al16(1024);
     h.off_xops = (uint32_t)o;
     uint32_t* xops = reinterpret_cast<uint32_t*>(base + o);
+    uint16_t* xops16 = reinterpret_cast<uint16_t*>(base + o);
+    const bool narrow = h.xop_bytes == 2;
     for (int t = 0; t < n_threads; ++t) xcount[(size_t)t + 1] += xcount[(size_t)t];
     h.n_xops = xcount[(size_t)n_threads];
     // ---- per-read pass 2 (parallel): joint-table indices (escapes listed), explicit ops ----
@@ -218,12 +225,13 @@ int mcov_pack_block(int64_t n, int64_t n_carry, const int32_t* tid, const int32_
         if (k >= 0) fc[i] = (uint8_t)k; else { fc[i] = 255; esc[(size_t)t].push_back((uint32_t)i); }
         if (cls[(size_t)i] >= 128) {
           const uint32_t nc = cls[(size_t)i] - 128u;
-          std::memcpy(xops + w, cig + cig_off[i], (size_t)nc * 4);
+          if (narrow) for (uint32_t q = 0; q < nc; ++q) xops16[w + q] = (uint16_t)cig[cig_off[i] + q];
+          else std::memcpy(xops + w, cig + cig_off[i], (size_t)nc * 4);
           w += nc;
         }
       }
     });
-    o += al16((size_t)h.n_xops * 4 + 16);
+    o += al16((size_t)h.n_xops * (size_t)h.xop_bytes + 16);
     // ---- escapes ----
     size_t n_esc = 0;
     for (auto& v : esc) n_esc += v.size();

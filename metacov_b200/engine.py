@@ -194,6 +194,19 @@ class CoverageEngine:
         buf, nbytes = block
         self._check(lib.mcov_depth_sorted_block(self._ctx, _capi.ptr(buf), int(nbytes), 1 if wait else 0))
 
+    def block_unpack(self, block):
+        """The SoA columns a transport block widens into on the device, copied back (``mcov_block_unpack``):
+        dict with tid, pos, flag, mapq, cig_off (n + 1), cig."""
+        import struct
+        buf, nbytes = block
+        raw = buf.numpy() if _is_torch(buf) else np.asarray(buf)
+        n, _n_carry, n_cigar = struct.unpack_from("<qqq", raw[:32].tobytes(), 8)
+        out = {"tid": np.empty(n, np.int32), "pos": np.empty(n, np.int32), "flag": np.empty(n, np.uint16),
+               "mapq": np.empty(n, np.uint8), "cig_off": np.empty(n + 1, np.uint32), "cig": np.empty(n_cigar, np.uint32)}
+        self._check(lib.mcov_block_unpack(self._ctx, _capi.ptr(buf), int(nbytes), *[_capi.ptr(out[k]) for k in
+                                                                                  ("tid", "pos", "flag", "mapq", "cig_off", "cig")]))
+        return out
+
     def stream_push_block(self, block, last=False):
         """One batch of a streamed pass as a transport block; returns the resend point like ``stream_push``."""
         buf, nbytes = block

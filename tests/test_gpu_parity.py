@@ -755,3 +755,64 @@ def test_warp_statistics_window_guess_refit_and_retry():
         assert d0[:512].min() - d0.min() > 256 and d0.max() - d0.min() < 1024
         assert d1.max() - d1.min() >= 1024
         assert d2.max() - d2[:512].min() > 768 and d2.max() - d2.min() < 1024
+
+
+def test_block_unpack_column_by_column():
+    """mcov_block_unpack: the columns k_block_index / reduce / prefix / expand rebuild from a transport block are the
+    columns it was packed from -- contig starts on, just before and just after the 2 048-read chunk borders, runs of
+    empty contigs, an unplaced tail, batches of 0 / 1 / 2 047 / 2 048 / 2 049 reads, position exceptions and escapes in
+    every chunk, explicit ops in the u16 and (an op of 4 096 or more) the u32 form, many small contigs (C3-like)."""
+    from metacov_b200 import ReadBatch, synth
+    from metacov_b200.engine import pack_block
+    rng = np.random.default_rng(11)
+
+    def check(b, n_contigs, with_mapq=False, pinned=False):
+        blk = pack_block(b, n_contigs, with_mapq=with_mapq, pinned=pinned)
+        with engine_for(np.full(n_contigs, 6_000_000, np.int32)) as eng:
+            u = eng.block_unpack(blk)
+        tid = np.asarray(b.tid)
+        valid = (tid >= 0) & (tid < n_contigs)
+        assert np.array_equal(u["tid"][valid], tid[valid]) and np.all(u["tid"][~valid] == -1)
+        assert np.array_equal(u["pos"], np.asarray(b.pos)) and np.array_equal(u["flag"], np.asarray(b.flag))
+        assert np.array_equal(u["cig_off"], np.asarray(b.cig_off)) and np.array_equal(u["cig"], np.asarray(b.cig))
+        assert np.array_equal(u["mapq"], np.asarray(b.mapq)) if with_mapq else np.all(u["mapq"] == 0xff)
+        return blk
+
+    def batch(tid, wide=False, many_flags=False, big_gaps=False):
+        n = len(tid)
+        pos = np.zeros(n, np.int64)
+        for c in np.unique(tid):
+            m = tid == c
+            gaps = rng.integers(0, 12, int(m.sum()))
+            if big_gaps:
+                gaps[rng.random(len(gaps)) < 0.02] = rng.integers(256, 40_000)
+            pos[m] = np.cumsum(gaps) + rng.integers(0, 1000)
+        flag = (rng.integers(0, 4096, n) if many_flags else rng.choice(np.array([99, 147, 83, 163, 1024 + 99]), n)).astype(np.uint16)
+        n_op = rng.choice(np.array([1, 1, 1, 1, 2, 3, 5, 0]), n)
+        off = np.concatenate(([0], np.cumsum(n_op))).astype(np.uint32)
+        ln = rng.integers(1, 150, int(off[-1])).astype(np.uint32)
+        ln[off[:-1][n_op == 1]] = 150                           # the common single-op CIGAR: a dictionary entry
+        if wide and len(ln):
+            ln[rng.integers(0, len(ln))] = 5000
+        cig = (ln << 4) | rng.choice(np.array([0, 1, 2, 4, 7, 8], np.uint32), len(ln)).astype(np.uint32)
+        return ReadBatch(tid.astype(np.int32), pos.astype(np.int32), flag, rng.integers(0, 61, n).astype(np.uint8), off, cig)
+
+    # contig starts around the chunk borders; empty contigs in runs; an unplaced tail
+    sizes = [2048, 0, 0, 2047, 1, 0, 2049, 4095, 1, 1, 0, 0, 0, 4096, 5, 0]
+    tid = np.repeat(np.arange(len(sizes)), sizes)
+    tid = np.r_[tid, np.full(3000, -1)]
+    for kw in ({}, {"big_gaps": True}, {"many_flags": True, "big_gaps": True}, {"wide": True}):
+        b = batch(tid, **kw)
+        blk = check(b, len(sizes), with_mapq=bool(kw.get("wide")), pinned=bool(kw.get("big_gaps")))
+    for n in (0, 1, 2047, 2048, 2049, 4096, 4097):
+        check(batch(np.zeros(n, np.int64)), 1)
+        check(batch(np.sort(rng.integers(0, 7, n))), 9, with_mapq=True)
+        check(batch(np.full(n, -1)), 3)                            # nothing but unplaced reads
+    # many small contigs (some empty), like C3
+    check(batch(np.sort(rng.integers(0, 30_000, 60_000)), big_gaps=True), 30_000)
+    w = synth.c3(0.002)
+    b3, _ = synth.generate_host(w)
+    check(b3, w.n_contigs)
+    w = synth.c2(0.01)
+    b2, _ = synth.generate_host(w)
+    check(b2, w.n_contigs, pinned=True)

@@ -101,17 +101,18 @@ def test_partition_positions_covers_every_base_once():
 
 
 def _unpack_block(buf):
-    """The transport block (include/metacov_b200.h: mcov_block_hdr, version 2) decoded in numpy: what k_block_seed /
-    k_block_patch / k_delta_patch / k_block_counts / the prefix sums / k_block_finish rebuild on the device."""
+    """The transport block (include/metacov_b200.h: mcov_block_hdr, version 3) decoded in numpy: what k_block_index /
+    k_block_reduce / k_block_prefix / k_block_expand rebuild on the device."""
     import struct
     raw = np.asarray(buf, dtype=np.uint8)
-    (magic, version, n, n_carry, n_cigar, n_exc, n_esc, n_xops, total, n_contigs, n_jt, n_dict, n_dictops, has_mapq, _r0,
+    (magic, version, n, n_carry, n_cigar, n_exc, n_esc, n_xops, total, n_contigs, n_jt, n_dict, n_dictops, has_mapq, xop_bytes,
      last_tid, last_pos, o_crs, o_dpos, o_ei, o_ev, o_fc, o_jt, o_qi, o_qf, o_qc, o_doff, o_dops, o_xops, o_mapq, _r1) = struct.unpack_from(
         "<IIqqqqqqqiiiiiiiiIIIIIIIIIIIIII", raw.tobytes()[:200])
-    assert magic == 0x4256434D and version == 2 and total <= len(raw)
+    assert magic == 0x4256434D and version == 3 and total <= len(raw) and xop_bytes in (2, 4)
     view = lambda off, cnt, dt: raw[off:off + cnt * np.dtype(dt).itemsize].view(dt)
     crs = view(o_crs, n_contigs + 1, np.int64)
     d = view(o_dpos, n, np.uint8).astype(np.int64)
+    assert np.all(np.diff(view(o_ei, n_exc, np.uint32).astype(np.int64)) > 0)            # ascending: the device relies on it
     d[view(o_ei, n_exc, np.uint32)] = view(o_ev, n_exc, np.int32)
     S = np.cumsum(d)
     pos = np.empty(n, np.int64)
@@ -126,11 +127,12 @@ def _unpack_block(buf):
     e = jt[fc]
     flag, cc = (e >> 8).astype(np.uint16), (e & 255).astype(np.int64)
     qi = view(o_qi, n_esc, np.uint32)
-    assert np.array_equal(np.sort(qi), np.nonzero(fc == 255)[0])
+    assert np.array_equal(qi, np.nonzero(fc == 255)[0])                                  # ascending
     flag[qi] = view(o_qf, n_esc, np.uint16)
     cc[qi] = view(o_qc, n_esc, np.uint8)
     doff = view(o_doff, n_dict + 1, np.uint32).astype(np.int64)
-    dops, xops = view(o_dops, n_dictops, np.uint32), view(o_xops, n_xops, np.uint32)
+    dops = view(o_dops, n_dictops, np.uint32)
+    xops = view(o_xops, n_xops, np.uint16 if xop_bytes == 2 else np.uint32).astype(np.uint32)
     cig, ncig, x = [], np.zeros(n, np.int64), 0
     for i in range(n):
         if cc[i] < 128:
@@ -141,7 +143,8 @@ def _unpack_block(buf):
     assert x == n_xops and int(ncig.sum()) == n_cigar
     mapq = view(o_mapq, n, np.uint8) if has_mapq else None
     return dict(n=n, n_carry=n_carry, tid=tid, pos=pos.astype(np.int64), flag=flag, ncig=ncig, mapq=mapq,
-                cig=np.concatenate(cig) if cig else np.zeros(0, np.uint32), last=(last_tid, last_pos), n_exc=n_exc, n_esc=n_esc)
+                cig=np.concatenate(cig) if cig else np.zeros(0, np.uint32), last=(last_tid, last_pos), n_exc=n_exc, n_esc=n_esc,
+                xop_bytes=xop_bytes)
 
 
 def test_block_packer_round_trip():
