@@ -215,7 +215,7 @@ int  mcov_depth_sorted_delta(mcov_ctx* ctx, int64_t n,
 /* ---- the transport block: what the host decoder hands to the GPU ----------------
  * ONE contiguous host buffer per batch of coordinate-sorted reads -> ONE host-to-device
  * copy; the SoA columns are rebuilt on the device.  The end-to-end rate is bound by the
- * PCIe link, so the block is as narrow as the data allows (config C2: 2.3 bytes per
+ * PCIe link, so the block is as narrow as the data allows (config C2: 1.4 bytes per
  * read instead of 19.6 for the plain columns):
  *   crs      int64[n_contigs+1]  reads [crs[c], crs[c+1]) belong to contig c, reads from
  *                                crs[n_contigs] on are unplaced (instead of tid[n])
@@ -234,18 +234,30 @@ int  mcov_depth_sorted_delta(mcov_ctx* ctx, int64_t n,
  *                                (len << 4 | op) when every explicit op of the batch is
  *                                shorter than 4096 (xop_bytes = 2), else u32
  *   mapq     u8[n]               only when the filter asks for it (min_mapq > 0)
+ * NIBBLE FORM (nib = 1; chosen by the packer when it is the smaller one -- deep short-read
+ * data, where most differences are below 15 and a handful of (flag, CIGAR) pairs cover
+ * most reads; config C2: 1.4 bytes per read): dpos[] and fc[] are replaced by
+ *   nb       u8[n]               low nibble: the position difference 0..14, or 15 = the
+ *                                difference (15..255) is the next entry of dq u8[] (reads
+ *                                listed as exceptions carry 0); high nibble: the joint-table
+ *                                index 0..14, or 15 = the index (15..254, 255 = escape) is
+ *                                the next entry of fq u8[]
+ *   chunk    u32[2*ceil(n/2048)] where the entries of dq / fq of every 2048 reads begin
  * A batch with a CIGAR of more than 127 ops (long reads) does not qualify
  * (mcov_pack_block returns MCOV_ERR_RANGE): it travels as plain columns or through
  * mcov_depth_sorted_packed.  All sections start on 16-byte boundaries. */
 #define MCOV_BLOCK_MAGIC 0x4256434Du   /* "MCVB" */
 typedef struct mcov_block_hdr {
-  uint32_t magic, version;                     /* version 3 */
+  uint32_t magic, version;                     /* version 4 */
   int64_t  n, n_carry, n_cigar, n_exc, n_esc, n_xops, total_bytes;
   int32_t  n_contigs, n_jt, n_dict, n_dictops, has_mapq, xop_bytes;   /* xop_bytes: 2 or 4 (width of an explicit op) */
   int32_t  last_tid, last_pos;                 /* the batch's last read (streams: how far the depth becomes final) */
   uint32_t off_crs, off_dpos, off_exc_idx, off_exc_val, off_fc, off_jt, off_esc_idx, off_esc_flag, off_esc_cls,
-           off_dict_off, off_dict_ops, off_xops, off_mapq, reserved1;
+           off_dict_off, off_dict_ops, off_xops, off_mapq, nib;         /* nib: 1 = nibble form (off_dpos = off_fc = 0) */
+  int64_t  n_dq, n_fq;                         /* nibble form: entries of the two side lists */
+  uint32_t off_nb, off_dq, off_fq, off_chunk;
 } mcov_block_hdr;
+#define MCOV_BLOCK_CHUNK 2048                  /* reads per entry of the chunk table (and per CTA of the unpack kernels) */
 /* Upper bound of the block size for a batch of n reads with n_cigar ops over n_contigs contigs. */
 int64_t mcov_block_bound(int64_t n, int64_t n_cigar, int32_t n_contigs);
 /* Pack a coordinate-sorted SoA batch (host arrays, grouped by contig with unplaced reads last; the first

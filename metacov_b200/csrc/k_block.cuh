@@ -1,8 +1,8 @@
-// k_block.cuh -- the transport block (include/metacov_b200.h: mcov_block_hdr, version 3) widened into SoA columns on the
+// k_block.cuh -- the transport block (include/metacov_b200.h: mcov_block_hdr, version 4) widened into SoA columns on the
 // device.
 //
-// One host-to-device copy brings the block; three launches rebuild the columns, each read of the block touched twice
-// (2.3 bytes) and every column written once:
+// One host-to-device copy brings the block; four launches rebuild the columns, each byte of the block touched twice
+// and every column written once:
 //   k_block_index   (one thread per escape / exception) where the ascending escape and exception lists enter each
 //                   chunk of 2 048 reads;
 //   k_block_reduce  (one CTA per chunk) the chunk's totals: CIGAR ops, explicit ops, and the position sum since the
@@ -12,9 +12,10 @@
 //   k_block_expand  (one CTA per chunk) tid (running maximum over the contig starts inside the chunk), pos (segmented
 //                   scan with the chunk's carry), flag, mapq, op offsets, and every read's ops copied from the
 //                   dictionary (shared memory) or the explicit list -- eight consecutive reads per thread, 64-bit
-//                   loads of the two byte columns, 128-bit stores of the columns.
-// Round 2's first version took eight launches (seed, two patches, counts, three look-back scans, finish) and 340 us for
-// 10 M reads; this one takes ~60 us, so an end-to-end step is the PCIe copy and nothing else.
+//                   loads of the per-read bytes, 128-bit stores of the columns.
+// The per-read bytes come wide (dpos[], fc[]) or as nibbles with side lists (blk_load), as the packer chose.
+// Round 2's first version took eight launches (seed, two patches, counts, three look-back scans, finish) and 335 us for
+// 10 M reads.
 #pragma once
 #include "common.cuh"
 
@@ -23,6 +24,7 @@ namespace mcov {
 constexpr int kBlkThreads = 256;
 constexpr int kBlkPer = 8;
 constexpr int kBlkChunk = kBlkThreads * kBlkPer;          // 2 048 reads per CTA
+static_assert(kBlkChunk == MCOV_BLOCK_CHUNK, "the block's chunk table is per CTA of the unpack kernels");
 constexpr uint32_t kBlkNone = 0xFFFFFFFFu;
 
 struct BlockArgs {
@@ -77,6 +79,7 @@ struct BlkShared {
   int32_t d[kBlkChunk];       // per read: position difference (patching the exceptions)
   unsigned long long w64[kBlkThreads / 32];
   int32_t w_s[kBlkThreads / 32], w_f[kBlkThreads / 32], w_m[kBlkThreads / 32];
+  uint32_t w_n[kBlkThreads / 32];
   int32_t c_lo, c_hi;
 };
 
@@ -95,7 +98,52 @@ __device__ __forceinline__ void blk_load(const BlockArgs& a, BlkShared& sm, int6
   const int64_t n = h.n, c0 = chunk * kBlkChunk, i0 = c0 + (int64_t)threadIdx.x * kBlkPer;
   const uint8_t* fc = reinterpret_cast<const uint8_t*>(a.blk + h.off_fc);
   const uint8_t* dp = reinterpret_cast<const uint8_t*>(a.blk + h.off_dpos);
-  if (i0 + kBlkPer <= n) {
+  if (h.nib) {
+    // nibble form: one byte per read; a nibble of 15 sends to the next entry of a side list, whose place is the chunk's
+    // offset (chunk table of the block) + the number of such nibbles in front of the read (one scan over the CTA)
+    const uint8_t* nb = reinterpret_cast<const uint8_t*>(a.blk + h.off_nb);
+    uint32_t lo[kBlkPer], hi[kBlkPer];
+    if (i0 + kBlkPer <= n) {
+      const uint2 q = *reinterpret_cast<const uint2*>(nb + i0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t b0 = (q.x >> (8 * j)) & 255u, b1 = (q.y >> (8 * j)) & 255u;
+        lo[j] = b0 & 15u; hi[j] = b0 >> 4; lo[j + 4] = b1 & 15u; hi[j + 4] = b1 >> 4;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kBlkPer; ++j) {
+        const uint32_t b = i0 + j < n ? (uint32_t)nb[i0 + j] : 0x1000u;       // (beyond n: no difference; index 256 = no ops)
+        lo[j] = b & 15u; hi[j] = b >> 4;
+      }
+    }
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int j = 0; j < kBlkPer; ++j) cnt += (lo[j] == 15u ? 1u : 0u) + (hi[j] == 15u ? 0x10000u : 0u);
+    uint32_t inc = cnt;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+    if (lane == 31) sm.w_n[warp] = inc;
+    __syncthreads();
+    uint32_t ex = inc - cnt;
+    for (int w = 0; w < warp; ++w) ex += sm.w_n[w];
+    uint32_t kd = 0, kf = 0;
+    if (c0 < n) {
+      const uint32_t* ct = reinterpret_cast<const uint32_t*>(a.blk + h.off_chunk);
+      kd = ct[2 * chunk] + (ex & 0xFFFFu); kf = ct[2 * chunk + 1] + (ex >> 16);
+    }
+    const uint8_t* dq = reinterpret_cast<const uint8_t*>(a.blk + h.off_dq);
+    const uint8_t* fq = reinterpret_cast<const uint8_t*>(a.blk + h.off_fq);
+#pragma unroll
+    for (int j = 0; j < kBlkPer; ++j) {
+      uint32_t dv = lo[j], fi = hi[j];
+      if (dv == 15u) { dv = (int64_t)kd < h.n_dq ? (uint32_t)dq[kd] : 0u; ++kd; }
+      if (fi == 15u) { fi = (int64_t)kf < h.n_fq ? (uint32_t)fq[kf] : 255u; ++kf; }
+      d[j] = (int32_t)dv;
+      e[j] = fi < 256u ? sm.jt[fi] : 128u;
+    }
+  } else if (i0 + kBlkPer <= n) {
     const uint2 f = *reinterpret_cast<const uint2*>(fc + i0), q = *reinterpret_cast<const uint2*>(dp + i0);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {

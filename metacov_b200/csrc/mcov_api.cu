@@ -345,17 +345,21 @@ int block_stage(mcov_ctx* ctx, const void* block, int64_t bytes, ExpandArgs& a, 
   *used = nullptr;
   if (!block || bytes < (int64_t)sizeof(mcov_block_hdr)) return fail(ctx, MCOV_ERR_ARG, "transport block: null or too short");
   std::memcpy(&h, block, sizeof(h));
-  if (h.magic != MCOV_BLOCK_MAGIC || h.version != 3) return fail(ctx, MCOV_ERR_ARG, "transport block: bad magic / version");
+  if (h.magic != MCOV_BLOCK_MAGIC || h.version != 4) return fail(ctx, MCOV_ERR_ARG, "transport block: bad magic / version");
   const int64_t n = h.n;
   if (n < 0 || n >= 0xFFFFFFF0ll || h.n_carry < 0 || h.n_carry > n || h.n_exc < 0 || h.n_esc < 0 || h.n_esc > n || h.n_xops < 0 || h.n_cigar < 0 ||
       h.n_cigar > 0xFFFFFFF0ll || h.n_xops > h.n_cigar || h.total_bytes > bytes || h.n_contigs != ctx->n_contigs || h.n_dict < 0 || h.n_dict > 128 ||
-      h.n_jt < 0 || h.n_jt > 255 || h.n_dictops < 0 || h.n_dictops > 512 || (h.xop_bytes != 2 && h.xop_bytes != 4))
+      h.n_jt < 0 || h.n_jt > 255 || h.n_dictops < 0 || h.n_dictops > 512 || (h.xop_bytes != 2 && h.xop_bytes != 4) || h.nib > 1 ||
+      (h.nib && (h.n_dq < 0 || h.n_dq > n || h.n_fq < 0 || h.n_fq > n)))
     return fail(ctx, MCOV_ERR_ARG, "transport block: inconsistent header (or packed for another contig table)");
   {
     const uint64_t tb = (uint64_t)h.total_bytes, n1 = (uint64_t)std::max<int64_t>(n, 1);
     auto in = [&](uint32_t off, uint64_t len) { return (off & 15u) == 0 && (uint64_t)off + len <= tb; };
-    if (!in(h.off_crs, ((uint64_t)h.n_contigs + 1) * 8) || !in(h.off_dpos, n1) || !in(h.off_exc_idx, (uint64_t)h.n_exc * 4) ||
-        !in(h.off_exc_val, (uint64_t)h.n_exc * 4) || !in(h.off_fc, n1) || !in(h.off_jt, 1024) || !in(h.off_esc_idx, (uint64_t)h.n_esc * 4) ||
+    const bool per_read = h.nib ? in(h.off_nb, n1) && in(h.off_dq, (uint64_t)h.n_dq) && in(h.off_fq, (uint64_t)h.n_fq) &&
+                                  in(h.off_chunk, (uint64_t)((n + MCOV_BLOCK_CHUNK - 1) / MCOV_BLOCK_CHUNK) * 8)
+                                : in(h.off_dpos, n1) && in(h.off_fc, n1);
+    if (!in(h.off_crs, ((uint64_t)h.n_contigs + 1) * 8) || !per_read || !in(h.off_exc_idx, (uint64_t)h.n_exc * 4) ||
+        !in(h.off_exc_val, (uint64_t)h.n_exc * 4) || !in(h.off_jt, 1024) || !in(h.off_esc_idx, (uint64_t)h.n_esc * 4) ||
         !in(h.off_esc_flag, (uint64_t)h.n_esc * 2) || !in(h.off_esc_cls, (uint64_t)h.n_esc) || !in(h.off_dict_off, 129 * 4) ||
         !in(h.off_dict_ops, 2048) || !in(h.off_xops, (uint64_t)h.n_xops * (uint64_t)h.xop_bytes) || (h.has_mapq && !in(h.off_mapq, n1)))
       return fail(ctx, MCOV_ERR_ARG, "transport block: a section lies outside the block");

@@ -61,7 +61,7 @@ int mcov_pack_block(int64_t n, int64_t n_carry, const int32_t* tid, const int32_
     char* base = static_cast<char*>(out);
     mcov_block_hdr h;
     std::memset(&h, 0, sizeof(h));
-    h.magic = MCOV_BLOCK_MAGIC; h.version = 3; h.n = n; h.n_carry = n_carry; h.n_cigar = n_cig; h.n_contigs = n_contigs;
+    h.magic = MCOV_BLOCK_MAGIC; h.version = 4; h.n = n; h.n_carry = n_carry; h.n_cigar = n_cig; h.n_contigs = n_contigs;
     h.last_tid = n > 0 ? tid[n - 1] : -1; h.last_pos = n > 0 ? pos[n - 1] : 0;
     h.has_mapq = mapq ? 1 : 0;
     size_t o = al16(sizeof(mcov_block_hdr));
@@ -80,9 +80,8 @@ int mcov_pack_block(int64_t n, int64_t n_carry, const int32_t* tid, const int32_
     }
     const size_t n1 = (size_t)std::max<int64_t>(n, 1);
     // ---- positions: u8 differences + exceptions ----
-    h.off_dpos = (uint32_t)o;
-    uint8_t* dpos = reinterpret_cast<uint8_t*>(base + o);
-    o += al16(n1);
+    std::vector<uint8_t> dpos_v(n1), fc_v(n1);                 // placed (wide or as nibbles) once both are known
+    uint8_t* dpos = dpos_v.data();
     std::vector<std::vector<std::pair<uint32_t, int32_t>>> exc((size_t)n_threads);
     // ---- CIGAR dictionary: the 128 most frequent CIGARs of up to four ops (counted on a sample of the batch) ----
     std::vector<Cand> table(kTable);
@@ -202,9 +201,7 @@ int mcov_pack_block(int64_t n, int64_t n_carry, const int32_t* tid, const int32_
       }
       return -1;
     };
-    h.off_fc = (uint32_t)o;
-    uint8_t* fc = reinterpret_cast<uint8_t*>(base + o);
-    o += al16(n1);
+    uint8_t* fc = fc_v.data();
     h.off_jt = (uint32_t)o;
     h.n_jt = (int32_t)jt.size();
     std::memset(base + o, 0, 1024);
@@ -232,6 +229,48 @@ int mcov_pack_block(int64_t n, int64_t n_carry, const int32_t* tid, const int32_
       }
     });
     o += al16((size_t)h.n_xops * (size_t)h.xop_bytes + 16);
+    // ---- the two per-read bytes: wide (dpos[], fc[]) or as nibbles + side lists, whichever is smaller ----
+    {
+      const int64_t n_chunks = (n + MCOV_BLOCK_CHUNK - 1) / MCOV_BLOCK_CHUNK;
+      std::vector<uint32_t> cd((size_t)n_chunks + 1, 0), cf((size_t)n_chunks + 1, 0);
+      // (threads split the READS; a thread takes the chunks that begin in its range)
+      auto chunks_of = [](int64_t a) { return (a + MCOV_BLOCK_CHUNK - 1) / MCOV_BLOCK_CHUNK; };
+      par_for(n, n_threads, [&](int, int64_t ra, int64_t rb) {
+        for (int64_t c = chunks_of(ra); c < chunks_of(rb); ++c) {
+          uint32_t kd = 0, kf = 0;
+          const int64_t e = std::min<int64_t>(n, (c + 1) * MCOV_BLOCK_CHUNK);
+          for (int64_t i = c * MCOV_BLOCK_CHUNK; i < e; ++i) { kd += dpos[i] >= 15; kf += fc[i] >= 15; }
+          cd[(size_t)c + 1] = kd; cf[(size_t)c + 1] = kf;
+        }
+      });
+      for (int64_t c = 0; c < n_chunks; ++c) { cd[(size_t)c + 1] += cd[(size_t)c]; cf[(size_t)c + 1] += cf[(size_t)c]; }
+      const size_t n_dq = cd[(size_t)n_chunks], n_fq = cf[(size_t)n_chunks];
+      const size_t nib_bytes = al16(n1) + al16(n_dq + 16) + al16(n_fq + 16) + al16((size_t)n_chunks * 8 + 16);
+      if (nib_bytes < 2 * al16(n1)) {
+        h.nib = 1; h.n_dq = (int64_t)n_dq; h.n_fq = (int64_t)n_fq;
+        h.off_nb = (uint32_t)o; uint8_t* nb = reinterpret_cast<uint8_t*>(base + o); o += al16(n1);
+        h.off_dq = (uint32_t)o; uint8_t* dq = reinterpret_cast<uint8_t*>(base + o); o += al16(n_dq + 16);
+        h.off_fq = (uint32_t)o; uint8_t* fq = reinterpret_cast<uint8_t*>(base + o); o += al16(n_fq + 16);
+        h.off_chunk = (uint32_t)o; uint32_t* ct = reinterpret_cast<uint32_t*>(base + o); o += al16((size_t)n_chunks * 8 + 16);
+        par_for(n, n_threads, [&](int, int64_t ra, int64_t rb) {
+          for (int64_t c = chunks_of(ra); c < chunks_of(rb); ++c) {
+            uint32_t wd = cd[(size_t)c], wf = cf[(size_t)c];
+            ct[2 * c] = wd; ct[2 * c + 1] = wf;
+            const int64_t e = std::min<int64_t>(n, (c + 1) * MCOV_BLOCK_CHUNK);
+            for (int64_t i = c * MCOV_BLOCK_CHUNK; i < e; ++i) {
+              uint8_t lo = dpos[i], hi = fc[i];
+              if (lo >= 15) { dq[wd++] = lo; lo = 15; }
+              if (hi >= 15) { fq[wf++] = hi; hi = 15; }
+              nb[i] = (uint8_t)(lo | (hi << 4));
+            }
+          }
+        });
+      } else {
+        h.nib = 0;
+        h.off_dpos = (uint32_t)o; if (n > 0) std::memcpy(base + o, dpos, (size_t)n); o += al16(n1);
+        h.off_fc = (uint32_t)o; if (n > 0) std::memcpy(base + o, fc, (size_t)n); o += al16(n1);
+      }
+    }
     // ---- escapes ----
     size_t n_esc = 0;
     for (auto& v : esc) n_esc += v.size();

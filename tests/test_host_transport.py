@@ -101,17 +101,31 @@ def test_partition_positions_covers_every_base_once():
 
 
 def _unpack_block(buf):
-    """The transport block (include/metacov_b200.h: mcov_block_hdr, version 3) decoded in numpy: what k_block_index /
+    """The transport block (include/metacov_b200.h: mcov_block_hdr, version 4) decoded in numpy: what k_block_index /
     k_block_reduce / k_block_prefix / k_block_expand rebuild on the device."""
     import struct
     raw = np.asarray(buf, dtype=np.uint8)
     (magic, version, n, n_carry, n_cigar, n_exc, n_esc, n_xops, total, n_contigs, n_jt, n_dict, n_dictops, has_mapq, xop_bytes,
-     last_tid, last_pos, o_crs, o_dpos, o_ei, o_ev, o_fc, o_jt, o_qi, o_qf, o_qc, o_doff, o_dops, o_xops, o_mapq, _r1) = struct.unpack_from(
-        "<IIqqqqqqqiiiiiiiiIIIIIIIIIIIIII", raw.tobytes()[:200])
-    assert magic == 0x4256434D and version == 3 and total <= len(raw) and xop_bytes in (2, 4)
+     last_tid, last_pos, o_crs, o_dpos, o_ei, o_ev, o_fc, o_jt, o_qi, o_qf, o_qc, o_doff, o_dops, o_xops, o_mapq, nib,
+     n_dq, n_fq, o_nb, o_dq, o_fq, o_chunk) = struct.unpack_from("<IIqqqqqqqiiiiiiiiIIIIIIIIIIIIIIqqIIII", raw.tobytes()[:200])
+    assert magic == 0x4256434D and version == 4 and total <= len(raw) and xop_bytes in (2, 4) and nib in (0, 1)
     view = lambda off, cnt, dt: raw[off:off + cnt * np.dtype(dt).itemsize].view(dt)
     crs = view(o_crs, n_contigs + 1, np.int64)
-    d = view(o_dpos, n, np.uint8).astype(np.int64)
+    if nib:
+        nbv = view(o_nb, n, np.uint8)
+        d, fc = (nbv & 15).astype(np.int64), (nbv >> 4).astype(np.int64)
+        dq, fq = view(o_dq, n_dq, np.uint8), view(o_fq, n_fq, np.uint8)
+        assert int((d == 15).sum()) == n_dq and int((fc == 15).sum()) == n_fq and np.all(dq >= 15) and np.all(fq >= 15)
+        # the chunk table: where the side-list entries of every 2 048 reads begin
+        ct = view(o_chunk, 2 * ((n + 2047) // 2048), np.uint32).reshape(-1, 2)
+        assert np.array_equal(ct[:, 0], np.concatenate(([0], np.cumsum(d == 15)))[0:n:2048])
+        assert np.array_equal(ct[:, 1], np.concatenate(([0], np.cumsum(fc == 15)))[0:n:2048])
+        d[d == 15] = dq
+        fc[fc == 15] = fq
+        fc = fc.astype(np.uint8)
+    else:
+        d = view(o_dpos, n, np.uint8).astype(np.int64)
+        fc = view(o_fc, n, np.uint8)
     assert np.all(np.diff(view(o_ei, n_exc, np.uint32).astype(np.int64)) > 0)            # ascending: the device relies on it
     d[view(o_ei, n_exc, np.uint32)] = view(o_ev, n_exc, np.int32)
     S = np.cumsum(d)
@@ -122,7 +136,6 @@ def _unpack_block(buf):
             pos[a:b] = S[a:b] - (S[a - 1] if a > 0 else 0)
             tid[a:b] = c if c < n_contigs else -1
     jt = np.concatenate([view(o_jt, n_jt, np.uint32), np.zeros(256 - n_jt, np.uint32)])
-    fc = view(o_fc, n, np.uint8)
     assert np.all((fc < n_jt) | (fc == 255))
     e = jt[fc]
     flag, cc = (e >> 8).astype(np.uint16), (e & 255).astype(np.int64)
@@ -144,7 +157,7 @@ def _unpack_block(buf):
     mapq = view(o_mapq, n, np.uint8) if has_mapq else None
     return dict(n=n, n_carry=n_carry, tid=tid, pos=pos.astype(np.int64), flag=flag, ncig=ncig, mapq=mapq,
                 cig=np.concatenate(cig) if cig else np.zeros(0, np.uint32), last=(last_tid, last_pos), n_exc=n_exc, n_esc=n_esc,
-                xop_bytes=xop_bytes)
+                xop_bytes=xop_bytes, nib=nib)
 
 
 def test_block_packer_round_trip():
@@ -169,7 +182,8 @@ def test_block_packer_round_trip():
     w = synth.c2(0.01)
     b, _ = synth.generate_host(w)
     u, nb = check(b, w.n_contigs, with_mapq=False, n_carry=17)
-    assert nb / len(b.tid) < 3.0 and u["n_carry"] == 17 and u["n_exc"] == 0 and u["n_esc"] < 0.02 * len(b.tid)
+    assert nb / len(b.tid) < 1.6 and u["nib"] == 1 and u["xop_bytes"] == 2                 # C2: the nibble form, u16 explicit ops
+    assert u["n_carry"] == 17 and u["n_exc"] == 0 and u["n_esc"] < 0.02 * len(b.tid)
     check(b, w.n_contigs, with_mapq=True, threads=3)
     z, fb = load_soa("fixture_soa.npz")
     check(fb, 2, with_mapq=True)
