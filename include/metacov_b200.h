@@ -242,7 +242,11 @@ int  mcov_depth_sorted_delta(mcov_ctx* ctx, int64_t n,
  *                                listed as exceptions carry 0); high nibble: the joint-table
  *                                index 0..14, or 15 = the index (15..254, 255 = escape) is
  *                                the next entry of fq u8[]
- *   chunk    u32[2*ceil(n/2048)] where the entries of dq / fq of every 2048 reads begin
+ * and, in both forms, a CHUNK TABLE (mcov_block_chunk per 2048 reads): where the chunk's
+ * entries of dq / fq / xops and of the escape and exception lists begin, the op offset of
+ * its first read and the position of the read before it -- all the packer has at hand, and
+ * all a CTA needs to rebuild its 2048 reads without looking at any other chunk (ONE unpack
+ * kernel, no device-side prefix sums).
  * A batch with a CIGAR of more than 127 ops (long reads) does not qualify
  * (mcov_pack_block returns MCOV_ERR_RANGE): it travels as plain columns or through
  * mcov_depth_sorted_packed.  All sections start on 16-byte boundaries. */
@@ -257,7 +261,14 @@ typedef struct mcov_block_hdr {
   int64_t  n_dq, n_fq;                         /* nibble form: entries of the two side lists */
   uint32_t off_nb, off_dq, off_fq, off_chunk;
 } mcov_block_hdr;
-#define MCOV_BLOCK_CHUNK 2048                  /* reads per entry of the chunk table (and per CTA of the unpack kernels) */
+#define MCOV_BLOCK_CHUNK 2048                  /* reads per entry of the chunk table (and per CTA of the unpack kernel) */
+typedef struct mcov_block_chunk {
+  uint32_t dq_off, fq_off;                     /* nibble form: first entry of dq / fq that belongs to the chunk */
+  uint32_t op_off, xop_off;                    /* cig_off of the chunk's first read; first explicit op of the chunk */
+  int32_t  pos_carry;                          /* position of the read in front of the chunk (0 for the first chunk) */
+  uint32_t esc_first, exc_first;               /* first escape / exception at or after the chunk's first read that lies in the chunk (0xFFFFFFFF: none) */
+  uint32_t reserved;
+} mcov_block_chunk;
 /* Upper bound of the block size for a batch of n reads with n_cigar ops over n_contigs contigs. */
 int64_t mcov_block_bound(int64_t n, int64_t n_cigar, int32_t n_contigs);
 /* Pack a coordinate-sorted SoA batch (host arrays, grouped by contig with unplaced reads last; the first

@@ -355,9 +355,9 @@ int block_stage(mcov_ctx* ctx, const void* block, int64_t bytes, ExpandArgs& a, 
   {
     const uint64_t tb = (uint64_t)h.total_bytes, n1 = (uint64_t)std::max<int64_t>(n, 1);
     auto in = [&](uint32_t off, uint64_t len) { return (off & 15u) == 0 && (uint64_t)off + len <= tb; };
-    const bool per_read = h.nib ? in(h.off_nb, n1) && in(h.off_dq, (uint64_t)h.n_dq) && in(h.off_fq, (uint64_t)h.n_fq) &&
-                                  in(h.off_chunk, (uint64_t)((n + MCOV_BLOCK_CHUNK - 1) / MCOV_BLOCK_CHUNK) * 8)
-                                : in(h.off_dpos, n1) && in(h.off_fc, n1);
+    const bool per_read = (h.nib ? in(h.off_nb, n1) && in(h.off_dq, (uint64_t)h.n_dq) && in(h.off_fq, (uint64_t)h.n_fq)
+                                 : in(h.off_dpos, n1) && in(h.off_fc, n1)) &&
+                          in(h.off_chunk, (uint64_t)((n + MCOV_BLOCK_CHUNK - 1) / MCOV_BLOCK_CHUNK) * sizeof(mcov_block_chunk));
     if (!in(h.off_crs, ((uint64_t)h.n_contigs + 1) * 8) || !per_read || !in(h.off_exc_idx, (uint64_t)h.n_exc * 4) ||
         !in(h.off_exc_val, (uint64_t)h.n_exc * 4) || !in(h.off_jt, 1024) || !in(h.off_esc_idx, (uint64_t)h.n_esc * 4) ||
         !in(h.off_esc_flag, (uint64_t)h.n_esc * 2) || !in(h.off_esc_cls, (uint64_t)h.n_esc) || !in(h.off_dict_off, 129 * 4) ||
@@ -375,25 +375,15 @@ int block_stage(mcov_ctx* ctx, const void* block, int64_t bytes, ExpandArgs& a, 
   CU(st.tid.ensure((size_t)n1 * 4)); CU(st.pos.ensure((size_t)n1 * 4)); CU(st.flag.ensure((size_t)n1 * 2)); CU(st.mapq.ensure((size_t)n1));
   CU(st.cig_off.ensure((size_t)off_len * 4)); CU(st.cig.ensure((size_t)h.n_cigar * 4 + 16));
   const int64_t n_chunks = (off_len + kBlkChunk - 1) / kBlkChunk;
-  CU(ctx->d_end_slot.ensure((size_t)n_chunks * 40 + 64));               // chunk tables of the unpack kernels (free until the prep kernel)
   CU(cudaMemcpyAsync(st.raw.p, block, (size_t)h.total_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
   CU(cudaEventRecord(ctx->copied, ctx->copy_stream));
   CU(cudaStreamWaitEvent(ctx->stream, ctx->copied, 0));
   cudaStream_t s = ctx->stream;
   BlockArgs b;
-  b.blk = st.raw.as<char>(); b.h = h; b.off_len = off_len; b.n_chunks = n_chunks;
-  b.agg = ctx->d_end_slot.as<uint4>(); b.pre = b.agg + n_chunks;
-  b.esc_first = reinterpret_cast<uint32_t*>(b.pre + n_chunks); b.exc_first = b.esc_first + n_chunks;
+  b.blk = st.raw.as<char>(); b.h = h; b.off_len = off_len;
   b.tid = st.tid.as<int32_t>(); b.pos = st.pos.as<int32_t>(); b.flag = st.flag.as<uint16_t>(); b.mapq = st.mapq.as<uint8_t>();
   b.cig_off = st.cig_off.as<uint32_t>(); b.cig = st.cig.as<uint32_t>();
-  ctx->prof_begin(kKBlockUnpack);
-  cudaMemsetAsync(b.esc_first, 0xff, (size_t)n_chunks * 8, s);
-  if (h.n_esc + h.n_exc) k_block_index<<<(unsigned)((h.n_esc + h.n_exc + 255) / 256), 256, 0, s>>>(b);
-  k_block_reduce<<<(unsigned)n_chunks, kBlkThreads, 0, s>>>(b);
-  k_block_prefix<<<1, kBlkPrefixThreads, 0, s>>>(b);
-  k_block_expand<<<(unsigned)n_chunks, kBlkThreads, 0, s>>>(b);
-  ctx->prof_end();
-  ctx->n_launches += 3;                                                 // (prof_begin counted one)
+  MCOV_LAUNCH(ctx, kKBlockUnpack, (k_block_expand<<<(unsigned)n_chunks, kBlkThreads, 0, s>>>(b)));
   CU(cudaGetLastError());
   std::memset(&a, 0, sizeof(a));
   a.n = n; a.n_cig = h.n_cigar;
@@ -413,6 +403,7 @@ int configure_kernels(mcov_ctx* ctx) {
   CU(cudaFuncSetAttribute(k_fused_prep_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kPtSmemBytes));
   CU(cudaFuncSetAttribute(k_stats_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, kSsSmemBytes));
   CU(cudaFuncSetAttribute(k_fused_prep_tma, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  CU(cudaFuncSetAttribute(k_block_expand, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
   CU(cudaFuncSetAttribute(k_fused_prep<false>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
   CU(cudaFuncSetAttribute(k_scan_inplace<false>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
   CU(cudaFuncSetAttribute(k_far_scatter, cudaFuncAttributePreferredSharedMemoryCarveout, mx));

@@ -45,7 +45,7 @@ int64_t mcov_block_bound(int64_t n, int64_t n_cigar, int32_t n_contigs) {
   const size_t n1 = (size_t)std::max<int64_t>(n, 1);
   return (int64_t)(al16(sizeof(mcov_block_hdr)) + al16(((size_t)n_contigs + 1) * 8) + al16(n1) /*dpos*/ + 2 * al16(n1 * 4) /*exceptions*/ +
                    al16(n1) /*fc*/ + al16(1024) /*jt*/ + al16(n1 * 4) + al16(n1 * 2) + al16(n1) /*escapes*/ + al16(129 * 4) +
-                   al16(128 * 4 * 4) + al16((size_t)n_cigar * 4 + 16) + al16(n1) /*mapq*/ + 256);
+                   al16(128 * 4 * 4) + al16((size_t)n_cigar * 4 + 16) + al16(n1) /*mapq*/ + al16((n1 / MCOV_BLOCK_CHUNK + 2) * sizeof(mcov_block_chunk)) + 320);
 }
 
 int mcov_pack_block(int64_t n, int64_t n_carry, const int32_t* tid, const int32_t* pos, const uint16_t* flag,
@@ -229,33 +229,35 @@ int mcov_pack_block(int64_t n, int64_t n_carry, const int32_t* tid, const int32_
       }
     });
     o += al16((size_t)h.n_xops * (size_t)h.xop_bytes + 16);
-    // ---- the two per-read bytes: wide (dpos[], fc[]) or as nibbles + side lists, whichever is smaller ----
-    {
-      const int64_t n_chunks = (n + MCOV_BLOCK_CHUNK - 1) / MCOV_BLOCK_CHUNK;
-      std::vector<uint32_t> cd((size_t)n_chunks + 1, 0), cf((size_t)n_chunks + 1, 0);
-      // (threads split the READS; a thread takes the chunks that begin in its range)
-      auto chunks_of = [](int64_t a) { return (a + MCOV_BLOCK_CHUNK - 1) / MCOV_BLOCK_CHUNK; };
-      par_for(n, n_threads, [&](int, int64_t ra, int64_t rb) {
-        for (int64_t c = chunks_of(ra); c < chunks_of(rb); ++c) {
-          uint32_t kd = 0, kf = 0;
-          const int64_t e = std::min<int64_t>(n, (c + 1) * MCOV_BLOCK_CHUNK);
-          for (int64_t i = c * MCOV_BLOCK_CHUNK; i < e; ++i) { kd += dpos[i] >= 15; kf += fc[i] >= 15; }
-          cd[(size_t)c + 1] = kd; cf[(size_t)c + 1] = kf;
+    // ---- the two per-read bytes: wide (dpos[], fc[]) or as nibbles + side lists, whichever is smaller; per chunk of
+    //      MCOV_BLOCK_CHUNK reads, where its entries of the side lists and of the explicit ops begin ----
+    const int64_t n_chunks = (n + MCOV_BLOCK_CHUNK - 1) / MCOV_BLOCK_CHUNK;
+    std::vector<uint32_t> cd((size_t)n_chunks + 1, 0), cf((size_t)n_chunks + 1, 0), cx((size_t)n_chunks + 1, 0);
+    // (threads split the READS; a thread takes the chunks that begin in its range)
+    auto chunks_of = [](int64_t a) { return (a + MCOV_BLOCK_CHUNK - 1) / MCOV_BLOCK_CHUNK; };
+    par_for(n, n_threads, [&](int, int64_t ra, int64_t rb) {
+      for (int64_t c = chunks_of(ra); c < chunks_of(rb); ++c) {
+        uint32_t kd = 0, kf = 0, kx = 0;
+        const int64_t e = std::min<int64_t>(n, (c + 1) * MCOV_BLOCK_CHUNK);
+        for (int64_t i = c * MCOV_BLOCK_CHUNK; i < e; ++i) {
+          kd += dpos[i] >= 15; kf += fc[i] >= 15;
+          if (cls[(size_t)i] >= 128) kx += cls[(size_t)i] - 128u;
         }
-      });
-      for (int64_t c = 0; c < n_chunks; ++c) { cd[(size_t)c + 1] += cd[(size_t)c]; cf[(size_t)c + 1] += cf[(size_t)c]; }
+        cd[(size_t)c + 1] = kd; cf[(size_t)c + 1] = kf; cx[(size_t)c + 1] = kx;
+      }
+    });
+    for (int64_t c = 0; c < n_chunks; ++c) { cd[(size_t)c + 1] += cd[(size_t)c]; cf[(size_t)c + 1] += cf[(size_t)c]; cx[(size_t)c + 1] += cx[(size_t)c]; }
+    {
       const size_t n_dq = cd[(size_t)n_chunks], n_fq = cf[(size_t)n_chunks];
-      const size_t nib_bytes = al16(n1) + al16(n_dq + 16) + al16(n_fq + 16) + al16((size_t)n_chunks * 8 + 16);
+      const size_t nib_bytes = al16(n1) + al16(n_dq + 16) + al16(n_fq + 16);
       if (nib_bytes < 2 * al16(n1)) {
         h.nib = 1; h.n_dq = (int64_t)n_dq; h.n_fq = (int64_t)n_fq;
         h.off_nb = (uint32_t)o; uint8_t* nb = reinterpret_cast<uint8_t*>(base + o); o += al16(n1);
         h.off_dq = (uint32_t)o; uint8_t* dq = reinterpret_cast<uint8_t*>(base + o); o += al16(n_dq + 16);
         h.off_fq = (uint32_t)o; uint8_t* fq = reinterpret_cast<uint8_t*>(base + o); o += al16(n_fq + 16);
-        h.off_chunk = (uint32_t)o; uint32_t* ct = reinterpret_cast<uint32_t*>(base + o); o += al16((size_t)n_chunks * 8 + 16);
         par_for(n, n_threads, [&](int, int64_t ra, int64_t rb) {
           for (int64_t c = chunks_of(ra); c < chunks_of(rb); ++c) {
             uint32_t wd = cd[(size_t)c], wf = cf[(size_t)c];
-            ct[2 * c] = wd; ct[2 * c + 1] = wf;
             const int64_t e = std::min<int64_t>(n, (c + 1) * MCOV_BLOCK_CHUNK);
             for (int64_t i = c * MCOV_BLOCK_CHUNK; i < e; ++i) {
               uint8_t lo = dpos[i], hi = fc[i];
@@ -296,6 +298,21 @@ int mcov_pack_block(int64_t n, int64_t n_carry, const int32_t* tid, const int32_
     int32_t* ev = reinterpret_cast<int32_t*>(base + o);
     o += al16(std::max<size_t>(n_exc, 1) * 4);
     { size_t k = 0; for (auto& v : exc) for (auto& e : v) { ei[k] = e.first; ev[k] = e.second; ++k; } }
+    // ---- chunk table: everything a CTA of the unpack kernel needs to start at its chunk without looking at the others ----
+    h.off_chunk = (uint32_t)o;
+    {
+      mcov_block_chunk* ct = reinterpret_cast<mcov_block_chunk*>(base + o);
+      o += al16((size_t)std::max<int64_t>(n_chunks, 1) * sizeof(mcov_block_chunk));
+      for (int64_t c = 0; c < n_chunks; ++c) {
+        const int64_t c0 = c * MCOV_BLOCK_CHUNK;
+        mcov_block_chunk& e = ct[c];
+        e.dq_off = cd[(size_t)c]; e.fq_off = cf[(size_t)c]; e.op_off = cig_off[c0]; e.xop_off = cx[(size_t)c];
+        e.pos_carry = c0 > 0 ? pos[c0 - 1] : 0;
+        e.esc_first = 0xFFFFFFFFu; e.exc_first = 0xFFFFFFFFu; e.reserved = 0;
+      }
+      for (size_t k = 0; k < n_esc; ++k) if (k == 0 || qi[k - 1] / MCOV_BLOCK_CHUNK != qi[k] / MCOV_BLOCK_CHUNK) ct[qi[k] / MCOV_BLOCK_CHUNK].esc_first = (uint32_t)k;
+      for (size_t k = 0; k < n_exc; ++k) if (k == 0 || ei[k - 1] / MCOV_BLOCK_CHUNK != ei[k] / MCOV_BLOCK_CHUNK) ct[ei[k] / MCOV_BLOCK_CHUNK].exc_first = (uint32_t)k;
+    }
     // ---- mapq ----
     h.off_mapq = 0;
     if (mapq) { h.off_mapq = (uint32_t)o; if (n > 0) std::memcpy(base + o, mapq, (size_t)n); o += al16(n1); }

@@ -116,10 +116,6 @@ def _unpack_block(buf):
         d, fc = (nbv & 15).astype(np.int64), (nbv >> 4).astype(np.int64)
         dq, fq = view(o_dq, n_dq, np.uint8), view(o_fq, n_fq, np.uint8)
         assert int((d == 15).sum()) == n_dq and int((fc == 15).sum()) == n_fq and np.all(dq >= 15) and np.all(fq >= 15)
-        # the chunk table: where the side-list entries of every 2 048 reads begin
-        ct = view(o_chunk, 2 * ((n + 2047) // 2048), np.uint32).reshape(-1, 2)
-        assert np.array_equal(ct[:, 0], np.concatenate(([0], np.cumsum(d == 15)))[0:n:2048])
-        assert np.array_equal(ct[:, 1], np.concatenate(([0], np.cumsum(fc == 15)))[0:n:2048])
         d[d == 15] = dq
         fc[fc == 15] = fq
         fc = fc.astype(np.uint8)
@@ -155,6 +151,21 @@ def _unpack_block(buf):
         ncig[i] = len(cig[-1])
     assert x == n_xops and int(ncig.sum()) == n_cigar
     mapq = view(o_mapq, n, np.uint8) if has_mapq else None
+    # the chunk table (one row of eight u32 per 2 048 reads): where the chunk's entries of the side lists, the explicit ops, the
+    # escapes and the exceptions begin; op offset of its first read; position of the read in front of it
+    ct = view(o_chunk, 8 * ((n + 2047) // 2048), np.uint32).reshape(-1, 8)
+    starts = np.arange(0, n, 2048)
+    if nib:
+        assert np.array_equal(ct[:, 0], np.concatenate(([0], np.cumsum(nbv & 15 == 15)))[starts])
+        assert np.array_equal(ct[:, 1], np.concatenate(([0], np.cumsum(nbv >> 4 == 15)))[starts])
+    assert np.array_equal(ct[:, 2], np.concatenate(([0], np.cumsum(ncig)))[starts])
+    assert np.array_equal(ct[:, 3], np.concatenate(([0], np.cumsum(np.where(cc >= 128, cc - 128, 0))))[starts])
+    assert np.array_equal(ct[1:, 4].view(np.int32), pos[starts[1:] - 1].astype(np.int32)) and (len(ct) == 0 or ct[0, 4] == 0)
+    for col, lst in ((5, qi), (6, view(o_ei, n_exc, np.uint32))):
+        first = np.full(len(ct), 0xFFFFFFFF, np.uint32)
+        for k in range(len(lst) - 1, -1, -1):
+            first[lst[k] // 2048] = k
+        assert np.array_equal(ct[:, col], first)
     return dict(n=n, n_carry=n_carry, tid=tid, pos=pos.astype(np.int64), flag=flag, ncig=ncig, mapq=mapq,
                 cig=np.concatenate(cig) if cig else np.zeros(0, np.uint32), last=(last_tid, last_pos), n_exc=n_exc, n_esc=n_esc,
                 xop_bytes=xop_bytes, nib=nib)
