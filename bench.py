@@ -482,8 +482,9 @@ def run_ours(args):
         try:
             blk = pack_block(hbatch, g, with_mapq=False, pinned=True)
             pack_ms = 1e3 * (time.perf_counter() - t_pack)
-            transport = ("transport block of the product decoder (mcov_pack_block: contig prefix, u8 position differences + "
-                         "exceptions, flag dictionary, CIGAR dictionary + explicit ops, no mapq): ONE pinned buffer, ONE H2D copy")
+            transport = ("transport block of the product decoder (mcov_pack_block v4: contig prefix, one byte per read = position "
+                         "difference | (flag, CIGAR class) index as nibbles with u8 side lists, exceptions / escapes, CIGAR dictionary + "
+                         "u16 explicit ops, chunk table, no mapq): ONE pinned buffer, ONE H2D copy, ONE unpack kernel")
             depth_packed = lambda wait=False: eng.depth_sorted_block(blk, wait=wait)
             h2d_bytes = int(blk[1])
         except ValueError:
@@ -533,7 +534,24 @@ def run_ours(args):
 
         soa_step()
         dt_soa = timed(soa_step, args.e2e_steps)
-        e2e = {"value": aligned_total / dt, "unit": UNIT,
+        # the block's copy alone (same pinned buffer, same size): what the link allows per step
+        h2d_only_ms = None
+        try:
+            src = blk[0][:h2d_bytes]
+            dst = torch.empty(h2d_bytes, dtype=torch.uint8, device=dev)
+            for _ in range(3):
+                dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(20):
+                dst.copy_(src, non_blocking=True)
+            c1.record(); torch.cuda.synchronize()
+            h2d_only_ms = c0.elapsed_time(c1) / 20
+            del dst
+        except Exception:
+            pass
+        e2e = {"value": aligned_total / dt, "unit": UNIT, "h2d_only_ms": h2d_only_ms,
                "h2d_bytes_per_step": h2d_bytes + g * 16, "d2h_bytes_per_step": g * 64 + 64,
                "ms_per_step": 1e3 * dt, "unpipelined_ms_per_step": 1e3 * dt_sync,
                "bytes_scope": "per rank (every rank copies its own shard; multiply by n_gpus for the whole job)" if world > 1 else "whole job",
@@ -752,7 +770,7 @@ def _main(real_stdout):
                     help="depth formulation of the device-resident step: fused sorted path (default, what sorted BAM input takes) "
                          "or the any-order push path (clear + atomics + decoupled look-back scan)")
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the named workload per GPU")
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the e2e legs (0: as many as --steps, at least 5)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-bam", action="store_true", help="skip the from-the-BAM-file leg of e2e")
     ap.add_argument("--bam-reads", type=int, default=2_000_000, help="reads written to the synthetic BAM of the from-file leg")
@@ -763,6 +781,8 @@ def _main(real_stdout):
     ap.add_argument("--breakdown", action="store_true", help="print a host-side time breakdown of one step to stderr")
     args = ap.parse_args()
     args.real_stdout = real_stdout
+    if args.e2e_steps <= 0:
+        args.e2e_steps = max(5, args.steps)
     if args.impl == "reference":
         run_reference(args)
     else:
