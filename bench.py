@@ -475,7 +475,12 @@ def run_ours(args):
     # way from the compressed file.
     e2e = None
     hbatch = None
-    if not args.no_e2e:
+    # a batch of 2^32 or more CIGAR ops (config C5 at full size: 56 GB of ops) has no host-side leg here: it would have to sit
+    # in pinned host memory as plain 64-bit-offset columns
+    wide_ops = dbatch.cig_off.dtype == torch.int64 and int(dbatch.cig_off[-1].item()) > 0xFFFFFFFF
+    if wide_ops and not args.no_e2e:
+        e2e = {"skipped": "the batch holds 2^32 or more CIGAR ops (64-bit offsets): no narrow host transport; device-resident leg only"}
+    if not args.no_e2e and not wide_ops:
         from metacov_b200.engine import pack_batch, pack_block, packed_bytes
         hbatch = ReadBatch(*[t.cpu() for t in dbatch])
         t_pack = time.perf_counter()

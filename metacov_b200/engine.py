@@ -451,6 +451,19 @@ class CoverageEngine:
                 n_bins *= 2
 
 
+def _offsets_u32(cig_off, who):
+    """cig_off as uint32 -- refusing, instead of truncating, 64-bit offsets that do not fit (a batch of 2^32 or more
+    ops travels through the *_wide entry points as plain columns)."""
+    a = cig_off.cpu().numpy() if _is_torch(cig_off) else np.asarray(cig_off)
+    a = np.ascontiguousarray(a)
+    if a.dtype.itemsize == 4:
+        return a.view(np.uint32)
+    if len(a) and (int(a.max()) > 0xFFFFFFFF or int(a.min()) < 0):
+        raise ValueError("%s: the batch holds 2^32 or more CIGAR ops (64-bit offsets): it does not qualify for the narrow "
+                         "transports; use depth_sorted / push with the wide offsets" % who)
+    return a.astype(np.uint32)
+
+
 def pack_batch(batch, n_contigs, with_mapq=False, pinned=False):
     """Compact host transport of a coordinate-sorted ``ReadBatch`` (numpy or CPU torch members):
     per-contig read prefix instead of ``tid``, u16 op counts instead of u32 offsets, ``mapq`` only
@@ -467,7 +480,7 @@ def pack_batch(batch, n_contigs, with_mapq=False, pinned=False):
         raise ValueError("pack_batch: reads are not grouped by contig (unplaced reads must come last)")
     crs = np.zeros(n_contigs + 1, dtype=np.int64)
     np.cumsum(np.bincount(placed, minlength=n_contigs), out=crs[1:])
-    off = as_np(batch.cig_off, np.uint32).astype(np.int64)
+    off = _offsets_u32(batch.cig_off, "pack_batch").astype(np.int64)
     ncig = np.diff(off)
     if len(ncig) and ncig.max() > 65535:
         raise ValueError("pack_batch: a CIGAR has more than 65535 ops")
@@ -530,7 +543,7 @@ def pack_block(batch, n_contigs, with_mapq=False, n_carry=0, pinned=False, threa
         return a.view(dt) if a.dtype.itemsize == np.dtype(dt).itemsize else a.astype(dt)
     tid, pos = as_np(batch.tid, np.int32), as_np(batch.pos, np.int32)
     flag, mapq = as_np(batch.flag, np.uint16), as_np(batch.mapq, np.uint8)
-    off, cig = as_np(batch.cig_off, np.uint32), as_np(batch.cig, np.uint32)
+    off, cig = _offsets_u32(batch.cig_off, "pack_block"), as_np(batch.cig, np.uint32)
     n = len(tid)
     cap = lib.mcov_block_bound(n, int(off[-1]) if n else 0, int(n_contigs))
     if pinned:

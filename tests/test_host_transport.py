@@ -225,3 +225,18 @@ def test_block_packer_round_trip():
         pack_block(b5, w5.n_contigs)
     with pytest.raises(ValueError):
         pack_block(ReadBatch(b.tid[::-1].copy(), b.pos, b.flag, b.mapq, b.cig_off, b.cig), w.n_contigs)   # not grouped by contig
+
+
+def test_narrow_packers_refuse_64bit_offsets():
+    """pack_block / pack_batch / pack_batch_delta take 64-bit offset arrays only when they fit 32 bits: a batch of 2^32 or
+    more ops (config C5 at full size) is refused instead of truncated (it travels through the *_wide entry points)."""
+    from metacov_b200 import ReadBatch
+    from metacov_b200.engine import pack_batch, pack_batch_delta, pack_block
+    n = 4
+    cols = (np.zeros(n, np.int32), np.arange(n, dtype=np.int32), np.zeros(n, np.uint16), np.zeros(n, np.uint8))
+    big = ReadBatch(*cols, np.array([0, 1, 2, 3, 1 << 33], np.int64), np.full(4, 100 << 4, np.uint32))
+    for f in (pack_block, pack_batch, pack_batch_delta):
+        with pytest.raises(ValueError):
+            f(big, 1)
+    ok = ReadBatch(*cols, np.array([0, 1, 2, 3, 4], np.int64), np.full(4, 100 << 4, np.uint32))
+    assert pack_batch(ok, 1)["n_cig_total"] == 4 and pack_block(ok, 1)[1] > 0 and pack_batch_delta(ok, 1)["n_cig_total"] == 4
