@@ -29,6 +29,7 @@ constexpr int kBlkPer = 8;
 constexpr int kBlkChunk = kBlkThreads * kBlkPer;          // 2 048 reads per CTA
 static_assert(kBlkChunk == MCOV_BLOCK_CHUNK, "the block's chunk table is per CTA of the unpack kernel");
 constexpr uint32_t kBlkNone = 0xFFFFFFFFu;
+constexpr uint32_t kBlkEscape = 0xFFFFFFFFu;              // joint-table entry of an index beyond the table (no flag << 8 | class looks like it)
 constexpr int kBlkOpCap = 2 * kBlkChunk;                  // ops of a chunk staged in shared memory (more: direct stores)
 constexpr int kBlkXopCap = kBlkChunk;                     // explicit ops of a chunk staged in shared memory
 
@@ -67,7 +68,9 @@ struct BlkShared {
   unsigned long long w64[kBlkThreads / 32];
   int32_t w_s[kBlkThreads / 32], w_f[kBlkThreads / 32], w_m[kBlkThreads / 32];
   uint32_t w_n[kBlkThreads / 32];
-  int32_t c_lo;
+  int32_t c_lo, starts;
+  uint32_t list_n;
+  uint32_t list[kBlkChunk];   // reads of more than one op: {image offset, ops, source}
 };
 static_assert(offsetof(BlkShared, d) == offsetof(BlkShared, e) + sizeof(uint32_t) * kBlkChunk, "e[] and d[] form one array");
 
@@ -97,8 +100,16 @@ __device__ __forceinline__ void blk_load(const BlockArgs& a, BlkShared& sm, int6
       }
     }
     uint32_t cnt = 0;
+    if (i0 + kBlkPer <= n) {
+      // bit 0 of every nibble of y: the nibble is 15
+      const uint2 q = *reinterpret_cast<const uint2*>(nb + i0);
+      uint32_t y0 = q.x & (q.x >> 1), y1 = q.y & (q.y >> 1);
+      y0 &= y0 >> 2; y1 &= y1 >> 2;
+      cnt = (uint32_t)(__popc(y0 & 0x01010101u) + __popc(y1 & 0x01010101u)) + ((uint32_t)(__popc(y0 & 0x10101010u) + __popc(y1 & 0x10101010u)) << 16);
+    } else {
 #pragma unroll
-    for (int j = 0; j < kBlkPer; ++j) cnt += (lo[j] == 15u ? 1u : 0u) + (hi[j] == 15u ? 0x10000u : 0u);
+      for (int j = 0; j < kBlkPer; ++j) cnt += (lo[j] == 15u ? 1u : 0u) + (hi[j] == 15u ? 0x10000u : 0u);
+    }
     uint32_t inc = cnt;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -139,8 +150,36 @@ __device__ __forceinline__ void blk_load(const BlockArgs& a, BlkShared& sm, int6
     }
   }
   const uint32_t kf = ce.esc_first, xf = ce.exc_first;                        // (uniform over the CTA)
-  if (kf == kBlkNone && xf == kBlkNone) return;
   const int64_t c1 = c0 + kBlkChunk;
+  if (xf == kBlkNone) {
+    if (kf == kBlkNone) {
+#pragma unroll
+      for (int j = 0; j < kBlkPer; ++j) if (e[j] == kBlkEscape) e[j] = 128u;   // (an escape the list does not hold: a malformed block)
+      return;
+    }
+    // no exception in the chunk (the common case): the few escapes are dropped at their reads' places in shared memory
+    // and only the reads whose table index said "escape" look there
+    {
+      const uint32_t* qi = reinterpret_cast<const uint32_t*>(a.blk + h.off_esc_idx);
+      const uint16_t* qf = reinterpret_cast<const uint16_t*>(a.blk + h.off_esc_flag);
+      const uint8_t* qc = reinterpret_cast<const uint8_t*>(a.blk + h.off_esc_cls);
+      for (int64_t k = (int64_t)kf + threadIdx.x; k < h.n_esc; k += kBlkThreads) {
+        const int64_t i = qi[k];
+        if (i >= c1 || i >= n) break;                                         // (ascending: the rest belongs to later chunks)
+        if (i >= c0) sm.e[i - c0] = ((uint32_t)qf[k] << 8) | qc[k];
+      }
+    }
+    __syncthreads();
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < kBlkPer; ++j) any |= e[j] == kBlkEscape;
+    if (any) {
+#pragma unroll
+      for (int j = 0; j < kBlkPer; ++j) if (e[j] == kBlkEscape) e[j] = sm.e[threadIdx.x * kBlkPer + j] & 0xFFFFFFu;
+    }
+    __syncthreads();                                                          // (sm.e is reused for the contig marks)
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < kBlkPer; ++j) { sm.e[threadIdx.x * kBlkPer + j] = e[j]; sm.d[threadIdx.x * kBlkPer + j] = d[j]; }
   __syncthreads();
@@ -165,7 +204,10 @@ __device__ __forceinline__ void blk_load(const BlockArgs& a, BlkShared& sm, int6
   }
   __syncthreads();
 #pragma unroll
-  for (int j = 0; j < kBlkPer; ++j) { e[j] = sm.e[threadIdx.x * kBlkPer + j]; d[j] = sm.d[threadIdx.x * kBlkPer + j]; }
+  for (int j = 0; j < kBlkPer; ++j) {
+    e[j] = sm.e[threadIdx.x * kBlkPer + j]; d[j] = sm.d[threadIdx.x * kBlkPer + j];
+    if (e[j] == kBlkEscape) e[j] = 128u;                                      // (an escape the list does not hold: a malformed block)
+  }
   __syncthreads();                                                            // (sm.e is reused for the contig marks)
 }
 
@@ -190,14 +232,17 @@ __global__ void __launch_bounds__(kBlkThreads, 4) k_block_expand(const __grid_co
     const uint32_t* jt = reinterpret_cast<const uint32_t*>(a.blk + h.off_jt);
     const uint32_t* dict_off = reinterpret_cast<const uint32_t*>(a.blk + h.off_dict_off);
     const uint32_t* dict_ops = reinterpret_cast<const uint32_t*>(a.blk + h.off_dict_ops);
-    for (int k = t; k < 256; k += kBlkThreads) sm.jt[k] = k < h.n_jt ? jt[k] : ((0x4u << 8) | 128u);   // (255: an escape, patched in blk_load)
+    for (int k = t; k < 256; k += kBlkThreads) sm.jt[k] = k < h.n_jt ? jt[k] : kBlkEscape;            // (255: an escape, patched in blk_load)
     for (int k = t; k < 128; k += kBlkThreads) sm.dn[k] = k < h.n_dict ? min(dict_off[k + 1] - dict_off[k], 4u) : 0u;
     for (int k = t; k < 129; k += kBlkThreads) sm.dict_off[k] = k <= h.n_dict ? min(dict_off[k], 508u) : 0u;
     for (int k = t; k < 512; k += kBlkThreads) sm.dict_ops[k] = k < h.n_dictops ? dict_ops[k] : 0u;
   }
   if (t < 32) {                                           // contig of the chunk's first read
     const int32_t c = blk_warp_search(crs, h.n_contigs, c0);
-    if (t == 0) sm.c_lo = c;
+    if (t == 0) {
+      sm.c_lo = c;
+      sm.starts = (crs[c] == c0 || (c < h.n_contigs && crs[c + 1] < c1)) ? 1 : 0;    // does a contig start inside the chunk?
+    }
   }
   __syncthreads();
   uint32_t e[kBlkPer];
@@ -205,22 +250,25 @@ __global__ void __launch_bounds__(kBlkThreads, 4) k_block_expand(const __grid_co
   blk_load(a, sm, chunk, ce, e, d);
   // contig starts inside the chunk: mark = contig index + 1 at the start's place (empty contigs share a start: the last wins)
   const int32_t c_lo = sm.c_lo;
+  const bool starts = sm.starts != 0;                     // (uniform: most chunks of deep data lie inside one contig)
+  if (starts) {
 #pragma unroll
-  for (int j = 0; j < kBlkPer; ++j) sm.e[t * kBlkPer + j] = 0u;
-  __syncthreads();
-  if (t == 0 && crs[c_lo] == c0) sm.e[0] = (uint32_t)c_lo + 1u;
-  for (int64_t base = (int64_t)c_lo + 1;; base += kBlkThreads) {
-    const int64_t c = base + t;
-    const bool v = c <= h.n_contigs && crs[min(c, (int64_t)h.n_contigs)] < c1;
-    if (v) atomicMax(&sm.e[crs[c] - c0], (uint32_t)c + 1u);
-    if (!__syncthreads_and(v ? 1 : 0)) break;
+    for (int j = 0; j < kBlkPer; ++j) sm.e[t * kBlkPer + j] = 0u;
+    __syncthreads();
+    if (t == 0 && crs[c_lo] == c0) sm.e[0] = (uint32_t)c_lo + 1u;
+    for (int64_t base = (int64_t)c_lo + 1;; base += kBlkThreads) {
+      const int64_t c = base + t;
+      const bool v = c <= h.n_contigs && crs[min(c, (int64_t)h.n_contigs)] < c1;
+      if (v) atomicMax(&sm.e[crs[c] - c0], (uint32_t)c + 1u);
+      if (!__syncthreads_and(v ? 1 : 0)) break;
+    }
   }
   // thread-local walks: contig (running maximum of the marks), segmented position sum, op counts
   uint32_t mk[kBlkPer], ps[kBlkPer], cn[kBlkPer];
   uint32_t m = 0, s = 0, f = 0, nc = 0, nx = 0;
 #pragma unroll
   for (int j = 0; j < kBlkPer; ++j) {
-    const uint32_t q = sm.e[t * kBlkPer + j];
+    const uint32_t q = starts ? sm.e[t * kBlkPer + j] : 0u;
     if (q) { m = q; s = (uint32_t)d[j]; f |= 1u << j; } else s += (uint32_t)d[j];
     if (f) f |= 1u << j;
     mk[j] = m; ps[j] = s;
@@ -313,16 +361,32 @@ __global__ void __launch_bounds__(kBlkThreads, 4) k_block_expand(const __grid_co
     // every read's ops -- dictionary entry or its slice of the chunk's explicit ops, both in shared memory -- gathered into the
     // image of the chunk's op range, then the image stored coalesced
     uint32_t* img = sm.e;                                                     // e[] and d[]: kBlkOpCap words
+    if (t == 0) sm.list_n = 0;
     __syncthreads();                                                          // (xo[] loaded)
+    // the first op of every read here; the reads with more ops (one in ten on short-read data) go to a list that the CTA
+    // then works through together -- a loop `for k < c` per read makes every warp wait for its longest CIGAR eight times
+    // (o0 + c <= n_ops <= kBlkOpCap and o_x + c <= n_xo <= kBlkXopCap hold by construction: all four are sums of the same cn[])
 #pragma unroll
     for (int j = 0; j < kBlkPer; ++j) {
-      const uint32_t cls = e[j] & 255u;
-      // (o0 + c <= n_ops <= kBlkOpCap and o_x + c <= n_xo <= kBlkXopCap hold by construction: all four are sums of the same cn[])
-      const uint32_t* src = cls < 128u ? sm.dict_ops + sm.dict_off[cls] : sm.xo + o_x;
-      const uint32_t c = cn[j], o0 = v_off[j];
-      if (c > 0) img[o0] = src[0];
+      const uint32_t cls = e[j] & 255u, c = cn[j], o0 = v_off[j];
+      const bool dict = cls < 128u;
+      const uint32_t si = dict ? sm.dict_off[cls] : o_x;
+      if (c > 0) img[o0] = dict ? sm.dict_ops[si] : sm.xo[si];
+      const uint32_t more = __ballot_sync(0xffffffffu, c > 1);
+      if (more) {
+        uint32_t base = 0;
+        const int leader = __ffs(more) - 1;
+        if (lane == leader) base = atomicAdd(&sm.list_n, (uint32_t)__popc(more));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (c > 1) sm.list[base + __popc(more & ((1u << lane) - 1u))] = o0 | (c << 12) | (dict ? 0u : 1u << 19) | (si << 20);
+      }
+      if (!dict) o_x += c;
+    }
+    __syncthreads();
+    for (uint32_t q = t; q < sm.list_n; q += kBlkThreads) {
+      const uint32_t en = sm.list[q], o0 = en & 4095u, c = (en >> 12) & 127u, si = en >> 20;
+      const uint32_t* src = (en >> 19) & 1u ? sm.xo + si : sm.dict_ops + si;
       for (uint32_t k = 1; k < c; ++k) img[o0 + k] = src[k];
-      if (cls >= 128u) o_x += c;
     }
     __syncthreads();
     for (uint32_t q = t; q < n_ops; q += kBlkThreads) if (ce.op_off + q < n_cig) a.cig[ce.op_off + q] = img[q];
