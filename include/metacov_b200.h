@@ -442,6 +442,13 @@ int  mcov_kmer_hist(mcov_ctx* ctx, int64_t n, const uint16_t* flag, const int32_
                     const uint8_t* seq_win, int32_t win_bytes, int32_t win_bases,
                     int32_t K, int32_t NK, int32_t STEP, int32_t OFFSET,
                     int32_t n_group_flags, const uint16_t* group_flags, uint32_t* hist_out);
+/* The same with flag / l_seq / seq_win in host or DEVICE memory (mem_kind): a file decoded on the GPU
+ * (mcov_bam_decode_gpu + mcov_bam_gpu_names_seq into device buffers) is scanned without its columns or its
+ * SEQ windows ever crossing the bus -- the `scan` loop of scan.pyx:653-667 with nothing on the host. */
+int  mcov_kmer_hist_mem(mcov_ctx* ctx, int64_t n, const uint16_t* flag, const int32_t* l_seq,
+                        const uint8_t* seq_win, int mem_kind, int32_t win_bytes, int32_t win_bases,
+                        int32_t K, int32_t NK, int32_t STEP, int32_t OFFSET,
+                        int32_t n_group_flags, const uint16_t* group_flags, uint32_t* hist_out);
 
 /* ---- the second coverage definition: pileup.experimental ------------------ */
 

@@ -159,6 +159,7 @@ SIGNATURES = {
     "mcov_profile_read": (C.c_int, [_vp, C.POINTER(KernelTime), C.c_int]),
     "mcov_isize_hist": (C.c_int, [_vp, _i64, _vp, _vp, C.c_int, _i32, _vp, _i32, _vp, _vp, _vp]),
     "mcov_kmer_hist": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "mcov_kmer_hist_mem": (C.c_int, [_vp, _i64, _vp, _vp, _vp, C.c_int, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "mcov_bam_load_seq": (C.c_int, [_vp]),
     "mcov_bam_seq_windows": (C.c_int, [_vp, _i32, _vp]),
     "mcov_bam_name_hash": (_vp, [_vp]),

@@ -15,6 +15,21 @@ from . import _capi
 from ._capi import lib
 
 
+class DevView:
+    """A device pointer with a length: quacks like a CUDA tensor for the engine's pointer-taking calls."""
+    is_cuda = True
+
+    def __init__(self, ptr, n):
+        self._ptr, self._n = int(ptr or 0), int(n)
+        self.shape = (self._n,)
+
+    def data_ptr(self):
+        return self._ptr
+
+    def __len__(self):
+        return self._n
+
+
 class DeviceSoA:
     """Device pointers of a decoded BAM (``mcov_bam_dev``); valid until the next decode on the same engine."""
 
@@ -30,11 +45,26 @@ class DeviceSoA:
     def _len(self, name):
         return self.n_cigar if name == "cig" else (self.n_records + 1 if name == "cig_off" else self.n_records)
 
+    def device_view(self, name, n=None):
+        """One column as a device-resident view (``DevView``: pointer + length, what the engine's calls take for
+        device memory) -- valid until the next decode on the same engine."""
+        return DevView(getattr(self.raw, name), self._len(name) if n is None else int(n))
+
     def to_host(self, name):
         """One column copied to a numpy array (tests, accessors)."""
         dt = dict(self.COLS)[name]
         out = np.empty(self._len(name), dtype=dt)
         self._engine._check(lib.mcov_copy_to_host(self._engine._ctx, getattr(self.raw, name), _capi.ptr(out), out.nbytes))
+        return out
+
+    def seq_windows_device(self, win_bases):
+        """The k-mer histogram's view of SEQ left ON THE DEVICE: a torch uint8 tensor [n, (win_bases+1)//2]."""
+        import torch
+        n = self.n_records
+        out = torch.empty((n, (win_bases + 1) // 2), dtype=torch.uint8, device="cuda:%d" % self._engine.device)
+        if n:
+            self._engine._check(lib.mcov_bam_gpu_names_seq(self._engine._ctx, 0, int(win_bases), None, None, out.data_ptr(),
+                                                           _capi.MEM_DEVICE))
         return out
 
     def names_seq(self, name_hash=False, k_len=0, win_bases=0):

@@ -1697,7 +1697,15 @@ int mcov_isize_hist(mcov_ctx* ctx, int64_t n, const uint16_t* flag, const int32_
 int mcov_kmer_hist(mcov_ctx* ctx, int64_t n, const uint16_t* flag, const int32_t* l_seq, const uint8_t* seq_win,
                    int32_t win_bytes, int32_t win_bases, int32_t K, int32_t NK, int32_t STEP, int32_t OFFSET,
                    int32_t n_group_flags, const uint16_t* group_flags, uint32_t* hist_out) {
+  return mcov_kmer_hist_mem(ctx, n, flag, l_seq, seq_win, MCOV_MEM_HOST, win_bytes, win_bases, K, NK, STEP, OFFSET, n_group_flags,
+                            group_flags, hist_out);
+}
+
+int mcov_kmer_hist_mem(mcov_ctx* ctx, int64_t n, const uint16_t* flag, const int32_t* l_seq, const uint8_t* seq_win, int mem_kind,
+                       int32_t win_bytes, int32_t win_bases, int32_t K, int32_t NK, int32_t STEP, int32_t OFFSET,
+                       int32_t n_group_flags, const uint16_t* group_flags, uint32_t* hist_out) {
   if (!ctx) return MCOV_ERR_ARG;
+  if (mem_kind != MCOV_MEM_HOST && mem_kind != MCOV_MEM_DEVICE) return fail(ctx, MCOV_ERR_ARG, "mcov_kmer_hist: bad mem_kind");
   if (n < 0 || K < 1 || K > 12 || NK < 1 || STEP < 1 || OFFSET < 0 || n_group_flags < 0 || n_group_flags > kMaxGroupFlags ||
       win_bases < OFFSET + (NK - 1) * STEP + K || win_bytes < (win_bases + 1) / 2 || !hist_out ||
       (n > 0 && (!flag || !l_seq || !seq_win)) || (n_group_flags > 0 && !group_flags))
@@ -1709,14 +1717,19 @@ int mcov_kmer_hist(mcov_ctx* ctx, int64_t n, const uint16_t* flag, const int32_t
   CU(ctx->d_win_out.ensure(hist_bytes));
   CU(cudaMemsetAsync(ctx->d_win_out.p, 0, hist_bytes, s));
   if (n > 0) {
-    ReadStage& st = ctx->stage[0];
-    if (st.in_flight) { CU(cudaEventSynchronize(st.consumed)); st.in_flight = false; }
-    CU(st.flag.ensure((size_t)n * 2)); CU(st.pos.ensure((size_t)n * 4)); CU(st.cig.ensure((size_t)n * win_bytes));
-    CU(cudaMemcpyAsync(st.flag.p, flag, (size_t)n * 2, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(st.pos.p, l_seq, (size_t)n * 4, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(st.cig.p, seq_win, (size_t)n * win_bytes, cudaMemcpyHostToDevice, s));
     KmerArgs a;
-    a.n = n; a.flag = st.flag.as<uint16_t>(); a.l_seq = st.pos.as<int32_t>(); a.win = st.cig.as<uint8_t>();
+    a.n = n;
+    if (mem_kind == MCOV_MEM_DEVICE) {                          // (a GPU-decoded file: the columns never leave the device)
+      a.flag = flag; a.l_seq = l_seq; a.win = seq_win;
+    } else {
+      ReadStage& st = ctx->stage[0];
+      if (st.in_flight) { CU(cudaEventSynchronize(st.consumed)); st.in_flight = false; }
+      CU(st.flag.ensure((size_t)n * 2)); CU(st.pos.ensure((size_t)n * 4)); CU(st.cig.ensure((size_t)n * win_bytes));
+      CU(cudaMemcpyAsync(st.flag.p, flag, (size_t)n * 2, cudaMemcpyHostToDevice, s));
+      CU(cudaMemcpyAsync(st.pos.p, l_seq, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+      CU(cudaMemcpyAsync(st.cig.p, seq_win, (size_t)n * win_bytes, cudaMemcpyHostToDevice, s));
+      a.flag = st.flag.as<uint16_t>(); a.l_seq = st.pos.as<int32_t>(); a.win = st.cig.as<uint8_t>();
+    }
     a.win_bytes = win_bytes; a.win_bases = win_bases; a.K = K; a.NK = NK; a.STEP = STEP; a.OFFSET = OFFSET;
     a.n_group_flags = n_group_flags;
     for (int k = 0; k < kMaxGroupFlags; ++k) a.group_flags[k] = k < n_group_flags ? group_flags[k] : 0;

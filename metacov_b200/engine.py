@@ -394,15 +394,18 @@ class CoverageEngine:
     def kmer_hist(self, flag, l_seq, seq_win, win_bases, K, NK, STEP, OFFSET, group_flags=()):
         """ByFlag-grouped k-mer histogram -> uint32[groups, 4**K + 1, NK] (see mcov_kmer_hist)."""
         gf = np.ascontiguousarray(group_flags, dtype=np.uint16)
-        flag = np.ascontiguousarray(flag, dtype=np.uint16)
-        l_seq = np.ascontiguousarray(l_seq, dtype=np.int32)
-        seq_win = np.ascontiguousarray(seq_win, dtype=np.uint8)
+        dev = _is_torch(flag) and flag.is_cuda               # device-resident columns (a GPU-decoded file): no copies
+        if not dev:
+            flag = np.ascontiguousarray(flag, dtype=np.uint16)
+            l_seq = np.ascontiguousarray(l_seq, dtype=np.int32)
+            seq_win = np.ascontiguousarray(seq_win, dtype=np.uint8)
         n = len(flag)
-        win_bytes = seq_win.shape[1] if seq_win.ndim == 2 else (win_bases + 1) // 2
+        win_bytes = seq_win.shape[1] if len(seq_win.shape) == 2 else (win_bases + 1) // 2
         hist = np.zeros((1 << len(gf), 4 ** K + 1, NK), dtype=np.uint32)
-        self._check(lib.mcov_kmer_hist(self._ctx, n, _capi.ptr(flag), _capi.ptr(l_seq), _capi.ptr(seq_win), win_bytes,
-                                       win_bases, K, NK, STEP, OFFSET, len(gf), _capi.ptr(gf) if len(gf) else None,
-                                       _capi.ptr(hist)))
+        self._check(lib.mcov_kmer_hist_mem(self._ctx, n, _capi.ptr(flag), _capi.ptr(l_seq), _capi.ptr(seq_win),
+                                           _capi.MEM_DEVICE if dev else _capi.MEM_HOST, win_bytes,
+                                           win_bases, K, NK, STEP, OFFSET, len(gf), _capi.ptr(gf) if len(gf) else None,
+                                           _capi.ptr(hist)))
         return hist
 
     def depth_runs(self, tid0=0, tid1=None, skip_zero=False):

@@ -186,7 +186,10 @@ class KmerHist(ReadProcessor):
             raise ValueError("KmerHist: a negative OFFSET reads outside the read in the reference "
                              "(SURVEY.md Appendix C-9); not supported")
         win_bases = self.OFFSET + (self.NK - 1) * self.STEP + self.K
-        win = ctx["infile"].seq_windows(win_bases)[:len(ctx["flag"])]
+        if "device_soa" in ctx:
+            win = ctx["device_soa"].seq_windows_device(win_bases)      # (rows beyond maxreads are simply not looked at)
+        else:
+            win = ctx["infile"].seq_windows(win_bases)[:len(ctx["flag"])]
         hist = ctx["engine"].kmer_hist(ctx["flag"], ctx["l_seq"], win, win_bases, self.K, self.NK, self.STEP,
                                        self.OFFSET, group_flags)
         for g, t in enumerate(targets):
@@ -233,6 +236,23 @@ def scan_reads(infile, fasta, counters, progress_interval=10000000, progress_cb=
     else:
         raise Exception("mah")               # scan.pyx:649
     processor.set_max_readlen(50)
+    gpu = getattr(infile, "_gpu", None)
+    if gpu is not None:
+        # a file decoded on the GPU: flag / isize / l_seq (and, for KmerHist, the SEQ windows) stay where the decoder left
+        # them, the accumulators run on the decoder's own engine, and only the histograms come back
+        engine, dsoa = gpu
+        n = int(dsoa.n_records)
+        if maxreads and n > maxreads:
+            n = int(maxreads)
+        ctx = {"engine": engine, "infile": infile, "flag": dsoa.device_view("flag", n), "isize": dsoa.device_view("isize", n),
+               "l_seq": dsoa.device_view("l_seq", n), "device_soa": dsoa}
+        processor._accumulate(ctx, [], [processor])
+        if n:
+            processor.set_max_readlen(max(50, int(dsoa.to_host("l_seq")[:n].max())))
+        if progress_cb:
+            for _ in range(n // max(int(progress_interval), 1)):
+                progress_cb()
+        return n
     soa = infile.soa()
     n = len(soa["flag"])
     if maxreads and n > maxreads:

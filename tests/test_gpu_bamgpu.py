@@ -162,7 +162,20 @@ def test_names_and_seq_on_the_device(tmp_path):
             mscan.scan_reads(f, None, [kh])
             rows.append(kh.counts.copy())
         assert np.array_equal(rows[0], rows[1]) and rows[0].sum() > 0
+        # the whole `scan` stack on the device-resident columns (mcov_kmer_hist_mem / mcov_isize_hist with MCOV_MEM_DEVICE):
+        # ByFlag over IsizeHist + KmerHist, all records and a maxreads prefix, equal the host-decoded file's
+        for maxreads in (0, 37):
+            res = []
+            for f in (host, gpu):
+                bf = mscan.ByFlag([mscan.IsizeHist(), mscan.KmerHist(3, 4, 3, 1)], [mscan.Flags["Readdir"], mscan.Flags["IsRead1"]])
+                nrec = mscan.scan_reads(f, None, bf, maxreads=maxreads)
+                res.append((nrec, [[list(map(str, r)) for r in bf.get_rows(i)] for i in range(2)]))
+            assert res[0][0] == res[1][0] == (maxreads or n)
+            assert res[0][1] == res[1][1]
         assert gpu._h is None
+    with AlignmentFile(p, decode="gpu") as fresh:
+        mscan.scan_reads(fresh, None, mscan.ByFlag([mscan.IsizeHist(), mscan.KmerHist(3, 4, 3, 1)], [mscan.Flags["IsRead1"]]))
+        assert fresh._h is None and fresh._soa is None           # neither the host reader nor a host copy of the columns
 
 
 def test_alignmentfile_and_cli_with_gpu_decode(tmp_path):
