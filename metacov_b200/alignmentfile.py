@@ -400,9 +400,16 @@ class AlignmentFile:
             j, ent, slots = i, 0, 0
             while j < g and (j == i or (ent + ub[j] - lb[j] < (1 << 30) and slots + ends[j] - starts[j] < (1 << 29))):
                 ent += int(ub[j] - lb[j]); slots += int(ends[j] - starts[j]); j += 1
-            out[i:j] = eng.experimental_stats(s, hashes, codes, k_len, kc_val, kc_has,
+            # only the reads the batch's regions can touch travel to the device: [lo, hi) of the file order (a single region
+            # of a 10 M-read file is a few thousand reads, not 266 MB of columns)
+            lo, hi = int(lb[i:j].min()), int(ub[i:j].max())
+            hi = max(hi, lo)
+            o0, o1 = int(s["cig_off"][lo]), int(s["cig_off"][hi])
+            sub = {"pos": s["pos"][lo:hi], "flag": s["flag"][lo:hi], "cig": s["cig"][o0:o1],
+                   "cig_off": (s["cig_off"][lo:hi + 1] - np.uint32(o0)).astype(np.uint32)}
+            out[i:j] = eng.experimental_stats(sub, hashes[lo:hi], codes[lo:hi], k_len, kc_val, kc_has,
                                               np.asarray(starts[i:j], dtype=np.int32), np.asarray(ends[i:j], dtype=np.int32),
-                                              lb[i:j], ub[i:j])
+                                              lb[i:j] - lo, ub[i:j] - lo)
             i = j
         return out
 
