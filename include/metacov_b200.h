@@ -615,6 +615,8 @@ typedef struct mcov_bam_dev {
   const uint8_t*  inflated;
 } mcov_bam_dev;
 int  mcov_bam_decode_gpu(mcov_ctx* ctx, const void* file_bytes, int64_t n_bytes, int verify_crc, mcov_bam_dev* out);
+/* The same straight from the file (the image is mapped, not read into a buffer of the caller's). */
+int  mcov_bam_decode_gpu_file(mcov_ctx* ctx, const char* path, int verify_crc, mcov_bam_dev* out);
 /* Read names and SEQ of the file last decoded on this context, computed on the
  * device from the inflated stream (no host reader is opened).  Each output is
  * optional (NULL = not wanted) and lies in host or device memory per mem_kind:
@@ -633,7 +635,7 @@ int  mcov_bam_gpu_names_seq(mcov_ctx* ctx, int32_t k_len, int32_t win_bases,
                             uint64_t* name_hash_out, int32_t* kmer_code_out, uint8_t* seq_win_out, int mem_kind);
 
 /* A BAM of ANY size through the GPU decoder into the streamed depth pass: the file
- * is read chunk_bytes at a time (<= 0: 256 MiB) into pinned memory by a host thread
+ * is read chunk_bytes at a time (<= 0: 64 MiB) into pinned memory by a host thread
  * while the GPU inflates the previous chunk, establishes its record chain (a record
  * cut by the chunk border is completed with the next chunk), writes the columns and
  * pushes them, led by the reads the pass wants again, through mcov_stream_push from

@@ -138,6 +138,7 @@ SIGNATURES = {
     "mcov_sync": (C.c_int, [_vp]),
     "mcov_copy_to_host": (C.c_int, [_vp, _vp, _vp, C.c_int64]),
     "mcov_bam_decode_gpu": (C.c_int, [_vp, _vp, C.c_int64, C.c_int, _vp]),
+    "mcov_bam_decode_gpu_file": (C.c_int, [_vp, C.c_char_p, C.c_int, _vp]),
     "mcov_bam_gpu_names_seq": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, C.c_int]),
     "mcov_bam_gpu_stream_depth": (C.c_int, [_vp, C.c_char_p, _i64, C.c_int, _vp]),
     "mcov_inflate_host": (C.c_int, [_vp, C.c_uint32, _vp, C.c_uint32]),

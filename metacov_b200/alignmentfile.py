@@ -139,7 +139,7 @@ class AlignmentFile:
         batch; decode="gpu": the compressed file goes to the device and is inflated and parsed there (csrc/bam_gpu.cu) --
         the coverage path then never holds the records on the host, and the file is decoded ~10x faster than 16 host
         cores manage (tools/bench_bam.py), but the compressed image, the inflated stream and the columns must fit the
-        device; decode="gpu-stream": the file is read in chunks (``gpu_chunk_bytes``, default 256 MiB) and every chunk is
+        device; decode="gpu-stream": the file is read in chunks (``gpu_chunk_bytes``, default 64 MiB) and every chunk is
         inflated, parsed and pushed into the streamed depth pass on the device (mcov_bam_gpu_stream_depth) -- any file size,
         the host only reads; accessors that need every record on the host (soa(), read names) open the host reader on
         demand; decode="auto": "gpu" when the whole file fits the device (file size x GPU_DECODE_FOOTPRINT below the free
@@ -150,7 +150,7 @@ class AlignmentFile:
             raise ValueError("decode must be 'host', 'gpu', 'gpu-stream' or 'auto'")
         if decode == "auto":
             decode = "gpu" if self._fits_device(filename, device) else "gpu-stream"
-        self._gpu_chunk_bytes = int(kw.get("gpu_chunk_bytes", 256 << 20))
+        self._gpu_chunk_bytes = int(kw.get("gpu_chunk_bytes", 64 << 20))
         self.gpu_stream_info = None
         self.decode = decode
         self.filename = filename
@@ -193,9 +193,7 @@ class AlignmentFile:
         self._h = None
         eng = CoverageEngine([1], device=device)            # the contig table follows once the header is decoded
         try:
-            with open(filename, "rb") as fh:
-                image = fh.read()
-            dsoa = bamgpu.decode(eng, image)
+            dsoa = bamgpu.decode(eng, os.fspath(filename))      # (the library maps the file: no host copy of the image)
             self.text, refs = dsoa.header()
         except McovError as e:
             eng.close()

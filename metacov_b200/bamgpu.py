@@ -8,6 +8,7 @@ metacov/scan.pyx:204, 216; cli.py:56) without the host decode of ``alignmentfile
     bamgpu.depth_sorted(eng, soa)                # per-base depth straight from them
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -107,9 +108,10 @@ def decode(engine, source, verify_crc=True):
     """Decode a BAM on the GPU.  ``source``: a path, ``bytes`` or a uint8 numpy array / pinned torch tensor
     holding the file image.  Returns a ``DeviceSoA``."""
     keep = None
-    if isinstance(source, (str, bytes)) and not isinstance(source, bytes):
-        with open(source, "rb") as fh:
-            source = fh.read()
+    if isinstance(source, (str, os.PathLike)):              # a path: the library maps the file itself
+        raw = _capi.BamDev()
+        engine._check(lib.mcov_bam_decode_gpu_file(engine._ctx, os.fsencode(source), 1 if verify_crc else 0, C.byref(raw)))
+        return DeviceSoA(engine, raw)
     if isinstance(source, bytes):
         keep = np.frombuffer(source, dtype=np.uint8)
         ptr, n = keep.ctypes.data, keep.nbytes
@@ -132,7 +134,7 @@ def depth_sorted(engine, soa, wait=True):
     engine._check(fn(engine._ctx, soa.n_records, r.tid, r.pos, r.flag, r.mapq, r.cig_off, r.cig, _capi.MEM_DEVICE))
 
 
-def stream_depth(engine, path, chunk_bytes=256 << 20, verify_crc=True):
+def stream_depth(engine, path, chunk_bytes=64 << 20, verify_crc=True):
     """Per-base depth of a coordinate-sorted BAM of any size: the file goes through the GPU decoder chunk by chunk into the
     streamed depth pass (``mcov_bam_gpu_stream_depth``); the engine's contig table must be the file's.  Returns the
     decoder's counters (records, chunks, bytes)."""

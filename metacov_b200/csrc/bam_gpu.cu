@@ -567,13 +567,34 @@ extern "C" int mcov_bam_gpu_names_seq(mcov_ctx* ctx, int32_t k_len, int32_t win_
 // ---------------------------------------------------------------------------------------------------------------------
 #include <cstdio>
 #include <future>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+// The whole-file decode straight from the file: the image is mapped (page cache, no copy into a host buffer of the
+// caller's) and handed to mcov_bam_decode_gpu.
+extern "C" int mcov_bam_decode_gpu_file(mcov_ctx* ctx, const char* path, int verify_crc, mcov_bam_dev* out) {
+  if (!ctx) return MCOV_ERR_ARG;
+  if (!path || !out) return bfail(ctx, MCOV_ERR_ARG, "mcov_bam_decode_gpu_file: bad arguments");
+  const int fd = ::open(path, O_RDONLY);
+  if (fd < 0) return bfail(ctx, MCOV_ERR_IO, "mcov_bam_decode_gpu_file: cannot open the file");
+  struct stat st;
+  if (::fstat(fd, &st) != 0 || st.st_size <= 0) { ::close(fd); return bfail(ctx, MCOV_ERR_IO, "mcov_bam_decode_gpu_file: empty or unreadable file"); }
+  void* map = ::mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+  ::close(fd);
+  if (map == MAP_FAILED) return bfail(ctx, MCOV_ERR_IO, "mcov_bam_decode_gpu_file: cannot map the file");
+  const int rc = mcov_bam_decode_gpu(ctx, map, (int64_t)st.st_size, verify_crc, out);
+  ::munmap(map, (size_t)st.st_size);
+  return rc;
+}
 
 extern "C" int mcov_bam_gpu_stream_depth(mcov_ctx* ctx, const char* path, int64_t chunk_bytes, int verify_crc,
                                          mcov_bam_gpu_stream_info* info) {
   if (!ctx) return MCOV_ERR_ARG;
   if (!path || !info) return bfail(ctx, MCOV_ERR_ARG, "mcov_bam_gpu_stream_depth: bad arguments");
   std::memset(info, 0, sizeof(*info));
-  if (chunk_bytes <= 0) chunk_bytes = 256ll << 20;
+  if (chunk_bytes <= 0) chunk_bytes = 64ll << 20;
   chunk_bytes = std::max<int64_t>(chunk_bytes, 1 << 17);          // at least one BGZF block (<= 64 KiB) beside a leftover
   CUB(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
@@ -582,6 +603,12 @@ extern "C" int mcov_bam_gpu_stream_depth(mcov_ctx* ctx, const char* path, int64_
   FILE* fh = std::fopen(path, "rb");
   if (!fh) return bfail(ctx, MCOV_ERR_IO, "mcov_bam_gpu_stream_depth: cannot open the file");
   struct Closer { FILE* f; ~Closer() { if (f) std::fclose(f); } } closer{fh};
+  // a file smaller than the chunk: pin no more than the file needs (pinning costs ~0.6 ms per MB)
+  if (std::fseek(fh, 0, SEEK_END) == 0) {
+    const long long fsz = (long long)std::ftell(fh);
+    if (fsz > 0 && fsz + 1 < chunk_bytes) chunk_bytes = std::max<int64_t>(fsz + 1, 1 << 17);
+    std::rewind(fh);
+  }
   // two pinned buffers: [leftover of an incomplete block | chunk_bytes of file]
   const size_t cap = (size_t)chunk_bytes + (1u << 17);
   CUB(B.pin[0].ensure(cap)); CUB(B.pin[1].ensure(cap));
