@@ -53,7 +53,9 @@ struct SsArgs {
   const int32_t* region_len;
   const int32_t* region_pad;
   uint32_t* split_hist;             // [n_split][kHistBins], zero between runs
-  RegionScratch* split_scratch;     // [n_split] bin range of the merged histogram (done unused), zero between runs
+  RegionScratch* split_scratch;     // [n_split] arrival counter + bin range of the merged histogram, zero between runs
+  const int32_t* split_pieces;      // [n_split] pieces of the split region: the CTA that merges the last one walks the region
+                                    // (nullptr: k_stats_split_finish does, the tuning hook MCOV_SPLIT_FINISH_KERNEL)
   mcov_region_stats* out;
   int32_t breadth_n;
 };
@@ -68,6 +70,7 @@ k_stats_stream(const __grid_constant__ SsArgs a) {
   __shared__ unsigned long long s_u64[6 * (kSsConsumers / 32)];
   __shared__ int s_i32[4 * (kSsConsumers / 32)];
   __shared__ int s_med[2];
+  __shared__ int s_last;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   {
     uint4* h4 = reinterpret_cast<uint4*>(s_hist);
@@ -162,18 +165,42 @@ k_stats_stream(const __grid_constant__ SsArgs a) {
       if (t == 0) write_stats(a.out + d.region, w);
     } else {
       uint32_t* gh = a.split_hist + (int64_t)d.split * kHistBins;
+      RegionScratch* rs = a.split_scratch + d.split;
       for (int b = lo + t; b <= hi; b += kSsConsumers) {
         const uint32_t c = s_hist[b];
         if (c) atomicAdd(gh + b, c);
       }
+      if (a.split_pieces) named_bar_sync<1, kSsConsumers>();             // the CTA's merges are issued before its arrival
       if (t == 0) {
         if (d.pad > 0) { atomicAdd(gh, (uint32_t)d.pad); lo = 0; if (hi < 0) hi = 0; }
         if (hi >= lo) {
-          atomicMax(&a.split_scratch[d.split].max_bin, (uint32_t)hi);
-          atomicMax(&a.split_scratch[d.split].min_bin_inv, (uint32_t)(kHistBins - 1 - lo));
+          atomicMax(&rs->max_bin, (uint32_t)hi);
+          atomicMax(&rs->min_bin_inv, (uint32_t)(kHistBins - 1 - lo));
+        }
+        if (a.split_pieces) {
+          __threadfence();
+          const unsigned prev = atomicAdd(&rs->done, 1u);
+          s_last = prev == (unsigned)(a.split_pieces[d.split] - 1) ? 1 : 0;
         }
       }
       if (hi < lo) { lo = 0; hi = -1; }
+      if (a.split_pieces) {
+        named_bar_sync<1, kSsConsumers>();
+        if (s_last) {
+          // the last piece of the region has arrived here: pull the merged bin range (it contains this piece's), leave the
+          // global copy zeroed for the next run, walk -- what k_stats_split_finish did in a launch of its own
+          __threadfence();
+          int mlo = kHistBins - 1 - (int)*((volatile uint32_t*)&rs->min_bin_inv), mhi = (int)*((volatile uint32_t*)&rs->max_bin);
+          if (mhi < mlo) { mlo = 0; mhi = 0; }
+          for (int b = mlo + t; b <= mhi; b += kSsConsumers) { s_hist[b] = __ldcg(gh + b); gh[b] = 0u; }
+          named_bar_sync<1, kSsConsumers>();
+          if (t == 0) { rs->done = 0u; rs->max_bin = 0u; rs->min_bin_inv = 0u; }
+          const long long n_region = (long long)a.region_len[d.region] + a.region_pad[d.region];
+          const WalkOut w = hist_walk<kSsConsumers, true>(s_hist, n_region, a.breadth_n, mlo, mhi, s_u64, s_i32, s_med);
+          if (t == 0) write_stats(a.out + d.region, w);
+          lo = mlo; hi = mhi;                                            // (the range to clear below)
+        }
+      }
     }
     named_bar_sync<1, kSsConsumers>();                                  // walk / merge have read the bins
     for (int b = lo + t; b <= hi; b += kSsConsumers) s_hist[b] = 0u;     // only the touched range needs clearing

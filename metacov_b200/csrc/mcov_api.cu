@@ -1178,7 +1178,7 @@ static int stats_launch(mcov_ctx* ctx, int64_t g, const int32_t* tid, const int3
       int64_t total_big = 0;
       for (int64_t i = 0; i < g; ++i) if (rchunks[i] >= 1 && !(rchunks[i] == 1 && rp.rlen[i] <= kSmallRegion)) total_big += rp.rlen[i];
       std::vector<SsPiece> pieces;
-      std::vector<int32_t> cta_start, split_region;
+      std::vector<int32_t> cta_start, split_region, split_npieces;
       int32_t grid = (int32_t)std::min<int64_t>((int64_t)ctx->n_sm * MCOV_SS_CTAS, std::max<int64_t>(1, total_big / 16384));
       const int64_t W = std::max<int64_t>(4, ((total_big + grid - 1) / grid + 3) & ~(int64_t)3);
       int64_t room = W;
@@ -1199,6 +1199,7 @@ static int stats_launch(mcov_ctx* ctx, int64_t g, const int32_t* tid, const int3
         if (pieces.size() - first_piece > 1) {
           const int32_t id = (int32_t)split_region.size();
           split_region.push_back((int32_t)i);
+          split_npieces.push_back((int32_t)(pieces.size() - first_piece));
           for (size_t k = first_piece; k < pieces.size(); ++k) pieces[k].split = id;
         }
       }
@@ -1208,12 +1209,14 @@ static int stats_launch(mcov_ctx* ctx, int64_t g, const int32_t* tid, const int3
       if (rp.ss_grid > 0) {
         CU(ctx->d_ss_pieces.ensure(pieces.size() * sizeof(SsPiece)));
         CU(ctx->d_ss_cta.ensure(cta_start.size() * 4));
-        CU(ctx->d_ss_split.ensure(std::max<size_t>(split_region.size(), 1) * 4));
+        CU(ctx->d_ss_split.ensure(std::max<size_t>(split_region.size(), 1) * 8));      // [region of the split | its pieces]
         CU(ctx->d_ss_pool.ensure((size_t)std::max(rp.n_split, 1) * (sizeof(RegionScratch) + (size_t)kHistBins * 4)));
         CU(cudaMemcpyAsync(ctx->d_ss_pieces.p, pieces.data(), pieces.size() * sizeof(SsPiece), cudaMemcpyHostToDevice, s));
         CU(cudaMemcpyAsync(ctx->d_ss_cta.p, cta_start.data(), cta_start.size() * 4, cudaMemcpyHostToDevice, s));
         if (rp.n_split) {
           CU(cudaMemcpyAsync(ctx->d_ss_split.p, split_region.data(), split_region.size() * 4, cudaMemcpyHostToDevice, s));
+          CU(cudaMemcpyAsync(ctx->d_ss_split.as<int32_t>() + split_region.size(), split_npieces.data(), split_npieces.size() * 4,
+                             cudaMemcpyHostToDevice, s));
           CU(cudaMemsetAsync(ctx->d_ss_pool.p, 0, (size_t)rp.n_split * (sizeof(RegionScratch) + (size_t)kHistBins * 4), s));
         }
         CU(cudaStreamSynchronize(s));                 // the host vectors above go out of scope
@@ -1256,9 +1259,11 @@ static int stats_launch(mcov_ctx* ctx, int64_t g, const int32_t* tid, const int3
       a.split_scratch = ctx->d_ss_pool.as<RegionScratch>();
       a.split_hist = reinterpret_cast<uint32_t*>(ctx->d_ss_pool.as<char>() + (size_t)rp.n_split * sizeof(RegionScratch));
       a.out = d_out; a.breadth_n = breadth_n;
+      static const bool finish_kernel = std::getenv("MCOV_SPLIT_FINISH_KERNEL") != nullptr;   // tuning hook: split regions walked by a second launch
+      a.split_pieces = (rp.n_split && !finish_kernel) ? ctx->d_ss_split.as<int32_t>() + rp.n_split : nullptr;
       const bool pdl = ctx->n_slots <= kPdlMaxSlots;
       MCOV_LAUNCH(ctx, kKStatsStream, CU(launch_pdl(pdl, k_stats_stream, dim3((unsigned)rp.ss_grid), dim3(kSsThreads), (size_t)kSsSmemBytes, s, a)));
-      if (rp.n_split)
+      if (rp.n_split && finish_kernel)
         MCOV_LAUNCH(ctx, kKStatsSplitFinish, CU(launch_pdl(pdl, k_stats_split_finish, dim3((unsigned)rp.n_split), dim3(kSsConsumers), 0, s, a,
                                                      (const int32_t*)ctx->d_ss_split.as<int32_t>())));
     } else if (rp.n_tasks) {
