@@ -561,6 +561,11 @@ int mcov_depth_sorted_delta(mcov_ctx* ctx, int64_t n, const int64_t* contig_read
   if (rc) return rc;
   if (contig_read_start[0] != 0 || contig_read_start[ctx->n_contigs] > n)
     return fail(ctx, MCOV_ERR_ARG, "mcov_depth_sorted_delta: contig_read_start must start at 0 and end <= n");
+  {
+    uint64_t sum = 0;
+    for (int64_t i = 0; i < n; ++i) sum += n_cigar[i];
+    if (sum != (uint64_t)n_cig_total) return fail(ctx, MCOV_ERR_ARG, "mcov_depth_sorted_delta: the op counts do not add up to n_cig_total");
+  }
   { int wrc = wait_pending_copy(ctx); if (wrc) return wrc; }
   CU(cudaMemsetAsync(ctx->d_pc.p, 0, sizeof(PassCounters), ctx->stream));
   ReadStage& st = ctx->stage[ctx->stage_next];
@@ -957,6 +962,12 @@ int mcov_depth_sorted_packed(mcov_ctx* ctx, int64_t n, const int64_t* contig_rea
   if (rc) return rc;
   if (contig_read_start[0] != 0 || contig_read_start[ctx->n_contigs] > n)
     return fail(ctx, MCOV_ERR_ARG, "mcov_depth_sorted_packed: contig_read_start must start at 0 and end <= n");
+  {
+    // the op counts must add up to the op array: the device rebuilds the offsets from them and reads cig[] there
+    uint64_t sum = 0;
+    for (int64_t i = 0; i < n; ++i) sum += n_cigar[i];
+    if (sum != (uint64_t)n_cig_total) return fail(ctx, MCOV_ERR_ARG, "mcov_depth_sorted_packed: the op counts do not add up to n_cig_total");
+  }
   { int wrc = wait_pending_copy(ctx); if (wrc) return wrc; }
   CU(cudaMemsetAsync(ctx->d_pc.p, 0, sizeof(PassCounters), ctx->stream));
   ReadStage& st = ctx->stage[ctx->stage_next];

@@ -438,6 +438,12 @@ def test_packed_host_transport_equals_soa_path(wl, scale):
             assert np.array_equal(d, want[c]), c
         pi = eng.pass_info()
         assert pi["n_pass"] == info["n_pass"] and pi["aligned_bases"] == info["aligned_bases"] and pi["sorted"] == 1
+        # op counts that do not add up to the op array are refused (the device would read cig[] by them)
+        bad = dict(packed)
+        bad["n_cigar"] = np.array(packed["n_cigar"], copy=True)
+        bad["n_cigar"][len(bad["n_cigar"]) // 2] += 3
+        with pytest.raises(McovError):
+            eng.depth_sorted_packed(bad)
         # with mapq shipped and a mapq filter
         eng.set_filter(min_mapq=30)
         with pytest.raises(McovError):
