@@ -603,15 +603,19 @@ extern "C" int mcov_bam_gpu_stream_depth(mcov_ctx* ctx, const char* path, int64_
   FILE* fh = std::fopen(path, "rb");
   if (!fh) return bfail(ctx, MCOV_ERR_IO, "mcov_bam_gpu_stream_depth: cannot open the file");
   struct Closer { FILE* f; ~Closer() { if (f) std::fclose(f); } } closer{fh};
-  // a file smaller than the chunk: pin no more than the file needs (pinning costs ~0.6 ms per MB)
+  // a file smaller than the chunk: buffers no larger than the file needs.  The two host buffers are PINNED only for a long
+  // stream (>= 1 GiB of file): pinning costs 0.6 - 2.4 ms per MB on these boxes (and as much again to free), which a short
+  // file never earns back -- its chunks go through the driver's own staging (still faster than the inflate consumes them)
+  long long fsz = -1;
   if (std::fseek(fh, 0, SEEK_END) == 0) {
-    const long long fsz = (long long)std::ftell(fh);
+    fsz = (long long)std::ftell(fh);
     if (fsz > 0 && fsz + 1 < chunk_bytes) chunk_bytes = std::max<int64_t>(fsz + 1, 1 << 17);
     std::rewind(fh);
   }
+  const bool pin = fsz >= (1ll << 30);
   // two pinned buffers: [leftover of an incomplete block | chunk_bytes of file]
   const size_t cap = (size_t)chunk_bytes + (1u << 17);
-  CUB(B.pin[0].ensure(cap)); CUB(B.pin[1].ensure(cap));
+  CUB(B.pin[0].ensure(cap, pin)); CUB(B.pin[1].ensure(cap, pin));
   CUB(B.status.ensure(64));
   auto read_into = [fh](uint8_t* dst, size_t want) -> size_t { return std::fread(dst, 1, want, fh); };
   int rc = mcov_stream_begin(ctx);
