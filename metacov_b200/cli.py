@@ -48,10 +48,11 @@ def main():
 @click.option("--window", "-w", type=click.IntRange(1), metavar="N",
               help="Also write the mean depth of fixed windows of N bp to --window-out. Not in the reference: additive.")
 @click.option("--window-out", "-wo", type=click.File("w"), metavar="FILE", help="Output CSV of --window (sacc,start,end,avg)")
-@click.option("--bam-decode", type=click.Choice(["host", "gpu", "gpu-stream", "auto"]), default="host", show_default=True,
-              help="Where the BAM file is inflated and parsed: host threads (zlib) or the GPU. Not in the reference: additive.")
+@click.option("--bam-decode", type=click.Choice(["host", "gpu", "gpu-stream", "auto"]), default="auto", show_default=True,
+              help="Where the BAM file is inflated and parsed: host threads (zlib), the GPU (whole file / streamed in chunks), or "
+                   "auto = the GPU, streamed when the file does not fit it. Not in the reference: additive.")
 def pileup(bamfile, reference_fasta, regionfile_blast7, regionfile_csv, kmer_histogram, kmer_length, outfile,
-           bedgraph=None, window=None, window_out=None, bam_decode="host"):
+           bedgraph=None, window=None, window_out=None, bam_decode="auto"):
     """
     Compute fold coverage values
     """
@@ -152,9 +153,12 @@ def write_windows(bam, window, out):
               help="Palindrome length is 2N+1")
 @click.option("--out-isizehist", "-I", type=click.File("w", lazy=False), metavar="FILE",
               help="Compute histogram of insert sizes.")
+@click.option("--bam-decode", type=click.Choice(["host", "gpu", "gpu-stream", "auto"]), default="auto", show_default=True,
+              help="Where the BAM file is inflated and parsed (see `pileup`); with the GPU the accumulators run on the "
+                   "device-resident columns. Not in the reference: additive.")
 @click.argument("readfile", nargs=-1, required=True)
 def scan(readfile, readfile_type, out_basehist, boffset, out_kmerhist, k, number, step, offset, max_reads,
-         reference_fasta, out_mirrorhist, mirror_offset, mirror_length, out_isizehist, group_by):
+         reference_fasta, out_mirrorhist, mirror_offset, mirror_length, out_isizehist, group_by, bam_decode="auto"):
     """
     Gather read statistics
     """
@@ -183,7 +187,7 @@ def scan(readfile, readfile_type, out_basehist, boffset, out_kmerhist, k, number
     if max_reads and max_reads > 0 and max_reads / 100 < update_every:
         update_every = int(max_reads + 50 / 100)        # sic (reference cli.py:205-206)
 
-    infile = AlignmentFile(readfile[0])
+    infile = AlignmentFile(readfile[0], decode=bam_decode)
     log.info("mapped = {}, unmapped = {}, total = {}".format(infile.mapped, infile.unmapped,
                                                              infile.mapped + infile.unmapped))
     length = infile.mapped + infile.unmapped
