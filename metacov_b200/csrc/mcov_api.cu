@@ -255,8 +255,15 @@ int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a, int64_t tile_lo = -1,
   // prep -> scan_counts -> far_scatter -> tile (-> statistics) are chained with programmatic dependent
   // launches: each kernel's CTAs are in place before its predecessor has drained
   const bool pdl = ctx->n_slots <= kPdlMaxSlots;
-  MCOV_LAUNCH(ctx, kKScanCounts, CU(launch_pdl(pdl, k_scan_inplace<false>, dim3((unsigned)scan_tiles), dim3(kScanThreads), 0, s,
-      f.tile_agg, scan_len, reinterpret_cast<unsigned long long*>(z + o_st), pc_of(ctx))));
+  // (measured on C2, 48 840 counters: look-back kernel 8.7 us by events; ONE CTA of 1 024 threads 45 us -- a single SM's
+  //  dependent L2 round trips; an 8-CTA cluster exchanging totals through distributed shared memory 10.7 us -- the cluster
+  //  launch and its two barriers cost more than the look-back's spin.  The cluster variant stays behind MCOV_SCAN_CLUSTER.)
+  static const bool scan_cluster = std::getenv("MCOV_SCAN_CLUSTER") != nullptr;             // tuning hook
+  if (scan_len <= kScanSmallMax && scan_cluster)
+    MCOV_LAUNCH(ctx, kKScanCounts, CU(launch_pdl(pdl, k_scan_small, dim3(kScanSmallCluster), dim3(kScanSmallThreads), 0, s, f.tile_agg, scan_len)));
+  else
+    MCOV_LAUNCH(ctx, kKScanCounts, CU(launch_pdl(pdl, k_scan_inplace<false>, dim3((unsigned)scan_tiles), dim3(kScanThreads), 0, s,
+        f.tile_agg, scan_len, reinterpret_cast<unsigned long long*>(z + o_st), pc_of(ctx))));
   MCOV_LAUNCH(ctx, kKFarScatter, CU(launch_pdl(pdl, k_far_scatter, dim3(ctx->n_sm * 2), dim3(256), 0, s, f)));
   ctx->fused_blob.assign(reinterpret_cast<const unsigned char*>(&f), reinterpret_cast<const unsigned char*>(&f) + sizeof(f));
   {
@@ -406,6 +413,7 @@ int configure_kernels(mcov_ctx* ctx) {
   CU(cudaFuncSetAttribute(k_block_expand, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
   CU(cudaFuncSetAttribute(k_fused_prep<false>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
   CU(cudaFuncSetAttribute(k_scan_inplace<false>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  CU(cudaFuncSetAttribute(k_scan_small, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
   CU(cudaFuncSetAttribute(k_far_scatter, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
   CU(cudaFuncSetAttribute(k_fused_tile_tma, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
   CU(cudaFuncSetAttribute(k_fused_tile, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
