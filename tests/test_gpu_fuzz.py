@@ -4,6 +4,8 @@ flag bit, spans longer than a tile (the far-read tables), unplaced reads, duplic
 thousand, random filters, random (overlapping, overhanging, empty) regions -- against the C oracle, on both
 depth formulations, the packed host transport, the run-length export and the insert-size histogram.  Seeds
 are fixed: failures reproduce."""
+import os
+
 import numpy as np
 import pytest
 
@@ -70,7 +72,8 @@ def _case(seed):
     return ReadBatch(tid, pos, flag, mapq, cig_off, cig), isize, lengths, (rt, rs, re), filt
 
 
-@pytest.mark.parametrize("block", range(6))
+# MCOV_FUZZ_BLOCKS=60 runs 600 cases instead of 60 (a one-off of the builder: profiles/r02_fuzz_600.txt)
+@pytest.mark.parametrize("block", range(int(os.environ.get("MCOV_FUZZ_BLOCKS", "6"))))
 def test_random_cases_match_oracle(block):
     from metacov_b200 import CoverageEngine, McovError, _capi
     from metacov_b200.engine import pack_batch, pack_batch_delta, pack_block
@@ -97,7 +100,13 @@ def test_random_cases_match_oracle(block):
                         if path == "packed":
                             eng.depth_sorted_packed(pack_batch(b, len(lengths), with_mapq=True))
                         elif path == "block":
-                            eng.depth_sorted_block(pack_block(b, len(lengths), with_mapq=True))
+                            blk = pack_block(b, len(lengths), with_mapq=True)
+                            u = eng.block_unpack(blk)                      # the rebuilt columns themselves
+                            ok = (b.tid >= 0) & (b.tid < len(lengths))
+                            assert np.array_equal(u["tid"][ok], b.tid[ok]) and np.all(u["tid"][~ok] == -1), seed
+                            assert np.array_equal(u["pos"], b.pos) and np.array_equal(u["flag"], b.flag) and np.array_equal(u["mapq"], b.mapq), seed
+                            assert np.array_equal(u["cig_off"], b.cig_off) and np.array_equal(u["cig"], b.cig), seed
+                            eng.depth_sorted_block(blk)
                         else:
                             eng.depth_sorted_delta(pack_batch_delta(b, len(lengths), with_mapq=True))
                     except ValueError:
