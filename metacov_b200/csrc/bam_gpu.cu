@@ -29,6 +29,7 @@
 // Replaces, for this path, `pysam.AlignmentFile` + `IteratorRowAll` (reference metacov/scan.pyx:204,
 // 216; cli.py:56) -- like bamio.cpp, which stays the host decoder.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -612,7 +613,8 @@ extern "C" int mcov_bam_gpu_stream_depth(mcov_ctx* ctx, const char* path, int64_
     if (fsz > 0 && fsz + 1 < chunk_bytes) chunk_bytes = std::max<int64_t>(fsz + 1, 1 << 17);
     std::rewind(fh);
   }
-  const bool pin = fsz >= (1ll << 30);
+  static const bool force_pin = std::getenv("MCOV_STREAM_PIN") != nullptr;     // test / tuning hook: pinned buffers whatever the size
+  const bool pin = force_pin || fsz >= (1ll << 30);
   // two pinned buffers: [leftover of an incomplete block | chunk_bytes of file]
   const size_t cap = (size_t)chunk_bytes + (1u << 17);
   CUB(B.pin[0].ensure(cap, pin)); CUB(B.pin[1].ensure(cap, pin));

@@ -5,6 +5,8 @@ corrupt files fail loudly; depth from the device-resident columns equals the ora
 import struct
 import zlib
 
+import os
+
 import numpy as np
 import pytest
 
@@ -269,6 +271,22 @@ def test_streamed_gpu_decode_matches_whole_file(tmp_path):
             for c in range(len(lengths)):
                 assert np.array_equal(eng.copy_depth(c), want[woff[c]:woff[c] + lengths[c]]), (chunk, c)
             assert info["max_carry"] < 5000                    # the unplaced tail is not dragged along
+    # the long-stream arrangement (pinned host buffers, taken by files of 1 GiB and more) on the same file: a child process,
+    # because the switch is read once per process
+    import subprocess, sys
+    code = ("import sys, numpy as np; sys.path.insert(0, %r)\n"
+            "from metacov_b200 import CoverageEngine, bamgpu\n"
+            "lengths = %r\n"
+            "with CoverageEngine(lengths) as eng:\n"
+            "    info = bamgpu.stream_depth(eng, %r, chunk_bytes=1 << 17)\n"
+            "    pi = eng.pass_info()\n"
+            "    print(info['n_records'], info['n_chunks'], pi['n_pass'], pi['aligned_bases'], int(eng.copy_depth(1).astype(np.int64).sum()))\n"
+            % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), lengths, p))
+    res = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, MCOV_STREAM_PIN="1"), capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    got = [int(x) for x in res.stdout.split()]
+    assert got[0] == len(tid) and got[1] >= 4 and got[2] == winfo["n_pass"] and got[3] == winfo["aligned_bases"]
+    assert got[4] == int(want[woff[1]:woff[1] + lengths[1]].astype(np.int64).sum())
     # truncated file
     raw = open(p, "rb").read()
     (tmp_path / "cut.bam").write_bytes(raw[:len(raw) * 2 // 3])
