@@ -77,7 +77,10 @@ static_assert(offsetof(BlkShared, d) == offsetof(BlkShared, e) + sizeof(uint32_t
 // the chunk's reads into registers: e[j] = flag << 8 | class, d[j] = position difference, escapes and exceptions applied
 // (reads at and beyond n: class 128 = no ops, difference 0)
 __device__ __forceinline__ void blk_load(const BlockArgs& a, BlkShared& sm, int64_t chunk, const mcov_block_chunk& ce,
-                                         uint32_t (&e)[kBlkPer], int32_t (&d)[kBlkPer]) {
+                                         const bool marks_follow, const uint2 w0, const uint2 w1, uint32_t (&e)[kBlkPer],
+                                         int32_t (&d)[kBlkPer]) {
+  // w0 / w1: the thread's eight per-read bytes (nibble form: w0; wide form: w0 = fc, w1 = dpos), fetched by the caller before
+  // its first barrier when all eight reads exist
   const mcov_block_hdr& h = a.h;
   const int64_t n = h.n, c0 = chunk * kBlkChunk, i0 = c0 + (int64_t)threadIdx.x * kBlkPer;
   if (h.nib) {
@@ -86,7 +89,7 @@ __device__ __forceinline__ void blk_load(const BlockArgs& a, BlkShared& sm, int6
     const uint8_t* nb = reinterpret_cast<const uint8_t*>(a.blk + h.off_nb);
     uint32_t lo[kBlkPer], hi[kBlkPer];
     if (i0 + kBlkPer <= n) {
-      const uint2 q = *reinterpret_cast<const uint2*>(nb + i0);
+      const uint2 q = w0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const uint32_t b0 = (q.x >> (8 * j)) & 255u, b1 = (q.y >> (8 * j)) & 255u;
@@ -102,7 +105,7 @@ __device__ __forceinline__ void blk_load(const BlockArgs& a, BlkShared& sm, int6
     uint32_t cnt = 0;
     if (i0 + kBlkPer <= n) {
       // bit 0 of every nibble of y: the nibble is 15
-      const uint2 q = *reinterpret_cast<const uint2*>(nb + i0);
+      const uint2 q = w0;
       uint32_t y0 = q.x & (q.x >> 1), y1 = q.y & (q.y >> 1);
       y0 &= y0 >> 2; y1 &= y1 >> 2;
       cnt = (uint32_t)(__popc(y0 & 0x01010101u) + __popc(y1 & 0x01010101u)) + ((uint32_t)(__popc(y0 & 0x10101010u) + __popc(y1 & 0x10101010u)) << 16);
@@ -134,7 +137,7 @@ __device__ __forceinline__ void blk_load(const BlockArgs& a, BlkShared& sm, int6
     const uint8_t* fc = reinterpret_cast<const uint8_t*>(a.blk + h.off_fc);
     const uint8_t* dp = reinterpret_cast<const uint8_t*>(a.blk + h.off_dpos);
     if (i0 + kBlkPer <= n) {
-      const uint2 f = *reinterpret_cast<const uint2*>(fc + i0), q = *reinterpret_cast<const uint2*>(dp + i0);
+      const uint2 f = w0, q = w1;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         e[j] = sm.jt[(f.x >> (8 * j)) & 255u]; e[j + 4] = sm.jt[(f.y >> (8 * j)) & 255u];
@@ -177,7 +180,8 @@ __device__ __forceinline__ void blk_load(const BlockArgs& a, BlkShared& sm, int6
 #pragma unroll
       for (int j = 0; j < kBlkPer; ++j) if (e[j] == kBlkEscape) e[j] = sm.e[threadIdx.x * kBlkPer + j] & 0xFFFFFFu;
     }
-    __syncthreads();                                                          // (sm.e is reused for the contig marks)
+    if (marks_follow) __syncthreads();                                        // (sm.e is rewritten at once by the contig marks; else
+                                                                              //  only behind the next barriers, as the op image)
     return;
   }
 #pragma unroll
@@ -228,6 +232,33 @@ __global__ void __launch_bounds__(kBlkThreads, 4) k_block_expand(const __grid_co
     ce.dq_off = 0; ce.fq_off = 0; ce.op_off = (uint32_t)h.n_cigar; ce.xop_off = (uint32_t)h.n_xops;
     ce.pos_carry = 0; ce.esc_first = kBlkNone; ce.exc_first = kBlkNone; ce.reserved = 0;
   }
+  // the chunk's explicit ops into shared memory (coalesced) -- their number is known from the table (the next row's entry
+  // point), so the loads are issued now and have landed long before the ops are gathered
+  const uint32_t n_cig = (uint32_t)h.n_cigar, n_xops = (uint32_t)h.n_xops;
+  const bool narrow = h.xop_bytes == 2;
+  const uint32_t* x32 = reinterpret_cast<const uint32_t*>(a.blk + h.off_xops);
+  const uint16_t* x16 = reinterpret_cast<const uint16_t*>(a.blk + h.off_xops);
+  uint32_t n_xo_tab = 0;
+  if (c0 < n) {
+    const uint32_t x_end = c1 < n ? (reinterpret_cast<const uint4*>(a.blk + h.off_chunk) + 2 * (chunk + 1))->w : n_xops;
+    n_xo_tab = x_end >= ce.xop_off ? x_end - ce.xop_off : 0u;
+    if (n_xo_tab <= (uint32_t)kBlkXopCap) {
+      for (uint32_t q = t; q < n_xo_tab; q += kBlkThreads) {
+        const uint32_t g = ce.xop_off + q;
+        sm.xo[q] = g < n_xops ? (narrow ? (uint32_t)x16[g] : x32[g]) : 0u;
+      }
+    }
+  }
+  if (t == 0) sm.list_n = 0;
+  // the thread's own eight per-read bytes, in flight while the tables load
+  uint2 w0 = make_uint2(0u, 0u), w1 = make_uint2(0u, 0u);
+  {
+    const int64_t i0 = c0 + (int64_t)t * kBlkPer;
+    if (i0 + kBlkPer <= n) {
+      if (h.nib) w0 = *reinterpret_cast<const uint2*>(a.blk + h.off_nb + i0);
+      else { w0 = *reinterpret_cast<const uint2*>(a.blk + h.off_fc + i0); w1 = *reinterpret_cast<const uint2*>(a.blk + h.off_dpos + i0); }
+    }
+  }
   {
     const uint32_t* jt = reinterpret_cast<const uint32_t*>(a.blk + h.off_jt);
     const uint32_t* dict_off = reinterpret_cast<const uint32_t*>(a.blk + h.off_dict_off);
@@ -247,7 +278,7 @@ __global__ void __launch_bounds__(kBlkThreads, 4) k_block_expand(const __grid_co
   __syncthreads();
   uint32_t e[kBlkPer];
   int32_t d[kBlkPer];
-  blk_load(a, sm, chunk, ce, e, d);
+  blk_load(a, sm, chunk, ce, sm.starts != 0, w0, w1, e, d);
   // contig starts inside the chunk: mark = contig index + 1 at the start's place (empty contigs share a start: the last wins)
   const int32_t c_lo = sm.c_lo;
   const bool starts = sm.starts != 0;                     // (uniform: most chunks of deep data lie inside one contig)
@@ -305,18 +336,8 @@ __global__ void __launch_bounds__(kBlkThreads, 4) k_block_expand(const __grid_co
     if (lane > 0) { pm = max(pm, em); pp = ef ? es : pp + es; pcx += ec; }
   }
   const uint32_t n_ops = (uint32_t)tot, n_xo = (uint32_t)(tot >> 32);       // of the chunk
-  // the chunk's explicit ops into shared memory (coalesced)
-  const uint32_t n_cig = (uint32_t)h.n_cigar, n_xops = (uint32_t)h.n_xops;
-  const bool narrow = h.xop_bytes == 2;
-  const uint32_t* x32 = reinterpret_cast<const uint32_t*>(a.blk + h.off_xops);
-  const uint16_t* x16 = reinterpret_cast<const uint16_t*>(a.blk + h.off_xops);
-  const bool staged = n_ops <= (uint32_t)kBlkOpCap && n_xo <= (uint32_t)kBlkXopCap;
-  if (staged) {
-    for (uint32_t q = t; q < n_xo; q += kBlkThreads) {
-      const uint32_t g = ce.xop_off + q;
-      sm.xo[q] = g < n_xops ? (narrow ? (uint32_t)x16[g] : x32[g]) : 0u;
-    }
-  }
+  // (a table that disagrees with the classes -- a malformed block -- sends the chunk down the unstaged path)
+  const bool staged = n_ops <= (uint32_t)kBlkOpCap && n_xo <= (uint32_t)kBlkXopCap && n_xo == n_xo_tab;
   // outputs
   const int64_t i0 = c0 + (int64_t)t * kBlkPer;
   uint32_t o_c = (uint32_t)pcx, o_x = (uint32_t)(pcx >> 32);                  // relative to the chunk
@@ -360,9 +381,8 @@ __global__ void __launch_bounds__(kBlkThreads, 4) k_block_expand(const __grid_co
   if (staged) {
     // every read's ops -- dictionary entry or its slice of the chunk's explicit ops, both in shared memory -- gathered into the
     // image of the chunk's op range, then the image stored coalesced
-    uint32_t* img = sm.e;                                                     // e[] and d[]: kBlkOpCap words
-    if (t == 0) sm.list_n = 0;
-    __syncthreads();                                                          // (xo[] loaded)
+    uint32_t* img = sm.e;                                                     // e[] and d[]: kBlkOpCap words (free since the barrier
+                                                                              // behind the scans, which also covers xo[] and list_n)
     // the first op of every read here; the reads with more ops (one in ten on short-read data) go to a list that the CTA
     // then works through together -- a loop `for k < c` per read makes every warp wait for its longest CIGAR eight times
     // (o0 + c <= n_ops <= kBlkOpCap and o_x + c <= n_xo <= kBlkXopCap hold by construction: all four are sums of the same cn[])
