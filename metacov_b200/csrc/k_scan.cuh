@@ -31,6 +31,9 @@ namespace mcov {
 #ifndef MCOV_SCAN_THREADS
 #define MCOV_SCAN_THREADS 512
 #endif
+#ifndef MCOV_SCAN_TICKET
+#define MCOV_SCAN_TICKET 1                                    // 0: tile id = blockIdx.x (relies on in-order CTA dispatch)
+#endif
 constexpr int kScanThreads = MCOV_SCAN_THREADS;
 constexpr int kScanVec = MCOV_SCAN_VEC;                       // int4 per thread
 constexpr int kScanTile = kScanThreads * kScanVec * 4;        // 16384 slots (64 KB)
@@ -71,10 +74,20 @@ k_scan_inplace(int32_t* __restrict__ data, int64_t n_slots, unsigned long long* 
                PassCounters* pc) {
   __shared__ int s_warp[kScanThreads / 32];
   __shared__ int s_prefix;
-  // CTAs are dispatched in index order (CUB's decoupled look-back relies on the same), so a tile's
-  // predecessors are always running or done; an atomic ticket costs a dependent L2 round trip per CTA
-  const int64_t tile = blockIdx.x;
+  // A tile spins on its predecessors, so they must be running or done.  CTAs are dispatched in index order in practice
+  // (CUB's decoupled look-back with static tile ids relies on the same), but nothing guarantees it -- least of all next
+  // to programmatic dependent launches -- so the tile id is a TICKET drawn from a counter behind the status words: a
+  // CTA only ever waits for tiles whose CTAs have started.  Cost: one L2 round trip per CTA (0.2 us on the three-tile
+  // scan between prep and tile, nothing measurable on the 3 052 tiles of the push path).
+  __shared__ unsigned s_tile;
   pdl_wait();
+#if MCOV_SCAN_TICKET
+  if (threadIdx.x == 0) s_tile = atomicAdd(reinterpret_cast<unsigned*>(status + gridDim.x), 1u);
+  __syncthreads();
+  const int64_t tile = s_tile;
+#else
+  const int64_t tile = blockIdx.x;
+#endif
   pdl_launch_dependents();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t base = tile * kScanTile;

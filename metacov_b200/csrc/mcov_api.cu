@@ -189,7 +189,7 @@ int fused_depth_sorted(mcov_ctx* ctx, const ExpandArgs& a, int64_t tile_lo = -1,
   // one zeroed scratch block: [tile_agg | tile_cnt | tile_cursor | tile_cap | scan status | per-contig "capped" flags]
   const size_t o_agg = 0, o_cnt = o_agg + (size_t)cnt_pad * 4, o_cur = o_cnt + (size_t)cnt_pad * 4,
                o_cap = o_cur + (size_t)n_tiles * 4, o_st = (o_cap + (size_t)n_tiles * 4 + 7) & ~(size_t)7,
-               o_flag = o_st + (size_t)scan_tiles * 8, z_bytes = o_flag + (size_t)ctx->n_contigs;
+               o_flag = o_st + ((size_t)scan_tiles + 1) * 8 /* + the ticket word */, z_bytes = o_flag + (size_t)ctx->n_contigs;
   CU(ctx->d_status.ensure(z_bytes));
   CU(ctx->d_start_slot.ensure((size_t)(std::max<int64_t>(n, 1) + 8) * sizeof(uint32_t)));   // rec (+ vector-load padding)
   CU(ctx->d_tile_off.ensure((size_t)(n_tiles + 1) * 4));                                 // tile_first
@@ -304,8 +304,8 @@ int runs_depth(mcov_ctx* ctx, const ExpandArgs& a, int64_t i_begin, bool clear, 
   }
   if (finalize) {
     const int64_t n_tiles = (ctx->n_slots + kScanTile - 1) / kScanTile;
-    CU(ctx->d_status.ensure((size_t)n_tiles * 8));
-    CU(cudaMemsetAsync(ctx->d_status.p, 0, (size_t)n_tiles * 8, s));
+    CU(ctx->d_status.ensure(((size_t)n_tiles + 1) * 8));            // status words + the ticket word
+    CU(cudaMemsetAsync(ctx->d_status.p, 0, ((size_t)n_tiles + 1) * 8, s));
     MCOV_LAUNCH(ctx, kKScan, (k_scan_inplace<true><<<(unsigned)n_tiles, kScanThreads, 0, s>>>(ctx->depth, ctx->n_slots,
                                                                                             ctx->d_status.as<unsigned long long>(), pc_of(ctx))));
     CU(cudaGetLastError());
@@ -622,11 +622,11 @@ int mcov_depth_sorted_delta(mcov_ctx* ctx, int64_t n, const int64_t* contig_read
   CU(cudaGetLastError());
   {
     const int64_t tiles = (off_len + kScanTile - 1) / kScanTile;
-    CU(ctx->d_tile_cnt.ensure((size_t)tiles * 16));
-    CU(cudaMemsetAsync(ctx->d_tile_cnt.p, 0, (size_t)tiles * 16, s));
+    CU(ctx->d_tile_cnt.ensure(((size_t)tiles + 1) * 16));             // two scans: status words + a ticket word each
+    CU(cudaMemsetAsync(ctx->d_tile_cnt.p, 0, ((size_t)tiles + 1) * 16, s));
     unsigned long long* stw = ctx->d_tile_cnt.as<unsigned long long>();
     MCOV_LAUNCH(ctx, kKScanCounts, (k_scan_inplace<false><<<(unsigned)tiles, kScanThreads, 0, s>>>(st.cig_off.as<int32_t>(), off_len, stw, pc_of(ctx))));
-    MCOV_LAUNCH(ctx, kKScanCounts, (k_scan_inplace<false><<<(unsigned)tiles, kScanThreads, 0, s>>>(S, off_len, stw + tiles, pc_of(ctx))));
+    MCOV_LAUNCH(ctx, kKScanCounts, (k_scan_inplace<false><<<(unsigned)tiles, kScanThreads, 0, s>>>(S, off_len, stw + tiles + 1, pc_of(ctx))));
     CU(cudaGetLastError());
   }
   MCOV_LAUNCH(ctx, kKDeltaUnpack, (k_delta_finish<<<grid_for(ctx, std::max<int64_t>(n1, n_cig_total), 256, 8), 256, 0, s>>>(
@@ -712,8 +712,8 @@ int mcov_finalize(mcov_ctx* ctx) {
   if (ctx->state != kAccumulating) return fail(ctx, MCOV_ERR_STATE, "mcov_finalize: nothing accumulated");
   CU(cudaSetDevice(ctx->device));
   int64_t n_tiles = (ctx->n_slots + kScanTile - 1) / kScanTile;
-  CU(ctx->d_status.ensure((size_t)n_tiles * 8));
-  CU(cudaMemsetAsync(ctx->d_status.p, 0, (size_t)n_tiles * 8, ctx->stream));
+  CU(ctx->d_status.ensure(((size_t)n_tiles + 1) * 8));              // status words + the ticket word
+  CU(cudaMemsetAsync(ctx->d_status.p, 0, ((size_t)n_tiles + 1) * 8, ctx->stream));
   MCOV_LAUNCH(ctx, kKScan, (k_scan_inplace<true><<<(unsigned)n_tiles, kScanThreads, 0, ctx->stream>>>(
       ctx->depth, ctx->n_slots, ctx->d_status.as<unsigned long long>(), pc_of(ctx))));
   CU(cudaGetLastError());
@@ -1008,8 +1008,8 @@ int mcov_depth_sorted_packed(mcov_ctx* ctx, int64_t n, const int64_t* contig_rea
   CU(cudaGetLastError());
   {
     const int64_t tiles = (off_len + kScanTile - 1) / kScanTile;
-    CU(ctx->d_tile_cnt.ensure((size_t)tiles * 8));
-    CU(cudaMemsetAsync(ctx->d_tile_cnt.p, 0, (size_t)tiles * 8, s));
+    CU(ctx->d_tile_cnt.ensure(((size_t)tiles + 1) * 8));              // status words + the ticket word
+    CU(cudaMemsetAsync(ctx->d_tile_cnt.p, 0, ((size_t)tiles + 1) * 8, s));
     MCOV_LAUNCH(ctx, kKScanCounts, (k_scan_inplace<false><<<(unsigned)tiles, kScanThreads, 0, s>>>(
         st.cig_off.as<int32_t>(), off_len, ctx->d_tile_cnt.as<unsigned long long>(), pc_of(ctx))));
     CU(cudaGetLastError());
