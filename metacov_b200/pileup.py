@@ -46,6 +46,38 @@ def finish_classic(st, n):
     }
 
 
+def finish_classic_many(st, ns):
+    """``finish_classic`` for an array of records: the same seven values per region, computed with numpy over all
+    regions at once (500 k contigs cost the per-record version 8 s of Python; the GPU pass behind them takes 4 ms).
+    Bit-identical to ``finish_classic``: a region whose integer moments leave the range where float64 holds them
+    exactly (2**53) takes the scalar path."""
+    g = len(st)
+    ns = np.asarray(ns, dtype=np.int64)
+    if g == 0:
+        return []
+    total = st["sum"].astype(np.int64)
+    sumsq = st["sumsq"].astype(np.int64)
+    lim = float(1 << 53)
+    nf, tf, sf = ns.astype(np.float64), total.astype(np.float64), sumsq.astype(np.float64)
+    exact = (nf * sf < lim) & (tf * tf < lim) & (nf * nf < lim) & (ns > 0)
+    var_num = ns * sumsq - total * total                       # (only looked at where `exact`)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        std = np.where(var_num > 0, np.sqrt(var_num.astype(np.float64) / (ns * ns).astype(np.float64)), 0.0)
+        avg = tf / nf
+        iq_n = ns - 2 * (ns // 4)
+        q23 = np.where(iq_n > 0, st["iq_sum"].astype(np.float64) / np.where(iq_n > 0, iq_n, 1).astype(np.float64), np.nan)
+    exact &= st["iq_sum"].astype(np.float64) < lim
+    std, avg, q23 = np.round(std, 2), np.round(avg, 2), np.round(q23, 2)
+    med = (st["med_lo"].astype(np.int64) + st["med_hi"].astype(np.int64)) // 2
+    mn, mx = st["min"].tolist(), st["max"].tolist()
+    med, total_l = med.tolist(), total.tolist()
+    out = [{"min": a, "max": b, "med": c, "std": d, "avg": e, "q23": f, "sum": t}
+           for a, b, c, d, e, f, t in zip(mn, mx, med, list(std), list(avg), list(q23), total_l)]     # (list(): numpy.float64 items)
+    for i in np.nonzero(~exact)[0]:
+        out[i] = finish_classic(st[i], int(ns[i]))
+    return out
+
+
 def _engine_of(bam):
     eng = getattr(bam, "coverage_engine", None)
     if eng is None:
@@ -68,7 +100,7 @@ def classic_many(bam, refs, starts, ends):
     # A region may reach past its contig: the reference's vector is end-start long whatever the
     # contig length (pileup.py:10-11) and stays 0 there; the C-ABI counts those positions as 0.
     st = eng.region_stats(tids, starts, ends)
-    return [finish_classic(st[i], int(ends[i] - starts[i])) for i in range(len(tids))]
+    return finish_classic_many(st, ends - starts)
 
 
 def classic(bam, ref, start, end):

@@ -182,3 +182,34 @@ def test_native_bam_reader_rejects_malformed_sizes(tmp_path):
     assert _capi.lib.mcov_bam_load(h, 0) == _capi.MCOV_ERR_IO
     assert _capi.lib.mcov_bam_load_seq(h) == _capi.MCOV_ERR_IO
     _capi.lib.mcov_bam_close(h)
+
+
+def test_finish_classic_many_equals_the_per_record_version():
+    """pileup.finish_classic_many (numpy over all regions) returns exactly what finish_classic returns record by record --
+    values, value types, NaN for a q23 without an interquartile range -- including regions whose integer moments leave the
+    range float64 holds exactly (those take the scalar path)."""
+    from metacov_b200 import _capi
+    from metacov_b200.pileup import finish_classic, finish_classic_many
+    rng = np.random.default_rng(7)
+    g = 4000
+    st = np.zeros(g, dtype=_capi.REGION_STATS_DTYPE)
+    n = rng.integers(1, 60000, g)
+    dm = np.where(rng.random(g) < 0.8, rng.integers(0, 200, g), rng.integers(0, 9000, g))
+    st["sum"] = n * dm + rng.integers(0, 50, g)
+    st["sumsq"] = n * (dm.astype(np.int64) ** 2) + rng.integers(0, 99999, g)
+    iqn = n - 2 * (n // 4)
+    st["iq_sum"] = iqn * dm + rng.integers(0, 7, g)
+    st["max"] = dm * 2
+    st["med_lo"] = dm
+    st["med_hi"] = dm + rng.integers(0, 3, g)
+    n[:20] = 90_000_000                                  # beyond the exact range
+    st["sumsq"][:20] = 1 << 60
+    n[20:40] = rng.integers(1, 4, 20)                    # 1..3 slots: iq range of 1 or 2
+    got = finish_classic_many(st, n)
+    assert finish_classic_many(st[:0], n[:0]) == []
+    for i in range(g):
+        want = finish_classic(st[i], n[i])
+        assert set(got[i]) == set(want)
+        for k, v in want.items():
+            assert type(got[i][k]) is type(v), (i, k)
+            assert got[i][k] == v or (v != v and got[i][k] != got[i][k]), (i, k, got[i][k], v)
