@@ -59,12 +59,12 @@ __device__ __forceinline__ int32_t blk_warp_search(const int64_t* __restrict__ c
 struct BlkShared {
   uint32_t jt[256];           // joint table: flag << 8 | class
   uint32_t dn[128];           // ops of a dictionary entry
-  uint32_t dict_off[129], dict_ops[512];
+  uint32_t dict_off[129];
+  uint32_t src[512 + kBlkXopCap];   // op sources of the chunk in one array: [0, 512) the dictionary's ops, behind them the chunk's explicit ops
   // per read: flag << 8 | class and position difference while the escapes / exceptions are patched; then e[] holds the
   // contig-start marks; then e[] and d[] together are the image of the chunk's op range
   uint32_t e[kBlkChunk];
   int32_t d[kBlkChunk];
-  uint32_t xo[kBlkXopCap];    // the chunk's explicit ops
   unsigned long long w64[kBlkThreads / 32];
   int32_t w_s[kBlkThreads / 32], w_f[kBlkThreads / 32], w_m[kBlkThreads / 32];
   uint32_t w_n[kBlkThreads / 32];
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(kBlkThreads, 4) k_block_expand(const __grid_co
     if (n_xo_tab <= (uint32_t)kBlkXopCap) {
       for (uint32_t q = t; q < n_xo_tab; q += kBlkThreads) {
         const uint32_t g = ce.xop_off + q;
-        sm.xo[q] = g < n_xops ? (narrow ? (uint32_t)x16[g] : x32[g]) : 0u;
+        sm.src[512 + q] = g < n_xops ? (narrow ? (uint32_t)x16[g] : x32[g]) : 0u;
       }
     }
   }
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(kBlkThreads, 4) k_block_expand(const __grid_co
     for (int k = t; k < 256; k += kBlkThreads) sm.jt[k] = k < h.n_jt ? jt[k] : kBlkEscape;            // (255: an escape, patched in blk_load)
     for (int k = t; k < 128; k += kBlkThreads) sm.dn[k] = k < h.n_dict ? min(dict_off[k + 1] - dict_off[k], 4u) : 0u;
     for (int k = t; k < 129; k += kBlkThreads) sm.dict_off[k] = k <= h.n_dict ? min(dict_off[k], 508u) : 0u;
-    for (int k = t; k < 512; k += kBlkThreads) sm.dict_ops[k] = k < h.n_dictops ? dict_ops[k] : 0u;
+    for (int k = t; k < 512; k += kBlkThreads) sm.src[k] = k < h.n_dictops ? dict_ops[k] : 0u;
   }
   if (t < 32) {                                           // contig of the chunk's first read
     const int32_t c = blk_warp_search(crs, h.n_contigs, c0);
@@ -383,30 +383,32 @@ __global__ void __launch_bounds__(kBlkThreads, 4) k_block_expand(const __grid_co
     // image of the chunk's op range, then the image stored coalesced
     uint32_t* img = sm.e;                                                     // e[] and d[]: kBlkOpCap words (free since the barrier
                                                                               // behind the scans, which also covers xo[] and list_n)
-    // the first op of every read here; the reads with more ops (one in ten on short-read data) go to a list that the CTA
-    // then works through together -- a loop `for k < c` per read makes every warp wait for its longest CIGAR eight times
+    // up to three ops of every read here (predicated: a read of short-read data has one op, one in ten two or three);
+    // the rare longer CIGARs go to a list that the CTA then works through together -- a loop `for k < c` per read makes
+    // every warp wait for its longest CIGAR eight times
     // (o0 + c <= n_ops <= kBlkOpCap and o_x + c <= n_xo <= kBlkXopCap hold by construction: all four are sums of the same cn[])
 #pragma unroll
     for (int j = 0; j < kBlkPer; ++j) {
       const uint32_t cls = e[j] & 255u, c = cn[j], o0 = v_off[j];
       const bool dict = cls < 128u;
-      const uint32_t si = dict ? sm.dict_off[cls] : o_x;
-      if (c > 0) img[o0] = dict ? sm.dict_ops[si] : sm.xo[si];
-      const uint32_t more = __ballot_sync(0xffffffffu, c > 1);
+      const uint32_t si = dict ? sm.dict_off[cls] : 512u + o_x;
+      if (c > 0) img[o0] = sm.src[si];
+      if (c > 1) img[o0 + 1] = sm.src[si + 1];
+      if (c > 2) img[o0 + 2] = sm.src[si + 2];
+      const uint32_t more = __ballot_sync(0xffffffffu, c > 3);
       if (more) {
         uint32_t base = 0;
         const int leader = __ffs(more) - 1;
         if (lane == leader) base = atomicAdd(&sm.list_n, (uint32_t)__popc(more));
         base = __shfl_sync(0xffffffffu, base, leader);
-        if (c > 1) sm.list[base + __popc(more & ((1u << lane) - 1u))] = o0 | (c << 12) | (dict ? 0u : 1u << 19) | (si << 20);
+        if (c > 3) sm.list[base + __popc(more & ((1u << lane) - 1u))] = o0 | (c << 12) | (si << 19);
       }
       if (!dict) o_x += c;
     }
     __syncthreads();
     for (uint32_t q = t; q < sm.list_n; q += kBlkThreads) {
-      const uint32_t en = sm.list[q], o0 = en & 4095u, c = (en >> 12) & 127u, si = en >> 20;
-      const uint32_t* src = (en >> 19) & 1u ? sm.xo + si : sm.dict_ops + si;
-      for (uint32_t k = 1; k < c; ++k) img[o0 + k] = src[k];
+      const uint32_t en = sm.list[q], o0 = en & 4095u, c = (en >> 12) & 127u, si = en >> 19;
+      for (uint32_t k = 3; k < c; ++k) img[o0 + k] = sm.src[si + k];
     }
     __syncthreads();
     for (uint32_t q = t; q < n_ops; q += kBlkThreads) if (ce.op_off + q < n_cig) a.cig[ce.op_off + q] = img[q];
@@ -417,7 +419,7 @@ __global__ void __launch_bounds__(kBlkThreads, 4) k_block_expand(const __grid_co
       const uint32_t cls = e[j] & 255u, o0 = ce.op_off + v_off[j];
       if (cls < 128u) {
         const uint32_t b = sm.dict_off[cls];
-        for (uint32_t k = 0; k < cn[j]; ++k) if (o0 + k < n_cig) a.cig[o0 + k] = sm.dict_ops[b + k];
+        for (uint32_t k = 0; k < cn[j]; ++k) if (o0 + k < n_cig) a.cig[o0 + k] = sm.src[b + k];
       } else {
         const uint32_t g = ce.xop_off + o_x;
         for (uint32_t k = 0; k < cn[j]; ++k)
