@@ -125,10 +125,14 @@ __device__ __forceinline__ void blk_load(const BlockArgs& a, BlkShared& sm, int6
     const uint8_t* dq = reinterpret_cast<const uint8_t*>(a.blk + h.off_dq);
     const uint8_t* fq = reinterpret_cast<const uint8_t*>(a.blk + h.off_fq);
     if (cnt) {
+      const uint32_t n_dq = (uint32_t)h.n_dq, n_fq = (uint32_t)h.n_fq;          // (both at most n < 2^32)
+      if (cnt & 0xFFFFu) {
 #pragma unroll
-      for (int j = 0; j < kBlkPer; ++j) {
-        if (lo[j] == 15u) { lo[j] = (int64_t)kd < h.n_dq ? (uint32_t)dq[kd] : 0u; ++kd; }
-        if (hi[j] == 15u) { hi[j] = (int64_t)kf < h.n_fq ? (uint32_t)fq[kf] : 255u; ++kf; }
+        for (int j = 0; j < kBlkPer; ++j) if (lo[j] == 15u) { lo[j] = kd < n_dq ? (uint32_t)dq[kd] : 0u; ++kd; }
+      }
+      if (cnt >> 16) {
+#pragma unroll
+        for (int j = 0; j < kBlkPer; ++j) if (hi[j] == 15u) { hi[j] = kf < n_fq ? (uint32_t)fq[kf] : 255u; ++kf; }
       }
     }
 #pragma unroll
