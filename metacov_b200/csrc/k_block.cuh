@@ -87,34 +87,33 @@ __device__ __forceinline__ void blk_load(const BlockArgs& a, BlkShared& sm, int6
     // nibble form: one byte per read; a nibble of 15 sends to the next entry of a side list, whose place is the chunk's
     // offset (chunk table) + the number of such nibbles in front of the read (one scan over the CTA)
     const uint8_t* nb = reinterpret_cast<const uint8_t*>(a.blk + h.off_nb);
-    uint32_t lo[kBlkPer], hi[kBlkPer];
-    if (i0 + kBlkPer <= n) {
-      const uint2 q = w0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t b0 = (q.x >> (8 * j)) & 255u, b1 = (q.y >> (8 * j)) & 255u;
-        lo[j] = b0 & 15u; hi[j] = b0 >> 4; lo[j + 4] = b1 & 15u; hi[j + 4] = b1 >> 4;
-      }
+    const uint8_t* dq = reinterpret_cast<const uint8_t*>(a.blk + h.off_dq);
+    const uint8_t* fq = reinterpret_cast<const uint8_t*>(a.blk + h.off_fq);
+    const uint32_t n_dq = (uint32_t)h.n_dq, n_fq = (uint32_t)h.n_fq;            // (both at most n < 2^32)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool full = i0 + kBlkPer <= n;
+    // the eight bytes as one 64-bit word: low / high nibbles spread to bytes, and one bit per nibble that is 15 (bit 0 of
+    // a nibble of y: all four of its bits are set) -- the side-list entries are then patched in by a loop over those bits,
+    // which a thread with none (most) skips, instead of eight predicated look-ups
+    unsigned long long L = 0, H = 0, ml = 0, mh = 0;
+    uint32_t lo[kBlkPer], hi[kBlkPer];                                         // (the ragged last chunk only)
+    uint32_t cnt = 0;
+    if (full) {
+      const unsigned long long W = (unsigned long long)w0.x | ((unsigned long long)w0.y << 32);
+      L = W & 0x0F0F0F0F0F0F0F0Full; H = (W >> 4) & 0x0F0F0F0F0F0F0F0Full;
+      unsigned long long y = W & (W >> 1);
+      y &= y >> 2;
+      ml = y & 0x0101010101010101ull; mh = (y >> 4) & 0x0101010101010101ull;
+      cnt = (uint32_t)__popcll(ml) | ((uint32_t)__popcll(mh) << 16);
     } else {
 #pragma unroll
       for (int j = 0; j < kBlkPer; ++j) {
         const uint32_t b = i0 + j < n ? (uint32_t)nb[i0 + j] : 0x1000u;       // (beyond n: no difference; index 256 = no ops)
         lo[j] = b & 15u; hi[j] = b >> 4;
+        cnt += (lo[j] == 15u ? 1u : 0u) + (hi[j] == 15u ? 0x10000u : 0u);
       }
     }
-    uint32_t cnt = 0;
-    if (i0 + kBlkPer <= n) {
-      // bit 0 of every nibble of y: the nibble is 15
-      const uint2 q = w0;
-      uint32_t y0 = q.x & (q.x >> 1), y1 = q.y & (q.y >> 1);
-      y0 &= y0 >> 2; y1 &= y1 >> 2;
-      cnt = (uint32_t)(__popc(y0 & 0x01010101u) + __popc(y1 & 0x01010101u)) + ((uint32_t)(__popc(y0 & 0x10101010u) + __popc(y1 & 0x10101010u)) << 16);
-    } else {
-#pragma unroll
-      for (int j = 0; j < kBlkPer; ++j) cnt += (lo[j] == 15u ? 1u : 0u) + (hi[j] == 15u ? 0x10000u : 0u);
-    }
     uint32_t inc = cnt;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
     if (lane == 31) sm.w_n[warp] = inc;
@@ -122,21 +121,38 @@ __device__ __forceinline__ void blk_load(const BlockArgs& a, BlkShared& sm, int6
     uint32_t ex = inc - cnt;
     for (int w = 0; w < warp; ++w) ex += sm.w_n[w];
     uint32_t kd = ce.dq_off + (ex & 0xFFFFu), kf = ce.fq_off + (ex >> 16);
-    const uint8_t* dq = reinterpret_cast<const uint8_t*>(a.blk + h.off_dq);
-    const uint8_t* fq = reinterpret_cast<const uint8_t*>(a.blk + h.off_fq);
-    if (cnt) {
-      const uint32_t n_dq = (uint32_t)h.n_dq, n_fq = (uint32_t)h.n_fq;          // (both at most n < 2^32)
-      if (cnt & 0xFFFFu) {
-#pragma unroll
-        for (int j = 0; j < kBlkPer; ++j) if (lo[j] == 15u) { lo[j] = kd < n_dq ? (uint32_t)dq[kd] : 0u; ++kd; }
+    if (full) {
+      while (ml) {
+        const int b = __ffsll((long long)ml) - 1;                             // bit 8j
+        ml &= ml - 1;
+        const unsigned long long v = kd < n_dq ? (unsigned long long)dq[kd] : 0ull;
+        ++kd;
+        L = (L & ~(0xFFull << b)) | (v << b);
       }
-      if (cnt >> 16) {
-#pragma unroll
-        for (int j = 0; j < kBlkPer; ++j) if (hi[j] == 15u) { hi[j] = kf < n_fq ? (uint32_t)fq[kf] : 255u; ++kf; }
+      while (mh) {
+        const int b = __ffsll((long long)mh) - 1;
+        mh &= mh - 1;
+        const unsigned long long v = kf < n_fq ? (unsigned long long)fq[kf] : 255ull;
+        ++kf;
+        H = (H & ~(0xFFull << b)) | (v << b);
       }
+      const uint32_t l0 = (uint32_t)L, l1 = (uint32_t)(L >> 32), h0 = (uint32_t)H, h1 = (uint32_t)(H >> 32);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        d[j] = (int32_t)((l0 >> (8 * j)) & 255u); d[j + 4] = (int32_t)((l1 >> (8 * j)) & 255u);
+        e[j] = sm.jt[(h0 >> (8 * j)) & 255u]; e[j + 4] = sm.jt[(h1 >> (8 * j)) & 255u];
+      }
+    } else {
+      if (cnt) {
+#pragma unroll
+        for (int j = 0; j < kBlkPer; ++j) {
+          if (lo[j] == 15u) { lo[j] = kd < n_dq ? (uint32_t)dq[kd] : 0u; ++kd; }
+          if (hi[j] == 15u) { hi[j] = kf < n_fq ? (uint32_t)fq[kf] : 255u; ++kf; }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kBlkPer; ++j) { d[j] = (int32_t)lo[j]; e[j] = hi[j] < 256u ? sm.jt[hi[j]] : 128u; }
     }
-#pragma unroll
-    for (int j = 0; j < kBlkPer; ++j) { d[j] = (int32_t)lo[j]; e[j] = hi[j] < 256u ? sm.jt[hi[j]] : 128u; }
   } else {
     const uint8_t* fc = reinterpret_cast<const uint8_t*>(a.blk + h.off_fc);
     const uint8_t* dp = reinterpret_cast<const uint8_t*>(a.blk + h.off_dpos);
