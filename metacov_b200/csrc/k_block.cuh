@@ -189,7 +189,7 @@ __device__ __forceinline__ void blk_load(const BlockArgs& a, BlkShared& sm, int6
       for (int64_t k = (int64_t)kf + threadIdx.x; k < h.n_esc; k += kBlkThreads) {
         const int64_t i = qi[k];
         if (i >= c1 || i >= n) break;                                         // (ascending: the rest belongs to later chunks)
-        if (i >= c0) sm.e[i - c0] = ((uint32_t)qf[k] << 8) | qc[k];
+        if (i >= c0) { const uint32_t cls = qc[k]; sm.e[i - c0] = ((uint32_t)qf[k] << 8) | cls | ((cls < 128u ? sm.dn[cls] : cls - 128u) << 24); }
       }
     }
     __syncthreads();
@@ -198,7 +198,7 @@ __device__ __forceinline__ void blk_load(const BlockArgs& a, BlkShared& sm, int6
     for (int j = 0; j < kBlkPer; ++j) any |= e[j] == kBlkEscape;
     if (any) {
 #pragma unroll
-      for (int j = 0; j < kBlkPer; ++j) if (e[j] == kBlkEscape) e[j] = sm.e[threadIdx.x * kBlkPer + j] & 0xFFFFFFu;
+      for (int j = 0; j < kBlkPer; ++j) if (e[j] == kBlkEscape) e[j] = sm.e[threadIdx.x * kBlkPer + j] & 0x7FFFFFFFu;
     }
     if (marks_follow) __syncthreads();                                        // (sm.e is rewritten at once by the contig marks; else
                                                                               //  only behind the next barriers, as the op image)
@@ -214,7 +214,7 @@ __device__ __forceinline__ void blk_load(const BlockArgs& a, BlkShared& sm, int6
     for (int64_t k = (int64_t)kf + threadIdx.x; k < h.n_esc; k += kBlkThreads) {
       const int64_t i = qi[k];
       if (i >= c1 || i >= n) break;                                           // (ascending: the rest belongs to later chunks)
-      if (i >= c0) sm.e[i - c0] = ((uint32_t)qf[k] << 8) | qc[k];
+      if (i >= c0) { const uint32_t cls = qc[k]; sm.e[i - c0] = ((uint32_t)qf[k] << 8) | cls | ((cls < 128u ? sm.dn[cls] : cls - 128u) << 24); }
     }
   }
   if (xf != kBlkNone) {
@@ -283,7 +283,18 @@ __global__ void __launch_bounds__(kBlkThreads, 4) k_block_expand(const __grid_co
     const uint32_t* jt = reinterpret_cast<const uint32_t*>(a.blk + h.off_jt);
     const uint32_t* dict_off = reinterpret_cast<const uint32_t*>(a.blk + h.off_dict_off);
     const uint32_t* dict_ops = reinterpret_cast<const uint32_t*>(a.blk + h.off_dict_ops);
-    for (int k = t; k < 256; k += kBlkThreads) sm.jt[k] = k < h.n_jt ? jt[k] : kBlkEscape;            // (255: an escape, patched in blk_load)
+    // joint table entry: flag << 8 | class, and the read's op count in bits 24..30 (dictionary entry: its length; explicit:
+    // class - 128), so that the count is one shift away
+    for (int k = t; k < 256; k += kBlkThreads) {
+      uint32_t en = kBlkEscape;                                               // (255: an escape, patched in blk_load)
+      if (k < h.n_jt) {
+        en = jt[k] & 0xFFFFFFu;
+        const uint32_t cls = en & 255u;
+        const uint32_t cnt = cls >= 128u ? cls - 128u : ((int)cls < h.n_dict ? min(dict_off[cls + 1] - dict_off[cls], 4u) : 0u);
+        en |= cnt << 24;
+      }
+      sm.jt[k] = en;
+    }
     for (int k = t; k < 128; k += kBlkThreads) sm.dn[k] = k < h.n_dict ? min(dict_off[k + 1] - dict_off[k], 4u) : 0u;
     for (int k = t; k < 129; k += kBlkThreads) sm.dict_off[k] = k <= h.n_dict ? min(dict_off[k], 508u) : 0u;
     for (int k = t; k < 512; k += kBlkThreads) sm.src[k] = k < h.n_dictops ? dict_ops[k] : 0u;
@@ -324,7 +335,7 @@ __global__ void __launch_bounds__(kBlkThreads, 4) k_block_expand(const __grid_co
     if (f) f |= 1u << j;
     mk[j] = m; ps[j] = s;
     const uint32_t cls = e[j] & 255u;
-    cn[j] = cls < 128u ? sm.dn[cls] : cls - 128u;
+    cn[j] = e[j] >> 24;
     nc += cn[j]; nx += cls < 128u ? 0u : cn[j];
   }
   // scans over the threads of the CTA
@@ -375,8 +386,9 @@ __global__ void __launch_bounds__(kBlkThreads, 4) k_block_expand(const __grid_co
     int4* pt = reinterpret_cast<int4*>(a.tid + i0); int4* pq = reinterpret_cast<int4*>(a.pos + i0);
     pt[0] = make_int4(v_tid[0], v_tid[1], v_tid[2], v_tid[3]); pt[1] = make_int4(v_tid[4], v_tid[5], v_tid[6], v_tid[7]);
     pq[0] = make_int4(v_pos[0], v_pos[1], v_pos[2], v_pos[3]); pq[1] = make_int4(v_pos[4], v_pos[5], v_pos[6], v_pos[7]);
-    *reinterpret_cast<uint4*>(a.flag + i0) = make_uint4((e[0] >> 8) | ((e[1] >> 8) << 16), (e[2] >> 8) | ((e[3] >> 8) << 16),
-                                                        (e[4] >> 8) | ((e[5] >> 8) << 16), (e[6] >> 8) | ((e[7] >> 8) << 16));
+    // (bytes 1, 2 of an entry are the flag: one byte permute packs two flags)
+    *reinterpret_cast<uint4*>(a.flag + i0) = make_uint4(__byte_perm(e[0], e[1], 0x6521), __byte_perm(e[2], e[3], 0x6521),
+                                                        __byte_perm(e[4], e[5], 0x6521), __byte_perm(e[6], e[7], 0x6521));
     uint2 mq = make_uint2(0xffffffffu, 0xffffffffu);
     if (h.has_mapq) mq = *reinterpret_cast<const uint2*>(a.blk + h.off_mapq + i0);
     *reinterpret_cast<uint2*>(a.mapq + i0) = mq;
