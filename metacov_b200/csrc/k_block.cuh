@@ -56,14 +56,14 @@ __device__ __forceinline__ int32_t blk_warp_search(const int64_t* __restrict__ c
   return lo;
 }
 
-struct BlkShared {
+struct alignas(16) BlkShared {
   uint32_t jt[256];           // joint table: flag << 8 | class
   uint32_t dn[128];           // ops of a dictionary entry
-  uint32_t dict_off[129];
+  uint32_t dict_off[132];     // (129 used; padded so that what follows stays 16-byte aligned)
   uint32_t src[512 + kBlkXopCap];   // op sources of the chunk in one array: [0, 512) the dictionary's ops, behind them the chunk's explicit ops
   // per read: flag << 8 | class and position difference while the escapes / exceptions are patched; then e[] holds the
   // contig-start marks; then e[] and d[] together are the image of the chunk's op range
-  uint32_t e[kBlkChunk];
+  alignas(16) uint32_t e[kBlkChunk];
   int32_t d[kBlkChunk];
   unsigned long long w64[kBlkThreads / 32];
   int32_t w_s[kBlkThreads / 32], w_f[kBlkThreads / 32], w_m[kBlkThreads / 32];
@@ -368,7 +368,9 @@ __global__ void __launch_bounds__(kBlkThreads, 4) k_block_expand(const __grid_co
   }
   const uint32_t n_ops = (uint32_t)tot, n_xo = (uint32_t)(tot >> 32);       // of the chunk
   // (a table that disagrees with the classes -- a malformed block -- sends the chunk down the unstaged path)
-  const bool staged = n_ops <= (uint32_t)kBlkOpCap && n_xo <= (uint32_t)kBlkXopCap && n_xo == n_xo_tab;
+  const bool staged = n_ops + 3u <= (uint32_t)kBlkOpCap && n_xo <= (uint32_t)kBlkXopCap && n_xo == n_xo_tab;
+  const uint32_t pad = ce.op_off & 3u;                                        // the image starts `pad` words in: image index = global
+                                                                              // op index mod 4, so both sides of the flush are 16-byte aligned
   // outputs
   const int64_t i0 = c0 + (int64_t)t * kBlkPer;
   uint32_t o_c = (uint32_t)pcx, o_x = (uint32_t)(pcx >> 32);                  // relative to the chunk
@@ -421,7 +423,7 @@ __global__ void __launch_bounds__(kBlkThreads, 4) k_block_expand(const __grid_co
     // (o0 + c <= n_ops <= kBlkOpCap and o_x + c <= n_xo <= kBlkXopCap hold by construction: all four are sums of the same cn[])
 #pragma unroll
     for (int j = 0; j < kBlkPer; ++j) {
-      const uint32_t cls = e[j] & 255u, c = cn[j], o0 = v_off[j];
+      const uint32_t cls = e[j] & 255u, c = cn[j], o0 = v_off[j] + pad;
       const bool dict = cls < 128u;
       const uint32_t si = dict ? sm.dict_off[cls] : 512u + o_x;
       if (c > 0) img[o0] = sm.src[si];
@@ -443,7 +445,23 @@ __global__ void __launch_bounds__(kBlkThreads, 4) k_block_expand(const __grid_co
       for (uint32_t k = 3; k < c; ++k) img[o0 + k] = sm.src[si + k];
     }
     __syncthreads();
-    for (uint32_t q = t; q < n_ops; q += kBlkThreads) if (ce.op_off + q < n_cig) a.cig[ce.op_off + q] = img[q];
+    {
+      // 128-bit loads from the image, 128-bit stores to cig[]; the first and the last vector may be partial
+      uint32_t* gbase = a.cig + (ce.op_off - pad);                            // 16-byte aligned (cig[] is, and op_off - pad is a multiple of 4)
+      const uint32_t gb = ce.op_off - pad;
+      const uint32_t end = pad + n_ops, lim = n_cig > gb ? n_cig - gb : 0u;   // image indices [pad, end) hold ops; global room from gbase
+      const uint32_t nvec = (end + 3u) >> 2;
+      for (uint32_t v = t; v < nvec; v += kBlkThreads) {
+        const uint32_t q = 4u * v;
+        const uint4 x = *reinterpret_cast<const uint4*>(img + q);
+        if (q >= pad && q + 4u <= end && q + 4u <= lim) *reinterpret_cast<uint4*>(gbase + q) = x;
+        else {
+          const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) if (q + u >= pad && q + u < end && q + u < lim) gbase[q + u] = xs[u];
+        }
+      }
+    }
   } else {
     // a chunk of long CIGARs: every thread stores its reads' ops itself
 #pragma unroll
