@@ -86,6 +86,8 @@ struct mcov_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaStream_t d2h_stream = nullptr;   // copy-back of pipelined statistics records (overlaps the next pass)
   cudaEvent_t copied = nullptr;
+  cudaStream_t unpack_stream = nullptr;   // the transport block's unpack kernel: depends on the block's copy only, so it may
+  cudaEvent_t unpacked = nullptr;         // overlap the kernels of the previous pass on the main stream
   bool copy_pending = false;       // a transport block's copy has been enqueued and not yet waited for
   std::string err;
 

@@ -384,13 +384,24 @@ int block_stage(mcov_ctx* ctx, const void* block, int64_t bytes, ExpandArgs& a, 
   const int64_t n_chunks = (off_len + kBlkChunk - 1) / kBlkChunk;
   CU(cudaMemcpyAsync(st.raw.p, block, (size_t)h.total_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
   CU(cudaEventRecord(ctx->copied, ctx->copy_stream));
-  CU(cudaStreamWaitEvent(ctx->stream, ctx->copied, 0));
-  cudaStream_t s = ctx->stream;
   BlockArgs b;
   b.blk = st.raw.as<char>(); b.h = h; b.off_len = off_len;
   b.tid = st.tid.as<int32_t>(); b.pos = st.pos.as<int32_t>(); b.flag = st.flag.as<uint16_t>(); b.mapq = st.mapq.as<uint8_t>();
   b.cig_off = st.cig_off.as<uint32_t>(); b.cig = st.cig.as<uint32_t>();
-  MCOV_LAUNCH(ctx, kKBlockUnpack, (k_block_expand<<<(unsigned)n_chunks, kBlkThreads, 0, s>>>(b)));
+  // The unpack kernel needs the block's copy and nothing else -- it writes the columns of THIS staging set, which no kernel
+  // of the previous pass reads -- so it runs on a stream of its own and fills whatever the previous pass leaves idle (the
+  // tails of its kernels, the gaps between them) instead of queueing behind it.  (Per-kernel timing keeps it on the main
+  // stream: the event pairs are recorded there.  MCOV_UNPACK_INLINE: the same without timing, for A/B.)
+  static const bool unpack_inline = std::getenv("MCOV_UNPACK_INLINE") != nullptr;
+  if (ctx->profiling || unpack_inline) {
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->copied, 0));
+    MCOV_LAUNCH(ctx, kKBlockUnpack, (k_block_expand<<<(unsigned)n_chunks, kBlkThreads, 0, ctx->stream>>>(b)));
+  } else {
+    CU(cudaStreamWaitEvent(ctx->unpack_stream, ctx->copied, 0));
+    MCOV_LAUNCH(ctx, kKBlockUnpack, (k_block_expand<<<(unsigned)n_chunks, kBlkThreads, 0, ctx->unpack_stream>>>(b)));
+    CU(cudaEventRecord(ctx->unpacked, ctx->unpack_stream));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->unpacked, 0));
+  }
   CU(cudaGetLastError());
   std::memset(&a, 0, sizeof(a));
   a.n = n; a.n_cig = h.n_cigar;
@@ -463,6 +474,8 @@ int mcov_create(mcov_ctx** out, int device, void* stream) {
   bool ok = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreateWithFlags(&ctx->copied, cudaEventDisableTiming) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&ctx->unpack_stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ctx->unpacked, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&ctx->stage[0].consumed, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&ctx->stage[1].consumed, cudaEventDisableTiming) == cudaSuccess;
   if (!ok) { mcov_destroy(ctx); return MCOV_ERR_CUDA; }
@@ -480,6 +493,8 @@ void mcov_destroy(mcov_ctx* ctx) {
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   if (ctx->d2h_stream) { cudaStreamSynchronize(ctx->d2h_stream); cudaStreamDestroy(ctx->d2h_stream); }
   if (ctx->copied) cudaEventDestroy(ctx->copied);
+  if (ctx->unpack_stream) { cudaStreamSynchronize(ctx->unpack_stream); cudaStreamDestroy(ctx->unpack_stream); }
+  if (ctx->unpacked) cudaEventDestroy(ctx->unpacked);
   for (auto& s : ctx->stage) {
     if (s.consumed) cudaEventDestroy(s.consumed);
     s.tid.release(); s.pos.release(); s.flag.release(); s.mapq.release(); s.cig_off.release(); s.cig.release(); s.raw.release();
