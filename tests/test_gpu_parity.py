@@ -822,3 +822,58 @@ def test_block_unpack_column_by_column():
     w = synth.c2(0.01)
     b2, _ = synth.generate_host(w)
     check(b2, w.n_contigs, pinned=True)
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("MCOV_BLOCK_FUZZ", "6"))))
+def test_block_unpack_random_batches(seed):
+    """Random batches of tens of thousands of reads (dozens of 2 048-read chunks) through mcov_pack_block ->
+    mcov_block_unpack: random contig structure (runs of empty contigs, contigs of one read, an unplaced tail), gap
+    distributions that favour the nibble or the wide form, position exceptions, escapes, CIGARs of 0..9 ops with the
+    occasional op of 4 096 and more.  MCOV_BLOCK_FUZZ=N runs N seeds (the builder ran 300: profiles/r02_fuzz_3000.txt)."""
+    from metacov_b200 import ReadBatch
+    from metacov_b200.engine import pack_block
+    rng = np.random.default_rng(50_000 + seed)
+    n = int(rng.integers(3000, 120_000))
+    n_contigs = int(rng.choice([1, 3, 40, 2000, 30_000]))
+    # reads per contig: skewed, many empty
+    w = rng.random(n_contigs) ** int(rng.integers(1, 6))
+    if n_contigs > 10:
+        w[rng.random(n_contigs) < 0.3] = 0
+    if w.sum() == 0:
+        w[0] = 1
+    tid = np.sort(rng.choice(n_contigs, n, p=w / w.sum())).astype(np.int64)
+    n_un = int(rng.integers(0, 3000)) if seed % 3 else 0
+    tid = np.r_[tid, np.full(n_un, -1)]
+    n = len(tid)
+    mean_gap = float(rng.choice([1.5, 5, 12, 60, 400]))
+    gaps = rng.geometric(1.0 / (1.0 + mean_gap), n) - 1
+    gaps[rng.random(n) < float(rng.choice([0, 0.001, 0.02]))] = rng.integers(256, 3_000_000)
+    pos = np.zeros(n, np.int64)
+    first = np.r_[True, tid[1:] != tid[:-1]]
+    seg = np.cumsum(first) - 1
+    start_of = np.flatnonzero(first)
+    csum = np.cumsum(gaps)
+    pos = csum - csum[start_of][seg] + rng.integers(0, 5000, len(start_of))[seg]
+    if seed % 5 == 4:                                      # a few reads out of order inside their contig: negative differences
+        k = rng.integers(1, n, 20)
+        pos[k] = np.maximum(pos[k] - rng.integers(1, 400, 20), 0)
+    nf = int(rng.choice([3, 12, 400, 5000]))
+    flag = rng.choice(rng.integers(0, 65536, nf), n).astype(np.uint16)
+    n_op = rng.choice(np.array([1, 1, 1, 1, 1, 2, 3, 3, 5, 9, 0]), n)
+    off = np.concatenate(([0], np.cumsum(n_op))).astype(np.uint32)
+    ln = rng.integers(1, 151, int(off[-1])).astype(np.uint32)
+    single = off[:-1][n_op == 1]
+    ln[single] = rng.choice(np.array([150, 150, 150, 100, 75], np.uint32), len(single))
+    if seed % 4 == 1 and len(ln):
+        ln[rng.integers(0, len(ln), 3)] = rng.integers(4096, 100_000, 3)
+    cig = (ln << 4) | rng.choice(np.array([0, 0, 0, 1, 2, 4, 7, 8], np.uint32), len(ln)).astype(np.uint32)
+    b = ReadBatch(tid.astype(np.int32), pos.astype(np.int32), flag, rng.integers(0, 61, n).astype(np.uint8), off, cig)
+    with_mapq = bool(seed % 2)
+    blk = pack_block(b, n_contigs, with_mapq=with_mapq, pinned=bool(seed % 3 == 0))
+    with engine_for(np.full(n_contigs, 2_000_000_000 // max(n_contigs, 1) + 1000, np.int32)) as eng:
+        u = eng.block_unpack(blk)
+    ok = b.tid >= 0
+    assert np.array_equal(u["tid"][ok], b.tid[ok]) and np.all(u["tid"][~ok] == -1)
+    assert np.array_equal(u["pos"], b.pos) and np.array_equal(u["flag"], b.flag)
+    assert np.array_equal(u["cig_off"], b.cig_off) and np.array_equal(u["cig"], b.cig)
+    assert np.array_equal(u["mapq"], b.mapq) if with_mapq else np.all(u["mapq"] == 0xff)
