@@ -684,6 +684,10 @@ extern "C" int mcov_bam_gpu_stream_depth(mcov_ctx* ctx, const char* path, int64_
       uint64_t chain_end = rec_begin;
       segs.clear(); wo.clear();
       if (total > rec_begin) { err_rc = bam_dev_chain(ctx, total, rec_begin, n_ref, !was_eof, segs, wo, &chain_end); if (err_rc) break; }
+      // The chain may stop in front of a record that continues in the next chunk: the write pass must stop there too.  (Its
+      // walk runs to the segment's limit; left at `total` it parsed the cut record -- with fewer than 36 of its bytes present
+      // it took the op count from whatever lay behind the stream and wrote that many "ops" past the end of the op column.)
+      if (!segs.empty()) segs.back().limit = chain_end;
       uint64_t n_rec = 0, n_cig = 0;
       for (size_t i = 0; i < segs.size(); ++i) { segs[i].rec_base = (uint64_t)n_carry + n_rec; segs[i].cig_base = (uint64_t)carry_ops + n_cig; n_rec += wo[i].n_rec; n_cig += wo[i].n_cig; }
       const uint64_t n_tot = (uint64_t)n_carry + n_rec, ops_tot = (uint64_t)carry_ops + n_cig;

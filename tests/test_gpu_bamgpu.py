@@ -310,3 +310,31 @@ def test_streamed_gpu_decode_matches_whole_file(tmp_path):
         assert gs.stream_batches >= 4 and gs.gpu_stream_info["n_records"] == len(tid)
     with AlignmentFile(pu) as host, AlignmentFile(pu, decode="gpu-stream", gpu_chunk_bytes=1 << 17) as gs:
         assert pileup.classic(gs, "c1", 0, lengths[1]) == pileup.classic(host, "c1", 0, lengths[1])
+
+
+def test_streamed_gpu_decode_random_chunk_sizes(tmp_path):
+    """The streamed GPU decoder against the whole-file GPU decode of the same 400 000-read file for a dozen chunk sizes:
+    whatever the chunk borders cut -- BGZF blocks, records, a record of which fewer than 36 bytes are present (chunk size
+    1 287 135 on this file: the write pass once parsed such a stub and wrote its garbage op count past the op column) --
+    every contig's depth and the pass counters are identical.  `tools/stream_fuzz.py N` runs N random sizes."""
+    from metacov_b200 import CoverageEngine, bamgpu, synth
+    w = synth.c2(0.04)
+    hb, isz = synth.generate_host(w)
+    path = str(tmp_path / "f.bam")
+    synth.write_bam(path, w, hb, isz)
+    size = os.path.getsize(path)
+    lengths = [int(x) for x in w.contig_len]
+    with CoverageEngine(lengths) as eng:
+        bamgpu.depth_sorted(eng, bamgpu.decode(eng, path))
+        want = [eng.copy_depth(c) for c in range(len(lengths))]
+        pi0 = eng.pass_info()
+    rng = np.random.default_rng(77)
+    sizes = [1_287_135] + [int(rng.integers(1 << 17, size // 2)) for _ in range(11)]
+    for chunk in sizes:
+        with CoverageEngine(lengths) as eng:
+            info = bamgpu.stream_depth(eng, path, chunk_bytes=chunk)
+            pi = eng.pass_info()
+            assert info["n_records"] == len(hb.tid), chunk
+            assert pi["n_pass"] == pi0["n_pass"] and pi["aligned_bases"] == pi0["aligned_bases"], chunk
+            for c in range(len(lengths)):
+                assert np.array_equal(eng.copy_depth(c), want[c]), (chunk, c)
