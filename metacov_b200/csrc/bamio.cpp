@@ -542,7 +542,10 @@ bool stream_refill(mcov_bam_stream* s) {
   // drop what has been parsed
   if (s->data_pos > 0) { s->data.erase(s->data.begin(), s->data.begin() + (ptrdiff_t)s->data_pos); s->data_pos = 0; }
   // (the first read is small: opening a file should cost no more than its header)
-  const size_t want = s->header_done ? kStreamChunk : (size_t)256 << 10;
+  // (MCOV_STREAM_READ_BYTES: test hook -- small reads put a chunk border into every BGZF block and record of a small file)
+  size_t chunk = kStreamChunk;
+  if (const char* e = std::getenv("MCOV_STREAM_READ_BYTES")) { const long long v = std::atoll(e); if (v >= 1024) chunk = (size_t)v; }
+  const size_t want = s->header_done ? chunk : std::min<size_t>(chunk, (size_t)256 << 10);
   const size_t old = s->raw.size();
   s->raw.resize(old + want);
   const size_t got = std::fread(s->raw.data() + old, 1, want, s->fh);

@@ -123,3 +123,37 @@ def test_bam_streamed_in_batches_equals_one_shot(tmp_path):
         fw, foff, _ = cport.depth(fb, np.asarray(af.lengths, np.int32), mode="diff")
         for c in range(2):
             assert np.array_equal(eng.copy_depth(c), fw[foff[c]:foff[c] + af.lengths[c]])
+
+
+def test_stream_reader_with_small_file_reads(tmp_path, monkeypatch):
+    """The streaming host reader reads the file in pieces (32 MB in production); MCOV_STREAM_READ_BYTES makes the pieces
+    small, so that their borders cut the BGZF blocks and records of a small file everywhere.  Whatever the piece and batch
+    sizes, the batches put together are the file (columns of the oracle's reader)."""
+    from metacov_b200.alignmentfile import BamStream
+    path = _write_synth_bam(tmp_path, scale=0.002)[0]
+    hdr, recs = bamio.read_bam(path)
+    size = os.path.getsize(path)
+    rng = np.random.default_rng(3)
+    for trial in range(14):
+        piece = int(rng.integers(1024, max(2048, size // 2)))
+        batch_reads = int(rng.integers(200, 9000))
+        monkeypatch.setenv("MCOV_STREAM_READ_BYTES", str(piece))
+        cols = {k: [] for k in ("tid", "pos", "flag", "mapq", "cig", "ncig")}
+        with BamStream(path, batch_reads=batch_reads, threads=2) as st:
+            assert st.references == tuple(hdr.references)
+            while True:
+                item = st.next_batch()
+                if item is None:
+                    break
+                b, n_carry, last, extra = item
+                assert n_carry == 0
+                for k in ("tid", "pos", "flag", "mapq", "cig"):
+                    cols[k].append(np.array(getattr(b, k)))
+                cols["ncig"].append(np.diff(b.cig_off.astype(np.int64)))
+                if last:
+                    break
+            assert st.n_records == len(recs.tid), (piece, batch_reads)
+        got = {k: np.concatenate(v) for k, v in cols.items()}
+        for k, want in (("tid", recs.tid), ("pos", recs.pos), ("flag", recs.flag), ("mapq", recs.mapq), ("cig", recs.cig),
+                        ("ncig", np.diff(np.asarray(recs.cig_off, dtype=np.int64)))):
+            assert np.array_equal(got[k], np.asarray(want)), (piece, batch_reads, k)
