@@ -829,7 +829,7 @@ def test_block_unpack_random_batches(seed):
     """Random batches of tens of thousands of reads (dozens of 2 048-read chunks) through mcov_pack_block ->
     mcov_block_unpack: random contig structure (runs of empty contigs, contigs of one read, an unplaced tail), gap
     distributions that favour the nibble or the wide form, position exceptions, escapes, CIGARs of 0..9 ops with the
-    occasional op of 4 096 and more.  MCOV_BLOCK_FUZZ=N runs N seeds (the builder ran 300: profiles/r02_fuzz_3000.txt)."""
+    occasional op of 4 096 and more.  MCOV_BLOCK_FUZZ=N runs N seeds (the builder ran 300: profiles/r02_fuzz.txt)."""
     from metacov_b200 import ReadBatch
     from metacov_b200.engine import pack_block
     rng = np.random.default_rng(50_000 + seed)
